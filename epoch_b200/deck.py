@@ -1,0 +1,305 @@
+"""Host-side description of a run and the PROGRAM pic time loop.
+
+This mirrors, on the host, the pieces of EPOCH that stay on the Fortran side of
+the drop-in boundary: grid/timestep set-up (housekeeping/setup.F90:162-204,
+:633-711), domain decomposition arithmetic (housekeeping/mpi_routines.F90:
+317-351), laser source evaluation (laser.f90:253-269,343-352) and the main loop
+call order (epoch2d.F90:144-268).  It is not a deck parser: the `.deck` surface
+stays EPOCH's own; tests and the bench construct `Deck` objects directly.
+
+A backend (the CUDA library behind `epoch_b200.pic.Simulation`, or the CPU
+oracle in tests) only has to provide: init(), fields_half(), push(),
+current_finish(), fields_final(), set_laser_source(local_rank, side, s1, s2).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+# constants.F90:192-199
+pi = 3.141592653589793238462643383279503
+q0 = 1.602176565e-19
+m0 = 9.10938291e-31
+c = 2.99792458e8
+kb = 1.3806488e-23
+epsilon0 = 8.854187817620389850536563031710750e-12
+ev = q0
+micron = 1e-6
+femto = 1e-15
+
+# constants.F90:75-90
+BC = {
+    "periodic": 1, "other": 2, "simple_laser": 3, "simple_outflow": 4, "open": 5,
+    "zero_gradient": 7, "clamp": 8, "reflect": 9, "conduct": 10, "thermal": 11,
+}
+
+NG = 5  # triangle shape: png = 3, ng = png + 2 (constants.F90:549-559)
+
+
+def gauss(x, x0, w):
+    """parser/evaluator_blocks.F90:998-1001"""
+    return np.exp(-(((x - x0) / w) ** 2))
+
+
+@dataclass
+class Species:
+    name: str
+    charge: float            # C
+    mass: float              # kg
+    npart_per_cell: float = 0
+    density: float = 0.0     # m^-3, uniform inside box
+    temp: Sequence[float] = (0.0, 0.0, 0.0)    # K
+    drift: Sequence[float] = (0.0, 0.0, 0.0)   # kg m/s
+    box_lo: Sequence[float] = (-1e300, -1e300, -1e300)
+    box_hi: Sequence[float] = (1e300, 1e300, 1e300)
+    bc_particle: Optional[Sequence[str]] = None  # default: follows the field BCs
+    zero_current: bool = False
+    immobile: bool = False
+
+
+@dataclass
+class Laser:
+    boundary: str                    # 'x_min' | 'x_max'
+    amp: float
+    omega: float
+    pol_angle: float = 0.0
+    t_start: float = 0.0
+    t_end: Optional[float] = None    # default: deck t_end (laser.f90:40)
+    profile: Optional[Callable] = None   # f(y, z) -> array, default 1
+    phase: Optional[Callable] = None     # f(y, z) -> array, default 0
+    t_profile: Optional[Callable] = None  # f(time) -> float, default 1
+
+    @staticmethod
+    def amp_from_intensity_w_cm2(i_w_cm2: float) -> float:
+        """deck/deck_laser_block.f90:132-136"""
+        return math.sqrt(i_w_cm2 / (c * epsilon0 / 2.0)) * 100.0
+
+
+@dataclass
+class Deck:
+    ndims: int
+    n: Sequence[int]
+    xmin: Sequence[float]
+    xmax: Sequence[float]
+    bc_field: Sequence[str]                 # 2*ndims names, x_min,x_max,y_min,...
+    species: List[Species] = field(default_factory=list)
+    lasers: List[Laser] = field(default_factory=list)
+    t_end: float = 0.0
+    nsteps: int = -1
+    dt_multiplier: float = 0.95
+    nproc: Sequence[int] = (1, 1, 1)
+    seed: int = 7842432
+    dt_snapshot: float = -1.0
+
+    # -- grid (setup.F90:162-204) ------------------------------------------
+    def dx(self, d: int) -> float:
+        return (self.xmax[d] - self.xmin[d]) / float(self.n[d])
+
+    def grid_min(self, d: int) -> float:
+        return self.xmin[d] + self.dx(d) / 2.0
+
+    def x_global(self, d: int, i):
+        """Cell-centre coordinate of global cell i (1-based), setup.F90:188."""
+        return self.grid_min(d) + (np.asarray(i, dtype=np.float64) - 1.0) * self.dx(d)
+
+    def bc_codes(self) -> List[int]:
+        out = [BC["periodic"]] * 6
+        for i, name in enumerate(self.bc_field):
+            out[i] = BC[name]
+        return out
+
+    def species_bc_codes(self, s: Species) -> List[int]:
+        names = s.bc_particle if s.bc_particle is not None else self.bc_field
+        out = [BC["periodic"]] * 6
+        for i, name in enumerate(names):
+            out[i] = BC[name]
+        return out
+
+    def any_open(self) -> bool:
+        # boundary.F90:41-57
+        return any(b in ("simple_laser", "simple_outflow", "open") for b in self.bc_field)
+
+    # -- timestep (setup.F90:577-711; 1D :574-606; 3D :700-746) --------------
+    def dt_plasma_frequency(self) -> float:
+        min_dt = 1000000.0
+        k_max = 2.0 * pi / min(self.dx(d) for d in range(self.ndims))
+        for s in self.species:
+            fac1 = q0 ** 2 / s.mass / epsilon0
+            fac2 = 3.0 * k_max ** 2 * kb / s.mass
+            omega2 = fac1 * s.density + fac2 * max(s.temp)
+            if omega2 <= 1e-50:
+                continue
+            omega = math.sqrt(omega2)
+            if 2.0 * pi / omega < min_dt:
+                min_dt = 2.0 * pi / omega
+        return min_dt / 2.0
+
+    def dt_laser(self) -> float:
+        v = 1.7976931348623157e308
+        for l in self.lasers:
+            v = min(v, 2.0 * pi / l.omega)
+        return v / 2.0
+
+    def dt(self) -> float:
+        d = [self.dx(i) for i in range(self.ndims)]
+        if self.ndims == 1:
+            solver = d[0] / c
+        elif self.ndims == 2:
+            solver = d[0] * d[1] / math.sqrt(d[0] ** 2 + d[1] ** 2) / c
+        else:
+            solver = d[0] * d[1] * d[2] / math.sqrt(
+                (d[0] * d[1]) ** 2 + (d[1] * d[2]) ** 2 + (d[2] * d[0]) ** 2) / c
+        dt = 1.0 * solver  # cfl = 1 for field_order 2 (fields.f90:39-40)
+        if self.any_open():
+            dt = min(dt, solver)
+        dtp = self.dt_plasma_frequency()
+        if dtp > 1e-50:
+            dt = min(dt, dtp)
+        dtl = self.dt_laser()
+        if dtl > 1e-50:
+            dt = min(dt, dtl)
+        return self.dt_multiplier * dt
+
+    # -- decomposition (mpi_routines.F90:317-351) ---------------------------
+    def cell_ranges(self, d: int):
+        npd = max(1, self.nproc[d]) if d < self.ndims else 1
+        ng_ = self.n[d] if d < self.ndims else 1
+        n0 = ng_ // npd
+        nxp = (n0 + 1) * npd - ng_ if n0 * npd != ng_ else npd
+        mins, maxs = [], []
+        for i in range(1, nxp + 1):
+            mins.append((i - 1) * n0 + 1)
+            maxs.append(i * n0)
+        for i in range(nxp + 1, npd + 1):
+            mins.append(nxp * n0 + (i - nxp - 1) * (n0 + 1) + 1)
+            maxs.append(nxp * n0 + (i - nxp) * (n0 + 1))
+        return mins, maxs
+
+    def nranks(self) -> int:
+        r = 1
+        for d in range(self.ndims):
+            r *= max(1, self.nproc[d])
+        return r
+
+    def rank_coords(self, rank: int):
+        """MPI_CART row-major with dims=(nprocz,nprocy,nprocx): x fastest
+        (mpi_routines.F90:186-187,239-245)."""
+        npx = max(1, self.nproc[0])
+        npy = max(1, self.nproc[1]) if self.ndims >= 2 else 1
+        return (rank % npx, (rank // npx) % npy, rank // (npx * npy))
+
+    def local_extent(self, rank: int):
+        """(n_local[3], global_min[3]) of a rank."""
+        co = self.rank_coords(rank)
+        n, g = [1, 1, 1], [1, 1, 1]
+        for d in range(self.ndims):
+            mins, maxs = self.cell_ranges(d)
+            g[d] = mins[co[d]]
+            n[d] = maxs[co[d]] - mins[co[d]] + 1
+        return n, g
+
+    # -- laser sources (laser.f90:253-269, 338-357) --------------------------
+    def laser_sources(self, rank: int, side: int, time: float):
+        """source1/source2 on the local transverse plane (0:ny, 0:nz), y fastest."""
+        n, g = self.local_extent(rank)
+        ny = n[1] if self.ndims >= 2 else 0
+        nz = n[2] if self.ndims >= 3 else 0
+        jj = np.arange(0, ny + 1)
+        kk = np.arange(0, nz + 1)
+        y = self.x_global(1, jj + g[1] - 1) if self.ndims >= 2 else np.zeros(1)
+        z = self.x_global(2, kk + g[2] - 1) if self.ndims >= 3 else np.zeros(1)
+        Y, Z = np.meshgrid(y, z, indexing="xy")  # shape (nz+1, ny+1)
+        s1 = np.zeros_like(Y)
+        s2 = np.zeros_like(Y)
+        name = "x_min" if side == 0 else "x_max"
+        for l in self.lasers:
+            if l.boundary != name:
+                continue
+            t_end = self.t_end if l.t_end is None else l.t_end
+            if not (time >= l.t_start and time <= t_end):
+                continue
+            integral_phase = l.omega * time
+            prof = np.ones_like(Y) if l.profile is None else np.broadcast_to(l.profile(Y, Z), Y.shape)
+            ph = np.zeros_like(Y) if l.phase is None else np.broadcast_to(l.phase(Y, Z), Y.shape)
+            t_env = (1.0 if l.t_profile is None else float(l.t_profile(time))) * l.amp
+            base = t_env * prof * np.sin(integral_phase + ph)
+            s1 = s1 + base * math.cos(l.pol_angle)
+            s2 = s2 + base * math.sin(l.pol_angle)
+        return np.ascontiguousarray(s1.ravel()), np.ascontiguousarray(s2.ravel())
+
+    def has_boundary_source(self, side: int) -> bool:
+        return self.bc_field[side] in ("simple_laser", "simple_outflow", "open")
+
+
+class DumpClock:
+    """Time-based dump decision, io/diagnostics.F90:1218-1343 (dt_snapshot only)."""
+
+    def __init__(self, dt_snapshot: float):
+        self.dt_snapshot = dt_snapshot
+        self.time_prev = 0.0
+        self.first = True
+
+    def due(self, time: float, last: bool) -> bool:
+        dump = False
+        if self.first:
+            dump = True
+            self.first = False
+        if last:
+            dump = True
+        if self.dt_snapshot > 0:
+            t0 = self.time_prev + self.dt_snapshot
+            if time >= t0:
+                while True:
+                    t0 = self.time_prev + self.dt_snapshot
+                    if t0 > time:
+                        break
+                    self.time_prev = t0
+                dump = True
+        return dump
+
+
+def run(deck: Deck, backend, local_ranks: Sequence[int], on_dump: Optional[Callable] = None,
+        max_steps: Optional[int] = None):
+    """PROGRAM pic main loop (epoch2d.F90:144-268).  Returns (step, time).
+
+    `local_ranks` are the decomposition ranks this backend instance owns
+    (all of them for the in-process oracle, one for a GPU process).
+    """
+    dt = deck.dt()
+    time = 0.0
+    step = 0
+    clock = DumpClock(deck.dt_snapshot)
+
+    def push_sources(t):
+        for lr, rank in enumerate(local_ranks):
+            for side in (0, 1):
+                if deck.has_boundary_source(side):
+                    s1, s2 = deck.laser_sources(rank, side, t)
+                    backend.set_laser_source(lr, side, s1, s2)
+
+    # epoch2d.F90:158-162: dt halved, time advanced, bfield_final_bcs, dt restored
+    time = time + dt / 2.0
+    push_sources(time)
+    backend.init()
+    if on_dump is not None and clock.due(time, False):
+        on_dump(step, time)
+    nsteps = deck.nsteps if max_steps is None else max_steps
+    while True:
+        backend.fields_half()
+        backend.push()
+        backend.current_finish()
+        step += 1
+        time = time + dt / 2.0
+        if (nsteps >= 0 and step >= nsteps) or (deck.t_end > 0 and time >= deck.t_end):
+            break
+        if on_dump is not None and clock.due(time, False):
+            on_dump(step, time)
+        time = time + dt / 2.0
+        push_sources(time)
+        backend.fields_final()
+    if on_dump is not None:
+        on_dump(step, time)
+    return step, time

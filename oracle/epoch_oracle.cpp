@@ -1,0 +1,1452 @@
+// epoch_oracle.cpp — CPU restatement of EPOCH's per-timestep PIC hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load it.  The product library (epoch_b200/csrc) never links or calls it.
+//
+// Parity status: the FIELD half (FDTD + field BCs + laser/outflow boundary) is
+// pinned against the reference's own golden scalars
+// (epoch{1,2,3}d/tests/test_laser.py:70-80).  The PARTICLE half (push, deposit,
+// particle exchange) is "parity unpinned": the reference ships no numeric
+// assertion for it (tests/test_twostream.py, test_landau.py only plot), and the
+// reference binary (Fortran 2003 + MPI) cannot be built in this image.  It is
+// checked instead through exact discrete charge conservation, which is the
+// property particles.F90:30-34 claims.
+//
+// Each routine cites the reference file:line it restates.  2D line numbers are
+// epoch2d/src/..., with the 1D/3D trees cited where they differ textually.
+// Arithmetic keeps the reference's operation order; build with
+// -ffp-contract=off (the reference's gfortran -O3 build has no -march flag and
+// therefore no FMA contraction, epoch2d/Makefile:72).
+//
+// Supported: ndims 1/2/3, triangle shape (default build), per-particle weight,
+// Boris push, Yee order-2 FDTD, field BCs periodic/clamp/zero_gradient/
+// simple_laser/simple_outflow (laser/outflow on x_min/x_max), particle BCs
+// periodic/reflect/open, in-process multi-"rank" domain decomposition that
+// replays the MPI_SENDRECV sequences of boundary.F90.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+// constants.F90:192-199
+constexpr double pi = 3.141592653589793238462643383279503;
+constexpr double q0 = 1.602176565e-19;
+constexpr double m0 = 9.10938291e-31;
+constexpr double c = 2.99792458e8;
+constexpr double kb = 1.3806488e-23;
+constexpr double epsilon0 = 8.854187817620389850536563031710750e-12;
+
+// constants.F90:75-90
+enum {
+  c_bc_periodic = 1,
+  c_bc_other = 2,
+  c_bc_simple_laser = 3,
+  c_bc_simple_outflow = 4,
+  c_bc_open = 5,
+  c_bc_zero_gradient = 7,
+  c_bc_clamp = 8,
+  c_bc_reflect = 9,
+  c_bc_conduct = 10,
+  c_bc_thermal = 11,
+};
+
+// constants.F90:549-559 (triangle): sf_min=-1, sf_max=1, png=3, ng=png+2
+constexpr int sf_min = -1, sf_max = 1, png = 3, NG = png + 2;
+
+enum { EX, EY, EZ, BX, BY, BZ, JX, JY, JZ, NFIELD };
+
+// Fortran-style array  a(1-g:n1+g [, 1-g:n2+g [, 1-g:n3+g]])
+struct Arr {
+  int lo[3] = {1, 1, 1}, sz[3] = {1, 1, 1};
+  std::vector<double> v;
+  void init(const int n[3], int nd, int g = NG) {
+    for (int d = 0; d < 3; d++) {
+      if (d < nd) { lo[d] = 1 - g; sz[d] = n[d] + 2 * g; }
+      else { lo[d] = 1; sz[d] = 1; }
+    }
+    v.assign((size_t)sz[0] * sz[1] * sz[2], 0.0);
+  }
+  inline size_t idx(int i, int j, int k) const {
+    return (size_t)(i - lo[0]) + (size_t)sz[0] * ((size_t)(j - lo[1]) + (size_t)sz[1] * (size_t)(k - lo[2]));
+  }
+  inline double &operator()(int i, int j = 1, int k = 1) { return v[idx(i, j, k)]; }
+  inline double operator()(int i, int j = 1, int k = 1) const { return v[idx(i, j, k)]; }
+};
+
+struct Particle {  // shared_data.F90:93-142 (default flags)
+  double pos[3];
+  double p[3];
+  double w;
+};
+
+struct SpeciesCfg {  // C-ABI mirror, see orc_species in epoch_oracle.h
+  double charge, mass;
+  int bc_particle[6];
+  double npart_per_cell;
+  double density;      // uniform number density inside the box below
+  double box_lo[3], box_hi[3];  // density = 0 outside [lo,hi) per active dim
+  double temp[3];      // K
+  double drift[3];     // kg m/s
+  int zero_current;
+  int immobile;
+};
+
+struct Config {
+  int ndims;
+  int n_global[3];
+  int nproc[3];
+  double xmin[3], xmax[3];
+  int bc_field[6];
+  double dt;
+  int n_species;
+  int seed;  // 7842432 by default (setup.F90:567)
+};
+
+// random_generator.f90:23-78 (KISS), :112-173 (polar Box-Muller)
+struct Rng {
+  int32_t x, y, z, w;
+  bool cached = false;
+  double cached_value = 0.0;
+  static inline int32_t wrap(int64_t a) { return (int32_t)(uint32_t)(uint64_t)a; }
+  double random() {
+    x = wrap((int64_t)69069 * x + 1327217885);
+    uint32_t a1 = (uint32_t)y;
+    uint32_t a2 = a1 ^ (a1 << 13);
+    uint32_t a3 = a2 ^ (a2 >> 17);
+    y = (int32_t)(a3 ^ (a3 << 5));
+    z = wrap((int64_t)18000 * (z & 65535) + (int64_t)((uint32_t)z >> 16));
+    w = wrap((int64_t)30903 * (w & 65535) + (int64_t)((uint32_t)w >> 16));
+    int32_t kiss = wrap((int64_t)x + (int64_t)y + (int64_t)(int32_t)((uint32_t)z << 16) + (int64_t)w);
+    return ((double)kiss + 2147483648.0) / 4294967296.0;
+  }
+  void init(int seed) {
+    x = wrap((int64_t)123456789 + seed);
+    y = wrap((int64_t)362436069 + seed);
+    z = wrap((int64_t)521288629 + seed);
+    w = wrap((int64_t)916191069 + seed);
+    cached = false;
+    cached_value = 0.0;
+    for (int i = 0; i < 1000; i++) (void)random();
+  }
+  double box_muller(double stdev, double mu) {
+    const double c_tiny = 2.2250738585072014e-308;
+    double r;
+    if (cached) {
+      cached = false;
+      r = cached_value * stdev + mu;
+    } else {
+      cached = true;
+      double rand1, rand2, ww;
+      for (;;) {
+        rand1 = random();
+        rand2 = random();
+        rand1 = 2.0 * rand1 - 1.0;
+        rand2 = 2.0 * rand2 - 1.0;
+        ww = rand1 * rand1 + rand2 * rand2;
+        if (ww > c_tiny && ww < 1.0) break;
+      }
+      ww = std::sqrt((-2.0 * std::log(ww)) / ww);
+      r = rand1 * ww * stdev + mu;
+      cached_value = rand2 * ww;
+    }
+    return r;
+  }
+};
+
+struct Rank {
+  int rank;
+  int coords[3] = {0, 0, 0};
+  int n[3] = {1, 1, 1};           // nx, ny, nz (local)
+  int gmin[3] = {1, 1, 1};        // nx_global_min ...
+  bool is_bnd[6] = {false, false, false, false, false, false};
+  int neighbour[3][3][3];         // [iz+1][iy+1][ix+1], -1 = MPI_PROC_NULL
+  double grid_min_local[3] = {0, 0, 0};
+  double min_local[3] = {0, 0, 0}, max_local[3] = {0, 0, 0};
+  Arr f[NFIELD];
+  // setup.F90:391-447 boundary snapshots on x_min / x_max (index by field 0..5)
+  Arr snap_min[6], snap_max[6];
+  Arr src1[2], src2[2];  // laser sources on x_min / x_max, set by the host each step
+  std::vector<std::vector<Particle>> part;       // per species
+  std::vector<std::vector<int64_t>> bnd_cand;    // boundary candidate indices per species
+  Rng rng;
+};
+
+struct World {
+  Config cfg;
+  std::vector<SpeciesCfg> sp;
+  int nd;
+  int nranks;
+  double d[3] = {1, 1, 1};  // dx,dy,dz
+  double length[3] = {0, 0, 0};
+  double grid_min[3] = {0, 0, 0};  // x_grid_min (cell centre of global cell 1)
+  double min_outer[3], max_outer[3];
+  std::vector<int> cell_min[3], cell_max[3];
+  bool periods[3] = {false, false, false};
+  int bc_field[6];
+  int bc_allspecies[6];
+  double dt;
+  std::vector<Rank> r;
+};
+
+inline double x_global(const World &w, int d, int i) {
+  // setup.F90:188  x_global(ix) = x_grid_min + (ix - 1) * dx
+  return w.grid_min[d] + (double)(i - 1) * w.d[d];
+}
+
+// ---------------------------------------------------------------------------
+// Setup: boundaries.F90:30-74, mpi_routines.F90:179-275,279-365,
+// setup.F90:162-204, utilities.f90:343-421
+// ---------------------------------------------------------------------------
+void setup_world(World &w) {
+  const Config &cf = w.cfg;
+  const int nd = w.nd = cf.ndims;
+  w.dt = cf.dt;
+  for (int i = 0; i < 6; i++) {
+    int b = cf.bc_field[i];
+    // boundary.F90:44-57
+    if (b == c_bc_other) b = c_bc_clamp;
+    if (b == c_bc_reflect) b = c_bc_clamp;
+    if (b == c_bc_open) b = c_bc_simple_outflow;
+    w.bc_field[i] = b;
+  }
+  for (auto &s : w.sp)
+    for (int i = 0; i < 2 * nd; i++) {
+      int &b = s.bc_particle[i];
+      // boundary.F90:108-122
+      if (b == c_bc_other || b == c_bc_conduct) b = c_bc_reflect;
+      if (b == c_bc_simple_laser || b == c_bc_simple_outflow) b = c_bc_open;
+    }
+  // deck_species_block.F90:182-199
+  for (int i = 0; i < 6; i++) w.bc_allspecies[i] = c_bc_open;
+  for (size_t is = 0; is < w.sp.size(); is++)
+    for (int i = 0; i < 2 * nd; i++) {
+      int b = w.sp[is].bc_particle[i];
+      if (b != c_bc_reflect && b != c_bc_periodic) b = c_bc_open;
+      if (is == 0) w.bc_allspecies[i] = b;
+      else if (w.bc_allspecies[i] != b) w.bc_allspecies[i] = -99;  // c_bc_mixed: unsupported
+    }
+  if (w.sp.empty())
+    for (int i = 0; i < 2 * nd; i++)
+      w.bc_allspecies[i] = (cf.bc_field[i] == c_bc_periodic) ? c_bc_periodic : c_bc_open;
+
+  // setup.F90:167-181 (cpml_thickness = 0)
+  for (int d = 0; d < nd; d++) {
+    w.length[d] = cf.xmax[d] - cf.xmin[d];
+    w.d[d] = w.length[d] / (double)cf.n_global[d];
+    double g = cf.xmin[d] - w.d[d] * 0.0;
+    w.grid_min[d] = g + w.d[d] / 2.0;
+    // utilities.f90:367-369
+    double boundary_shift = (double)((1 + png + 0) / 2);
+    w.min_outer[d] = cf.xmin[d] - boundary_shift * w.d[d];
+    w.max_outer[d] = cf.xmax[d] + boundary_shift * w.d[d];
+  }
+  // mpi_routines.F90:194-221
+  for (int d = 0; d < nd; d++) {
+    bool per = (w.bc_field[2 * d] == c_bc_periodic);
+    for (auto &s : w.sp)
+      if (s.bc_particle[2 * d] == c_bc_periodic) per = true;
+    w.periods[d] = per;
+  }
+  // mpi_routines.F90:317-351
+  int np[3] = {1, 1, 1};
+  for (int d = 0; d < nd; d++) {
+    np[d] = std::max(1, cf.nproc[d]);
+    int ng_ = cf.n_global[d];
+    int n0 = ng_ / np[d];
+    int nxp = (n0 * np[d] != ng_) ? (n0 + 1) * np[d] - ng_ : np[d];
+    w.cell_min[d].resize(np[d]);
+    w.cell_max[d].resize(np[d]);
+    for (int i = 1; i <= nxp; i++) {
+      w.cell_min[d][i - 1] = (i - 1) * n0 + 1;
+      w.cell_max[d][i - 1] = i * n0;
+    }
+    for (int i = nxp + 1; i <= np[d]; i++) {
+      w.cell_min[d][i - 1] = nxp * n0 + (i - nxp - 1) * (n0 + 1) + 1;
+      w.cell_max[d][i - 1] = nxp * n0 + (i - nxp) * (n0 + 1);
+    }
+  }
+  w.nranks = np[0] * np[1] * np[2];
+  w.r.resize(w.nranks);
+  for (int rk = 0; rk < w.nranks; rk++) {
+    Rank &R = w.r[rk];
+    R.rank = rk;
+    // MPI_CART_CREATE with dims = (nprocz, nprocy, nprocx), row major:
+    // x_coords varies fastest (mpi_routines.F90:186-187, 239-245)
+    R.coords[0] = rk % np[0];
+    R.coords[1] = (rk / np[0]) % np[1];
+    R.coords[2] = rk / (np[0] * np[1]);
+    for (int d = 0; d < 3; d++) {
+      if (d < nd) {
+        R.gmin[d] = w.cell_min[d][R.coords[d]];
+        R.n[d] = w.cell_max[d][R.coords[d]] - R.gmin[d] + 1;
+        R.is_bnd[2 * d] = (R.coords[d] == 0);
+        R.is_bnd[2 * d + 1] = (R.coords[d] == np[d] - 1);
+        // utilities.f90:349-365
+        R.grid_min_local[d] = x_global(w, d, w.cell_min[d][R.coords[d]]);
+        double hdx = 0.5 * w.d[d];
+        R.min_local[d] = R.grid_min_local[d] - hdx;
+        R.max_local[d] = x_global(w, d, w.cell_max[d][R.coords[d]] + 1) - hdx;
+      }
+    }
+    // mpi_routines.F90:256-273
+    for (int iz = -1; iz <= 1; iz++)
+      for (int iy = -1; iy <= 1; iy++)
+        for (int ix = -1; ix <= 1; ix++) {
+          int t[3] = {R.coords[0] + ix, R.coords[1] + iy, R.coords[2] + iz};
+          bool op = true;
+          for (int d = 0; d < 3; d++) {
+            if (d >= nd) { if (t[d] != 0) op = false; continue; }
+            if (t[d] < 0 || t[d] >= np[d]) {
+              if (!w.periods[d]) op = false;
+              else t[d] = (t[d] + np[d]) % np[d];
+            }
+          }
+          R.neighbour[iz + 1][iy + 1][ix + 1] = op ? (t[2] * np[1] + t[1]) * np[0] + t[0] : -1;
+        }
+    for (int i = 0; i < NFIELD; i++) R.f[i].init(R.n, nd);
+    int pn[3] = {1, R.n[1], R.n[2]};
+    for (int i = 0; i < 6; i++) {
+      // planes (1-ng:ny+ng, 1-ng:nz+ng) stored with a unit x extent
+      Arr &a = R.snap_min[i], &b = R.snap_max[i];
+      for (Arr *q : {&a, &b}) {
+        q->lo[0] = 1; q->sz[0] = 1;
+        for (int d = 1; d < 3; d++) {
+          if (d < nd) { q->lo[d] = 1 - NG; q->sz[d] = pn[d] + 2 * NG; }
+          else { q->lo[d] = 1; q->sz[d] = 1; }
+        }
+        q->v.assign((size_t)q->sz[1] * q->sz[2], 0.0);
+      }
+    }
+    for (int s = 0; s < 2; s++)
+      for (Arr *q : {&R.src1[s], &R.src2[s]}) {
+        *q = R.snap_min[0];
+        std::fill(q->v.begin(), q->v.end(), 0.0);
+      }
+    R.part.resize(w.sp.size());
+    R.bnd_cand.resize(w.sp.size());
+    // setup.F90:566-571
+    R.rng.init(cf.seed + rk);
+  }
+}
+
+inline int nbr(const Rank &R, int d, int s) {  // neighbour along one axis
+  int o[3] = {0, 0, 0};
+  o[d] = s;
+  return R.neighbour[o[2] + 1][o[1] + 1][o[0] + 1];
+}
+
+// ---------------------------------------------------------------------------
+// Ghost-cell exchange: boundary.F90:222-315 (2D), epoch3d boundary.F90:317-470,
+// epoch1d boundary.F90:143-190
+// ---------------------------------------------------------------------------
+struct Box { int lo[3], hi[3]; };
+
+inline Box full_box(const Arr &a) {
+  Box b;
+  for (int d = 0; d < 3; d++) { b.lo[d] = a.lo[d]; b.hi[d] = a.lo[d] + a.sz[d] - 1; }
+  return b;
+}
+
+void copy_out(const Arr &a, const Box &b, std::vector<double> &t) {
+  t.clear();
+  for (int k = b.lo[2]; k <= b.hi[2]; k++)
+    for (int j = b.lo[1]; j <= b.hi[1]; j++)
+      for (int i = b.lo[0]; i <= b.hi[0]; i++) t.push_back(a(i, j, k));
+}
+
+void field_bc(World &w, int which) {
+  const int nd = w.nd;
+  std::vector<std::vector<double>> temp(w.nranks);
+  for (int d = 0; d < nd; d++) {
+    // pass 1: send low interior strip to proc_min, receive from proc_max into high ghosts
+    // pass 2: send high interior strip to proc_max, receive from proc_min into low ghosts
+    for (int pass = 0; pass < 2; pass++) {
+      for (int rk = 0; rk < w.nranks; rk++) {
+        Rank &R = w.r[rk];
+        temp[rk].clear();
+        int src = nbr(R, d, pass == 0 ? +1 : -1);
+        if (src < 0) continue;
+        const Rank &S = w.r[src];
+        const Arr &a = S.f[which];
+        Box b = full_box(a);
+        if (pass == 0) { b.lo[d] = 1; b.hi[d] = NG; }
+        else { b.lo[d] = S.n[d] + 1 - NG; b.hi[d] = S.n[d]; }
+        copy_out(a, b, temp[rk]);
+      }
+      for (int rk = 0; rk < w.nranks; rk++) {
+        Rank &R = w.r[rk];
+        if (temp[rk].empty()) continue;
+        int bd = (pass == 0) ? 2 * d + 1 : 2 * d;
+        if (R.is_bnd[bd] && w.bc_field[bd] != c_bc_periodic) continue;
+        Arr &a = R.f[which];
+        Box b = full_box(a);
+        if (pass == 0) { b.lo[d] = R.n[d] + 1; b.hi[d] = R.n[d] + NG; }
+        else { b.lo[d] = 1 - NG; b.hi[d] = 0; }
+        size_t n = 0;
+        for (int k = b.lo[2]; k <= b.hi[2]; k++)
+          for (int j = b.lo[1]; j <= b.hi[1]; j++)
+            for (int i = b.lo[0]; i <= b.hi[0]; i++) a(i, j, k) = temp[rk][n++];
+      }
+    }
+  }
+}
+
+// stagger(dir, field): setup.F90:124-134
+inline bool stagger(int dir, int field) {
+  switch (field) {
+    case EX: return dir == 0;
+    case EY: return dir == 1;
+    case EZ: return dir == 2;
+    case BX: return dir != 0;
+    case BY: return dir != 1;
+    case BZ: return dir != 2;
+  }
+  return false;
+}
+
+// boundary.F90:416-469 (sign=+1) and :473-530 (sign=-1, zero on the staggered plane)
+void field_mirror(World &w, int which, int boundary, double sign) {
+  if (w.bc_field[boundary] == c_bc_periodic) return;
+  const int d = boundary / 2;
+  if (d >= w.nd) return;
+  const bool is_max = boundary & 1;
+  for (Rank &R : w.r) {
+    if (!R.is_bnd[boundary]) continue;
+    Arr &a = R.f[which];
+    Box b = full_box(a);
+    auto plane_copy = [&](int dst, int src, bool zero) {
+      Box q = b;
+      q.lo[d] = q.hi[d] = dst;
+      for (int k = q.lo[2]; k <= q.hi[2]; k++)
+        for (int j = q.lo[1]; j <= q.hi[1]; j++)
+          for (int i = q.lo[0]; i <= q.hi[0]; i++) {
+            int s[3] = {i, j, k};
+            s[d] = src;
+            a(i, j, k) = zero ? 0.0 : sign * a(s[0], s[1], s[2]);
+          }
+    };
+    const int nn = R.n[d];
+    const bool clamp = sign < 0;
+    if (!is_max) {
+      if (stagger(d, which)) {
+        for (int i = 1; i <= NG - 1; i++) plane_copy(i - NG, NG - i, false);
+        if (clamp) plane_copy(0, 0, true);
+      } else {
+        for (int i = 1; i <= NG; i++) plane_copy(i - NG, NG + 1 - i, false);
+      }
+    } else {
+      if (stagger(d, which)) {
+        if (clamp) plane_copy(nn, nn, true);
+        for (int i = 1; i <= NG - 1; i++) plane_copy(nn + i, nn - i, false);
+      } else {
+        for (int i = 1; i <= NG; i++) plane_copy(nn + i, nn + 1 - i, false);
+      }
+    }
+  }
+}
+
+// boundary.F90:808-854 / :858-907
+void field_bcs3(World &w, int f0, bool mpi_only) {
+  for (int i = 0; i < 3; i++) field_bc(w, f0 + i);
+  if (mpi_only) return;
+  for (int i = 0; i < 2 * w.nd; i++) {
+    int b = w.bc_field[i];
+    if (b == c_bc_clamp || b == c_bc_simple_laser || b == c_bc_simple_outflow)
+      for (int q = 0; q < 3; q++) field_mirror(w, f0 + q, i, -1.0);
+    if (b == c_bc_zero_gradient)
+      for (int q = 0; q < 3; q++) field_mirror(w, f0 + q, i, +1.0);
+  }
+}
+void efield_bcs(World &w) { field_bcs3(w, EX, false); }
+void bfield_bcs(World &w, bool mpi_only) { field_bcs3(w, BX, mpi_only); }
+
+// ---------------------------------------------------------------------------
+// FDTD: fields.f90:206-225 (E), :422-439 (B) for 2D; epoch3d fields.f90:312-337,
+// :632-654; epoch1d fields.f90:150-166, :296-303.  Yee, order 2, no CPML.
+// ---------------------------------------------------------------------------
+template <int ND>
+void update_e_field(World &w, double hdt) {
+  const double cnx = hdt / w.d[0] * (c * c);
+  const double cny = ND >= 2 ? hdt / w.d[1] * (c * c) : 0.0;
+  const double cnz = ND >= 3 ? hdt / w.d[2] * (c * c) : 0.0;
+  const double fac = hdt / epsilon0;
+  for (Rank &R : w.r) {
+    Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
+    const Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
+    const Arr &jx = R.f[JX], &jy = R.f[JY], &jz = R.f[JZ];
+    const int k0 = ND >= 3 ? 0 : 1, k1 = ND >= 3 ? R.n[2] : 1;
+    const int j0 = ND >= 2 ? 0 : 1, j1 = ND >= 2 ? R.n[1] : 1;
+    for (int iz = k0; iz <= k1; iz++)
+      for (int iy = j0; iy <= j1; iy++)
+        for (int ix = 0; ix <= R.n[0]; ix++) {
+          if (ND == 1) {
+            ex(ix) = ex(ix) - fac * jx(ix);
+            ey(ix) = ey(ix) - cnx * (bz(ix) - bz(ix - 1)) - fac * jy(ix);
+            ez(ix) = ez(ix) + cnx * (by(ix) - by(ix - 1)) - fac * jz(ix);
+          } else if (ND == 2) {
+            ex(ix, iy) = ex(ix, iy) + cny * (bz(ix, iy) - bz(ix, iy - 1)) - fac * jx(ix, iy);
+            ey(ix, iy) = ey(ix, iy) - cnx * (bz(ix, iy) - bz(ix - 1, iy)) - fac * jy(ix, iy);
+            ez(ix, iy) = ez(ix, iy) + cnx * (by(ix, iy) - by(ix - 1, iy)) -
+                         cny * (bx(ix, iy) - bx(ix, iy - 1)) - fac * jz(ix, iy);
+          } else {
+            ex(ix, iy, iz) = ex(ix, iy, iz) + cny * (bz(ix, iy, iz) - bz(ix, iy - 1, iz)) -
+                             cnz * (by(ix, iy, iz) - by(ix, iy, iz - 1)) - fac * jx(ix, iy, iz);
+            ey(ix, iy, iz) = ey(ix, iy, iz) + cnz * (bx(ix, iy, iz) - bx(ix, iy, iz - 1)) -
+                             cnx * (bz(ix, iy, iz) - bz(ix - 1, iy, iz)) - fac * jy(ix, iy, iz);
+            ez(ix, iy, iz) = ez(ix, iy, iz) + cnx * (by(ix, iy, iz) - by(ix - 1, iy, iz)) -
+                             cny * (bx(ix, iy, iz) - bx(ix, iy - 1, iz)) - fac * jz(ix, iy, iz);
+          }
+        }
+  }
+}
+
+template <int ND>
+void update_b_field(World &w, double hdt) {
+  const double hdtx = hdt / w.d[0];
+  const double hdty = ND >= 2 ? hdt / w.d[1] : 0.0;
+  const double hdtz = ND >= 3 ? hdt / w.d[2] : 0.0;
+  for (Rank &R : w.r) {
+    const Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
+    Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
+    const int k0 = ND >= 3 ? 0 : 1, k1 = ND >= 3 ? R.n[2] : 1;
+    const int j0 = ND >= 2 ? 0 : 1, j1 = ND >= 2 ? R.n[1] : 1;
+    for (int iz = k0; iz <= k1; iz++)
+      for (int iy = j0; iy <= j1; iy++)
+        for (int ix = 0; ix <= R.n[0]; ix++) {
+          if (ND == 1) {
+            by(ix) = by(ix) + hdtx * (ez(ix + 1) - ez(ix));
+            bz(ix) = bz(ix) - hdtx * (ey(ix + 1) - ey(ix));
+          } else if (ND == 2) {
+            bx(ix, iy) = bx(ix, iy) - hdty * (ez(ix, iy + 1) - ez(ix, iy));
+            by(ix, iy) = by(ix, iy) + hdtx * (ez(ix + 1, iy) - ez(ix, iy));
+            bz(ix, iy) = bz(ix, iy) - hdtx * (ey(ix + 1, iy) - ey(ix, iy)) +
+                         hdty * (ex(ix, iy + 1) - ex(ix, iy));
+          } else {
+            bx(ix, iy, iz) = bx(ix, iy, iz) - hdty * (ez(ix, iy + 1, iz) - ez(ix, iy, iz)) +
+                             hdtz * (ey(ix, iy, iz + 1) - ey(ix, iy, iz));
+            by(ix, iy, iz) = by(ix, iy, iz) - hdtz * (ex(ix, iy, iz + 1) - ex(ix, iy, iz)) +
+                             hdtx * (ez(ix + 1, iy, iz) - ez(ix, iy, iz));
+            bz(ix, iy, iz) = bz(ix, iy, iz) - hdtx * (ey(ix + 1, iy, iz) - ey(ix, iy, iz)) +
+                             hdty * (ex(ix, iy + 1, iz) - ex(ix, iy, iz));
+          }
+        }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Laser / outflow boundary on x_min, x_max: laser.f90:310-458 (2D),
+// epoch3d laser.f90:350-506, epoch1d laser.f90:260-392.
+// source1/source2 are evaluated by the host (deck expressions) and stored in
+// R.src1/src2 before the call.
+// ---------------------------------------------------------------------------
+template <int ND>
+void outflow_bcs_x(World &w, bool is_max, double dt) {
+  const double dtc2 = dt * (c * c);
+  const double lx = dtc2 / w.d[0];
+  const double ly = ND >= 2 ? dtc2 / w.d[1] : 0.0;
+  const double lz = ND >= 3 ? dtc2 / w.d[2] : 0.0;
+  const double sum = 1.0 / (lx + c);
+  const double diff = lx - c;
+  const double dt_eps = dt / epsilon0;
+  for (Rank &R : w.r) {
+    if (!R.is_bnd[is_max ? 1 : 0]) continue;
+    Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
+    const Arr &ey = R.f[EY], &ez = R.f[EZ], &jy = R.f[JY], &jz = R.f[JZ];
+    const Arr *snap = is_max ? R.snap_max : R.snap_min;
+    const Arr &s1 = R.src1[is_max ? 1 : 0], &s2 = R.src2[is_max ? 1 : 0];
+    const int k0 = ND >= 3 ? 0 : 1, k1 = ND >= 3 ? R.n[2] : 1;
+    const int j0 = ND >= 2 ? 0 : 1, j1 = ND >= 2 ? R.n[1] : 1;
+    const int nx = R.n[0];
+    // all right-hand sides use pre-update values (Fortran array assignment);
+    // bz is written before by is evaluated but by's RHS never reads bz.
+    for (int k = k0; k <= k1; k++)
+      for (int j = j0; j <= j1; j++) {
+        if (!is_max) bx(0, j, k) = snap[BX](1, j, k);
+        else bx(nx + 1, j, k) = snap[BX](1, j, k);
+      }
+    for (int k = k0; k <= k1; k++)
+      for (int j = j0; j <= j1; j++) {
+        if (!is_max) {
+          const int lp = 1;
+          double t = 4.0 * s1(1, j, k) + 2.0 * (snap[EY](1, j, k) + c * snap[BZ](1, j, k)) -
+                     2.0 * ey(lp, j, k);
+          if (ND == 3) t = t - lz * (bx(lp, j, k) - bx(lp, j, k - 1));
+          t = t + dt_eps * jy(lp, j, k) + diff * bz(lp, j, k);
+          bz(lp - 1, j, k) = sum * t;
+        } else {
+          const int lp = nx;
+          double t = -4.0 * s1(1, j, k) - 2.0 * (snap[EY](1, j, k) - c * snap[BZ](1, j, k)) +
+                     2.0 * ey(lp, j, k);
+          if (ND == 3) t = t + lz * (bx(lp, j, k) - bx(lp, j, k - 1));
+          t = t - dt_eps * jy(lp, j, k) + diff * bz(lp - 1, j, k);
+          bz(lp, j, k) = sum * t;
+        }
+      }
+    for (int k = k0; k <= k1; k++)
+      for (int j = j0; j <= j1; j++) {
+        if (!is_max) {
+          const int lp = 1;
+          double t = -4.0 * s2(1, j, k) - 2.0 * (snap[EZ](1, j, k) - c * snap[BY](1, j, k)) +
+                     2.0 * ez(lp, j, k);
+          if (ND >= 2) t = t - ly * (bx(lp, j, k) - bx(lp, j - 1, k));
+          t = t - dt_eps * jz(lp, j, k) + diff * by(lp, j, k);
+          by(lp - 1, j, k) = sum * t;
+        } else {
+          const int lp = nx;
+          double t = 4.0 * s2(1, j, k) + 2.0 * (snap[EZ](1, j, k) + c * snap[BY](1, j, k)) -
+                     2.0 * ez(lp, j, k);
+          if (ND >= 2) t = t + ly * (bx(lp, j, k) - bx(lp, j - 1, k));
+          t = t + dt_eps * jz(lp, j, k) + diff * by(lp - 1, j, k);
+          by(lp, j, k) = sum * t;
+        }
+      }
+  }
+}
+
+// setup.F90:391-447 (x boundaries only)
+void setup_field_boundaries(World &w) {
+  for (Rank &R : w.r) {
+    const int nx0 = 1, nx1 = R.n[0];
+    for (int f = 0; f < 6; f++) {
+      const Arr &a = R.f[f];
+      Arr &lo = R.snap_min[f], &hi = R.snap_max[f];
+      const bool avg = (f == EX || f == BY || f == BZ);
+      for (int k = lo.lo[2]; k < lo.lo[2] + lo.sz[2]; k++)
+        for (int j = lo.lo[1]; j < lo.lo[1] + lo.sz[1]; j++) {
+          lo(1, j, k) = avg ? 0.5 * (a(nx0, j, k) + a(nx0 - 1, j, k)) : a(nx0, j, k);
+          hi(1, j, k) = avg ? 0.5 * (a(nx1, j, k) + a(nx1 - 1, j, k)) : a(nx1, j, k);
+        }
+    }
+  }
+}
+
+// boundary.F90:911-944
+template <int ND>
+void bfield_final_bcs(World &w, double dt) {
+  bfield_bcs(w, false);
+  for (int s = 0; s < 2; s++) {
+    int b = w.bc_field[s];
+    if (b == c_bc_simple_laser || b == c_bc_simple_outflow) outflow_bcs_x<ND>(w, s == 1, dt);
+  }
+  bfield_bcs(w, true);
+}
+
+// fields.f90:533-582
+template <int ND>
+void update_eb_fields_half(World &w) {
+  const double hdt = 0.5 * w.dt;
+  update_e_field<ND>(w, hdt);
+  efield_bcs(w);
+  update_b_field<ND>(w, hdt);
+  bfield_bcs(w, true);
+}
+template <int ND>
+void update_eb_fields_final(World &w) {
+  const double hdt = 0.5 * w.dt;
+  update_b_field<ND>(w, hdt);
+  bfield_final_bcs<ND>(w, w.dt);
+  update_e_field<ND>(w, hdt);
+  efield_bcs(w);
+}
+
+// ---------------------------------------------------------------------------
+// Particle push: particles.F90:28-650 (2D), epoch3d particles.F90, epoch1d
+// particles.F90.  Triangle shape: include/triangle/{gx,hx_dcell,e_part,b_part}.inc
+// ---------------------------------------------------------------------------
+inline void tri_weights(double f, double *g) {  // g points at index 0
+  // include/triangle/gx.inc:1-4
+  double cf2 = f * f;
+  g[-1] = 0.25 + cf2 + f;
+  g[0] = 1.5 - 2.0 * cf2;
+  g[1] = 0.25 + cf2 - f;
+}
+
+template <int ND>
+inline double gather(const Arr &F, const double *wx, int cx, const double *wy, int cy,
+                     const double *wz, int cz) {
+  // include/triangle/e_part.inc: rows are parenthesised, sums left to right
+  if (ND == 1) {
+    return wx[-1] * F(cx - 1) + wx[0] * F(cx) + wx[1] * F(cx + 1);
+  } else if (ND == 2) {
+    double r = 0.0;
+    for (int iy = -1; iy <= 1; iy++) {
+      double row = wx[-1] * F(cx - 1, cy + iy) + wx[0] * F(cx, cy + iy) + wx[1] * F(cx + 1, cy + iy);
+      double t = wy[iy] * row;
+      r = (iy == -1) ? t : r + t;
+    }
+    return r;
+  } else {
+    double r = 0.0;
+    for (int iz = -1; iz <= 1; iz++) {
+      double pl = 0.0;
+      for (int iy = -1; iy <= 1; iy++) {
+        double row = wx[-1] * F(cx - 1, cy + iy, cz + iz) + wx[0] * F(cx, cy + iy, cz + iz) +
+                     wx[1] * F(cx + 1, cy + iy, cz + iz);
+        double t = wy[iy] * row;
+        pl = (iy == -1) ? t : pl + t;
+      }
+      double t = wz[iz] * pl;
+      r = (iz == -1) ? t : r + t;
+    }
+    return r;
+  }
+}
+
+template <int ND>
+void push_particles(World &w) {
+  const double dt = w.dt;
+  for (Rank &R : w.r) {
+    for (int q = JX; q <= JZ; q++) std::fill(R.f[q].v.begin(), R.f[q].v.end(), 0.0);
+    // particles.F90:128-136, 155-167
+    double fac = 1.0;
+    for (int d = 0; d < ND; d++) fac *= 0.5;
+    const double idx = 1.0 / w.d[0];
+    const double idy = ND >= 2 ? 1.0 / w.d[1] : 0.0;
+    const double idz = ND >= 3 ? 1.0 / w.d[2] : 0.0;
+    const double idt = 1.0 / dt;
+    const double dto2 = dt / 2.0;
+    const double dtco2 = c * dto2;
+    const double dtfac = 0.5 * dt * fac;
+    const double third = 1.0 / 3.0;
+    // 2D: idty, idtx, idxy; 3D: idtyz, idtxz, idtxy; 1D: idtf, idxf
+    double k_fcx, k_fcy, k_fcz;
+    if (ND == 1) { k_fcx = idt * fac; k_fcy = idx * fac; k_fcz = 0.0; }
+    else if (ND == 2) { k_fcx = idt * idy * fac; k_fcy = idt * idx * fac; k_fcz = idx * idy * fac; }
+    else { k_fcx = idt * idy * idz * fac; k_fcy = idt * idx * idz * fac; k_fcz = idt * idx * idy * fac; }
+
+    const Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
+    const Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
+    Arr &jx = R.f[JX], &jy = R.f[JY], &jz = R.f[JZ];
+
+    for (size_t is = 0; is < w.sp.size(); is++) {
+      const SpeciesCfg &S = w.sp[is];
+      R.bnd_cand[is].clear();
+      if (S.immobile) continue;
+      // particles.F90:189-221 (no thermal / cpml): candidate bounds
+      double bnd_min[3], bnd_max[3];
+      for (int d = 0; d < ND; d++) { bnd_min[d] = R.min_local[d]; bnd_max[d] = R.max_local[d]; }
+      // particles.F90:251-256
+      const double part_q = S.charge;
+      const double part_mc = c * S.mass;
+      const double ipart_mc = 1.0 / part_mc;
+      const double cmratio = part_q * dtfac * ipart_mc;
+      const double ccmratio = c * cmratio;
+      const bool deposit = !S.zero_current;
+
+      // gx,gy,gz: entries sf_min-1 and sf_max+1 stay zero (particles.F90:152-153)
+      double G[3][5] = {{0}}, H[3][5];
+      std::vector<Particle> &pl = R.part[is];
+      for (size_t ip = 0; ip < pl.size(); ip++) {
+        Particle &P = pl[ip];
+        const double part_weight = P.w;
+        const double fcx = k_fcx * part_weight;
+        const double fcy = k_fcy * part_weight;
+        const double fcz = k_fcz * part_weight;
+        // :289-302
+        double part_pos[3];
+        for (int d = 0; d < ND; d++) part_pos[d] = P.pos[d] - R.grid_min_local[d];
+        double part_ux = P.p[0] * ipart_mc;
+        double part_uy = P.p[1] * ipart_mc;
+        double part_uz = P.p[2] * ipart_mc;
+        double gamma_rel = std::sqrt(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0);
+        double root = dtco2 / gamma_rel;
+        const double u[3] = {part_ux, part_uy, part_uz};
+        for (int d = 0; d < ND; d++) part_pos[d] = part_pos[d] + u[d] * root;
+        // :319-354
+        const double id[3] = {idx, idy, idz};
+        int cell1[3] = {1, 1, 1}, cell2[3] = {1, 1, 1};
+        for (int d = 0; d < ND; d++) {
+          double cell_r = part_pos[d] * id[d];
+          int c1 = (int)std::floor(cell_r + 0.5);
+          double cell_frac = (double)c1 - cell_r;
+          cell1[d] = c1 + 1;
+          tri_weights(cell_frac, &G[d][2]);
+          int c2 = (int)std::floor(cell_r);
+          cell_frac = (double)c2 - cell_r + 0.5;
+          cell2[d] = c2 + 1;
+          for (int i = 0; i < 5; i++) H[d][i] = 0.0;
+          tri_weights(cell_frac, &H[d][2]);
+        }
+        const double *gx = &G[0][2], *gy = &G[1][2], *gz = &G[2][2];
+        const double *hx = &H[0][2], *hy = &H[1][2], *hz = &H[2][2];
+        // e_part.inc / b_part.inc
+        double ex_part = gather<ND>(ex, hx, cell2[0], gy, cell1[1], gz, cell1[2]);
+        double ey_part = gather<ND>(ey, gx, cell1[0], hy, cell2[1], gz, cell1[2]);
+        double ez_part = gather<ND>(ez, gx, cell1[0], gy, cell1[1], hz, cell2[2]);
+        double bx_part = gather<ND>(bx, gx, cell1[0], hy, cell2[1], hz, cell2[2]);
+        double by_part = gather<ND>(by, hx, cell2[0], gy, cell1[1], hz, cell2[2]);
+        double bz_part = gather<ND>(bz, hx, cell2[0], hy, cell2[1], gz, cell1[2]);
+        // :382-428 Boris
+        double uxm = part_ux + cmratio * ex_part;
+        double uym = part_uy + cmratio * ey_part;
+        double uzm = part_uz + cmratio * ez_part;
+        gamma_rel = std::sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+        root = ccmratio / gamma_rel;
+        double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+        double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+        double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+        double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                      2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+        double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                      2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+        double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                      2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+        part_ux = uxp + cmratio * ex_part;
+        part_uy = uyp + cmratio * ey_part;
+        part_uz = uzp + cmratio * ez_part;
+        // :431-442; the three trees differ textually here
+        double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+        gamma_rel = std::sqrt(part_u2 + 1.0);
+        double delta[3] = {0, 0, 0}, part_vy = 0.0, part_vz = 0.0;
+        if (ND == 1) {
+          // epoch1d particles.F90:392-396
+          root = c / gamma_rel;
+          delta[0] = part_ux * root * dto2;
+          part_vy = part_uy * root;
+          part_vz = part_uz * root;
+        } else if (ND == 2) {
+          // epoch2d particles.F90:433-438
+          double igamma = 1.0 / gamma_rel;
+          root = dtco2 * igamma;
+          delta[0] = part_ux * root;
+          delta[1] = part_uy * root;
+          part_vz = part_uz * c * igamma;
+        } else {
+          // epoch3d particles.F90:470-474
+          root = dtco2 / gamma_rel;
+          delta[0] = part_ux * root;
+          delta[1] = part_uy * root;
+          delta[2] = part_uz * root;
+        }
+        for (int d = 0; d < ND; d++) part_pos[d] = part_pos[d] + delta[d];
+        // :446-459
+        bool cand = false;
+        for (int d = 0; d < ND; d++) {
+          P.pos[d] = part_pos[d] + R.grid_min_local[d];
+          if (P.pos[d] < bnd_min[d] || P.pos[d] > bnd_max[d]) cand = true;
+        }
+        P.p[0] = part_mc * part_ux;
+        P.p[1] = part_mc * part_uy;
+        P.p[2] = part_mc * part_uz;
+        if (cand) R.bnd_cand[is].push_back((int64_t)ip);
+
+        if (!deposit) continue;
+        // :494-547
+        int dcell[3] = {0, 0, 0}, mn[3], mx[3];
+        for (int d = 0; d < ND; d++) {
+          part_pos[d] = part_pos[d] + delta[d];
+          double cell_r = part_pos[d] * id[d];
+          int c3 = (int)std::floor(cell_r + 0.5);
+          double cell_frac = (double)c3 - cell_r;
+          c3 = c3 + 1;
+          for (int i = 0; i < 5; i++) H[d][i] = 0.0;
+          dcell[d] = c3 - cell1[d];
+          tri_weights(cell_frac, &H[d][2 + dcell[d]]);
+          for (int i = 0; i < 5; i++) H[d][i] = H[d][i] - G[d][i];
+          mn[d] = sf_min + (dcell[d] - 1) / 2;
+          mx[d] = sf_max + (dcell[d] + 1) / 2;
+        }
+        if (ND == 1) {
+          // epoch1d particles.F90:489-507
+          const double fjx = fcx * part_q;
+          const double fjy = fcy * part_q * part_vy;
+          const double fjz = fcy * part_q * part_vz;
+          double jxh = 0.0;
+          for (int ix = mn[0]; ix <= mx[0]; ix++) {
+            int cx = cell1[0] + ix;
+            double wx = hx[ix];
+            double wy = gx[ix] + 0.5 * hx[ix];
+            jxh = jxh - fjx * wx;
+            double jyh = fjy * wy;
+            double jzh = fjz * wy;
+            jx(cx) = jx(cx) + jxh;
+            jy(cx) = jy(cx) + jyh;
+            jz(cx) = jz(cx) + jzh;
+          }
+        } else if (ND == 2) {
+          // epoch2d particles.F90:549-579
+          const double fjx = fcx * part_q;
+          const double fjy = fcy * part_q;
+          const double fjz = fcz * part_q * part_vz;
+          double jyh[5] = {0, 0, 0, 0, 0};
+          for (int iy = mn[1]; iy <= mx[1]; iy++) {
+            int cy = cell1[1] + iy;
+            double yfac1 = gy[iy] + 0.5 * hy[iy];
+            double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+            double hy_iy = hy[iy];
+            double jxh = 0.0;
+            for (int ix = mn[0]; ix <= mx[0]; ix++) {
+              int cx = cell1[0] + ix;
+              double xfac1 = gx[ix] + 0.5 * hx[ix];
+              double wx = hx[ix] * yfac1;
+              double wy = hy_iy * xfac1;
+              double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
+              jxh = jxh - fjx * wx;
+              jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+              double jzh = fjz * wz;
+              jx(cx, cy) = jx(cx, cy) + jxh;
+              jy(cx, cy) = jy(cx, cy) + jyh[ix + 2];
+              jz(cx, cy) = jz(cx, cy) + jzh;
+            }
+          }
+        } else {
+          // epoch3d particles.F90:603-648
+          const double fjx = fcx * part_q;
+          const double fjy = fcy * part_q;
+          const double fjz = fcz * part_q;
+          double jzh[5][5];
+          for (auto &row : jzh) for (double &v : row) v = 0.0;
+          for (int iz = mn[2]; iz <= mx[2]; iz++) {
+            int cz = cell1[2] + iz;
+            double zfac1 = gz[iz] + 0.5 * hz[iz];
+            double zfac2 = third * hz[iz] + 0.5 * gz[iz];
+            double gz_iz = gz[iz], hz_iz = hz[iz];
+            double jyh[5] = {0, 0, 0, 0, 0};
+            for (int iy = mn[1]; iy <= mx[1]; iy++) {
+              int cy = cell1[1] + iy;
+              double yfac1 = gy[iy] + 0.5 * hy[iy];
+              double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+              double hygz = hy[iy] * gz_iz;
+              double hyhz = hy[iy] * hz_iz;
+              double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
+              double hzyfac1 = hz_iz * yfac1;
+              double hzyfac2 = hz_iz * yfac2;
+              double jxh = 0.0;
+              for (int ix = mn[0]; ix <= mx[0]; ix++) {
+                int cx = cell1[0] + ix;
+                double xfac1 = gx[ix] + 0.5 * hx[ix];
+                double xfac2 = third * hx[ix] + 0.5 * gx[ix];
+                double wx = hx[ix] * yzfac;
+                double wy = xfac1 * hygz + xfac2 * hyhz;
+                double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
+                jxh = jxh - fjx * wx;
+                jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+                jzh[iy + 2][ix + 2] = jzh[iy + 2][ix + 2] - fjz * wz;
+                jx(cx, cy, cz) = jx(cx, cy, cz) + jxh;
+                jy(cx, cy, cz) = jy(cx, cy, cz) + jyh[ix + 2];
+                jz(cx, cy, cz) = jz(cx, cy, cz) + jzh[iy + 2][ix + 2];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// boundary.F90:948-1025
+void setup_bc_lists(World &w) {
+  for (Rank &R : w.r)
+    for (size_t is = 0; is < w.sp.size(); is++) {
+      R.bnd_cand[is].clear();
+      auto &pl = R.part[is];
+      for (size_t ip = 0; ip < pl.size(); ip++) {
+        bool cand = false;
+        for (int d = 0; d < w.nd; d++)
+          if (pl[ip].pos[d] < R.min_local[d] || pl[ip].pos[d] > R.max_local[d]) cand = true;
+        if (cand) R.bnd_cand[is].push_back((int64_t)ip);
+      }
+    }
+}
+
+// boundary.F90:1029-1462 (2D); 3D/1D identical per axis.  No thermal / CPML.
+void particle_bcs(World &w) {
+  const int nd = w.nd;
+  double shift[3];
+  for (int d = 0; d < nd; d++) shift[d] = w.length[d] + 2.0 * w.d[d] * 0.0;
+  for (size_t is = 0; is < w.sp.size(); is++) {
+    const SpeciesCfg &S = w.sp[is];
+    // send lists per rank per direction
+    std::vector<std::vector<Particle>> send(w.nranks * 27);
+    for (Rank &R : w.r) {
+      auto &pl = R.part[is];
+      std::vector<char> gone(pl.size(), 0);
+      for (int64_t ip : R.bnd_cand[is]) {
+        Particle &cur = pl[ip];
+        int bd[3] = {0, 0, 0};
+        bool out_of_bounds = false;
+        for (int d = 0; d < nd; d++) {
+          const double part_pos = cur.pos[d];
+          // min side (:1076-1159)
+          int sgn = -1;
+          if (part_pos < R.min_local[d]) {
+            bd[d] = sgn;
+            int bc = S.bc_particle[2 * d];
+            if (bc == c_bc_reflect) {
+              if (R.is_bnd[2 * d]) {
+                bd[d] = 0;
+                cur.pos[d] = 2.0 * w.cfg.xmin[d] - part_pos;
+                cur.p[d] = -cur.p[d];
+              }
+            } else if (bc == c_bc_periodic) {
+              if (R.is_bnd[2 * d]) cur.pos[d] = part_pos - sgn * shift[d];
+            } else {
+              if (part_pos < w.min_outer[d]) { bd[d] = 0; out_of_bounds = true; }
+              else if (R.is_bnd[2 * d]) bd[d] = 0;
+            }
+          }
+          // max side (:1161-1244)
+          sgn = 1;
+          if (part_pos >= R.max_local[d]) {
+            bd[d] = sgn;
+            int bc = S.bc_particle[2 * d + 1];
+            if (bc == c_bc_reflect) {
+              if (R.is_bnd[2 * d + 1]) {
+                bd[d] = 0;
+                cur.pos[d] = 2.0 * w.cfg.xmax[d] - part_pos;
+                cur.p[d] = -cur.p[d];
+              }
+            } else if (bc == c_bc_periodic) {
+              if (R.is_bnd[2 * d + 1]) cur.pos[d] = part_pos - sgn * shift[d];
+            } else {
+              if (part_pos >= w.max_outer[d]) { bd[d] = 0; out_of_bounds = true; }
+              else if (R.is_bnd[2 * d + 1]) bd[d] = 0;
+            }
+          }
+        }
+        if (out_of_bounds) {
+          gone[ip] = 1;
+        } else if (std::abs(bd[0]) + std::abs(bd[1]) + std::abs(bd[2]) > 0) {
+          gone[ip] = 1;
+          send[R.rank * 27 + (bd[2] + 1) * 9 + (bd[1] + 1) * 3 + (bd[0] + 1)].push_back(cur);
+        }
+      }
+      size_t o = 0;
+      for (size_t ip = 0; ip < pl.size(); ip++)
+        if (!gone[ip]) pl[o++] = pl[ip];
+      pl.resize(o);
+      R.bnd_cand[is].clear();
+    }
+    // :1436-1446: recv(-ix,-iy) from neighbour(-ix,-iy) gets that rank's send(ix,iy)
+    for (Rank &R : w.r) {
+      const int z0 = nd >= 3 ? -1 : 0, y0 = nd >= 2 ? -1 : 0;
+      for (int iz = z0; iz <= -z0; iz++)
+        for (int iy = y0; iy <= -y0; iy++)
+          for (int ix = -1; ix <= 1; ix++) {
+            if (std::abs(ix) + std::abs(iy) + std::abs(iz) == 0) continue;
+            int src = R.neighbour[-iz + 1][-iy + 1][-ix + 1];
+            if (src < 0) continue;
+            auto &sv = send[src * 27 + (iz + 1) * 9 + (iy + 1) * 3 + (ix + 1)];
+            // the sender addressed neighbour(ix,iy,iz); it must be us
+            if (w.r[src].neighbour[iz + 1][iy + 1][ix + 1] != R.rank) continue;
+            R.part[is].insert(R.part[is].end(), sv.begin(), sv.end());
+          }
+    }
+  }
+}
+
+// boundary.F90:534-630: reflecting fold of J ghost cells
+void particle_reflection_bcs(World &w, int which, int flip_dir) {
+  for (Rank &R : w.r) {
+    Arr &a = R.f[which];
+    for (int d = 0; d < w.nd; d++) {
+      const int nn = R.n[d];
+      Box b = full_box(a);
+      auto fold = [&](int dst, int src, double sgn) {
+        Box q = b;
+        q.lo[d] = q.hi[d] = dst;
+        for (int k = q.lo[2]; k <= q.hi[2]; k++)
+          for (int j = q.lo[1]; j <= q.hi[1]; j++)
+            for (int i = q.lo[0]; i <= q.hi[0]; i++) {
+              int s[3] = {i, j, k};
+              s[d] = src;
+              a(i, j, k) = a(i, j, k) + sgn * a(s[0], s[1], s[2]);
+              a(s[0], s[1], s[2]) = 0.0;
+            }
+      };
+      if (R.is_bnd[2 * d] && w.bc_allspecies[2 * d] == c_bc_reflect) {
+        if (flip_dir == d) for (int i = 1; i <= NG - 1; i++) fold(i, -i, -1.0);
+        else for (int i = 1; i <= NG - 1; i++) fold(i, 1 - i, +1.0);
+      }
+      if (R.is_bnd[2 * d + 1] && w.bc_allspecies[2 * d + 1] == c_bc_reflect) {
+        if (flip_dir == d) for (int i = 1; i <= NG; i++) fold(nn - i, nn + i, -1.0);
+        else for (int i = 1; i <= NG; i++) fold(nn + 1 - i, nn + i, +1.0);
+      }
+    }
+  }
+}
+
+// boundary.F90:634-751: send ghost layers, add into the neighbour's interior
+void particle_periodic_bcs(World &w, int which) {
+  std::vector<std::vector<double>> temp(w.nranks);
+  for (int d = 0; d < w.nd; d++) {
+    for (int pass = 0; pass < 2; pass++) {
+      // pass 0: send high ghosts (nn+1..nn+ng) to +1, receive from -1, add into 1..ng
+      // pass 1: send low ghosts (1-ng..0) to -1, receive from +1, add into nn+1-ng..nn
+      for (int rk = 0; rk < w.nranks; rk++) {
+        Rank &R = w.r[rk];
+        temp[rk].clear();
+        int nl[2] = {nbr(R, d, -1), nbr(R, d, +1)};
+        if (R.is_bnd[2 * d] && w.bc_allspecies[2 * d] != c_bc_periodic) nl[0] = -1;
+        if (R.is_bnd[2 * d + 1] && w.bc_allspecies[2 * d + 1] != c_bc_periodic) nl[1] = -1;
+        int src = pass == 0 ? nl[0] : nl[1];
+        if (src < 0) continue;
+        const Rank &S = w.r[src];
+        // the sender must also be willing to send towards us
+        int snl = pass == 0 ? nbr(S, d, +1) : nbr(S, d, -1);
+        int sb = pass == 0 ? 2 * d + 1 : 2 * d;
+        if (S.is_bnd[sb] && w.bc_allspecies[sb] != c_bc_periodic) snl = -1;
+        if (snl != rk) continue;
+        const Arr &a = S.f[which];
+        Box b = full_box(a);
+        if (pass == 0) { b.lo[d] = S.n[d] + 1; b.hi[d] = S.n[d] + NG; }
+        else { b.lo[d] = 1 - NG; b.hi[d] = 0; }
+        copy_out(a, b, temp[rk]);
+      }
+      for (int rk = 0; rk < w.nranks; rk++) {
+        if (temp[rk].empty()) continue;
+        Rank &R = w.r[rk];
+        Arr &a = R.f[which];
+        Box b = full_box(a);
+        if (pass == 0) { b.lo[d] = 1; b.hi[d] = NG; }
+        else { b.lo[d] = R.n[d] + 1 - NG; b.hi[d] = R.n[d]; }
+        size_t n = 0;
+        for (int k = b.lo[2]; k <= b.hi[2]; k++)
+          for (int j = b.lo[1]; j <= b.hi[1]; j++)
+            for (int i = b.lo[0]; i <= b.hi[0]; i++) a(i, j, k) = a(i, j, k) + temp[rk][n++];
+      }
+    }
+  }
+}
+
+// current_smooth.F90:29-45 with boundary.F90:1466-1475, 783-804
+void current_finish(World &w) {
+  for (int q = 0; q < 3; q++) {
+    particle_reflection_bcs(w, JX + q, q);
+    particle_periodic_bcs(w, JX + q);
+  }
+  for (int q = 0; q < 3; q++) field_bc(w, JX + q);
+}
+
+// ---------------------------------------------------------------------------
+// Loader: helper.F90:371-661 (load_particles, npart_per_cell >= 0 branch),
+// :667-776 (setup_particle_density), particle_temperature.F90:30-81,388-398,
+// include/particle_to_grid.inc, include/triangle/gxfac.inc
+// ---------------------------------------------------------------------------
+inline void particle_to_grid(const World &w, const Rank &R, const Particle &P, int cell[3],
+                             double g[3][3]) {
+  for (int d = 0; d < w.nd; d++) {
+    double cell_r = (P.pos[d] - R.grid_min_local[d]) / w.d[d];
+    int cx = (int)std::floor(cell_r + 0.5);
+    double cf = (double)cx - cell_r;
+    cell[d] = cx + 1;
+    double c2 = cf * cf;
+    g[d][0] = 0.5 * (0.25 + c2 + cf);
+    g[d][1] = 0.75 - c2;
+    g[d][2] = 0.5 * (0.25 + c2 - cf);
+  }
+  for (int d = w.nd; d < 3; d++) { cell[d] = 1; g[d][0] = g[d][2] = 0.0; g[d][1] = 1.0; }
+}
+
+void auto_load(World &w) {
+  const int nd = w.nd;
+  for (size_t is = 0; is < w.sp.size(); is++) {
+    const SpeciesCfg &S = w.sp[is];
+    for (Rank &R : w.r) {
+      // density(ix,iy) evaluated at cell centres incl. ghosts, then field_bc
+      // (periodic wrap / neighbour copy reproduces the same analytic values)
+      Arr dens, map;
+      dens.init(R.n, nd);
+      map.init(R.n, nd);
+      Box b = full_box(dens);
+      for (int k = b.lo[2]; k <= b.hi[2]; k++)
+        for (int j = b.lo[1]; j <= b.hi[1]; j++)
+          for (int i = b.lo[0]; i <= b.hi[0]; i++) {
+            int ii[3] = {i, j, k};
+            bool in = true;
+            for (int d = 0; d < nd; d++) {
+              int gi = ii[d] + R.gmin[d] - 1;
+              // periodic images of ghost cells map back into the domain
+              if (w.bc_field[2 * d] == c_bc_periodic) {
+                int ng_ = w.cfg.n_global[d];
+                gi = ((gi - 1) % ng_ + ng_) % ng_ + 1;
+              }
+              double xc = x_global(w, d, gi);
+              if (xc < S.box_lo[d] || xc >= S.box_hi[d]) in = false;
+            }
+            double v = in ? S.density : 0.0;
+            const double density_min = 2.220446049250313e-16;  // helper.F90:198
+            if (v >= density_min) map(i, j, k) = 1.0;
+            else v = 0.0;
+            dens(i, j, k) = v;
+          }
+      // load_particles, helper.F90:556-583
+      std::vector<Particle> &pl = R.part[is];
+      pl.clear();
+      const int64_t npc = (int64_t)std::floor(S.npart_per_cell);
+      const int k1 = nd >= 3 ? R.n[2] : 1, j1 = nd >= 2 ? R.n[1] : 1;
+      for (int iz = 1; iz <= k1; iz++)
+        for (int iy = 1; iy <= j1; iy++)
+          for (int ix = 1; ix <= R.n[0]; ix++) {
+            if (map(ix, iy, iz) == 0.0) continue;
+            int ii[3] = {ix, iy, iz};
+            for (int64_t ipart = 0; ipart < npc; ipart++) {
+              Particle P;
+              std::memset(&P, 0, sizeof P);
+              for (int d = 0; d < nd; d++) {
+                double xc = x_global(w, d, ii[d] + R.gmin[d] - 1);
+                P.pos[d] = xc + (R.rng.random() - 0.5) * w.d[d];
+              }
+              pl.push_back(P);
+            }
+          }
+    }
+    // helper.F90:658-659
+    setup_bc_lists(w);
+    particle_bcs(w);
+    for (Rank &R : w.r) {
+      std::vector<Particle> &pl = R.part[is];
+      // recompute density map for weights (same as above)
+      Arr dens, map, cnt;
+      dens.init(R.n, nd);
+      map.init(R.n, nd);
+      cnt.init(R.n, nd);
+      Box b = full_box(dens);
+      for (int k = b.lo[2]; k <= b.hi[2]; k++)
+        for (int j = b.lo[1]; j <= b.hi[1]; j++)
+          for (int i = b.lo[0]; i <= b.hi[0]; i++) {
+            int ii[3] = {i, j, k};
+            bool in = true;
+            for (int d = 0; d < nd; d++) {
+              int gi = ii[d] + R.gmin[d] - 1;
+              if (w.bc_field[2 * d] == c_bc_periodic) {
+                int ng_ = w.cfg.n_global[d];
+                gi = ((gi - 1) % ng_ + ng_) % ng_ + 1;
+              }
+              double xc = x_global(w, d, gi);
+              if (xc < S.box_lo[d] || xc >= S.box_hi[d]) in = false;
+            }
+            double v = in ? S.density : 0.0;
+            if (v >= 2.220446049250313e-16) map(i, j, k) = 1.0;
+            else v = 0.0;
+            dens(i, j, k) = v;
+          }
+      // helper.F90:711-757
+      for (Particle &P : pl) {
+        int cell[3];
+        double g[3][3];
+        particle_to_grid(w, R, P, cell, g);
+        double wdata = 0.0;
+        const int z0 = nd >= 3 ? -1 : 0, y0 = nd >= 2 ? -1 : 0;
+        for (int sz_ = z0; sz_ <= -z0; sz_++) {
+          int i = cell[0], j = cell[1], k = cell[2] + sz_;
+          if (nd >= 3 && map(i, j, k) == 0.0) k = cell[2] + sz_ / 2;
+          for (int sy = y0; sy <= -y0; sy++) {
+            i = cell[0];
+            j = cell[1] + sy;
+            if (nd >= 2 && map(i, j, k) == 0.0) j = cell[1] + sy / 2;
+            for (int sx = -1; sx <= 1; sx++) {
+              i = cell[0] + sx;
+              if (map(i, j, k) == 0.0) i = cell[0] + sx / 2;
+              double wgt = g[0][sx + 1];
+              if (nd >= 2) wgt = wgt * g[1][sy + 1];
+              if (nd >= 3) wgt = wgt * g[2][sz_ + 1];
+              wdata = wdata + wgt * dens(i, j, k);
+            }
+          }
+        }
+        P.w = wdata;
+        cnt(cell[0], cell[1], cell[2]) += 1.0;
+      }
+      double vol = 1.0;
+      if (nd == 1) vol = w.d[0];
+      else if (nd == 2) vol = w.d[0] * w.d[1];
+      else vol = w.d[0] * w.d[1] * w.d[2];
+      for (Particle &P : pl) {
+        int cell[3] = {1, 1, 1};
+        for (int d = 0; d < nd; d++)
+          cell[d] = (int)std::floor((P.pos[d] - R.grid_min_local[d]) / w.d[d] + 1.5);
+        P.w = P.w * vol / cnt(cell[0], cell[1], cell[2]);
+      }
+    }
+    // helper.F90:142-145: x pass over all particles, then y, then z
+    for (Rank &R : w.r)
+      for (int dir = 0; dir < 3; dir++)
+        for (Particle &P : R.part[is]) {
+          // uniform temperature / drift: the interpolation sum of a constant
+          int cell[3];
+          double g[3][3];
+          particle_to_grid(w, R, P, cell, g);
+          double temp_local = 0.0, drift_local = 0.0;
+          const int z0 = nd >= 3 ? -1 : 0, y0 = nd >= 2 ? -1 : 0;
+          if (nd == 1) {
+            for (int sx = -1; sx <= 1; sx++) {
+              temp_local = temp_local + g[0][sx + 1] * S.temp[dir];
+              drift_local = drift_local + g[0][sx + 1] * S.drift[dir];
+            }
+          } else if (nd == 2) {
+            for (int sy = y0; sy <= -y0; sy++)
+              for (int sx = -1; sx <= 1; sx++) {
+                temp_local = temp_local + g[0][sx + 1] * g[1][sy + 1] * S.temp[dir];
+                drift_local = drift_local + g[0][sx + 1] * g[1][sy + 1] * S.drift[dir];
+              }
+          } else {
+            for (int sz_ = z0; sz_ <= -z0; sz_++)
+              for (int sy = y0; sy <= -y0; sy++)
+                for (int sx = -1; sx <= 1; sx++) {
+                  temp_local = temp_local + g[0][sx + 1] * g[1][sy + 1] * g[2][sz_ + 1] * S.temp[dir];
+                  drift_local = drift_local + g[0][sx + 1] * g[1][sy + 1] * g[2][sz_ + 1] * S.drift[dir];
+                }
+          }
+          // particle_temperature.F90:388-398
+          double stdev = std::sqrt(temp_local * kb * S.mass);
+          P.p[dir] = R.rng.box_muller(stdev, drift_local);
+        }
+  }
+}
+
+template <int ND>
+void init_sequence(World &w) {
+  // epoch2d.F90:144-162
+  setup_field_boundaries(w);  // after_deck_last, setup.F90:208 → :391
+  setup_bc_lists(w);
+  particle_bcs(w);
+  efield_bcs(w);
+  bfield_final_bcs<ND>(w, w.dt / 2.0);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C interface (ctypes)
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void *orc_create(const Config *cfg, const SpeciesCfg *sp) {
+  World *w = new World;
+  w->cfg = *cfg;
+  for (int i = 0; i < cfg->n_species; i++) w->sp.push_back(sp[i]);
+  setup_world(*w);
+  return w;
+}
+void orc_destroy(void *h) { delete (World *)h; }
+int orc_nranks(void *h) { return ((World *)h)->nranks; }
+double orc_dx(void *h, int d) { return ((World *)h)->d[d]; }
+
+// out: n[3], gmin[3], coords[3], is_bnd[6], neighbour[27]
+void orc_rank_info(void *h, int rk, int *n, int *gmin, int *coords, int *is_bnd, int *neighbour,
+                   double *grid_min_local, double *min_local, double *max_local) {
+  Rank &R = ((World *)h)->r[rk];
+  for (int d = 0; d < 3; d++) {
+    n[d] = R.n[d]; gmin[d] = R.gmin[d]; coords[d] = R.coords[d];
+    grid_min_local[d] = R.grid_min_local[d]; min_local[d] = R.min_local[d]; max_local[d] = R.max_local[d];
+  }
+  for (int i = 0; i < 6; i++) is_bnd[i] = R.is_bnd[i];
+  for (int i = 0; i < 27; i++) neighbour[i] = (&R.neighbour[0][0][0])[i];
+}
+void orc_outer(void *h, double *min_outer, double *max_outer) {
+  World &w = *(World *)h;
+  for (int d = 0; d < 3; d++) { min_outer[d] = w.min_outer[d]; max_outer[d] = w.max_outer[d]; }
+}
+double *orc_field(void *h, int rk, int which) { return ((World *)h)->r[rk].f[which].v.data(); }
+int64_t orc_field_size(void *h, int rk) { return (int64_t)((World *)h)->r[rk].f[0].v.size(); }
+int64_t orc_species_count(void *h, int rk, int is) { return (int64_t)((World *)h)->r[rk].part[is].size(); }
+// packed layout = pack_particle order (partlist.F90:414-486): pos(1..ndims), p(1..3), weight
+void orc_get_particles(void *h, int rk, int is, double *out) {
+  World &w = *(World *)h;
+  const int nv = w.nd + 4;
+  auto &pl = w.r[rk].part[is];
+  for (size_t i = 0; i < pl.size(); i++) {
+    double *o = out + i * nv;
+    for (int d = 0; d < w.nd; d++) o[d] = pl[i].pos[d];
+    for (int d = 0; d < 3; d++) o[w.nd + d] = pl[i].p[d];
+    o[w.nd + 3] = pl[i].w;
+  }
+}
+void orc_set_particles(void *h, int rk, int is, int64_t n, const double *in) {
+  World &w = *(World *)h;
+  const int nv = w.nd + 4;
+  auto &pl = w.r[rk].part[is];
+  pl.resize(n);
+  for (int64_t i = 0; i < n; i++) {
+    const double *o = in + i * nv;
+    std::memset(&pl[i], 0, sizeof(Particle));
+    for (int d = 0; d < w.nd; d++) pl[i].pos[d] = o[d];
+    for (int d = 0; d < 3; d++) pl[i].p[d] = o[w.nd + d];
+    pl[i].w = o[w.nd + 3];
+  }
+}
+// src arrays are local planes (0:ny, 0:nz), x fastest = iy
+void orc_set_laser_source(void *h, int rk, int side, const double *s1, const double *s2) {
+  World &w = *(World *)h;
+  Rank &R = w.r[rk];
+  const int ny = w.nd >= 2 ? R.n[1] : 0, nz = w.nd >= 3 ? R.n[2] : 0;
+  size_t n = 0;
+  for (int k = 0; k <= nz; k++)
+    for (int j = 0; j <= ny; j++, n++) {
+      int jj = w.nd >= 2 ? j : 1, kk = w.nd >= 3 ? k : 1;
+      R.src1[side](1, jj, kk) = s1[n];
+      R.src2[side](1, jj, kk) = s2[n];
+    }
+}
+void orc_auto_load(void *h) { auto_load(*(World *)h); }
+void orc_init(void *h) {
+  World &w = *(World *)h;
+  if (w.nd == 1) init_sequence<1>(w);
+  else if (w.nd == 2) init_sequence<2>(w);
+  else init_sequence<3>(w);
+}
+void orc_fields_half(void *h) {
+  World &w = *(World *)h;
+  if (w.nd == 1) update_eb_fields_half<1>(w);
+  else if (w.nd == 2) update_eb_fields_half<2>(w);
+  else update_eb_fields_half<3>(w);
+}
+void orc_fields_final(void *h) {
+  World &w = *(World *)h;
+  if (w.nd == 1) update_eb_fields_final<1>(w);
+  else if (w.nd == 2) update_eb_fields_final<2>(w);
+  else update_eb_fields_final<3>(w);
+}
+// push_particles = zero J + push + deposit (+ current_bcs(species) no-op) + particle_bcs
+void orc_push(void *h) {
+  World &w = *(World *)h;
+  if (w.nd == 1) push_particles<1>(w);
+  else if (w.nd == 2) push_particles<2>(w);
+  else push_particles<3>(w);
+  particle_bcs(w);
+}
+// push without the trailing particle_bcs (for kernel-level parity checks)
+void orc_push_only(void *h) {
+  World &w = *(World *)h;
+  if (w.nd == 1) push_particles<1>(w);
+  else if (w.nd == 2) push_particles<2>(w);
+  else push_particles<3>(w);
+}
+void orc_particle_bcs(void *h) { particle_bcs(*(World *)h); }
+void orc_setup_bc_lists(void *h) { setup_bc_lists(*(World *)h); }
+void orc_current_finish(void *h) { current_finish(*(World *)h); }
+void orc_efield_bcs(void *h) { efield_bcs(*(World *)h); }
+void orc_bfield_bcs(void *h, int mpi_only) { bfield_bcs(*(World *)h, mpi_only != 0); }
+
+// calc_ppc, io/calc_df.F90:761-808 (triangle): cell = FLOOR((pos-x_grid_min_local)/dx + 0.5) + 1
+// out has the local interior shape (nx,ny,nz), x fastest; out-of-range particles are skipped
+void orc_cell_counts(void *h, int rk, int is, int32_t *out) {
+  World &w = *(World *)h;
+  Rank &R = w.r[rk];
+  std::fill(out, out + (size_t)R.n[0] * R.n[1] * R.n[2], 0);
+  for (const Particle &P : R.part[is]) {
+    int cell[3] = {1, 1, 1};
+    bool ok = true;
+    for (int d = 0; d < w.nd; d++) {
+      cell[d] = (int)std::floor((P.pos[d] - R.grid_min_local[d]) / w.d[d] + 0.5) + 1;
+      if (cell[d] < 1 || cell[d] > R.n[d]) ok = false;
+    }
+    if (ok) out[(size_t)(cell[0] - 1) + (size_t)R.n[0] * ((size_t)(cell[1] - 1) + (size_t)R.n[1] * (cell[2] - 1))]++;
+  }
+}
+
+// KISS stream check hook: fills out[n] with successive random() values for `seed`
+void orc_kiss(int seed, int n, double *out) {
+  Rng g;
+  g.init(seed);
+  for (int i = 0; i < n; i++) out[i] = g.random();
+}
+
+}  // extern "C"
