@@ -1,0 +1,117 @@
+"""Oracle particle half: the reference holds no golden numbers for push/deposit
+(SURVEY.md §4), so the restatement is checked through the property particles.F90:30-34
+claims: the Esirkepov deposit satisfies d(rho)/dt + div(J) = 0 exactly on the grid."""
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from oracle.oracle import Oracle
+from tests import decks
+
+
+def _rho(dk, pos, w, q):
+    """Charge density with the triangle shape at cell centres (calc_charge_density,
+    io/calc_df.F90:608-685), periodic wrap; pos are positions at a half time level."""
+    nd = dk.ndims
+    n = [dk.n[d] for d in range(nd)]
+    rho = np.zeros(n[::-1])
+    cells, gs = [], []
+    for d in range(nd):
+        r = (pos[:, d] - dk.grid_min(d)) / dk.dx(d)
+        cx = np.floor(r + 0.5)
+        f = cx - r
+        cells.append(cx.astype(np.int64))
+        gs.append([0.5 * (0.25 + f * f + f), 0.75 - f * f, 0.5 * (0.25 + f * f - f)])
+    vol = np.prod([dk.dx(d) for d in range(nd)])
+    import itertools
+    for offs in itertools.product((-1, 0, 1), repeat=nd):
+        wgt = q * w / vol
+        idx = []
+        for d in range(nd):
+            wgt = wgt * gs[d][offs[d] + 1]
+            idx.append((cells[d] + offs[d]) % n[d])
+        np.add.at(rho, tuple(idx[::-1]), wgt)
+    return rho
+
+
+def _half_positions(dk, p, mass, sign):
+    """x(t -/+ dt/2) from the stored x(t), p(t): x + sign * u c dt/2 / gamma (particles.F90:297-302)."""
+    nd = dk.ndims
+    u = p[:, nd:nd + 3] / (mass * D.c)
+    gamma = np.sqrt((u ** 2).sum(axis=1) + 1.0)
+    return p[:, :nd] + sign * u[:, :nd] * (D.c * dk.dt() / 2.0) / gamma[:, None]
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 7, 6))])
+def test_charge_conservation(ndims, n):
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=5.0e8, nsteps=3)  # hot: many cell crossings
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    s = dk.species[0]
+    rng = np.random.default_rng(1)
+    for name in ("ex", "ey", "ez", "bx", "by", "bz"):
+        a = o.field(0, name)
+        a[...] = rng.normal(size=a.shape) * (1e9 if name[0] == "e" else 3.0)
+    o.lib = None
+    for _ in range(3):
+        before = o.get_particles(0, 0)
+        o.push_only()
+        after = o.get_particles(0, 0)
+        o.current_finish()          # folds ghost J back (periodic) before particle_bcs reorders
+        # x(t+dt/2) from the old state, x(t+3dt/2) from the new state
+        rho0 = _rho(dk, _half_positions(dk, before, s.mass, +1), before[:, -1], s.charge)
+        rho1 = _rho(dk, _half_positions(dk, after, s.mass, +1), after[:, -1], s.charge)
+        div = np.zeros_like(rho0)
+        for d, name in zip(range(ndims), ("jx", "jy", "jz")):
+            j = o.interior(0, name)
+            ax = 2 - d
+            div += (j - np.roll(j, 1, axis=ax)).reshape(rho0.shape) / dk.dx(d)
+        resid = (rho1 - rho0) / dk.dt() + div
+        scale = np.abs(div).max()
+        assert scale > 0
+        assert np.abs(resid).max() < 1e-11 * scale
+        o.particle_bcs()
+        assert o.count(0, 0) == before.shape[0]
+
+
+def test_loader_counts_and_weights():
+    dk = decks.thermal(2, (12, 10), ppc=5, nproc=(2, 2, 1))
+    o = Oracle(dk)
+    o.auto_load()
+    total = 0
+    for r in range(o.nranks):
+        cc = o.cell_counts(r, 0)
+        assert (cc == 5).all()      # npart_per_cell in every valid cell (helper.F90:556-583)
+        p = o.get_particles(r, 0)
+        total += p.shape[0]
+        # weight = density * dx*dy / npart_in_cell for a uniform plasma (helper.F90:711-770)
+        assert np.allclose(p[:, -1], dk.species[0].density * dk.dx(0) * dk.dx(1) / 5, rtol=1e-12)
+    assert total == 12 * 10 * 5
+
+
+def test_decomposed_matches_single_rank_fields():
+    """Same particles pushed on 1 rank and on 2x2 ranks give the same J to round-off."""
+    dk1 = decks.thermal(2, (16, 12), ppc=4, temp_k=2.0e8)
+    dk4 = decks.thermal(2, (16, 12), ppc=4, temp_k=2.0e8, nproc=(2, 2, 1))
+    o1, o4 = Oracle(dk1), Oracle(dk4)
+    o1.auto_load()
+    allp = o1.get_particles(0, 0)
+    for r in range(4):
+        info = o4.rank_info(r)
+        m = np.ones(allp.shape[0], bool)
+        for d in range(2):
+            m &= (allp[:, d] >= info["min_local"][d]) & (allp[:, d] < info["max_local"][d])
+        o4.set_particles(r, 0, allp[m])
+    for o in (o1, o4):
+        o.init()
+        for _ in range(4):
+            o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+    assert sum(o4.count(r, 0) for r in range(4)) == o1.count(0, 0)
+    full = o1.interior(0, "ey")[0]
+    for r in range(4):
+        info = o4.rank_info(r)
+        x0, y0 = info["gmin"][0] - 1, info["gmin"][1] - 1
+        loc = o4.interior(r, "ey")[0]
+        ref = full[y0:y0 + loc.shape[0], x0:x0 + loc.shape[1]]
+        assert np.allclose(loc, ref, rtol=0, atol=1e-9 * np.abs(full).max())
