@@ -1,0 +1,138 @@
+// Internal declarations shared by the translation units of libepoch_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/epoch_b200.h"
+
+#define EPB_NG 5  // triangle shape: png = 3, ng = png + 2 (constants.F90:549-559)
+
+// constants.F90:192-199
+#define EPB_C 2.99792458e8
+#define EPB_EPS0 8.854187817620389850536563031710750e-12
+#define EPB_KB 1.3806488e-23
+
+// Tile geometry of the cell-sorted particle layout.  A tile is TX*TY*TZ cells; the
+// sort key of a particle is tile_id * cells_per_tile + cell-in-tile, so every tile
+// (one CTA of the push kernel) owns a contiguous, cell-ordered particle range.
+struct TileGeom {
+  int T[3];    // cells per tile along x,y,z (1 on inactive dims)
+  int nt[3];   // tiles along x,y,z
+  int cpt;     // cells per tile
+  int ntiles;
+  int nkeys;   // ntiles * cpt
+};
+
+// Everything the push kernels need, passed by value (__grid_constant__).
+struct PushParams {
+  int nd;
+  int n[3];
+  int sz[3];               // array extents incl. ghosts
+  const double *e[3];
+  const double *b[3];
+  double *j[3];
+  double idx[3];           // 1/dx
+  double grid_min_local[3];
+  double dto2, dtco2, third;
+  double kfc[3];           // idty/idtx/idxy (2D), idtyz/idtxz/idtxy (3D), idtf/idxf (1D)
+  // species (particles.F90:251-256)
+  double part_q, part_mc, ipart_mc, cmratio, ccmratio;
+  int deposit;
+  // particle SoA
+  double *x[3];
+  double *p[3];
+  double *w;
+  long long first, last;   // particle range of a generic launch
+  const int *tile_start;   // tiled launch: ntiles+1 offsets into the sorted prefix
+  long long n_sorted_clip; // tile ranges are clipped to this count
+  TileGeom tg;
+  // particle boundary conditions (particles.F90:189-221, boundary.F90:1029-1462)
+  double bnd_min[3], bnd_max[3];
+  double min_local[3], max_local[3];
+  double gmin[3], gmax[3], shift[3];
+  double min_outer[3], max_outer[3];
+  int bc_min[3], bc_max[3];
+  int is_bnd_min[3], is_bnd_max[3];
+  int nbr_is_self[27];     // neighbour(ix,iy,iz) == this rank
+  int nbr_valid[27];
+  // outbox: particles that leave this rank (index lists per direction; slot 13 = deleted)
+  int *out_count;          // [27]
+  int *out_idx;            // [27][out_cap]
+  unsigned char *gone;     // per particle flag
+  int out_cap;
+};
+
+struct SpeciesDev {
+  epb_species cfg;
+  long long n = 0;         // attached_list%count
+  long long n_sorted = 0;  // [0,n_sorted) follows tile_start
+  long long cap = 0;
+  double *buf[2][7] = {{0}};  // double buffer for the out-of-place sort: x,y,z,px,py,pz,w
+  int cur = 0;
+  int *key = nullptr;
+  int *tile_start = nullptr;
+  unsigned char *gone = nullptr;
+};
+
+struct epb_handle {
+  epb_config cfg;
+  std::vector<SpeciesDev> sp;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sz[3] = {1, 1, 1};
+  size_t fsize = 0;             // elements per field array
+  double *fields = nullptr;     // 9 * fsize
+  size_t plane = 0;             // (ny+2ng)*(nz+2ng)
+  double *snap = nullptr;       // [2 sides][6 fields][plane]
+  double *src = nullptr;        // [2 sides][2][plane]
+  TileGeom tg;
+  int *cell_count = nullptr;    // nkeys + 1
+  int *cell_start = nullptr;    // nkeys + 1
+  void *cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  int *out_count = nullptr;     // device [27]
+  int *out_idx = nullptr;       // device [27][out_cap]
+  int out_cap = 0;
+  int *h_counts = nullptr;      // pinned [64]
+  int *d_scratch = nullptr;     // device ints
+  double *sendbuf = nullptr, *recvbuf = nullptr;  // halo + particle staging
+  size_t sendbuf_elems = 0, recvbuf_elems = 0;
+  void *nccl = nullptr;         // ncclComm_t
+  std::string err;
+  long long launches = 0;
+  int pushes_since_sort = 0;
+  // push-kernel timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  double push_ms_sum = 0.0;
+  long long push_ms_n = 0;
+  int time_push = 0;
+
+  double *f(int which) const { return fields + (size_t)which * fsize; }
+};
+
+// push_*.cu
+void epb_launch_push_strict(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches);
+void epb_launch_push_fast(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches);
+
+// sort.cu
+int epb_sort_species(epb_handle *h, int is);
+void epb_make_tiles(const epb_config &cfg, TileGeom &tg);
+
+// exchange.cu
+int epb_particle_exchange(epb_handle *h, int is);
+int epb_halo_exchange(epb_handle *h, int f0, int nf, bool add);
+int epb_comm_init(epb_handle *h, const void *id128);
+void epb_comm_destroy(epb_handle *h);
+
+int epb_fail(epb_handle *h, int code, const char *fmt, ...);
+#define EPB_CUDA(h, call)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return epb_fail((h), EPB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,  \
+                      cudaGetErrorString(e_));                                         \
+  } while (0)

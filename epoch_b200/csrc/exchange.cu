@@ -1,0 +1,375 @@
+// exchange.cu — ghost-cell halos, current-sum halos and particle migration.
+//
+// Replaces the MPI_SENDRECV sequences of boundary.F90:
+//   do_field_mpi_with_lengths (:222-315)  -> epb_halo_exchange(add=false)
+//   particle_periodic_bcs     (:634-751)  -> epb_halo_exchange(add=true)
+//   particle_bcs exchange     (:1436-1446) + partlist_sendrecv (partlist.F90:830-884)
+//                                         -> epb_particle_exchange
+// One rank per GPU.  A dimension with a single rank wraps onto itself with device
+// copies; otherwise strips are packed by a kernel, moved with grouped
+// ncclSend/ncclRecv over NVLink, and unpacked (copy or add) by a kernel, all on the
+// handle's stream.  The three components of E, B or J travel in one message.
+#include <nccl.h>
+
+#include "epb_internal.h"
+
+int epb_halo_local(epb_handle *h, int f0, int nf, bool add, int d, int pass);
+
+namespace {
+
+constexpr int NG = EPB_NG;
+
+struct PackOp {
+  double *f[3];
+  int nf, nd, sz[3];
+  int lo[3], ext[3];
+  double *buf;
+  int mode;  // 0 pack (array -> buf), 1 unpack copy, 2 unpack add
+};
+__device__ __forceinline__ size_t pofs(const int *sz, int nd, int i, int j, int k) {
+  size_t o = (size_t)(i + NG - 1);
+  if (nd >= 2) o += (size_t)sz[0] * (size_t)(j + NG - 1);
+  if (nd >= 3) o += (size_t)sz[0] * (size_t)sz[1] * (size_t)(k + NG - 1);
+  return o;
+}
+__global__ void __launch_bounds__(256) k_pack(const __grid_constant__ PackOp B) {
+  const size_t total = (size_t)B.ext[0] * B.ext[1] * B.ext[2];
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int a = (int)(t % B.ext[0]);
+    const int b = (int)((t / B.ext[0]) % B.ext[1]);
+    const int c_ = (int)(t / ((size_t)B.ext[0] * B.ext[1]));
+    const size_t o = pofs(B.sz, B.nd, B.lo[0] + a, B.lo[1] + b, B.lo[2] + c_);
+    for (int q = 0; q < B.nf; q++) {
+      double *p = B.buf + (size_t)q * total + t;
+      if (B.mode == 0) *p = B.f[q][o];
+      else if (B.mode == 1) B.f[q][o] = *p;
+      else B.f[q][o] = B.f[q][o] + *p;
+    }
+  }
+}
+
+inline int nblk(size_t total, int cap = 148 * 16) {
+  size_t b = (total + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+inline int nbr1(const epb_config &c, int d, int s) {
+  int o[3] = {0, 0, 0};
+  o[d] = s;
+  return c.neighbour[(o[2] + 1) * 9 + (o[1] + 1) * 3 + (o[0] + 1)];
+}
+int bc_allspecies(const epb_handle *h, int i) {
+  if (h->sp.empty()) return h->cfg.bc_field[i] == EPB_BC_PERIODIC ? EPB_BC_PERIODIC : EPB_BC_OPEN;
+  int b = h->sp[0].cfg.bc_particle[i];
+  if (b != EPB_BC_REFLECT && b != EPB_BC_PERIODIC) b = EPB_BC_OPEN;
+  return b;
+}
+int ensure_buf(epb_handle *h, double **buf, size_t *have, size_t need) {
+  if (need <= *have) return EPB_OK;
+  if (*buf) { cudaStreamSynchronize(h->stream); cudaFree(*buf); *buf = nullptr; }
+  size_t n = need + need / 4 + 1024;
+  EPB_CUDA(h, cudaMalloc(buf, n * sizeof(double)));
+  *have = n;
+  return EPB_OK;
+}
+#define EPB_NCCL(h, call)                                                                         \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess)                                                                        \
+      return epb_fail((h), EPB_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+  } while (0)
+
+void run_pack(epb_handle *h, int f0, int nf, const int lo[3], const int ext[3], double *buf, int mode) {
+  PackOp B;
+  B.nf = nf;
+  B.nd = h->cfg.ndims;
+  for (int q = 0; q < nf; q++) B.f[q] = h->f(f0 + q);
+  for (int q = 0; q < 3; q++) { B.sz[q] = h->sz[q]; B.lo[q] = lo[q]; B.ext[q] = ext[q]; }
+  B.buf = buf;
+  B.mode = mode;
+  size_t total = (size_t)ext[0] * ext[1] * ext[2];
+  k_pack<<<nblk(total), 256, 0, h->stream>>>(B);
+  h->launches++;
+}
+
+// ---- particle migration kernels -------------------------------------------------
+struct PPackOp {
+  const double *src[7];
+  int nv, nd;
+  const int *idx;   // outbox list of one direction
+  int count;
+  double *buf;      // AoS, pack_particle order
+};
+__global__ void __launch_bounds__(256) k_ppack(const __grid_constant__ PPackOp O) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < O.count; t += gridDim.x * blockDim.x) {
+    const int i = O.idx[t];
+    double *o = O.buf + (size_t)t * O.nv;
+    int q = 0;
+    for (int d = 0; d < O.nd; d++) o[q++] = O.src[d][i];
+    for (int d = 3; d < 7; d++) o[q++] = O.src[d][i];
+  }
+}
+struct PUnpackOp {
+  double *dst[7];
+  int nv, nd;
+  long long first;
+  int count;
+  const double *buf;
+};
+__global__ void __launch_bounds__(256) k_punpack(const __grid_constant__ PUnpackOp O) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < O.count; t += gridDim.x * blockDim.x) {
+    const double *o = O.buf + (size_t)t * O.nv;
+    const long long i = O.first + t;
+    int q = 0;
+    for (int d = 0; d < O.nd; d++) O.dst[d][i] = o[q++];
+    for (int d = 3; d < 7; d++) O.dst[d][i] = o[q++];
+  }
+}
+// survivors in the tail [n_new, n_old) that must move into holes below n_new
+__global__ void __launch_bounds__(256) k_tail_movers(const unsigned char *gone, long long n_new, long long n_old,
+                                                     int *movers, int *counter) {
+  for (long long j = n_new + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_old; j += (long long)gridDim.x * blockDim.x)
+    if (!gone[j]) movers[atomicAdd(counter, 1)] = (int)j;
+}
+struct FillOp {
+  double *a[7];
+  unsigned char *gone;
+  const int *idx;   // outbox list of one direction
+  int count;
+  long long n_new;
+  const int *movers;
+  int *cursor;
+};
+__global__ void __launch_bounds__(256) k_fill_holes(const __grid_constant__ FillOp F) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < F.count; t += gridDim.x * blockDim.x) {
+    const int hole = F.idx[t];
+    F.gone[hole] = 0;
+    if (hole < F.n_new) {
+      const int src = F.movers[atomicAdd(F.cursor, 1)];
+#pragma unroll
+      for (int q = 0; q < 7; q++)
+        if (F.a[q]) F.a[q][hole] = F.a[q][src];
+    }
+  }
+}
+
+}  // namespace
+
+int epb_comm_init(epb_handle *h, const void *id128) {
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t comm;
+  EPB_NCCL(h, ncclCommInitRank(&comm, h->cfg.nranks, id, h->cfg.rank));
+  h->nccl = comm;
+  return EPB_OK;
+}
+void epb_comm_destroy(epb_handle *h) {
+  if (h->nccl) { ncclCommDestroy((ncclComm_t)h->nccl); h->nccl = nullptr; }
+}
+
+extern "C" int epb_nccl_unique_id(void *id128) {
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return EPB_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id128, &id, sizeof id);
+  return EPB_OK;
+}
+extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
+  if (!h || !id128) return EPB_ERR_ARG;
+  if (h->cfg.nranks <= 1) return EPB_OK;
+  return epb_comm_init(h, id128);
+}
+
+extern "C" int epb_global_count(epb_handle *h, int is, int64_t *n) {
+  if (!h || is < 0 || is >= (int)h->sp.size() || !n) return EPB_ERR_ARG;
+  long long local = h->sp[is].n;
+  if (h->cfg.nranks <= 1 || !h->nccl) { *n = local; return EPB_OK; }
+  long long *d = (long long *)h->d_scratch;
+  EPB_CUDA(h, cudaMemcpyAsync(d, &local, sizeof local, cudaMemcpyHostToDevice, h->stream));
+  EPB_NCCL(h, ncclAllReduce(d, d + 1, 1, ncclInt64, ncclSum, (ncclComm_t)h->nccl, h->stream));
+  long long out = 0;
+  EPB_CUDA(h, cudaMemcpyAsync(&out, d + 1, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n = out;
+  return EPB_OK;
+}
+
+int epb_halo_exchange(epb_handle *h, int f0, int nf, bool add) {
+  const epb_config &c = h->cfg;
+  for (int d = 0; d < c.ndims; d++) {
+    const int nm = nbr1(c, d, -1), np = nbr1(c, d, +1);
+    bool lo_ok, hi_ok;  // do we take part in an exchange across our low / high face
+    if (!add) {
+      lo_ok = (!c.is_boundary[2 * d] || c.bc_field[2 * d] == EPB_BC_PERIODIC) && nm >= 0;
+      hi_ok = (!c.is_boundary[2 * d + 1] || c.bc_field[2 * d + 1] == EPB_BC_PERIODIC) && np >= 0;
+    } else {
+      lo_ok = !(c.is_boundary[2 * d] && bc_allspecies(h, 2 * d) != EPB_BC_PERIODIC) && nm >= 0;
+      hi_ok = !(c.is_boundary[2 * d + 1] && bc_allspecies(h, 2 * d + 1) != EPB_BC_PERIODIC) && np >= 0;
+    }
+    const bool self = (nm == c.rank || nm < 0) && (np == c.rank || np < 0);
+    if (self) {
+      // copy: pass 0 fills the high ghosts (received from proc_max), pass 1 the low ghosts
+      // add : pass 0 adds into the low interior (received from neighbour -1), pass 1 the high interior
+      if (!add) {
+        if (hi_ok) epb_halo_local(h, f0, nf, false, d, 0);
+        if (lo_ok) epb_halo_local(h, f0, nf, false, d, 1);
+      } else {
+        if (lo_ok) epb_halo_local(h, f0, nf, true, d, 0);
+        if (hi_ok) epb_halo_local(h, f0, nf, true, d, 1);
+      }
+      continue;
+    }
+    if (!h->nccl) return epb_fail(h, EPB_ERR_NCCL, "rank has remote neighbours but epb_set_comm was not called");
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    int lo[3], ext[3];
+    for (int q = 0; q < 3; q++) { lo[q] = q < c.ndims ? 1 - NG : 1; ext[q] = h->sz[q]; }
+    ext[d] = NG;
+    const size_t strip = (size_t)ext[0] * ext[1] * ext[2] * nf;
+    int rc = ensure_buf(h, &h->sendbuf, &h->sendbuf_elems, 2 * strip);
+    if (rc) return rc;
+    rc = ensure_buf(h, &h->recvbuf, &h->recvbuf_elems, 2 * strip);
+    if (rc) return rc;
+    double *sA = h->sendbuf, *sB = h->sendbuf + strip;   // A goes to nm, B goes to np
+    double *rA = h->recvbuf, *rB = h->recvbuf + strip;   // rA comes from np, rB comes from nm
+    const int n = c.n[d];
+    int l2[3] = {lo[0], lo[1], lo[2]};
+    if (lo_ok) { l2[d] = add ? 1 - NG : 1; run_pack(h, f0, nf, l2, ext, sA, 0); }
+    if (hi_ok) { l2[d] = add ? n + 1 : n + 1 - NG; run_pack(h, f0, nf, l2, ext, sB, 0); }
+    EPB_NCCL(h, ncclGroupStart());
+    if (lo_ok) EPB_NCCL(h, ncclSend(sA, strip, ncclDouble, nm, comm, h->stream));
+    if (hi_ok) EPB_NCCL(h, ncclSend(sB, strip, ncclDouble, np, comm, h->stream));
+    if (hi_ok) EPB_NCCL(h, ncclRecv(rA, strip, ncclDouble, np, comm, h->stream));
+    if (lo_ok) EPB_NCCL(h, ncclRecv(rB, strip, ncclDouble, nm, comm, h->stream));
+    EPB_NCCL(h, ncclGroupEnd());
+    h->launches++;
+    if (!add) {
+      if (hi_ok) { l2[d] = n + 1; run_pack(h, f0, nf, l2, ext, rA, 1); }
+      if (lo_ok) { l2[d] = 1 - NG; run_pack(h, f0, nf, l2, ext, rB, 1); }
+    } else {
+      // np's low ghosts add into our high interior; nm's high ghosts add into our low interior
+      if (lo_ok) { l2[d] = 1; run_pack(h, f0, nf, l2, ext, rB, 2); }
+      if (hi_ok) { l2[d] = n + 1 - NG; run_pack(h, f0, nf, l2, ext, rA, 2); }
+    }
+  }
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
+// particle_bcs tail: remove leavers, exchange with up to 26 neighbours, append arrivals
+int epb_particle_exchange(epb_handle *h, int is) {
+  const epb_config &c = h->cfg;
+  SpeciesDev &S = h->sp[is];
+  if (h->out_cap == 0 || S.cfg.immobile) return EPB_OK;
+  const int nd = c.ndims, nv = nd + 4;
+  int *cnt = h->h_counts;
+  EPB_CUDA(h, cudaMemcpyAsync(cnt, h->out_count, 27 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long gone_total = 0;
+  for (int q = 0; q < 27; q++) {
+    if (cnt[q] > h->out_cap)
+      return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %d particles leave in direction %d > outbox capacity %d", is, cnt[q], q, h->out_cap);
+    gone_total += cnt[q];
+  }
+  const bool remote = c.nranks > 1 && h->nccl;
+  int sendc[27], recvc[27];
+  size_t send_off[27], recv_off[27];
+  size_t send_tot = 0, recv_tot = 0;
+  for (int q = 0; q < 27; q++) { sendc[q] = (q == 13) ? 0 : cnt[q]; recvc[q] = 0; }
+  if (remote) {
+    // count exchange (partlist.F90:850): for direction q we send to neighbour(q) and receive
+    // from neighbour(-q) what that rank sends in direction q
+    int *d_send = h->d_scratch + 64, *d_recv = h->d_scratch + 128;
+    EPB_CUDA(h, cudaMemcpyAsync(d_send, h->out_count, 27 * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    EPB_CUDA(h, cudaMemsetAsync(d_recv, 0, 27 * sizeof(int), h->stream));
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    EPB_NCCL(h, ncclGroupStart());
+    for (int q = 0; q < 27; q++) {
+      if (q == 13) continue;
+      const int to = c.neighbour[q], from = c.neighbour[26 - q];
+      if (to >= 0 && to != c.rank) EPB_NCCL(h, ncclSend(d_send + q, 1, ncclInt32, to, comm, h->stream));
+      if (from >= 0 && from != c.rank) EPB_NCCL(h, ncclRecv(d_recv + q, 1, ncclInt32, from, comm, h->stream));
+    }
+    EPB_NCCL(h, ncclGroupEnd());
+    h->launches++;
+    EPB_CUDA(h, cudaMemcpyAsync(recvc, d_recv, 27 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  for (int q = 0; q < 27; q++) {
+    send_off[q] = send_tot; send_tot += (size_t)sendc[q] * nv;
+    recv_off[q] = recv_tot; recv_tot += (size_t)recvc[q] * nv;
+  }
+  const long long n_recv = (long long)(recv_tot / nv);
+  if (gone_total == 0 && n_recv == 0) return EPB_OK;
+  if (S.n - gone_total + n_recv > S.cap)
+    return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %lld particles after migration > capacity %lld", is, S.n - gone_total + n_recv, S.cap);
+  double *const *arr = S.buf[S.cur];
+  if (remote && (send_tot || recv_tot)) {
+    int rc = ensure_buf(h, &h->sendbuf, &h->sendbuf_elems, send_tot);
+    if (rc) return rc;
+    rc = ensure_buf(h, &h->recvbuf, &h->recvbuf_elems, recv_tot);
+    if (rc) return rc;
+    for (int q = 0; q < 27; q++) {
+      if (!sendc[q]) continue;
+      PPackOp O;
+      for (int k = 0; k < 7; k++) O.src[k] = arr[k];
+      O.nv = nv; O.nd = nd;
+      O.idx = h->out_idx + (size_t)q * h->out_cap;
+      O.count = sendc[q];
+      O.buf = h->sendbuf + send_off[q];
+      k_ppack<<<nblk((size_t)sendc[q]), 256, 0, h->stream>>>(O);
+      h->launches++;
+    }
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    EPB_NCCL(h, ncclGroupStart());
+    for (int q = 0; q < 27; q++) {
+      if (q == 13) continue;
+      const int to = c.neighbour[q], from = c.neighbour[26 - q];
+      if (sendc[q] && to >= 0 && to != c.rank)
+        EPB_NCCL(h, ncclSend(h->sendbuf + send_off[q], (size_t)sendc[q] * nv, ncclDouble, to, comm, h->stream));
+      if (recvc[q] && from >= 0 && from != c.rank)
+        EPB_NCCL(h, ncclRecv(h->recvbuf + recv_off[q], (size_t)recvc[q] * nv, ncclDouble, from, comm, h->stream));
+    }
+    EPB_NCCL(h, ncclGroupEnd());
+    h->launches++;
+  }
+  // compaction: holes below n_new are filled with the survivors of the tail [n_new, n_old)
+  if (gone_total > 0) {
+    const long long n_old = S.n, n_new = S.n - gone_total;
+    int *ctr = h->d_scratch;  // [0] mover count, [1] fill cursor
+    EPB_CUDA(h, cudaMemsetAsync(ctr, 0, 2 * sizeof(int), h->stream));
+    k_tail_movers<<<nblk((size_t)gone_total), 256, 0, h->stream>>>(S.gone, n_new, n_old, S.key, ctr);
+    h->launches++;
+    for (int q = 0; q < 27; q++) {
+      if (!cnt[q]) continue;
+      FillOp F;
+      for (int k = 0; k < 7; k++) F.a[k] = arr[k];
+      F.gone = S.gone;
+      F.idx = h->out_idx + (size_t)q * h->out_cap;
+      F.count = cnt[q];
+      F.n_new = n_new;
+      F.movers = S.key;
+      F.cursor = ctr + 1;
+      k_fill_holes<<<nblk((size_t)cnt[q]), 256, 0, h->stream>>>(F);
+      h->launches++;
+    }
+    S.n = n_new;
+    if (S.n_sorted > S.n) S.n_sorted = S.n;
+  }
+  // append arrivals in the reference's direction order (boundary.F90:1436-1446)
+  for (int q = 0; q < 27; q++) {
+    if (!recvc[q]) continue;
+    PUnpackOp O;
+    for (int k = 0; k < 7; k++) O.dst[k] = arr[k];
+    O.nv = nv; O.nd = nd;
+    O.first = S.n;
+    O.count = recvc[q];
+    O.buf = h->recvbuf + recv_off[q];
+    k_punpack<<<nblk((size_t)recvc[q]), 256, 0, h->stream>>>(O);
+    h->launches++;
+    S.n += recvc[q];
+  }
+  EPB_CUDA(h, cudaMemsetAsync(h->out_count, 0, 27 * sizeof(int), h->stream));
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}

@@ -1,0 +1,715 @@
+// push.cuh — Boris push + triangle-shape gather + Esirkepov deposit + particle BC
+// classification, for sm_100a.  Included twice: push_strict.cu (compiled with
+// -fmad=false: operation-for-operation the arithmetic of particles.F90, which the
+// reference builds without FMA contraction, epoch2d/Makefile:72) and push_fast.cu
+// (FMA contraction allowed; differs from the former at the 1e-16 level).
+//
+// Reference: epoch{1,2,3}d/src/particles.F90:28-650 and
+// src/include/triangle/{gx,hx_dcell,e_part,b_part}.inc; boundary classification
+// follows boundary.F90:1064-1433 (no thermal / CPML).
+//
+// Two kernels:
+//  * push_generic<ND>: any particle range; gathers E/B through the read-only path
+//    and deposits with native global FP64 reductions (RED.E.ADD.F64).  Used for 1D
+//    and 3D, for the unsorted tail (arrivals since the last sort) and as the
+//    per-particle fallback of the tiled kernel.
+//  * push_tiled_2d: one CTA per 16x16-cell tile of the cell-sorted layout.  The
+//    E/B tile (+3 halo cells) is staged in shared memory, J is accumulated in a
+//    shared tile and flushed once with global reductions.  Because the particle
+//    range is cell-ordered, the 32 lanes of a warp mostly sit in one or two cells:
+//    their 3x3x3 deposit values are summed across the warp with a transposing
+//    butterfly (31 shuffles) and only 27 lanes issue one shared-memory update
+//    each, instead of 27 CAS loops per particle (shared FP64 atomicAdd is an
+//    ATOMS.CAST.SPIN loop on sm_100a).
+#pragma once
+#include "epb_internal.h"
+
+namespace EPB_NS {
+
+constexpr int NG = EPB_NG;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void tri(double f, double &gm, double &g0, double &gp) {
+  // include/triangle/gx.inc:1-4
+  double cf2 = f * f;
+  gm = 0.25 + cf2 + f;
+  g0 = 1.5 - 2.0 * cf2;
+  gp = 0.25 + cf2 - f;
+}
+
+// boundary.F90:1064-1433 for one particle.  Returns -1 if the particle stays on
+// this rank, else the outbox slot: direction index (iz+1)*9+(iy+1)*3+(ix+1), or 13
+// for a particle that left the system (open boundary, beyond x_min_outer).
+template <int ND>
+__device__ __forceinline__ int particle_bc(const PushParams &P, double *pos, double *mom) {
+  bool cand = false;
+#pragma unroll
+  for (int d = 0; d < ND; d++) cand = cand || (pos[d] < P.bnd_min[d]) || (pos[d] > P.bnd_max[d]);
+  if (!cand) return -1;
+  int bd[3] = {0, 0, 0};
+  bool oob = false;
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    const double part_pos = pos[d];
+    if (part_pos < P.min_local[d]) {
+      bd[d] = -1;
+      const int bc = P.bc_min[d];
+      if (bc == EPB_BC_REFLECT) {
+        if (P.is_bnd_min[d]) {
+          bd[d] = 0;
+          pos[d] = 2.0 * P.gmin[d] - part_pos;
+          mom[d] = -mom[d];
+        }
+      } else if (bc == EPB_BC_PERIODIC) {
+        if (P.is_bnd_min[d]) pos[d] = part_pos + P.shift[d];
+      } else {
+        if (part_pos < P.min_outer[d]) { bd[d] = 0; oob = true; }
+        else if (P.is_bnd_min[d]) bd[d] = 0;
+      }
+    }
+    if (part_pos >= P.max_local[d]) {
+      bd[d] = 1;
+      const int bc = P.bc_max[d];
+      if (bc == EPB_BC_REFLECT) {
+        if (P.is_bnd_max[d]) {
+          bd[d] = 0;
+          pos[d] = 2.0 * P.gmax[d] - part_pos;
+          mom[d] = -mom[d];
+        }
+      } else if (bc == EPB_BC_PERIODIC) {
+        if (P.is_bnd_max[d]) pos[d] = part_pos - P.shift[d];
+      } else {
+        if (part_pos >= P.max_outer[d]) { bd[d] = 0; oob = true; }
+        else if (P.is_bnd_max[d]) bd[d] = 0;
+      }
+    }
+  }
+  if (oob) return 13;
+  const int dir = (bd[2] + 1) * 9 + (bd[1] + 1) * 3 + (bd[0] + 1);
+  if (dir == 13) return -1;
+  if (P.nbr_is_self[dir]) return -1;  // periodic wrap onto this rank: already shifted
+  return dir;
+}
+
+__device__ __forceinline__ void outbox_put(const PushParams &P, long long i, int dir) {
+  int slot = atomicAdd(&P.out_count[dir], 1);
+  if (slot < P.out_cap) P.out_idx[(size_t)dir * P.out_cap + slot] = (int)i;
+  P.gone[i] = 1;
+}
+
+template <int ND>
+__device__ __forceinline__ size_t gofs(const PushParams &P, int cx, int cy, int cz) {
+  size_t o = (size_t)(cx + NG - 1);
+  if (ND >= 2) o += (size_t)P.sz[0] * (size_t)(cy + NG - 1);
+  if (ND >= 3) o += (size_t)P.sz[0] * (size_t)P.sz[1] * (size_t)(cz + NG - 1);
+  return o;
+}
+
+// include/triangle/e_part.inc: rows parenthesised, sums left to right
+template <int ND>
+__device__ __forceinline__ double gather_g(const PushParams &P, const double *__restrict__ F,
+                                           const double *wx, int cx, const double *wy, int cy,
+                                           const double *wz, int cz) {
+  if (ND == 1) {
+    size_t o = gofs<1>(P, cx, 1, 1);
+    return wx[0] * __ldg(F + o - 1) + wx[1] * __ldg(F + o) + wx[2] * __ldg(F + o + 1);
+  } else if (ND == 2) {
+    double r = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++) {
+      size_t o = gofs<2>(P, cx, cy + iy - 1, 1);
+      double row = wx[0] * __ldg(F + o - 1) + wx[1] * __ldg(F + o) + wx[2] * __ldg(F + o + 1);
+      double t = wy[iy] * row;
+      r = (iy == 0) ? t : r + t;
+    }
+    return r;
+  } else {
+    double r = 0.0;
+#pragma unroll
+    for (int iz = 0; iz < 3; iz++) {
+      double pl = 0.0;
+#pragma unroll
+      for (int iy = 0; iy < 3; iy++) {
+        size_t o = gofs<3>(P, cx, cy + iy - 1, cz + iz - 1);
+        double row = wx[0] * __ldg(F + o - 1) + wx[1] * __ldg(F + o) + wx[2] * __ldg(F + o + 1);
+        double t = wy[iy] * row;
+        pl = (iy == 0) ? t : pl + t;
+      }
+      double t = wz[iz] * pl;
+      r = (iz == 0) ? t : r + t;
+    }
+    return r;
+  }
+}
+
+// One particle, everything through global memory.  Mirrors the oracle routine
+// push_particles<ND> line by line.
+template <int ND>
+__device__ __noinline__ void push_one(const PushParams &P, long long i) {
+  const double c = EPB_C;
+  const double part_weight = P.w[i];
+  const double fcx = P.kfc[0] * part_weight;
+  const double fcy = P.kfc[1] * part_weight;
+  const double fcz = P.kfc[2] * part_weight;
+  double part_pos[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < ND; d++) part_pos[d] = P.x[d][i] - P.grid_min_local[d];
+  double part_ux = P.p[0][i] * P.ipart_mc;
+  double part_uy = P.p[1][i] * P.ipart_mc;
+  double part_uz = P.p[2][i] * P.ipart_mc;
+  double gamma_rel = sqrt(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0);
+  double root = P.dtco2 / gamma_rel;
+  {
+    const double u[3] = {part_ux, part_uy, part_uz};
+#pragma unroll
+    for (int d = 0; d < ND; d++) part_pos[d] = part_pos[d] + u[d] * root;
+  }
+  double G[3][5], H[3][5];
+  int cell1[3] = {1, 1, 1}, cell2[3] = {1, 1, 1};
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int q = 0; q < 5; q++) { G[d][q] = 0.0; H[d][q] = 0.0; }
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    double cell_r = part_pos[d] * P.idx[d];
+    int c1 = __double2int_rd(cell_r + 0.5);
+    double cell_frac = (double)c1 - cell_r;
+    cell1[d] = c1 + 1;
+    tri(cell_frac, G[d][1], G[d][2], G[d][3]);
+    int c2 = __double2int_rd(cell_r);
+    cell_frac = (double)c2 - cell_r + 0.5;
+    cell2[d] = c2 + 1;
+    tri(cell_frac, H[d][1], H[d][2], H[d][3]);
+  }
+  const double *gx = &G[0][1], *gy = &G[1][1], *gz = &G[2][1];
+  const double *hx = &H[0][1], *hy = &H[1][1], *hz = &H[2][1];
+  const double ex_part = gather_g<ND>(P, P.e[0], hx, cell2[0], gy, cell1[1], gz, cell1[2]);
+  const double ey_part = gather_g<ND>(P, P.e[1], gx, cell1[0], hy, cell2[1], gz, cell1[2]);
+  const double ez_part = gather_g<ND>(P, P.e[2], gx, cell1[0], gy, cell1[1], hz, cell2[2]);
+  const double bx_part = gather_g<ND>(P, P.b[0], gx, cell1[0], hy, cell2[1], hz, cell2[2]);
+  const double by_part = gather_g<ND>(P, P.b[1], hx, cell2[0], gy, cell1[1], hz, cell2[2]);
+  const double bz_part = gather_g<ND>(P, P.b[2], hx, cell2[0], hy, cell2[1], gz, cell1[2]);
+  // particles.F90:382-428
+  const double cmratio = P.cmratio;
+  double uxm = part_ux + cmratio * ex_part;
+  double uym = part_uy + cmratio * ey_part;
+  double uzm = part_uz + cmratio * ez_part;
+  gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+  root = P.ccmratio / gamma_rel;
+  double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+  double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+  double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+  double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+  double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+  double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+  part_ux = uxp + cmratio * ex_part;
+  part_uy = uyp + cmratio * ey_part;
+  part_uz = uzp + cmratio * ez_part;
+  double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+  gamma_rel = sqrt(part_u2 + 1.0);
+  double delta[3] = {0, 0, 0}, part_vy = 0.0, part_vz = 0.0;
+  if (ND == 1) {  // epoch1d particles.F90:392-396
+    root = c / gamma_rel;
+    delta[0] = part_ux * root * P.dto2;
+    part_vy = part_uy * root;
+    part_vz = part_uz * root;
+  } else if (ND == 2) {  // epoch2d particles.F90:433-438
+    double igamma = 1.0 / gamma_rel;
+    root = P.dtco2 * igamma;
+    delta[0] = part_ux * root;
+    delta[1] = part_uy * root;
+    part_vz = part_uz * c * igamma;
+  } else {  // epoch3d particles.F90:470-474
+    root = P.dtco2 / gamma_rel;
+    delta[0] = part_ux * root;
+    delta[1] = part_uy * root;
+    delta[2] = part_uz * root;
+  }
+#pragma unroll
+  for (int d = 0; d < ND; d++) part_pos[d] = part_pos[d] + delta[d];
+  {
+    double pos[3] = {0, 0, 0}, mom[3];
+#pragma unroll
+    for (int d = 0; d < ND; d++) pos[d] = part_pos[d] + P.grid_min_local[d];
+    mom[0] = P.part_mc * part_ux;
+    mom[1] = P.part_mc * part_uy;
+    mom[2] = P.part_mc * part_uz;
+    int dir = particle_bc<ND>(P, pos, mom);
+#pragma unroll
+    for (int d = 0; d < ND; d++) P.x[d][i] = pos[d];
+#pragma unroll
+    for (int d = 0; d < 3; d++) P.p[d][i] = mom[d];
+    if (dir >= 0) outbox_put(P, i, dir);
+  }
+  if (!P.deposit) return;
+  int dcell[3] = {0, 0, 0}, mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    part_pos[d] = part_pos[d] + delta[d];
+    double cell_r = part_pos[d] * P.idx[d];
+    int c3 = __double2int_rd(cell_r + 0.5);
+    double cell_frac = (double)c3 - cell_r;
+    c3 = c3 + 1;
+    dcell[d] = c3 - cell1[d];
+    double wm, w0, wp;
+    tri(cell_frac, wm, w0, wp);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      // hx = 0; hx(dcell-1:dcell+1) = weights; hx = hx - gx   (particles.F90:521-538)
+      int r = q - 2 - dcell[d];
+      double hv = (r == -1) ? wm : (r == 0) ? w0 : (r == 1) ? wp : 0.0;
+      H[d][q] = hv - G[d][q];
+    }
+    mn[d] = -1 + (dcell[d] - 1) / 2;
+    mx[d] = 1 + (dcell[d] + 1) / 2;
+  }
+  gx = &G[0][2]; gy = &G[1][2]; gz = &G[2][2];
+  hx = &H[0][2]; hy = &H[1][2]; hz = &H[2][2];
+  const double third = P.third;
+  if (ND == 1) {  // epoch1d particles.F90:489-507
+    const double fjx = fcx * P.part_q;
+    const double fjy = fcy * P.part_q * part_vy;
+    const double fjz = fcy * P.part_q * part_vz;
+    double jxh = 0.0;
+    for (int ix = mn[0]; ix <= mx[0]; ix++) {
+      size_t o = gofs<1>(P, cell1[0] + ix, 1, 1);
+      double wx = hx[ix];
+      double wy = gx[ix] + 0.5 * hx[ix];
+      jxh = jxh - fjx * wx;
+      atomicAdd(P.j[0] + o, jxh);
+      atomicAdd(P.j[1] + o, fjy * wy);
+      atomicAdd(P.j[2] + o, fjz * wy);
+    }
+  } else if (ND == 2) {  // epoch2d particles.F90:549-579
+    const double fjx = fcx * P.part_q;
+    const double fjy = fcy * P.part_q;
+    const double fjz = fcz * P.part_q * part_vz;
+    double jyh[5] = {0, 0, 0, 0, 0};
+    for (int iy = mn[1]; iy <= mx[1]; iy++) {
+      double yfac1 = gy[iy] + 0.5 * hy[iy];
+      double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+      double hy_iy = hy[iy];
+      double jxh = 0.0;
+      for (int ix = mn[0]; ix <= mx[0]; ix++) {
+        size_t o = gofs<2>(P, cell1[0] + ix, cell1[1] + iy, 1);
+        double xfac1 = gx[ix] + 0.5 * hx[ix];
+        double wx = hx[ix] * yfac1;
+        double wy = hy_iy * xfac1;
+        double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
+        jxh = jxh - fjx * wx;
+        jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+        double jzh = fjz * wz;
+        atomicAdd(P.j[0] + o, jxh);
+        atomicAdd(P.j[1] + o, jyh[ix + 2]);
+        atomicAdd(P.j[2] + o, jzh);
+      }
+    }
+  } else {  // epoch3d particles.F90:603-648
+    const double fjx = fcx * P.part_q;
+    const double fjy = fcy * P.part_q;
+    const double fjz = fcz * P.part_q;
+    double jzh[5][5];
+    for (int a = 0; a < 5; a++)
+      for (int b = 0; b < 5; b++) jzh[a][b] = 0.0;
+    for (int iz = mn[2]; iz <= mx[2]; iz++) {
+      double zfac1 = gz[iz] + 0.5 * hz[iz];
+      double zfac2 = third * hz[iz] + 0.5 * gz[iz];
+      double gz_iz = gz[iz], hz_iz = hz[iz];
+      double jyh[5] = {0, 0, 0, 0, 0};
+      for (int iy = mn[1]; iy <= mx[1]; iy++) {
+        double yfac1 = gy[iy] + 0.5 * hy[iy];
+        double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+        double hygz = hy[iy] * gz_iz;
+        double hyhz = hy[iy] * hz_iz;
+        double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
+        double hzyfac1 = hz_iz * yfac1;
+        double hzyfac2 = hz_iz * yfac2;
+        double jxh = 0.0;
+        for (int ix = mn[0]; ix <= mx[0]; ix++) {
+          size_t o = gofs<3>(P, cell1[0] + ix, cell1[1] + iy, cell1[2] + iz);
+          double xfac1 = gx[ix] + 0.5 * hx[ix];
+          double xfac2 = third * hx[ix] + 0.5 * gx[ix];
+          double wx = hx[ix] * yzfac;
+          double wy = xfac1 * hygz + xfac2 * hyhz;
+          double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
+          jxh = jxh - fjx * wx;
+          jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+          jzh[iy + 2][ix + 2] = jzh[iy + 2][ix + 2] - fjz * wz;
+          atomicAdd(P.j[0] + o, jxh);
+          atomicAdd(P.j[1] + o, jyh[ix + 2]);
+          atomicAdd(P.j[2] + o, jzh[iy + 2][ix + 2]);
+        }
+      }
+    }
+  }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) push_generic(const __grid_constant__ PushParams P) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = P.first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.last; i += stride)
+    push_one<ND>(P, i);
+}
+
+// ---------------------------------------------------------------------------
+// Tiled 2D kernel
+// ---------------------------------------------------------------------------
+constexpr int T2X = 16, T2Y = 16, HALO = 3;
+constexpr int TW = T2X + 2 * HALO, TH = T2Y + 2 * HALO;
+constexpr int TILE_ELEMS = TW * TH;
+constexpr int PUSH2D_THREADS = 256;
+constexpr size_t PUSH2D_SMEM = (size_t)9 * TILE_ELEMS * sizeof(double);
+
+__device__ __forceinline__ void smem_add(double *addr, double v) {
+  // shared FP64 add: compiles to an ATOMS.CAST.SPIN loop; conflicts between warps are rare
+  atomicAdd(addr, v);
+}
+
+// sum v[0..26] of the lanes in `grp` (others pass zeros); lane L returns the total of v[L]
+__device__ __forceinline__ double warp_transpose_reduce27(double (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int q = 0; q < s; q++) {
+      double a = v[q], b = v[q + s];
+      double send = up ? a : b;
+      double keep = up ? b : a;
+      v[q] = keep + __shfl_xor_sync(FULL, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <bool REDUCE>
+__global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_constant__ PushParams P) {
+  extern __shared__ double sm[];
+  double *sF = sm;                     // [6][TH][TW]
+  double *sJ = sm + 6 * TILE_ELEMS;    // [3][TH][TW]
+  const int tile = blockIdx.x;
+  const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
+  const int ox = ttx * T2X + 1 - HALO;  // cell index of shared column 0
+  const int oy = tty * T2Y + 1 - HALO;
+  const long long start = P.tile_start[tile];
+  long long end = P.tile_start[tile + 1];
+  if (end > P.n_sorted_clip) end = P.n_sorted_clip;
+  if (start >= end) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
+    const int lx = q % TW, ly = q / TW;
+    const int cx = ox + lx, cy = oy + ly;
+    const bool ok = (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
+    const size_t o = ok ? gofs<2>(P, cx, cy, 1) : 0;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      sF[f * TILE_ELEMS + q] = ok ? __ldg(P.e[f] + o) : 0.0;
+      sF[(3 + f) * TILE_ELEMS + q] = ok ? __ldg(P.b[f] + o) : 0.0;
+      sJ[f * TILE_ELEMS + q] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  const double c = EPB_C;
+  const double third = P.third;
+  const double *sEx = sF, *sEy = sF + TILE_ELEMS, *sEz = sF + 2 * TILE_ELEMS;
+  const double *sBx = sF + 3 * TILE_ELEMS, *sBy = sF + 4 * TILE_ELEMS, *sBz = sF + 5 * TILE_ELEMS;
+
+  for (long long base = start; base < end; base += PUSH2D_THREADS) {
+    const long long i = base + tid;
+    const bool active = i < end;
+    bool fast = false;
+    int cx1 = 0, cy1 = 0;
+    double part_weight = 0.0;
+    double px_ = 0, py_ = 0, part_ux = 0, part_uy = 0, part_uz = 0;
+    if (active) {
+      part_weight = P.w[i];
+      px_ = P.x[0][i] - P.grid_min_local[0];
+      py_ = P.x[1][i] - P.grid_min_local[1];
+      part_ux = P.p[0][i] * P.ipart_mc;
+      part_uy = P.p[1][i] * P.ipart_mc;
+      part_uz = P.p[2][i] * P.ipart_mc;
+    }
+    double cell_x_r = 0, cell_y_r = 0;
+    if (active) {
+      double gamma_rel = sqrt(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0);
+      double root = P.dtco2 / gamma_rel;
+      px_ = px_ + part_ux * root;
+      py_ = py_ + part_uy * root;
+      cell_x_r = px_ * P.idx[0];
+      cell_y_r = py_ * P.idx[1];
+      cx1 = __double2int_rd(cell_x_r + 0.5) + 1;
+      cy1 = __double2int_rd(cell_y_r + 0.5) + 1;
+      // the gather reads cell1-2..cell1+1, the deposit writes cell1-2..cell1+2
+      fast = (cx1 - 2 >= ox) && (cx1 + 2 <= ox + TW - 1) && (cy1 - 2 >= oy) && (cy1 + 2 <= oy + TH - 1);
+      if (!fast) push_one<2>(P, i);
+    }
+    double v[32];
+#pragma unroll
+    for (int q = 0; q < 32; q++) v[q] = 0.0;
+    int dcx = 0, dcy = 0;
+    // values the rare extra-row/column path needs
+    double fjx = 0, fjy = 0, fjz = 0, hxm2 = 0, hxp2 = 0, hym2 = 0, hyp2 = 0;
+    double gxa[3] = {0, 0, 0}, gya[3] = {0, 0, 0}, hxa[3] = {0, 0, 0}, hya[3] = {0, 0, 0};
+    if (fast) {
+      double gx[3], gy[3], hx[3], hy[3];
+      tri((double)(cx1 - 1) - cell_x_r, gx[0], gx[1], gx[2]);
+      tri((double)(cy1 - 1) - cell_y_r, gy[0], gy[1], gy[2]);
+      int cx2 = __double2int_rd(cell_x_r);
+      tri((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
+      cx2 += 1;
+      int cy2 = __double2int_rd(cell_y_r);
+      tri((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
+      cy2 += 1;
+      // shared-tile offsets of (cell-1, cell-1)
+      const int o11 = (cy1 - 1 - oy) * TW + (cx1 - 1 - ox);
+      const int o21 = (cy1 - 1 - oy) * TW + (cx2 - 1 - ox);
+      const int o12 = (cy2 - 1 - oy) * TW + (cx1 - 1 - ox);
+      const int o22 = (cy2 - 1 - oy) * TW + (cx2 - 1 - ox);
+      auto gat = [&](const double *F, int o, const double *wx, const double *wy) {
+        double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
+        double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
+        double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
+        return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
+      };
+      const double ex_part = gat(sEx, o21, hx, gy);
+      const double ey_part = gat(sEy, o12, gx, hy);
+      const double ez_part = gat(sEz, o11, gx, gy);
+      const double bx_part = gat(sBx, o12, gx, hy);
+      const double by_part = gat(sBy, o21, hx, gy);
+      const double bz_part = gat(sBz, o22, hx, hy);
+      const double cmratio = P.cmratio;
+      double uxm = part_ux + cmratio * ex_part;
+      double uym = part_uy + cmratio * ey_part;
+      double uzm = part_uz + cmratio * ez_part;
+      double gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+      double root = P.ccmratio / gamma_rel;
+      double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+      double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+      double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+      double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                    2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+      double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                    2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+      double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                    2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+      part_ux = uxp + cmratio * ex_part;
+      part_uy = uyp + cmratio * ey_part;
+      part_uz = uzp + cmratio * ez_part;
+      double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+      gamma_rel = sqrt(part_u2 + 1.0);
+      double igamma = 1.0 / gamma_rel;
+      root = P.dtco2 * igamma;
+      const double delta_x = part_ux * root;
+      const double delta_y = part_uy * root;
+      const double part_vz = part_uz * c * igamma;
+      px_ = px_ + delta_x;
+      py_ = py_ + delta_y;
+      {
+        double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
+        double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
+        int dir = particle_bc<2>(P, pos, mom);
+        P.x[0][i] = pos[0];
+        P.x[1][i] = pos[1];
+        P.p[0][i] = mom[0];
+        P.p[1][i] = mom[1];
+        P.p[2][i] = mom[2];
+        if (dir >= 0) outbox_put(P, i, dir);
+      }
+      if (P.deposit) {
+        px_ = px_ + delta_x;
+        py_ = py_ + delta_y;
+        const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
+        const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
+        double wxm, wx0, wxp, wym, wy0, wyp;
+        tri((double)cx3 - cxr, wxm, wx0, wxp);
+        tri((double)cy3 - cyr, wym, wy0, wyp);
+        dcx = cx3 + 1 - cx1;
+        dcy = cy3 + 1 - cy1;
+        // hx(-2..2) = shifted new weights - gx (particles.F90:521-538)
+        hxm2 = (dcx == -1) ? wxm : 0.0;
+        hxp2 = (dcx == 1) ? wxp : 0.0;
+        hx[0] = ((dcx == -1) ? wx0 : (dcx == 0) ? wxm : 0.0) - gx[0];
+        hx[1] = ((dcx == -1) ? wxp : (dcx == 0) ? wx0 : wxm) - gx[1];
+        hx[2] = ((dcx == 0) ? wxp : (dcx == 1) ? wx0 : 0.0) - gx[2];
+        hym2 = (dcy == -1) ? wym : 0.0;
+        hyp2 = (dcy == 1) ? wyp : 0.0;
+        hy[0] = ((dcy == -1) ? wy0 : (dcy == 0) ? wym : 0.0) - gy[0];
+        hy[1] = ((dcy == -1) ? wyp : (dcy == 0) ? wy0 : wym) - gy[1];
+        hy[2] = ((dcy == 0) ? wyp : (dcy == 1) ? wy0 : 0.0) - gy[2];
+        const double fcx = P.kfc[0] * part_weight;
+        const double fcy = P.kfc[1] * part_weight;
+        const double fcz = P.kfc[2] * part_weight;
+        fjx = fcx * P.part_q;
+        fjy = fcy * P.part_q;
+        fjz = fcz * P.part_q * part_vz;
+        double xfac1[3];
+#pragma unroll
+        for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
+        // row iy=-2 precedes the core rows in the running jyh(ix) sums (only when dcy=-1;
+        // otherwise hy(-2)=0 and this is 0 - 0)
+        double jyh[3];
+#pragma unroll
+        for (int ix = 0; ix < 3; ix++) jyh[ix] = 0.0 - fjy * (hym2 * xfac1[ix]);
+#pragma unroll
+        for (int iy = 0; iy < 3; iy++) {
+          const double yfac1 = gy[iy] + 0.5 * hy[iy];
+          const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+          // column ix=-2 precedes the core columns in the running jxh sum
+          double jxh = 0.0 - fjx * (hxm2 * yfac1);
+#pragma unroll
+          for (int ix = 0; ix < 3; ix++) {
+            const double wx = hx[ix] * yfac1;
+            const double wy = hy[iy] * xfac1[ix];
+            const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
+            jxh = jxh - fjx * wx;
+            jyh[ix] = jyh[ix] - fjy * wy;
+            v[iy * 3 + ix] = jxh;
+            v[9 + iy * 3 + ix] = jyh[ix];
+            v[18 + iy * 3 + ix] = fjz * wz;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) { gxa[q] = gx[q]; gya[q] = gy[q]; hxa[q] = hx[q]; hya[q] = hy[q]; }
+      }
+    }
+    if (!P.deposit) continue;
+    const bool dep = fast;
+    if (REDUCE) {
+      // cell-ordered lanes: sum per distinct cell across the warp, 27 lanes update shared J
+      const int key = dep ? ((cy1 - oy) * TW + (cx1 - ox)) : -1;
+      unsigned todo = __ballot_sync(FULL, key >= 0);
+      int iter = 0;
+      while (todo) {
+        if (iter == 3) {
+          // many distinct cells in this warp (stale sort): remaining lanes update individually
+          if (key >= 0 && ((todo >> lane) & 1u)) {
+#pragma unroll
+            for (int q = 0; q < 27; q++)
+              smem_add(&sJ[(q / 9) * TILE_ELEMS + key + ((q % 9) / 3 - 1) * TW + (q % 3 - 1)], v[q]);
+          }
+          break;
+        }
+        const int leader = __ffs(todo) - 1;
+        const int k = __shfl_sync(FULL, key, leader);
+        const bool mine = (key == k);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        double r[32];
+#pragma unroll
+        for (int q = 0; q < 32; q++) r[q] = mine ? v[q] : 0.0;
+        const double tot = warp_transpose_reduce27(r, lane);
+        if (lane < 27)
+          smem_add(&sJ[(lane / 9) * TILE_ELEMS + k + ((lane % 9) / 3 - 1) * TW + (lane % 3 - 1)], tot);
+        todo &= ~grp;
+        iter++;
+      }
+    } else {
+      if (dep) {
+        const int key = (cy1 - oy) * TW + (cx1 - ox);
+#pragma unroll
+        for (int q = 0; q < 27; q++)
+          smem_add(&sJ[(q / 9) * TILE_ELEMS + key + ((q % 9) / 3 - 1) * TW + (q % 3 - 1)], v[q]);
+      }
+    }
+    // extra column / row / corner when the particle changed its nearest cell (rare)
+    if (dep && (dcx != 0 || dcy != 0)) {
+      const int key = (cy1 - oy) * TW + (cx1 - ox);
+      double yfac1[3], yfac2[3], xfac1[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        yfac1[q] = gya[q] + 0.5 * hya[q];
+        yfac2[q] = third * hya[q] + 0.5 * gya[q];
+        xfac1[q] = gxa[q] + 0.5 * hxa[q];
+      }
+      const double hxe = (dcx < 0) ? hxm2 : hxp2;   // hx(+-2); gx(+-2) = 0
+      const double hye = (dcy < 0) ? hym2 : hyp2;
+      const double xfac1e = 0.5 * hxe;              // gx(+-2) + 0.5*hx(+-2)
+      const double yfac1e = 0.5 * hye;
+      const double yfac2e = third * hye;            // third*hy + 0.5*gy(+-2)
+      double col_jy_last = 0.0, row_jx_last = 0.0;
+      if (dcx != 0) {
+        const int ixe = 2 * dcx;
+        double jyrun = 0.0 - fjy * (hym2 * xfac1e);
+#pragma unroll
+        for (int iy = 0; iy < 3; iy++) {
+          const double jxv = (dcx < 0) ? (0.0 - fjx * (hxe * yfac1[iy]))
+                                       : (v[iy * 3 + 2] - fjx * (hxe * yfac1[iy]));
+          jyrun = jyrun - fjy * (hya[iy] * xfac1e);
+          const double jzv = fjz * (hxe * yfac2[iy]);
+          const int o = key + (iy - 1) * TW + ixe;
+          smem_add(&sJ[o], jxv);
+          smem_add(&sJ[TILE_ELEMS + o], jyrun);
+          smem_add(&sJ[2 * TILE_ELEMS + o], jzv);
+        }
+        col_jy_last = jyrun;
+      }
+      if (dcy != 0) {
+        const int iye = 2 * dcy;
+        double jxh = 0.0 - fjx * (hxm2 * yfac1e);
+#pragma unroll
+        for (int ix = 0; ix < 3; ix++) {
+          jxh = jxh - fjx * (hxa[ix] * yfac1e);
+          const double jyv = (dcy < 0) ? (0.0 - fjy * (hye * xfac1[ix]))
+                                       : (v[9 + 6 + ix] - fjy * (hye * xfac1[ix]));
+          const double jzv = fjz * (gxa[ix] * yfac1e + hxa[ix] * yfac2e);
+          const int o = key + iye * TW + (ix - 1);
+          smem_add(&sJ[o], jxh);
+          smem_add(&sJ[TILE_ELEMS + o], jyv);
+          smem_add(&sJ[2 * TILE_ELEMS + o], jzv);
+        }
+        row_jx_last = jxh;
+      }
+      if (dcx != 0 && dcy != 0) {
+        const int o = key + 2 * dcy * TW + 2 * dcx;
+        const double jxv = (dcx < 0) ? (0.0 - fjx * (hxe * yfac1e)) : (row_jx_last - fjx * (hxe * yfac1e));
+        const double jyv = (dcy < 0) ? (0.0 - fjy * (hye * xfac1e)) : (col_jy_last - fjy * (hye * xfac1e));
+        const double jzv = fjz * (hxe * yfac2e);
+        smem_add(&sJ[o], jxv);
+        smem_add(&sJ[TILE_ELEMS + o], jyv);
+        smem_add(&sJ[2 * TILE_ELEMS + o], jzv);
+      }
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
+    const int lx = q % TW, ly = q / TW;
+    const int cx = ox + lx, cy = oy + ly;
+    const bool ok = (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
+    if (!ok) continue;
+    const size_t o = gofs<2>(P, cx, cy, 1);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double val = sJ[f * TILE_ELEMS + q];
+      if (val != 0.0) atomicAdd(P.j[f] + o, val);
+    }
+  }
+}
+
+inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
+  static bool attr_set = false;
+  if (tiled && nd == 2) {
+    if (!attr_set) {
+      cudaFuncSetAttribute(push_tiled_2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      attr_set = true;
+    }
+    if (P.tg.ntiles > 0) {
+      push_tiled_2d<true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
+      (*launches)++;
+    }
+    return;
+  }
+  const long long cnt = P.last - P.first;
+  if (cnt <= 0) return;
+  long long blocks = (cnt + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (nd == 1) push_generic<1><<<(int)blocks, 256, 0, s>>>(P);
+  else if (nd == 2) push_generic<2><<<(int)blocks, 256, 0, s>>>(P);
+  else push_generic<3><<<(int)blocks, 256, 0, s>>>(P);
+  (*launches)++;
+}
+
+}  // namespace EPB_NS

@@ -1,0 +1,163 @@
+// sort.cu — on-GPU counting sort of a species into tile-major cell order.
+//
+// Replaces the reference's per-particle heap nodes (TYPE particle_list,
+// shared_data.F90:159-171) and supersedes reorder_particles_to_grid
+// (housekeeping/split_particle.F90:29-77): after the sort, every tile of the push
+// kernel owns one contiguous particle range and, inside it, particles of the same
+// cell are adjacent.  Out of place (double buffer), three passes:
+//   keys + histogram  ->  exclusive scan  ->  scatter.
+#include <cub/cub.cuh>
+
+#include "epb_internal.h"
+
+namespace {
+
+struct KeyOp {
+  const double *x[3];
+  long long n;
+  int nd, nloc[3];
+  double gmin[3], dx[3];
+  TileGeom tg;
+  int *key;
+  int *count;
+};
+
+__device__ __forceinline__ int cell_key(const KeyOp &K, long long i) {
+  int t[3] = {0, 0, 0}, in[3] = {0, 0, 0};
+  for (int d = 0; d < K.nd; d++) {
+    // nearest cell as calc_ppc defines it (io/calc_df.F90:795-796), clamped into 1..n
+    int cell = __double2int_rd((K.x[d][i] - K.gmin[d]) / K.dx[d] + 0.5);
+    cell = cell < 0 ? 0 : (cell > K.nloc[d] - 1 ? K.nloc[d] - 1 : cell);
+    t[d] = cell / K.tg.T[d];
+    in[d] = cell - t[d] * K.tg.T[d];
+  }
+  const int tile = (t[2] * K.tg.nt[1] + t[1]) * K.tg.nt[0] + t[0];
+  const int intile = (in[2] * K.tg.T[1] + in[1]) * K.tg.T[0] + in[0];
+  return tile * K.tg.cpt + intile;
+}
+
+// warp-aggregated increment: lanes with equal keys share one atomic
+__device__ __forceinline__ int agg_inc(int *ctr, int key, bool active) {
+  const int lane = threadIdx.x & 31;
+  const unsigned m = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
+  int base = 0;
+  if (active) {
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(&ctr[key], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    base += __popc(m & ((1u << lane) - 1u));
+  }
+  return base;
+}
+
+__global__ void __launch_bounds__(256) k_keys(const __grid_constant__ KeyOp K) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = (K.n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool active = i < K.n;
+    int key = 0;
+    if (active) { key = cell_key(K, i); K.key[i] = key; }
+    (void)agg_inc(K.count, key, active);
+  }
+}
+
+struct ScatterOp {
+  const double *src[7];
+  double *dst[7];
+  long long n;
+  const int *key;
+  const int *start;
+  int *cursor;
+};
+__global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ ScatterOp S) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = (S.n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool active = i < S.n;
+    const int key = active ? S.key[i] : 0;
+    const int r = agg_inc(S.cursor, key, active);
+    if (active) {
+      const long long dst = (long long)S.start[key] + r;
+#pragma unroll
+      for (int q = 0; q < 7; q++)
+        if (S.src[q]) S.dst[q][dst] = S.src[q][i];
+    }
+  }
+}
+
+__global__ void k_tile_start(const int *cell_start, int *tile_start, int ntiles, int cpt) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= ntiles) tile_start[t] = cell_start[(size_t)t * cpt];
+}
+
+}  // namespace
+
+void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
+  const int nd = cfg.ndims;
+  int T[3] = {1, 1, 1};
+  if (nd == 1) T[0] = 256;
+  else if (nd == 2) { T[0] = 16; T[1] = 16; }  // must match T2X/T2Y in push.cuh
+  else { T[0] = 8; T[1] = 8; T[2] = 8; }
+  tg.cpt = 1;
+  tg.ntiles = 1;
+  for (int d = 0; d < 3; d++) {
+    tg.T[d] = T[d];
+    tg.nt[d] = d < nd ? (cfg.n[d] + T[d] - 1) / T[d] : 1;
+    tg.cpt *= T[d];
+    tg.ntiles *= tg.nt[d];
+  }
+  tg.nkeys = tg.ntiles * tg.cpt;
+}
+
+int epb_sort_species(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  const epb_config &c = h->cfg;
+  const int nkeys = h->tg.nkeys;
+  EPB_CUDA(h, cudaMemsetAsync(h->cell_count, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
+  if (S.n > 0) {
+    KeyOp K;
+    for (int d = 0; d < 3; d++) {
+      K.x[d] = S.buf[S.cur][d];
+      K.nloc[d] = c.n[d];
+      K.gmin[d] = c.grid_min_local[d];
+      K.dx[d] = c.dx[d];
+    }
+    K.n = S.n;
+    K.nd = c.ndims;
+    K.tg = h->tg;
+    K.key = S.key;
+    K.count = h->cell_count;
+    long long nb = (S.n + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    k_keys<<<(int)nb, 256, 0, h->stream>>>(K);
+    h->launches++;
+  }
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, h->cell_start, nkeys + 1, h->stream);
+  if (need > h->cub_tmp_bytes) {
+    cudaFree(h->cub_tmp);
+    EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
+    h->cub_tmp_bytes = need;
+  }
+  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_tmp, need, h->cell_count, h->cell_start, nkeys + 1, h->stream));
+  h->launches++;
+  if (S.n > 0) {
+    EPB_CUDA(h, cudaMemsetAsync(h->cell_count, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
+    ScatterOp Sc;
+    for (int q = 0; q < 7; q++) { Sc.src[q] = S.buf[S.cur][q]; Sc.dst[q] = S.buf[S.cur ^ 1][q]; }
+    Sc.n = S.n;
+    Sc.key = S.key;
+    Sc.start = h->cell_start;
+    Sc.cursor = h->cell_count;
+    long long nb = (S.n + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    k_scatter<<<(int)nb, 256, 0, h->stream>>>(Sc);
+    h->launches++;
+    S.cur ^= 1;
+  }
+  k_tile_start<<<(h->tg.ntiles + 1 + 255) / 256, 256, 0, h->stream>>>(h->cell_start, S.tile_start, h->tg.ntiles, h->tg.cpt);
+  h->launches++;
+  S.n_sorted = S.n;
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}

@@ -1,0 +1,249 @@
+"""Host-side mirror of the hot-path procedures PROGRAM pic calls, bound to the CUDA library.
+
+`Simulation` owns one epb handle = one GPU = one decomposition rank.  Method names follow
+the reference routines: fields_half (update_eb_fields_half, fields.f90:533), push
+(push_particles, particles.F90:28), current_finish (current_smooth.F90:29), fields_final
+(update_eb_fields_final, fields.f90:563).  Any error raises; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from .deck import NG, Deck
+
+
+class EpbError(RuntimeError):
+    pass
+
+
+def _neighbour_table(deck: Deck, rank: int, periods):
+    """mpi_routines.F90:256-273"""
+    nd = deck.ndims
+    np_ = [max(1, deck.nproc[d]) if d < nd else 1 for d in range(3)]
+    co = deck.rank_coords(rank)
+    out = [-1] * 27
+    for iz in (-1, 0, 1):
+        for iy in (-1, 0, 1):
+            for ix in (-1, 0, 1):
+                t = [co[0] + ix, co[1] + iy, co[2] + iz]
+                ok = True
+                for d in range(3):
+                    if d >= nd:
+                        if t[d] != 0:
+                            ok = False
+                        continue
+                    if t[d] < 0 or t[d] >= np_[d]:
+                        if not periods[d]:
+                            ok = False
+                        else:
+                            t[d] %= np_[d]
+                if ok:
+                    out[(iz + 1) * 9 + (iy + 1) * 3 + (ix + 1)] = (t[2] * np_[1] + t[1]) * np_[0] + t[0]
+    return out
+
+
+def rank_geometry(deck: Deck, rank: int):
+    """Per-rank grid scalars, operation-for-operation as utilities.f90:343-421."""
+    nd = deck.ndims
+    n, g = deck.local_extent(rank)
+    co = deck.rank_coords(rank)
+    geo = dict(n=n, gmin=g, coords=co, is_bnd=[0] * 6, grid_min_local=[0.0] * 3, min_local=[0.0] * 3,
+               max_local=[0.0] * 3, min_outer=[0.0] * 3, max_outer=[0.0] * 3)
+    png = 3
+    for d in range(nd):
+        npd = max(1, deck.nproc[d])
+        mins, maxs = deck.cell_ranges(d)
+        dx = deck.dx(d)
+        geo["is_bnd"][2 * d] = int(co[d] == 0)
+        geo["is_bnd"][2 * d + 1] = int(co[d] == npd - 1)
+        geo["grid_min_local"][d] = float(deck.x_global(d, mins[co[d]]))
+        hdx = 0.5 * dx
+        geo["min_local"][d] = geo["grid_min_local"][d] - hdx
+        geo["max_local"][d] = float(deck.x_global(d, maxs[co[d]] + 1)) - hdx
+        shift = float((1 + png + 0) // 2)
+        geo["min_outer"][d] = deck.xmin[d] - shift * dx
+        geo["max_outer"][d] = deck.xmax[d] + shift * dx
+    return geo
+
+
+class Simulation:
+    def __init__(self, deck: Deck, rank: int = 0, strict_fp: bool = True, sort_interval: int = 1,
+                 capacity_factor: float = 1.5, min_capacity: int = 4096, stream: Optional[int] = None):
+        self.deck = deck
+        self.rank = rank
+        self.L = _lib.load()
+        nd = deck.ndims
+        geo = rank_geometry(deck, rank)
+        self.geo = geo
+        bcf = deck.bc_codes()
+        # setup_boundaries normalisation (boundary.F90:44-57)
+        for i in range(6):
+            if bcf[i] in (2, 9):
+                bcf[i] = 8
+            if bcf[i] == 5:
+                bcf[i] = 4
+        periods = []
+        for d in range(3):
+            per = d < nd and bcf[2 * d] == 1
+            for s in deck.species:
+                if d < nd and deck.species_bc_codes(s)[2 * d] == 1:
+                    per = True
+            periods.append(per)
+        cfg = _lib.Config()
+        cfg.ndims = nd
+        for d in range(3):
+            cfg.n[d] = geo["n"][d]
+            cfg.n_global[d] = deck.n[d] if d < nd else 1
+            cfg.dx[d] = deck.dx(d) if d < nd else 1.0
+            cfg.grid_min_local[d] = geo["grid_min_local"][d]
+            cfg.min_local[d] = geo["min_local"][d]
+            cfg.max_local[d] = geo["max_local"][d]
+            cfg.gmin[d] = deck.xmin[d] if d < nd else 0.0
+            cfg.gmax[d] = deck.xmax[d] if d < nd else 0.0
+            cfg.min_outer[d] = geo["min_outer"][d]
+            cfg.max_outer[d] = geo["max_outer"][d]
+        cfg.ng = NG
+        for i in range(6):
+            cfg.bc_field[i] = bcf[i]
+            cfg.is_boundary[i] = geo["is_bnd"][i]
+        for i, v in enumerate(_neighbour_table(deck, rank, periods)):
+            cfg.neighbour[i] = v
+        cfg.rank = rank
+        cfg.nranks = deck.nranks()
+        cfg.n_species = len(deck.species)
+        cfg.strict_fp = int(strict_fp)
+        cfg.sort_interval = sort_interval
+        cfg.dt = deck.dt()
+        ncell = geo["n"][0] * geo["n"][1] * geo["n"][2]
+        sp = (_lib.SpeciesCfg * max(1, len(deck.species)))()
+        for i, s in enumerate(deck.species):
+            sp[i].charge, sp[i].mass = s.charge, s.mass
+            for k, b in enumerate(deck.species_bc_codes(s)):
+                # setup_particle_boundary (boundary.F90:108-122)
+                if b in (2, 10):
+                    b = 9
+                if b in (3, 4):
+                    b = 5
+                sp[i].bc_particle[k] = b
+            sp[i].zero_current = int(s.zero_current)
+            sp[i].immobile = int(s.immobile)
+            sp[i].capacity = max(min_capacity, int(capacity_factor * s.npart_per_cell * ncell))
+        self._h = C.c_void_p()
+        rc = self.L.epb_create(C.byref(cfg), sp, C.byref(self._h))
+        if rc != 0:
+            raise EpbError(f"epb_create failed with code {rc} (see stderr)")
+        self.cfg = cfg
+        self.nd = nd
+        self.shape = tuple((geo["n"][d] + 2 * NG) if d < nd else 1 for d in (2, 1, 0))
+        if stream is not None:
+            self._chk(self.L.epb_set_stream(self._h, C.c_void_p(stream)))
+
+    # ------------------------------------------------------------------
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self.L.epb_last_error(self._h)
+            raise EpbError(f"epoch_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.epb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state transfer ---------------------------------------------------
+    def upload_field(self, name: str, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(self.shape)
+        self._chk(self.L.epb_upload_field(self._h, _lib.FIELD_NAMES.index(name), a.ctypes.data))
+
+    def download_field(self, name: str):
+        a = np.empty(self.shape, dtype=np.float64)
+        self._chk(self.L.epb_download_field(self._h, _lib.FIELD_NAMES.index(name), a.ctypes.data))
+        return a
+
+    def interior(self, name: str):
+        a = self.download_field(name)
+        sl = tuple(slice(NG, -NG) if a.shape[ax] > 1 else slice(None) for ax in range(3))
+        return a[sl]
+
+    def upload_species(self, isp: int, packed):
+        p = np.ascontiguousarray(packed, dtype=np.float64)
+        self._chk(self.L.epb_upload_species(self._h, isp, p.shape[0], p.ctypes.data))
+
+    def count(self, isp: int) -> int:
+        n = C.c_int64()
+        self._chk(self.L.epb_species_count(self._h, isp, C.byref(n)))
+        return n.value
+
+    def global_count(self, isp: int) -> int:
+        n = C.c_int64()
+        self._chk(self.L.epb_global_count(self._h, isp, C.byref(n)))
+        return n.value
+
+    def download_species(self, isp: int):
+        n = self.count(isp)
+        out = np.empty((n, self.nd + 4), dtype=np.float64)
+        if n:
+            self._chk(self.L.epb_download_species(self._h, isp, n, out.ctypes.data))
+        return out
+
+    def cell_counts(self, isp: int):
+        n = self.geo["n"]
+        out = np.zeros((n[2], n[1], n[0]), dtype=np.int32)
+        self._chk(self.L.epb_cell_counts(self._h, isp, out.ctypes.data))
+        return out
+
+    def load_uniform(self, isp: int, seed: int = 12345):
+        s = self.deck.species[isp]
+        t = (C.c_double * 3)(*s.temp)
+        d = (C.c_double * 3)(*s.drift)
+        self._chk(self.L.epb_load_uniform(self._h, isp, int(s.npart_per_cell), s.density, t, d, seed))
+
+    def set_comm(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._chk(self.L.epb_set_comm(self._h, buf))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        L = _lib.load()
+        buf = C.create_string_buffer(128)
+        if L.epb_nccl_unique_id(buf) != 0:
+            raise EpbError("ncclGetUniqueId failed")
+        return buf.raw
+
+    # -- backend interface used by deck.run --------------------------------
+    def set_laser_source(self, local_rank: int, side: int, s1, s2):
+        s1 = np.ascontiguousarray(s1, dtype=np.float64)
+        s2 = np.ascontiguousarray(s2, dtype=np.float64)
+        self._chk(self.L.epb_set_laser_source(self._h, side, s1.ctypes.data, s2.ctypes.data))
+
+    def init(self): self._chk(self.L.epb_init_boundaries(self._h))
+    def fields_half(self): self._chk(self.L.epb_fields_half(self._h))
+    def push(self): self._chk(self.L.epb_push(self._h))
+    def current_finish(self): self._chk(self.L.epb_current_finish(self._h))
+    def fields_final(self): self._chk(self.L.epb_fields_final(self._h))
+    def sort(self): self._chk(self.L.epb_sort(self._h))
+    def synchronize(self): self._chk(self.L.epb_synchronize(self._h))
+
+    def step(self):
+        """One pass of the hot path with no boundary sources (uniform-plasma benchmark step)."""
+        self.fields_half()
+        self.push()
+        self.current_finish()
+        self.fields_final()
+
+    def launch_count(self) -> int:
+        return int(self.L.epb_launch_count(self._h))
+
+    def push_kernel_ms(self, reset: int = 0):
+        ms = C.c_double(); n = C.c_int64()
+        self._chk(self.L.epb_push_kernel_ms(self._h, C.byref(ms), C.byref(n), reset))
+        return ms.value, n.value

@@ -1,0 +1,162 @@
+/* epoch_b200.h — C ABI of the B200-native PIC hot path (drop-in boundary).
+ *
+ * EPOCH has no plugin/FFI layer: PROGRAM pic calls argument-less module
+ * procedures that work on shared_data globals (epoch2d/src/epoch2d.F90:211,216,
+ * 250,265).  "Drop-in" therefore means a Fortran shim whose procedure bodies call
+ * these entry points through ISO_C_BINDING (fortran/epoch_b200_mod.F90,
+ * INTEGRATION.md).  Every entry point names the reference routine it replaces.
+ *
+ * Conventions
+ *  - all functions return 0 on success, non-zero on error (epb_last_error());
+ *    EPB_ERR_UNSUPPORTED is returned by epb_create for configurations the device
+ *    path does not implement, instead of silently diverging (the shim maps any
+ *    non-zero code to abort_code(c_err_generic_error), utilities.f90:261-281).
+ *  - host arrays are the Fortran allocatables passed with C_LOC: column-major,
+ *    full extent incl. ghost cells, field(1-ng:nx+ng [,1-ng:ny+ng [,1-ng:nz+ng]])
+ *    (mpi_routines.F90:379-388).  The library copies; it never keeps a host pointer.
+ *  - particle blocks use the pack_particle wire layout (partlist.F90:414-486,
+ *    default flags): nvar = ndims + 4 doubles per particle:
+ *    pos(1..ndims), p(1..3), weight.
+ *  - one host thread <-> one handle <-> one GPU <-> one rank.
+ */
+#ifndef EPOCH_B200_H
+#define EPOCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct epb_handle epb_handle;
+
+enum {
+  EPB_OK = 0,
+  EPB_ERR_ARG = 1,
+  EPB_ERR_CUDA = 2,
+  EPB_ERR_UNSUPPORTED = 3,
+  EPB_ERR_CAPACITY = 4,
+  EPB_ERR_NCCL = 5,
+};
+
+/* boundary codes, identical to constants.F90:75-90 */
+enum {
+  EPB_BC_PERIODIC = 1,
+  EPB_BC_OTHER = 2,
+  EPB_BC_SIMPLE_LASER = 3,
+  EPB_BC_SIMPLE_OUTFLOW = 4,
+  EPB_BC_OPEN = 5,
+  EPB_BC_ZERO_GRADIENT = 7,
+  EPB_BC_CLAMP = 8,
+  EPB_BC_REFLECT = 9,
+  EPB_BC_CONDUCT = 10,
+  EPB_BC_THERMAL = 11,
+};
+
+/* field ids for upload/download */
+enum { EPB_EX = 0, EPB_EY, EPB_EZ, EPB_BX, EPB_BY, EPB_BZ, EPB_JX, EPB_JY, EPB_JZ, EPB_NFIELD };
+
+/* Mirror of the shared_data globals the hot path reads (shared_data.F90:484-683).
+ * All values are the caller's: the library derives nothing that would change
+ * bit-level bookkeeping (x_min_local etc. come from utilities.f90:343-421). */
+typedef struct epb_config {
+  int32_t ndims;            /* c_ndims: 1, 2 or 3 */
+  int32_t n[3];             /* nx, ny, nz of this rank */
+  int32_t n_global[3];      /* nx_global ... */
+  int32_t ng;               /* ghost cells; must be 5 (triangle shape: png+2) */
+  int32_t bc_field[6];      /* bc_field(c_bd_x_min..c_bd_z_max) after setup_boundaries */
+  int32_t is_boundary[6];   /* x_min_boundary, x_max_boundary, ... */
+  int32_t neighbour[27];    /* neighbour(ix,iy,iz) at [(iz+1)*9+(iy+1)*3+(ix+1)], -1 = MPI_PROC_NULL */
+  int32_t rank, nranks;
+  int32_t n_species;
+  int32_t strict_fp;        /* 1: kernels built without FMA contraction (bit-level parity build) */
+  int32_t sort_interval;    /* steps between on-GPU counting sorts (>=1) */
+  int32_t reserved[5];
+  double dx[3];             /* dx, dy, dz */
+  double dt;
+  double grid_min_local[3]; /* x_grid_min_local ... (cell centre of local cell 1) */
+  double min_local[3];      /* x_min_local ... */
+  double max_local[3];      /* x_max_local ... */
+  double gmin[3], gmax[3];  /* x_min, x_max ... (global domain) */
+  double min_outer[3];      /* x_min_outer ... (utilities.f90:367-369) */
+  double max_outer[3];
+} epb_config;
+
+/* Mirror of TYPE particle_species (shared_data.F90:194-285), hot-path members only */
+typedef struct epb_species {
+  double charge;            /* C */
+  double mass;              /* kg */
+  int32_t bc_particle[6];   /* after setup_particle_boundary (boundary.F90:99-139) */
+  int32_t zero_current;     /* tracer species: pushed, no current */
+  int32_t immobile;
+  int64_t capacity;         /* device slots to reserve for this species on this rank */
+} epb_species;
+
+/* -- lifetime ----------------------------------------------------------------
+ * replaces: mpi_initialise's ALLOCATE of ex..jz (mpi_routines.F90:379-388) and
+ * the per-species particle lists (partlist.F90:89-113). */
+int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **out);
+int epb_destroy(epb_handle *h);
+const char *epb_last_error(const epb_handle *h);
+const char *epb_version(void);
+/* run every kernel on this cudaStream_t (default: a stream owned by the handle) */
+int epb_set_stream(epb_handle *h, void *cuda_stream);
+int epb_synchronize(epb_handle *h);
+
+/* -- multi-GPU ----------------------------------------------------------------
+ * replaces: the Cartesian communicator (mpi_routines.F90:179-275).  id is the
+ * 128-byte ncclUniqueId produced by epb_nccl_unique_id on rank 0 and broadcast
+ * by the host (MPI_BCAST on the Fortran side, torch.distributed in the harness). */
+int epb_nccl_unique_id(void *id128);
+int epb_set_comm(epb_handle *h, const void *id128);
+
+/* -- state transfer ------------------------------------------------------------ */
+int epb_upload_field(epb_handle *h, int field, const double *host);
+int epb_download_field(epb_handle *h, int field, double *host);
+int epb_upload_species(epb_handle *h, int ispecies, int64_t n, const double *packed);
+int epb_download_species(epb_handle *h, int ispecies, int64_t n, double *packed);
+int epb_species_count(epb_handle *h, int ispecies, int64_t *n);   /* attached_list%count */
+/* device-side loader for the bench: npart_per_cell particles per cell, uniform
+ * density, Maxwellian momenta (stands in for auto_load, helper.F90:95, whose
+ * KISS stream is host-serial; parity runs upload the oracle's particles instead) */
+int epb_load_uniform(epb_handle *h, int ispecies, int32_t npart_per_cell, double density,
+                     const double temp_k[3], const double drift[3], uint64_t seed);
+/* particles-per-cell as calc_ppc defines it (io/calc_df.F90:761-808); out(nx,ny,nz) int32 */
+int epb_cell_counts(epb_handle *h, int ispecies, int32_t *out);
+/* device pointers of the field arrays, for harness-side reductions (may be NULL-checked) */
+int epb_field_device_ptr(epb_handle *h, int field, void **dptr);
+
+/* -- laser / outflow boundary sources -------------------------------------------
+ * side 0 = x_min, 1 = x_max.  source1/source2 are laser.f90:347-352's arrays on the
+ * local plane (0:ny, 0:nz), y fastest, evaluated by the host each step (the time
+ * profile is a deck expression, laser.f90:159-176). */
+int epb_set_laser_source(epb_handle *h, int side, const double *source1, const double *source2);
+
+/* -- the hot path ---------------------------------------------------------------- */
+/* epoch2d.F90:144-162: setup_field_boundaries snapshots, setup_bc_lists + particle_bcs,
+ * efield_bcs, bfield_final_bcs with dt/2 */
+int epb_init_boundaries(epb_handle *h);
+/* update_eb_fields_half (fields.f90:533-559) */
+int epb_fields_half(epb_handle *h);
+/* push_particles (particles.F90:28-650) incl. particle_bcs (boundary.F90:1029-1462) */
+int epb_push(epb_handle *h);
+/* current_finish (current_smooth.F90:29-45) */
+int epb_current_finish(epb_handle *h);
+/* update_eb_fields_final (fields.f90:563-582) */
+int epb_fields_final(epb_handle *h);
+/* counting sort of every species by cell (supersedes reorder_particles_to_grid,
+ * split_particle.F90:29-77); also runs automatically every sort_interval pushes */
+int epb_sort(epb_handle *h);
+/* update_particle_count (partlist.F90:984-1003): global count of a species */
+int epb_global_count(epb_handle *h, int ispecies, int64_t *n);
+
+/* -- instrumentation ---------------------------------------------------------------
+ * kernel launch counter since creation (bench.py's gpu_launches), and CUDA-event
+ * timing of the push/deposit kernel alone: average ms per launch since the last reset */
+int64_t epb_launch_count(const epb_handle *h);
+int epb_push_kernel_ms(epb_handle *h, double *avg_ms, int64_t *launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPOCH_B200_H */

