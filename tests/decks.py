@@ -53,7 +53,8 @@ def thermal(ndims, n, ppc=8, nproc=(1, 1, 1), temp_k=1.0e7, density=1.0e25, bc="
     if two_species:
         sp.append(D.Species("proton", D.q0, 1836.2 * D.m0, npart_per_cell=ppc, density=density,
                             temp=(temp_k,) * 3))
-    return D.Deck(ndims, list(n), xmin, xmax, [bc] * (2 * ndims), species=sp, nsteps=nsteps,
+    bcs = [bc] * (2 * ndims) if isinstance(bc, str) else list(bc)
+    return D.Deck(ndims, list(n), xmin, xmax, bcs, species=sp, nsteps=nsteps,
                   nproc=nproc, seed=seed)
 
 

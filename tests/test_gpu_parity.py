@@ -123,7 +123,7 @@ def test_reflecting_walls(ndims, n):
 
 
 def test_open_boundaries_delete_particles():
-    dk = decks.thermal(2, (32, 24), ppc=5, temp_k=2.0e9, bc="open")
+    dk = decks.thermal(2, (32, 24), ppc=5, temp_k=2.0e9, bc=["open", "open", "periodic", "periodic"])
     o, sim = make_pair(dk)
     run_both(dk, o, sim, 25)
     assert o.count(0, 0) < 32 * 24 * 5          # particles really left
