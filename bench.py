@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py — particle-updates/s of the PIC hot path (push + deposit + FDTD + exchange
+[+ amortised sort]) on BASELINE.md config C2: epoch2d uniform thermal plasma, periodic,
+4096 x 4096 cells, 64 particles per cell (1.07e9 particles) per B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun, one rank per GPU; the domain is decomposed as EPOCH's
+split_domain would (mpi_routines.F90:107-138) with 4096^2 cells per rank (weak scaling).
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of EPOCH's
+algorithm (oracle/) on the host cores: the reference binary is Fortran 2003 + MPI and can
+not be built in this image (no Fortran compiler, no MPI), see DESIGN.md.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/s (push+deposit+FDTD)"
+UNIT = "particle-updates/s"
+
+
+def c2_deck(n_local, ppc, nproc, temp_k=1.0e7, density=1.0e25):
+    """uniform thermal electrons, dx = dy = Debye length."""
+    from epoch_b200 import deck as D
+    debye = math.sqrt(D.epsilon0 * D.kb * temp_k / (density * D.q0 ** 2))
+    n = [n_local * nproc[0], n_local * nproc[1]]
+    sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=ppc, density=density, temp=(temp_k,) * 3)]
+    return D.Deck(2, n, [0.0, 0.0], [debye * n[0], debye * n[1]], ["periodic"] * 4, species=sp,
+                  nproc=(nproc[0], nproc[1], 1))
+
+
+def split_2d(nranks):
+    """split_domain's minimum-surface rule for a square per-rank tile (mpi_routines.F90:107-138):
+    8 -> (2,4), 4 -> (2,2), 2 -> (1,2), 1 -> (1,1)."""
+    best, area = (1, nranks), None
+    for ix in range(1, nranks + 1):
+        iy = nranks // ix
+        if ix * iy != nranks:
+            continue
+        a = ix + iy
+        if area is None or a < area:
+            best, area = (ix, iy), a
+    return best
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.rows, self.proc = [], None
+        self.index = index
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        mx = 0
+        for r in self.rows:
+            try:
+                mx = max(mx, int(float(r[1])))
+            except Exception:
+                pass
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _oracle_sample(args):
+    n, ppc, steps, seed = args
+    from oracle.oracle import Oracle
+    dk = c2_deck(n, ppc, (1, 1))
+    dk.seed = seed
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+    return n * n * ppc * steps, time.perf_counter() - t0
+
+
+def cpu_baseline(n=192, ppc=64, steps=4, procs=1):
+    """CPU restatement of EPOCH's algorithm on a bounded sample of the C2 workload."""
+    import multiprocessing as mp
+    from oracle import oracle as _o
+    _o.build()
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_oracle_sample((n, ppc, steps, 7842432))]
+        wall = res[0][1]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_oracle_sample, [(n, ppc, steps, 7842432 + i) for i in range(procs)])
+        wall = max(r[1] for r in res)
+    updates = sum(r[0] for r in res)
+    return {"value": updates / wall, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{procs} x (C2 physics at {n}x{n} cells, {ppc} ppc, {steps} steps; "
+                      f"oracle/epoch_oracle.cpp, g++ -O3 -ffp-contract=off); "
+                      "CPU restatement of EPOCH's algorithm, not the EPOCH binary",
+            "wall_s": time.perf_counter() - t0}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        b = cpu_baseline(n=128, ppc=64, steps=2, procs=procs)
+        if i >= args.warmup:
+            vals.append(b)
+    v = sum(b["value"] for b in vals) / len(vals)
+    sample = vals[-1]["sample"]
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(b["wall_s"] for b in vals) / len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "epoch2d uniform thermal plasma (BASELINE C2 physics), bounded CPU sample"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=4096, help="cells per side per GPU")
+    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "4")))
+    ap.add_argument("--strict", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from epoch_b200.pic import Simulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; epoch_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nproc = split_2d(world)
+    dk = c2_deck(args.n, args.ppc, nproc)
+    stream = torch.cuda.Stream()
+    sim = Simulation(dk, rank=rank, strict_fp=bool(args.strict), sort_interval=args.sort_interval,
+                     capacity_factor=1.02 if world == 1 else 1.15, stream=stream.cuda_stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(Simulation.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        sim.set_comm(bytes(idt.cpu().tolist()))
+    sim.load_uniform(0, seed=20261017)
+    sim.init()
+    n_local = sim.count(0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") --------------------------------------
+    for _ in range(args.warmup):
+        sim.step()
+    sim.push_kernel_ms(reset=1)   # start timing the push kernel with CUDA events on its stream
+    launches0 = sim.launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            sim.step()
+        e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count() - launches0
+    push_ms, push_n = sim.push_kernel_ms(reset=2)
+    n_total = sim.global_count(0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ("e2e") ------------------
+    # Per step the host supplies what EPOCH's Fortran side evaluates each step (the boundary
+    # source planes, laser.f90:347-352; zero for this periodic deck but copied all the same)
+    # from pinned memory, and reads back the step's results: the global particle count
+    # (update_particle_count), the field energies (calc_total_energy_sum) and the Ey array as
+    # a field dump would.  The particle state itself stays device-resident by design.
+    ny1 = sim.geo["n"][1] + 1
+    src = torch.zeros(2, ny1, dtype=torch.float64).pin_memory()
+    ey_host = torch.empty(sim.shape, dtype=torch.float64).pin_memory()
+    h2d = 2 * 2 * ny1 * 8
+    d2h = ey_host.numel() * 8 + 8 + 16
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for side in (0, 1):
+            sim.L.epb_set_laser_source(sim._h, side, src[0].data_ptr(), src[1].data_ptr())
+        sim.step()
+        sim.global_count(0)
+        sim.field_energy()
+        sim.download_field_into("ey", ey_host.data_ptr())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n_total * args.steps / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_per_update = 88.0 + 120.0 / args.ppc       # push+deposit kernel
+        achieved = (n_local * bytes_per_update / (push_ms * 1e-3)) / 1e9 if push_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "push_traffic_bytes.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"epoch2d uniform thermal plasma, periodic, {args.n}x{args.n} cells per GPU, "
+                                   f"{args.ppc} ppc ({n_local} particles per GPU), triangle shape, Yee order 2 "
+                                   "(BASELINE C2)",
+                       "decomposition": f"{nproc[0]}x{nproc[1]}", "sort_interval": args.sort_interval,
+                       "strict_fp": int(args.strict), "particles_total": n_total,
+                       "l2_policy": "inputs (51.5 GB of particle state per GPU) far exceed the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "kernel": "push_tiled_2d (push+deposit)", "bytes_per_update": bytes_per_update,
+                         "kernel_ms": push_ms, "kernel_launches": push_n,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            b = cpu_baseline()
+            b.pop("wall_s", None)
+            line["cpu_baseline"] = b
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -340,6 +340,42 @@ __global__ void __launch_bounds__(256) k_load_uniform(const __grid_constant__ Lo
   }
 }
 
+// calc_total_energy_sum (io/calc_df.F90:1321-1417)
+struct EnergyOp {
+  const double *f[6];
+  int nd, n[3], sz[3];
+  double *out;  // [2]
+};
+__global__ void __launch_bounds__(256) k_field_energy(const __grid_constant__ EnergyOp E) {
+  const size_t total = (size_t)E.n[0] * E.n[1] * E.n[2];
+  double se = 0.0, sb = 0.0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % E.n[0]) + 1;
+    const int iy = (int)((t / E.n[0]) % E.n[1]) + 1;
+    const int iz = (int)(t / ((size_t)E.n[0] * E.n[1])) + 1;
+    const size_t o = fofs(E.sz, E.nd, ix, iy, iz);
+    se += E.f[0][o] * E.f[0][o] + E.f[1][o] * E.f[1][o] + E.f[2][o] * E.f[2][o];
+    sb += E.f[3][o] * E.f[3][o] + E.f[4][o] * E.f[4][o] + E.f[5][o] * E.f[5][o];
+  }
+  for (int s = 16; s >= 1; s >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, s);
+    sb += __shfl_xor_sync(0xffffffffu, sb, s);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&E.out[0], se); atomicAdd(&E.out[1], sb); }
+}
+__global__ void __launch_bounds__(256) k_kinetic_energy(const double *px, const double *py, const double *pz,
+                                                        const double *w, long long n, double mc, double mc2, double *out) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double ux = px[i] / mc, uy = py[i] / mc, uz = pz[i] / mc;
+    const double u2 = ux * ux + uy * uy + uz * uz;
+    const double gamma = sqrt(u2 + 1.0);
+    s += w[i] * (u2 / (gamma + 1.0)) * mc2;  // (gamma-1) m c^2 without cancellation
+  }
+  for (int q = 16; q >= 1; q >>= 1) s += __shfl_xor_sync(0xffffffffu, s, q);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
 inline int nblocks(size_t total, int cap = 148 * 16) {
   size_t b = (total + 255) / 256;
   if (b < 1) b = 1;
@@ -675,8 +711,8 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     EPB_CUDA(h, cudaMalloc(&h->out_count, 64 * sizeof(int)));
     EPB_CUDA(h, cudaMemsetAsync(h->out_count, 0, 64 * sizeof(int), h->stream));
     EPB_CUDA(h, cudaMalloc(&h->out_idx, ((size_t)27 * h->out_cap + 1) * sizeof(int)));
-    EPB_CUDA(h, cudaMalloc(&h->d_scratch, 1024 * sizeof(int)));
   }
+  EPB_CUDA(h, cudaMalloc(&h->d_scratch, 1024 * sizeof(int)));
   EPB_CUDA(h, cudaMallocHost(&h->h_counts, 256 * sizeof(int)));
   EPB_CUDA(h, cudaEventCreate(&h->ev0));
   EPB_CUDA(h, cudaEventCreate(&h->ev1));
@@ -989,6 +1025,49 @@ int epb_current_finish(epb_handle *h) {
   rc = epb_halo_exchange(h, EPB_JX, 3, false);  // field_bc(jx|jy|jz, jng)
   if (rc) return rc;
   EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
+int epb_field_energy(epb_handle *h, double out[2]) {
+  if (!h || !out) return EPB_ERR_ARG;
+  const epb_config &c = h->cfg;
+  double *d = (double *)(h->d_scratch ? h->d_scratch + 256 : nullptr);
+  bool tmp = false;
+  if (!d) { EPB_CUDA(h, cudaMalloc(&d, 2 * sizeof(double))); tmp = true; }
+  EPB_CUDA(h, cudaMemsetAsync(d, 0, 2 * sizeof(double), h->stream));
+  EnergyOp E;
+  for (int q = 0; q < 6; q++) E.f[q] = h->f(q);
+  E.nd = c.ndims;
+  for (int q = 0; q < 3; q++) { E.n[q] = c.n[q]; E.sz[q] = h->sz[q]; }
+  E.out = d;
+  size_t total = (size_t)c.n[0] * c.n[1] * c.n[2];
+  k_field_energy<<<nblocks(total, 148 * 8), 256, 0, h->stream>>>(E);
+  h->launches++;
+  double v[2];
+  EPB_CUDA(h, cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (tmp) cudaFree(d);
+  double dv = 1.0;
+  for (int q = 0; q < c.ndims; q++) dv *= c.dx[q];
+  const double mu0 = 4.e-7 * 3.141592653589793238462643383279503;
+  out[0] = 0.5 * EPB_EPS0 * v[0] * dv;
+  out[1] = 0.5 / mu0 * v[1] * dv;
+  return EPB_OK;
+}
+
+int epb_kinetic_energy(epb_handle *h, int is, double *out) {
+  if (!h || is < 0 || is >= (int)h->sp.size() || !out) return EPB_ERR_ARG;
+  SpeciesDev &S = h->sp[is];
+  double *d = (double *)(h->d_scratch + 256);
+  EPB_CUDA(h, cudaMemsetAsync(d, 0, sizeof(double), h->stream));
+  const double mc = EPB_C * S.cfg.mass;
+  if (S.n > 0) {
+    k_kinetic_energy<<<nblocks((size_t)S.n, 148 * 8), 256, 0, h->stream>>>(S.buf[S.cur][3], S.buf[S.cur][4], S.buf[S.cur][5],
+                                                                    S.buf[S.cur][6], S.n, mc, mc * EPB_C, d);
+    h->launches++;
+  }
+  EPB_CUDA(h, cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   return EPB_OK;
 }
 

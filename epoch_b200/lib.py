@@ -21,7 +21,8 @@ SYMBOLS = (
     "epb_upload_species", "epb_download_species", "epb_species_count", "epb_load_uniform",
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
-    "epb_global_count", "epb_launch_count", "epb_push_kernel_ms",
+    "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy",
+    "epb_kinetic_energy",
 )
 
 
@@ -80,6 +81,8 @@ def load():
                  "epb_fields_final", "epb_sort"):
         getattr(L, name).argtypes = [vp]
     L.epb_global_count.argtypes = [vp, i32, C.POINTER(i64)]
+    L.epb_field_energy.argtypes = [vp, dp]
+    L.epb_kinetic_energy.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.epb_launch_count.argtypes = [vp]; L.epb_launch_count.restype = i64
     L.epb_push_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), i32]
     _lib = L

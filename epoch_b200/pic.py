@@ -240,6 +240,21 @@ class Simulation:
         self.current_finish()
         self.fields_final()
 
+    def field_energy(self):
+        """(electric, magnetic) field energy of the local interior, calc_df.F90:1321-1417"""
+        out = (C.c_double * 2)()
+        self._chk(self.L.epb_field_energy(self._h, out))
+        return out[0], out[1]
+
+    def kinetic_energy(self, isp: int) -> float:
+        out = C.c_double()
+        self._chk(self.L.epb_kinetic_energy(self._h, isp, C.byref(out)))
+        return out.value
+
+    def download_field_into(self, name: str, host_ptr: int):
+        """D2H of one field array (with ghosts) into caller-owned (e.g. pinned) host memory."""
+        self._chk(self.L.epb_download_field(self._h, _lib.FIELD_NAMES.index(name), C.c_void_p(host_ptr)))
+
     def launch_count(self) -> int:
         return int(self.L.epb_launch_count(self._h))
 

@@ -150,6 +150,12 @@ int epb_sort(epb_handle *h);
 /* update_particle_count (partlist.F90:984-1003): global count of a species */
 int epb_global_count(epb_handle *h, int ispecies, int64_t *n);
 
+/* -- device-side diagnostics (feed output_routines without downloading the state) ----
+ * calc_total_energy_sum (io/calc_df.F90:1321-1417): out[0] = 0.5*eps0*sum(E^2)*dV,
+ * out[1] = 0.5/mu0*sum(B^2)*dV over the local interior; kinetic: sum w*(gamma-1)*m*c^2 */
+int epb_field_energy(epb_handle *h, double out[2]);
+int epb_kinetic_energy(epb_handle *h, int ispecies, double *out);
+
 /* -- instrumentation ---------------------------------------------------------------
  * kernel launch counter since creation (bench.py's gpu_launches), and CUDA-event
  * timing of the push/deposit kernel alone: average ms per launch since the last reset */
