@@ -624,6 +624,14 @@ int epb_halo_local(epb_handle *h, int f0, int nf, bool add, int d, int pass) {
 extern "C" {
 
 const char *epb_version(void) { return "epoch_b200 0.1 (sm_100a)"; }
+int epb_abi_info(int32_t out[4]) {
+  if (!out) return EPB_ERR_ARG;
+  out[0] = (int32_t)sizeof(epb_config);
+  out[1] = (int32_t)sizeof(epb_species);
+  out[2] = NG;
+  out[3] = EPB_NFIELD;
+  return EPB_OK;
+}
 const char *epb_last_error(const epb_handle *h) { return h ? h->err.c_str() : "null handle"; }
 int64_t epb_launch_count(const epb_handle *h) { return h ? h->launches : 0; }
 
@@ -885,14 +893,6 @@ int epb_set_laser_source(epb_handle *h, int side, const double *s1, const double
   return EPB_OK;
 }
 
-static int run_particle_bcs(epb_handle *h) {
-  for (int is = 0; is < (int)h->sp.size(); is++) {
-    int rc = epb_particle_exchange(h, is);
-    if (rc) return rc;
-  }
-  return EPB_OK;
-}
-
 int epb_init_boundaries(epb_handle *h) {
   if (!h) return EPB_ERR_ARG;
   const epb_config &c = h->cfg;
@@ -963,7 +963,12 @@ int epb_push(epb_handle *h) {
   EPB_CUDA(h, cudaMemsetAsync(h->f(EPB_JX), 0, 3 * h->fsize * sizeof(double), h->stream));
   for (int is = 0; is < (int)h->sp.size(); is++) {
     SpeciesDev &S = h->sp[is];
-    if (S.cfg.immobile || S.n == 0) continue;
+    if (S.cfg.immobile) continue;
+    if (S.n == 0) {  // nothing to push, but neighbours may still send us particles
+      int rc0 = epb_particle_exchange(h, is);
+      if (rc0) return rc0;
+      continue;
+    }
     PushParams P;
     fill_push_params(h, is, P);
     auto launch = c.strict_fp ? epb_launch_push_strict : epb_launch_push_fast;
@@ -987,11 +992,16 @@ int epb_push(epb_handle *h) {
       cudaEventRecord(e1, h->stream);
       h->ev_pool.push_back({e0, e1});
     }
+    EPB_CUDA(h, cudaGetLastError());
+    // particle_bcs (particles.F90:648) for this species.  The outbox is shared by all
+    // species, so it is drained before the next species is pushed; the reference runs
+    // particle_bcs after the species loop, which is equivalent because a species' push
+    // reads no other species' particles.
+    int rc = epb_particle_exchange(h, is);
+    if (rc) return rc;
   }
-  EPB_CUDA(h, cudaGetLastError());
   h->pushes_since_sort++;
-  // particle_bcs (particles.F90:648)
-  return run_particle_bcs(h);
+  return EPB_OK;
 }
 
 int epb_current_finish(epb_handle *h) {

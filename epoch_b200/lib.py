@@ -16,7 +16,7 @@ FIELD_NAMES = ("ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz")
 
 # every symbol include/epoch_b200.h declares
 SYMBOLS = (
-    "epb_create", "epb_destroy", "epb_last_error", "epb_version", "epb_set_stream", "epb_synchronize",
+    "epb_create", "epb_destroy", "epb_last_error", "epb_version", "epb_abi_info", "epb_set_stream", "epb_synchronize",
     "epb_nccl_unique_id", "epb_set_comm", "epb_upload_field", "epb_download_field",
     "epb_upload_species", "epb_download_species", "epb_species_count", "epb_load_uniform",
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
@@ -58,12 +58,30 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C epoch_b200/csrc).  epoch_b200 has no CPU fallback.")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    # libepoch_b200.so needs libnccl.so.2.  If PyTorch is importable its bundled (newer) NCCL must be
+    # the one copy in the process, whichever of the two libraries gets loaded first; a Fortran host
+    # simply links the system NCCL.
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec is not None and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+    except Exception:
+        pass
+    L = C.CDLL(LIB_PATH)
     vp, i32, i64, dp = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
     L.epb_create.argtypes = [C.POINTER(Config), C.POINTER(SpeciesCfg), C.POINTER(vp)]
     L.epb_destroy.argtypes = [vp]
     L.epb_last_error.argtypes = [vp]; L.epb_last_error.restype = C.c_char_p
     L.epb_version.restype = C.c_char_p
+    L.epb_abi_info.argtypes = [C.POINTER(C.c_int32)]
+    info = (C.c_int32 * 4)()
+    L.epb_abi_info(info)
+    if info[0] != C.sizeof(Config) or info[1] != C.sizeof(SpeciesCfg):
+        raise RuntimeError(f"ABI mismatch: library has sizeof(epb_config)={info[0]}, sizeof(epb_species)={info[1]}; "
+                           f"binding has {C.sizeof(Config)}, {C.sizeof(SpeciesCfg)}")
     L.epb_set_stream.argtypes = [vp, vp]
     L.epb_synchronize.argtypes = [vp]
     L.epb_nccl_unique_id.argtypes = [vp]

@@ -99,6 +99,9 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
 int epb_destroy(epb_handle *h);
 const char *epb_last_error(const epb_handle *h);
 const char *epb_version(void);
+/* ABI self-description for the binding side (the Fortran shim checks it once at start-up):
+ * out[0] = sizeof(epb_config), out[1] = sizeof(epb_species), out[2] = ng, out[3] = EPB_NFIELD */
+int epb_abi_info(int32_t out[4]);
 /* run every kernel on this cudaStream_t (default: a stream owned by the handle) */
 int epb_set_stream(epb_handle *h, void *cuda_stream);
 int epb_synchronize(epb_handle *h);

@@ -1,0 +1,33 @@
+#!/bin/bash
+# Run on the B200 box through gpurun: GPU parity tests, the C2 bench line, the ncu launch
+# list of the same bench command (reduced grid) and one full ncu capture of the push kernel.
+# Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+STAGES="${1:-tests bench launches ncu}"
+for s in $STAGES; do
+case $s in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+  echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log ;;
+smoke)
+  timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log ;;
+bench)
+  timeout 1500 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+  echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+benchref)
+  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+  cat gpurun_out/bench_ref.json ;;
+launches)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --n 2048 --steps 4 --warmup 3 --no-cpu-baseline \
+      > gpurun_out/launches_bench.log 2>&1
+  echo "launches rc=$?" ;;
+ncu)
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:push_tiled -s 3 -c 2 \
+      -f -o gpurun_out/prof_push python bench.py --n 2048 --steps 2 --warmup 3 --no-cpu-baseline \
+      > gpurun_out/ncu_push.log 2>&1
+  echo "ncu rc=$?" ;;
+esac
+done
