@@ -1,0 +1,426 @@
+! epoch_b200_mod.F90 -- ISO_C_BINDING shim between EPOCH's Fortran host and libepoch_b200.so.
+!
+! SOURCE ONLY: the build image has no Fortran compiler (SURVEY.md section 0), so this file is
+! delivered as the binding a maintainer adds to epoch{1,2,3}d/src/; everything below the C ABI
+! is verified through the ctypes harness (epoch_b200/lib.py), which binds the same symbols
+! with the same struct layout (checked at start-up through epb_abi_info).
+!
+! How it drops in (INTEGRATION.md has the step list):
+!   * PROGRAM pic keeps its call order (epoch2d.F90:211,216,250,265).  The four routines it calls
+!     get the one-line bodies at the bottom of this file (compile with -DEPOCH_B200):
+!       update_eb_fields_half  -> epb_fields_half      (fields.f90:533)
+!       push_particles         -> epb_push             (particles.F90:28, incl. particle_bcs)
+!       current_finish         -> epb_current_finish   (housekeeping/current_smooth.F90:29)
+!       update_eb_fields_final -> epb_fields_final     (fields.f90:563)
+!   * b200_attach is called once after set_dt / before setup_bc_lists (epoch2d.F90:139-146): it
+!     creates the device state from shared_data and uploads fields and particles.
+!   * b200_download is called from output_routines when a dump is due (io/diagnostics.F90:206)
+!     and before any host-side package that walks species_list(:)%attached_list.
+!
+! c_ndims = 2 is written out; the 1D/3D trees differ only in array ranks.
+
+MODULE epoch_b200_mod
+
+  USE, INTRINSIC :: ISO_C_BINDING
+  USE shared_data
+  USE partlist
+
+  IMPLICIT NONE
+
+  ! struct epb_config (include/epoch_b200.h)
+  TYPE, BIND(C) :: epb_config
+    INTEGER(C_INT32_T) :: ndims
+    INTEGER(C_INT32_T) :: n(3)
+    INTEGER(C_INT32_T) :: n_global(3)
+    INTEGER(C_INT32_T) :: ng
+    INTEGER(C_INT32_T) :: bc_field(6)
+    INTEGER(C_INT32_T) :: is_boundary(6)
+    INTEGER(C_INT32_T) :: neighbour(27)
+    INTEGER(C_INT32_T) :: rank, nranks
+    INTEGER(C_INT32_T) :: n_species
+    INTEGER(C_INT32_T) :: strict_fp
+    INTEGER(C_INT32_T) :: sort_interval
+    INTEGER(C_INT32_T) :: reserved(5)
+    REAL(C_DOUBLE) :: dx(3)
+    REAL(C_DOUBLE) :: dt
+    REAL(C_DOUBLE) :: grid_min_local(3)
+    REAL(C_DOUBLE) :: min_local(3)
+    REAL(C_DOUBLE) :: max_local(3)
+    REAL(C_DOUBLE) :: gmin(3), gmax(3)
+    REAL(C_DOUBLE) :: min_outer(3)
+    REAL(C_DOUBLE) :: max_outer(3)
+  END TYPE epb_config
+
+  ! struct epb_species
+  TYPE, BIND(C) :: epb_species
+    REAL(C_DOUBLE) :: charge
+    REAL(C_DOUBLE) :: mass
+    INTEGER(C_INT32_T) :: bc_particle(6)
+    INTEGER(C_INT32_T) :: zero_current
+    INTEGER(C_INT32_T) :: immobile
+    INTEGER(C_INT64_T) :: capacity
+  END TYPE epb_species
+
+  INTEGER, PARAMETER :: epb_ex = 0, epb_ey = 1, epb_ez = 2, epb_bx = 3, epb_by = 4, &
+      epb_bz = 5, epb_jx = 6, epb_jy = 7, epb_jz = 8
+
+  INTERFACE
+    FUNCTION epb_abi_info(info) BIND(C, NAME='epb_abi_info') RESULT(rc)
+      IMPORT :: C_INT, C_INT32_T
+      INTEGER(C_INT32_T) :: info(4)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_create(cfg, species, handle) BIND(C, NAME='epb_create') RESULT(rc)
+      IMPORT :: C_INT, C_PTR, epb_config, epb_species
+      TYPE(epb_config), INTENT(IN) :: cfg
+      TYPE(epb_species), INTENT(IN) :: species(*)
+      TYPE(C_PTR), INTENT(OUT) :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_destroy(handle) BIND(C, NAME='epb_destroy') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_last_error(handle) BIND(C, NAME='epb_last_error') RESULT(msg)
+      IMPORT :: C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      TYPE(C_PTR) :: msg
+    END FUNCTION
+    FUNCTION epb_nccl_unique_id(id) BIND(C, NAME='epb_nccl_unique_id') RESULT(rc)
+      IMPORT :: C_INT, C_CHAR
+      CHARACTER(KIND=C_CHAR) :: id(128)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_set_comm(handle, id) BIND(C, NAME='epb_set_comm') RESULT(rc)
+      IMPORT :: C_INT, C_PTR, C_CHAR
+      TYPE(C_PTR), VALUE :: handle
+      CHARACTER(KIND=C_CHAR) :: id(128)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_upload_field(handle, field, host) BIND(C, NAME='epb_upload_field') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: field
+      TYPE(C_PTR), VALUE :: host
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_download_field(handle, field, host) BIND(C, NAME='epb_download_field') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: field
+      TYPE(C_PTR), VALUE :: host
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_upload_species(handle, ispecies, n, packed) &
+        BIND(C, NAME='epb_upload_species') RESULT(rc)
+      IMPORT :: C_INT, C_INT64_T, C_PTR, C_DOUBLE
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: ispecies
+      INTEGER(C_INT64_T), VALUE :: n
+      REAL(C_DOUBLE), INTENT(IN) :: packed(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_download_species(handle, ispecies, n, packed) &
+        BIND(C, NAME='epb_download_species') RESULT(rc)
+      IMPORT :: C_INT, C_INT64_T, C_PTR, C_DOUBLE
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: ispecies
+      INTEGER(C_INT64_T), VALUE :: n
+      REAL(C_DOUBLE), INTENT(OUT) :: packed(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_species_count(handle, ispecies, n) BIND(C, NAME='epb_species_count') RESULT(rc)
+      IMPORT :: C_INT, C_INT64_T, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: ispecies
+      INTEGER(C_INT64_T), INTENT(OUT) :: n
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_global_count(handle, ispecies, n) BIND(C, NAME='epb_global_count') RESULT(rc)
+      IMPORT :: C_INT, C_INT64_T, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: ispecies
+      INTEGER(C_INT64_T), INTENT(OUT) :: n
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_set_laser_source(handle, side, source1, source2) &
+        BIND(C, NAME='epb_set_laser_source') RESULT(rc)
+      IMPORT :: C_INT, C_PTR, C_DOUBLE
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: side
+      REAL(C_DOUBLE), INTENT(IN) :: source1(*), source2(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_init_boundaries(handle) BIND(C, NAME='epb_init_boundaries') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_fields_half(handle) BIND(C, NAME='epb_fields_half') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_push(handle) BIND(C, NAME='epb_push') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_current_finish(handle) BIND(C, NAME='epb_current_finish') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_fields_final(handle) BIND(C, NAME='epb_fields_final') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+  END INTERFACE
+
+  TYPE(C_PTR), SAVE :: b200 = C_NULL_PTR
+  LOGICAL, SAVE :: b200_fields_on_host = .TRUE.
+
+CONTAINS
+
+  SUBROUTINE b200_check(rc)
+
+    INTEGER(C_INT), INTENT(IN) :: rc
+
+    ! the reference aborts through abort_code (utilities.f90:261-281)
+    IF (rc /= 0) THEN
+      IF (rank == 0) PRINT *, '*** ERROR *** epoch_b200 returned code ', rc
+      errcode = c_err_generic_error
+      CALL abort_code(errcode)
+    END IF
+
+  END SUBROUTINE b200_check
+
+
+
+  ! Build the device state from shared_data (after set_dt, epoch2d.F90:139).
+  SUBROUTINE b200_attach
+
+    TYPE(epb_config) :: cfg
+    TYPE(epb_species), ALLOCATABLE :: sp(:)
+    CHARACTER(KIND=C_CHAR) :: id(128)
+    INTEGER(C_INT32_T) :: info(4)
+    INTEGER :: ispecies, i, ix, iy, ierr
+
+    CALL b200_check(epb_abi_info(info))
+    IF (info(1) /= C_SIZEOF(cfg)) CALL b200_check(1_C_INT)
+
+    cfg%ndims = c_ndims
+    cfg%n = (/ nx, ny, 1 /)
+    cfg%n_global = (/ nx_global, ny_global, 1 /)
+    cfg%ng = ng
+    cfg%bc_field = c_bc_periodic
+    cfg%bc_field(1:2*c_ndims) = bc_field(1:2*c_ndims)
+    cfg%is_boundary = 0
+    IF (x_min_boundary) cfg%is_boundary(1) = 1
+    IF (x_max_boundary) cfg%is_boundary(2) = 1
+    IF (y_min_boundary) cfg%is_boundary(3) = 1
+    IF (y_max_boundary) cfg%is_boundary(4) = 1
+    cfg%neighbour = -1
+    DO iy = -1, 1
+      DO ix = -1, 1
+        ! neighbour(ix,iy) at [(iz+1)*9 + (iy+1)*3 + (ix+1)], iz = 0; MPI_PROC_NULL -> -1
+        i = 9 + (iy + 1) * 3 + (ix + 1) + 1
+        IF (neighbour(ix,iy) /= MPI_PROC_NULL) cfg%neighbour(i) = neighbour(ix,iy)
+      END DO
+    END DO
+    cfg%rank = rank
+    cfg%nranks = nproc
+    cfg%n_species = n_species
+    cfg%strict_fp = 1
+    cfg%sort_interval = 4
+    cfg%reserved = 0
+    cfg%dx = (/ dx, dy, 1.0_num /)
+    cfg%dt = dt
+    cfg%grid_min_local = (/ x_grid_min_local, y_grid_min_local, 0.0_num /)
+    cfg%min_local = (/ x_min_local, y_min_local, 0.0_num /)
+    cfg%max_local = (/ x_max_local, y_max_local, 0.0_num /)
+    cfg%gmin = (/ x_min, y_min, 0.0_num /)
+    cfg%gmax = (/ x_max, y_max, 0.0_num /)
+    cfg%min_outer = (/ x_min_outer, y_min_outer, 0.0_num /)
+    cfg%max_outer = (/ x_max_outer, y_max_outer, 0.0_num /)
+
+    ALLOCATE(sp(n_species))
+    DO ispecies = 1, n_species
+      sp(ispecies)%charge = species_list(ispecies)%charge
+      sp(ispecies)%mass = species_list(ispecies)%mass
+      sp(ispecies)%bc_particle = c_bc_periodic
+      sp(ispecies)%bc_particle(1:2*c_ndims) = species_list(ispecies)%bc_particle(1:2*c_ndims)
+      sp(ispecies)%zero_current = MERGE(1, 0, species_list(ispecies)%zero_current)
+      sp(ispecies)%immobile = MERGE(1, 0, species_list(ispecies)%immobile)
+      ! head-room for migration; the library reports EPB_ERR_CAPACITY if it is exceeded
+      sp(ispecies)%capacity = species_list(ispecies)%attached_list%count * 3 / 2 + 65536
+    END DO
+
+    CALL b200_check(epb_create(cfg, sp, b200))
+    DEALLOCATE(sp)
+
+    IF (nproc > 1) THEN
+      IF (rank == 0) CALL b200_check(epb_nccl_unique_id(id))
+      CALL MPI_BCAST(id, 128, MPI_CHARACTER, 0, comm, ierr)
+      CALL b200_check(epb_set_comm(b200, id))
+    END IF
+
+    CALL b200_upload
+    ! setup_bc_lists + particle_bcs + efield_bcs + bfield_final_bcs(dt/2), epoch2d.F90:144-162
+    CALL b200_push_laser_sources
+    CALL b200_check(epb_init_boundaries(b200))
+
+  END SUBROUTINE b200_attach
+
+
+
+  ! Host arrays / particle lists -> device (also after any host package changed them).
+  SUBROUTINE b200_upload
+
+    REAL(num), ALLOCATABLE, TARGET :: buf(:)
+    TYPE(particle), POINTER :: cur
+    INTEGER(i8) :: npart, ipart
+    INTEGER :: ispecies
+
+    CALL b200_check(epb_upload_field(b200, epb_ex, C_LOC(ex)))
+    CALL b200_check(epb_upload_field(b200, epb_ey, C_LOC(ey)))
+    CALL b200_check(epb_upload_field(b200, epb_ez, C_LOC(ez)))
+    CALL b200_check(epb_upload_field(b200, epb_bx, C_LOC(bx)))
+    CALL b200_check(epb_upload_field(b200, epb_by, C_LOC(by)))
+    CALL b200_check(epb_upload_field(b200, epb_bz, C_LOC(bz)))
+
+    DO ispecies = 1, n_species
+      npart = species_list(ispecies)%attached_list%count
+      ALLOCATE(buf(MAX(npart * nvar, 1_i8)))
+      cur => species_list(ispecies)%attached_list%head
+      ipart = 0
+      DO WHILE (ASSOCIATED(cur))
+        ! wire layout of pack_particle (partlist.F90:414-486)
+        CALL pack_particle(buf(ipart*nvar+1:(ipart+1)*nvar), cur)
+        ipart = ipart + 1
+        cur => cur%next
+      END DO
+      CALL b200_check(epb_upload_species(b200, ispecies - 1, npart, buf))
+      DEALLOCATE(buf)
+    END DO
+
+  END SUBROUTINE b200_upload
+
+
+
+  ! Device -> host arrays and lists (before output_routines or a host-side package).
+  SUBROUTINE b200_download(with_particles)
+
+    LOGICAL, INTENT(IN) :: with_particles
+    REAL(num), ALLOCATABLE, TARGET :: buf(:)
+    TYPE(particle), POINTER :: cur
+    INTEGER(C_INT64_T) :: npart
+    INTEGER(i8) :: ipart
+    INTEGER :: ispecies
+
+    CALL b200_check(epb_download_field(b200, epb_ex, C_LOC(ex)))
+    CALL b200_check(epb_download_field(b200, epb_ey, C_LOC(ey)))
+    CALL b200_check(epb_download_field(b200, epb_ez, C_LOC(ez)))
+    CALL b200_check(epb_download_field(b200, epb_bx, C_LOC(bx)))
+    CALL b200_check(epb_download_field(b200, epb_by, C_LOC(by)))
+    CALL b200_check(epb_download_field(b200, epb_bz, C_LOC(bz)))
+    CALL b200_check(epb_download_field(b200, epb_jx, C_LOC(jx)))
+    CALL b200_check(epb_download_field(b200, epb_jy, C_LOC(jy)))
+    CALL b200_check(epb_download_field(b200, epb_jz, C_LOC(jz)))
+    IF (.NOT. with_particles) RETURN
+
+    DO ispecies = 1, n_species
+      CALL b200_check(epb_species_count(b200, ispecies - 1, npart))
+      ALLOCATE(buf(MAX(npart * nvar, 1_i8)))
+      CALL b200_check(epb_download_species(b200, ispecies - 1, npart, buf))
+      CALL destroy_partlist(species_list(ispecies)%attached_list)
+      CALL create_allocated_partlist(species_list(ispecies)%attached_list, npart)
+      cur => species_list(ispecies)%attached_list%head
+      ipart = 0
+      DO WHILE (ASSOCIATED(cur))
+        CALL unpack_particle(buf(ipart*nvar+1:(ipart+1)*nvar), cur)
+        ipart = ipart + 1
+        cur => cur%next
+      END DO
+      DEALLOCATE(buf)
+    END DO
+
+  END SUBROUTINE b200_download
+
+
+
+  ! The deck expressions of the laser blocks are evaluated on the host exactly as
+  ! outflow_bcs_x_min/x_max do (laser.f90:338-357, 418-437) and the two source lines
+  ! are handed to the device boundary kernel.
+  SUBROUTINE b200_push_laser_sources
+
+    REAL(num), ALLOCATABLE :: source1(:), source2(:)
+    TYPE(laser_block), POINTER :: current
+    REAL(num) :: t_env, base
+    INTEGER :: side, i
+
+    ALLOCATE(source1(0:ny), source2(0:ny))
+    DO side = 0, 1
+      IF (side == 0 .AND. .NOT. x_min_boundary) CYCLE
+      IF (side == 1 .AND. .NOT. x_max_boundary) CYCLE
+      source1 = 0.0_num
+      source2 = 0.0_num
+      IF (add_laser(side + 1)) THEN
+        current => lasers
+        DO WHILE (ASSOCIATED(current))
+          IF (current%boundary == side + 1 &
+              .AND. time >= current%t_start .AND. time <= current%t_end) THEN
+            IF (current%use_phase_function) CALL laser_update_phase(current)
+            IF (current%use_profile_function) CALL laser_update_profile(current)
+            t_env = laser_time_profile(current) * current%amp
+            DO i = 0, ny
+              base = t_env * current%profile(i) &
+                  * SIN(current%current_integral_phase + current%phase(i))
+              source1(i) = source1(i) + base * COS(current%pol_angle)
+              source2(i) = source2(i) + base * SIN(current%pol_angle)
+            END DO
+          END IF
+          current => current%next
+        END DO
+      END IF
+      CALL b200_check(epb_set_laser_source(b200, side, source1, source2))
+    END DO
+    DEALLOCATE(source1, source2)
+
+  END SUBROUTINE b200_push_laser_sources
+
+END MODULE epoch_b200_mod
+
+
+#ifdef EPOCH_B200
+! Replacement bodies (each goes into the module that owns the routine):
+
+!   MODULE fields
+!     SUBROUTINE update_eb_fields_half
+!       CALL b200_check(epb_fields_half(b200))
+!     END SUBROUTINE
+!     SUBROUTINE update_eb_fields_final
+!       CALL update_laser_omegas                 ! laser.f90:253-269 (host state)
+!       CALL b200_push_laser_sources             ! sources at time = (k + 1/2) dt
+!       CALL b200_check(epb_fields_final(b200))
+!     END SUBROUTINE
+!
+!   MODULE particles
+!     SUBROUTINE push_particles
+!       CALL b200_check(epb_push(b200))          ! zero J, push, deposit, particle_bcs, migration
+!     END SUBROUTINE
+!
+!   MODULE current_smooth
+!     SUBROUTINE current_finish
+!       CALL b200_check(epb_current_finish(b200))
+!     END SUBROUTINE
+!
+!   MODULE partlist
+!     SUBROUTINE update_particle_count           ! partlist.F90:984-1003
+!       DO ispecies = 1, n_species
+!         CALL b200_check(epb_global_count(b200, ispecies - 1, species_list(ispecies)%count))
+!       END DO
+!     END SUBROUTINE
+#endif
