@@ -358,38 +358,107 @@ __global__ void __launch_bounds__(256) push_generic(const __grid_constant__ Push
 // ---------------------------------------------------------------------------
 // Tiled 2D kernel
 // ---------------------------------------------------------------------------
+// One CTA per 16x16-cell tile of the cell-sorted layout, two CTAs per SM.  Shared memory:
+//   sF  [6][TH][TW]   E/B tile + 3 halo cells
+//   sJ  [3][TH][TW]   current accumulated by this CTA, flushed once with global reductions
+//   sS  [warp][27][33] per-warp transposition scratch for the deposit reduction
+//   sQ* [warp][...]    per-warp queue of particles that changed their nearest cell this step
+//   sSlow             CTA list of particles outside the tile's halo (stale sort, wrapped)
+// The 32 lanes of a warp hold 32 consecutive particles of the sorted range, i.e. mostly one
+// or two cells.  Each lane writes its 27 deposit values (3 components x 3x3 cells around its
+// nearest cell) to a column of sS; lane q < 27 then sums row q over the lanes that share a
+// cell key and issues ONE shared-memory update per key (shared FP64 atomicAdd is a CAS loop
+// on sm_100a, so updates per particle are what must be avoided).  The cost is independent of
+// how many distinct cells the warp spans, which keeps the kernel efficient between sorts.
+// Particles whose nearest cell changed during the step (a few %) have a wider stencil: they
+// are queued and deposited densely, 32 at a time, with the reference's general loop.
 constexpr int T2X = 16, T2Y = 16, HALO = 3;
 constexpr int TW = T2X + 2 * HALO, TH = T2Y + 2 * HALO;
 constexpr int TILE_ELEMS = TW * TH;
-constexpr int PUSH2D_THREADS = 256;
-constexpr size_t PUSH2D_SMEM = (size_t)9 * TILE_ELEMS * sizeof(double);
+constexpr int PUSH2D_THREADS = 256, PUSH2D_WARPS = PUSH2D_THREADS / 32;
+constexpr int SROWS = 27, SPITCH = 33;
+constexpr int QCAP = 32, QDBL = 7;
+constexpr int SLOWCAP = 510;
+constexpr size_t PUSH2D_SMEM =
+    sizeof(double) * ((size_t)9 * TILE_ELEMS + (size_t)PUSH2D_WARPS * SROWS * SPITCH + (size_t)PUSH2D_WARPS * QDBL * QCAP) +
+    sizeof(int) * ((size_t)PUSH2D_WARPS * QCAP + SLOWCAP + 2);
 
 __device__ __forceinline__ void smem_add(double *addr, double v) {
-  // shared FP64 add: compiles to an ATOMS.CAST.SPIN loop; conflicts between warps are rare
+  // shared FP64 add: an ATOMS.CAST.SPIN loop; conflicts between warps are rare
   atomicAdd(addr, v);
 }
 
-// sum v[0..26] of the lanes in `grp` (others pass zeros); lane L returns the total of v[L]
-__device__ __forceinline__ double warp_transpose_reduce27(double (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int q = 0; q < s; q++) {
-      double a = v[q], b = v[q + s];
-      double send = up ? a : b;
-      double keep = up ? b : a;
-      v[q] = keep + __shfl_xor_sync(FULL, send, s);
-    }
-  }
-  return v[0];
+// 1/sqrt(s) and friends.  The parity build keeps the reference's sqrt + divide sequence.
+__device__ __forceinline__ void gamma_root(double s, double num, double &root) {
+#ifdef EPB_FAST_MATH
+  root = num * rsqrt(s);
+#else
+  root = num / sqrt(s);
+#endif
 }
 
-template <bool REDUCE>
+// Deposit of queued particles (nearest cell changed: dcell != 0 in x and/or y): the general
+// loop of particles.F90:549-579 over xmin..xmax, ymin..ymax with shared-memory updates.
+__device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, const double *Qd, const int *Qk,
+                                             int n, int lane) {
+  if (lane >= n) return;
+  const int pk = Qk[lane];
+  const int key = pk & 1023, dcx = ((pk >> 10) & 3) - 1, dcy = ((pk >> 12) & 3) - 1;
+  const double fjx = Qd[4 * QCAP + lane], fjy = Qd[5 * QCAP + lane], fjz = Qd[6 * QCAP + lane];
+  double gx[5], gy[5], hx[5], hy[5];
+  gx[0] = gx[4] = gy[0] = gy[4] = 0.0;
+  tri(Qd[0 * QCAP + lane], gx[1], gx[2], gx[3]);
+  tri(Qd[2 * QCAP + lane], gy[1], gy[2], gy[3]);
+  double wm, w0, wp;
+  tri(Qd[1 * QCAP + lane], wm, w0, wp);
+#pragma unroll
+  for (int q = 0; q < 5; q++) {
+    const int r = q - 2 - dcx;
+    hx[q] = ((r == -1) ? wm : (r == 0) ? w0 : (r == 1) ? wp : 0.0) - gx[q];
+  }
+  tri(Qd[3 * QCAP + lane], wm, w0, wp);
+#pragma unroll
+  for (int q = 0; q < 5; q++) {
+    const int r = q - 2 - dcy;
+    hy[q] = ((r == -1) ? wm : (r == 0) ? w0 : (r == 1) ? wp : 0.0) - gy[q];
+  }
+  const int xmin = -1 + (dcx - 1) / 2, xmax = 1 + (dcx + 1) / 2;
+  const int ymin = -1 + (dcy - 1) / 2, ymax = 1 + (dcy + 1) / 2;
+  const double third = P.third;
+  double jyh[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int iy = -2; iy <= 2; iy++) {
+    if (iy < ymin || iy > ymax) continue;
+    const double yfac1 = gy[iy + 2] + 0.5 * hy[iy + 2];
+    const double yfac2 = third * hy[iy + 2] + 0.5 * gy[iy + 2];
+    double jxh = 0.0;
+#pragma unroll
+    for (int ix = -2; ix <= 2; ix++) {
+      if (ix < xmin || ix > xmax) continue;
+      const double xfac1 = gx[ix + 2] + 0.5 * hx[ix + 2];
+      const double wx = hx[ix + 2] * yfac1;
+      const double wy = hy[iy + 2] * xfac1;
+      const double wz = gx[ix + 2] * yfac1 + hx[ix + 2] * yfac2;
+      jxh = jxh - fjx * wx;
+      jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+      const double jzh = fjz * wz;
+      const int o = key + iy * TW + ix;
+      smem_add(&sJ[o], jxh);
+      smem_add(&sJ[TILE_ELEMS + o], jyh[ix + 2]);
+      smem_add(&sJ[2 * TILE_ELEMS + o], jzh);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_constant__ PushParams P) {
   extern __shared__ double sm[];
-  double *sF = sm;                     // [6][TH][TW]
-  double *sJ = sm + 6 * TILE_ELEMS;    // [3][TH][TW]
+  double *sF = sm;                                   // [6][TH][TW]
+  double *sJ = sF + 6 * TILE_ELEMS;                  // [3][TH][TW]
+  double *sS_all = sJ + 3 * TILE_ELEMS;              // [warps][27][33]
+  double *sQd_all = sS_all + PUSH2D_WARPS * SROWS * SPITCH;
+  int *sQk_all = reinterpret_cast<int *>(sQd_all + PUSH2D_WARPS * QDBL * QCAP);
+  int *sSlow = sQk_all + PUSH2D_WARPS * QCAP;
+  int *sSlowCount = sSlow + SLOWCAP;
   const int tile = blockIdx.x;
   const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
   const int ox = ttx * T2X + 1 - HALO;  // cell index of shared column 0
@@ -398,7 +467,8 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
   long long end = P.tile_start[tile + 1];
   if (end > P.n_sorted_clip) end = P.n_sorted_clip;
   if (start >= end) return;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *sSlowCount = 0;
   for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
     const int lx = q % TW, ly = q / TW;
     const int cx = ox + lx, cy = oy + ly;
@@ -417,263 +487,240 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
   const double third = P.third;
   const double *sEx = sF, *sEy = sF + TILE_ELEMS, *sEz = sF + 2 * TILE_ELEMS;
   const double *sBx = sF + 3 * TILE_ELEMS, *sBy = sF + 4 * TILE_ELEMS, *sBz = sF + 5 * TILE_ELEMS;
+  double *S = sS_all + warp * SROWS * SPITCH;
+  double *Qd = sQd_all + warp * QDBL * QCAP;
+  int *Qk = sQk_all + warp * QCAP;
+  int qcount = 0;  // warp-uniform
+  // lane q < 27 owns deposit value q = comp*9 + iy*3 + ix of the 3x3 stencil
+  const int offq = (lane / 9) * TILE_ELEMS + ((lane % 9) / 3 - 1) * TW + (lane % 3 - 1);
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (long long base = start; base < end; base += PUSH2D_THREADS) {
-    const long long i = base + tid;
+  // software pipeline: the next batch's particle loads are in flight while this one computes
+  long long i = start + warp * 32 + lane;
+  double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
+  if (i < end) {
+    n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
+    n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
+  }
+  for (; i - lane < end; i += PUSH2D_THREADS) {
     const bool active = i < end;
-    bool fast = false;
-    int cx1 = 0, cy1 = 0;
-    double part_weight = 0.0;
-    double px_ = 0, py_ = 0, part_ux = 0, part_uy = 0, part_uz = 0;
-    if (active) {
-      part_weight = P.w[i];
-      px_ = P.x[0][i] - P.grid_min_local[0];
-      py_ = P.x[1][i] - P.grid_min_local[1];
-      part_ux = P.p[0][i] * P.ipart_mc;
-      part_uy = P.p[1][i] * P.ipart_mc;
-      part_uz = P.p[2][i] * P.ipart_mc;
+    const double part_weight = n_w;
+    double px_ = n_x - P.grid_min_local[0];
+    double py_ = n_y - P.grid_min_local[1];
+    double part_ux = n_px * P.ipart_mc;
+    double part_uy = n_py * P.ipart_mc;
+    double part_uz = n_pz * P.ipart_mc;
+    {
+      const long long in = i + PUSH2D_THREADS;
+      if (in < end) {
+        n_w = P.w[in]; n_x = P.x[0][in]; n_y = P.x[1][in];
+        n_px = P.p[0][in]; n_py = P.p[1][in]; n_pz = P.p[2][in];
+      }
     }
-    double cell_x_r = 0, cell_y_r = 0;
+    int key = -1;       // cell key of a lane that takes part in the transposed reduction
+    bool extras = false;
+    int dcx = 0, dcy = 0;
+    double q_fxo = 0, q_fxn = 0, q_fyo = 0, q_fyn = 0, fjx = 0, fjy = 0, fjz = 0;
     if (active) {
-      double gamma_rel = sqrt(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0);
-      double root = P.dtco2 / gamma_rel;
+      double root;
+      gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
       px_ = px_ + part_ux * root;
       py_ = py_ + part_uy * root;
-      cell_x_r = px_ * P.idx[0];
-      cell_y_r = py_ * P.idx[1];
-      cx1 = __double2int_rd(cell_x_r + 0.5) + 1;
-      cy1 = __double2int_rd(cell_y_r + 0.5) + 1;
+      const double cell_x_r = px_ * P.idx[0];
+      const double cell_y_r = py_ * P.idx[1];
+      const int cx1 = __double2int_rd(cell_x_r + 0.5) + 1;
+      const int cy1 = __double2int_rd(cell_y_r + 0.5) + 1;
       // the gather reads cell1-2..cell1+1, the deposit writes cell1-2..cell1+2
-      fast = (cx1 - 2 >= ox) && (cx1 + 2 <= ox + TW - 1) && (cy1 - 2 >= oy) && (cy1 + 2 <= oy + TH - 1);
-      if (!fast) push_one<2>(P, i);
-    }
-    double v[32];
-#pragma unroll
-    for (int q = 0; q < 32; q++) v[q] = 0.0;
-    int dcx = 0, dcy = 0;
-    // values the rare extra-row/column path needs
-    double fjx = 0, fjy = 0, fjz = 0, hxm2 = 0, hxp2 = 0, hym2 = 0, hyp2 = 0;
-    double gxa[3] = {0, 0, 0}, gya[3] = {0, 0, 0}, hxa[3] = {0, 0, 0}, hya[3] = {0, 0, 0};
-    if (fast) {
-      double gx[3], gy[3], hx[3], hy[3];
-      tri((double)(cx1 - 1) - cell_x_r, gx[0], gx[1], gx[2]);
-      tri((double)(cy1 - 1) - cell_y_r, gy[0], gy[1], gy[2]);
-      int cx2 = __double2int_rd(cell_x_r);
-      tri((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
-      cx2 += 1;
-      int cy2 = __double2int_rd(cell_y_r);
-      tri((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
-      cy2 += 1;
-      // shared-tile offsets of (cell-1, cell-1)
-      const int o11 = (cy1 - 1 - oy) * TW + (cx1 - 1 - ox);
-      const int o21 = (cy1 - 1 - oy) * TW + (cx2 - 1 - ox);
-      const int o12 = (cy2 - 1 - oy) * TW + (cx1 - 1 - ox);
-      const int o22 = (cy2 - 1 - oy) * TW + (cx2 - 1 - ox);
-      auto gat = [&](const double *F, int o, const double *wx, const double *wy) {
-        double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
-        double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
-        double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
-        return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
-      };
-      const double ex_part = gat(sEx, o21, hx, gy);
-      const double ey_part = gat(sEy, o12, gx, hy);
-      const double ez_part = gat(sEz, o11, gx, gy);
-      const double bx_part = gat(sBx, o12, gx, hy);
-      const double by_part = gat(sBy, o21, hx, gy);
-      const double bz_part = gat(sBz, o22, hx, hy);
-      const double cmratio = P.cmratio;
-      double uxm = part_ux + cmratio * ex_part;
-      double uym = part_uy + cmratio * ey_part;
-      double uzm = part_uz + cmratio * ez_part;
-      double gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
-      double root = P.ccmratio / gamma_rel;
-      double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
-      double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
-      double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
-      double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
-                    2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
-      double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
-                    2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
-      double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
-                    2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
-      part_ux = uxp + cmratio * ex_part;
-      part_uy = uyp + cmratio * ey_part;
-      part_uz = uzp + cmratio * ez_part;
-      double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
-      gamma_rel = sqrt(part_u2 + 1.0);
-      double igamma = 1.0 / gamma_rel;
-      root = P.dtco2 * igamma;
-      const double delta_x = part_ux * root;
-      const double delta_y = part_uy * root;
-      const double part_vz = part_uz * c * igamma;
-      px_ = px_ + delta_x;
-      py_ = py_ + delta_y;
-      {
-        double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
-        double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
-        int dir = particle_bc<2>(P, pos, mom);
-        P.x[0][i] = pos[0];
-        P.x[1][i] = pos[1];
-        P.p[0][i] = mom[0];
-        P.p[1][i] = mom[1];
-        P.p[2][i] = mom[2];
-        if (dir >= 0) outbox_put(P, i, dir);
-      }
-      if (P.deposit) {
+      const bool fast = (cx1 - 2 >= ox) && (cx1 + 2 <= ox + TW - 1) && (cy1 - 2 >= oy) && (cy1 + 2 <= oy + TH - 1);
+      if (!fast) {
+        const int slot = atomicAdd(sSlowCount, 1);
+        if (slot < SLOWCAP) sSlow[slot] = (int)i;
+        else push_one<2>(P, i);
+      } else {
+        double gx[3], gy[3], hx[3], hy[3];
+        const double fxo = (double)(cx1 - 1) - cell_x_r, fyo = (double)(cy1 - 1) - cell_y_r;
+        tri(fxo, gx[0], gx[1], gx[2]);
+        tri(fyo, gy[0], gy[1], gy[2]);
+        int cx2 = __double2int_rd(cell_x_r);
+        tri((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
+        cx2 += 1;
+        int cy2 = __double2int_rd(cell_y_r);
+        tri((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
+        cy2 += 1;
+        // shared-tile offsets of (cell-1, cell-1)
+        const int o11 = (cy1 - 1 - oy) * TW + (cx1 - 1 - ox);
+        const int o21 = (cy1 - 1 - oy) * TW + (cx2 - 1 - ox);
+        const int o12 = (cy2 - 1 - oy) * TW + (cx1 - 1 - ox);
+        const int o22 = (cy2 - 1 - oy) * TW + (cx2 - 1 - ox);
+        auto gat = [&](const double *F, int o, const double *wx, const double *wy) {
+          double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
+          double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
+          double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
+          return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
+        };
+        const double ex_part = gat(sEx, o21, hx, gy);
+        const double ey_part = gat(sEy, o12, gx, hy);
+        const double ez_part = gat(sEz, o11, gx, gy);
+        const double bx_part = gat(sBx, o12, gx, hy);
+        const double by_part = gat(sBy, o21, hx, gy);
+        const double bz_part = gat(sBz, o22, hx, hy);
+        const double cmratio = P.cmratio;
+        const double uxm = part_ux + cmratio * ex_part;
+        const double uym = part_uy + cmratio * ey_part;
+        const double uzm = part_uz + cmratio * ez_part;
+        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+        const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+        const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+        const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+        const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                            2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+        const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                            2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+        const double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                            2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+        part_ux = uxp + cmratio * ex_part;
+        part_uy = uyp + cmratio * ey_part;
+        part_uz = uzp + cmratio * ez_part;
+        const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+#ifdef EPB_FAST_MATH
+        const double igamma = rsqrt(part_u2 + 1.0);
+#else
+        const double igamma = 1.0 / sqrt(part_u2 + 1.0);
+#endif
+        root = P.dtco2 * igamma;
+        const double delta_x = part_ux * root;
+        const double delta_y = part_uy * root;
+        const double part_vz = part_uz * c * igamma;
         px_ = px_ + delta_x;
         py_ = py_ + delta_y;
-        const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
-        const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
-        double wxm, wx0, wxp, wym, wy0, wyp;
-        tri((double)cx3 - cxr, wxm, wx0, wxp);
-        tri((double)cy3 - cyr, wym, wy0, wyp);
-        dcx = cx3 + 1 - cx1;
-        dcy = cy3 + 1 - cy1;
-        // hx(-2..2) = shifted new weights - gx (particles.F90:521-538)
-        hxm2 = (dcx == -1) ? wxm : 0.0;
-        hxp2 = (dcx == 1) ? wxp : 0.0;
-        hx[0] = ((dcx == -1) ? wx0 : (dcx == 0) ? wxm : 0.0) - gx[0];
-        hx[1] = ((dcx == -1) ? wxp : (dcx == 0) ? wx0 : wxm) - gx[1];
-        hx[2] = ((dcx == 0) ? wxp : (dcx == 1) ? wx0 : 0.0) - gx[2];
-        hym2 = (dcy == -1) ? wym : 0.0;
-        hyp2 = (dcy == 1) ? wyp : 0.0;
-        hy[0] = ((dcy == -1) ? wy0 : (dcy == 0) ? wym : 0.0) - gy[0];
-        hy[1] = ((dcy == -1) ? wyp : (dcy == 0) ? wy0 : wym) - gy[1];
-        hy[2] = ((dcy == 0) ? wyp : (dcy == 1) ? wy0 : 0.0) - gy[2];
-        const double fcx = P.kfc[0] * part_weight;
-        const double fcy = P.kfc[1] * part_weight;
-        const double fcz = P.kfc[2] * part_weight;
-        fjx = fcx * P.part_q;
-        fjy = fcy * P.part_q;
-        fjz = fcz * P.part_q * part_vz;
-        double xfac1[3];
+        {
+          double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
+          double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
+          const int dir = particle_bc<2>(P, pos, mom);
+          P.x[0][i] = pos[0];
+          P.x[1][i] = pos[1];
+          P.p[0][i] = mom[0];
+          P.p[1][i] = mom[1];
+          P.p[2][i] = mom[2];
+          if (dir >= 0) outbox_put(P, i, dir);
+        }
+        if (P.deposit) {
+          px_ = px_ + delta_x;
+          py_ = py_ + delta_y;
+          const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
+          const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
+          const double fxn = (double)cx3 - cxr, fyn = (double)cy3 - cyr;
+          dcx = cx3 + 1 - cx1;
+          dcy = cy3 + 1 - cy1;
+          const double fcx = P.kfc[0] * part_weight;
+          const double fcy = P.kfc[1] * part_weight;
+          const double fcz = P.kfc[2] * part_weight;
+          fjx = fcx * P.part_q;
+          fjy = fcy * P.part_q;
+          fjz = fcz * P.part_q * part_vz;
+          const int k = (cy1 - oy) * TW + (cx1 - ox);
+          if ((dcx | dcy) != 0) {
+            extras = true;
+            key = k;  // kept for the queue entry; excluded from the reduction below
+            q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          } else {
+            key = k;
+            // dcell = 0: hx = new weights - gx on the same three cells (particles.F90:521-538)
+            tri(fxn, hx[0], hx[1], hx[2]);
+            tri(fyn, hy[0], hy[1], hy[2]);
 #pragma unroll
-        for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
-        // row iy=-2 precedes the core rows in the running jyh(ix) sums (only when dcy=-1;
-        // otherwise hy(-2)=0 and this is 0 - 0)
-        double jyh[3];
+            for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
+            double xfac1[3], jyh[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int ix = 0; ix < 3; ix++) jyh[ix] = 0.0 - fjy * (hym2 * xfac1[ix]);
+            for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
+            double *col = S + lane;
 #pragma unroll
-        for (int iy = 0; iy < 3; iy++) {
-          const double yfac1 = gy[iy] + 0.5 * hy[iy];
-          const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
-          // column ix=-2 precedes the core columns in the running jxh sum
-          double jxh = 0.0 - fjx * (hxm2 * yfac1);
+            for (int iy = 0; iy < 3; iy++) {
+              const double yfac1 = gy[iy] + 0.5 * hy[iy];
+              const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+              double jxh = 0.0;
 #pragma unroll
-          for (int ix = 0; ix < 3; ix++) {
-            const double wx = hx[ix] * yfac1;
-            const double wy = hy[iy] * xfac1[ix];
-            const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
-            jxh = jxh - fjx * wx;
-            jyh[ix] = jyh[ix] - fjy * wy;
-            v[iy * 3 + ix] = jxh;
-            v[9 + iy * 3 + ix] = jyh[ix];
-            v[18 + iy * 3 + ix] = fjz * wz;
+              for (int ix = 0; ix < 3; ix++) {
+                const double wx = hx[ix] * yfac1;
+                const double wy = hy[iy] * xfac1[ix];
+                const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
+                jxh = jxh - fjx * wx;
+                jyh[ix] = jyh[ix] - fjy * wy;
+                col[(iy * 3 + ix) * SPITCH] = jxh;
+                col[(9 + iy * 3 + ix) * SPITCH] = jyh[ix];
+                col[(18 + iy * 3 + ix) * SPITCH] = fjz * wz;
+              }
+            }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 3; q++) { gxa[q] = gx[q]; gya[q] = gy[q]; hxa[q] = hx[q]; hya[q] = hy[q]; }
       }
     }
     if (!P.deposit) continue;
-    const bool dep = fast;
-    if (REDUCE) {
-      // cell-ordered lanes: sum per distinct cell across the warp, 27 lanes update shared J
-      const int key = dep ? ((cy1 - oy) * TW + (cx1 - ox)) : -1;
-      unsigned todo = __ballot_sync(FULL, key >= 0);
-      int iter = 0;
-      while (todo) {
-        if (iter == 3) {
-          // many distinct cells in this warp (stale sort): remaining lanes update individually
-          if (key >= 0 && ((todo >> lane) & 1u)) {
-#pragma unroll
-            for (int q = 0; q < 27; q++)
-              smem_add(&sJ[(q / 9) * TILE_ELEMS + key + ((q % 9) / 3 - 1) * TW + (q % 3 - 1)], v[q]);
-          }
-          break;
-        }
-        const int leader = __ffs(todo) - 1;
-        const int k = __shfl_sync(FULL, key, leader);
-        const bool mine = (key == k);
-        const unsigned grp = __ballot_sync(FULL, mine);
-        double r[32];
-#pragma unroll
-        for (int q = 0; q < 32; q++) r[q] = mine ? v[q] : 0.0;
-        const double tot = warp_transpose_reduce27(r, lane);
-        if (lane < 27)
-          smem_add(&sJ[(lane / 9) * TILE_ELEMS + k + ((lane % 9) / 3 - 1) * TW + (lane % 3 - 1)], tot);
-        todo &= ~grp;
-        iter++;
+    // ---- queue the particles with a wider stencil -------------------------------------
+    const unsigned em = __ballot_sync(FULL, extras);
+    if (em) {
+      const int ne = __popc(em);
+      if (qcount + ne > QCAP) {
+        __syncwarp();
+        drain_extras(P, sJ, Qd, Qk, qcount, lane);
+        __syncwarp();
+        qcount = 0;
       }
-    } else {
-      if (dep) {
-        const int key = (cy1 - oy) * TW + (cx1 - ox);
+      if (extras) {
+        const int slot = qcount + __popc(em & lt_mask);
+        Qk[slot] = key | ((dcx + 1) << 10) | ((dcy + 1) << 12);
+        Qd[0 * QCAP + slot] = q_fxo; Qd[1 * QCAP + slot] = q_fxn;
+        Qd[2 * QCAP + slot] = q_fyo; Qd[3 * QCAP + slot] = q_fyn;
+        Qd[4 * QCAP + slot] = fjx; Qd[5 * QCAP + slot] = fjy; Qd[6 * QCAP + slot] = fjz;
+        key = -1;
+      }
+      qcount += ne;
+    }
+    // ---- transposed reduction: one shared update per (cell key, stencil value) ------------
+    __syncwarp();
+    unsigned rest = __ballot_sync(FULL, key >= 0);
+    if (rest) {
+      const int k0 = __shfl_sync(FULL, key, __ffs(rest) - 1);
+      const unsigned m0 = __ballot_sync(FULL, key == k0);
+      rest &= ~m0;
+      int k1 = 0;
+      unsigned m1 = 0;
+      if (rest) {
+        k1 = __shfl_sync(FULL, key, __ffs(rest) - 1);
+        m1 = __ballot_sync(FULL, key == k1);
+        rest &= ~m1;
+      }
+      if (lane < SROWS) {
+        const double *row = S + lane * SPITCH;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 27; q++)
-          smem_add(&sJ[(q / 9) * TILE_ELEMS + key + ((q % 9) / 3 - 1) * TW + (q % 3 - 1)], v[q]);
+        for (int j = 0; j < 32; j++) {
+          const double v = row[j];
+          if ((m0 >> j) & 1u) a0 += v;
+          else if ((m1 >> j) & 1u) a1 += v;
+        }
+        smem_add(&sJ[offq + k0], a0);
+        if (m1) smem_add(&sJ[offq + k1], a1);
+      }
+      while (rest) {  // lanes in further cells (stale sort): one update per lane and value
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int kj = __shfl_sync(FULL, key, j);
+        if (lane < SROWS) smem_add(&sJ[offq + kj], S[lane * SPITCH + j]);
       }
     }
-    // extra column / row / corner when the particle changed its nearest cell (rare)
-    if (dep && (dcx != 0 || dcy != 0)) {
-      const int key = (cy1 - oy) * TW + (cx1 - ox);
-      double yfac1[3], yfac2[3], xfac1[3];
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        yfac1[q] = gya[q] + 0.5 * hya[q];
-        yfac2[q] = third * hya[q] + 0.5 * gya[q];
-        xfac1[q] = gxa[q] + 0.5 * hxa[q];
-      }
-      const double hxe = (dcx < 0) ? hxm2 : hxp2;   // hx(+-2); gx(+-2) = 0
-      const double hye = (dcy < 0) ? hym2 : hyp2;
-      const double xfac1e = 0.5 * hxe;              // gx(+-2) + 0.5*hx(+-2)
-      const double yfac1e = 0.5 * hye;
-      const double yfac2e = third * hye;            // third*hy + 0.5*gy(+-2)
-      double col_jy_last = 0.0, row_jx_last = 0.0;
-      if (dcx != 0) {
-        const int ixe = 2 * dcx;
-        double jyrun = 0.0 - fjy * (hym2 * xfac1e);
-#pragma unroll
-        for (int iy = 0; iy < 3; iy++) {
-          const double jxv = (dcx < 0) ? (0.0 - fjx * (hxe * yfac1[iy]))
-                                       : (v[iy * 3 + 2] - fjx * (hxe * yfac1[iy]));
-          jyrun = jyrun - fjy * (hya[iy] * xfac1e);
-          const double jzv = fjz * (hxe * yfac2[iy]);
-          const int o = key + (iy - 1) * TW + ixe;
-          smem_add(&sJ[o], jxv);
-          smem_add(&sJ[TILE_ELEMS + o], jyrun);
-          smem_add(&sJ[2 * TILE_ELEMS + o], jzv);
-        }
-        col_jy_last = jyrun;
-      }
-      if (dcy != 0) {
-        const int iye = 2 * dcy;
-        double jxh = 0.0 - fjx * (hxm2 * yfac1e);
-#pragma unroll
-        for (int ix = 0; ix < 3; ix++) {
-          jxh = jxh - fjx * (hxa[ix] * yfac1e);
-          const double jyv = (dcy < 0) ? (0.0 - fjy * (hye * xfac1[ix]))
-                                       : (v[9 + 6 + ix] - fjy * (hye * xfac1[ix]));
-          const double jzv = fjz * (gxa[ix] * yfac1e + hxa[ix] * yfac2e);
-          const int o = key + iye * TW + (ix - 1);
-          smem_add(&sJ[o], jxh);
-          smem_add(&sJ[TILE_ELEMS + o], jyv);
-          smem_add(&sJ[2 * TILE_ELEMS + o], jzv);
-        }
-        row_jx_last = jxh;
-      }
-      if (dcx != 0 && dcy != 0) {
-        const int o = key + 2 * dcy * TW + 2 * dcx;
-        const double jxv = (dcx < 0) ? (0.0 - fjx * (hxe * yfac1e)) : (row_jx_last - fjx * (hxe * yfac1e));
-        const double jyv = (dcy < 0) ? (0.0 - fjy * (hye * xfac1e)) : (col_jy_last - fjy * (hye * xfac1e));
-        const double jzv = fjz * (hxe * yfac2e);
-        smem_add(&sJ[o], jxv);
-        smem_add(&sJ[TILE_ELEMS + o], jyv);
-        smem_add(&sJ[2 * TILE_ELEMS + o], jzv);
-      }
-    }
+    __syncwarp();
+  }
+  if (qcount) {
+    __syncwarp();
+    drain_extras(P, sJ, Qd, Qk, qcount, lane);
   }
   __syncthreads();
+  {
+    int ns = *sSlowCount;
+    if (ns > SLOWCAP) ns = SLOWCAP;
+    for (int q = tid; q < ns; q += PUSH2D_THREADS) push_one<2>(P, sSlow[q]);
+  }
   for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
     const int lx = q % TW, ly = q / TW;
     const int cx = ox + lx, cy = oy + ly;
@@ -692,12 +739,11 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
   static bool attr_set = false;
   if (tiled && nd == 2) {
     if (!attr_set) {
-      cudaFuncSetAttribute(push_tiled_2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
-      cudaFuncSetAttribute(push_tiled_2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
       attr_set = true;
     }
     if (P.tg.ntiles > 0) {
-      push_tiled_2d<true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
+      push_tiled_2d<<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
       (*launches)++;
     }
     return;
