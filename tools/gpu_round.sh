@@ -29,5 +29,8 @@ ncu)
       -f -o gpurun_out/prof_push python bench.py --n 2048 --steps 2 --warmup 3 --no-cpu-baseline \
       > gpurun_out/ncu_push.log 2>&1
   echo "ncu rc=$?" ;;
+micro)
+  (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu) > gpurun_out/micro_build.log 2>&1
+  timeout 300 tools/microbench > gpurun_out/microbench.json 2>&1; cat gpurun_out/microbench.json ;;
 esac
 done
