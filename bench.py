@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=4096, help="cells per side per GPU")
+    ap.add_argument("--cells", dest="n", type=int, default=4096, help="cells per side per GPU")
     ap.add_argument("--ppc", type=int, default=64)
     ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "4")))
     ap.add_argument("--strict", type=int, default=0)

@@ -21,14 +21,22 @@ benchref)
   cat gpurun_out/bench_ref.json ;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --n 2048 --steps 4 --warmup 3 --no-cpu-baseline \
+      --log-file gpurun_out/launches.csv python bench.py --cells 2048 --steps 4 --warmup 3 --no-cpu-baseline \
       > gpurun_out/launches_bench.log 2>&1
   echo "launches rc=$?" ;;
 ncu)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:push_tiled -s 3 -c 2 \
-      -f -o gpurun_out/prof_push python bench.py --n 2048 --steps 2 --warmup 3 --no-cpu-baseline \
+      -f -o gpurun_out/prof_push python bench.py --cells 2048 --steps 2 --warmup 3 --no-cpu-baseline \
       > gpurun_out/ncu_push.log 2>&1
   echo "ncu rc=$?" ;;
+multi)
+  timeout 1500 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/pytest_multi.log 2>&1
+  echo "pytest multi rc=$?" >> gpurun_out/pytest_multi.log; tail -30 gpurun_out/pytest_multi.log ;;
+benchN)
+  NG=$(nvidia-smi -L | wc -l)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $NG --cells ${BENCH_N:-2048} --steps 8 --warmup 3 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
+  echo "benchN rc=$?"; cat gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err ;;
 micro)
   (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu) > gpurun_out/micro_build.log 2>&1
   timeout 300 tools/microbench > gpurun_out/microbench.json 2>&1; cat gpurun_out/microbench.json ;;
