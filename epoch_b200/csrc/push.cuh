@@ -384,11 +384,14 @@ constexpr int TW = T2X + 2 * HALO, TH = T2Y + 2 * HALO;
 constexpr int TILE_ELEMS = TW * TH;
 constexpr int PUSH2D_THREADS = 256, PUSH2D_WARPS = PUSH2D_THREADS / 32;
 constexpr int SPAIRS = 14, SPITCH = 33;
+// sJ is padded (row pitch 29, component stride 649 doubles) so that the 27 addresses of one
+// flush fall into distinct 8-byte banks at most twice
+constexpr int JP = 29, JC = 633;
 constexpr int QCAP = 32;
-constexpr int SLOWCAP = 510;
+constexpr int SLOWCAP = 254;
 constexpr size_t PUSH2D_SMEM =
     sizeof(double2) * ((size_t)2 * TILE_ELEMS + (size_t)PUSH2D_WARPS * SPAIRS * SPITCH + (size_t)PUSH2D_WARPS * 4 * QCAP) +
-    sizeof(double) * ((size_t)5 * TILE_ELEMS) + sizeof(int) * (SLOWCAP + 2);
+    sizeof(double) * ((size_t)2 * TILE_ELEMS + 3 * JC) + sizeof(int) * (SLOWCAP + 2);
 
 __device__ __forceinline__ void smem_add(double *addr, double v) {
   // shared FP64 add: an ATOMS.CAST.SPIN loop; conflicts between warps are rare
@@ -449,10 +452,10 @@ __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, co
       jxh = jxh - fjx * wx;
       jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
       const double jzh = fjz * wz;
-      const int o = key + iy * TW + ix;
+      const int o = key + iy * JP + ix;
       smem_add(&sJ[o], jxh);
-      smem_add(&sJ[TILE_ELEMS + o], jyh[ix + 2]);
-      smem_add(&sJ[2 * TILE_ELEMS + o], jzh);
+      smem_add(&sJ[JC + o], jyh[ix + 2]);
+      smem_add(&sJ[2 * JC + o], jzh);
     }
   }
 }
@@ -470,8 +473,8 @@ __device__ __forceinline__ double2 row_sum(const double2 *row, int lo, int hi, i
   }
   if (j < e) { const double2 u = row[j]; a.x += u.x; a.y += u.y; }
   a.x += b.x; a.y += b.y;
-  a.x += __shfl_xor_sync(FULL, a.x, 1);
-  a.y += __shfl_xor_sync(FULL, a.y, 1);
+  a.x += __shfl_xor_sync(FULL, a.x, 16);
+  a.y += __shfl_xor_sync(FULL, a.y, 16);
   return a;
 }
 
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
   double *sEz = reinterpret_cast<double *>(sQ_all + PUSH2D_WARPS * 4 * QCAP);
   double *sBz = sEz + TILE_ELEMS;
   double *sJ = sBz + TILE_ELEMS;                                // [3][TH][TW]
-  int *sSlow = reinterpret_cast<int *>(sJ + 3 * TILE_ELEMS);
+  int *sSlow = reinterpret_cast<int *>(sJ + 3 * JC);
   int *sSlowCount = sSlow + SLOWCAP;
   const int tile = blockIdx.x;
   const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
@@ -505,10 +508,8 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     sEB2[q] = ok ? make_double2(__ldg(P.e[1] + o), __ldg(P.b[0] + o)) : make_double2(0.0, 0.0);
     sEz[q] = ok ? __ldg(P.e[2] + o) : 0.0;
     sBz[q] = ok ? __ldg(P.b[2] + o) : 0.0;
-    sJ[q] = 0.0;
-    sJ[TILE_ELEMS + q] = 0.0;
-    sJ[2 * TILE_ELEMS + q] = 0.0;
   }
+  for (int q = tid; q < 3 * JC; q += PUSH2D_THREADS) sJ[q] = 0.0;
   __syncthreads();
 
   const double c = EPB_C;
@@ -519,15 +520,17 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
   // reduction role of this lane: pair-row prow (0..13), half; after the pair's halves are
   // combined the lane owns ONE deposit value: rows 0..8 = (jx, jy) of stencil cell prow,
   // rows 9..13 = (jz[2(prow-9)], jz[2(prow-9)+1])
-  const int prow = lane >> 1, half = lane & 1;
+  // (lanes 0..13 = first half of the columns, lanes 16..29 = second half: each quarter-warp
+  // then reads 8 different pair-rows of one column, which is bank-conflict free)
+  const int prow = lane & 15, half = lane >> 4;
   int offq;
   {
     const int comp = prow < 9 ? half : 2;
     const int cell = prow < 9 ? prow : 2 * (prow - 9) + half;
-    offq = comp * TILE_ELEMS + (cell / 3 - 1) * TW + (cell % 3 - 1);
+    offq = comp * JC + (cell / 3 - 1) * JP + (cell % 3 - 1);
   }
-  const bool owner = lane < 27;  // lane 27 would be jz[9], lanes 28.. have no row
-  const double2 *row = S + (lane < 28 ? prow : 0) * SPITCH;
+  const bool owner = prow < 13 || (prow == 13 && half == 0);  // (13, 1) would be jz[9]
+  const double2 *row = S + (prow < SPAIRS ? prow : 0) * SPITCH;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // each warp streams its own contiguous eighth of the tile's (cell-ordered) range, so that
@@ -675,7 +678,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
           fjx = fcx * P.part_q;
           fjy = fcy * P.part_q;
           fjz = fcz * P.part_q * part_vz;
-          key = (cy1 - oy) * TW + (cx1 - ox);
+          key = (cy1 - oy) * JP + (cx1 - ox);
           extras = (dcx | dcy) != 0;
           dep = !extras;
         }
@@ -802,7 +805,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     const size_t o = gofs<2>(P, cx, cy, 1);
 #pragma unroll
     for (int f = 0; f < 3; f++) {
-      const double val = sJ[f * TILE_ELEMS + q];
+      const double val = sJ[f * JC + ly * JP + lx];
       if (val != 0.0) atomicAdd(P.j[f] + o, val);
     }
   }
