@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "epb_internal.h"
 
@@ -582,6 +583,8 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
   P.out_idx = h->out_idx;
   P.out_cap = h->out_cap;
   P.gone = S.gone;
+  static int experiment = getenv("EPB_PUSH_EXPERIMENT") ? atoi(getenv("EPB_PUSH_EXPERIMENT")) : 0;
+  P.experiment = experiment;
 }
 
 }  // namespace

@@ -63,6 +63,7 @@ struct PushParams {
   int *out_idx;            // [27][out_cap]
   unsigned char *gone;     // per particle flag
   int out_cap;
+  int experiment;          // profiling only (EPB_PUSH_EXPERIMENT): disables parts of the tiled kernel
 };
 
 struct SpeciesDev {

@@ -22,6 +22,8 @@
 //    each, instead of 27 CAS loops per particle (shared FP64 atomicAdd is an
 //    ATOMS.CAST.SPIN loop on sm_100a).
 #pragma once
+#include <cstdlib>
+
 #include "epb_internal.h"
 
 namespace EPB_NS {
@@ -359,44 +361,42 @@ __global__ void __launch_bounds__(256) push_generic(const __grid_constant__ Push
 // Tiled 2D kernel
 // ---------------------------------------------------------------------------
 // One CTA per 16x16-cell tile of the cell-sorted layout, two CTAs per SM.  The kernel is
-// bound by the SM's load/store issue rate (about 2 cycles per shared-memory or shuffle
-// instruction whatever its width, tools/microbench.cu) and by the FP64 pipe, not by HBM,
-// so the shared-memory layout is chosen to minimise the NUMBER of LDS/STS instructions:
-//   sEB1 [TH][TW] double2 (ex, by)  both gathered with weights (hx, gy) at (cell_x2, cell_y1)
-//   sEB2 [TH][TW] double2 (ey, bx)  both gathered with weights (gx, hy) at (cell_x1, cell_y2)
-//   sEz, sBz [TH][TW]               (gx, gy) at (x1, y1) / (hx, hy) at (x2, y2)
-//   sJ  [3][TH][TW]   current accumulated by this CTA, flushed once with global reductions
-//   sS  [warp][14][33] double2: per-warp transposition scratch for the deposit reduction
+// bound by the SM's shared-memory data path (wavefronts) and the FP64 pipe, not by HBM
+// (tools/microbench.cu, profiles/).  Shared memory:
+//   sF  [6][TH][TW]    E/B tile + 3 halo cells
+//   sJ  [3] padded     current accumulated by this CTA, flushed once with global reductions
+//   sS  [warp][27][33] per-warp transposition scratch for the deposit reduction
 //   sQ  [warp][4][32]  double2: per-warp queue of particles whose nearest cell changed
-//   sSlow             CTA list of particles outside the tile's halo (stale sort, wrapped)
+//   sSlow              CTA list of particles outside the tile's halo (stale sort, wrapped)
 // The 32 lanes of a warp hold 32 consecutive particles of the sorted range, i.e. mostly one
 // or two cells.  Each lane writes its 27 deposit values (3 components x 3x3 cells around its
-// nearest cell) as 14 double2 into one column of sS; lane (p, half) then sums pair-row p over
-// half of the columns that share a cell key, the two halves are combined with one shuffle,
-// and ONE shared-memory update per (key, value) is issued (shared FP64 atomicAdd is a CAS
-// loop on sm_100a, so updates per particle are what must be avoided).  The partial sum of
-// the last key is carried in registers into the next batch.  The cost is independent of how
-// many distinct cells the warp spans, which keeps the kernel efficient between sorts.
+// nearest cell) into one column of sS; lane q < 27 then sums row q over the columns that
+// share a cell key and issues ONE shared-memory update per (key, value) (shared FP64
+// atomicAdd is a per-lane serialised CAS loop on sm_100a, so updates per particle are what
+// must be avoided).  The partial sum of the last key is carried in registers into the next
+// batch.  The cost is independent of how many distinct cells the warp spans, which keeps the
+// kernel efficient between sorts.
 // Particles whose nearest cell changed during the step (a few %) have a wider stencil: they
 // are queued and deposited densely, 32 at a time, with the reference's general loop.
 constexpr int T2X = 16, T2Y = 16, HALO = 3;
 constexpr int TW = T2X + 2 * HALO, TH = T2Y + 2 * HALO;
 constexpr int TILE_ELEMS = TW * TH;
 constexpr int PUSH2D_THREADS = 256, PUSH2D_WARPS = PUSH2D_THREADS / 32;
-constexpr int SPAIRS = 14, SPITCH = 33;
+constexpr int SROWS = 27, SPITCH = 34;  // even pitch: rows are read two columns at a time
 // sJ is padded (row pitch 29, component stride 649 doubles) so that the 27 addresses of one
 // flush fall into distinct 8-byte banks at most twice
 constexpr int JP = 29, JC = 633;
 constexpr int QCAP = 32;
 constexpr int SLOWCAP = 254;
 constexpr size_t PUSH2D_SMEM =
-    sizeof(double2) * ((size_t)2 * TILE_ELEMS + (size_t)PUSH2D_WARPS * SPAIRS * SPITCH + (size_t)PUSH2D_WARPS * 4 * QCAP) +
-    sizeof(double) * ((size_t)2 * TILE_ELEMS + 3 * JC) + sizeof(int) * (SLOWCAP + 2);
+    sizeof(double2) * ((size_t)PUSH2D_WARPS * 4 * QCAP + 2 * TILE_ELEMS) +
+    sizeof(double) * ((size_t)2 * TILE_ELEMS + 3 * JC + 1 + (size_t)PUSH2D_WARPS * SROWS * SPITCH) + sizeof(int) * (SLOWCAP + 2);
 
 __device__ __forceinline__ void smem_add(double *addr, double v) {
   // shared FP64 add: an ATOMS.CAST.SPIN loop; conflicts between warps are rare
   atomicAdd(addr, v);
 }
+#define SMEM_ADD(addr, v) do { if (!(P.experiment & 1)) smem_add((addr), (v)); else if ((v) == 1.2345e300) *(addr) = 0.0; } while (0)
 
 // num / sqrt(s).  The parity build keeps the reference's sqrt + divide sequence.
 __device__ __forceinline__ double over_sqrt(double num, double s) {
@@ -460,34 +460,31 @@ __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, co
   }
 }
 
-// sum of pair-row `row` over columns [lo, hi) split between the two lanes of a pair
-__device__ __forceinline__ double2 row_sum(const double2 *row, int lo, int hi, int half) {
-  const int mid = lo + ((hi - lo + 1) >> 1);
-  int j = half ? mid : lo;
-  const int e = half ? hi : mid;
-  double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
-  for (; j + 2 <= e; j += 2) {
-    const double2 u = row[j], v = row[j + 1];
-    a.x += u.x; a.y += u.y;
-    b.x += v.x; b.y += v.y;
+// sum of row `row` over columns [lo, hi); the row is 16-byte aligned and read with LDS.128
+__device__ __forceinline__ double row_sum(const double *row, int lo, int hi) {
+  double a = 0.0, b = 0.0;
+  int j = lo;
+  if ((j & 1) && j < hi) { a = row[j]; j++; }
+  for (; j + 2 <= hi; j += 2) {
+    const double2 u = *reinterpret_cast<const double2 *>(row + j);
+    a += u.x;
+    b += u.y;
   }
-  if (j < e) { const double2 u = row[j]; a.x += u.x; a.y += u.y; }
-  a.x += b.x; a.y += b.y;
-  a.x += __shfl_xor_sync(FULL, a.x, 16);
-  a.y += __shfl_xor_sync(FULL, a.y, 16);
-  return a;
+  if (j < hi) a += row[j];
+  return a + b;
 }
 
+template <bool CHUNK, bool CARRY>
 __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_constant__ PushParams P) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  double2 *sEB1 = reinterpret_cast<double2 *>(smraw);           // (ex, by)
+  double2 *sQ_all = reinterpret_cast<double2 *>(smraw);         // [warps][4][32]
+  double2 *sEB1 = sQ_all + PUSH2D_WARPS * 4 * QCAP;             // (ex, by) [TH][TW]
   double2 *sEB2 = sEB1 + TILE_ELEMS;                            // (ey, bx)
-  double2 *sS_all = sEB2 + TILE_ELEMS;                          // [warps][14][33]
-  double2 *sQ_all = sS_all + PUSH2D_WARPS * SPAIRS * SPITCH;    // [warps][4][32]
-  double *sEz = reinterpret_cast<double *>(sQ_all + PUSH2D_WARPS * 4 * QCAP);
+  double *sS_all = reinterpret_cast<double *>(sEB2 + TILE_ELEMS);   // [warps][27][34], 16-byte aligned rows
+  double *sEz = sS_all + PUSH2D_WARPS * SROWS * SPITCH;
   double *sBz = sEz + TILE_ELEMS;
-  double *sJ = sBz + TILE_ELEMS;                                // [3][TH][TW]
-  int *sSlow = reinterpret_cast<int *>(sJ + 3 * JC);
+  double *sJ = sBz + TILE_ELEMS;                                // [3] padded tiles
+  int *sSlow = reinterpret_cast<int *>(sJ + 3 * JC + 1);
   int *sSlowCount = sSlow + SLOWCAP;
   const int tile = blockIdx.x;
   const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
@@ -514,36 +511,30 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
 
   const double c = EPB_C;
   const double third = P.third;
-  double2 *S = sS_all + warp * SPAIRS * SPITCH;
+  double *S = sS_all + warp * SROWS * SPITCH;
   double2 *Q = sQ_all + warp * 4 * QCAP;
   int qcount = 0;  // warp-uniform
-  // reduction role of this lane: pair-row prow (0..13), half; after the pair's halves are
-  // combined the lane owns ONE deposit value: rows 0..8 = (jx, jy) of stencil cell prow,
-  // rows 9..13 = (jz[2(prow-9)], jz[2(prow-9)+1])
-  // (lanes 0..13 = first half of the columns, lanes 16..29 = second half: each quarter-warp
-  // then reads 8 different pair-rows of one column, which is bank-conflict free)
-  const int prow = lane & 15, half = lane >> 4;
-  int offq;
-  {
-    const int comp = prow < 9 ? half : 2;
-    const int cell = prow < 9 ? prow : 2 * (prow - 9) + half;
-    offq = comp * JC + (cell / 3 - 1) * JP + (cell % 3 - 1);
-  }
-  const bool owner = prow < 13 || (prow == 13 && half == 0);  // (13, 1) would be jz[9]
-  const double2 *row = S + (prow < SPAIRS ? prow : 0) * SPITCH;
+  // lane q < 27 owns deposit value q = comp*9 + iy*3 + ix of the 3x3 stencil
+  const int offq = (lane / 9) * JC + ((lane % 9) / 3 - 1) * JP + (lane % 3 - 1);
+  const bool owner = lane < SROWS;
+  const double *row = S + (owner ? lane : 0) * SPITCH;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // each warp streams its own contiguous eighth of the tile's (cell-ordered) range, so that
   // concurrent warps work on different cells and consecutive batches of a warp share cells
   long long wend;
   long long i;
-  {
+  if (CHUNK) {
     const long long total = end - start;
     const long long chunk = ((total + PUSH2D_WARPS - 1) / PUSH2D_WARPS + 31) / 32 * 32;
     const long long wstart = start + warp * chunk;
     wend = wstart + chunk < end ? wstart + chunk : end;
     i = wstart + lane;
+  } else {  // batches interleaved between the warps
+    wend = end;
+    i = start + warp * 32 + lane;
   }
+  constexpr int STEP = CHUNK ? 32 : PUSH2D_THREADS;
   // carried partial sum of the reduction: the lane's value for cell key ck (warp-uniform)
   int ck = -1;
   double ca = 0.0;
@@ -553,7 +544,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
     n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
   }
-  for (; i - lane < wend; i += 32) {
+  for (; i - lane < wend; i += STEP) {
     const bool active = i < wend;
     const double part_weight = n_w;
     double px_ = n_x - P.grid_min_local[0];
@@ -562,7 +553,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     double part_uy = n_py * P.ipart_mc;
     double part_uz = n_pz * P.ipart_mc;
     {
-      const long long in = i + 32;
+      const long long in = i + STEP;
       if (in < wend) {
         n_w = P.w[in]; n_x = P.x[0][in]; n_y = P.x[1][in];
         n_px = P.p[0][in]; n_py = P.p[1][in]; n_pz = P.p[2][in];
@@ -611,6 +602,8 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
           const double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
           return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
         };
+        // (ex, by) share the weights (hx, gy) and the offset (cell_x2, cell_y1), (ey, bx) share
+        // (gx, hy) at (cell_x1, cell_y2): one 16-byte shared load fetches both
         auto gat2 = [&](const double2 *F, int o, const double *wx, const double *wy, double &ra, double &rb) {
           double a[3], b[3];
 #pragma unroll
@@ -623,8 +616,8 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
           rb = wy[0] * b[0] + wy[1] * b[1] + wy[2] * b[2];
         };
         double ex_part, ey_part, bx_part, by_part;
-        gat2(sEB1, o21, hx, gy, ex_part, by_part);
-        gat2(sEB2, o12, gx, hy, ey_part, bx_part);
+        gat2(sEB1, (P.experiment & 4) ? 50 : o21, hx, gy, ex_part, by_part);
+        gat2(sEB2, (P.experiment & 4) ? 50 : o12, gx, hy, ey_part, bx_part);
         const double ez_part = gat(sEz, o11, gx, gy);
         const double bz_part = gat(sBz, o22, hx, hy);
         const double cmratio = P.cmratio;
@@ -686,7 +679,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     }
     if (!P.deposit) continue;
     // ---- queue the particles with a wider stencil -------------------------------------
-    const unsigned em = __ballot_sync(FULL, extras);
+    const unsigned em = __ballot_sync(FULL, extras && !(P.experiment & 8));
     if (em) {
       const int ne = __popc(em);
       if (qcount + ne > QCAP) {
@@ -708,7 +701,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     // Lanes are grouped by cell key: group 0 = key of the first lane, group 1 = the next key,
     // the rest (further cells; stale sort) are handled one by one.  Columns of sS are assigned
     // group by group so that the reducing lanes sum plain index ranges.
-    unsigned rest = __ballot_sync(FULL, dep);
+    unsigned rest = __ballot_sync(FULL, dep && !(P.experiment & 2));
     if (rest) {
       const int k0 = __shfl_sync(FULL, key, __ffs(rest) - 1);
       const unsigned m0 = __ballot_sync(FULL, dep && key == k0);
@@ -734,10 +727,10 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         tri(fyn, hy[0], hy[1], hy[2]);
 #pragma unroll
         for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
-        double xfac1[3], jyh[3] = {0.0, 0.0, 0.0}, jz[9];
+        double xfac1[3], jyh[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
-        double2 *col = S + colidx;
+        double *col = S + colidx;
 #pragma unroll
         for (int iy = 0; iy < 3; iy++) {
           const double yfac1 = gy[iy] + 0.5 * hy[iy];
@@ -750,43 +743,43 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
             const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
             jxh = jxh - fjx * wx;
             jyh[ix] = jyh[ix] - fjy * wy;
-            jz[iy * 3 + ix] = fjz * wz;
-            col[(iy * 3 + ix) * SPITCH] = make_double2(jxh, jyh[ix]);
+            col[(iy * 3 + ix) * SPITCH] = jxh;
+            col[(9 + iy * 3 + ix) * SPITCH] = jyh[ix];
+            col[(18 + iy * 3 + ix) * SPITCH] = fjz * wz;
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++) col[(9 + q) * SPITCH] = make_double2(jz[2 * q], jz[2 * q + 1]);
-        col[13 * SPITCH] = make_double2(jz[8], 0.0);
       }
       __syncwarp();
       {
-        const double2 t = row_sum(row, 0, n0, half);
-        const double a0 = half ? t.y : t.x;
-        if (k0 == ck) ca += a0;
+        const double a0 = row_sum(row, 0, n0);
+        if (CARRY && k0 == ck) ca += a0;
         else {
-          if (ck >= 0 && owner) smem_add(&sJ[offq + ck], ca);
+          if (ck >= 0 && owner) SMEM_ADD(&sJ[offq + ck], ca);
           ck = k0;
           ca = a0;
         }
       }
       if (n1) {
-        const double2 t = row_sum(row, n0, n0 + n1, half);
-        if (owner) smem_add(&sJ[offq + ck], ca);
+        const double a1 = row_sum(row, n0, n0 + n1);
+        if (owner) SMEM_ADD(&sJ[offq + ck], ca);
         ck = k1;
-        ca = half ? t.y : t.x;
+        ca = a1;
+      }
+      if (!CARRY) {
+        if (owner) SMEM_ADD(&sJ[offq + ck], ca);
+        ck = -1;
       }
       int j = n0 + n1;
       while (rest) {  // lanes in further cells (stale sort): one update per lane and value
         const int kj = __shfl_sync(FULL, key, __ffs(rest) - 1);
         rest &= rest - 1;
-        const double2 t = row[j];
-        if (owner) smem_add(&sJ[offq + kj], half ? t.y : t.x);
+        if (owner) SMEM_ADD(&sJ[offq + kj], row[j]);
         j++;
       }
     }
     __syncwarp();
   }
-  if (ck >= 0 && owner) smem_add(&sJ[offq + ck], ca);
+  if (ck >= 0 && owner) SMEM_ADD(&sJ[offq + ck], ca);
   if (qcount) {
     __syncwarp();
     drain_extras(P, sJ, Q, qcount, lane);
@@ -813,13 +806,23 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
 
 inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
   static bool attr_set = false;
+  static int variant = 0;
   if (tiled && nd == 2) {
     if (!attr_set) {
-      cudaFuncSetAttribute(push_tiled_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      if (const char *e = getenv("EPB_PUSH_VARIANT")) variant = atoi(e);
       attr_set = true;
     }
     if (P.tg.ntiles > 0) {
-      push_tiled_2d<<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
+      switch (variant) {
+        case 1: push_tiled_2d<true, false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
+        case 2: push_tiled_2d<false, true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
+        case 3: push_tiled_2d<false, false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
+        default: push_tiled_2d<true, true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
+      }
       (*launches)++;
     }
     return;

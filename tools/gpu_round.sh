@@ -37,6 +37,18 @@ benchN)
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $NG --cells ${BENCH_N:-2048} --steps 8 --warmup 3 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
   echo "benchN rc=$?"; cat gpurun_out/bench_n$NG.json; tail -5 gpurun_out/bench_n$NG.err ;;
+variants)
+  for v in ${VARIANTS:-0 1 2 3}; do
+    for si in ${SORTS:-4}; do
+      EPB_PUSH_VARIANT=$v timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval $si --no-cpu-baseline 2>/dev/null | \
+        python -c "import sys,json; d=json.loads(sys.stdin.read()); print('variant $v sort $si: push_ms %.3f step_ms %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step']))" | tee -a gpurun_out/variants.log
+    done
+  done ;;
+experiments)
+  for e in ${EXPS:-0 1 2 3 8 11 4 15}; do
+    EPB_PUSH_EXPERIMENT=$e timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval 4 --no-cpu-baseline 2>/dev/null | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('experiment $e: push_ms %.3f step_ms %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step']))" | tee -a gpurun_out/experiments.log
+  done ;;
 micro)
   (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu) > gpurun_out/micro_build.log 2>&1
   timeout 300 tools/microbench > gpurun_out/microbench.json 2>&1; cat gpurun_out/microbench.json ;;
