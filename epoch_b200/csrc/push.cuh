@@ -360,73 +360,65 @@ __global__ void __launch_bounds__(256) push_generic(const __grid_constant__ Push
 // ---------------------------------------------------------------------------
 // Tiled 2D kernel
 // ---------------------------------------------------------------------------
-// One CTA per 16x16-cell tile of the cell-sorted layout, two CTAs per SM.  The kernel is
-// bound by the SM's shared-memory data path (wavefronts) and the FP64 pipe, not by HBM
-// (tools/microbench.cu, profiles/).  Shared memory:
-//   sF  [6][TH][TW]    E/B tile + 3 halo cells
-//   sJ  [3] padded     current accumulated by this CTA, flushed once with global reductions
+// One CTA per 16x16-cell tile of the cell-sorted layout, two CTAs per SM.  Shared memory:
+//   sF  [6][TH][TW]   E/B tile + 3 halo cells
+//   sJ  [3][TH][TW]   current accumulated by this CTA, flushed once with global reductions
 //   sS  [warp][27][33] per-warp transposition scratch for the deposit reduction
-//   sQ  [warp][4][32]  double2: per-warp queue of particles whose nearest cell changed
-//   sSlow              CTA list of particles outside the tile's halo (stale sort, wrapped)
+//   sQ* [warp][...]    per-warp queue of particles that changed their nearest cell this step
+//   sSlow             CTA list of particles outside the tile's halo (stale sort, wrapped)
 // The 32 lanes of a warp hold 32 consecutive particles of the sorted range, i.e. mostly one
 // or two cells.  Each lane writes its 27 deposit values (3 components x 3x3 cells around its
-// nearest cell) into one column of sS; lane q < 27 then sums row q over the columns that
-// share a cell key and issues ONE shared-memory update per (key, value) (shared FP64
-// atomicAdd is a per-lane serialised CAS loop on sm_100a, so updates per particle are what
-// must be avoided).  The partial sum of the last key is carried in registers into the next
-// batch.  The cost is independent of how many distinct cells the warp spans, which keeps the
-// kernel efficient between sorts.
+// nearest cell) to a column of sS; lane q < 27 then sums row q over the lanes that share a
+// cell key and issues ONE shared-memory update per key (shared FP64 atomicAdd is a CAS loop
+// on sm_100a, so updates per particle are what must be avoided).  The cost is independent of
+// how many distinct cells the warp spans, which keeps the kernel efficient between sorts.
 // Particles whose nearest cell changed during the step (a few %) have a wider stencil: they
 // are queued and deposited densely, 32 at a time, with the reference's general loop.
 constexpr int T2X = 16, T2Y = 16, HALO = 3;
 constexpr int TW = T2X + 2 * HALO, TH = T2Y + 2 * HALO;
 constexpr int TILE_ELEMS = TW * TH;
 constexpr int PUSH2D_THREADS = 256, PUSH2D_WARPS = PUSH2D_THREADS / 32;
-constexpr int SROWS = 27, SPITCH = 34;  // even pitch: rows are read two columns at a time
-// sJ is padded (row pitch 29, component stride 649 doubles) so that the 27 addresses of one
-// flush fall into distinct 8-byte banks at most twice
-constexpr int JP = 29, JC = 633;
-constexpr int QCAP = 32;
-constexpr int SLOWCAP = 254;
+constexpr int SROWS = 27, SPITCH = 33;
+constexpr int QCAP = 32, QDBL = 7;
+constexpr int SLOWCAP = 510;
 constexpr size_t PUSH2D_SMEM =
-    sizeof(double2) * ((size_t)PUSH2D_WARPS * 4 * QCAP + 2 * TILE_ELEMS) +
-    sizeof(double) * ((size_t)2 * TILE_ELEMS + 3 * JC + 1 + (size_t)PUSH2D_WARPS * SROWS * SPITCH) + sizeof(int) * (SLOWCAP + 2);
+    sizeof(double) * ((size_t)9 * TILE_ELEMS + (size_t)PUSH2D_WARPS * SROWS * SPITCH + (size_t)PUSH2D_WARPS * QDBL * QCAP) +
+    sizeof(int) * ((size_t)PUSH2D_WARPS * QCAP + SLOWCAP + 2);
 
 __device__ __forceinline__ void smem_add(double *addr, double v) {
   // shared FP64 add: an ATOMS.CAST.SPIN loop; conflicts between warps are rare
   atomicAdd(addr, v);
 }
-#define SMEM_ADD(addr, v) do { if (!(P.experiment & 1)) smem_add((addr), (v)); else if ((v) == 1.2345e300) *(addr) = 0.0; } while (0)
 
-// num / sqrt(s).  The parity build keeps the reference's sqrt + divide sequence.
-__device__ __forceinline__ double over_sqrt(double num, double s) {
+// 1/sqrt(s) and friends.  The parity build keeps the reference's sqrt + divide sequence.
+__device__ __forceinline__ void gamma_root(double s, double num, double &root) {
 #ifdef EPB_FAST_MATH
-  return num * rsqrt(s);
+  root = num * rsqrt(s);
 #else
-  return num / sqrt(s);
+  root = num / sqrt(s);
 #endif
 }
 
 // Deposit of queued particles (nearest cell changed: dcell != 0 in x and/or y): the general
 // loop of particles.F90:549-579 over xmin..xmax, ymin..ymax with shared-memory updates.
-__device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, const double2 *Q, int n, int lane) {
+__device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, const double *Qd, const int *Qk,
+                                             int n, int lane) {
   if (lane >= n) return;
-  const double2 qx = Q[0 * QCAP + lane], qy = Q[1 * QCAP + lane], qj = Q[2 * QCAP + lane], qz = Q[3 * QCAP + lane];
-  const int pk = __double2loint(qz.y);
+  const int pk = Qk[lane];
   const int key = pk & 1023, dcx = ((pk >> 10) & 3) - 1, dcy = ((pk >> 12) & 3) - 1;
-  const double fjx = qj.x, fjy = qj.y, fjz = qz.x;
+  const double fjx = Qd[4 * QCAP + lane], fjy = Qd[5 * QCAP + lane], fjz = Qd[6 * QCAP + lane];
   double gx[5], gy[5], hx[5], hy[5];
   gx[0] = gx[4] = gy[0] = gy[4] = 0.0;
-  tri(qx.x, gx[1], gx[2], gx[3]);
-  tri(qy.x, gy[1], gy[2], gy[3]);
+  tri(Qd[0 * QCAP + lane], gx[1], gx[2], gx[3]);
+  tri(Qd[2 * QCAP + lane], gy[1], gy[2], gy[3]);
   double wm, w0, wp;
-  tri(qx.y, wm, w0, wp);
+  tri(Qd[1 * QCAP + lane], wm, w0, wp);
 #pragma unroll
   for (int q = 0; q < 5; q++) {
     const int r = q - 2 - dcx;
     hx[q] = ((r == -1) ? wm : (r == 0) ? w0 : (r == 1) ? wp : 0.0) - gx[q];
   }
-  tri(qy.y, wm, w0, wp);
+  tri(Qd[3 * QCAP + lane], wm, w0, wp);
 #pragma unroll
   for (int q = 0; q < 5; q++) {
     const int r = q - 2 - dcy;
@@ -452,39 +444,24 @@ __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, co
       jxh = jxh - fjx * wx;
       jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
       const double jzh = fjz * wz;
-      const int o = key + iy * JP + ix;
+      const int o = key + iy * TW + ix;
       smem_add(&sJ[o], jxh);
-      smem_add(&sJ[JC + o], jyh[ix + 2]);
-      smem_add(&sJ[2 * JC + o], jzh);
+      smem_add(&sJ[TILE_ELEMS + o], jyh[ix + 2]);
+      smem_add(&sJ[2 * TILE_ELEMS + o], jzh);
     }
   }
 }
 
-// sum of row `row` over columns [lo, hi); the row is 16-byte aligned and read with LDS.128
-__device__ __forceinline__ double row_sum(const double *row, int lo, int hi) {
-  double a = 0.0, b = 0.0;
-  int j = lo;
-  if ((j & 1) && j < hi) { a = row[j]; j++; }
-  for (; j + 2 <= hi; j += 2) {
-    const double2 u = *reinterpret_cast<const double2 *>(row + j);
-    a += u.x;
-    b += u.y;
-  }
-  if (j < hi) a += row[j];
-  return a + b;
-}
-
-template <bool CHUNK, bool CARRY>
+// V21: drop the six structurally cancelling stencil values (last jx column, last jy row)
+template <bool V21>
 __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_constant__ PushParams P) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  double2 *sQ_all = reinterpret_cast<double2 *>(smraw);         // [warps][4][32]
-  double2 *sEB1 = sQ_all + PUSH2D_WARPS * 4 * QCAP;             // (ex, by) [TH][TW]
-  double2 *sEB2 = sEB1 + TILE_ELEMS;                            // (ey, bx)
-  double *sS_all = reinterpret_cast<double *>(sEB2 + TILE_ELEMS);   // [warps][27][34], 16-byte aligned rows
-  double *sEz = sS_all + PUSH2D_WARPS * SROWS * SPITCH;
-  double *sBz = sEz + TILE_ELEMS;
-  double *sJ = sBz + TILE_ELEMS;                                // [3] padded tiles
-  int *sSlow = reinterpret_cast<int *>(sJ + 3 * JC + 1);
+  extern __shared__ double sm[];
+  double *sF = sm;                                   // [6][TH][TW]
+  double *sJ = sF + 6 * TILE_ELEMS;                  // [3][TH][TW]
+  double *sS_all = sJ + 3 * TILE_ELEMS;              // [warps][27][33]
+  double *sQd_all = sS_all + PUSH2D_WARPS * SROWS * SPITCH;
+  int *sQk_all = reinterpret_cast<int *>(sQd_all + PUSH2D_WARPS * QDBL * QCAP);
+  int *sSlow = sQk_all + PUSH2D_WARPS * QCAP;
   int *sSlowCount = sSlow + SLOWCAP;
   const int tile = blockIdx.x;
   const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
@@ -501,51 +478,47 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     const int cx = ox + lx, cy = oy + ly;
     const bool ok = (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
     const size_t o = ok ? gofs<2>(P, cx, cy, 1) : 0;
-    sEB1[q] = ok ? make_double2(__ldg(P.e[0] + o), __ldg(P.b[1] + o)) : make_double2(0.0, 0.0);
-    sEB2[q] = ok ? make_double2(__ldg(P.e[1] + o), __ldg(P.b[0] + o)) : make_double2(0.0, 0.0);
-    sEz[q] = ok ? __ldg(P.e[2] + o) : 0.0;
-    sBz[q] = ok ? __ldg(P.b[2] + o) : 0.0;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      sF[f * TILE_ELEMS + q] = ok ? __ldg(P.e[f] + o) : 0.0;
+      sF[(3 + f) * TILE_ELEMS + q] = ok ? __ldg(P.b[f] + o) : 0.0;
+      sJ[f * TILE_ELEMS + q] = 0.0;
+    }
   }
-  for (int q = tid; q < 3 * JC; q += PUSH2D_THREADS) sJ[q] = 0.0;
   __syncthreads();
 
   const double c = EPB_C;
   const double third = P.third;
+  const double *sEx = sF, *sEy = sF + TILE_ELEMS, *sEz = sF + 2 * TILE_ELEMS;
+  const double *sBx = sF + 3 * TILE_ELEMS, *sBy = sF + 4 * TILE_ELEMS, *sBz = sF + 5 * TILE_ELEMS;
   double *S = sS_all + warp * SROWS * SPITCH;
-  double2 *Q = sQ_all + warp * 4 * QCAP;
+  double *Qd = sQd_all + warp * QDBL * QCAP;
+  int *Qk = sQk_all + warp * QCAP;
   int qcount = 0;  // warp-uniform
-  // lane q < 27 owns deposit value q = comp*9 + iy*3 + ix of the 3x3 stencil
-  const int offq = (lane / 9) * JC + ((lane % 9) / 3 - 1) * JP + (lane % 3 - 1);
-  const bool owner = lane < SROWS;
-  const double *row = S + (owner ? lane : 0) * SPITCH;
+  // lane q < NR owns one deposit value: q = comp*9 + iy*3 + ix of the 3x3 stencil, or (V21)
+  // rows 0..5 = jx(iy, ix<2), 6..11 = jy(iy<2, ix), 12..20 = jz(iy, ix)
+  constexpr int NR = V21 ? 21 : SROWS;
+  int offq;
+  {
+    int comp, diy, dix;
+    if (V21) {
+      if (lane < 6) { comp = 0; diy = lane / 2; dix = lane % 2; }
+      else if (lane < 12) { comp = 1; diy = (lane - 6) / 3; dix = (lane - 6) % 3; }
+      else { comp = 2; diy = (lane - 12) / 3; dix = (lane - 12) % 3; }
+    } else { comp = lane / 9; diy = (lane % 9) / 3; dix = lane % 3; }
+    offq = comp * TILE_ELEMS + (diy - 1) * TW + (dix - 1);
+  }
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // each warp streams its own contiguous eighth of the tile's (cell-ordered) range, so that
-  // concurrent warps work on different cells and consecutive batches of a warp share cells
-  long long wend;
-  long long i;
-  if (CHUNK) {
-    const long long total = end - start;
-    const long long chunk = ((total + PUSH2D_WARPS - 1) / PUSH2D_WARPS + 31) / 32 * 32;
-    const long long wstart = start + warp * chunk;
-    wend = wstart + chunk < end ? wstart + chunk : end;
-    i = wstart + lane;
-  } else {  // batches interleaved between the warps
-    wend = end;
-    i = start + warp * 32 + lane;
-  }
-  constexpr int STEP = CHUNK ? 32 : PUSH2D_THREADS;
-  // carried partial sum of the reduction: the lane's value for cell key ck (warp-uniform)
-  int ck = -1;
-  double ca = 0.0;
   // software pipeline: the next batch's particle loads are in flight while this one computes
+  long long i = start + warp * 32 + lane;
   double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
-  if (i < wend) {
+  if (i < end) {
     n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
     n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
   }
-  for (; i - lane < wend; i += STEP) {
-    const bool active = i < wend;
+  for (; i - lane < end; i += PUSH2D_THREADS) {
+    const bool active = i < end;
     const double part_weight = n_w;
     double px_ = n_x - P.grid_min_local[0];
     double py_ = n_y - P.grid_min_local[1];
@@ -553,19 +526,19 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     double part_uy = n_py * P.ipart_mc;
     double part_uz = n_pz * P.ipart_mc;
     {
-      const long long in = i + STEP;
-      if (in < wend) {
+      const long long in = i + PUSH2D_THREADS;
+      if (in < end) {
         n_w = P.w[in]; n_x = P.x[0][in]; n_y = P.x[1][in];
         n_px = P.p[0][in]; n_py = P.p[1][in]; n_pz = P.p[2][in];
       }
     }
-    int key = -1;       // cell key (offset of the nearest cell in the shared tile)
-    bool dep = false;   // lane takes part in the transposed reduction
+    int key = -1;       // cell key of a lane that takes part in the transposed reduction
     bool extras = false;
     int dcx = 0, dcy = 0;
-    double fxo = 0, fxn = 0, fyo = 0, fyn = 0, fjx = 0, fjy = 0, fjz = 0;
+    double q_fxo = 0, q_fxn = 0, q_fyo = 0, q_fyn = 0, fjx = 0, fjy = 0, fjz = 0;
     if (active) {
-      double root = over_sqrt(P.dtco2, part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0);
+      double root;
+      gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
       px_ = px_ + part_ux * root;
       py_ = py_ + part_uy * root;
       const double cell_x_r = px_ * P.idx[0];
@@ -580,8 +553,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         else push_one<2>(P, i);
       } else {
         double gx[3], gy[3], hx[3], hy[3];
-        fxo = (double)(cx1 - 1) - cell_x_r;
-        fyo = (double)(cy1 - 1) - cell_y_r;
+        const double fxo = (double)(cx1 - 1) - cell_x_r, fyo = (double)(cy1 - 1) - cell_y_r;
         tri(fxo, gx[0], gx[1], gx[2]);
         tri(fyo, gy[0], gy[1], gy[2]);
         int cx2 = __double2int_rd(cell_x_r);
@@ -595,36 +567,23 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         const int o21 = (cy1 - 1 - oy) * TW + (cx2 - 1 - ox);
         const int o12 = (cy2 - 1 - oy) * TW + (cx1 - 1 - ox);
         const int o22 = (cy2 - 1 - oy) * TW + (cx2 - 1 - ox);
-        // include/triangle/e_part.inc, b_part.inc: rows parenthesised, sums left to right
         auto gat = [&](const double *F, int o, const double *wx, const double *wy) {
-          const double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
-          const double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
-          const double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
+          double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
+          double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
+          double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
           return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
         };
-        // (ex, by) share the weights (hx, gy) and the offset (cell_x2, cell_y1), (ey, bx) share
-        // (gx, hy) at (cell_x1, cell_y2): one 16-byte shared load fetches both
-        auto gat2 = [&](const double2 *F, int o, const double *wx, const double *wy, double &ra, double &rb) {
-          double a[3], b[3];
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            const double2 f0 = F[o + r * TW], f1 = F[o + r * TW + 1], f2 = F[o + r * TW + 2];
-            a[r] = wx[0] * f0.x + wx[1] * f1.x + wx[2] * f2.x;
-            b[r] = wx[0] * f0.y + wx[1] * f1.y + wx[2] * f2.y;
-          }
-          ra = wy[0] * a[0] + wy[1] * a[1] + wy[2] * a[2];
-          rb = wy[0] * b[0] + wy[1] * b[1] + wy[2] * b[2];
-        };
-        double ex_part, ey_part, bx_part, by_part;
-        gat2(sEB1, (P.experiment & 4) ? 50 : o21, hx, gy, ex_part, by_part);
-        gat2(sEB2, (P.experiment & 4) ? 50 : o12, gx, hy, ey_part, bx_part);
+        const double ex_part = gat(sEx, o21, hx, gy);
+        const double ey_part = gat(sEy, o12, gx, hy);
         const double ez_part = gat(sEz, o11, gx, gy);
+        const double bx_part = gat(sBx, o12, gx, hy);
+        const double by_part = gat(sBy, o21, hx, gy);
         const double bz_part = gat(sBz, o22, hx, hy);
         const double cmratio = P.cmratio;
         const double uxm = part_ux + cmratio * ex_part;
         const double uym = part_uy + cmratio * ey_part;
         const double uzm = part_uz + cmratio * ez_part;
-        root = over_sqrt(P.ccmratio, uxm * uxm + uym * uym + uzm * uzm + 1.0);
+        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
         const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
         const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
         const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
@@ -638,7 +597,11 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         part_uy = uyp + cmratio * ey_part;
         part_uz = uzp + cmratio * ez_part;
         const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
-        const double igamma = over_sqrt(1.0, part_u2 + 1.0);
+#ifdef EPB_FAST_MATH
+        const double igamma = rsqrt(part_u2 + 1.0);
+#else
+        const double igamma = 1.0 / sqrt(part_u2 + 1.0);
+#endif
         root = P.dtco2 * igamma;
         const double delta_x = part_ux * root;
         const double delta_y = part_uy * root;
@@ -661,8 +624,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
           py_ = py_ + delta_y;
           const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
           const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
-          fxn = (double)cx3 - cxr;
-          fyn = (double)cy3 - cyr;
+          const double fxn = (double)cx3 - cxr, fyn = (double)cy3 - cyr;
           dcx = cx3 + 1 - cx1;
           dcy = cy3 + 1 - cy1;
           const double fcx = P.kfc[0] * part_weight;
@@ -671,118 +633,102 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
           fjx = fcx * P.part_q;
           fjy = fcy * P.part_q;
           fjz = fcz * P.part_q * part_vz;
-          key = (cy1 - oy) * JP + (cx1 - ox);
-          extras = (dcx | dcy) != 0;
-          dep = !extras;
+          const int k = (cy1 - oy) * TW + (cx1 - ox);
+          if ((dcx | dcy) != 0) {
+            extras = true;
+            key = k;  // kept for the queue entry; excluded from the reduction below
+            q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          } else {
+            key = k;
+            // dcell = 0: hx = new weights - gx on the same three cells (particles.F90:521-538)
+            tri(fxn, hx[0], hx[1], hx[2]);
+            tri(fyn, hy[0], hy[1], hy[2]);
+#pragma unroll
+            for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
+            double xfac1[3], jyh[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
+            double *col = S + lane;
+#pragma unroll
+            for (int iy = 0; iy < 3; iy++) {
+              const double yfac1 = gy[iy] + 0.5 * hy[iy];
+              const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+              double jxh = 0.0;
+#pragma unroll
+              for (int ix = 0; ix < 3; ix++) {
+                const double wx = hx[ix] * yfac1;
+                const double wy = hy[iy] * xfac1[ix];
+                const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
+                jxh = jxh - fjx * wx;
+                jyh[ix] = jyh[ix] - fjy * wy;
+                if (!V21 || ix < 2) col[(V21 ? iy * 2 + ix : iy * 3 + ix) * SPITCH] = jxh;
+                if (!V21 || iy < 2) col[(V21 ? 6 + iy * 3 + ix : 9 + iy * 3 + ix) * SPITCH] = jyh[ix];
+                col[((V21 ? 12 : 18) + iy * 3 + ix) * SPITCH] = fjz * wz;
+              }
+            }
+          }
         }
       }
     }
     if (!P.deposit) continue;
     // ---- queue the particles with a wider stencil -------------------------------------
-    const unsigned em = __ballot_sync(FULL, extras && !(P.experiment & 8));
+    const unsigned em = __ballot_sync(FULL, extras);
     if (em) {
       const int ne = __popc(em);
       if (qcount + ne > QCAP) {
         __syncwarp();
-        drain_extras(P, sJ, Q, qcount, lane);
+        drain_extras(P, sJ, Qd, Qk, qcount, lane);
         __syncwarp();
         qcount = 0;
       }
       if (extras) {
         const int slot = qcount + __popc(em & lt_mask);
-        Q[0 * QCAP + slot] = make_double2(fxo, fxn);
-        Q[1 * QCAP + slot] = make_double2(fyo, fyn);
-        Q[2 * QCAP + slot] = make_double2(fjx, fjy);
-        Q[3 * QCAP + slot] = make_double2(fjz, __hiloint2double(0, key | ((dcx + 1) << 10) | ((dcy + 1) << 12)));
+        Qk[slot] = key | ((dcx + 1) << 10) | ((dcy + 1) << 12);
+        Qd[0 * QCAP + slot] = q_fxo; Qd[1 * QCAP + slot] = q_fxn;
+        Qd[2 * QCAP + slot] = q_fyo; Qd[3 * QCAP + slot] = q_fyn;
+        Qd[4 * QCAP + slot] = fjx; Qd[5 * QCAP + slot] = fjy; Qd[6 * QCAP + slot] = fjz;
+        key = -1;
       }
       qcount += ne;
     }
     // ---- transposed reduction: one shared update per (cell key, stencil value) ------------
-    // Lanes are grouped by cell key: group 0 = key of the first lane, group 1 = the next key,
-    // the rest (further cells; stale sort) are handled one by one.  Columns of sS are assigned
-    // group by group so that the reducing lanes sum plain index ranges.
-    unsigned rest = __ballot_sync(FULL, dep && !(P.experiment & 2));
+    __syncwarp();
+    unsigned rest = __ballot_sync(FULL, key >= 0);
     if (rest) {
       const int k0 = __shfl_sync(FULL, key, __ffs(rest) - 1);
-      const unsigned m0 = __ballot_sync(FULL, dep && key == k0);
+      const unsigned m0 = __ballot_sync(FULL, key == k0);
       rest &= ~m0;
-      int k1 = -1;
+      int k1 = 0;
       unsigned m1 = 0;
       if (rest) {
         k1 = __shfl_sync(FULL, key, __ffs(rest) - 1);
-        m1 = __ballot_sync(FULL, dep && key == k1);
+        m1 = __ballot_sync(FULL, key == k1);
         rest &= ~m1;
       }
-      const int n0 = __popc(m0), n1 = __popc(m1);
-      if (dep) {
-        const unsigned me = 1u << lane;
-        const int colidx = (m0 & me) ? __popc(m0 & lt_mask)
-                         : (m1 & me) ? n0 + __popc(m1 & lt_mask)
-                                     : n0 + n1 + __popc(rest & lt_mask);
-        // dcell = 0: hx = new weights - gx on the same three cells (particles.F90:521-538)
-        double gx[3], gy[3], hx[3], hy[3];
-        tri(fxo, gx[0], gx[1], gx[2]);
-        tri(fyo, gy[0], gy[1], gy[2]);
-        tri(fxn, hx[0], hx[1], hx[2]);
-        tri(fyn, hy[0], hy[1], hy[2]);
+      if (lane < NR) {
+        const double *row = S + lane * SPITCH;
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
-        double xfac1[3], jyh[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
-        double *col = S + colidx;
-#pragma unroll
-        for (int iy = 0; iy < 3; iy++) {
-          const double yfac1 = gy[iy] + 0.5 * hy[iy];
-          const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
-          double jxh = 0.0;
-#pragma unroll
-          for (int ix = 0; ix < 3; ix++) {
-            const double wx = hx[ix] * yfac1;
-            const double wy = hy[iy] * xfac1[ix];
-            const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
-            jxh = jxh - fjx * wx;
-            jyh[ix] = jyh[ix] - fjy * wy;
-            col[(iy * 3 + ix) * SPITCH] = jxh;
-            col[(9 + iy * 3 + ix) * SPITCH] = jyh[ix];
-            col[(18 + iy * 3 + ix) * SPITCH] = fjz * wz;
-          }
+        for (int j = 0; j < 32; j++) {
+          const double v = row[j];
+          if ((m0 >> j) & 1u) a0 += v;
+          else if ((m1 >> j) & 1u) a1 += v;
         }
+        smem_add(&sJ[offq + k0], a0);
+        if (m1) smem_add(&sJ[offq + k1], a1);
       }
-      __syncwarp();
-      {
-        const double a0 = row_sum(row, 0, n0);
-        if (CARRY && k0 == ck) ca += a0;
-        else {
-          if (ck >= 0 && owner) SMEM_ADD(&sJ[offq + ck], ca);
-          ck = k0;
-          ca = a0;
-        }
-      }
-      if (n1) {
-        const double a1 = row_sum(row, n0, n0 + n1);
-        if (owner) SMEM_ADD(&sJ[offq + ck], ca);
-        ck = k1;
-        ca = a1;
-      }
-      if (!CARRY) {
-        if (owner) SMEM_ADD(&sJ[offq + ck], ca);
-        ck = -1;
-      }
-      int j = n0 + n1;
       while (rest) {  // lanes in further cells (stale sort): one update per lane and value
-        const int kj = __shfl_sync(FULL, key, __ffs(rest) - 1);
+        const int j = __ffs(rest) - 1;
         rest &= rest - 1;
-        if (owner) SMEM_ADD(&sJ[offq + kj], row[j]);
-        j++;
+        const int kj = __shfl_sync(FULL, key, j);
+        if (lane < NR) smem_add(&sJ[offq + kj], S[lane * SPITCH + j]);
       }
     }
     __syncwarp();
   }
-  if (ck >= 0 && owner) SMEM_ADD(&sJ[offq + ck], ca);
   if (qcount) {
     __syncwarp();
-    drain_extras(P, sJ, Q, qcount, lane);
+    drain_extras(P, sJ, Qd, Qk, qcount, lane);
   }
   __syncthreads();
   {
@@ -798,31 +744,26 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
     const size_t o = gofs<2>(P, cx, cy, 1);
 #pragma unroll
     for (int f = 0; f < 3; f++) {
-      const double val = sJ[f * JC + ly * JP + lx];
+      const double val = sJ[f * TILE_ELEMS + q];
       if (val != 0.0) atomicAdd(P.j[f] + o, val);
     }
   }
 }
+
 
 inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
   static bool attr_set = false;
   static int variant = 0;
   if (tiled && nd == 2) {
     if (!attr_set) {
-      cudaFuncSetAttribute(push_tiled_2d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
-      cudaFuncSetAttribute(push_tiled_2d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
-      cudaFuncSetAttribute(push_tiled_2d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
-      cudaFuncSetAttribute(push_tiled_2d<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
+      cudaFuncSetAttribute(push_tiled_2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
       if (const char *e = getenv("EPB_PUSH_VARIANT")) variant = atoi(e);
       attr_set = true;
     }
     if (P.tg.ntiles > 0) {
-      switch (variant) {
-        case 1: push_tiled_2d<true, false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
-        case 2: push_tiled_2d<false, true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
-        case 3: push_tiled_2d<false, false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
-        default: push_tiled_2d<true, true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P); break;
-      }
+      if (variant == 1) push_tiled_2d<true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
+      else push_tiled_2d<false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
       (*launches)++;
     }
     return;
