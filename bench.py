@@ -158,12 +158,15 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", dest="n", type=int, default=4096, help="cells per side per GPU")
     ap.add_argument("--ppc", type=int, default=64)
-    ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "4")))
+    ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "8")))
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.warmup < 3:
         args.warmup = 3
 
