@@ -404,6 +404,7 @@ int update_e(epb_handle *h, double hdt) {
   F.cy = F.nd >= 2 ? hdt / h->cfg.dx[1] * (c * c) : 0.0;
   F.cz = F.nd >= 3 ? hdt / h->cfg.dx[2] * (c * c) : 0.0;
   F.fac = hdt / EPB_EPS0;
+  if (h->tma_ok) { epb_fdtd_tma_launch(h, true, F.cx, F.cy, F.cz, F.fac); return EPB_OK; }
   size_t total = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
   int nb = nblocks(total, 148 * 32);
   if (F.nd == 1) k_update_e<1><<<nb, 256, 0, h->stream>>>(F);
@@ -420,6 +421,7 @@ int update_b(epb_handle *h, double hdt) {
   F.cy = F.nd >= 2 ? hdt / h->cfg.dx[1] : 0.0;
   F.cz = F.nd >= 3 ? hdt / h->cfg.dx[2] : 0.0;
   F.fac = 0.0;
+  if (h->tma_ok) { epb_fdtd_tma_launch(h, false, F.cx, F.cy, F.cz, F.fac); return EPB_OK; }
   size_t total = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
   int nb = nblocks(total, 148 * 32);
   if (F.nd == 1) k_update_b<1><<<nb, 256, 0, h->stream>>>(F);
@@ -682,6 +684,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   EPB_CUDA(h, cudaMemsetAsync(h->snap, 0, 12 * h->plane * sizeof(double), h->stream));
   EPB_CUDA(h, cudaMalloc(&h->src, 4 * h->plane * sizeof(double)));
   EPB_CUDA(h, cudaMemsetAsync(h->src, 0, 4 * h->plane * sizeof(double), h->stream));
+  epb_fdtd_tma_setup(h);
   epb_make_tiles(h->cfg, h->tg);
   EPB_CUDA(h, cudaMalloc(&h->cell_count, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   EPB_CUDA(h, cudaMalloc(&h->cell_start, ((size_t)h->tg.nkeys + 1) * sizeof(int)));

@@ -78,6 +78,9 @@ struct SpeciesDev {
   unsigned char *gone = nullptr;
 };
 
+// opaque storage of a CUtensorMap (128 bytes, 64-byte aligned), see fdtd_tma.cu
+struct alignas(64) TmapStorage { unsigned char b[128]; };
+
 struct epb_handle {
   epb_config cfg;
   std::vector<SpeciesDev> sp;
@@ -111,6 +114,9 @@ struct epb_handle {
   double push_ms_sum = 0.0;
   long long push_ms_n = 0;
   int time_push = 0;
+  // TMA descriptors of ex,ey,ez,bx,by,bz for the staged FDTD kernels
+  TmapStorage tmap[6];
+  bool tma_ok = false;
 
   double *f(int which) const { return fields + (size_t)which * fsize; }
 };
@@ -118,6 +124,10 @@ struct epb_handle {
 // push_*.cu
 void epb_launch_push_strict(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches);
 void epb_launch_push_fast(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches);
+
+// fdtd_tma.cu
+bool epb_fdtd_tma_setup(epb_handle *h);
+void epb_fdtd_tma_launch(epb_handle *h, bool is_e, double cx, double cy, double cz, double fac);
 
 // sort.cu
 int epb_sort_species(epb_handle *h, int is);
