@@ -561,6 +561,7 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
   P.ccmratio = cc * P.cmratio;
   P.deposit = !S.cfg.zero_current;
   P.tile_start = S.tile_start;
+  P.cell_start = S.cell_start;
   P.tg = h->tg;
   for (int d = 0; d < 3; d++) {
     P.bnd_min[d] = c.min_local[d];
@@ -704,6 +705,10 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     EPB_CUDA(h, cudaMalloc(&S.key, (size_t)S.cap * sizeof(int)));
     EPB_CUDA(h, cudaMalloc(&S.tile_start, ((size_t)h->tg.ntiles + 1) * sizeof(int)));
     EPB_CUDA(h, cudaMemsetAsync(S.tile_start, 0, ((size_t)h->tg.ntiles + 1) * sizeof(int), h->stream));
+    if (h->tg.layout == 1) {
+      EPB_CUDA(h, cudaMalloc(&S.cell_start, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
+      EPB_CUDA(h, cudaMemsetAsync(S.cell_start, 0, ((size_t)h->tg.nkeys + 1) * sizeof(int), h->stream));
+    }
     EPB_CUDA(h, cudaMalloc(&S.gone, (size_t)S.cap));
     EPB_CUDA(h, cudaMemsetAsync(S.gone, 0, (size_t)S.cap, h->stream));
   }
@@ -746,7 +751,7 @@ int epb_destroy(epb_handle *h) {
   for (auto &S : h->sp) {
     for (int b = 0; b < 2; b++)
       for (int q = 0; q < 7; q++) cudaFree(S.buf[b][q]);
-    cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.gone);
+    cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.cell_start); cudaFree(S.gone);
   }
   if (h->h_counts) cudaFreeHost(h->h_counts);
   for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }

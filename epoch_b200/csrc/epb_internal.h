@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@ struct TileGeom {
   int cpt;     // cells per tile
   int ntiles;
   int nkeys;   // ntiles * cpt
+  int layout;  // 0: cell-major inside a tile; 1 (2D): 8x4-cell warp groups, particles of a group interleaved by rank (see push_cell_2d)
 };
 
 // Everything the push kernels need, passed by value (__grid_constant__).
@@ -47,6 +49,7 @@ struct PushParams {
   double *w;
   long long first, last;   // particle range of a generic launch
   const int *tile_start;   // tiled launch: ntiles+1 offsets into the sorted prefix
+  const int *cell_start;   // layout 1: nkeys+1 offsets (exclusive scan of the per-key counts)
   long long n_sorted_clip; // tile ranges are clipped to this count
   TileGeom tg;
   // particle boundary conditions (particles.F90:189-221, boundary.F90:1029-1462)
@@ -75,6 +78,7 @@ struct SpeciesDev {
   int cur = 0;
   int *key = nullptr;
   int *tile_start = nullptr;
+  int *cell_start = nullptr;  // layout 1: this species' copy of the key offsets
   unsigned char *gone = nullptr;
 };
 
@@ -120,6 +124,14 @@ struct epb_handle {
 
   double *f(int which) const { return fields + (size_t)which * fsize; }
 };
+
+// EPB_PUSH_VARIANT: 0 = push_tiled_2d (27-value transposition), 1 = its 21-value form,
+// 2 = push_cell_2d (one lane per cell, register accumulators, interleaved layout)
+inline int epb_push_variant() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 0; }
+  return v;
+}
 
 // push_*.cu
 void epb_launch_push_strict(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches);

@@ -402,7 +402,7 @@ __device__ __forceinline__ void gamma_root(double s, double num, double &root) {
 // Deposit of queued particles (nearest cell changed: dcell != 0 in x and/or y): the general
 // loop of particles.F90:549-579 over xmin..xmax, ymin..ymax with shared-memory updates.
 __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, const double *Qd, const int *Qk,
-                                             int n, int lane) {
+                                             int n, int lane, int jstride = TILE_ELEMS, int pitch = TW) {
   if (lane >= n) return;
   const int pk = Qk[lane];
   const int key = pk & 1023, dcx = ((pk >> 10) & 3) - 1, dcy = ((pk >> 12) & 3) - 1;
@@ -444,10 +444,10 @@ __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, co
       jxh = jxh - fjx * wx;
       jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
       const double jzh = fjz * wz;
-      const int o = key + iy * TW + ix;
+      const int o = key + iy * pitch + ix;
       smem_add(&sJ[o], jxh);
-      smem_add(&sJ[TILE_ELEMS + o], jyh[ix + 2]);
-      smem_add(&sJ[2 * TILE_ELEMS + o], jzh);
+      smem_add(&sJ[jstride + o], jyh[ix + 2]);
+      smem_add(&sJ[2 * jstride + o], jzh);
     }
   }
 }
@@ -751,6 +751,342 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
 }
 
 
+// ---------------------------------------------------------------------------
+// Cell-owner 2D kernel (layout 1, EPB_PUSH_VARIANT=2)
+// ---------------------------------------------------------------------------
+// One CTA per 16xCTY-cell tile, one warp per 16x2-cell group, ONE LANE PER CELL (a half-warp
+// is one row of the tile; the shared row pitch of 32 doubles then keeps the 64-bit gather
+// loads of a half-warp conflict-free up to the +-1 cell spread of the staggered stencils).  The sort
+// (k_scatter_il) stores the particles of a group interleaved by their rank within the cell,
+// so round r of a warp -- the r-th particle of each of its 32 cells -- is one coalesced load.
+// A lane keeps the 21 non-cancelling deposit sums of its cell's 3x3 stencil in registers for
+// the whole tile (raw sums; the running prefixes of particles.F90:563-571 are linear, so they
+// are applied once per cell at the end) and touches shared memory for the deposit only in the
+// final flush: no per-particle or per-batch shared FP64 updates, no transposition scratch.
+// The sort key is the cell the particle will be gathered in (sort.cu, predict), so right
+// after a sort every particle sits with the lane that owns its stencil.  Particles that are
+// not "regular" for their lane -- nearest cell changed during the step (wider stencil), or
+// stale order between sorts -- are queued per warp and deposited densely with the
+// reference's general loop and shared-memory updates (drain_extras); because a round spans 32
+// different cells those updates rarely collide.  Correctness never depends on the order.
+// CTY = tile height in cells (16 or 8; width is always 16), MINB = CTAs per SM the register
+// budget is sized for: <16,2> 128 registers, <8,3> 168, <16,1> 255.
+constexpr int CPITCH = 32;  // shared row pitch (doubles) of the cell-owner kernel; 22 columns used
+template <int CTY>
+constexpr size_t pushcell_smem() {
+  return sizeof(double) * ((size_t)9 * CPITCH * (CTY + 2 * HALO) + (size_t)(CTY / 2) * QDBL * QCAP) +
+         sizeof(int) * ((size_t)(CTY / 2) * QCAP + SLOWCAP + 2);
+}
+
+template <int CTY, int MINB>
+__global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_constant__ PushParams P) {
+  constexpr int T2Y = CTY, TH = CTY + 2 * HALO, TW = CPITCH, TWU = T2X + 2 * HALO, TILE_ELEMS = TW * TH;
+  constexpr int PUSH2D_THREADS = CTY * 16, PUSH2D_WARPS = CTY / 2;
+  extern __shared__ double sm[];
+  double *sF = sm;                                   // [6][TH][TW]
+  double *sJ = sF + 6 * TILE_ELEMS;                  // [3][TH][TW]
+  double *sQd_all = sJ + 3 * TILE_ELEMS;
+  int *sQk_all = reinterpret_cast<int *>(sQd_all + PUSH2D_WARPS * QDBL * QCAP);
+  int *sSlow = sQk_all + PUSH2D_WARPS * QCAP;
+  int *sSlowCount = sSlow + SLOWCAP;
+  const int tile = blockIdx.x;
+  const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
+  const int ox = ttx * T2X + 1 - HALO;  // cell index of shared column 0
+  const int oy = tty * T2Y + 1 - HALO;
+  const int *cs = P.cell_start + (size_t)tile * (T2X * T2Y);
+  const long long clip = P.n_sorted_clip;
+  {
+    const long long start = cs[0], end = cs[T2X * T2Y];
+    if (start >= end || start >= clip) return;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *sSlowCount = 0;
+  for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
+    const int lx = q % TW, ly = q / TW;
+    const int cx = ox + lx, cy = oy + ly;
+    const bool ok = (lx < TWU) && (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
+    const size_t o = ok ? gofs<2>(P, cx, cy, 1) : 0;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      sF[f * TILE_ELEMS + q] = ok ? __ldg(P.e[f] + o) : 0.0;
+      sF[(3 + f) * TILE_ELEMS + q] = ok ? __ldg(P.b[f] + o) : 0.0;
+      sJ[f * TILE_ELEMS + q] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  const double c = EPB_C;
+  const double third = P.third;
+  const double *sEx = sF, *sEy = sF + TILE_ELEMS, *sEz = sF + 2 * TILE_ELEMS;
+  const double *sBx = sF + 3 * TILE_ELEMS, *sBy = sF + 4 * TILE_ELEMS, *sBz = sF + 5 * TILE_ELEMS;
+  double *Qd = sQd_all + warp * QDBL * QCAP;
+  int *Qk = sQk_all + warp * QCAP;
+  int qcount = 0;  // warp-uniform
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // this lane's cell (1-based cell indices as in the reference) and its particle count
+  const int hcx = ttx * T2X + (lane & 15) + 1;
+  const int hcy = tty * T2Y + warp * 2 + (lane >> 4) + 1;
+  const int my_start = cs[warp * 32 + lane];
+  const int my_cnt = cs[warp * 32 + lane + 1] - my_start;
+  const int maxcnt = __reduce_max_sync(FULL, my_cnt);
+  long long rbase = __shfl_sync(FULL, my_start, 0);
+
+  // raw deposit sums of this lane's cell: AX[iy][ix<2], AY[iy<2][ix], AZ[iy][ix]
+  double AX[3][2], AY[2][3], AZ[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      AZ[a][b] = 0.0;
+      if (b < 2) AX[a][b] = 0.0;
+      if (a < 2) AY[a][b] = 0.0;
+    }
+  }
+
+  // software pipeline: the next round's particle loads are in flight while this one computes
+  long long i;
+  bool act;
+  {
+    const bool na = my_cnt > 0;
+    const unsigned bal = __ballot_sync(FULL, na);
+    i = rbase + __popc(bal & lt_mask);
+    rbase += __popc(bal);
+    act = na && i < clip;
+  }
+  double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
+  if (act) {
+    n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
+    n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
+  }
+  for (int r = 0; r < maxcnt; r++) {
+    const bool active = act;
+    const long long ci = i;
+    const double part_weight = n_w;
+    double px_ = n_x - P.grid_min_local[0];
+    double py_ = n_y - P.grid_min_local[1];
+    double part_ux = n_px * P.ipart_mc;
+    double part_uy = n_py * P.ipart_mc;
+    double part_uz = n_pz * P.ipart_mc;
+    {
+      const bool na = my_cnt > r + 1;
+      const unsigned bal = __ballot_sync(FULL, na);
+      i = rbase + __popc(bal & lt_mask);
+      rbase += __popc(bal);
+      act = na && i < clip;
+      if (act) {
+        n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
+        n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
+      }
+    }
+    bool extras = false;
+    int key = 0, dcx = 0, dcy = 0;
+    double q_fxo = 0, q_fxn = 0, q_fyo = 0, q_fyn = 0, fjx = 0, fjy = 0, fjz = 0;
+    if (active) {
+      double root;
+      gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
+      px_ = px_ + part_ux * root;
+      py_ = py_ + part_uy * root;
+      const double cell_x_r = px_ * P.idx[0];
+      const double cell_y_r = py_ * P.idx[1];
+      const int cx1 = __double2int_rd(cell_x_r + 0.5) + 1;
+      const int cy1 = __double2int_rd(cell_y_r + 0.5) + 1;
+      // the gather reads cell1-2..cell1+1, the deposit writes cell1-2..cell1+2
+      const bool fast = (cx1 - 2 >= ox) && (cx1 + 2 <= ox + TWU - 1) && (cy1 - 2 >= oy) && (cy1 + 2 <= oy + TH - 1);
+      if (!fast) {
+        const int slot = atomicAdd(sSlowCount, 1);
+        if (slot < SLOWCAP) sSlow[slot] = (int)ci;
+        else push_one<2>(P, ci);
+      } else {
+        double gx[3], gy[3], hx[3], hy[3];
+        const double fxo = (double)(cx1 - 1) - cell_x_r, fyo = (double)(cy1 - 1) - cell_y_r;
+        tri(fxo, gx[0], gx[1], gx[2]);
+        tri(fyo, gy[0], gy[1], gy[2]);
+        int cx2 = __double2int_rd(cell_x_r);
+        tri((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
+        cx2 += 1;
+        int cy2 = __double2int_rd(cell_y_r);
+        tri((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
+        cy2 += 1;
+        // shared-tile offsets of (cell-1, cell-1)
+        const int o11 = (cy1 - 1 - oy) * TW + (cx1 - 1 - ox);
+        const int o21 = (cy1 - 1 - oy) * TW + (cx2 - 1 - ox);
+        const int o12 = (cy2 - 1 - oy) * TW + (cx1 - 1 - ox);
+        const int o22 = (cy2 - 1 - oy) * TW + (cx2 - 1 - ox);
+        auto gat = [&](const double *F, int o, const double *wx, const double *wy) {
+          double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
+          double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
+          double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
+          return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
+        };
+        const double ex_part = gat(sEx, o21, hx, gy);
+        const double ey_part = gat(sEy, o12, gx, hy);
+        const double ez_part = gat(sEz, o11, gx, gy);
+        const double bx_part = gat(sBx, o12, gx, hy);
+        const double by_part = gat(sBy, o21, hx, gy);
+        const double bz_part = gat(sBz, o22, hx, hy);
+        const double cmratio = P.cmratio;
+        const double uxm = part_ux + cmratio * ex_part;
+        const double uym = part_uy + cmratio * ey_part;
+        const double uzm = part_uz + cmratio * ez_part;
+        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+        const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+        const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+        const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+        const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                            2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+        const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                            2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+        const double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                            2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+        part_ux = uxp + cmratio * ex_part;
+        part_uy = uyp + cmratio * ey_part;
+        part_uz = uzp + cmratio * ez_part;
+        const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+#ifdef EPB_FAST_MATH
+        const double igamma = rsqrt(part_u2 + 1.0);
+#else
+        const double igamma = 1.0 / sqrt(part_u2 + 1.0);
+#endif
+        root = P.dtco2 * igamma;
+        const double delta_x = part_ux * root;
+        const double delta_y = part_uy * root;
+        const double part_vz = part_uz * c * igamma;
+        px_ = px_ + delta_x;
+        py_ = py_ + delta_y;
+        {
+          double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
+          double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
+          const int dir = particle_bc<2>(P, pos, mom);
+          P.x[0][ci] = pos[0];
+          P.x[1][ci] = pos[1];
+          P.p[0][ci] = mom[0];
+          P.p[1][ci] = mom[1];
+          P.p[2][ci] = mom[2];
+          if (dir >= 0) outbox_put(P, ci, dir);
+        }
+        if (P.deposit) {
+          px_ = px_ + delta_x;
+          py_ = py_ + delta_y;
+          const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
+          const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
+          const double fxn = (double)cx3 - cxr, fyn = (double)cy3 - cyr;
+          dcx = cx3 + 1 - cx1;
+          dcy = cy3 + 1 - cy1;
+          const double fcx = P.kfc[0] * part_weight;
+          const double fcy = P.kfc[1] * part_weight;
+          const double fcz = P.kfc[2] * part_weight;
+          fjx = fcx * P.part_q;
+          fjy = fcy * P.part_q;
+          fjz = fcz * P.part_q * part_vz;
+          if ((dcx | dcy) != 0 || cx1 != hcx || cy1 != hcy) {
+            extras = true;
+            key = (cy1 - oy) * TW + (cx1 - ox);
+            q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          } else {
+            // dcell = 0 in this lane's own cell: hx = new weights - gx on the same three cells
+            // (particles.F90:521-538); sums of fj*w per stencil point, prefixes applied at the end
+            tri(fxn, hx[0], hx[1], hx[2]);
+            tri(fyn, hy[0], hy[1], hy[2]);
+#pragma unroll
+            for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
+            double xfac1[3], yfac1[3], yfac2[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              xfac1[q] = gx[q] + 0.5 * hx[q];
+              yfac1[q] = gy[q] + 0.5 * hy[q];
+              yfac2[q] = third * hy[q] + 0.5 * gy[q];
+            }
+            const double fhx0 = fjx * hx[0], fhx1 = fjx * hx[1];
+            const double fhy0 = fjy * hy[0], fhy1 = fjy * hy[1];
+#pragma unroll
+            for (int iy = 0; iy < 3; iy++) {
+              AX[iy][0] += fhx0 * yfac1[iy];
+              AX[iy][1] += fhx1 * yfac1[iy];
+            }
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) {
+              AY[0][ix] += fhy0 * xfac1[ix];
+              AY[1][ix] += fhy1 * xfac1[ix];
+            }
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) {
+              const double zg = fjz * gx[ix], zh = fjz * hx[ix];
+#pragma unroll
+              for (int iy = 0; iy < 3; iy++) AZ[iy][ix] += zg * yfac1[iy] + zh * yfac2[iy];
+            }
+          }
+        }
+      }
+    }
+    if (!P.deposit) continue;
+    // ---- queue the particles that are not regular for their lane ---------------------------
+    const unsigned em = __ballot_sync(FULL, extras);
+    if (em) {
+      const int ne = __popc(em);
+      if (qcount + ne > QCAP) {
+        __syncwarp();
+        drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
+        __syncwarp();
+        qcount = 0;
+      }
+      if (extras) {
+        const int slot = qcount + __popc(em & lt_mask);
+        Qk[slot] = key | ((dcx + 1) << 10) | ((dcy + 1) << 12);
+        Qd[0 * QCAP + slot] = q_fxo; Qd[1 * QCAP + slot] = q_fxn;
+        Qd[2 * QCAP + slot] = q_fyo; Qd[3 * QCAP + slot] = q_fyn;
+        Qd[4 * QCAP + slot] = fjx; Qd[5 * QCAP + slot] = fjy; Qd[6 * QCAP + slot] = fjz;
+      }
+      qcount += ne;
+    }
+  }
+  if (qcount) {
+    __syncwarp();
+    drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
+  }
+  // ---- flush this lane's cell sums: prefixes of particles.F90:563-571, one update per point ----
+  if (P.deposit && my_cnt > 0) {
+    const int hb = (hcy - oy) * TW + (hcx - ox);
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++) {
+      const double v0 = -AX[iy][0];
+      const double v1 = v0 - AX[iy][1];
+      smem_add(&sJ[hb + (iy - 1) * TW - 1], v0);
+      smem_add(&sJ[hb + (iy - 1) * TW], v1);
+    }
+#pragma unroll
+    for (int ix = 0; ix < 3; ix++) {
+      const double v0 = -AY[0][ix];
+      const double v1 = v0 - AY[1][ix];
+      smem_add(&sJ[TILE_ELEMS + hb - TW + (ix - 1)], v0);
+      smem_add(&sJ[TILE_ELEMS + hb + (ix - 1)], v1);
+    }
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++)
+#pragma unroll
+      for (int ix = 0; ix < 3; ix++) smem_add(&sJ[2 * TILE_ELEMS + hb + (iy - 1) * TW + (ix - 1)], AZ[iy][ix]);
+  }
+  __syncthreads();
+  {
+    int ns = *sSlowCount;
+    if (ns > SLOWCAP) ns = SLOWCAP;
+    for (int q = tid; q < ns; q += PUSH2D_THREADS) push_one<2>(P, sSlow[q]);
+  }
+  for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
+    const int lx = q % TW, ly = q / TW;
+    const int cx = ox + lx, cy = oy + ly;
+    const bool ok = (lx < TWU) && (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
+    if (!ok) continue;
+    const size_t o = gofs<2>(P, cx, cy, 1);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double val = sJ[f * TILE_ELEMS + q];
+      if (val != 0.0) atomicAdd(P.j[f] + o, val);
+    }
+  }
+}
+
+
 inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
   static bool attr_set = false;
   static int variant = 0;
@@ -758,11 +1094,19 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
     if (!attr_set) {
       cudaFuncSetAttribute(push_tiled_2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
       cudaFuncSetAttribute(push_tiled_2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH2D_SMEM);
-      if (const char *e = getenv("EPB_PUSH_VARIANT")) variant = atoi(e);
+      cudaFuncSetAttribute(push_cell_2d<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushcell_smem<16>());
+      cudaFuncSetAttribute(push_cell_2d<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushcell_smem<16>());
+      cudaFuncSetAttribute(push_cell_2d<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushcell_smem<8>());
+      variant = epb_push_variant();
       attr_set = true;
     }
     if (P.tg.ntiles > 0) {
-      if (variant == 1) push_tiled_2d<true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
+      if (P.tg.layout == 1) {
+        if (P.tg.T[1] == 8) push_cell_2d<8, 3><<<P.tg.ntiles, 128, pushcell_smem<8>(), s>>>(P);
+        else if (variant == 4) push_cell_2d<16, 1><<<P.tg.ntiles, 256, pushcell_smem<16>(), s>>>(P);
+        else push_cell_2d<16, 2><<<P.tg.ntiles, 256, pushcell_smem<16>(), s>>>(P);
+      }
+      else if (variant == 1) push_tiled_2d<true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
       else push_tiled_2d<false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
       (*launches)++;
     }

@@ -14,6 +14,9 @@ namespace {
 
 struct KeyOp {
   const double *x[3];
+  const double *p[3];      // layout 1: momenta, for the predicted gather cell
+  double ipart_mc, dtco2, idx[3];
+  int predict;
   long long n;
   int nd, nloc[3];
   double gmin[3], dx[3];
@@ -24,14 +27,29 @@ struct KeyOp {
 
 __device__ __forceinline__ int cell_key(const KeyOp &K, long long i) {
   int t[3] = {0, 0, 0}, in[3] = {0, 0, 0};
+  double root = 0.0;
+  if (K.predict) {
+    // the cell the NEXT push gathers in: position advanced by half a step with the stored
+    // momentum, exactly as particles.F90:289-322 does at the top of push_particles
+    const double ux = K.p[0][i] * K.ipart_mc, uy = K.p[1][i] * K.ipart_mc, uz = K.p[2][i] * K.ipart_mc;
+    root = K.dtco2 / sqrt(ux * ux + uy * uy + uz * uz + 1.0);
+  }
   for (int d = 0; d < K.nd; d++) {
-    // nearest cell as calc_ppc defines it (io/calc_df.F90:795-796), clamped into 1..n
-    int cell = __double2int_rd((K.x[d][i] - K.gmin[d]) / K.dx[d] + 0.5);
+    int cell;
+    if (K.predict) {
+      double part_x = K.x[d][i] - K.gmin[d];
+      part_x = part_x + (K.p[d][i] * K.ipart_mc) * root;
+      cell = __double2int_rd(part_x * K.idx[d] + 0.5);
+    } else {
+      // nearest cell as calc_ppc defines it (io/calc_df.F90:795-796), clamped into 1..n
+      cell = __double2int_rd((K.x[d][i] - K.gmin[d]) / K.dx[d] + 0.5);
+    }
     cell = cell < 0 ? 0 : (cell > K.nloc[d] - 1 ? K.nloc[d] - 1 : cell);
     t[d] = cell / K.tg.T[d];
     in[d] = cell - t[d] * K.tg.T[d];
   }
   const int tile = (t[2] * K.tg.nt[1] + t[1]) * K.tg.nt[0] + t[0];
+  // layout 1 (2D, 16-wide tiles): a warp group of push_cell_2d = two tile rows = 32 consecutive keys
   const int intile = (in[2] * K.tg.T[1] + in[1]) * K.tg.T[0] + in[0];
   return tile * K.tg.cpt + intile;
 }
@@ -85,6 +103,39 @@ __global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ Scatter
   }
 }
 
+// Layout 1: inside a group of 32 keys the particles are interleaved by their rank r within the
+// key: all rank-0 particles of the group in key order, then all rank-1 particles, ... (keys
+// that have run out are skipped).  A warp of push_cell_2d whose lane l owns key l then reads
+// one round with a single coalesced load.  Position of (key l, rank r) inside the group =
+// sum over l' of min(count[l'], r + (l' < l)).
+__global__ void __launch_bounds__(256) k_scatter_il(const __grid_constant__ ScatterOp S) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = (S.n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool active = i < S.n;
+    const int key = active ? S.key[i] : 0;
+    const int r = agg_inc(S.cursor, key, active);
+    if (active) {
+      const int l = key & 31;
+      const int *st = S.start + (key - l);
+      const int s0 = __ldg(st);
+      int prev = s0, acc = 0;
+#pragma unroll 8
+      for (int q = 0; q < 32; q++) {
+        const int nxt = __ldg(st + q + 1);
+        const int c = nxt - prev;
+        prev = nxt;
+        const int lim = r + (q < l ? 1 : 0);
+        acc += c < lim ? c : lim;
+      }
+      const long long dst = (long long)s0 + acc;
+#pragma unroll
+      for (int q = 0; q < 7; q++)
+        if (S.src[q]) S.dst[q][dst] = S.src[q][i];
+    }
+  }
+}
+
 __global__ void k_tile_start(const int *cell_start, int *tile_start, int ntiles, int cpt) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t <= ntiles) tile_start[t] = cell_start[(size_t)t * cpt];
@@ -98,6 +149,8 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   if (nd == 1) T[0] = 256;
   else if (nd == 2) { T[0] = 16; T[1] = 16; }  // must match T2X/T2Y in push.cuh
   else { T[0] = 8; T[1] = 8; T[2] = 8; }
+  const int variant = epb_push_variant();
+  if (nd == 2 && variant == 3) T[1] = 8;      // push_cell_2d<8,3>: 16x8-cell tiles
   tg.cpt = 1;
   tg.ntiles = 1;
   for (int d = 0; d < 3; d++) {
@@ -107,6 +160,7 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
     tg.ntiles *= tg.nt[d];
   }
   tg.nkeys = tg.ntiles * tg.cpt;
+  tg.layout = (nd == 2 && variant >= 2 && variant <= 4) ? 1 : 0;
 }
 
 int epb_sort_species(epb_handle *h, int is) {
@@ -127,19 +181,27 @@ int epb_sort_species(epb_handle *h, int is) {
     K.tg = h->tg;
     K.key = S.key;
     K.count = h->cell_count;
+    K.predict = (h->tg.layout == 1);
+    for (int d = 0; d < 3; d++) {
+      K.p[d] = S.buf[S.cur][3 + d];
+      K.idx[d] = d < c.ndims ? 1.0 / c.dx[d] : 0.0;
+    }
+    K.ipart_mc = 1.0 / (EPB_C * S.cfg.mass);
+    K.dtco2 = EPB_C * (c.dt / 2.0);
     long long nb = (S.n + 255) / 256;
     if (nb > 148LL * 32) nb = 148LL * 32;
     k_keys<<<(int)nb, 256, 0, h->stream>>>(K);
     h->launches++;
   }
+  int *cstart = (h->tg.layout == 1 && S.cell_start) ? S.cell_start : h->cell_start;
   size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, h->cell_start, nkeys + 1, h->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, cstart, nkeys + 1, h->stream);
   if (need > h->cub_tmp_bytes) {
     cudaFree(h->cub_tmp);
     EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
     h->cub_tmp_bytes = need;
   }
-  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_tmp, need, h->cell_count, h->cell_start, nkeys + 1, h->stream));
+  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_tmp, need, h->cell_count, cstart, nkeys + 1, h->stream));
   h->launches++;
   if (S.n > 0) {
     EPB_CUDA(h, cudaMemsetAsync(h->cell_count, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
@@ -147,15 +209,16 @@ int epb_sort_species(epb_handle *h, int is) {
     for (int q = 0; q < 7; q++) { Sc.src[q] = S.buf[S.cur][q]; Sc.dst[q] = S.buf[S.cur ^ 1][q]; }
     Sc.n = S.n;
     Sc.key = S.key;
-    Sc.start = h->cell_start;
+    Sc.start = cstart;
     Sc.cursor = h->cell_count;
     long long nb = (S.n + 255) / 256;
     if (nb > 148LL * 32) nb = 148LL * 32;
-    k_scatter<<<(int)nb, 256, 0, h->stream>>>(Sc);
+    if (h->tg.layout == 1) k_scatter_il<<<(int)nb, 256, 0, h->stream>>>(Sc);
+    else k_scatter<<<(int)nb, 256, 0, h->stream>>>(Sc);
     h->launches++;
     S.cur ^= 1;
   }
-  k_tile_start<<<(h->tg.ntiles + 1 + 255) / 256, 256, 0, h->stream>>>(h->cell_start, S.tile_start, h->tg.ntiles, h->tg.cpt);
+  k_tile_start<<<(h->tg.ntiles + 1 + 255) / 256, 256, 0, h->stream>>>(cstart, S.tile_start, h->tg.ntiles, h->tg.cpt);
   h->launches++;
   S.n_sorted = S.n;
   EPB_CUDA(h, cudaGetLastError());

@@ -11,6 +11,13 @@ case $s in
 tests)
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log ;;
+testsv)
+  # 2D parity tests under the alternative push kernels (EPB_PUSH_VARIANT is read once per process)
+  for v in ${TESTVARIANTS:-3 2 4}; do
+    EPB_PUSH_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden_fixtures.py -m gpu -q \
+      -k "2-n or 2d or sort_interval or open_boundaries or foil or full_size or cuda_path" > gpurun_out/pytest_gpu_v$v.log 2>&1
+    echo "variant $v pytest rc=$?" >> gpurun_out/pytest_gpu_v$v.log; tail -4 gpurun_out/pytest_gpu_v$v.log
+  done ;;
 smoke)
   timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log ;;
 bench)
@@ -25,7 +32,7 @@ launches)
       > gpurun_out/launches_bench.log 2>&1
   echo "launches rc=$?" ;;
 ncu)
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:push_tiled -s 3 -c 2 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:push_${NCU_KERNEL:-tiled} -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-2} \
       -f -o gpurun_out/prof_push python bench.py --cells 2048 --steps 2 --warmup 3 --no-cpu-baseline \
       > gpurun_out/ncu_push.log 2>&1
   echo "ncu rc=$?" ;;
