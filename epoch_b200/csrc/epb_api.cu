@@ -562,6 +562,11 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
   P.deposit = !S.cfg.zero_current;
   P.tile_start = S.tile_start;
   P.cell_start = S.cell_start;
+  P.emit = 0;
+  P.key_out = S.key;
+  P.rank_out = S.rank;
+  P.stay_cnt = S.stay_cnt;
+  P.arr_cnt = S.arr_cnt;
   P.tg = h->tg;
   for (int d = 0; d < 3; d++) {
     P.bnd_min[d] = c.min_local[d];
@@ -708,6 +713,10 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     if (h->tg.layout == 1) {
       EPB_CUDA(h, cudaMalloc(&S.cell_start, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
       EPB_CUDA(h, cudaMemsetAsync(S.cell_start, 0, ((size_t)h->tg.nkeys + 1) * sizeof(int), h->stream));
+      EPB_CUDA(h, cudaMalloc(&S.rank, (size_t)S.cap * sizeof(int)));
+      EPB_CUDA(h, cudaMalloc(&S.perm, (size_t)S.cap * sizeof(int)));
+      EPB_CUDA(h, cudaMalloc(&S.stay_cnt, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
+      EPB_CUDA(h, cudaMalloc(&S.arr_cnt, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
     }
     EPB_CUDA(h, cudaMalloc(&S.gone, (size_t)S.cap));
     EPB_CUDA(h, cudaMemsetAsync(S.gone, 0, (size_t)S.cap, h->stream));
@@ -730,6 +739,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     EPB_CUDA(h, cudaMalloc(&h->out_count, 64 * sizeof(int)));
     EPB_CUDA(h, cudaMemsetAsync(h->out_count, 0, 64 * sizeof(int), h->stream));
     EPB_CUDA(h, cudaMalloc(&h->out_idx, ((size_t)27 * h->out_cap + 1) * sizeof(int)));
+    EPB_CUDA(h, cudaMalloc(&h->movers, ((size_t)27 * h->out_cap + 1) * sizeof(int)));
   }
   EPB_CUDA(h, cudaMalloc(&h->d_scratch, 1024 * sizeof(int)));
   EPB_CUDA(h, cudaMallocHost(&h->h_counts, 256 * sizeof(int)));
@@ -745,13 +755,13 @@ int epb_destroy(epb_handle *h) {
   cudaStreamSynchronize(h->stream);
   epb_comm_destroy(h);
   cudaFree(h->fields); cudaFree(h->snap); cudaFree(h->src);
-  cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp);
+  cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
   cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
     for (int b = 0; b < 2; b++)
       for (int q = 0; q < 7; q++) cudaFree(S.buf[b][q]);
-    cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.cell_start); cudaFree(S.gone);
+    cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.cell_start); cudaFree(S.rank); cudaFree(S.perm); cudaFree(S.stay_cnt); cudaFree(S.arr_cnt); cudaFree(S.gone);
   }
   if (h->h_counts) cudaFreeHost(h->h_counts);
   for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -810,6 +820,7 @@ int epb_upload_species(epb_handle *h, int is, int64_t n, const double *packed) {
   EPB_CUDA(h, cudaMemsetAsync(S.gone, 0, (size_t)S.cap, h->stream));
   S.n = n;
   S.n_sorted = 0;
+  S.info_valid = false;
   h->pushes_since_sort = 1 << 30;  // force a sort before the next push
   return EPB_OK;
 }
@@ -863,6 +874,7 @@ int epb_load_uniform(epb_handle *h, int is, int32_t ppc, double density, const d
   EPB_CUDA(h, cudaMemsetAsync(S.gone, 0, (size_t)S.cap, h->stream));
   S.n = total;
   S.n_sorted = 0;
+  S.info_valid = false;
   h->pushes_since_sort = 1 << 30;
   EPB_CUDA(h, cudaGetLastError());
   return EPB_OK;
@@ -956,7 +968,7 @@ int epb_fields_final(epb_handle *h) {
 int epb_sort(epb_handle *h) {
   if (!h) return EPB_ERR_ARG;
   for (int is = 0; is < (int)h->sp.size(); is++) {
-    int rc = epb_sort_species(h, is);
+    int rc = h->sp[is].info_valid ? epb_sort_species_emitted(h, is) : epb_sort_species(h, is);
     if (rc) return rc;
   }
   h->pushes_since_sort = 0;
@@ -985,6 +997,18 @@ int epb_push(epb_handle *h) {
     auto launch = c.strict_fp ? epb_launch_push_strict : epb_launch_push_fast;
     const bool tiled = (c.ndims == 2);
     long long sorted = S.n_sorted < S.n ? S.n_sorted : S.n;
+    // layout 1: the last push before a sort also records every particle's place in the next
+    // order, so that sort needs neither a key pass nor rank atomics (sort.cu)
+    static const int no_emit = getenv("EPB_NO_EMIT") ? atoi(getenv("EPB_NO_EMIT")) : 0;
+    S.info_valid = false;
+    if (tiled && sorted > 0 && h->tg.layout == 1 && P.deposit && !no_emit && h->pushes_since_sort + 1 >= c.sort_interval) {
+      const size_t kb = ((size_t)h->tg.nkeys + 1) * sizeof(int);
+      EPB_CUDA(h, cudaMemsetAsync(S.key, 0xff, (size_t)S.n * sizeof(int), h->stream));
+      EPB_CUDA(h, cudaMemsetAsync(S.stay_cnt, 0, kb, h->stream));
+      EPB_CUDA(h, cudaMemsetAsync(S.arr_cnt, 0, kb, h->stream));
+      P.emit = 1;
+      S.info_valid = true;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_push) {
       cudaEventCreate(&e0); cudaEventCreate(&e1);

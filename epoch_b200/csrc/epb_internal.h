@@ -50,6 +50,12 @@ struct PushParams {
   long long first, last;   // particle range of a generic launch
   const int *tile_start;   // tiled launch: ntiles+1 offsets into the sorted prefix
   const int *cell_start;   // layout 1: nkeys+1 offsets (exclusive scan of the per-key counts)
+  // layout 1, push before a sort: the kernel records where every particle goes in the next
+  // order (key_out = next gather cell's key, rank_out = rank inside that key; bit 30 set = rank
+  // among the key's arrivals, to be offset by stay_cnt[key]) so the sort needs no atomics
+  int emit;
+  int *key_out, *rank_out;
+  int *stay_cnt, *arr_cnt;
   long long n_sorted_clip; // tile ranges are clipped to this count
   TileGeom tg;
   // particle boundary conditions (particles.F90:189-221, boundary.F90:1029-1462)
@@ -79,6 +85,10 @@ struct SpeciesDev {
   int *key = nullptr;
   int *tile_start = nullptr;
   int *cell_start = nullptr;  // layout 1: this species' copy of the key offsets
+  int *perm = nullptr;        // layout 1: scratch of the emitted sort (destination -> source index)
+  int *rank = nullptr;        // layout 1: per-particle rank emitted by the push (see PushParams::emit)
+  int *stay_cnt = nullptr, *arr_cnt = nullptr;  // layout 1: per-key counts emitted by the push
+  bool info_valid = false;    // key/rank/stay_cnt/arr_cnt describe the current particle set
   unsigned char *gone = nullptr;
 };
 
@@ -106,6 +116,7 @@ struct epb_handle {
   int out_cap = 0;
   int *h_counts = nullptr;      // pinned [64]
   int *d_scratch = nullptr;     // device ints
+  int *movers = nullptr;        // exchange: tail survivors that fill holes (27*out_cap+1)
   double *sendbuf = nullptr, *recvbuf = nullptr;  // halo + particle staging
   size_t sendbuf_elems = 0, recvbuf_elems = 0;
   void *nccl = nullptr;         // ncclComm_t
@@ -143,6 +154,8 @@ void epb_fdtd_tma_launch(epb_handle *h, bool is_e, double cx, double cy, double 
 
 // sort.cu
 int epb_sort_species(epb_handle *h, int is);
+int epb_sort_species_emitted(epb_handle *h, int is);
+#define EPB_RANK_ARRIVAL (1 << 30)
 void epb_make_tiles(const epb_config &cfg, TileGeom &tg);
 
 // exchange.cu

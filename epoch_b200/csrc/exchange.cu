@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(256) k_ppack(const __grid_constant__ PPackOp O
 }
 struct PUnpackOp {
   double *dst[7];
+  int *key;  // emitted sort records (layout 1) or null
   int nv, nd;
   long long first;
   int count;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) k_punpack(const __grid_constant__ PUnpack
     int q = 0;
     for (int d = 0; d < O.nd; d++) O.dst[d][i] = o[q++];
     for (int d = 3; d < 7; d++) O.dst[d][i] = o[q++];
+    if (O.key) O.key[i] = -1;  // no emitted sort record for an arrival
   }
 }
 // survivors in the tail [n_new, n_old) that must move into holes below n_new
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(256) k_tail_movers(const unsigned char *gone, 
 }
 struct FillOp {
   double *a[7];
+  int *key, *rank;  // emitted sort records travel with the particle (layout 1), else null
   unsigned char *gone;
   const int *idx;   // outbox list of one direction
   int count;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256) k_fill_holes(const __grid_constant__ Fill
 #pragma unroll
       for (int q = 0; q < 7; q++)
         if (F.a[q]) F.a[q][hole] = F.a[q][src];
+      if (F.key) { F.key[hole] = F.key[src]; F.rank[hole] = F.rank[src]; }
     }
   }
 }
@@ -338,7 +342,7 @@ int epb_particle_exchange(epb_handle *h, int is) {
     const long long n_old = S.n, n_new = S.n - gone_total;
     int *ctr = h->d_scratch;  // [0] mover count, [1] fill cursor
     EPB_CUDA(h, cudaMemsetAsync(ctr, 0, 2 * sizeof(int), h->stream));
-    k_tail_movers<<<nblk((size_t)gone_total), 256, 0, h->stream>>>(S.gone, n_new, n_old, S.key, ctr);
+    k_tail_movers<<<nblk((size_t)gone_total), 256, 0, h->stream>>>(S.gone, n_new, n_old, h->movers, ctr);
     h->launches++;
     for (int q = 0; q < 27; q++) {
       if (!cnt[q]) continue;
@@ -348,7 +352,9 @@ int epb_particle_exchange(epb_handle *h, int is) {
       F.idx = h->out_idx + (size_t)q * h->out_cap;
       F.count = cnt[q];
       F.n_new = n_new;
-      F.movers = S.key;
+      F.movers = h->movers;
+      F.key = S.info_valid ? S.key : nullptr;
+      F.rank = S.rank;
       F.cursor = ctr + 1;
       k_fill_holes<<<nblk((size_t)cnt[q]), 256, 0, h->stream>>>(F);
       h->launches++;
@@ -363,6 +369,7 @@ int epb_particle_exchange(epb_handle *h, int is) {
     for (int k = 0; k < 7; k++) O.dst[k] = arr[k];
     O.nv = nv; O.nd = nd;
     O.first = S.n;
+    O.key = S.info_valid ? S.key : nullptr;
     O.count = recvc[q];
     O.buf = h->recvbuf + recv_off[q];
     k_punpack<<<nblk((size_t)recvc[q]), 256, 0, h->stream>>>(O);

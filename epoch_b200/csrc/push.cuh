@@ -399,6 +399,67 @@ __device__ __forceinline__ void gamma_root(double s, double num, double &root) {
 #endif
 }
 
+// Edge deposit of a queued "semi-regular" particle of push_cell_2d: its nearest cell moved by one
+// cell along exactly one axis (dc = +-1), its owner lane has already accumulated the 3x3 core of
+// the stencil in registers, and only the values outside the core remain: the extra column/row at
+// +-2, and -- because the lane keeps no sum for the third jx column / jy row -- the prefix value
+// at +1 when dc = +1.  8 shared-memory updates instead of the general loop's 36.
+__device__ __forceinline__ void drain_edge(const PushParams &P, double *sJ, double fxo, double fxn, double fyo,
+                                           double fyn, double fjx, double fjy, double fjz, int key, int dcx,
+                                           int dcy, int jstride, int pitch) {
+  double gx[3], gy[3], nx[3], ny[3], hx[3], hy[3];
+  tri(fxo, gx[0], gx[1], gx[2]);
+  tri(fyo, gy[0], gy[1], gy[2]);
+  tri(fxn, nx[0], nx[1], nx[2]);
+  tri(fyn, ny[0], ny[1], ny[2]);
+  const double third = P.third;
+  if (dcx != 0) {
+    const double hxe = dcx > 0 ? nx[2] : nx[0];
+    if (dcx > 0) { hx[0] = 0.0 - gx[0]; hx[1] = nx[0] - gx[1]; hx[2] = nx[1] - gx[2]; }
+    else { hx[0] = nx[1] - gx[0]; hx[1] = nx[2] - gx[1]; hx[2] = 0.0 - gx[2]; }
+#pragma unroll
+    for (int q = 0; q < 3; q++) hy[q] = ny[q] - gy[q];
+    const double xfac1e = 0.5 * hxe;
+    const double hxs = hx[0] + hx[1] + hx[2];
+    const int oe = key + 2 * dcx;
+    double jyh = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++) {
+      const double yfac1 = gy[iy] + 0.5 * hy[iy];
+      const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+      const int row = (iy - 1) * pitch;
+      if (dcx < 0) smem_add(&sJ[oe + row], -(fjx * (hxe * yfac1)));
+      else smem_add(&sJ[key + 1 + row], -(fjx * (hxs * yfac1)));
+      if (iy < 2) {
+        jyh = jyh - fjy * (hy[iy] * xfac1e);
+        smem_add(&sJ[jstride + oe + row], jyh);
+      }
+      smem_add(&sJ[2 * jstride + oe + row], fjz * (hxe * yfac2));
+    }
+  } else {
+    const double hye = dcy > 0 ? ny[2] : ny[0];
+    if (dcy > 0) { hy[0] = 0.0 - gy[0]; hy[1] = ny[0] - gy[1]; hy[2] = ny[1] - gy[2]; }
+    else { hy[0] = ny[1] - gy[0]; hy[1] = ny[2] - gy[1]; hy[2] = 0.0 - gy[2]; }
+#pragma unroll
+    for (int q = 0; q < 3; q++) hx[q] = nx[q] - gx[q];
+    const double yfac1e = 0.5 * hye, yfac2e = third * hye;
+    const double hys = hy[0] + hy[1] + hy[2];
+    const int oe = key + 2 * dcy * pitch;
+    double jxh = 0.0;
+#pragma unroll
+    for (int ix = 0; ix < 3; ix++) {
+      const double xfac1 = gx[ix] + 0.5 * hx[ix];
+      if (ix < 2) {
+        jxh = jxh - fjx * (hx[ix] * yfac1e);
+        smem_add(&sJ[oe + ix - 1], jxh);
+      }
+      if (dcy < 0) smem_add(&sJ[jstride + oe + ix - 1], -(fjy * (hye * xfac1)));
+      else smem_add(&sJ[jstride + key + pitch + ix - 1], -(fjy * (hys * xfac1)));
+      smem_add(&sJ[2 * jstride + oe + ix - 1], fjz * (gx[ix] * yfac1e + hx[ix] * yfac2e));
+    }
+  }
+}
+
 // Deposit of queued particles (nearest cell changed: dcell != 0 in x and/or y): the general
 // loop of particles.F90:549-579 over xmin..xmax, ymin..ymax with shared-memory updates.
 __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, const double *Qd, const int *Qk,
@@ -407,6 +468,45 @@ __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, co
   const int pk = Qk[lane];
   const int key = pk & 1023, dcx = ((pk >> 10) & 3) - 1, dcy = ((pk >> 12) & 3) - 1;
   const double fjx = Qd[4 * QCAP + lane], fjy = Qd[5 * QCAP + lane], fjz = Qd[6 * QCAP + lane];
+  if (pk & (1 << 14)) {  // push_cell_2d: core already accumulated by the owner lane
+    drain_edge(P, sJ, Qd[0 * QCAP + lane], Qd[1 * QCAP + lane], Qd[2 * QCAP + lane], Qd[3 * QCAP + lane], fjx, fjy,
+               fjz, key, dcx, dcy, jstride, pitch);
+    return;
+  }
+  if (pk & (1 << 15)) {
+    // push_cell_2d, particle outside its lane's cell (stale order) whose nearest cell did not
+    // change: the 3x3 stencil without its six structurally cancelling values (last jx column,
+    // last jy row), 21 updates instead of the general loop's 27
+    double g3x[3], g3y[3], h3x[3], h3y[3];
+    tri(Qd[0 * QCAP + lane], g3x[0], g3x[1], g3x[2]);
+    tri(Qd[2 * QCAP + lane], g3y[0], g3y[1], g3y[2]);
+    tri(Qd[1 * QCAP + lane], h3x[0], h3x[1], h3x[2]);
+    tri(Qd[3 * QCAP + lane], h3y[0], h3y[1], h3y[2]);
+#pragma unroll
+    for (int q = 0; q < 3; q++) { h3x[q] = h3x[q] - g3x[q]; h3y[q] = h3y[q] - g3y[q]; }
+    const double third = P.third;
+    double jyh[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++) {
+      const double yfac1 = g3y[iy] + 0.5 * h3y[iy];
+      const double yfac2 = third * h3y[iy] + 0.5 * g3y[iy];
+      double jxh = 0.0;
+#pragma unroll
+      for (int ix = 0; ix < 3; ix++) {
+        const int o = key + (iy - 1) * pitch + (ix - 1);
+        if (ix < 2) {
+          jxh = jxh - fjx * (h3x[ix] * yfac1);
+          smem_add(&sJ[o], jxh);
+        }
+        if (iy < 2) {
+          jyh[ix] = jyh[ix] - fjy * (h3y[iy] * (g3x[ix] + 0.5 * h3x[ix]));
+          smem_add(&sJ[jstride + o], jyh[ix]);
+        }
+        smem_add(&sJ[2 * jstride + o], fjz * (g3x[ix] * yfac1 + h3x[ix] * yfac2));
+      }
+    }
+    return;
+  }
   double gx[5], gy[5], hx[5], hy[5];
   gx[0] = gx[4] = gy[0] = gy[4] = 0.0;
   tri(Qd[0 * QCAP + lane], gx[1], gx[2], gx[3]);
@@ -827,6 +927,8 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
   // this lane's cell (1-based cell indices as in the reference) and its particle count
   const int hcx = ttx * T2X + (lane & 15) + 1;
   const int hcy = tty * T2Y + warp * 2 + (lane >> 4) + 1;
+  const int my_key = tile * (T2X * T2Y) + warp * 32 + lane;
+  int stay = 0;  // particles of this lane's cell that stay in it (their rank in the next order)
   const int my_start = cs[warp * 32 + lane];
   const int my_cnt = cs[warp * 32 + lane + 1] - my_start;
   const int maxcnt = __reduce_max_sync(FULL, my_cnt);
@@ -954,10 +1056,11 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
         const double part_vz = part_uz * c * igamma;
         px_ = px_ + delta_x;
         py_ = py_ + delta_y;
+        int dir;
         {
           double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
           double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
-          const int dir = particle_bc<2>(P, pos, mom);
+          dir = particle_bc<2>(P, pos, mom);
           P.x[0][ci] = pos[0];
           P.x[1][ci] = pos[1];
           P.p[0][ci] = mom[0];
@@ -979,17 +1082,32 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
           fjx = fcx * P.part_q;
           fjy = fcy * P.part_q;
           fjz = fcz * P.part_q * part_vz;
-          if ((dcx | dcy) != 0 || cx1 != hcx || cy1 != hcy) {
-            extras = true;
-            key = (cy1 - oy) * TW + (cx1 - ox);
-            q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          if (P.emit && dir < 0 && cx3 >= 0 && cx3 < P.n[0] && cy3 >= 0 && cy3 < P.n[1]) {
+            // record for the next sort: (cx3, cy3) is the cell the next push gathers in
+            const int nkey = ((cy3 / T2Y) * P.tg.nt[0] + (cx3 >> 4)) * (T2X * T2Y) + (cy3 % T2Y) * T2X + (cx3 & 15);
+            P.key_out[ci] = nkey;
+            P.rank_out[ci] = (nkey == my_key) ? stay++ : (atomicAdd(&P.arr_cnt[nkey], 1) | EPB_RANK_ARRIVAL);
+          }
+          key = (cy1 - oy) * TW + (cx1 - ox);
+          q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          if (cx1 != hcx || cy1 != hcy || (dcx != 0 && dcy != 0)) {
+            extras = true;  // not this lane's cell (stale order), or moved diagonally
+            if ((dcx | dcy) == 0) key |= 1 << 15;  // 3x3 stencil: 21-update drain
           } else {
-            // dcell = 0 in this lane's own cell: hx = new weights - gx on the same three cells
-            // (particles.F90:521-538); sums of fj*w per stencil point, prefixes applied at the end
-            tri(fxn, hx[0], hx[1], hx[2]);
-            tri(fyn, hy[0], hy[1], hy[2]);
-#pragma unroll
-            for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
+            // This lane's own cell, nearest cell unchanged or moved by one cell along one axis.
+            // New weights on the 3x3 core (particles.F90:521-538 with the shift by dcell); the
+            // part of a moved particle's stencil outside the core is queued (drain_edge).
+            double wm, w0, wp;
+            tri(fxn, wm, w0, wp);
+            hx[0] = (dcx == 0 ? wm : dcx > 0 ? 0.0 : w0) - gx[0];
+            hx[1] = (dcx == 0 ? w0 : dcx > 0 ? wm : wp) - gx[1];
+            hx[2] = (dcx == 0 ? wp : dcx > 0 ? w0 : 0.0) - gx[2];
+            const double hxa = hx[0] + (dcx < 0 ? wm : 0.0);  // running jx prefix enters the core with column -2
+            tri(fyn, wm, w0, wp);
+            hy[0] = (dcy == 0 ? wm : dcy > 0 ? 0.0 : w0) - gy[0];
+            hy[1] = (dcy == 0 ? w0 : dcy > 0 ? wm : wp) - gy[1];
+            hy[2] = (dcy == 0 ? wp : dcy > 0 ? w0 : 0.0) - gy[2];
+            const double hya = hy[0] + (dcy < 0 ? wm : 0.0);
             double xfac1[3], yfac1[3], yfac2[3];
 #pragma unroll
             for (int q = 0; q < 3; q++) {
@@ -997,8 +1115,8 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
               yfac1[q] = gy[q] + 0.5 * hy[q];
               yfac2[q] = third * hy[q] + 0.5 * gy[q];
             }
-            const double fhx0 = fjx * hx[0], fhx1 = fjx * hx[1];
-            const double fhy0 = fjy * hy[0], fhy1 = fjy * hy[1];
+            const double fhx0 = fjx * hxa, fhx1 = fjx * hx[1];
+            const double fhy0 = fjy * hya, fhy1 = fjy * hy[1];
 #pragma unroll
             for (int iy = 0; iy < 3; iy++) {
               AX[iy][0] += fhx0 * yfac1[iy];
@@ -1015,6 +1133,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
 #pragma unroll
               for (int iy = 0; iy < 3; iy++) AZ[iy][ix] += zg * yfac1[iy] + zh * yfac2[iy];
             }
+            if ((dcx | dcy) != 0) { extras = true; key |= 1 << 14; }
           }
         }
       }
@@ -1044,6 +1163,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
     __syncwarp();
     drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
   }
+  if (P.emit) P.stay_cnt[my_key] = stay;
   // ---- flush this lane's cell sums: prefixes of particles.F90:563-571, one update per point ----
   if (P.deposit && my_cnt > 0) {
     const int hb = (hcy - oy) * TW + (hcx - ox);

@@ -136,6 +136,70 @@ __global__ void __launch_bounds__(256) k_scatter_il(const __grid_constant__ Scat
   }
 }
 
+// ---- sort from the records the push emitted (PushParams::emit) ---------------------------------
+// Particles without a record (pushed by the generic kernel, arrived from a neighbour, wrapped)
+// get the predicted key here and a rank among their key's arrivals.
+__global__ void __launch_bounds__(256) k_keys_fix(const __grid_constant__ KeyOp K, int *rank, int *arr_cnt) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = (K.n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool missing = i < K.n && K.key[i] < 0;
+    if (!__any_sync(0xffffffffu, missing)) continue;
+    int key = 0;
+    if (missing) { key = cell_key(K, i); K.key[i] = key; }
+    const int r = agg_inc(arr_cnt, key, missing);
+    if (missing) rank[i] = r | EPB_RANK_ARRIVAL;
+  }
+}
+__global__ void __launch_bounds__(256) k_add_counts(const int *a, const int *b, int *out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+// The emitted ranks of a warp's 32 source particles differ by the number of particles that
+// left each cell before them, so a direct scatter writes partial sectors (measured: 21 sectors
+// per store, 2x DRAM traffic).  Instead the 4-byte source index is scattered (perm[dst] = src)
+// and the seven arrays are then gathered with fully coalesced stores.
+struct PermOp {
+  long long n;
+  const int *key, *rank, *stay, *start;
+  int *perm;
+};
+__global__ void __launch_bounds__(256) k_perm_emitted(const __grid_constant__ PermOp S) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += stride) {
+    const int key = S.key[i];
+    int r = S.rank[i];
+    if (r & EPB_RANK_ARRIVAL) r = (r & ~EPB_RANK_ARRIVAL) + __ldg(S.stay + key);
+    const int l = key & 31;
+    const int *st = S.start + (key - l);
+    const int s0 = __ldg(st);
+    int prev = s0, acc = 0;
+#pragma unroll 8
+    for (int q = 0; q < 32; q++) {
+      const int nxt = __ldg(st + q + 1);
+      const int c = nxt - prev;
+      prev = nxt;
+      const int lim = r + (q < l ? 1 : 0);
+      acc += c < lim ? c : lim;
+    }
+    S.perm[(long long)s0 + acc] = (int)i;
+  }
+}
+struct GatherOp {
+  const double *src[7];
+  double *dst[7];
+  long long n;
+  const int *perm;
+};
+__global__ void __launch_bounds__(256) k_gather_perm(const __grid_constant__ GatherOp S) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < S.n; j += stride) {
+    const int i = S.perm[j];
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+      if (S.src[q]) S.dst[q][j] = S.src[q][i];
+  }
+}
+
 __global__ void k_tile_start(const int *cell_start, int *tile_start, int ntiles, int cpt) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t <= ntiles) tile_start[t] = cell_start[(size_t)t * cpt];
@@ -163,10 +227,83 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   tg.layout = (nd == 2 && variant >= 2 && variant <= 4) ? 1 : 0;
 }
 
+static void fill_keyop(epb_handle *h, SpeciesDev &S, KeyOp &K) {
+  const epb_config &c = h->cfg;
+  for (int d = 0; d < 3; d++) {
+    K.x[d] = S.buf[S.cur][d];
+    K.nloc[d] = c.n[d];
+    K.gmin[d] = c.grid_min_local[d];
+    K.dx[d] = c.dx[d];
+    K.p[d] = S.buf[S.cur][3 + d];
+    K.idx[d] = d < c.ndims ? 1.0 / c.dx[d] : 0.0;
+  }
+  K.n = S.n;
+  K.nd = c.ndims;
+  K.tg = h->tg;
+  K.key = S.key;
+  K.count = h->cell_count;
+  K.predict = (h->tg.layout == 1);
+  K.ipart_mc = 1.0 / (EPB_C * S.cfg.mass);
+  K.dtco2 = EPB_C * (c.dt / 2.0);
+}
+
+// Sort from the records of the last push (layout 1): fix-up of the particles without a record,
+// counts = stayers + arrivals, scan, atomic-free scatter.
+int epb_sort_species_emitted(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  const int nkeys = h->tg.nkeys;
+  if (S.n > 0) {
+    KeyOp K;
+    fill_keyop(h, S, K);
+    long long nb = (S.n + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    k_keys_fix<<<(int)nb, 256, 0, h->stream>>>(K, S.rank, S.arr_cnt);
+    h->launches++;
+  }
+  k_add_counts<<<148 * 8, 256, 0, h->stream>>>(S.stay_cnt, S.arr_cnt, h->cell_count, nkeys + 1);
+  h->launches++;
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, S.cell_start, nkeys + 1, h->stream);
+  if (need > h->cub_tmp_bytes) {
+    cudaFree(h->cub_tmp);
+    EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
+    h->cub_tmp_bytes = need;
+  }
+  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_tmp, need, h->cell_count, S.cell_start, nkeys + 1, h->stream));
+  h->launches++;
+  if (S.n > 0) {
+    PermOp Pm;
+    Pm.n = S.n;
+    Pm.key = S.key;
+    Pm.rank = S.rank;
+    Pm.stay = S.stay_cnt;
+    Pm.start = S.cell_start;
+    Pm.perm = S.perm;
+    long long nb = (S.n + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    k_perm_emitted<<<(int)nb, 256, 0, h->stream>>>(Pm);
+    h->launches++;
+    GatherOp Ga;
+    for (int q = 0; q < 7; q++) { Ga.src[q] = S.buf[S.cur][q]; Ga.dst[q] = S.buf[S.cur ^ 1][q]; }
+    Ga.n = S.n;
+    Ga.perm = S.perm;
+    k_gather_perm<<<(int)nb, 256, 0, h->stream>>>(Ga);
+    h->launches++;
+    S.cur ^= 1;
+  }
+  k_tile_start<<<(h->tg.ntiles + 1 + 255) / 256, 256, 0, h->stream>>>(S.cell_start, S.tile_start, h->tg.ntiles, h->tg.cpt);
+  h->launches++;
+  S.n_sorted = S.n;
+  S.info_valid = false;
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
 int epb_sort_species(epb_handle *h, int is) {
   SpeciesDev &S = h->sp[is];
   const epb_config &c = h->cfg;
   const int nkeys = h->tg.nkeys;
+  S.info_valid = false;
   EPB_CUDA(h, cudaMemsetAsync(h->cell_count, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
   if (S.n > 0) {
     KeyOp K;
