@@ -406,7 +406,7 @@ __device__ __forceinline__ void gamma_root(double s, double num, double &root) {
 // at +1 when dc = +1.  8 shared-memory updates instead of the general loop's 36.
 __device__ __forceinline__ void drain_edge(const PushParams &P, double *sJ, double fxo, double fxn, double fyo,
                                            double fyn, double fjx, double fjy, double fjz, int key, int dcx,
-                                           int dcy, int jstride, int pitch) {
+                                           int dcy, int jstride, int pitch, bool core_has_third) {
   double gx[3], gy[3], nx[3], ny[3], hx[3], hy[3];
   tri(fxo, gx[0], gx[1], gx[2]);
   tri(fyo, gy[0], gy[1], gy[2]);
@@ -429,7 +429,7 @@ __device__ __forceinline__ void drain_edge(const PushParams &P, double *sJ, doub
       const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
       const int row = (iy - 1) * pitch;
       if (dcx < 0) smem_add(&sJ[oe + row], -(fjx * (hxe * yfac1)));
-      else smem_add(&sJ[key + 1 + row], -(fjx * (hxs * yfac1)));
+      else if (!core_has_third) smem_add(&sJ[key + 1 + row], -(fjx * (hxs * yfac1)));
       if (iy < 2) {
         jyh = jyh - fjy * (hy[iy] * xfac1e);
         smem_add(&sJ[jstride + oe + row], jyh);
@@ -454,7 +454,7 @@ __device__ __forceinline__ void drain_edge(const PushParams &P, double *sJ, doub
         smem_add(&sJ[oe + ix - 1], jxh);
       }
       if (dcy < 0) smem_add(&sJ[jstride + oe + ix - 1], -(fjy * (hye * xfac1)));
-      else smem_add(&sJ[jstride + key + pitch + ix - 1], -(fjy * (hys * xfac1)));
+      else if (!core_has_third) smem_add(&sJ[jstride + key + pitch + ix - 1], -(fjy * (hys * xfac1)));
       smem_add(&sJ[2 * jstride + oe + ix - 1], fjz * (gx[ix] * yfac1e + hx[ix] * yfac2e));
     }
   }
@@ -470,7 +470,7 @@ __device__ __forceinline__ void drain_extras(const PushParams &P, double *sJ, co
   const double fjx = Qd[4 * QCAP + lane], fjy = Qd[5 * QCAP + lane], fjz = Qd[6 * QCAP + lane];
   if (pk & (1 << 14)) {  // push_cell_2d: core already accumulated by the owner lane
     drain_edge(P, sJ, Qd[0 * QCAP + lane], Qd[1 * QCAP + lane], Qd[2 * QCAP + lane], Qd[3 * QCAP + lane], fjx, fjy,
-               fjz, key, dcx, dcy, jstride, pitch);
+               fjz, key, dcx, dcy, jstride, pitch, (pk & (1 << 16)) != 0);
     return;
   }
   if (pk & (1 << 15)) {
@@ -633,7 +633,8 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
       }
     }
     int key = -1;       // cell key of a lane that takes part in the transposed reduction
-    bool extras = false;
+    bool extras = false;  // queued: general loop (moved diagonally)
+    bool edge = false;    // queued: only the part of the stencil outside the 3x3 core
     int dcx = 0, dcy = 0;
     double q_fxo = 0, q_fxn = 0, q_fyo = 0, q_fyn = 0, fjx = 0, fjy = 0, fjz = 0;
     if (active) {
@@ -734,17 +735,27 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
           fjy = fcy * P.part_q;
           fjz = fcz * P.part_q * part_vz;
           const int k = (cy1 - oy) * TW + (cx1 - ox);
-          if ((dcx | dcy) != 0) {
-            extras = true;
-            key = k;  // kept for the queue entry; excluded from the reduction below
-            q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          key = k;
+          q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          if (dcx != 0 && dcy != 0) {
+            extras = true;  // moved diagonally (rare): general loop; excluded from the reduction below
           } else {
-            key = k;
-            // dcell = 0: hx = new weights - gx on the same three cells (particles.F90:521-538)
-            tri(fxn, hx[0], hx[1], hx[2]);
-            tri(fyn, hy[0], hy[1], hy[2]);
-#pragma unroll
-            for (int q = 0; q < 3; q++) { hx[q] = hx[q] - gx[q]; hy[q] = hy[q] - gy[q]; }
+            // Nearest cell unchanged, or moved by one cell along one axis.  New weights on the 3x3
+            // core around the old cell (particles.F90:521-538 with the shift by dcell); the running
+            // jx / jy prefixes of a particle that moved towards -x / -y enter the core with the
+            // value of the outer column / row (hxa, hya).  What lies outside the core (5 or 8
+            // values) is queued and deposited by drain_edge.
+            double wm, w0, wp;
+            tri(fxn, wm, w0, wp);
+            hx[0] = (dcx == 0 ? wm : dcx > 0 ? 0.0 : w0) - gx[0];
+            hx[1] = (dcx == 0 ? w0 : dcx > 0 ? wm : wp) - gx[1];
+            hx[2] = (dcx == 0 ? wp : dcx > 0 ? w0 : 0.0) - gx[2];
+            const double hxa = hx[0] + (dcx < 0 ? wm : 0.0);
+            tri(fyn, wm, w0, wp);
+            hy[0] = (dcy == 0 ? wm : dcy > 0 ? 0.0 : w0) - gy[0];
+            hy[1] = (dcy == 0 ? w0 : dcy > 0 ? wm : wp) - gy[1];
+            hy[2] = (dcy == 0 ? wp : dcy > 0 ? w0 : 0.0) - gy[2];
+            const double hya = hy[0] + (dcy < 0 ? wm : 0.0);
             double xfac1[3], jyh[3] = {0.0, 0.0, 0.0};
 #pragma unroll
             for (int ix = 0; ix < 3; ix++) xfac1[ix] = gx[ix] + 0.5 * hx[ix];
@@ -753,11 +764,12 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
             for (int iy = 0; iy < 3; iy++) {
               const double yfac1 = gy[iy] + 0.5 * hy[iy];
               const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+              const double hyw = iy == 0 ? hya : hy[iy];
               double jxh = 0.0;
 #pragma unroll
               for (int ix = 0; ix < 3; ix++) {
-                const double wx = hx[ix] * yfac1;
-                const double wy = hy[iy] * xfac1[ix];
+                const double wx = (ix == 0 ? hxa : hx[ix]) * yfac1;
+                const double wy = hyw * xfac1[ix];
                 const double wz = gx[ix] * yfac1 + hx[ix] * yfac2;
                 jxh = jxh - fjx * wx;
                 jyh[ix] = jyh[ix] - fjy * wy;
@@ -766,13 +778,14 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
                 col[((V21 ? 12 : 18) + iy * 3 + ix) * SPITCH] = fjz * wz;
               }
             }
+            if ((dcx | dcy) != 0) { edge = true; }
           }
         }
       }
     }
     if (!P.deposit) continue;
     // ---- queue the particles with a wider stencil -------------------------------------
-    const unsigned em = __ballot_sync(FULL, extras);
+    const unsigned em = __ballot_sync(FULL, extras || edge);
     if (em) {
       const int ne = __popc(em);
       if (qcount + ne > QCAP) {
@@ -781,13 +794,14 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         __syncwarp();
         qcount = 0;
       }
-      if (extras) {
+      if (extras || edge) {
         const int slot = qcount + __popc(em & lt_mask);
-        Qk[slot] = key | ((dcx + 1) << 10) | ((dcy + 1) << 12);
+        // bit 14: edge entry; bit 16: the core already holds the third jx column / jy row
+        Qk[slot] = key | ((dcx + 1) << 10) | ((dcy + 1) << 12) | (edge ? (1 << 14) | (V21 ? 0 : 1 << 16) : 0);
         Qd[0 * QCAP + slot] = q_fxo; Qd[1 * QCAP + slot] = q_fxn;
         Qd[2 * QCAP + slot] = q_fyo; Qd[3 * QCAP + slot] = q_fyn;
         Qd[4 * QCAP + slot] = fjx; Qd[5 * QCAP + slot] = fjy; Qd[6 * QCAP + slot] = fjz;
-        key = -1;
+        if (extras) key = -1;
       }
       qcount += ne;
     }
