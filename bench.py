@@ -37,6 +37,20 @@ def c2_deck(n_local, ppc, nproc, temp_k=1.0e7, density=1.0e25):
                   nproc=(nproc[0], nproc[1], 1))
 
 
+def c4_deck(n_local, ppc, nproc, temp_k=1.0e7, density=1.0e25):
+    """BASELINE.md C4 shape: epoch3d uniform thermal electrons, periodic, one n_local^3 block per GPU."""
+    from epoch_b200 import deck as D
+    debye = math.sqrt(D.epsilon0 * D.kb * temp_k / (density * D.q0 ** 2))
+    n = [n_local * nproc[0], n_local * nproc[1], n_local * nproc[2]]
+    sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=ppc, density=density, temp=(temp_k,) * 3)]
+    return D.Deck(3, n, [0.0] * 3, [debye * k for k in n], ["periodic"] * 6, species=sp, nproc=tuple(nproc))
+
+
+def split_3d(nranks):
+    """8 -> (2,2,2), 4 -> (1,2,2), 2 -> (1,1,2), 1 -> (1,1,1) (epoch3d mpi_routines.F90:127-153 on a cube)."""
+    return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[nranks]
+
+
 def split_2d(nranks):
     """split_domain's minimum-surface rule for a square per-rank tile (mpi_routines.F90:107-138):
     8 -> (2,4), 4 -> (2,2), 2 -> (1,2), 1 -> (1,1)."""
@@ -157,11 +171,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", dest="n", type=int, default=4096, help="cells per side per GPU")
-    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--ppc", type=int, default=None)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU")
     ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "8")))
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "c4":
+        if args.n == 4096:
+            args.n = 384
+        args.ppc = args.ppc or 8
+    args.ppc = args.ppc or 64
     if args.impl == "reference":
         return run_reference(args)
     # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
@@ -183,8 +204,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    nproc = split_2d(world)
-    dk = c2_deck(args.n, args.ppc, nproc)
+    if args.workload == "c4":
+        nproc = split_3d(world)
+        dk = c4_deck(args.n, args.ppc, nproc)
+    else:
+        nproc = split_2d(world)
+        dk = c2_deck(args.n, args.ppc, nproc)
     stream = torch.cuda.Stream()
     sim = Simulation(dk, rank=rank, strict_fp=bool(args.strict), sort_interval=args.sort_interval,
                      capacity_factor=1.02 if world == 1 else 1.15, stream=stream.cuda_stream)
@@ -237,7 +262,7 @@ def main():
     # from pinned memory, and reads back the step's results: the global particle count
     # (update_particle_count), the field energies (calc_total_energy_sum) and the Ey array as
     # a field dump would.  The particle state itself stays device-resident by design.
-    ny1 = sim.geo["n"][1] + 1
+    ny1 = (sim.geo["n"][1] + 1) * (sim.geo["n"][2] + 1 if args.workload == "c4" else 1)
     src = torch.zeros(2, ny1, dtype=torch.float64).pin_memory()
     ey_host = torch.empty(sim.shape, dtype=torch.float64).pin_memory()
     h2d = 2 * 2 * ny1 * 8
@@ -266,7 +291,9 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        bytes_per_update = 88.0 + 120.0 / args.ppc       # push+deposit kernel
+        is3d = args.workload == "c4"
+        # push+deposit kernel, particle state + 120 B/cell of E/B/J traffic
+        bytes_per_update = (104.0 if is3d else 88.0) + 120.0 / args.ppc
         achieved = (n_local * bytes_per_update / (push_ms * 1e-3)) / 1e9 if push_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "push_traffic_bytes.json")
@@ -279,10 +306,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"epoch2d uniform thermal plasma, periodic, {args.n}x{args.n} cells per GPU, "
-                                   f"{args.ppc} ppc ({n_local} particles per GPU), triangle shape, Yee order 2 "
-                                   "(BASELINE C2)",
-                       "decomposition": f"{nproc[0]}x{nproc[1]}", "sort_interval": args.sort_interval,
+            "config": {"workload": (f"epoch3d uniform thermal plasma, periodic, {args.n}^3 cells per GPU, "
+                                    f"{args.ppc} ppc ({n_local} particles per GPU), triangle shape, Yee order 2 "
+                                    "(BASELINE C4 per-GPU share)") if is3d else
+                                   (f"epoch2d uniform thermal plasma, periodic, {args.n}x{args.n} cells per GPU, "
+                                    f"{args.ppc} ppc ({n_local} particles per GPU), triangle shape, Yee order 2 "
+                                    "(BASELINE C2)"),
+                       "decomposition": "x".join(str(k) for k in nproc), "sort_interval": args.sort_interval,
                        "strict_fp": int(args.strict), "particles_total": n_total,
                        "l2_policy": "inputs (51.5 GB of particle state per GPU) far exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -290,7 +320,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "push_tiled_2d (push+deposit)", "bytes_per_update": bytes_per_update,
+                         "kernel": "push_tiled_3d (push+deposit)" if is3d else "push_tiled_2d (push+deposit)",
+                         "bytes_per_update": bytes_per_update,
                          "kernel_ms": push_ms, "kernel_launches": push_n,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
         }

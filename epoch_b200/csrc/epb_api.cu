@@ -995,7 +995,8 @@ int epb_push(epb_handle *h) {
     PushParams P;
     fill_push_params(h, is, P);
     auto launch = c.strict_fp ? epb_launch_push_strict : epb_launch_push_fast;
-    const bool tiled = (c.ndims == 2);
+    static const int no3d = getenv("EPB_NO_TILED_3D") ? atoi(getenv("EPB_NO_TILED_3D")) : 0;
+    const bool tiled = (c.ndims == 2) || (c.ndims == 3 && !no3d);
     long long sorted = S.n_sorted < S.n ? S.n_sorted : S.n;
     // layout 1: the last push before a sort also records every particle's place in the next
     // order, so that sort needs neither a key pass nor rank atomics (sort.cu)

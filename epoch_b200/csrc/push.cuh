@@ -1221,6 +1221,404 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
 }
 
 
+// ---------------------------------------------------------------------------
+// Tiled 3D kernel
+// ---------------------------------------------------------------------------
+// One CTA (16 warps) per 8x8x8-cell tile of the cell-sorted layout, one CTA per SM.  J is
+// accumulated in a shared tile (+3 halo cells, 66 KB) and flushed once with global reductions;
+// E/B are gathered through the read-only path (a 14^3 x 6 tile does not fit beside the J tile
+// and the reduction scratch; the tile's fields stay L1/L2 resident).  The deposit uses the
+// transposition of push_tiled_2d, generalised to any number of cells per warp (8 particles per
+// cell in the C4 workload means ~4 cells per batch): the lanes of a batch are first grouped by
+// cell key so that lanes of one cell own adjacent scratch columns; then, plane by plane of the
+// 3x3x3 stencil (21 + 21 + 12 = 54 values that do not cancel structurally), every lane stores
+// its values in its column and lane q sums row q run by run, one shared update per (cell, value).
+// Particles whose nearest cell changed (wider stencil) are queued per warp and deposited with
+// the reference's general loop (epoch3d particles.F90:603-648) on the shared tile.
+constexpr int T3 = 8, HALO3 = 3, JW3 = T3 + 2 * HALO3, JT3 = JW3 * JW3 * JW3;
+constexpr int P3_THREADS = 512, P3_WARPS = P3_THREADS / 32;
+constexpr int Q3CAP = 16, Q3DBL = 9, SLOW3CAP = 254;
+constexpr size_t PUSH3D_SMEM =
+    sizeof(double) * ((size_t)3 * JT3 + (size_t)P3_WARPS * SROWS * SPITCH + (size_t)P3_WARPS * Q3DBL * Q3CAP) +
+    sizeof(int) * ((size_t)P3_WARPS * Q3CAP + (size_t)P3_WARPS * 32 + SLOW3CAP + 2);
+
+// General deposit of queued particles on the shared tile: epoch3d particles.F90:603-648.
+__device__ __noinline__ void drain_extras_3d(const PushParams &P, double *sJ, const double *Qd, const int *Qk, int n,
+                                             int lane) {
+  if (lane >= n) return;
+  const int pk = Qk[lane];
+  const int key = pk & 4095;
+  int dcell[3] = {((pk >> 12) & 3) - 1, ((pk >> 14) & 3) - 1, ((pk >> 16) & 3) - 1};
+  const double fjx = Qd[6 * Q3CAP + lane], fjy = Qd[7 * Q3CAP + lane], fjz = Qd[8 * Q3CAP + lane];
+  double G[3][5], H[3][5];
+  int mn[3], mx[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    G[d][0] = G[d][4] = 0.0;
+    tri(Qd[(2 * d) * Q3CAP + lane], G[d][1], G[d][2], G[d][3]);
+    double wm, w0, wp;
+    tri(Qd[(2 * d + 1) * Q3CAP + lane], wm, w0, wp);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      const int r = q - 2 - dcell[d];
+      H[d][q] = ((r == -1) ? wm : (r == 0) ? w0 : (r == 1) ? wp : 0.0) - G[d][q];
+    }
+    mn[d] = -1 + (dcell[d] - 1) / 2;
+    mx[d] = 1 + (dcell[d] + 1) / 2;
+  }
+  const double *gx = &G[0][2], *gy = &G[1][2], *gz = &G[2][2];
+  const double *hx = &H[0][2], *hy = &H[1][2], *hz = &H[2][2];
+  const double third = P.third;
+  double jzh[5][5];
+  for (int a = 0; a < 5; a++)
+    for (int b = 0; b < 5; b++) jzh[a][b] = 0.0;
+  for (int iz = mn[2]; iz <= mx[2]; iz++) {
+    const double zfac1 = gz[iz] + 0.5 * hz[iz];
+    const double zfac2 = third * hz[iz] + 0.5 * gz[iz];
+    const double gz_iz = gz[iz], hz_iz = hz[iz];
+    double jyh[5] = {0, 0, 0, 0, 0};
+    for (int iy = mn[1]; iy <= mx[1]; iy++) {
+      const double yfac1 = gy[iy] + 0.5 * hy[iy];
+      const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+      const double hygz = hy[iy] * gz_iz;
+      const double hyhz = hy[iy] * hz_iz;
+      const double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
+      const double hzyfac1 = hz_iz * yfac1;
+      const double hzyfac2 = hz_iz * yfac2;
+      double jxh = 0.0;
+      for (int ix = mn[0]; ix <= mx[0]; ix++) {
+        const double xfac1 = gx[ix] + 0.5 * hx[ix];
+        const double xfac2 = third * hx[ix] + 0.5 * gx[ix];
+        const double wx = hx[ix] * yzfac;
+        const double wy = xfac1 * hygz + xfac2 * hyhz;
+        const double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
+        jxh = jxh - fjx * wx;
+        jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+        jzh[iy + 2][ix + 2] = jzh[iy + 2][ix + 2] - fjz * wz;
+        const int o = key + (iz * JW3 + iy) * JW3 + ix;
+        smem_add(&sJ[o], jxh);
+        smem_add(&sJ[JT3 + o], jyh[ix + 2]);
+        smem_add(&sJ[2 * JT3 + o], jzh[iy + 2][ix + 2]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_constant__ PushParams P) {
+  extern __shared__ double sm[];
+  double *sJ = sm;                                       // [3][JW3][JW3][JW3]
+  double *sS_all = sJ + 3 * JT3;                         // [warps][27][33]
+  double *sQd_all = sS_all + P3_WARPS * SROWS * SPITCH;  // [warps][9][Q3CAP]
+  int *sQk_all = reinterpret_cast<int *>(sQd_all + P3_WARPS * Q3DBL * Q3CAP);
+  int *sRK_all = sQk_all + P3_WARPS * Q3CAP;
+  int *sSlow = sRK_all + P3_WARPS * 32;
+  int *sSlowCount = sSlow + SLOW3CAP;
+  const int tile = blockIdx.x;
+  const int ttx = tile % P.tg.nt[0], tty = (tile / P.tg.nt[0]) % P.tg.nt[1], ttz = tile / (P.tg.nt[0] * P.tg.nt[1]);
+  const int ox = ttx * T3 + 1 - HALO3;  // cell index of shared column 0
+  const int oy = tty * T3 + 1 - HALO3;
+  const int oz = ttz * T3 + 1 - HALO3;
+  const long long start = P.tile_start[tile];
+  long long end = P.tile_start[tile + 1];
+  if (end > P.n_sorted_clip) end = P.n_sorted_clip;
+  if (start >= end) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *sSlowCount = 0;
+  for (int q = tid; q < 3 * JT3; q += P3_THREADS) sJ[q] = 0.0;
+  __syncthreads();
+
+  const double c = EPB_C;
+  const double third = P.third;
+  double *S = sS_all + warp * SROWS * SPITCH;
+  double *Qd = sQd_all + warp * Q3DBL * Q3CAP;
+  int *Qk = sQk_all + warp * Q3CAP;
+  int *RK = sRK_all + warp * 32;
+  int qcount = 0;  // warp-uniform
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // lane q owns row q of every plane pass: rows 0..5 = jx(iy, ix<2), 6..11 = jy(iy<2, ix), 12..20 = jz(iy, ix)
+  int off0;
+  {
+    int comp, diy, dix;
+    if (lane < 6) { comp = 0; diy = lane / 2; dix = lane % 2; }
+    else if (lane < 12) { comp = 1; diy = (lane - 6) / 3; dix = (lane - 6) % 3; }
+    else { comp = 2; diy = ((lane - 12) / 3) % 3; dix = (lane - 12) % 3; }
+    off0 = comp * JT3 + ((0 - 1) * JW3 + (diy - 1)) * JW3 + (dix - 1);
+  }
+
+  long long i = start + warp * 32 + lane;
+  double n_x = 0, n_y = 0, n_z = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
+  if (i < end) {
+    n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i]; n_z = P.x[2][i];
+    n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
+  }
+  for (; i - lane < end; i += P3_THREADS) {
+    const bool active = i < end;
+    const double part_weight = n_w;
+    double pp[3] = {n_x - P.grid_min_local[0], n_y - P.grid_min_local[1], n_z - P.grid_min_local[2]};
+    double part_ux = n_px * P.ipart_mc;
+    double part_uy = n_py * P.ipart_mc;
+    double part_uz = n_pz * P.ipart_mc;
+    {
+      const long long in = i + P3_THREADS;
+      if (in < end) {
+        n_w = P.w[in]; n_x = P.x[0][in]; n_y = P.x[1][in]; n_z = P.x[2][in];
+        n_px = P.p[0][in]; n_py = P.p[1][in]; n_pz = P.p[2][in];
+      }
+    }
+    // ---- phase A: half-step move and nearest cell (epoch3d particles.F90:320-370) ---------
+    int key = -1;
+    int cell1[3] = {0, 0, 0};
+    double cell_r[3] = {0, 0, 0};
+    if (active) {
+      double root;
+      gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
+      pp[0] = pp[0] + part_ux * root;
+      pp[1] = pp[1] + part_uy * root;
+      pp[2] = pp[2] + part_uz * root;
+      bool fast = true;
+      const int org[3] = {ox, oy, oz};
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        cell_r[d] = pp[d] * P.idx[d];
+        cell1[d] = __double2int_rd(cell_r[d] + 0.5) + 1;
+        fast = fast && (cell1[d] - 2 >= org[d]) && (cell1[d] + 2 <= org[d] + JW3 - 1);
+      }
+      if (!fast) {
+        const int slot = atomicAdd(sSlowCount, 1);
+        if (slot < SLOW3CAP) sSlow[slot] = (int)i;
+        else push_one<3>(P, i);
+      } else {
+        key = ((cell1[2] - oz) * JW3 + (cell1[1] - oy)) * JW3 + (cell1[0] - ox);
+      }
+    }
+    // ---- group the lanes by cell key: equal keys get adjacent scratch columns ----------------
+    int pos = 0;
+    unsigned bnd = 0;
+    if (P.deposit) {
+      unsigned rest = __ballot_sync(FULL, key >= 0);
+      int base = 0;
+      while (rest) {
+        const int l = __ffs(rest) - 1;
+        const int kl = __shfl_sync(FULL, key, l);
+        const unsigned m = __ballot_sync(FULL, key == kl);
+        if (key == kl) pos = base + __popc(m & lt_mask);
+        base += __popc(m);
+        bnd |= 1u << (base - 1);
+        if (lane == l) RK[base - 1] = kl;
+        rest &= ~m;
+      }
+    }
+    // ---- phase B: gather, Boris rotation, move, store ------------------------------------
+    bool regular = false, extras = false;
+    int dc[3] = {0, 0, 0};
+    double G[3][3], H[3][3];  // g weights at t+dt/2; H: staggered weights, later (new weights - g)
+    double fo[3] = {0, 0, 0}, fn[3] = {0, 0, 0};
+    double fjx = 0, fjy = 0, fjz = 0;
+    if (key >= 0) {
+      int cell2[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        fo[d] = (double)(cell1[d] - 1) - cell_r[d];
+        tri(fo[d], G[d][0], G[d][1], G[d][2]);
+        int c2 = __double2int_rd(cell_r[d]);
+        tri((double)c2 - cell_r[d] + 0.5, H[d][0], H[d][1], H[d][2]);
+        cell2[d] = c2 + 1;
+      }
+      const double ex_part = gather_g<3>(P, P.e[0], H[0], cell2[0], G[1], cell1[1], G[2], cell1[2]);
+      const double ey_part = gather_g<3>(P, P.e[1], G[0], cell1[0], H[1], cell2[1], G[2], cell1[2]);
+      const double ez_part = gather_g<3>(P, P.e[2], G[0], cell1[0], G[1], cell1[1], H[2], cell2[2]);
+      const double bx_part = gather_g<3>(P, P.b[0], G[0], cell1[0], H[1], cell2[1], H[2], cell2[2]);
+      const double by_part = gather_g<3>(P, P.b[1], H[0], cell2[0], G[1], cell1[1], H[2], cell2[2]);
+      const double bz_part = gather_g<3>(P, P.b[2], H[0], cell2[0], H[1], cell2[1], G[2], cell1[2]);
+      const double cmratio = P.cmratio;
+      const double uxm = part_ux + cmratio * ex_part;
+      const double uym = part_uy + cmratio * ey_part;
+      const double uzm = part_uz + cmratio * ez_part;
+      double root;
+      gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+      const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+      const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+      const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+      const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                          2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+      const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                          2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+      const double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                          2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+      part_ux = uxp + cmratio * ex_part;
+      part_uy = uyp + cmratio * ey_part;
+      part_uz = uzp + cmratio * ez_part;
+      // epoch3d particles.F90:470-474
+      gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
+      const double delta[3] = {part_ux * root, part_uy * root, part_uz * root};
+#pragma unroll
+      for (int d = 0; d < 3; d++) pp[d] = pp[d] + delta[d];
+      {
+        double pos3[3] = {pp[0] + P.grid_min_local[0], pp[1] + P.grid_min_local[1], pp[2] + P.grid_min_local[2]};
+        double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
+        const int dir = particle_bc<3>(P, pos3, mom);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { P.x[d][i] = pos3[d]; P.p[d][i] = mom[d]; }
+        if (dir >= 0) outbox_put(P, i, dir);
+      }
+      if (P.deposit) {
+        double W[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          pp[d] = pp[d] + delta[d];
+          const double cr = pp[d] * P.idx[d];
+          const int c3 = __double2int_rd(cr + 0.5);
+          fn[d] = (double)c3 - cr;
+          dc[d] = c3 + 1 - cell1[d];
+          tri(fn[d], W[d][0], W[d][1], W[d][2]);
+        }
+        const double fcx = P.kfc[0] * part_weight;
+        const double fcy = P.kfc[1] * part_weight;
+        const double fcz = P.kfc[2] * part_weight;
+        fjx = fcx * P.part_q;
+        fjy = fcy * P.part_q;
+        fjz = fcz * P.part_q;
+        if ((dc[0] | dc[1] | dc[2]) != 0) {
+          extras = true;
+        } else {
+          regular = true;
+#pragma unroll
+          for (int d = 0; d < 3; d++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) H[d][q] = W[d][q] - G[d][q];
+        }
+      }
+    }
+    if (!P.deposit) continue;
+    // ---- queue the particles with a wider stencil ---------------------------------------
+    const unsigned em = __ballot_sync(FULL, extras);
+    if (em) {
+      const int ne = __popc(em);
+      if (qcount + ne > Q3CAP) {
+        __syncwarp();
+        drain_extras_3d(P, sJ, Qd, Qk, qcount, lane);
+        __syncwarp();
+        qcount = 0;
+      }
+      // a batch may hold more wide particles than the queue: the surplus lanes deposit directly
+      const int myslot = qcount + __popc(em & lt_mask);
+      if (extras) {
+        if (myslot < Q3CAP) {
+          Qk[myslot] = key | ((dc[0] + 1) << 12) | ((dc[1] + 1) << 14) | ((dc[2] + 1) << 16);
+#pragma unroll
+          for (int d = 0; d < 3; d++) { Qd[(2 * d) * Q3CAP + myslot] = fo[d]; Qd[(2 * d + 1) * Q3CAP + myslot] = fn[d]; }
+          Qd[6 * Q3CAP + myslot] = fjx; Qd[7 * Q3CAP + myslot] = fjy; Qd[8 * Q3CAP + myslot] = fjz;
+        }
+      }
+      const int over = qcount + ne - Q3CAP;
+      qcount = over > 0 ? Q3CAP : qcount + ne;
+      if (over > 0) {  // warp-uniform: drain, then let the surplus lanes use the emptied queue
+        __syncwarp();
+        drain_extras_3d(P, sJ, Qd, Qk, qcount, lane);
+        __syncwarp();
+        qcount = 0;
+        if (extras && myslot >= Q3CAP) {
+          const int s2 = myslot - Q3CAP;
+          Qk[s2] = key | ((dc[0] + 1) << 12) | ((dc[1] + 1) << 14) | ((dc[2] + 1) << 16);
+#pragma unroll
+          for (int d = 0; d < 3; d++) { Qd[(2 * d) * Q3CAP + s2] = fo[d]; Qd[(2 * d + 1) * Q3CAP + s2] = fn[d]; }
+          Qd[6 * Q3CAP + s2] = fjx; Qd[7 * Q3CAP + s2] = fjy; Qd[8 * Q3CAP + s2] = fjz;
+        }
+        qcount = over;
+      }
+    }
+    // ---- transposed reduction, one z plane of the stencil per pass -------------------------
+    {
+      const double *gx = G[0], *gy = G[1], *gz = G[2], *hx = H[0], *hy = H[1], *hz = H[2];
+      double jzh[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) jzh[a][b] = 0.0;
+      double *col = S + pos;
+#pragma unroll
+      for (int iz = 0; iz < 3; iz++) {
+        const int nrows = iz < 2 ? 21 : 12;
+        if (regular) {
+          const double zfac1 = gz[iz] + 0.5 * hz[iz];
+          const double zfac2 = third * hz[iz] + 0.5 * gz[iz];
+          const double gz_iz = gz[iz], hz_iz = hz[iz];
+          double jyh[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int iy = 0; iy < 3; iy++) {
+            const double yfac1 = gy[iy] + 0.5 * hy[iy];
+            const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+            const double hygz = hy[iy] * gz_iz;
+            const double hyhz = hy[iy] * hz_iz;
+            const double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
+            const double hzyfac1 = hz_iz * yfac1;
+            const double hzyfac2 = hz_iz * yfac2;
+            double jxh = 0.0;
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) {
+              const double xfac1 = gx[ix] + 0.5 * hx[ix];
+              const double xfac2 = third * hx[ix] + 0.5 * gx[ix];
+              const double wx = hx[ix] * yzfac;
+              const double wy = xfac1 * hygz + xfac2 * hyhz;
+              const double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
+              jxh = jxh - fjx * wx;
+              jyh[ix] = jyh[ix] - fjy * wy;
+              jzh[iy][ix] = jzh[iy][ix] - fjz * wz;
+              if (ix < 2) col[(iy * 2 + ix) * SPITCH] = jxh;
+              if (iy < 2) col[(6 + iy * 3 + ix) * SPITCH] = jyh[ix];
+              if (iz < 2) col[(12 + iy * 3 + ix) * SPITCH] = jzh[iy][ix];
+            }
+          }
+        } else if (key >= 0) {
+          for (int q = 0; q < nrows; q++) col[q * SPITCH] = 0.0;
+        }
+        __syncwarp();
+        if (lane < nrows) {
+          const double *row = S + lane * SPITCH;
+          const int off = off0 + iz * JW3 * JW3;
+          unsigned b = bnd;
+          int lo = 0;
+          while (b) {  // one running sum per cell key (warp-uniform bounds)
+            const int hi = __ffs(b);
+            b &= b - 1;
+            double a0 = 0.0, a1 = 0.0;
+            int j = lo;
+            for (; j + 2 <= hi; j += 2) { a0 += row[j]; a1 += row[j + 1]; }
+            if (j < hi) a0 += row[j];
+            smem_add(&sJ[off + RK[hi - 1]], a0 + a1);
+            lo = hi;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (qcount) {
+    __syncwarp();
+    drain_extras_3d(P, sJ, Qd, Qk, qcount, lane);
+  }
+  __syncthreads();
+  {
+    int ns = *sSlowCount;
+    if (ns > SLOW3CAP) ns = SLOW3CAP;
+    for (int q = tid; q < ns; q += P3_THREADS) push_one<3>(P, sSlow[q]);
+  }
+  for (int q = tid; q < JT3; q += P3_THREADS) {
+    const int lx = q % JW3, ly = (q / JW3) % JW3, lz = q / (JW3 * JW3);
+    const int cx = ox + lx, cy = oy + ly, cz = oz + lz;
+    const bool ok = (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG) &&
+                    (cz >= 1 - NG) && (cz <= P.n[2] + NG);
+    if (!ok) continue;
+    const size_t o = gofs<3>(P, cx, cy, cz);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double val = sJ[f * JT3 + q];
+      if (val != 0.0) atomicAdd(P.j[f] + o, val);
+    }
+  }
+}
+
+
 inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
   static bool attr_set = false;
   static int variant = 0;
@@ -1242,6 +1640,18 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
       }
       else if (variant == 1) push_tiled_2d<true><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
       else push_tiled_2d<false><<<P.tg.ntiles, PUSH2D_THREADS, PUSH2D_SMEM, s>>>(P);
+      (*launches)++;
+    }
+    return;
+  }
+  if (tiled && nd == 3) {
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaFuncSetAttribute(push_tiled_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSH3D_SMEM);
+      attr3 = true;
+    }
+    if (P.tg.ntiles > 0) {
+      push_tiled_3d<<<P.tg.ntiles, P3_THREADS, PUSH3D_SMEM, s>>>(P);
       (*launches)++;
     }
     return;

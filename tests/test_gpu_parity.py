@@ -80,7 +80,9 @@ def test_single_push_matches_oracle(ndims, n, strict):
     if strict:
         assert np.array_equal(a, b)
     else:
-        assert np.allclose(a, b, rtol=1e-13, atol=0)
+        # performance build (FMA contraction, rsqrt): 1e-13 of each column's scale -- a momentum
+        # component that happens to be ~0 cannot hold a purely relative bound
+        assert np.all(np.abs(a - b) <= 1e-13 * np.max(np.abs(b), axis=0))
     for name in ("jx", "jy", "jz"):
         assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
     assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
@@ -98,7 +100,7 @@ def test_ten_steps_thermal(ndims, n, strict):
         assert sim.count(isp) == o.count(0, isp)
         assert np.array_equal(sim.cell_counts(isp), o.cell_counts(0, isp))
         a, b = sorted_rows(sim.download_species(isp)), sorted_rows(o.get_particles(0, isp))
-        assert np.allclose(a, b, rtol=1e-9, atol=0)
+        assert np.all(np.abs(a - b) <= 1e-9 * np.max(np.abs(b), axis=0))  # 1e-9 of each column's scale
 
 
 @pytest.mark.parametrize("sort_interval", [1, 3, 50])

@@ -56,6 +56,12 @@ experiments)
     EPB_PUSH_EXPERIMENT=$e timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval 4 --no-cpu-baseline 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('experiment $e: push_ms %.3f step_ms %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step']))" | tee -a gpurun_out/experiments.log
   done ;;
+bench3d)
+  for no3d in ${NO3D:-0 1}; do
+    EPB_NO_TILED_3D=$no3d timeout 900 python bench.py --workload c4 --cells ${CELLS3D:-192} --steps 4 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench3d.err | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('3d no_tiled=$no3d: push_ms %.3f step_ms %.3f value %.3e frac %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step'], d['value'], d['roofline']['frac']))" | tee -a gpurun_out/bench3d.log
+    tail -2 gpurun_out/bench3d.err
+  done ;;
 micro)
   (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu) > gpurun_out/micro_build.log 2>&1
   timeout 300 tools/microbench > gpurun_out/microbench.json 2>&1; cat gpurun_out/microbench.json ;;
