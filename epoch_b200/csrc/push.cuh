@@ -1296,9 +1296,10 @@ __device__ __noinline__ void drain_extras_3d(const PushParams &P, double *sJ, co
         jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
         jzh[iy + 2][ix + 2] = jzh[iy + 2][ix + 2] - fjz * wz;
         const int o = key + (iz * JW3 + iy) * JW3 + ix;
-        smem_add(&sJ[o], jxh);
-        smem_add(&sJ[JT3 + o], jyh[ix + 2]);
-        smem_add(&sJ[2 * JT3 + o], jzh[iy + 2][ix + 2]);
+        // the last column / row / plane of each running sum cancels structurally (sum of hx = 0)
+        if (ix < mx[0]) smem_add(&sJ[o], jxh);
+        if (iy < mx[1]) smem_add(&sJ[JT3 + o], jyh[ix + 2]);
+        if (iz < mx[2]) smem_add(&sJ[2 * JT3 + o], jzh[iy + 2][ix + 2]);
       }
     }
   }
