@@ -304,6 +304,7 @@ struct LoadOp {
   double weight;
   double stdev[3], drift[3];
   unsigned long long seed;
+  int mixed;  // 1: cell drawn at random per particle (Poisson counts, the long-time state of a thermal plasma)
 };
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long &s) {
   unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
@@ -318,10 +319,11 @@ __global__ void __launch_bounds__(256) k_load_uniform(const __grid_constant__ Lo
   const long long ncell = (long long)L.nloc[0] * L.nloc[1] * L.nloc[2];
   const long long total = ncell * L.ppc;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long cellid = i / L.ppc;
+    unsigned long long s = L.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(i + 1));
+    long long cellid = i / L.ppc;
+    if (L.mixed) cellid = (long long)(u01(s) * (double)ncell) % ncell;
     int cell[3] = {(int)(cellid % L.nloc[0]), (int)((cellid / L.nloc[0]) % L.nloc[1]),
                    (int)(cellid / ((long long)L.nloc[0] * L.nloc[1]))};
-    unsigned long long s = L.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(i + 1));
     for (int d = 0; d < L.nd; d++)
       L.x[d][i] = (L.gmin_local[d] + (double)cell[d] * L.dx[d]) + (u01(s) - 0.5) * L.dx[d];
     double g[4];
@@ -673,7 +675,6 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   }
   epb_handle *h = new epb_handle;
   h->cfg = *cfg;
-  if (h->cfg.sort_interval < 1) h->cfg.sort_interval = 1;
   const int nd = cfg->ndims;
   h->fsize = 1;
   for (int d = 0; d < 3; d++) {
@@ -692,6 +693,9 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   EPB_CUDA(h, cudaMemsetAsync(h->src, 0, 4 * h->plane * sizeof(double), h->stream));
   epb_fdtd_tma_setup(h);
   epb_make_tiles(h->cfg, h->tg);
+  // 0 = library default: the cell-owner kernel wants a fresh order (its sort is cheap), the
+  // transposition kernel tolerates a stale one
+  if (h->cfg.sort_interval < 1) h->cfg.sort_interval = (h->tg.layout == 1) ? 3 : 8;
   EPB_CUDA(h, cudaMalloc(&h->cell_count, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   EPB_CUDA(h, cudaMalloc(&h->cell_start, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   long long maxcap = 0;
@@ -865,6 +869,7 @@ int epb_load_uniform(epb_handle *h, int is, int32_t ppc, double density, const d
   L.w = S.buf[S.cur][6];
   L.nd = c.ndims;
   L.ppc = ppc;
+  L.mixed = getenv("EPB_LOAD_MIXED") ? atoi(getenv("EPB_LOAD_MIXED")) : 0;
   double vol = 1.0;
   for (int d = 0; d < c.ndims; d++) vol *= c.dx[d];
   L.weight = density * vol / ppc;

@@ -136,11 +136,13 @@ struct epb_handle {
   double *f(int which) const { return fields + (size_t)which * fsize; }
 };
 
-// EPB_PUSH_VARIANT: 0 = push_tiled_2d (27-value transposition), 1 = its 21-value form,
-// 2 = push_cell_2d (one lane per cell, register accumulators, interleaved layout)
+// 2D push kernel (EPB_PUSH_VARIANT): 3 (default) = push_cell_2d<8,3>: one lane per cell, register-resident
+// deposit sums, rank-interleaved layout, 16x8-cell tiles, 168 registers; 2 / 4 = the same kernel on
+// 16x16-cell tiles with 128 / 255 registers; 0 = push_tiled_2d (lane per particle, 27-value
+// transposed reduction, cell-major layout); 1 = its 21-value form.
 inline int epb_push_variant() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 0; }
+  if (v < 0) { const char *e = getenv("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 3; }
   return v;
 }
 

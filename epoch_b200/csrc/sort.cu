@@ -318,7 +318,8 @@ int epb_sort_species(epb_handle *h, int is) {
     K.tg = h->tg;
     K.key = S.key;
     K.count = h->cell_count;
-    K.predict = (h->tg.layout == 1);
+    static const int predict_env = getenv("EPB_SORT_PREDICT") ? atoi(getenv("EPB_SORT_PREDICT")) : 0;
+    K.predict = (h->tg.layout == 1) || predict_env;
     for (int d = 0; d < 3; d++) {
       K.p[d] = S.buf[S.cur][3 + d];
       K.idx[d] = d < c.ndims ? 1.0 / c.dx[d] : 0.0;

@@ -234,7 +234,7 @@ CONTAINS
     cfg%nranks = nproc
     cfg%n_species = n_species
     cfg%strict_fp = 1
-    cfg%sort_interval = 4
+    cfg%sort_interval = 0   ! library default
     cfg%reserved = 0
     cfg%dx = (/ dx, dy, 1.0_num /)
     cfg%dt = dt

@@ -70,7 +70,7 @@ typedef struct epb_config {
   int32_t rank, nranks;
   int32_t n_species;
   int32_t strict_fp;        /* 1: kernels built without FMA contraction (bit-level parity build) */
-  int32_t sort_interval;    /* steps between on-GPU counting sorts (>=1) */
+  int32_t sort_interval;    /* steps between on-GPU counting sorts; 0 = library default (3 or 8, by kernel) */
   int32_t reserved[5];
   double dx[3];             /* dx, dy, dz */
   double dt;

@@ -28,7 +28,7 @@ benchref)
   cat gpurun_out/bench_ref.json ;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --cells 2048 --steps 4 --warmup 3 --no-cpu-baseline \
+      --log-file gpurun_out/launches.csv python bench.py --cells ${CELLS:-2048} --steps 4 --warmup 3 --no-cpu-baseline \
       > gpurun_out/launches_bench.log 2>&1
   echo "launches rc=$?" ;;
 ncu)
