@@ -565,6 +565,9 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
   P.tile_start = S.tile_start;
   P.cell_start = S.cell_start;
   P.emit = 0;
+  P.perm = nullptr;
+  for (int d = 0; d < 3; d++) { P.xs[d] = P.x[d]; P.ps[d] = P.p[d]; }
+  P.ws = P.w;
   P.key_out = S.key;
   P.rank_out = S.rank;
   P.stay_cnt = S.stay_cnt;
@@ -825,6 +828,7 @@ int epb_upload_species(epb_handle *h, int is, int64_t n, const double *packed) {
   S.n = n;
   S.n_sorted = 0;
   S.info_valid = false;
+  S.pending_perm = false;
   h->pushes_since_sort = 1 << 30;  // force a sort before the next push
   return EPB_OK;
 }
@@ -880,6 +884,7 @@ int epb_load_uniform(epb_handle *h, int is, int32_t ppc, double density, const d
   S.n = total;
   S.n_sorted = 0;
   S.info_valid = false;
+  S.pending_perm = false;
   h->pushes_since_sort = 1 << 30;
   EPB_CUDA(h, cudaGetLastError());
   return EPB_OK;
@@ -1015,6 +1020,13 @@ int epb_push(epb_handle *h) {
       P.emit = 1;
       S.info_valid = true;
     }
+    const bool fuse_gather = S.pending_perm && tiled && sorted > 0 && h->tg.layout == 1 && sorted == S.n;
+    if (S.pending_perm && !fuse_gather) {
+      int rcp = epb_apply_pending_perm(h, is);
+      if (rcp) return rcp;
+      fill_push_params(h, is, P);  // the buffers were swapped
+      if (S.info_valid) P.emit = 1;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_push) {
       cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1022,6 +1034,20 @@ int epb_push(epb_handle *h) {
     }
     if (tiled && sorted > 0) {
       P.n_sorted_clip = sorted;
+      if (fuse_gather) {
+        // first push after an emitted sort: read the old order through perm, write the new one
+        P.perm = S.perm;
+        for (int d = 0; d < 3; d++) {
+          P.xs[d] = S.buf[S.cur][d];
+          P.ps[d] = S.buf[S.cur][3 + d];
+          P.x[d] = S.buf[S.cur ^ 1][d];
+          P.p[d] = S.buf[S.cur ^ 1][3 + d];
+        }
+        P.ws = S.buf[S.cur][6];
+        P.w = S.buf[S.cur ^ 1][6];
+        S.cur ^= 1;
+        S.pending_perm = false;
+      }
       launch(P, c.ndims, true, h->stream, &h->launches);
       P.first = sorted;
     } else {

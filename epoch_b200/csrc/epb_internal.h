@@ -54,6 +54,10 @@ struct PushParams {
   // order (key_out = next gather cell's key, rank_out = rank inside that key; bit 30 set = rank
   // among the key's arrivals, to be offset by stay_cnt[key]) so the sort needs no atomics
   int emit;
+  // layout 1, first push after a sort: the particle of slot i is read from xs/ps/ws[perm[i]] (the
+  // old order, other buffer) and written to x/p/w[i]; perm == nullptr: in place
+  const int *perm;
+  const double *xs[3], *ps[3], *ws;
   int *key_out, *rank_out;
   int *stay_cnt, *arr_cnt;
   long long n_sorted_clip; // tile ranges are clipped to this count
@@ -89,6 +93,7 @@ struct SpeciesDev {
   int *rank = nullptr;        // layout 1: per-particle rank emitted by the push (see PushParams::emit)
   int *stay_cnt = nullptr, *arr_cnt = nullptr;  // layout 1: per-key counts emitted by the push
   bool info_valid = false;    // key/rank/stay_cnt/arr_cnt describe the current particle set
+  bool pending_perm = false;  // the sort left the data in place: perm[new slot] = old index, applied by the next push
   unsigned char *gone = nullptr;
 };
 
@@ -157,6 +162,7 @@ void epb_fdtd_tma_launch(epb_handle *h, bool is_e, double cx, double cy, double 
 // sort.cu
 int epb_sort_species(epb_handle *h, int is);
 int epb_sort_species_emitted(epb_handle *h, int is);
+int epb_apply_pending_perm(epb_handle *h, int is);  // materialise a deferred reordering (gather)
 #define EPB_RANK_ARRIVAL (1 << 30)
 void epb_make_tiles(const epb_config &cfg, TileGeom &tg);
 

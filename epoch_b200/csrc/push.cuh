@@ -960,9 +960,12 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
     }
   }
 
-  // software pipeline: the next round's particle loads are in flight while this one computes
-  long long i;
-  bool act;
+  // software pipeline: the next round's particle loads are in flight while this one computes, and
+  // (fused gather after a sort) the source index of the round after that is already being fetched
+  const int *perm = P.perm;
+  long long i, i2;      // slot of the current/next round, slot of the round after
+  long long si2 = 0;    // source index of slot i2 (perm[i2], or i2 itself without a pending permutation)
+  bool act, act2;
   {
     const bool na = my_cnt > 0;
     const unsigned bal = __ballot_sync(FULL, na);
@@ -972,28 +975,43 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
   }
   double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
   if (act) {
-    n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
-    n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
+    const long long si = perm ? (long long)perm[i] : i;
+    n_w = P.ws[si]; n_x = P.xs[0][si]; n_y = P.xs[1][si];
+    n_px = P.ps[0][si]; n_py = P.ps[1][si]; n_pz = P.ps[2][si];
+  }
+  {
+    const bool na = my_cnt > 1;
+    const unsigned bal = __ballot_sync(FULL, na);
+    i2 = rbase + __popc(bal & lt_mask);
+    rbase += __popc(bal);
+    act2 = na && i2 < clip;
+    if (act2) si2 = perm ? (long long)perm[i2] : i2;
   }
   for (int r = 0; r < maxcnt; r++) {
     const bool active = act;
     const long long ci = i;
     const double part_weight = n_w;
+    const double raw_x = n_x, raw_y = n_y, raw_px = n_px, raw_py = n_py, raw_pz = n_pz;
     double px_ = n_x - P.grid_min_local[0];
     double py_ = n_y - P.grid_min_local[1];
     double part_ux = n_px * P.ipart_mc;
     double part_uy = n_py * P.ipart_mc;
     double part_uz = n_pz * P.ipart_mc;
     {
-      const bool na = my_cnt > r + 1;
-      const unsigned bal = __ballot_sync(FULL, na);
-      i = rbase + __popc(bal & lt_mask);
-      rbase += __popc(bal);
-      act = na && i < clip;
+      // loads of round r+1 (its source index arrived during the previous round)
+      i = i2;
+      act = act2;
       if (act) {
-        n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i];
-        n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
+        n_w = P.ws[si2]; n_x = P.xs[0][si2]; n_y = P.xs[1][si2];
+        n_px = P.ps[0][si2]; n_py = P.ps[1][si2]; n_pz = P.ps[2][si2];
       }
+      // slot and source index of round r+2
+      const bool na = my_cnt > r + 2;
+      const unsigned bal = __ballot_sync(FULL, na);
+      i2 = rbase + __popc(bal & lt_mask);
+      rbase += __popc(bal);
+      act2 = na && i2 < clip;
+      if (act2) si2 = perm ? (long long)perm[i2] : i2;
     }
     bool extras = false;
     int key = 0, dcx = 0, dcy = 0;
@@ -1010,6 +1028,11 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
       // the gather reads cell1-2..cell1+1, the deposit writes cell1-2..cell1+2
       const bool fast = (cx1 - 2 >= ox) && (cx1 + 2 <= ox + TWU - 1) && (cy1 - 2 >= oy) && (cy1 + 2 <= oy + TH - 1);
       if (!fast) {
+        if (perm) {  // push_one works in place on the destination slot
+          P.x[0][ci] = raw_x; P.x[1][ci] = raw_y;
+          P.p[0][ci] = raw_px; P.p[1][ci] = raw_py; P.p[2][ci] = raw_pz;
+          P.w[ci] = part_weight;
+        }
         const int slot = atomicAdd(sSlowCount, 1);
         if (slot < SLOWCAP) sSlow[slot] = (int)ci;
         else push_one<2>(P, ci);
@@ -1080,6 +1103,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
           P.p[0][ci] = mom[0];
           P.p[1][ci] = mom[1];
           P.p[2][ci] = mom[2];
+          if (perm) P.w[ci] = part_weight;
           if (dir >= 0) outbox_put(P, ci, dir);
         }
         if (P.deposit) {

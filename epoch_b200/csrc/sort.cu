@@ -249,9 +249,31 @@ static void fill_keyop(epb_handle *h, SpeciesDev &S, KeyOp &K) {
 
 // Sort from the records of the last push (layout 1): fix-up of the particles without a record,
 // counts = stayers + arrivals, scan, atomic-free scatter.
+int epb_apply_pending_perm(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  if (!S.pending_perm) return EPB_OK;
+  S.pending_perm = false;
+  if (S.n <= 0) return EPB_OK;
+  GatherOp Ga;
+  for (int q = 0; q < 7; q++) { Ga.src[q] = S.buf[S.cur][q]; Ga.dst[q] = S.buf[S.cur ^ 1][q]; }
+  Ga.n = S.n;
+  Ga.perm = S.perm;
+  long long nb = (S.n + 255) / 256;
+  if (nb > 148LL * 32) nb = 148LL * 32;
+  k_gather_perm<<<(int)nb, 256, 0, h->stream>>>(Ga);
+  h->launches++;
+  S.cur ^= 1;
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
 int epb_sort_species_emitted(epb_handle *h, int is) {
   SpeciesDev &S = h->sp[is];
   const int nkeys = h->tg.nkeys;
+  {
+    int rc = epb_apply_pending_perm(h, is);
+    if (rc) return rc;
+  }
   if (S.n > 0) {
     KeyOp K;
     fill_keyop(h, S, K);
@@ -283,13 +305,14 @@ int epb_sort_species_emitted(epb_handle *h, int is) {
     if (nb > 148LL * 32) nb = 148LL * 32;
     k_perm_emitted<<<(int)nb, 256, 0, h->stream>>>(Pm);
     h->launches++;
-    GatherOp Ga;
-    for (int q = 0; q < 7; q++) { Ga.src[q] = S.buf[S.cur][q]; Ga.dst[q] = S.buf[S.cur ^ 1][q]; }
-    Ga.n = S.n;
-    Ga.perm = S.perm;
-    k_gather_perm<<<(int)nb, 256, 0, h->stream>>>(Ga);
-    h->launches++;
-    S.cur ^= 1;
+    // the gather itself is left to the next push of this species (PushParams::perm), which reads
+    // the old order through perm and writes the new one: no separate 100 B/particle pass
+    S.pending_perm = true;
+    static const int no_fuse = getenv("EPB_NO_FUSED_GATHER") ? atoi(getenv("EPB_NO_FUSED_GATHER")) : 0;
+    if (no_fuse) {
+      int rc = epb_apply_pending_perm(h, is);
+      if (rc) return rc;
+    }
   }
   k_tile_start<<<(h->tg.ntiles + 1 + 255) / 256, 256, 0, h->stream>>>(S.cell_start, S.tile_start, h->tg.ntiles, h->tg.cpt);
   h->launches++;
@@ -304,6 +327,10 @@ int epb_sort_species(epb_handle *h, int is) {
   const epb_config &c = h->cfg;
   const int nkeys = h->tg.nkeys;
   S.info_valid = false;
+  {
+    int rc = epb_apply_pending_perm(h, is);
+    if (rc) return rc;
+  }
   EPB_CUDA(h, cudaMemsetAsync(h->cell_count, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
   if (S.n > 0) {
     KeyOp K;
