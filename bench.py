@@ -299,9 +299,9 @@ def main():
         achieved = (n_local * bytes_per_update / (push_ms * 1e-3)) / 1e9 if push_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "push_traffic_bytes.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        if os.path.exists(tpath) and not is3d and variant in (2, 3, 4) and args.sort_interval == 3:
+            try:  # ncu dram bytes per particle (mean over the fused / plain / emitting launch cycle) x particles per launch
+                traffic = json.load(open(tpath))["dram_bytes_per_particle"]["cycle_mean"] * n_local
             except Exception:
                 traffic = None
         line = {
