@@ -30,6 +30,11 @@ struct FieldParams {
   int n[3];
   int sz[3];
   double cx, cy, cz, fac;  // cnx.. (E update) or hdtx.. (B update)
+  // general solver (k_update_e_gen / k_update_b_gen): nt = field_order / 2 difference terms per
+  // derivative with coefficients c1..c3 * cx (fields.f90:128-204); ext: extended 2D B stencil
+  int nt, ext;
+  double kx[3], ky[3], kz[3];
+  double alphax, alphay, betaxy, betayx, deltax, deltay;
 };
 
 __device__ __forceinline__ size_t fofs(const int *sz, int nd, int i, int j, int k) {
@@ -398,6 +403,110 @@ void fill_field_params(epb_handle *h, FieldParams &F) {
   for (int d = 0; d < 3; d++) { F.n[d] = h->cfg.n[d]; F.sz[d] = h->sz[d]; }
 }
 
+// ---- field orders 4 / 6 and the extended 2D stencils ---------------------------------------------
+// Every c*(difference) term of the order-2 expressions becomes the group c1*c*(d1) + c2*c*(d2)
+// [+ c3*c*(d3)], added one after the other in the reference's textual order (fields.f90:128-204,
+// :468-529; epoch3d fields.f90:337-430, :734-830; epoch1d fields.f90:166-215, :315-360).
+template <int ND>
+__global__ void __launch_bounds__(256) k_update_e_gen(const __grid_constant__ FieldParams F) {
+  const int ex_ = F.n[0] + 1, ey_ = ND >= 2 ? F.n[1] + 1 : 1, ez_ = ND >= 3 ? F.n[2] + 1 : 1;
+  const size_t total = (size_t)ex_ * ey_ * ez_;
+  const ptrdiff_t sx = 1, sy = F.sz[0], szz = (ptrdiff_t)F.sz[0] * F.sz[1];
+  const int nt = F.nt;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % ex_);
+    const int iy = ND >= 2 ? (int)((t / ex_) % ey_) : 1;
+    const int iz = ND >= 3 ? (int)(t / ((size_t)ex_ * ey_)) : 1;
+    const ptrdiff_t o = (ptrdiff_t)fofs(F.sz, ND, ix, iy, iz);
+    double *ex = F.f[0], *ey = F.f[1], *ez = F.f[2];
+    const double *bx = F.f[3], *by = F.f[4], *bz = F.f[5];
+    const double *jx = F.f[6], *jy = F.f[7], *jz = F.f[8];
+    // backward difference k along stride s: f(i+k) - f(i-k-1)
+    auto db = [&](const double *f, ptrdiff_t s, int k) { return f[o + k * s] - f[o - (k + 1) * s]; };
+    double v = ex[o];
+    if (ND >= 2) for (int k = 0; k < nt; k++) v = v + F.ky[k] * db(bz, sy, k);
+    if (ND >= 3) for (int k = 0; k < nt; k++) v = v - F.kz[k] * db(by, szz, k);
+    ex[o] = v - F.fac * jx[o];
+    v = ey[o];
+    if (ND >= 3) for (int k = 0; k < nt; k++) v = v + F.kz[k] * db(bx, szz, k);
+    for (int k = 0; k < nt; k++) v = v - F.kx[k] * db(bz, sx, k);
+    ey[o] = v - F.fac * jy[o];
+    v = ez[o];
+    for (int k = 0; k < nt; k++) v = v + F.kx[k] * db(by, sx, k);
+    if (ND >= 2) for (int k = 0; k < nt; k++) v = v - F.ky[k] * db(bx, sy, k);
+    ez[o] = v - F.fac * jz[o];
+  }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) k_update_b_gen(const __grid_constant__ FieldParams F) {
+  const int ex_ = F.n[0] + 1, ey_ = ND >= 2 ? F.n[1] + 1 : 1, ez_ = ND >= 3 ? F.n[2] + 1 : 1;
+  const size_t total = (size_t)ex_ * ey_ * ez_;
+  const ptrdiff_t sx = 1, sy = F.sz[0], szz = (ptrdiff_t)F.sz[0] * F.sz[1];
+  const int nt = F.nt;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % ex_);
+    const int iy = ND >= 2 ? (int)((t / ex_) % ey_) : 1;
+    const int iz = ND >= 3 ? (int)(t / ((size_t)ex_ * ey_)) : 1;
+    const ptrdiff_t o = (ptrdiff_t)fofs(F.sz, ND, ix, iy, iz);
+    const double *ex = F.f[0], *ey = F.f[1], *ez = F.f[2];
+    double *bx = F.f[3], *by = F.f[4], *bz = F.f[5];
+    // forward difference k along stride s: f(i+k+1) - f(i-k)
+    auto df = [&](const double *f, ptrdiff_t s, int k) { return f[o + (k + 1) * s] - f[o - k * s]; };
+    if (ND == 2 && F.ext) {
+      // fields.f90:441-465
+      auto ddx = [&](const double *f) {
+        return F.alphax * (f[o + sx] - f[o]) +
+               F.betaxy * (f[o + sx + sy] - f[o + sy] + f[o + sx - sy] - f[o - sy]) +
+               F.deltax * (f[o + 2 * sx] - f[o - sx]);
+      };
+      auto ddy = [&](const double *f) {
+        return F.alphay * (f[o + sy] - f[o]) +
+               F.betayx * (f[o + sx + sy] - f[o + sx] + f[o - sx + sy] - f[o - sx]) +
+               F.deltay * (f[o + 2 * sy] - f[o - sy]);
+      };
+      bx[o] = bx[o] - F.cy * ddy(ez);
+      by[o] = by[o] + F.cx * ddx(ez);
+      bz[o] = bz[o] - F.cx * ddx(ey) + F.cy * ddy(ex);
+      continue;
+    }
+    double v;
+    if (ND >= 2) {
+      v = bx[o];
+      for (int k = 0; k < nt; k++) v = v - F.ky[k] * df(ez, sy, k);
+      if (ND >= 3) for (int k = 0; k < nt; k++) v = v + F.kz[k] * df(ey, szz, k);
+      bx[o] = v;
+    }
+    v = by[o];
+    if (ND >= 3) for (int k = 0; k < nt; k++) v = v - F.kz[k] * df(ex, szz, k);
+    for (int k = 0; k < nt; k++) v = v + F.kx[k] * df(ez, sx, k);
+    by[o] = v;
+    v = bz[o];
+    for (int k = 0; k < nt; k++) v = v - F.kx[k] * df(ey, sx, k);
+    if (ND >= 2) for (int k = 0; k < nt; k++) v = v + F.ky[k] * df(ex, sy, k);
+    bz[o] = v;
+  }
+}
+
+static void fd_coeffs(int order, double base, double *cc) {
+  if (order == 4) { cc[0] = (9.0 / 8.0) * base; cc[1] = (-1.0 / 24.0) * base; cc[2] = 0.0; }
+  else if (order == 6) { cc[0] = (75.0 / 64.0) * base; cc[1] = (-25.0 / 384.0) * base; cc[2] = (3.0 / 640.0) * base; }
+  else { cc[0] = base; cc[1] = 0.0; cc[2] = 0.0; }
+}
+// true: the deck asks for something the TMA order-2 Yee kernels do not cover
+static bool general_solver(const epb_handle *h, FieldParams &F) {
+  const epb_config &c = h->cfg;
+  const int order = c.field_order ? c.field_order : 2;
+  F.nt = order / 2;
+  F.ext = (c.ndims == 2 && c.maxwell_solver != 0) ? 1 : 0;
+  fd_coeffs(order, F.cx, F.kx);
+  fd_coeffs(order, F.cy, F.ky);
+  fd_coeffs(order, F.cz, F.kz);
+  F.alphax = c.stencil[0]; F.alphay = c.stencil[1]; F.betaxy = c.stencil[2];
+  F.betayx = c.stencil[3]; F.deltax = c.stencil[4]; F.deltay = c.stencil[5];
+  return order != 2 || F.ext;
+}
+
 int update_e(epb_handle *h, double hdt) {
   FieldParams F;
   fill_field_params(h, F);
@@ -406,6 +515,15 @@ int update_e(epb_handle *h, double hdt) {
   F.cy = F.nd >= 2 ? hdt / h->cfg.dx[1] * (c * c) : 0.0;
   F.cz = F.nd >= 3 ? hdt / h->cfg.dx[2] * (c * c) : 0.0;
   F.fac = hdt / EPB_EPS0;
+  if (general_solver(h, F)) {
+    size_t tot = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
+    int nbg = nblocks(tot, 148 * 32);
+    if (F.nd == 1) k_update_e_gen<1><<<nbg, 256, 0, h->stream>>>(F);
+    else if (F.nd == 2) k_update_e_gen<2><<<nbg, 256, 0, h->stream>>>(F);
+    else k_update_e_gen<3><<<nbg, 256, 0, h->stream>>>(F);
+    h->launches++;
+    return EPB_OK;
+  }
   if (h->tma_ok) { epb_fdtd_tma_launch(h, true, F.cx, F.cy, F.cz, F.fac); return EPB_OK; }
   size_t total = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
   int nb = nblocks(total, 148 * 32);
@@ -423,6 +541,15 @@ int update_b(epb_handle *h, double hdt) {
   F.cy = F.nd >= 2 ? hdt / h->cfg.dx[1] : 0.0;
   F.cz = F.nd >= 3 ? hdt / h->cfg.dx[2] : 0.0;
   F.fac = 0.0;
+  if (general_solver(h, F)) {
+    size_t tot = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
+    int nbg = nblocks(tot, 148 * 32);
+    if (F.nd == 1) k_update_b_gen<1><<<nbg, 256, 0, h->stream>>>(F);
+    else if (F.nd == 2) k_update_b_gen<2><<<nbg, 256, 0, h->stream>>>(F);
+    else k_update_b_gen<3><<<nbg, 256, 0, h->stream>>>(F);
+    h->launches++;
+    return EPB_OK;
+  }
   if (h->tma_ok) { epb_fdtd_tma_launch(h, false, F.cx, F.cy, F.cz, F.fac); return EPB_OK; }
   size_t total = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
   int nb = nblocks(total, 148 * 32);
@@ -656,6 +783,14 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   *out = nullptr;
   if (cfg->ndims < 1 || cfg->ndims > 3) return epb_fail(nullptr, EPB_ERR_ARG, "ndims must be 1..3");
   if (cfg->ng != NG) return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "ng must be %d (triangle shape)", NG);
+  {
+    const int fo = cfg->field_order;
+    if (fo != 0 && fo != 2 && fo != 4 && fo != 6)
+      return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "field_order %d (2, 4 or 6)", fo);
+    if (cfg->maxwell_solver != 0 && (cfg->ndims != 2 || (fo != 0 && fo != 2)))
+      return epb_fail(nullptr, EPB_ERR_UNSUPPORTED,
+                      "extended Maxwell stencils (maxwell_solver %d) are implemented for epoch2d, field_order 2", cfg->maxwell_solver);
+  }
   for (int d = 0; d < cfg->ndims; d++)
     if (cfg->n[d] < NG) return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "local extent %d < ng", cfg->n[d]);
   for (int i = 0; i < 2 * cfg->ndims; i++) {

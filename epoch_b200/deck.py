@@ -93,6 +93,9 @@ class Deck:
     nproc: Sequence[int] = (1, 1, 1)
     seed: int = 7842432
     dt_snapshot: float = -1.0
+    field_order: int = 2                    # control block field_order: 2, 4 or 6 (fields.f90:32-46)
+    maxwell_solver: str = "yee"             # yee | lehe_x | lehe_y | pukhov | custom (2D, order 2)
+    stencil_custom: Optional[dict] = None   # custom solver: betaxy, betayx, deltax, deltay, dt
 
     # -- grid (setup.F90:162-204) ------------------------------------------
     def dx(self, d: int) -> float:
@@ -152,9 +155,16 @@ class Deck:
         else:
             solver = d[0] * d[1] * d[2] / math.sqrt(
                 (d[0] * d[1]) ** 2 + (d[1] * d[2]) ** 2 + (d[2] * d[0]) ** 2) / c
-        dt = 1.0 * solver  # cfl = 1 for field_order 2 (fields.f90:39-40)
+        if self.maxwell_solver == "yee":
+            # cfl is a function of field_order (fields.f90:38-44)
+            cfl = {2: 1.0, 4: 6.0 / 7.0, 6: 120.0 / 149.0}[self.field_order]
+            dt = cfl * solver
+        else:
+            dt = min(d) / c        # setup.F90:645-649 (Lehe, Pukhov)
         if self.any_open():
             dt = min(dt, solver)
+        if self.maxwell_solver == "custom":
+            dt = float(self.stencil_custom["dt"])
         dtp = self.dt_plasma_frequency()
         if dtp > 1e-50:
             dt = min(dt, dtp)
@@ -162,6 +172,43 @@ class Deck:
         if dtl > 1e-50:
             dt = min(dt, dtl)
         return self.dt_multiplier * dt
+
+    def maxwell_solver_code(self) -> int:
+        return {"custom": -1, "yee": 0, "lehe_x": 2, "lehe_y": 3, "pukhov": 6}[self.maxwell_solver]  # constants.F90:173-180
+
+    def stencil(self) -> dict:
+        """set_maxwell_solver (epoch2d fields.f90:51-86): alpha/beta/delta of the extended B stencil."""
+        out = dict(alphax=1.0, alphay=1.0, betaxy=0.0, betayx=0.0, deltax=0.0, deltay=0.0)
+        if self.maxwell_solver == "yee":
+            return out
+        if self.ndims != 2:
+            raise NotImplementedError("extended Maxwell stencils are restated for epoch2d only")
+        dx, dy, dt = self.dx(0), self.dx(1), self.dt()
+        if self.maxwell_solver == "custom":
+            out.update({k: float(self.stencil_custom.get(k, 0.0)) for k in ("betaxy", "betayx", "deltax", "deltay")})
+            out["alphax"] = 1.0 - 2.0 * out["betaxy"] - 3.0 * out["deltax"]
+            out["alphay"] = 1.0 - 2.0 * out["betayx"] - 3.0 * out["deltay"]
+        elif self.maxwell_solver == "lehe_x":
+            dx_cdt = dx / (c * dt)
+            out["betaxy"] = 0.125 * (dx / dy) ** 2
+            out["betayx"] = 0.125
+            out["deltax"] = 0.25 * (1.0 - dx_cdt ** 2 * math.sin(0.5 * pi / dx_cdt) ** 2)
+            out["alphax"] = 1.0 - 2.0 * out["betaxy"] - 3.0 * out["deltax"]
+            out["alphay"] = 1.0 - 2.0 * out["betayx"]
+        elif self.maxwell_solver == "lehe_y":
+            dx_cdt = dy / (c * dt)
+            out["betayx"] = 0.125 * (dy / dx) ** 2
+            out["betaxy"] = 0.125
+            out["deltay"] = 0.25 * (1.0 - dx_cdt ** 2 * math.sin(0.5 * pi / dx_cdt) ** 2)
+            out["alphax"] = 1.0 - 2.0 * out["betaxy"]
+            out["alphay"] = 1.0 - 2.0 * out["betayx"] - 3.0 * out["deltay"]
+        elif self.maxwell_solver == "pukhov":
+            delta = min(dx, dy)
+            out["betayx"] = 0.125 * (delta / dx) ** 2
+            out["betaxy"] = 0.125 * (delta / dy) ** 2
+            out["alphax"] = 1.0 - 2.0 * out["betaxy"]
+            out["alphay"] = 1.0 - 2.0 * out["betayx"]
+        return out
 
     # -- decomposition (mpi_routines.F90:317-351) ---------------------------
     def cell_ranges(self, d: int):

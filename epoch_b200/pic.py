@@ -118,6 +118,11 @@ class Simulation:
         cfg.strict_fp = int(strict_fp)
         cfg.sort_interval = sort_interval
         cfg.dt = deck.dt()
+        cfg.field_order = int(deck.field_order)
+        cfg.maxwell_solver = deck.maxwell_solver_code()
+        st = deck.stencil()
+        for i, k in enumerate(("alphax", "alphay", "betaxy", "betayx", "deltax", "deltay")):
+            cfg.stencil[i] = st[k]
         ncell = geo["n"][0] * geo["n"][1] * geo["n"][2]
         sp = (_lib.SpeciesCfg * max(1, len(deck.species)))()
         for i, s in enumerate(deck.species):

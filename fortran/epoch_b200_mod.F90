@@ -40,7 +40,9 @@ MODULE epoch_b200_mod
     INTEGER(C_INT32_T) :: n_species
     INTEGER(C_INT32_T) :: strict_fp
     INTEGER(C_INT32_T) :: sort_interval
-    INTEGER(C_INT32_T) :: reserved(5)
+    INTEGER(C_INT32_T) :: field_order
+    INTEGER(C_INT32_T) :: maxwell_solver
+    INTEGER(C_INT32_T) :: reserved(3)
     REAL(C_DOUBLE) :: dx(3)
     REAL(C_DOUBLE) :: dt
     REAL(C_DOUBLE) :: grid_min_local(3)
@@ -49,6 +51,7 @@ MODULE epoch_b200_mod
     REAL(C_DOUBLE) :: gmin(3), gmax(3)
     REAL(C_DOUBLE) :: min_outer(3)
     REAL(C_DOUBLE) :: max_outer(3)
+    REAL(C_DOUBLE) :: stencil(6)
   END TYPE epb_config
 
   ! struct epb_species
@@ -236,6 +239,8 @@ CONTAINS
     cfg%strict_fp = 1
     cfg%sort_interval = 0   ! library default
     cfg%reserved = 0
+    cfg%field_order = field_order
+    cfg%maxwell_solver = maxwell_solver   ! c_maxwell_solver_* (constants.F90); 0 = yee
     cfg%dx = (/ dx, dy, 1.0_num /)
     cfg%dt = dt
     cfg%grid_min_local = (/ x_grid_min_local, y_grid_min_local, 0.0_num /)
@@ -245,6 +250,7 @@ CONTAINS
     cfg%gmax = (/ x_max, y_max, 0.0_num /)
     cfg%min_outer = (/ x_min_outer, y_min_outer, 0.0_num /)
     cfg%max_outer = (/ x_max_outer, y_max_outer, 0.0_num /)
+    cfg%stencil = (/ alphax, alphay, betaxy, betayx, deltax, deltay /)   ! fields.f90 module variables
 
     ALLOCATE(sp(n_species))
     DO ispecies = 1, n_species

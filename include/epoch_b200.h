@@ -71,7 +71,9 @@ typedef struct epb_config {
   int32_t n_species;
   int32_t strict_fp;        /* 1: kernels built without FMA contraction (bit-level parity build) */
   int32_t sort_interval;    /* steps between on-GPU counting sorts; 0 = library default (3 or 8, by kernel) */
-  int32_t reserved[5];
+  int32_t field_order;      /* 0 or 2, 4, 6: finite-difference order of the Yee solver (fields.f90:32-46) */
+  int32_t maxwell_solver;   /* c_maxwell_solver_* (constants.F90:173-180): 0 yee; -1 custom, 2 lehe_x, 3 lehe_y, 6 pukhov: extended B stencil, 2D, order 2 (fields.f90:51-100) */
+  int32_t reserved[3];
   double dx[3];             /* dx, dy, dz */
   double dt;
   double grid_min_local[3]; /* x_grid_min_local ... (cell centre of local cell 1) */
@@ -80,6 +82,7 @@ typedef struct epb_config {
   double gmin[3], gmax[3];  /* x_min, x_max ... (global domain) */
   double min_outer[3];      /* x_min_outer ... (utilities.f90:367-369) */
   double max_outer[3];
+  double stencil[6];        /* alphax, alphay, betaxy, betayx, deltax, deltay as set_maxwell_solver leaves them */
 } epb_config;
 
 /* Mirror of TYPE particle_species (shared_data.F90:194-285), hot-path members only */

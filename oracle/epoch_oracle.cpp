@@ -106,6 +106,11 @@ struct Config {
   double dt;
   int n_species;
   int seed;  // 7842432 by default (setup.F90:567)
+  // fields.f90:32-100: finite-difference order (2, 4, 6) of the Yee solver; extended 2D stencils
+  // (order 2 only): maxwell_solver != 0 with the coefficients set_maxwell_solver derives
+  int field_order;
+  int maxwell_solver;
+  double alphax, alphay, betaxy, betayx, deltax, deltay;
 };
 
 // random_generator.f90:23-78 (KISS), :112-173 (polar Box-Muller)
@@ -470,12 +475,28 @@ void bfield_bcs(World &w, bool mpi_only) { field_bcs3(w, BX, mpi_only); }
 // FDTD: fields.f90:206-225 (E), :422-439 (B) for 2D; epoch3d fields.f90:312-337,
 // :632-654; epoch1d fields.f90:150-166, :296-303.  Yee, order 2, no CPML.
 // ---------------------------------------------------------------------------
+// Orders 4 and 6 replace every c*(difference) term of the order-2 expressions by the group
+// c1*c*(d1) [+ c2*c*(d2) [+ c3*c*(d3)]] with (c1,c2,c3) = (9/8,-1/24) resp. (75/64,-25/384,3/640),
+// added one after the other in the textual order of fields.f90:128-204 (2D), epoch3d
+// fields.f90:337-430, epoch1d fields.f90:166-215.  nt = field_order / 2.
+static inline void fd_coeffs(int order, double base, double *cc) {
+  if (order == 4) { cc[0] = (9.0 / 8.0) * base; cc[1] = (-1.0 / 24.0) * base; cc[2] = 0.0; }
+  else if (order == 6) { cc[0] = (75.0 / 64.0) * base; cc[1] = (-25.0 / 384.0) * base; cc[2] = (3.0 / 640.0) * base; }
+  else { cc[0] = base; cc[1] = 0.0; cc[2] = 0.0; }
+}
+
 template <int ND>
 void update_e_field(World &w, double hdt) {
   const double cnx = hdt / w.d[0] * (c * c);
   const double cny = ND >= 2 ? hdt / w.d[1] * (c * c) : 0.0;
   const double cnz = ND >= 3 ? hdt / w.d[2] * (c * c) : 0.0;
   const double fac = hdt / epsilon0;
+  const int order = w.cfg.field_order ? w.cfg.field_order : 2;
+  const int nt = order / 2;
+  double cx[3], cy[3], cz[3];
+  fd_coeffs(order, cnx, cx);
+  fd_coeffs(order, cny, cy);
+  fd_coeffs(order, cnz, cz);
   for (Rank &R : w.r) {
     Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
     const Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
@@ -485,22 +506,48 @@ void update_e_field(World &w, double hdt) {
     for (int iz = k0; iz <= k1; iz++)
       for (int iy = j0; iy <= j1; iy++)
         for (int ix = 0; ix <= R.n[0]; ix++) {
+          // backward differences: term k is f(i+k) - f(i-k-1)
+          auto dxb = [&](const Arr &f, int k) {
+            return ND == 1 ? f(ix + k) - f(ix - k - 1)
+                 : ND == 2 ? f(ix + k, iy) - f(ix - k - 1, iy) : f(ix + k, iy, iz) - f(ix - k - 1, iy, iz);
+          };
+          auto dyb = [&](const Arr &f, int k) {
+            return ND == 2 ? f(ix, iy + k) - f(ix, iy - k - 1) : f(ix, iy + k, iz) - f(ix, iy - k - 1, iz);
+          };
+          auto dzb = [&](const Arr &f, int k) { return f(ix, iy, iz + k) - f(ix, iy, iz - k - 1); };
           if (ND == 1) {
-            ex(ix) = ex(ix) - fac * jx(ix);
-            ey(ix) = ey(ix) - cnx * (bz(ix) - bz(ix - 1)) - fac * jy(ix);
-            ez(ix) = ez(ix) + cnx * (by(ix) - by(ix - 1)) - fac * jz(ix);
+            double v = ex(ix);
+            ex(ix) = v - fac * jx(ix);
+            v = ey(ix);
+            for (int k = 0; k < nt; k++) v = v - cx[k] * dxb(bz, k);
+            ey(ix) = v - fac * jy(ix);
+            v = ez(ix);
+            for (int k = 0; k < nt; k++) v = v + cx[k] * dxb(by, k);
+            ez(ix) = v - fac * jz(ix);
           } else if (ND == 2) {
-            ex(ix, iy) = ex(ix, iy) + cny * (bz(ix, iy) - bz(ix, iy - 1)) - fac * jx(ix, iy);
-            ey(ix, iy) = ey(ix, iy) - cnx * (bz(ix, iy) - bz(ix - 1, iy)) - fac * jy(ix, iy);
-            ez(ix, iy) = ez(ix, iy) + cnx * (by(ix, iy) - by(ix - 1, iy)) -
-                         cny * (bx(ix, iy) - bx(ix, iy - 1)) - fac * jz(ix, iy);
+            double v = ex(ix, iy);
+            for (int k = 0; k < nt; k++) v = v + cy[k] * dyb(bz, k);
+            ex(ix, iy) = v - fac * jx(ix, iy);
+            v = ey(ix, iy);
+            for (int k = 0; k < nt; k++) v = v - cx[k] * dxb(bz, k);
+            ey(ix, iy) = v - fac * jy(ix, iy);
+            v = ez(ix, iy);
+            for (int k = 0; k < nt; k++) v = v + cx[k] * dxb(by, k);
+            for (int k = 0; k < nt; k++) v = v - cy[k] * dyb(bx, k);
+            ez(ix, iy) = v - fac * jz(ix, iy);
           } else {
-            ex(ix, iy, iz) = ex(ix, iy, iz) + cny * (bz(ix, iy, iz) - bz(ix, iy - 1, iz)) -
-                             cnz * (by(ix, iy, iz) - by(ix, iy, iz - 1)) - fac * jx(ix, iy, iz);
-            ey(ix, iy, iz) = ey(ix, iy, iz) + cnz * (bx(ix, iy, iz) - bx(ix, iy, iz - 1)) -
-                             cnx * (bz(ix, iy, iz) - bz(ix - 1, iy, iz)) - fac * jy(ix, iy, iz);
-            ez(ix, iy, iz) = ez(ix, iy, iz) + cnx * (by(ix, iy, iz) - by(ix - 1, iy, iz)) -
-                             cny * (bx(ix, iy, iz) - bx(ix, iy - 1, iz)) - fac * jz(ix, iy, iz);
+            double v = ex(ix, iy, iz);
+            for (int k = 0; k < nt; k++) v = v + cy[k] * dyb(bz, k);
+            for (int k = 0; k < nt; k++) v = v - cz[k] * dzb(by, k);
+            ex(ix, iy, iz) = v - fac * jx(ix, iy, iz);
+            v = ey(ix, iy, iz);
+            for (int k = 0; k < nt; k++) v = v + cz[k] * dzb(bx, k);
+            for (int k = 0; k < nt; k++) v = v - cx[k] * dxb(bz, k);
+            ey(ix, iy, iz) = v - fac * jy(ix, iy, iz);
+            v = ez(ix, iy, iz);
+            for (int k = 0; k < nt; k++) v = v + cx[k] * dxb(by, k);
+            for (int k = 0; k < nt; k++) v = v - cy[k] * dyb(bx, k);
+            ez(ix, iy, iz) = v - fac * jz(ix, iy, iz);
           }
         }
   }
@@ -511,6 +558,15 @@ void update_b_field(World &w, double hdt) {
   const double hdtx = hdt / w.d[0];
   const double hdty = ND >= 2 ? hdt / w.d[1] : 0.0;
   const double hdtz = ND >= 3 ? hdt / w.d[2] : 0.0;
+  const int order = w.cfg.field_order ? w.cfg.field_order : 2;
+  const int nt = order / 2;
+  double cx[3], cy[3], cz[3];
+  fd_coeffs(order, hdtx, cx);
+  fd_coeffs(order, hdty, cy);
+  fd_coeffs(order, hdtz, cz);
+  const bool ext = (ND == 2) && w.cfg.maxwell_solver != 0;  // fields.f90:441-465
+  const double alphax = w.cfg.alphax, alphay = w.cfg.alphay, betaxy = w.cfg.betaxy, betayx = w.cfg.betayx,
+               deltax = w.cfg.deltax, deltay = w.cfg.deltay;
   for (Rank &R : w.r) {
     const Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
     Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
@@ -519,21 +575,61 @@ void update_b_field(World &w, double hdt) {
     for (int iz = k0; iz <= k1; iz++)
       for (int iy = j0; iy <= j1; iy++)
         for (int ix = 0; ix <= R.n[0]; ix++) {
+          // forward differences: term k is f(i+k+1) - f(i-k)
+          auto dxf = [&](const Arr &f, int k) {
+            return ND == 1 ? f(ix + k + 1) - f(ix - k)
+                 : ND == 2 ? f(ix + k + 1, iy) - f(ix - k, iy) : f(ix + k + 1, iy, iz) - f(ix - k, iy, iz);
+          };
+          auto dyf = [&](const Arr &f, int k) {
+            return ND == 2 ? f(ix, iy + k + 1) - f(ix, iy - k) : f(ix, iy + k + 1, iz) - f(ix, iy - k, iz);
+          };
+          auto dzf = [&](const Arr &f, int k) { return f(ix, iy, iz + k + 1) - f(ix, iy, iz - k); };
           if (ND == 1) {
-            by(ix) = by(ix) + hdtx * (ez(ix + 1) - ez(ix));
-            bz(ix) = bz(ix) - hdtx * (ey(ix + 1) - ey(ix));
+            double v = by(ix);
+            for (int k = 0; k < nt; k++) v = v + cx[k] * dxf(ez, k);
+            by(ix) = v;
+            v = bz(ix);
+            for (int k = 0; k < nt; k++) v = v - cx[k] * dxf(ey, k);
+            bz(ix) = v;
+          } else if (ND == 2 && ext) {
+            // x-derivative of f at (ix+1/2, iy) and y-derivative at (ix, iy+1/2), extended stencil
+            auto ddx = [&](const Arr &f) {
+              return alphax * (f(ix + 1, iy) - f(ix, iy)) +
+                     betaxy * (f(ix + 1, iy + 1) - f(ix, iy + 1) + f(ix + 1, iy - 1) - f(ix, iy - 1)) +
+                     deltax * (f(ix + 2, iy) - f(ix - 1, iy));
+            };
+            auto ddy = [&](const Arr &f) {
+              return alphay * (f(ix, iy + 1) - f(ix, iy)) +
+                     betayx * (f(ix + 1, iy + 1) - f(ix + 1, iy) + f(ix - 1, iy + 1) - f(ix - 1, iy)) +
+                     deltay * (f(ix, iy + 2) - f(ix, iy - 1));
+            };
+            bx(ix, iy) = bx(ix, iy) - hdty * ddy(ez);
+            by(ix, iy) = by(ix, iy) + hdtx * ddx(ez);
+            bz(ix, iy) = bz(ix, iy) - hdtx * ddx(ey) + hdty * ddy(ex);
           } else if (ND == 2) {
-            bx(ix, iy) = bx(ix, iy) - hdty * (ez(ix, iy + 1) - ez(ix, iy));
-            by(ix, iy) = by(ix, iy) + hdtx * (ez(ix + 1, iy) - ez(ix, iy));
-            bz(ix, iy) = bz(ix, iy) - hdtx * (ey(ix + 1, iy) - ey(ix, iy)) +
-                         hdty * (ex(ix, iy + 1) - ex(ix, iy));
+            double v = bx(ix, iy);
+            for (int k = 0; k < nt; k++) v = v - cy[k] * dyf(ez, k);
+            bx(ix, iy) = v;
+            v = by(ix, iy);
+            for (int k = 0; k < nt; k++) v = v + cx[k] * dxf(ez, k);
+            by(ix, iy) = v;
+            v = bz(ix, iy);
+            for (int k = 0; k < nt; k++) v = v - cx[k] * dxf(ey, k);
+            for (int k = 0; k < nt; k++) v = v + cy[k] * dyf(ex, k);
+            bz(ix, iy) = v;
           } else {
-            bx(ix, iy, iz) = bx(ix, iy, iz) - hdty * (ez(ix, iy + 1, iz) - ez(ix, iy, iz)) +
-                             hdtz * (ey(ix, iy, iz + 1) - ey(ix, iy, iz));
-            by(ix, iy, iz) = by(ix, iy, iz) - hdtz * (ex(ix, iy, iz + 1) - ex(ix, iy, iz)) +
-                             hdtx * (ez(ix + 1, iy, iz) - ez(ix, iy, iz));
-            bz(ix, iy, iz) = bz(ix, iy, iz) - hdtx * (ey(ix + 1, iy, iz) - ey(ix, iy, iz)) +
-                             hdty * (ex(ix, iy + 1, iz) - ex(ix, iy, iz));
+            double v = bx(ix, iy, iz);
+            for (int k = 0; k < nt; k++) v = v - cy[k] * dyf(ez, k);
+            for (int k = 0; k < nt; k++) v = v + cz[k] * dzf(ey, k);
+            bx(ix, iy, iz) = v;
+            v = by(ix, iy, iz);
+            for (int k = 0; k < nt; k++) v = v - cz[k] * dzf(ex, k);
+            for (int k = 0; k < nt; k++) v = v + cx[k] * dxf(ez, k);
+            by(ix, iy, iz) = v;
+            v = bz(ix, iy, iz);
+            for (int k = 0; k < nt; k++) v = v - cx[k] * dxf(ey, k);
+            for (int k = 0; k < nt; k++) v = v + cy[k] * dyf(ex, k);
+            bz(ix, iy, iz) = v;
           }
         }
   }

@@ -20,6 +20,9 @@ class _Config(C.Structure):
         ("ndims", C.c_int), ("n_global", C.c_int * 3), ("nproc", C.c_int * 3),
         ("xmin", C.c_double * 3), ("xmax", C.c_double * 3), ("bc_field", C.c_int * 6),
         ("dt", C.c_double), ("n_species", C.c_int), ("seed", C.c_int),
+        ("field_order", C.c_int), ("maxwell_solver", C.c_int),
+        ("alphax", C.c_double), ("alphay", C.c_double), ("betaxy", C.c_double), ("betayx", C.c_double),
+        ("deltax", C.c_double), ("deltay", C.c_double),
     ]
 
 
@@ -94,6 +97,10 @@ class Oracle:
         cfg.dt = deck.dt()
         cfg.n_species = len(deck.species)
         cfg.seed = deck.seed
+        cfg.field_order = int(getattr(deck, "field_order", 2))
+        cfg.maxwell_solver = deck.maxwell_solver_code() if hasattr(deck, "maxwell_solver_code") else 0
+        for k, v in (deck.stencil() if hasattr(deck, "stencil") else {}).items():
+            setattr(cfg, k, v)
         sp = (_Species * max(1, len(deck.species)))()
         for i, s in enumerate(deck.species):
             sp[i].charge, sp[i].mass = s.charge, s.mass

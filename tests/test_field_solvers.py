@@ -1,0 +1,158 @@
+"""Field orders 4/6 and the extended Maxwell stencils (fields.f90:32-100, :128-204, :441-529).
+
+CPU: the oracle's solvers reproduce the group velocities the reference's own test asserts
+(epoch2d/tests/test_maxwell_solvers.py:55-63,150-171: Lehe, Pukhov and Yee dispersion, rtol 0.012) -- on a
+periodic box with an initial wave packet, because the reference deck's CPML boundaries are outside the
+hot path -- and the order-4/6 numerical dispersion relation.  GPU: the CUDA path agrees with the oracle
+to 1e-12 for every option in 1D/2D/3D."""
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from oracle.oracle import Oracle
+
+c = D.c
+FIELDS6 = ("ex", "ey", "ez", "bx", "by", "bz")
+
+
+def _box2d(solver="yee", order=2, nx=240, ny=24, custom=None):
+    # grid of the reference test deck (nx = 240 over 24 um, dx = dy = 0.1 um), periodic
+    L = 24e-6
+    return D.Deck(2, [nx, ny], [-L / 2, -L / 2 * ny / nx], [L / 2, L / 2 * ny / nx], ["periodic"] * 4,
+                  dt_multiplier=0.95, maxwell_solver=solver, field_order=order, stencil_custom=custom)
+
+
+def _steps(backend, n):
+    backend.init()
+    for _ in range(n):
+        backend.fields_half()
+        backend.push()
+        backend.current_finish()
+        backend.fields_final()
+
+
+def _packet(dk, o, lam=0.5e-6, x0=-6e-6, width=1.2e-6):
+    """Ey/Bz wave packet travelling in +x (plane in y), written into the oracle's arrays."""
+    ng = 5
+    dx = dk.dx(0)
+    dt = dk.dt()
+    k = 2 * np.pi / lam
+    ix = np.arange(1 - ng, dk.n[0] + ng + 1)
+    x_c = dk.grid_min(0) + (ix - 1) * dx                 # cell centres: ey
+    x_s = x_c + dx / 2                                   # staggered in x: bz
+    e0 = 1.0e9
+    ey = e0 * np.exp(-((x_c - x0) / width) ** 2) * np.sin(k * (x_c - x0))
+    # EPOCH's half-step splitting leaves E and B at the same time level at step boundaries
+    xs = x_s
+    bz = e0 / c * np.exp(-((xs - x0) / width) ** 2) * np.sin(k * (xs - x0))
+    o.field(0, "ey")[...] = ey      # arrays are (z, y, x): broadcast along x
+    o.field(0, "bz")[...] = bz
+    return x_c
+
+
+def _centroid(dk, o, x_c, half_window=3.0e-6):
+    """Centroid of the forward packet's envelope (analytic signal), in a window around its peak: the
+    initial condition E(x), B = E/c is not a pure forward mode of the discrete system, and the few per
+    mille of energy it puts into a backward wave would bias a whole-box centroid by more than the
+    tolerance."""
+    ng = 5
+    ey = o.field(0, "ey")[0, ng, ng:-ng]
+    x = x_c[ng:-ng]
+    F = np.fft.fft(ey)
+    n = ey.size
+    F[n // 2 + 1:] = 0.0
+    F[1:n // 2] *= 2.0
+    e2 = np.abs(np.fft.ifft(F)) ** 2
+    m = np.abs(x - x[np.argmax(e2)]) <= half_window
+    return float((x[m] * e2[m]).sum() / e2[m].sum())
+
+
+@pytest.mark.parametrize("solver", ["yee", "lehe_x", "pukhov"])
+def test_group_velocity_matches_reference_formulas(solver):
+    dk = _box2d(solver)
+    dx, dt, lam = dk.dx(0), dk.dt(), 0.5e-6
+    k_l = 2 * np.pi / lam
+    # epoch2d/tests/test_maxwell_solvers.py:59-63
+    vg = {"lehe_x": c * (1.0 + 2.0 * (1.0 - c * dt / dx) * (k_l * dx / 2.0) ** 2),
+          "yee": c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt / dx * np.sin(k_l * dx / 2.0)) ** 2),
+          "pukhov": c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt / dx * np.sin(k_l * dx / 2.0)) ** 2)}[solver]
+    o = Oracle(dk)
+    x_c = _packet(dk, o)
+    o.init()
+    ts, xs = [], []
+    nsteps = int(30e-15 / dt)
+    for n in range(nsteps):
+        o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+        if n % 5 == 4 and (n + 1) * dt > 12e-15:   # once the spurious backward wave has left the window
+            ts.append((n + 1) * dt)
+            xs.append(_centroid(dk, o, x_c))
+    vg_sim = np.polyfit(ts, xs, 1)[0]
+    assert np.isclose(vg_sim, vg, rtol=0.012), (solver, vg_sim, vg)
+
+
+@pytest.mark.parametrize("order", [2, 4, 6])
+def test_field_order_dispersion_1d(order):
+    """Standing plane wave on a periodic 1D grid: the measured frequency follows the order-N numerical
+    dispersion relation sin(w dt/2)/(c dt) = sum_k c_k sin((2k+1) kappa dx/2)/dx (fields.f90:134-167)."""
+    nx, mode = 64, 6
+    dk = D.Deck(1, [nx], [0.0], [1.0e-5], ["periodic"] * 2, dt_multiplier=0.5, field_order=order)
+    dx, dt = dk.dx(0), dk.dt()
+    kap = 2 * np.pi * mode / (dk.xmax[0] - dk.xmin[0])
+    ck = {2: [1.0], 4: [9 / 8, -1 / 24], 6: [75 / 64, -25 / 384, 3 / 640]}[order]
+    s = sum(cc * np.sin((2 * i + 1) * kap * dx / 2) for i, cc in enumerate(ck)) / dx
+    w_num = 2.0 / dt * np.arcsin(c * dt * s)
+    o = Oracle(dk)
+    ng = 5
+    ix = np.arange(1 - ng, nx + ng + 1)
+    x_c = dk.grid_min(0) + (ix - 1) * dx
+    o.field(0, "ey")[...] = np.sin(kap * x_c)           # standing wave: E = sin(kx) cos(wt), B = 0 at t = 0 ...
+    o.init()
+    amp, ts = [], []
+    nsteps = 400
+    for n in range(nsteps):
+        o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+        ey = o.field(0, "ey").reshape(-1)[ng:-ng]
+        amp.append(2.0 / nx * np.sum(ey * np.sin(kap * x_c[ng:-ng])))
+        ts.append((n + 1) * dt)
+    amp, ts = np.array(amp), np.array(ts)
+    # frequency from the zero crossings of the projected amplitude
+    zc = np.where(np.sign(amp[:-1]) != np.sign(amp[1:]))[0]
+    tz = ts[zc] + (ts[zc + 1] - ts[zc]) * amp[zc] / (amp[zc] - amp[zc + 1])
+    w_sim = np.pi / np.mean(np.diff(tz))
+    assert np.isclose(w_sim, w_num, rtol=2e-4), (order, w_sim, w_num, c * kap)
+    if order > 2:  # and it is closer to the vacuum value than order 2
+        s2 = np.sin(kap * dx / 2) / dx
+        w2 = 2.0 / dt * np.arcsin(c * dt * s2)
+        assert abs(w_num - c * kap) < abs(w2 - c * kap)
+
+
+CASES = [
+    (1, (48,), dict(field_order=4)), (1, (48,), dict(field_order=6)),
+    (2, (40, 24), dict(field_order=4)), (2, (40, 24), dict(field_order=6)),
+    (3, (12, 10, 9), dict(field_order=4)), (3, (12, 10, 9), dict(field_order=6)),
+    (2, (40, 24), dict(maxwell_solver="lehe_x")), (2, (40, 24), dict(maxwell_solver="lehe_y")),
+    (2, (40, 24), dict(maxwell_solver="pukhov")),
+    (2, (40, 24), dict(maxwell_solver="custom",
+                       stencil_custom=dict(betaxy=0.1, betayx=0.05, deltax=0.02, deltay=0.01, dt=1.0e-16))),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n,opts", CASES)
+def test_cuda_solver_options_match_oracle(ndims, n, opts):
+    from tests import decks
+    from tests.gpu_util import FIELDS, make_pair, rel_l2, run_both, set_random_fields
+    dk = decks.thermal(ndims, n, ppc=4, temp_k=1.0e8)
+    for k, v in opts.items():
+        setattr(dk, k, v)
+    o, sim = make_pair(dk, strict=True)
+    set_random_fields(o, sim, dk, e_amp=1e8, b_amp=0.3)
+    run_both(dk, o, sim, 6)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-12, name
+
+
+def test_unsupported_solver_combinations_are_refused():
+    dk = D.Deck(3, [8, 8, 8], [0.0] * 3, [1.0] * 3, ["periodic"] * 6, maxwell_solver="lehe_x")
+    with pytest.raises(NotImplementedError):
+        dk.stencil()
