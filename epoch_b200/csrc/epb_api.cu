@@ -488,6 +488,44 @@ __global__ void __launch_bounds__(256) k_update_b_gen(const __grid_constant__ Fi
   }
 }
 
+// smooth_array (current_smooth.F90:111-137; 1D :104-126; 3D :114-144): one strided binomial pass
+// of the three current components, work arrays -> J on the interior cells
+struct SmoothOp {
+  const double *wk[3];
+  double *a[3];
+  int nd, n[3], sz[3], cs;
+  double alpha, beta;
+};
+__global__ void __launch_bounds__(256) k_smooth(const __grid_constant__ SmoothOp S) {
+  const size_t total = (size_t)S.n[0] * S.n[1] * S.n[2];
+  const ptrdiff_t sx = S.cs, sy = (ptrdiff_t)S.sz[0] * S.cs, szz = (ptrdiff_t)S.sz[0] * S.sz[1] * S.cs;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % S.n[0]) + 1;
+    const int iy = (int)((t / S.n[0]) % S.n[1]) + 1;
+    const int iz = (int)(t / ((size_t)S.n[0] * S.n[1])) + 1;
+    const ptrdiff_t o = (ptrdiff_t)fofs(S.sz, S.nd, ix, iy, iz);
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const double *w = S.wk[q];
+      double nb = w[o - sx] + w[o + sx];
+      if (S.nd >= 2) nb = nb + w[o - sy] + w[o + sy];
+      if (S.nd >= 3) nb = nb + w[o - szz] + w[o + szz];
+      S.a[q][o] = S.alpha * w[o] + nb * S.beta;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_smooth_copyback(const __grid_constant__ SmoothOp S) {
+  const size_t total = (size_t)S.n[0] * S.n[1] * S.n[2];
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % S.n[0]) + 1;
+    const int iy = (int)((t / S.n[0]) % S.n[1]) + 1;
+    const int iz = (int)(t / ((size_t)S.n[0] * S.n[1])) + 1;
+    const size_t o = fofs(S.sz, S.nd, ix, iy, iz);
+#pragma unroll
+    for (int q = 0; q < 3; q++) const_cast<double *>(S.wk[q])[o] = S.a[q][o];
+  }
+}
+
 static void fd_coeffs(int order, double base, double *cc) {
   if (order == 4) { cc[0] = (9.0 / 8.0) * base; cc[1] = (-1.0 / 24.0) * base; cc[2] = 0.0; }
   else if (order == 6) { cc[0] = (75.0 / 64.0) * base; cc[1] = (-25.0 / 384.0) * base; cc[2] = (3.0 / 640.0) * base; }
@@ -787,6 +825,9 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     const int fo = cfg->field_order;
     if (fo != 0 && fo != 2 && fo != 4 && fo != 6)
       return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "field_order %d (2, 4 or 6)", fo);
+    for (int q = 0; q < 4; q++)
+      if (((cfg->smooth_strides >> (4 * q)) & 15) > NG)
+        return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "smoothing stride > %d ghost cells", NG);
     if (cfg->maxwell_solver != 0 && (cfg->ndims != 2 || (fo != 0 && fo != 2)))
       return epb_fail(nullptr, EPB_ERR_UNSUPPORTED,
                       "extended Maxwell stencils (maxwell_solver %d) are implemented for epoch2d, field_order 2", cfg->maxwell_solver);
@@ -823,8 +864,10 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   h->plane = (size_t)h->sz[1] * h->sz[2];
   EPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
-  EPB_CUDA(h, cudaMalloc(&h->fields, 9 * h->fsize * sizeof(double)));
-  EPB_CUDA(h, cudaMemsetAsync(h->fields, 0, 9 * h->fsize * sizeof(double), h->stream));
+  // ex..jz, plus the three work arrays of smooth_current when smoothing is on (field ids 9..11)
+  const int nfields = cfg->smooth_its + cfg->smooth_comp_its > 0 ? 12 : 9;
+  EPB_CUDA(h, cudaMalloc(&h->fields, nfields * h->fsize * sizeof(double)));
+  EPB_CUDA(h, cudaMemsetAsync(h->fields, 0, nfields * h->fsize * sizeof(double), h->stream));
   EPB_CUDA(h, cudaMalloc(&h->snap, 12 * h->plane * sizeof(double)));
   EPB_CUDA(h, cudaMemsetAsync(h->snap, 0, 12 * h->plane * sizeof(double), h->stream));
   EPB_CUDA(h, cudaMalloc(&h->src, 4 * h->plane * sizeof(double)));
@@ -1236,6 +1279,35 @@ int epb_current_finish(epb_handle *h) {
   if (rc) return rc;
   rc = epb_halo_exchange(h, EPB_JX, 3, false);  // field_bc(jx|jy|jz, jng)
   if (rc) return rc;
+  if (c.smooth_its + c.smooth_comp_its > 0) {  // smooth_current (current_smooth.F90:50-141)
+    const int WK0 = 9;
+    EPB_CUDA(h, cudaMemcpyAsync(h->f(WK0), h->f(EPB_JX), 3 * h->fsize * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    int strides[4] = {1, 0, 0, 0}, ns = 0;
+    for (int q = 0; q < 4; q++) {
+      const int v = (c.smooth_strides >> (4 * q)) & 15;
+      if (v) strides[ns++] = v;
+    }
+    if (ns == 0) ns = 1;
+    SmoothOp S;
+    for (int q = 0; q < 3; q++) { S.wk[q] = h->f(WK0 + q); S.a[q] = h->f(EPB_JX + q); }
+    S.nd = c.ndims;
+    for (int k = 0; k < 3; k++) { S.n[k] = c.n[k]; S.sz[k] = h->sz[k]; }
+    double alpha = 0.5;
+    S.beta = c.ndims == 1 ? (1.0 - alpha) * 0.5 : c.ndims == 2 ? (1.0 - alpha) * 0.25 : (1.0 - alpha) / 6.0;
+    const size_t total = (size_t)c.n[0] * c.n[1] * c.n[2];
+    for (int it = 1; it <= c.smooth_its + c.smooth_comp_its; it++) {
+      for (int is = 0; is < ns; is++) {
+        rc = epb_halo_exchange(h, WK0, 3, false);
+        if (rc) return rc;
+        S.cs = strides[is];
+        S.alpha = alpha;
+        k_smooth<<<nblocks(total, 148 * 32), 256, 0, h->stream>>>(S);
+        k_smooth_copyback<<<nblocks(total, 148 * 32), 256, 0, h->stream>>>(S);
+        h->launches += 2;
+      }
+      if (it > c.smooth_its) alpha = (double)c.smooth_its * 0.5 + 1.0;  // as in the reference: after the pass
+    }
+  }
   EPB_CUDA(h, cudaGetLastError());
   return EPB_OK;
 }

@@ -96,6 +96,10 @@ class Deck:
     field_order: int = 2                    # control block field_order: 2, 4 or 6 (fields.f90:32-46)
     maxwell_solver: str = "yee"             # yee | lehe_x | lehe_y | pukhov | custom (2D, order 2)
     stencil_custom: Optional[dict] = None   # custom solver: betaxy, betayx, deltax, deltay, dt
+    smooth_currents: bool = False           # control block (deck_control_block.F90:343,456-471)
+    smooth_iterations: int = 1
+    smooth_compensation: bool = False
+    smooth_strides: Sequence[int] = (1,)    # 'auto' = (1, 2, 3, 4)
 
     # -- grid (setup.F90:162-204) ------------------------------------------
     def dx(self, d: int) -> float:

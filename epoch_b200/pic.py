@@ -120,6 +120,10 @@ class Simulation:
         cfg.dt = deck.dt()
         cfg.field_order = int(deck.field_order)
         cfg.maxwell_solver = deck.maxwell_solver_code()
+        if deck.smooth_currents:
+            cfg.smooth_its = int(deck.smooth_iterations)
+            cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
+            cfg.smooth_strides = sum(int(v) << (4 * i) for i, v in enumerate(deck.smooth_strides))
         st = deck.stencil()
         for i, k in enumerate(("alphax", "alphay", "betaxy", "betayx", "deltax", "deltay")):
             cfg.stencil[i] = st[k]

@@ -42,7 +42,9 @@ MODULE epoch_b200_mod
     INTEGER(C_INT32_T) :: sort_interval
     INTEGER(C_INT32_T) :: field_order
     INTEGER(C_INT32_T) :: maxwell_solver
-    INTEGER(C_INT32_T) :: reserved(3)
+    INTEGER(C_INT32_T) :: smooth_its
+    INTEGER(C_INT32_T) :: smooth_comp_its
+    INTEGER(C_INT32_T) :: smooth_strides
     REAL(C_DOUBLE) :: dx(3)
     REAL(C_DOUBLE) :: dt
     REAL(C_DOUBLE) :: grid_min_local(3)
@@ -238,7 +240,18 @@ CONTAINS
     cfg%n_species = n_species
     cfg%strict_fp = 1
     cfg%sort_interval = 0   ! library default
-    cfg%reserved = 0
+    cfg%smooth_its = 0
+    cfg%smooth_comp_its = 0
+    cfg%smooth_strides = 0
+    IF (smooth_currents) THEN
+      cfg%smooth_its = smooth_its
+      cfg%smooth_comp_its = smooth_comp_its
+      IF (ALLOCATED(smooth_strides)) THEN
+        DO i = 1, MIN(4, SIZE(smooth_strides))
+          cfg%smooth_strides = IOR(cfg%smooth_strides, ISHFT(smooth_strides(i), 4 * (i - 1)))
+        END DO
+      END IF
+    END IF
     cfg%field_order = field_order
     cfg%maxwell_solver = maxwell_solver   ! c_maxwell_solver_* (constants.F90); 0 = yee
     cfg%dx = (/ dx, dy, 1.0_num /)

@@ -73,7 +73,9 @@ typedef struct epb_config {
   int32_t sort_interval;    /* steps between on-GPU counting sorts; 0 = library default (3 or 8, by kernel) */
   int32_t field_order;      /* 0 or 2, 4, 6: finite-difference order of the Yee solver (fields.f90:32-46) */
   int32_t maxwell_solver;   /* c_maxwell_solver_* (constants.F90:173-180): 0 yee; -1 custom, 2 lehe_x, 3 lehe_y, 6 pukhov: extended B stencil, 2D, order 2 (fields.f90:51-100) */
-  int32_t reserved[3];
+  int32_t smooth_its;       /* smooth_currents: smooth_its passes (0 = off), current_smooth.F90:50-141 */
+  int32_t smooth_comp_its;  /* smooth_compensation: 0 or 1 */
+  int32_t smooth_strides;   /* up to 4 strides (1..5), one per nibble, low nibble first; 0 = stride 1 */
   double dx[3];             /* dx, dy, dz */
   double dt;
   double grid_min_local[3]; /* x_grid_min_local ... (cell centre of local cell 1) */

@@ -59,7 +59,7 @@ enum {
 // constants.F90:549-559 (triangle): sf_min=-1, sf_max=1, png=3, ng=png+2
 constexpr int sf_min = -1, sf_max = 1, png = 3, NG = png + 2;
 
-enum { EX, EY, EZ, BX, BY, BZ, JX, JY, JZ, NFIELD };
+enum { EX, EY, EZ, BX, BY, BZ, JX, JY, JZ, WK, NFIELD };  // WK: work array of smooth_array
 
 // Fortran-style array  a(1-g:n1+g [, 1-g:n2+g [, 1-g:n3+g]])
 struct Arr {
@@ -111,6 +111,8 @@ struct Config {
   int field_order;
   int maxwell_solver;
   double alphax, alphay, betaxy, betayx, deltax, deltay;
+  // current_smooth.F90:50-141: smooth_currents with smooth_its (+ smooth_comp_its) passes over strides
+  int smooth_its, smooth_comp_its, smooth_nstrides, smooth_strides[4];
 };
 
 // random_generator.f90:23-78 (KISS), :112-173 (polar Box-Muller)
@@ -1211,6 +1213,54 @@ void particle_periodic_bcs(World &w, int which) {
   }
 }
 
+// current_smooth.F90:61-141 (strided binomial filter; 1D :104-126, 3D :114-144).  As in the
+// reference, beta is fixed by the initial alpha and alpha only changes after the first
+// compensation pass has already been done.
+void smooth_array(World &w, int which) {
+  const int nd = w.nd;
+  const int its = w.cfg.smooth_its, comp_its = w.cfg.smooth_comp_its;
+  int strides[4] = {1, 0, 0, 0}, ns = 1;
+  if (w.cfg.smooth_nstrides > 0) {
+    ns = w.cfg.smooth_nstrides;
+    for (int i = 0; i < ns; i++) strides[i] = w.cfg.smooth_strides[i];
+  }
+  double alpha = 0.5;
+  const double beta = nd == 1 ? (1.0 - alpha) * 0.5 : nd == 2 ? (1.0 - alpha) * 0.25 : (1.0 - alpha) / 6.0;
+  for (Rank &R : w.r) R.f[WK].v = R.f[which].v;
+  for (int it = 1; it <= its + comp_its; it++) {
+    for (int is = 0; is < ns; is++) {
+      field_bc(w, WK);
+      const int cs = strides[is];
+      for (Rank &R : w.r) {
+        Arr &a = R.f[which];
+        Arr &wk = R.f[WK];
+        const int k1 = nd >= 3 ? R.n[2] : 1, j1 = nd >= 2 ? R.n[1] : 1;
+        for (int iz = 1; iz <= k1; iz++)
+          for (int iy = 1; iy <= j1; iy++)
+            for (int ix = 1; ix <= R.n[0]; ix++) {
+              if (nd == 1)
+                a(ix) = alpha * wk(ix) + (wk(ix - cs) + wk(ix + cs)) * beta;
+              else if (nd == 2)
+                a(ix, iy) = alpha * wk(ix, iy) +
+                            (wk(ix - cs, iy) + wk(ix + cs, iy) + wk(ix, iy - cs) + wk(ix, iy + cs)) * beta;
+              else
+                a(ix, iy, iz) = alpha * wk(ix, iy, iz) +
+                                (wk(ix - cs, iy, iz) + wk(ix + cs, iy, iz) + wk(ix, iy - cs, iz) + wk(ix, iy + cs, iz) +
+                                 wk(ix, iy, iz - cs) + wk(ix, iy, iz + cs)) * beta;
+            }
+        for (int iz = 1; iz <= k1; iz++)
+          for (int iy = 1; iy <= j1; iy++)
+            for (int ix = 1; ix <= R.n[0]; ix++) {
+              if (nd == 1) wk(ix) = a(ix);
+              else if (nd == 2) wk(ix, iy) = a(ix, iy);
+              else wk(ix, iy, iz) = a(ix, iy, iz);
+            }
+      }
+    }
+    if (it > its) alpha = (double)its * 0.5 + 1.0;
+  }
+}
+
 // current_smooth.F90:29-45 with boundary.F90:1466-1475, 783-804
 void current_finish(World &w) {
   for (int q = 0; q < 3; q++) {
@@ -1218,6 +1268,8 @@ void current_finish(World &w) {
     particle_periodic_bcs(w, JX + q);
   }
   for (int q = 0; q < 3; q++) field_bc(w, JX + q);
+  if (w.cfg.smooth_its + w.cfg.smooth_comp_its > 0)
+    for (int q = 0; q < 3; q++) smooth_array(w, JX + q);
 }
 
 // ---------------------------------------------------------------------------

@@ -23,6 +23,8 @@ class _Config(C.Structure):
         ("field_order", C.c_int), ("maxwell_solver", C.c_int),
         ("alphax", C.c_double), ("alphay", C.c_double), ("betaxy", C.c_double), ("betayx", C.c_double),
         ("deltax", C.c_double), ("deltay", C.c_double),
+        ("smooth_its", C.c_int), ("smooth_comp_its", C.c_int), ("smooth_nstrides", C.c_int),
+        ("smooth_strides", C.c_int * 4),
     ]
 
 
@@ -101,6 +103,12 @@ class Oracle:
         cfg.maxwell_solver = deck.maxwell_solver_code() if hasattr(deck, "maxwell_solver_code") else 0
         for k, v in (deck.stencil() if hasattr(deck, "stencil") else {}).items():
             setattr(cfg, k, v)
+        if getattr(deck, "smooth_currents", False):
+            cfg.smooth_its = int(deck.smooth_iterations)
+            cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
+            cfg.smooth_nstrides = len(deck.smooth_strides)
+            for i, v in enumerate(deck.smooth_strides):
+                cfg.smooth_strides[i] = int(v)
         sp = (_Species * max(1, len(deck.species)))()
         for i, s in enumerate(deck.species):
             sp[i].charge, sp[i].mass = s.charge, s.mass

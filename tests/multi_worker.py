@@ -36,6 +36,11 @@ def make_deck(name, world):
         return decks.thermal(2, (48, 40), ppc=5, temp_k=4.0e8, nproc=(world, 1, 1), bc="reflect"), 10, 1e-12
     if name == "foil2d":
         return decks.foil2d(n=(96, 64), nproc=(world, 1, 1), nsteps=30), 30, 1e-11
+    if name == "solver2d":   # order-4 field solver + strided compensated current smoothing across ranks
+        dk = decks.thermal(2, (48, 40), ppc=5, temp_k=3.0e8, nproc=(world, 1, 1))
+        dk.field_order = 4
+        dk.smooth_currents, dk.smooth_iterations, dk.smooth_compensation, dk.smooth_strides = True, 2, True, (1, 2)
+        return dk, 8, 1e-12
     if name == "laser2d":
         return decks.laser2d(nproc=(world, 1, 1), n=64), 40, 1e-12
     raise KeyError(name)

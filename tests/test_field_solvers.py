@@ -152,6 +152,50 @@ def test_cuda_solver_options_match_oracle(ndims, n, opts):
         assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-12, name
 
 
+SMOOTH_CASES = [
+    (1, (48,), dict(smooth_iterations=1)),
+    (2, (40, 24), dict(smooth_iterations=1)),
+    (2, (40, 24), dict(smooth_iterations=2, smooth_compensation=True, smooth_strides=(1, 2, 3, 4))),
+    (3, (12, 10, 9), dict(smooth_iterations=1, smooth_compensation=True, smooth_strides=(1, 2))),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n,opts", SMOOTH_CASES)
+def test_cuda_current_smoothing_matches_oracle(ndims, n, opts):
+    """smooth_current (current_smooth.F90:50-141) on the device vs the oracle."""
+    from tests import decks
+    from tests.gpu_util import FIELDS, make_pair, rel_l2, run_both
+    dk = decks.thermal(ndims, n, ppc=4, temp_k=3.0e8)
+    dk.smooth_currents = True
+    for k, v in opts.items():
+        setattr(dk, k, v)
+    o, sim = make_pair(dk, strict=True)
+    run_both(dk, o, sim, 5)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-12, name
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 8, 6))])
+def test_binomial_filter_properties(ndims, n):
+    """One stride-1 pass (alpha = 1/2, beta = (1 - alpha) / (2 ndims)) removes the grid-scale (checkerboard)
+    mode exactly and leaves a uniform current unchanged (current_smooth.F90:104-126)."""
+    bcs = ["periodic"] * (2 * ndims)
+    dk = D.Deck(ndims, list(n), [0.0] * ndims, [1.0e-5] * ndims, bcs, smooth_currents=True)
+    o = Oracle(dk)
+    ng = 5
+    idx = np.indices(tuple(reversed(n))).sum(axis=0)          # (z, y, x) index sum
+    checker = np.where(idx % 2 == 0, 1.0, -1.0)
+    inner = tuple(slice(ng, -ng) if d >= 3 - ndims else slice(None) for d in range(3))
+    for name, val in (("jx", checker), ("jy", np.full_like(checker, 3.5))):
+        a = o.field(0, name)
+        a[...] = 0.0
+        a[inner] = val.reshape(a[inner].shape)
+    o.current_finish()
+    assert np.max(np.abs(o.field(0, "jx")[inner])) <= 1e-15
+    assert np.allclose(o.field(0, "jy")[inner], 3.5, rtol=1e-15)
+
+
 def test_unsupported_solver_combinations_are_refused():
     dk = D.Deck(3, [8, 8, 8], [0.0] * 3, [1.0] * 3, ["periodic"] * 6, maxwell_solver="lehe_x")
     with pytest.raises(NotImplementedError):
