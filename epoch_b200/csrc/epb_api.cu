@@ -280,6 +280,100 @@ __global__ void __launch_bounds__(256) k_outflow(const __grid_constant__ Outflow
   }
 }
 
+// ---- laser / outflow boundaries on the y and z faces ---------------------------------------------
+// setup_field_boundaries (setup.F90:430-447; epoch3d :431-500) and outflow_bcs_{y,z}_{min,max}
+// (laser.f90:462-610; epoch3d laser.f90:510-830): the x-face expressions under the cyclic permutation
+// of axes and components (a = face normal, b = a+1, cc = a+2).  Plane index t runs over the two other
+// axes in axis order, lower axis fastest, ghosted extents for the snapshots and (0:n) for the update.
+struct FaceOp {
+  double *f[9];
+  double *snap;            // [2][6][plane] of this axis
+  const double *s1, *s2;   // sources of this side
+  int nd, sz[3], n[3], a, is_max;
+  size_t plane;
+  double l[3], sum, diff, dt_eps;
+};
+__device__ __forceinline__ size_t face_plane_index(const FaceOp &O, const int *p) {
+  // position of (p) in the ghosted plane of axis a
+  size_t t = 0, mul = 1;
+  for (int d = 0; d < 3; d++) {
+    if (d == O.a || d >= O.nd) continue;
+    t += mul * (size_t)(p[d] + NG - 1);
+    mul *= (size_t)O.sz[d];
+  }
+  return t;
+}
+__global__ void __launch_bounds__(256) k_snapshot_face(const __grid_constant__ FaceOp O) {
+  int ext[3], lo[3];
+  size_t total = 1;
+  for (int d = 0; d < 3; d++) {
+    if (d == O.a || d >= O.nd) { ext[d] = 1; lo[d] = 1; }
+    else { ext[d] = O.sz[d]; lo[d] = 1 - NG; }
+    total *= (size_t)ext[d];
+  }
+  size_t str[3] = {1, (size_t)O.sz[0], (size_t)O.sz[0] * O.sz[1]};
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int p[3];
+    size_t r = t;
+    for (int d = 0; d < 3; d++) { p[d] = lo[d] + (int)(r % ext[d]); r /= ext[d]; }
+    const size_t tp = face_plane_index(O, p);
+    for (int side = 0; side < 2; side++) {
+      p[O.a] = side == 0 ? 1 : O.n[O.a];
+      const size_t o = fofs(O.sz, O.nd, p[0], p[1], p[2]);
+      for (int q = 0; q < 6; q++) {
+        const bool avg = q < 3 ? (q == O.a) : (q - 3 != O.a);
+        const double val = avg ? 0.5 * (O.f[q][o] + O.f[q][o - str[O.a]]) : O.f[q][o];
+        O.snap[((size_t)side * 6 + q) * O.plane + tp] = val;
+      }
+    }
+  }
+}
+template <int ND>
+__global__ void __launch_bounds__(256) k_outflow_face(const __grid_constant__ FaceOp O) {
+  const double c = EPB_C;
+  const int a = O.a, b = (a + 1) % 3, cc = (a + 2) % 3;
+  int ext[3];
+  size_t total = 1;
+  for (int d = 0; d < 3; d++) { ext[d] = (d == a || d >= ND) ? 1 : O.n[d] + 1; total *= (size_t)ext[d]; }
+  const ptrdiff_t str[3] = {1, (ptrdiff_t)O.sz[0], (ptrdiff_t)O.sz[0] * O.sz[1]};
+  double *Ba = O.f[3 + a], *Bb = O.f[3 + b], *Bc = O.f[3 + cc];
+  const double *Eb = O.f[b], *Ec = O.f[cc], *Jb = O.f[6 + b], *Jc = O.f[6 + cc];
+  const double *snap = O.snap + (size_t)O.is_max * 6 * O.plane;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int p[3];
+    size_t r = t;
+    for (int d = 0; d < 3; d++) { p[d] = (d == a || d >= ND) ? 1 : (int)(r % ext[d]); if (!(d == a || d >= ND)) r /= ext[d]; }
+    const size_t tp = face_plane_index(O, p);
+#define SN(q) snap[(size_t)(q) * O.plane + tp]
+    const double src1 = O.s1[t], src2 = O.s2[t];
+    p[a] = O.is_max ? O.n[a] : 1;  // laserpos
+    const ptrdiff_t o = (ptrdiff_t)fofs(O.sz, ND, p[0], p[1], p[2]);
+    const ptrdiff_t sa = str[a];
+    if (!O.is_max) {
+      Ba[o - sa] = SN(3 + a);
+      double tc = 4.0 * src1 + 2.0 * (SN(b) + c * SN(3 + cc)) - 2.0 * Eb[o];
+      if (cc < ND) tc = tc - O.l[cc] * (Ba[o] - Ba[o - str[cc]]);
+      tc = tc + O.dt_eps * Jb[o] + O.diff * Bc[o];
+      double tb = -4.0 * src2 - 2.0 * (SN(cc) - c * SN(3 + b)) + 2.0 * Ec[o];
+      if (b < ND) tb = tb - O.l[b] * (Ba[o] - Ba[o - str[b]]);
+      tb = tb - O.dt_eps * Jc[o] + O.diff * Bb[o];
+      Bc[o - sa] = O.sum * tc;
+      Bb[o - sa] = O.sum * tb;
+    } else {
+      Ba[o + sa] = SN(3 + a);
+      double tc = -4.0 * src1 - 2.0 * (SN(b) - c * SN(3 + cc)) + 2.0 * Eb[o];
+      if (cc < ND) tc = tc + O.l[cc] * (Ba[o] - Ba[o - str[cc]]);
+      tc = tc - O.dt_eps * Jb[o] + O.diff * Bc[o - sa];
+      double tb = 4.0 * src2 + 2.0 * (SN(cc) + c * SN(3 + b)) - 2.0 * Ec[o];
+      if (b < ND) tb = tb + O.l[b] * (Ba[o] - Ba[o - str[b]]);
+      tb = tb + O.dt_eps * Jc[o] + O.diff * Bb[o - sa];
+      Bc[o] = O.sum * tc;
+      Bb[o] = O.sum * tb;
+    }
+#undef SN
+  }
+}
+
 // calc_ppc (io/calc_df.F90:761-808): cell = FLOOR((pos - x_grid_min_local)/dx + 0.5) + 1
 struct CountOp {
   const double *x[3];
@@ -672,6 +766,38 @@ int outflow_x(epb_handle *h, int side, double dt) {
   return EPB_OK;
 }
 
+static void fill_face_op(epb_handle *h, int a, FaceOp &O) {
+  const epb_config &c = h->cfg;
+  for (int q = 0; q < 9; q++) O.f[q] = h->f(q);
+  O.snap = h->snapA[a];
+  O.nd = c.ndims;
+  for (int d = 0; d < 3; d++) { O.sz[d] = h->sz[d]; O.n[d] = c.n[d]; }
+  O.a = a;
+  O.plane = h->planeA[a];
+}
+int outflow_face(epb_handle *h, int boundary, double dt) {
+  const epb_config &c = h->cfg;
+  const int a = boundary / 2, side = boundary & 1;
+  FaceOp O;
+  fill_face_op(h, a, O);
+  O.is_max = side;
+  O.s1 = h->srcA[a] + ((size_t)side * 2 + 0) * h->planeA[a];
+  O.s2 = h->srcA[a] + ((size_t)side * 2 + 1) * h->planeA[a];
+  const double cc = EPB_C;
+  const double dtc2 = dt * (cc * cc);
+  for (int d = 0; d < 3; d++) O.l[d] = d < c.ndims ? dtc2 / c.dx[d] : 0.0;
+  O.sum = 1.0 / (O.l[a] + cc);
+  O.diff = O.l[a] - cc;
+  O.dt_eps = dt / EPB_EPS0;
+  size_t total = 1;
+  for (int d = 0; d < c.ndims; d++) if (d != a) total *= (size_t)(c.n[d] + 1);
+  const int nb = nblocks(total);
+  if (c.ndims == 2) k_outflow_face<2><<<nb, 256, 0, h->stream>>>(O);
+  else k_outflow_face<3><<<nb, 256, 0, h->stream>>>(O);
+  h->launches++;
+  return EPB_OK;
+}
+
 // bfield_final_bcs (boundary.F90:911-944)
 int bfield_final_bcs(epb_handle *h, double dt) {
   int rc = field_bcs3(h, EPB_BX, false);
@@ -679,6 +805,10 @@ int bfield_final_bcs(epb_handle *h, double dt) {
   for (int side = 0; side < 2; side++) {
     int b = h->cfg.bc_field[side];
     if (h->cfg.is_boundary[side] && (b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW)) outflow_x(h, side, dt);
+  }
+  for (int bd = 2; bd < 2 * h->cfg.ndims; bd++) {
+    int b = h->cfg.bc_field[bd];
+    if (h->cfg.is_boundary[bd] && (b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW)) outflow_face(h, bd, dt);
   }
   return field_bcs3(h, EPB_BX, true);
 }
@@ -837,7 +967,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   for (int i = 0; i < 2 * cfg->ndims; i++) {
     int b = cfg->bc_field[i];
     bool ok = b == EPB_BC_PERIODIC || b == EPB_BC_CLAMP || b == EPB_BC_ZERO_GRADIENT ||
-              ((b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW) && i < 2);
+              b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW;
     if (!ok) return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "field boundary code %d on boundary %d not implemented on the device path", b, i);
   }
   for (int s = 0; s < cfg->n_species; s++) {
@@ -872,6 +1002,15 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   EPB_CUDA(h, cudaMemsetAsync(h->snap, 0, 12 * h->plane * sizeof(double), h->stream));
   EPB_CUDA(h, cudaMalloc(&h->src, 4 * h->plane * sizeof(double)));
   EPB_CUDA(h, cudaMemsetAsync(h->src, 0, 4 * h->plane * sizeof(double), h->stream));
+  for (int a = 1; a < nd; a++) {  // y / z faces
+    size_t pl = 1;
+    for (int d = 0; d < nd; d++) if (d != a) pl *= (size_t)h->sz[d];
+    h->planeA[a] = pl;
+    EPB_CUDA(h, cudaMalloc(&h->snapA[a], 12 * pl * sizeof(double)));
+    EPB_CUDA(h, cudaMemsetAsync(h->snapA[a], 0, 12 * pl * sizeof(double), h->stream));
+    EPB_CUDA(h, cudaMalloc(&h->srcA[a], 4 * pl * sizeof(double)));
+    EPB_CUDA(h, cudaMemsetAsync(h->srcA[a], 0, 4 * pl * sizeof(double), h->stream));
+  }
   epb_fdtd_tma_setup(h);
   epb_make_tiles(h->cfg, h->tg);
   // 0 = library default: the cell-owner kernel wants a fresh order (its sort is cheap), the
@@ -940,6 +1079,7 @@ int epb_destroy(epb_handle *h) {
   cudaStreamSynchronize(h->stream);
   epb_comm_destroy(h);
   cudaFree(h->fields); cudaFree(h->snap); cudaFree(h->src);
+  for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
   cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
@@ -1094,11 +1234,16 @@ int epb_cell_counts(epb_handle *h, int is, int32_t *out) {
 }
 
 int epb_set_laser_source(epb_handle *h, int side, const double *s1, const double *s2) {
-  if (!h || side < 0 || side > 1) return EPB_ERR_ARG;
+  if (!h || side < 0 || side >= 2 * h->cfg.ndims) return EPB_ERR_ARG;
   const epb_config &c = h->cfg;
-  size_t n = (size_t)(c.ndims >= 2 ? c.n[1] + 1 : 1) * (c.ndims >= 3 ? c.n[2] + 1 : 1);
-  EPB_CUDA(h, cudaMemcpyAsync(h->src + ((size_t)side * 2 + 0) * h->plane, s1, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  EPB_CUDA(h, cudaMemcpyAsync(h->src + ((size_t)side * 2 + 1) * h->plane, s2, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int a = side / 2, sd = side & 1;
+  size_t n = 1;
+  for (int d = 0; d < c.ndims; d++) if (d != a) n *= (size_t)(c.n[d] + 1);
+  double *base = a == 0 ? h->src : h->srcA[a];
+  const size_t plane = a == 0 ? h->plane : h->planeA[a];
+  if (!base) return EPB_ERR_ARG;
+  EPB_CUDA(h, cudaMemcpyAsync(base + ((size_t)sd * 2 + 0) * plane, s1, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPB_CUDA(h, cudaMemcpyAsync(base + ((size_t)sd * 2 + 1) * plane, s2, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   // host buffers may be reused by the caller right after return
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   return EPB_OK;
@@ -1116,6 +1261,14 @@ int epb_init_boundaries(epb_handle *h) {
   S.plane = h->plane;
   k_snapshot<<<nblocks(h->plane), 256, 0, h->stream>>>(S);
   h->launches++;
+  for (int a = 1; a < c.ndims; a++) {
+    if (!h->snapA[a]) continue;
+    FaceOp O;
+    fill_face_op(h, a, O);
+    O.is_max = 0; O.s1 = O.s2 = nullptr; O.sum = O.diff = O.dt_eps = 0.0;
+    k_snapshot_face<<<nblocks(h->planeA[a]), 256, 0, h->stream>>>(O);
+    h->launches++;
+  }
   // setup_bc_lists + particle_bcs (epoch2d.F90:144-145): classification of the loaded particles
   // happens inside epb_push's kernel; uploaded particles are expected inside the local domain,
   // which the loaders guarantee (helper.F90:658-659 already ran particle_bcs).

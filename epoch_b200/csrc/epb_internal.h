@@ -111,6 +111,10 @@ struct epb_handle {
   size_t plane = 0;             // (ny+2ng)*(nz+2ng)
   double *snap = nullptr;       // [2 sides][6 fields][plane]
   double *src = nullptr;        // [2 sides][2][plane]
+  // the same for the y and z faces (index 1, 2): planes over the other two ghosted extents
+  size_t planeA[3] = {0, 0, 0};
+  double *snapA[3] = {nullptr, nullptr, nullptr};  // [2 sides][6 fields][planeA]
+  double *srcA[3] = {nullptr, nullptr, nullptr};   // [2 sides][2][planeA]
   TileGeom tg;
   int *cell_count = nullptr;    // nkeys + 1
   int *cell_start = nullptr;    // nkeys + 1

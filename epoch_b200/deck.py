@@ -254,18 +254,22 @@ class Deck:
 
     # -- laser sources (laser.f90:253-269, 338-357) --------------------------
     def laser_sources(self, rank: int, side: int, time: float):
-        """source1/source2 on the local transverse plane (0:ny, 0:nz), y fastest."""
+        """source1/source2 on the local plane of boundary `side` (0 x_min, 1 x_max, 2 y_min, ...): the two
+        transverse axes in axis order, (0:n) each, lower axis fastest.  Profile / phase callables get the
+        two transverse coordinates in that order ((y, z) on an x face, (x, z) on a y face, (x, y) on a z face)."""
         n, g = self.local_extent(rank)
-        ny = n[1] if self.ndims >= 2 else 0
-        nz = n[2] if self.ndims >= 3 else 0
-        jj = np.arange(0, ny + 1)
-        kk = np.arange(0, nz + 1)
-        y = self.x_global(1, jj + g[1] - 1) if self.ndims >= 2 else np.zeros(1)
-        z = self.x_global(2, kk + g[2] - 1) if self.ndims >= 3 else np.zeros(1)
-        Y, Z = np.meshgrid(y, z, indexing="xy")  # shape (nz+1, ny+1)
-        s1 = np.zeros_like(Y)
-        s2 = np.zeros_like(Y)
-        name = "x_min" if side == 0 else "x_max"
+        axis = side // 2
+        tr = [d for d in range(3) if d != axis]
+        coords = []
+        for d in tr:
+            if d < self.ndims:
+                coords.append(self.x_global(d, np.arange(0, n[d] + 1) + g[d] - 1))
+            else:
+                coords.append(np.zeros(1))
+        U, V = np.meshgrid(coords[0], coords[1], indexing="xy")  # shape (n_v+1, n_u+1): u fastest
+        s1 = np.zeros_like(U)
+        s2 = np.zeros_like(U)
+        name = ("x", "y", "z")[axis] + ("_min" if side % 2 == 0 else "_max")
         for l in self.lasers:
             if l.boundary != name:
                 continue
@@ -273,8 +277,8 @@ class Deck:
             if not (time >= l.t_start and time <= t_end):
                 continue
             integral_phase = l.omega * time
-            prof = np.ones_like(Y) if l.profile is None else np.broadcast_to(l.profile(Y, Z), Y.shape)
-            ph = np.zeros_like(Y) if l.phase is None else np.broadcast_to(l.phase(Y, Z), Y.shape)
+            prof = np.ones_like(U) if l.profile is None else np.broadcast_to(l.profile(U, V), U.shape)
+            ph = np.zeros_like(U) if l.phase is None else np.broadcast_to(l.phase(U, V), U.shape)
             t_env = (1.0 if l.t_profile is None else float(l.t_profile(time))) * l.amp
             base = t_env * prof * np.sin(integral_phase + ph)
             s1 = s1 + base * math.cos(l.pol_angle)
@@ -282,7 +286,7 @@ class Deck:
         return np.ascontiguousarray(s1.ravel()), np.ascontiguousarray(s2.ravel())
 
     def has_boundary_source(self, side: int) -> bool:
-        return self.bc_field[side] in ("simple_laser", "simple_outflow", "open")
+        return side < 2 * self.ndims and self.bc_field[side] in ("simple_laser", "simple_outflow", "open")
 
 
 class DumpClock:
@@ -326,7 +330,7 @@ def run(deck: Deck, backend, local_ranks: Sequence[int], on_dump: Optional[Calla
 
     def push_sources(t):
         for lr, rank in enumerate(local_ranks):
-            for side in (0, 1):
+            for side in range(2 * deck.ndims):
                 if deck.has_boundary_source(side):
                     s1, s2 = deck.laser_sources(rank, side, t)
                     backend.set_laser_source(lr, side, s1, s2)

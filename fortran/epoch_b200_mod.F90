@@ -378,12 +378,21 @@ CONTAINS
     REAL(num), ALLOCATABLE :: source1(:), source2(:)
     TYPE(laser_block), POINTER :: current
     REAL(num) :: t_env, base
-    INTEGER :: side, i
+    INTEGER :: side, i, nt
+    LOGICAL :: on_edge
 
-    ALLOCATE(source1(0:ny), source2(0:ny))
-    DO side = 0, 1
-      IF (side == 0 .AND. .NOT. x_min_boundary) CYCLE
-      IF (side == 1 .AND. .NOT. x_max_boundary) CYCLE
+    ! side = c_bd_x_min - 1 .. c_bd_y_max - 1 (epoch2d): the transverse extent is ny on the x
+    ! faces and nx on the y faces (laser.f90:338-357, :479-500)
+    DO side = 0, 3
+      SELECT CASE (side)
+        CASE (0); on_edge = x_min_boundary; nt = ny
+        CASE (1); on_edge = x_max_boundary; nt = ny
+        CASE (2); on_edge = y_min_boundary; nt = nx
+        CASE (3); on_edge = y_max_boundary; nt = nx
+      END SELECT
+      IF (.NOT. on_edge) CYCLE
+      IF (.NOT. (add_laser(side + 1) .OR. bc_field(side + 1) == c_bc_simple_outflow)) CYCLE
+      ALLOCATE(source1(0:nt), source2(0:nt))
       source1 = 0.0_num
       source2 = 0.0_num
       IF (add_laser(side + 1)) THEN
@@ -394,7 +403,7 @@ CONTAINS
             IF (current%use_phase_function) CALL laser_update_phase(current)
             IF (current%use_profile_function) CALL laser_update_profile(current)
             t_env = laser_time_profile(current) * current%amp
-            DO i = 0, ny
+            DO i = 0, nt
               base = t_env * current%profile(i) &
                   * SIN(current%current_integral_phase + current%phase(i))
               source1(i) = source1(i) + base * COS(current%pol_angle)
@@ -405,8 +414,8 @@ CONTAINS
         END DO
       END IF
       CALL b200_check(epb_set_laser_source(b200, side, source1, source2))
+      DEALLOCATE(source1, source2)
     END DO
-    DEALLOCATE(source1, source2)
 
   END SUBROUTINE b200_push_laser_sources
 

@@ -135,9 +135,11 @@ int epb_cell_counts(epb_handle *h, int ispecies, int32_t *out);
 int epb_field_device_ptr(epb_handle *h, int field, void **dptr);
 
 /* -- laser / outflow boundary sources -------------------------------------------
- * side 0 = x_min, 1 = x_max.  source1/source2 are laser.f90:347-352's arrays on the
- * local plane (0:ny, 0:nz), y fastest, evaluated by the host each step (the time
- * profile is a deck expression, laser.f90:159-176). */
+ * side = c_bd_x_min .. c_bd_z_max - 1: 0 x_min, 1 x_max, 2 y_min, 3 y_max, 4 z_min, 5 z_max.
+ * source1/source2 are the arrays of laser.f90:347-352 (x faces), :479-500 (y faces), epoch3d
+ * laser.f90 (z faces) on the local plane of that face: the two transverse axes in axis order,
+ * (0:n) each, lower axis fastest; evaluated by the host each step (the time profile is a deck
+ * expression, laser.f90:159-176). */
 int epb_set_laser_source(epb_handle *h, int side, const double *source1, const double *source2);
 
 /* -- the hot path ---------------------------------------------------------------- */

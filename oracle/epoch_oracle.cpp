@@ -178,6 +178,9 @@ struct Rank {
   Arr f[NFIELD];
   // setup.F90:391-447 boundary snapshots on x_min / x_max (index by field 0..5)
   Arr snap_min[6], snap_max[6];
+  // the same for the y and z faces: snapA[axis][side][field], srcA[axis][side][source1|source2]
+  // (planes with a unit extent along the axis; axis 0 keeps the arrays above)
+  Arr snapA[3][2][6], srcA[3][2][2];
   Arr src1[2], src2[2];  // laser sources on x_min / x_max, set by the host each step
   std::vector<std::vector<Particle>> part;       // per species
   std::vector<std::vector<int64_t>> bnd_cand;    // boundary candidate indices per species
@@ -334,6 +337,20 @@ void setup_world(World &w) {
       for (Arr *q : {&R.src1[s], &R.src2[s]}) {
         *q = R.snap_min[0];
         std::fill(q->v.begin(), q->v.end(), 0.0);
+      }
+    for (int a = 1; a < nd; a++)
+      for (int sd = 0; sd < 2; sd++) {
+        auto shape = [&](Arr &q) {
+          size_t tot = 1;
+          for (int d = 0; d < 3; d++) {
+            if (d == a || d >= nd) { q.lo[d] = 1; q.sz[d] = 1; }
+            else { q.lo[d] = 1 - NG; q.sz[d] = R.n[d] + 2 * NG; }
+            tot *= (size_t)q.sz[d];
+          }
+          q.v.assign(tot, 0.0);
+        };
+        for (int f = 0; f < 6; f++) shape(R.snapA[a][sd][f]);
+        for (int q = 0; q < 2; q++) shape(R.srcA[a][sd][q]);
       }
     R.part.resize(w.sp.size());
     R.bnd_cand.resize(w.sp.size());
@@ -721,6 +738,97 @@ void setup_field_boundaries(World &w) {
           hi(1, j, k) = avg ? 0.5 * (a(nx1, j, k) + a(nx1 - 1, j, k)) : a(nx1, j, k);
         }
     }
+    // y and z faces (setup.F90:430-447; epoch3d setup.F90:431-500): components staggered along the
+    // face normal (E normal, B transverse) are averaged across the boundary
+    for (int ax = 1; ax < w.nd; ax++)
+      for (int sd = 0; sd < 2; sd++)
+        for (int f = 0; f < 6; f++) {
+          const Arr &a = R.f[f];
+          Arr &q = R.snapA[ax][sd][f];
+          const bool avg = f < 3 ? (f == ax) : (f - 3 != ax);
+          const int n0 = sd == 0 ? 1 : R.n[ax];
+          int e[3] = {0, 0, 0};
+          e[ax] = 1;
+          for (int k = q.lo[2]; k < q.lo[2] + q.sz[2]; k++)
+            for (int j = q.lo[1]; j < q.lo[1] + q.sz[1]; j++)
+              for (int i = q.lo[0]; i < q.lo[0] + q.sz[0]; i++) {
+                int p[3] = {i, j, k};
+                p[ax] = n0;
+                const double v0 = a(p[0], p[1], p[2]);
+                q(i, j, k) = avg ? 0.5 * (v0 + a(p[0] - e[0], p[1] - e[1], p[2] - e[2])) : v0;
+              }
+        }
+  }
+}
+
+// outflow_bcs_{y,z}_{min,max} (laser.f90:462-610; epoch3d laser.f90:510-830): the x-face formulas under
+// the cyclic permutation x -> y -> z of axes and components (a = normal, b = a+1, cc = a+2).
+template <int ND>
+void outflow_bcs_axis(World &w, int a, bool is_max, double dt) {
+  const int b = (a + 1) % 3, cc = (a + 2) % 3;
+  const double dtc2 = dt * (c * c);
+  double l[3];
+  for (int d = 0; d < 3; d++) l[d] = d < ND ? dtc2 / w.d[d] : 0.0;
+  const double sum = 1.0 / (l[a] + c);
+  const double diff = l[a] - c;
+  const double dt_eps = dt / epsilon0;
+  for (Rank &R : w.r) {
+    if (!R.is_bnd[2 * a + (is_max ? 1 : 0)]) continue;
+    Arr &Ba = R.f[BX + a], &Bb = R.f[BX + b], &Bc = R.f[BX + cc];
+    const Arr &Eb = R.f[EX + b], &Ec = R.f[EX + cc], &Jb = R.f[JX + b], &Jc = R.f[JX + cc];
+    const Arr *snap = R.snapA[a][is_max ? 1 : 0];
+    const Arr &s1 = R.srcA[a][is_max ? 1 : 0][0], &s2 = R.srcA[a][is_max ? 1 : 0][1];
+    int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
+    for (int d = 0; d < ND; d++) if (d != a) { lo[d] = 0; hi[d] = R.n[d]; }
+    const int lp = is_max ? R.n[a] : 1;
+    int ea[3] = {0, 0, 0}, eb[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
+    ea[a] = 1; eb[b] = 1; ec[cc] = 1;
+    auto at = [&](const Arr &A, const int *p, const int *e, int m) {
+      return A(p[0] + m * e[0], p[1] + m * e[1], p[2] + m * e[2]);
+    };
+    auto pl = [&](const Arr &A, const int *p) {  // plane array: unit extent along a
+      int q[3] = {p[0], p[1], p[2]};
+      q[a] = 1;
+      return A(q[0], q[1], q[2]);
+    };
+    // the normal component first (array assignment in the reference), then the two transverse ones;
+    // their right-hand sides only read the laserpos plane of B_a, never the one just written
+    for (int pass = 0; pass < 3; pass++)
+      for (int k = lo[2]; k <= hi[2]; k++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+          for (int i = lo[0]; i <= hi[0]; i++) {
+            int p[3] = {i, j, k};
+            p[a] = lp;
+            int pw[3] = {p[0], p[1], p[2]};       // the plane that is written
+            pw[a] = is_max ? lp + 1 : lp - 1;
+            if (pass == 0) {
+              Ba(pw[0], pw[1], pw[2]) = pl(snap[BX + a], p);
+            } else if (pass == 1) {
+              if (!is_max) {
+                double t = 4.0 * pl(s1, p) + 2.0 * (pl(snap[EX + b], p) + c * pl(snap[BX + cc], p)) - 2.0 * at(Eb, p, ea, 0);
+                if (cc < ND) t = t - l[cc] * (at(Ba, p, ec, 0) - at(Ba, p, ec, -1));
+                t = t + dt_eps * at(Jb, p, ea, 0) + diff * at(Bc, p, ea, 0);
+                Bc(pw[0], pw[1], pw[2]) = sum * t;
+              } else {
+                double t = -4.0 * pl(s1, p) - 2.0 * (pl(snap[EX + b], p) - c * pl(snap[BX + cc], p)) + 2.0 * at(Eb, p, ea, 0);
+                if (cc < ND) t = t + l[cc] * (at(Ba, p, ec, 0) - at(Ba, p, ec, -1));
+                t = t - dt_eps * at(Jb, p, ea, 0) + diff * at(Bc, p, ea, -1);
+                Bc(p[0], p[1], p[2]) = sum * t;
+              }
+            } else {
+              if (!is_max) {
+                double t = -4.0 * pl(s2, p) - 2.0 * (pl(snap[EX + cc], p) - c * pl(snap[BX + b], p)) + 2.0 * at(Ec, p, ea, 0);
+                if (b < ND) t = t - l[b] * (at(Ba, p, eb, 0) - at(Ba, p, eb, -1));
+                t = t - dt_eps * at(Jc, p, ea, 0) + diff * at(Bb, p, ea, 0);
+                Bb(pw[0], pw[1], pw[2]) = sum * t;
+              } else {
+                double t = 4.0 * pl(s2, p) + 2.0 * (pl(snap[EX + cc], p) + c * pl(snap[BX + b], p)) - 2.0 * at(Ec, p, ea, 0);
+                if (b < ND) t = t + l[b] * (at(Ba, p, eb, 0) - at(Ba, p, eb, -1));
+                t = t + dt_eps * at(Jc, p, ea, 0) + diff * at(Bb, p, ea, -1);
+                Bb(p[0], p[1], p[2]) = sum * t;
+              }
+            }
+          }
   }
 }
 
@@ -731,6 +839,10 @@ void bfield_final_bcs(World &w, double dt) {
   for (int s = 0; s < 2; s++) {
     int b = w.bc_field[s];
     if (b == c_bc_simple_laser || b == c_bc_simple_outflow) outflow_bcs_x<ND>(w, s == 1, dt);
+  }
+  for (int s = 2; s < 2 * ND; s++) {
+    int b = w.bc_field[s];
+    if (b == c_bc_simple_laser || b == c_bc_simple_outflow) outflow_bcs_axis<ND>(w, s / 2, (s & 1) == 1, dt);
   }
   bfield_bcs(w, true);
 }
@@ -1520,18 +1632,25 @@ void orc_set_particles(void *h, int rk, int is, int64_t n, const double *in) {
     pl[i].w = o[w.nd + 3];
   }
 }
-// src arrays are local planes (0:ny, 0:nz), x fastest = iy
+// src arrays are local planes over the two transverse axes (0:n), lower axis fastest; side = 2*axis + is_max
 void orc_set_laser_source(void *h, int rk, int side, const double *s1, const double *s2) {
   World &w = *(World *)h;
   Rank &R = w.r[rk];
-  const int ny = w.nd >= 2 ? R.n[1] : 0, nz = w.nd >= 3 ? R.n[2] : 0;
+  const int a = side / 2, sd = side & 1;
+  int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
+  for (int d = 0; d < w.nd; d++) if (d != a) { lo[d] = 0; hi[d] = R.n[d]; }
   size_t n = 0;
-  for (int k = 0; k <= nz; k++)
-    for (int j = 0; j <= ny; j++, n++) {
-      int jj = w.nd >= 2 ? j : 1, kk = w.nd >= 3 ? k : 1;
-      R.src1[side](1, jj, kk) = s1[n];
-      R.src2[side](1, jj, kk) = s2[n];
-    }
+  for (int k = lo[2]; k <= hi[2]; k++)
+    for (int j = lo[1]; j <= hi[1]; j++)
+      for (int i = lo[0]; i <= hi[0]; i++, n++) {
+        if (a == 0) { R.src1[sd](1, j, k) = s1[n]; R.src2[sd](1, j, k) = s2[n]; }
+        else {
+          int q[3] = {i, j, k};
+          q[a] = 1;
+          R.srcA[a][sd][0](q[0], q[1], q[2]) = s1[n];
+          R.srcA[a][sd][1](q[0], q[1], q[2]) = s2[n];
+        }
+      }
 }
 void orc_auto_load(void *h) { auto_load(*(World *)h); }
 void orc_init(void *h) {

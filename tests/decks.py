@@ -30,6 +30,19 @@ def laser2d(nproc=(1, 1, 1), n=500):
                   t_end=50 * D.femto, dt_snapshot=25 * D.femto, nproc=nproc)
 
 
+def laser2d_y(nproc=(1, 1, 1), n=64, side="y_min"):
+    """The 2D laser deck with the laser on a y face (outflow_bcs_y_min/max, laser.f90:462-610), oblique
+    in x, circular-ish polarisation so that both source arrays are exercised."""
+    lam = lambda0 * math.cos(theta)
+    las = D.Laser(side, D.Laser.amp_from_intensity_w_cm2(1.0e15), 2 * D.pi * D.c / lam, pol_angle=0.6,
+                  phase=lambda x, z: -2.0 * D.pi * x * math.tan(theta) / lambda0,
+                  profile=lambda x, z: D.gauss(x, 0, 4 * D.micron))
+    ybc = ["simple_laser", "open"] if side == "y_min" else ["open", "simple_laser"]
+    return D.Deck(2, [n, n + 8], [-10 * D.micron] * 2, [10 * D.micron] * 2,
+                  ["periodic", "periodic"] + ybc, lasers=[las],
+                  t_end=50 * D.femto, dt_snapshot=25 * D.femto, nproc=nproc)
+
+
 def laser3d(nproc=(1, 1, 1), n=140):
     """epoch3d/tests/laser/input.deck"""
     lam = lambda0 * math.cos(theta)
@@ -38,6 +51,25 @@ def laser3d(nproc=(1, 1, 1), n=140):
                   profile=lambda y, z: D.gauss(np.sqrt(y * y + z * z), 0, 4 * D.micron))
     return D.Deck(3, [n] * 3, [-10 * D.micron] * 3, [10 * D.micron] * 3,
                   ["simple_laser", "open"] + ["periodic"] * 4, lasers=[las],
+                  t_end=50 * D.femto, dt_snapshot=25 * D.femto, nproc=nproc)
+
+
+def laser3d_face(face, nproc=(1, 1, 1), n=140):
+    """epoch3d/tests/laser/input.deck with the axes cyclically permuted so that the laser enters through
+    y_min ('y': old (x, y, z) -> new (y, z, x)) or z_min ('z': old (x, y, z) -> new (z, x, y)).  The
+    physics is identical, so the reference's golden sum(Ex^2) must reappear as sum(Ey^2) resp. sum(Ez^2):
+    this pins the y- and z-face laser / outflow boundaries on the reference's own numbers."""
+    lam = lambda0 * math.cos(theta)
+    prof = lambda u, v: D.gauss(np.sqrt(u * u + v * v), 0, 4 * D.micron)
+    if face == "y":    # callables get (x, z) = (old z, old y)
+        las = D.Laser("y_min", D.Laser.amp_from_intensity_w_cm2(1.0e15), 2 * D.pi * D.c / lam,
+                      phase=lambda u, v: -2.0 * D.pi * v * math.tan(theta) / lambda0, profile=prof)
+        bcs = ["periodic"] * 2 + ["simple_laser", "open"] + ["periodic"] * 2
+    else:              # callables get (x, y) = (old y, old z)
+        las = D.Laser("z_min", D.Laser.amp_from_intensity_w_cm2(1.0e15), 2 * D.pi * D.c / lam,
+                      phase=lambda u, v: -2.0 * D.pi * u * math.tan(theta) / lambda0, profile=prof)
+        bcs = ["periodic"] * 4 + ["simple_laser", "open"]
+    return D.Deck(3, [n] * 3, [-10 * D.micron] * 3, [10 * D.micron] * 3, bcs, lasers=[las],
                   t_end=50 * D.femto, dt_snapshot=25 * D.femto, nproc=nproc)
 
 

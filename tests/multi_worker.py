@@ -41,6 +41,8 @@ def make_deck(name, world):
         dk.field_order = 4
         dk.smooth_currents, dk.smooth_iterations, dk.smooth_compensation, dk.smooth_strides = True, 2, True, (1, 2)
         return dk, 8, 1e-12
+    if name == "laser2d_y":   # laser on y_min, decomposed along y and x
+        return decks.laser2d_y(nproc=(1, world, 1) if world < 4 else (2, world // 2, 1)), 40, 1e-12
     if name == "laser2d":
         return decks.laser2d(nproc=(world, 1, 1), n=64), 40, 1e-12
     raise KeyError(name)

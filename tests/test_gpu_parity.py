@@ -56,7 +56,9 @@ def test_laser3d_golden_gpu():
     assert np.isclose(res[2], 7.78759e+25)
 
 
-@pytest.mark.parametrize("mk", [decks.laser1d, lambda: decks.laser2d(n=64), lambda: decks.laser3d(n=24)])
+@pytest.mark.parametrize("mk", [decks.laser1d, lambda: decks.laser2d(n=64), lambda: decks.laser3d(n=24),
+                                lambda: decks.laser2d_y(), lambda: decks.laser2d_y(side="y_max"),
+                                lambda: decks.laser3d_face("y", n=24), lambda: decks.laser3d_face("z", n=24)])
 def test_fields_match_oracle(mk):
     dk = mk()
     o, sim = make_pair(dk, load=False)

@@ -62,6 +62,14 @@ def test_laser3d_golden_first_dump():
     assert np.isclose(res[1], 3.89491e+25)
 
 
+@pytest.mark.parametrize("face,fld", [("y", "ey"), ("z", "ez")])
+def test_laser3d_golden_on_other_faces(face, fld):
+    """The same golden value with the laser on y_min / z_min (axes permuted): pins outflow_bcs_{y,z}_*."""
+    res = _run(decks.laser3d_face(face), fld, max_dumps=2)
+    assert res[0] == 0.0
+    assert np.isclose(res[1], 3.89491e+25)
+
+
 @pytest.mark.slow
 def test_laser3d_golden_full():
     res = _run(decks.laser3d(nproc=(2, 2, 2)), "ex")
