@@ -390,10 +390,35 @@ __device__ __forceinline__ void smem_add(double *addr, double v) {
   atomicAdd(addr, v);
 }
 
+
+// Performance build only: reciprocal square root and reciprocal of arguments that are known to
+// be >= 1 (gamma^2 = u^2 + 1, 1 + tau^2), so the special-case paths of rsqrt() / the IEEE divide
+// (denormals, infinities, the out-of-line slow path) are dead weight.  MUFU seed (about 2^-22
+// relative error) + two Newton steps: within 1-2 ulp, like rsqrt().
+#ifdef EPB_FAST_MATH
+__device__ __forceinline__ double rsqrt_ge1(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double h = 0.5 * s;
+  y = y * (1.5 - h * y * y);
+  y = y * (1.5 - h * y * y);
+  return y;
+}
+__device__ __forceinline__ double rcp_ge1(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+#endif
+
 // 1/sqrt(s) and friends.  The parity build keeps the reference's sqrt + divide sequence.
 __device__ __forceinline__ void gamma_root(double s, double num, double &root) {
 #ifdef EPB_FAST_MATH
-  root = num * rsqrt(s);
+  root = num * rsqrt_ge1(s);
 #else
   root = num / sqrt(s);
 #endif
@@ -687,7 +712,11 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
         const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
         const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+#ifdef EPB_FAST_MATH
+        const double tau = rcp_ge1(1.0 + taux2 + tauy2 + tauz2);
+#else
         const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+#endif
         const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
                             2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
         const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
@@ -699,7 +728,7 @@ __global__ void __launch_bounds__(PUSH2D_THREADS, 2) push_tiled_2d(const __grid_
         part_uz = uzp + cmratio * ez_part;
         const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
 #ifdef EPB_FAST_MATH
-        const double igamma = rsqrt(part_u2 + 1.0);
+        const double igamma = rsqrt_ge1(part_u2 + 1.0);
 #else
         const double igamma = 1.0 / sqrt(part_u2 + 1.0);
 #endif
@@ -1071,7 +1100,11 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
         gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
         const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
         const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+#ifdef EPB_FAST_MATH
+        const double tau = rcp_ge1(1.0 + taux2 + tauy2 + tauz2);
+#else
         const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+#endif
         const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
                             2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
         const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
@@ -1083,7 +1116,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
         part_uz = uzp + cmratio * ez_part;
         const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
 #ifdef EPB_FAST_MATH
-        const double igamma = rsqrt(part_u2 + 1.0);
+        const double igamma = rsqrt_ge1(part_u2 + 1.0);
 #else
         const double igamma = 1.0 / sqrt(part_u2 + 1.0);
 #endif
@@ -1463,7 +1496,11 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
       gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
       const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
       const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+#ifdef EPB_FAST_MATH
+      const double tau = rcp_ge1(1.0 + taux2 + tauy2 + tauz2);
+#else
       const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+#endif
       const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
                           2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
       const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
