@@ -34,7 +34,7 @@ struct FieldParams {
   // derivative with coefficients c1..c3 * cx (fields.f90:128-204); ext: extended 2D B stencil
   int nt, ext;
   double kx[3], ky[3], kz[3];
-  double alphax, alphay, betaxy, betayx, deltax, deltay;
+  double alpha[3], beta[6], gamma[3], delta[3];  // beta[2a + k]: other axes of a, lower first
 };
 
 __device__ __forceinline__ size_t fofs(const int *sz, int nd, int i, int j, int k) {
@@ -547,21 +547,35 @@ __global__ void __launch_bounds__(256) k_update_b_gen(const __grid_constant__ Fi
     double *bx = F.f[3], *by = F.f[4], *bz = F.f[5];
     // forward difference k along stride s: f(i+k+1) - f(i-k)
     auto df = [&](const double *f, ptrdiff_t s, int k) { return f[o + (k + 1) * s] - f[o - k * s]; };
-    if (ND == 2 && F.ext) {
-      // fields.f90:441-465
-      auto ddx = [&](const double *f) {
-        return F.alphax * (f[o + sx] - f[o]) +
-               F.betaxy * (f[o + sx + sy] - f[o + sy] + f[o + sx - sy] - f[o - sy]) +
-               F.deltax * (f[o + 2 * sx] - f[o - sx]);
+    if (F.ext) {
+      // fields.f90:441-465, epoch3d fields.f90:655-730, epoch1d fields.f90:304-312: derivative along
+      // axis a = alpha + the two betas (lower other axis first; +1 then -1) + gamma (3D; first other
+      // axis + then -, second other axis - then +) + delta, added in that order
+      auto dd = [&](const double *f, int a) {
+        const ptrdiff_t sa = a == 0 ? sx : a == 1 ? sy : szz;
+        double v = F.alpha[a] * (f[o + sa] - f[o]);
+        const int b0 = a == 0 ? 1 : 0, b1 = a == 2 ? 1 : 2;
+        const ptrdiff_t s0 = b0 == 0 ? sx : sy, s1 = b1 == 1 ? sy : szz;
+        if (b0 < ND) v = v + F.beta[2 * a] * (f[o + sa + s0] - f[o + s0] + f[o + sa - s0] - f[o - s0]);
+        if (b1 < ND) v = v + F.beta[2 * a + 1] * (f[o + sa + s1] - f[o + s1] + f[o + sa - s1] - f[o - s1]);
+        if (ND == 3)
+          v = v + F.gamma[a] * (f[o + sa + s0 - s1] - f[o + s0 - s1] + f[o + sa - s0 - s1] - f[o - s0 - s1] +
+                                f[o + sa + s0 + s1] - f[o + s0 + s1] + f[o + sa - s0 + s1] - f[o - s0 + s1]);
+        v = v + F.delta[a] * (f[o + 2 * sa] - f[o - sa]);
+        return v;
       };
-      auto ddy = [&](const double *f) {
-        return F.alphay * (f[o + sy] - f[o]) +
-               F.betayx * (f[o + sx + sy] - f[o + sx] + f[o - sx + sy] - f[o - sx]) +
-               F.deltay * (f[o + 2 * sy] - f[o - sy]);
-      };
-      bx[o] = bx[o] - F.cy * ddy(ez);
-      by[o] = by[o] + F.cx * ddx(ez);
-      bz[o] = bz[o] - F.cx * ddx(ey) + F.cy * ddy(ex);
+      if (ND == 1) {
+        by[o] = by[o] + F.cx * dd(ez, 0);
+        bz[o] = bz[o] - F.cx * dd(ey, 0);
+      } else if (ND == 2) {
+        bx[o] = bx[o] - F.cy * dd(ez, 1);
+        by[o] = by[o] + F.cx * dd(ez, 0);
+        bz[o] = bz[o] - F.cx * dd(ey, 0) + F.cy * dd(ex, 1);
+      } else {
+        bx[o] = bx[o] - F.cy * dd(ez, 1) + F.cz * dd(ey, 2);
+        by[o] = by[o] - F.cz * dd(ex, 2) + F.cx * dd(ez, 0);
+        bz[o] = bz[o] - F.cx * dd(ey, 0) + F.cy * dd(ex, 1);
+      }
       continue;
     }
     double v;
@@ -630,12 +644,12 @@ static bool general_solver(const epb_handle *h, FieldParams &F) {
   const epb_config &c = h->cfg;
   const int order = c.field_order ? c.field_order : 2;
   F.nt = order / 2;
-  F.ext = (c.ndims == 2 && c.maxwell_solver != 0) ? 1 : 0;
+  F.ext = c.maxwell_solver != 0 ? 1 : 0;
   fd_coeffs(order, F.cx, F.kx);
   fd_coeffs(order, F.cy, F.ky);
   fd_coeffs(order, F.cz, F.kz);
-  F.alphax = c.stencil[0]; F.alphay = c.stencil[1]; F.betaxy = c.stencil[2];
-  F.betayx = c.stencil[3]; F.deltax = c.stencil[4]; F.deltay = c.stencil[5];
+  for (int q = 0; q < 3; q++) { F.alpha[q] = c.stencil[q]; F.gamma[q] = c.stencil[9 + q]; F.delta[q] = c.stencil[12 + q]; }
+  for (int q = 0; q < 6; q++) F.beta[q] = c.stencil[3 + q];
   return order != 2 || F.ext;
 }
 
@@ -958,9 +972,9 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     for (int q = 0; q < 4; q++)
       if (((cfg->smooth_strides >> (4 * q)) & 15) > NG)
         return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "smoothing stride > %d ghost cells", NG);
-    if (cfg->maxwell_solver != 0 && (cfg->ndims != 2 || (fo != 0 && fo != 2)))
+    if (cfg->maxwell_solver != 0 && fo != 0 && fo != 2)
       return epb_fail(nullptr, EPB_ERR_UNSUPPORTED,
-                      "extended Maxwell stencils (maxwell_solver %d) are implemented for epoch2d, field_order 2", cfg->maxwell_solver);
+                      "extended Maxwell stencils (maxwell_solver %d) exist for field_order 2 only", cfg->maxwell_solver);
   }
   for (int d = 0; d < cfg->ndims; d++)
     if (cfg->n[d] < NG) return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "local extent %d < ng", cfg->n[d]);

@@ -163,8 +163,12 @@ class Deck:
             # cfl is a function of field_order (fields.f90:38-44)
             cfl = {2: 1.0, 4: 6.0 / 7.0, 6: 120.0 / 149.0}[self.field_order]
             dt = cfl * solver
+        elif self.ndims == 3 and self.maxwell_solver in ("lehe_x", "lehe_y", "lehe_z"):
+            a = {"lehe_x": 0, "lehe_y": 1, "lehe_z": 2}[self.maxwell_solver]   # epoch3d setup.F90:707-715
+            o1, o2 = [d[i] for i in range(3) if i != a]
+            dt = min(d[a], o1 * o2 / math.sqrt(o1 ** 2 + o2 ** 2)) / c
         else:
-            dt = min(d) / c        # setup.F90:645-649 (Lehe, Pukhov)
+            dt = min(d) / c        # setup.F90:645-649 (Lehe, Pukhov), epoch3d :717-721 (Cowan), epoch1d :579-581
         if self.any_open():
             dt = min(dt, solver)
         if self.maxwell_solver == "custom":
@@ -178,41 +182,81 @@ class Deck:
         return self.dt_multiplier * dt
 
     def maxwell_solver_code(self) -> int:
-        return {"custom": -1, "yee": 0, "lehe_x": 2, "lehe_y": 3, "pukhov": 6}[self.maxwell_solver]  # constants.F90:173-180
+        return {"custom": -1, "yee": 0, "lehe_x": 2, "lehe_y": 3, "lehe_z": 4, "cowan": 5,
+                "pukhov": 6}[self.maxwell_solver]  # constants.F90:173-180
+
+    STENCIL_KEYS = ("alphax", "alphay", "alphaz", "betaxy", "betaxz", "betayx", "betayz", "betazx", "betazy",
+                    "gammax", "gammay", "gammaz", "deltax", "deltay", "deltaz")
 
     def stencil(self) -> dict:
-        """set_maxwell_solver (epoch2d fields.f90:51-86): alpha/beta/delta of the extended B stencil."""
-        out = dict(alphax=1.0, alphay=1.0, betaxy=0.0, betayx=0.0, deltax=0.0, deltay=0.0)
-        if self.maxwell_solver == "yee":
-            return out
-        if self.ndims != 2:
-            raise NotImplementedError("extended Maxwell stencils are restated for epoch2d only")
-        dx, dy, dt = self.dx(0), self.dx(1), self.dt()
-        if self.maxwell_solver == "custom":
-            out.update({k: float(self.stencil_custom.get(k, 0.0)) for k in ("betaxy", "betayx", "deltax", "deltay")})
-            out["alphax"] = 1.0 - 2.0 * out["betaxy"] - 3.0 * out["deltax"]
-            out["alphay"] = 1.0 - 2.0 * out["betayx"] - 3.0 * out["deltay"]
-        elif self.maxwell_solver == "lehe_x":
-            dx_cdt = dx / (c * dt)
-            out["betaxy"] = 0.125 * (dx / dy) ** 2
-            out["betayx"] = 0.125
-            out["deltax"] = 0.25 * (1.0 - dx_cdt ** 2 * math.sin(0.5 * pi / dx_cdt) ** 2)
-            out["alphax"] = 1.0 - 2.0 * out["betaxy"] - 3.0 * out["deltax"]
-            out["alphay"] = 1.0 - 2.0 * out["betayx"]
-        elif self.maxwell_solver == "lehe_y":
-            dx_cdt = dy / (c * dt)
-            out["betayx"] = 0.125 * (dy / dx) ** 2
-            out["betaxy"] = 0.125
-            out["deltay"] = 0.25 * (1.0 - dx_cdt ** 2 * math.sin(0.5 * pi / dx_cdt) ** 2)
-            out["alphax"] = 1.0 - 2.0 * out["betaxy"]
-            out["alphay"] = 1.0 - 2.0 * out["betayx"] - 3.0 * out["deltay"]
-        elif self.maxwell_solver == "pukhov":
-            delta = min(dx, dy)
-            out["betayx"] = 0.125 * (delta / dx) ** 2
-            out["betaxy"] = 0.125 * (delta / dy) ** 2
-            out["alphax"] = 1.0 - 2.0 * out["betaxy"]
-            out["alphay"] = 1.0 - 2.0 * out["betayx"]
-        return out
+        """set_maxwell_solver: epoch1d fields.f90:48-62, epoch2d :51-86, epoch3d :53-162."""
+        o = {k: 0.0 for k in self.STENCIL_KEYS}
+        o["alphax"] = o["alphay"] = o["alphaz"] = 1.0
+        ms, nd = self.maxwell_solver, self.ndims
+        if ms == "yee":
+            return o
+        ok = {1: ("lehe_x", "custom"), 2: ("lehe_x", "lehe_y", "pukhov", "custom"),
+              3: ("lehe_x", "lehe_y", "lehe_z", "cowan", "pukhov", "custom")}[nd]
+        if ms not in ok:
+            raise NotImplementedError(f"maxwell_solver {ms} does not exist in epoch{nd}d")
+        d = [self.dx(i) for i in range(nd)] + [0.0] * (3 - nd)
+        dx, dy, dz = d
+        dt = self.dt()
+
+        def lehe_delta(h):
+            r = h / (c * dt)
+            return 0.25 * (1.0 - r ** 2 * math.sin(0.5 * pi / r) ** 2)
+
+        if ms == "custom":
+            for k in self.STENCIL_KEYS[3:]:
+                o[k] = float(self.stencil_custom.get(k, 0.0))
+        elif ms == "lehe_x":
+            if nd >= 2:
+                o["betaxy"] = 0.125 * (dx / dy) ** 2
+                o["betayx"] = 0.125
+            if nd == 3:
+                o["betaxz"] = 0.125 * (dx / dz) ** 2
+                o["betazx"] = 0.125
+            o["deltax"] = lehe_delta(dx)
+        elif ms == "lehe_y":
+            o["betayx"] = 0.125 * (dy / dx) ** 2
+            o["betaxy"] = 0.125
+            if nd == 3:
+                o["betayz"] = 0.125 * (dy / dz) ** 2
+                o["betazy"] = 0.125
+            o["deltay"] = lehe_delta(dy)
+        elif ms == "lehe_z":
+            o["betazx"] = 0.125 * (dz / dx) ** 2
+            o["betazy"] = 0.125 * (dz / dy) ** 2
+            o["betaxz"] = 0.125
+            o["betayz"] = 0.125
+            o["deltaz"] = lehe_delta(dz)
+        elif ms == "pukhov":
+            delta = min(d[:nd])
+            o["betayx"] = 0.125 * (delta / dx) ** 2
+            o["betaxy"] = 0.125 * (delta / dy) ** 2
+            if nd == 3:
+                o["betaxz"] = 0.125 * (delta / dz) ** 2
+                o["betazx"] = o["betayx"]
+                o["betazy"] = o["betaxy"]
+                o["betayz"] = o["betaxz"]
+        elif ms == "cowan":
+            delta = min(dx, dy, dz)
+            c1, c2, c3 = (delta / dx) ** 2, (delta / dy) ** 2, (delta / dz) ** 2
+            cx1 = 1.0 / (c1 * c2 + c2 * c3 + c1 * c3)
+            cx2 = 1.0 - c1 * c2 * c3 * cx1
+            o["betayx"] = 0.125 * c1 * cx2
+            o["betaxy"] = 0.125 * c2 * cx2
+            o["betaxz"] = 0.125 * c3 * cx2
+            o["betazx"], o["betazy"], o["betayz"] = o["betayx"], o["betaxy"], o["betaxz"]
+            o["gammax"] = c2 * c3 * (0.0625 - 0.125 * c2 * c3 * cx1)
+            o["gammay"] = c1 * c3 * (0.0625 - 0.125 * c1 * c3 * cx1)
+            o["gammaz"] = c1 * c2 * (0.0625 - 0.125 * c1 * c2 * cx1)
+        # alpha = 1 - 2 beta - 2 beta' - 4 gamma - 3 delta, term by term as in the reference
+        o["alphax"] = 1.0 - 2.0 * o["betaxy"] - 2.0 * o["betaxz"] - 4.0 * o["gammax"] - 3.0 * o["deltax"]
+        o["alphay"] = 1.0 - 2.0 * o["betayx"] - 2.0 * o["betayz"] - 4.0 * o["gammay"] - 3.0 * o["deltay"]
+        o["alphaz"] = 1.0 - 2.0 * o["betazx"] - 2.0 * o["betazy"] - 4.0 * o["gammaz"] - 3.0 * o["deltaz"]
+        return o
 
     # -- decomposition (mpi_routines.F90:317-351) ---------------------------
     def cell_ranges(self, d: int):

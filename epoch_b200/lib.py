@@ -37,7 +37,7 @@ class Config(C.Structure):
         ("dx", C.c_double * 3), ("dt", C.c_double), ("grid_min_local", C.c_double * 3),
         ("min_local", C.c_double * 3), ("max_local", C.c_double * 3),
         ("gmin", C.c_double * 3), ("gmax", C.c_double * 3),
-        ("min_outer", C.c_double * 3), ("max_outer", C.c_double * 3), ("stencil", C.c_double * 6),
+        ("min_outer", C.c_double * 3), ("max_outer", C.c_double * 3), ("stencil", C.c_double * 15),
     ]
 
 

@@ -125,7 +125,7 @@ class Simulation:
             cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
             cfg.smooth_strides = sum(int(v) << (4 * i) for i, v in enumerate(deck.smooth_strides))
         st = deck.stencil()
-        for i, k in enumerate(("alphax", "alphay", "betaxy", "betayx", "deltax", "deltay")):
+        for i, k in enumerate(deck.STENCIL_KEYS):
             cfg.stencil[i] = st[k]
         ncell = geo["n"][0] * geo["n"][1] * geo["n"][2]
         sp = (_lib.SpeciesCfg * max(1, len(deck.species)))()

@@ -53,7 +53,7 @@ MODULE epoch_b200_mod
     REAL(C_DOUBLE) :: gmin(3), gmax(3)
     REAL(C_DOUBLE) :: min_outer(3)
     REAL(C_DOUBLE) :: max_outer(3)
-    REAL(C_DOUBLE) :: stencil(6)
+    REAL(C_DOUBLE) :: stencil(15)
   END TYPE epb_config
 
   ! struct epb_species
@@ -263,7 +263,12 @@ CONTAINS
     cfg%gmax = (/ x_max, y_max, 0.0_num /)
     cfg%min_outer = (/ x_min_outer, y_min_outer, 0.0_num /)
     cfg%max_outer = (/ x_max_outer, y_max_outer, 0.0_num /)
-    cfg%stencil = (/ alphax, alphay, betaxy, betayx, deltax, deltay /)   ! fields.f90 module variables
+    cfg%stencil = 0.0_num   ! fields.f90 module variables (epoch2d has no z / gamma terms)
+    cfg%stencil(1:2) = (/ alphax, alphay /)
+    cfg%stencil(3) = 1.0_num
+    cfg%stencil(4) = betaxy
+    cfg%stencil(6) = betayx
+    cfg%stencil(13:14) = (/ deltax, deltay /)
 
     ALLOCATE(sp(n_species))
     DO ispecies = 1, n_species

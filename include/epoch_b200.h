@@ -72,7 +72,7 @@ typedef struct epb_config {
   int32_t strict_fp;        /* 1: kernels built without FMA contraction (bit-level parity build) */
   int32_t sort_interval;    /* steps between on-GPU counting sorts; 0 = library default (3 or 8, by kernel) */
   int32_t field_order;      /* 0 or 2, 4, 6: finite-difference order of the Yee solver (fields.f90:32-46) */
-  int32_t maxwell_solver;   /* c_maxwell_solver_* (constants.F90:173-180): 0 yee; -1 custom, 2 lehe_x, 3 lehe_y, 6 pukhov: extended B stencil, 2D, order 2 (fields.f90:51-100) */
+  int32_t maxwell_solver;   /* c_maxwell_solver_* (constants.F90:173-180): 0 yee; -1 custom, 2..4 lehe_x/y/z, 5 cowan, 6 pukhov: extended B stencil, order 2 (fields.f90:51-100, epoch3d :53-162, epoch1d :48-62) */
   int32_t smooth_its;       /* smooth_currents: smooth_its passes (0 = off), current_smooth.F90:50-141 */
   int32_t smooth_comp_its;  /* smooth_compensation: 0 or 1 */
   int32_t smooth_strides;   /* up to 4 strides (1..5), one per nibble, low nibble first; 0 = stride 1 */
@@ -84,7 +84,7 @@ typedef struct epb_config {
   double gmin[3], gmax[3];  /* x_min, x_max ... (global domain) */
   double min_outer[3];      /* x_min_outer ... (utilities.f90:367-369) */
   double max_outer[3];
-  double stencil[6];        /* alphax, alphay, betaxy, betayx, deltax, deltay as set_maxwell_solver leaves them */
+  double stencil[15];       /* as set_maxwell_solver leaves them: alphax..z, betaxy, betaxz, betayx, betayz, betazx, betazy, gammax..z, deltax..z */
 } epb_config;
 
 /* Mirror of TYPE particle_species (shared_data.F90:194-285), hot-path members only */

@@ -110,7 +110,8 @@ struct Config {
   // (order 2 only): maxwell_solver != 0 with the coefficients set_maxwell_solver derives
   int field_order;
   int maxwell_solver;
-  double alphax, alphay, betaxy, betayx, deltax, deltay;
+  // alpha[a], beta[a][other axis, lower first], gamma[a], delta[a] (epoch3d fields.f90:53-162)
+  double st_alpha[3], st_beta[6], st_gamma[3], st_delta[3];
   // current_smooth.F90:50-141: smooth_currents with smooth_its (+ smooth_comp_its) passes over strides
   int smooth_its, smooth_comp_its, smooth_nstrides, smooth_strides[4];
 };
@@ -583,9 +584,8 @@ void update_b_field(World &w, double hdt) {
   fd_coeffs(order, hdtx, cx);
   fd_coeffs(order, hdty, cy);
   fd_coeffs(order, hdtz, cz);
-  const bool ext = (ND == 2) && w.cfg.maxwell_solver != 0;  // fields.f90:441-465
-  const double alphax = w.cfg.alphax, alphay = w.cfg.alphay, betaxy = w.cfg.betaxy, betayx = w.cfg.betayx,
-               deltax = w.cfg.deltax, deltay = w.cfg.deltay;
+  const bool ext = w.cfg.maxwell_solver != 0;  // fields.f90:441-465, epoch3d :655-730, epoch1d :304-312
+  const Config &cf = w.cfg;
   for (Rank &R : w.r) {
     const Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
     Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
@@ -603,28 +603,67 @@ void update_b_field(World &w, double hdt) {
             return ND == 2 ? f(ix, iy + k + 1) - f(ix, iy - k) : f(ix, iy + k + 1, iz) - f(ix, iy - k, iz);
           };
           auto dzf = [&](const Arr &f, int k) { return f(ix, iy, iz + k + 1) - f(ix, iy, iz - k); };
-          if (ND == 1) {
+          if (ND == 1 && !ext) {
             double v = by(ix);
             for (int k = 0; k < nt; k++) v = v + cx[k] * dxf(ez, k);
             by(ix) = v;
             v = bz(ix);
             for (int k = 0; k < nt; k++) v = v - cx[k] * dxf(ey, k);
             bz(ix) = v;
-          } else if (ND == 2 && ext) {
-            // x-derivative of f at (ix+1/2, iy) and y-derivative at (ix, iy+1/2), extended stencil
-            auto ddx = [&](const Arr &f) {
-              return alphax * (f(ix + 1, iy) - f(ix, iy)) +
-                     betaxy * (f(ix + 1, iy + 1) - f(ix, iy + 1) + f(ix + 1, iy - 1) - f(ix, iy - 1)) +
-                     deltax * (f(ix + 2, iy) - f(ix - 1, iy));
+          } else if (ext) {
+            // derivative of f along axis a at the staggered point: alpha, the two betas (lower other axis
+            // first; +1 then -1), gamma (3D; first other axis + then -, second other axis - then +), delta
+            auto F = [&](const Arr &f, int dx_, int dy_, int dz_) {
+              return ND == 1 ? f(ix + dx_) : ND == 2 ? f(ix + dx_, iy + dy_) : f(ix + dx_, iy + dy_, iz + dz_);
             };
-            auto ddy = [&](const Arr &f) {
-              return alphay * (f(ix, iy + 1) - f(ix, iy)) +
-                     betayx * (f(ix + 1, iy + 1) - f(ix + 1, iy) + f(ix - 1, iy + 1) - f(ix - 1, iy)) +
-                     deltay * (f(ix, iy + 2) - f(ix, iy - 1));
+            auto dd = [&](const Arr &f, int a) {
+              int e[3] = {0, 0, 0};
+              e[a] = 1;
+              auto df = [&](int ox, int oy, int oz) {  // f(+a) - f(0), both shifted by (ox, oy, oz)
+                return F(f, e[0] + ox, e[1] + oy, e[2] + oz) - F(f, ox, oy, oz);
+              };
+              double v = cf.st_alpha[a] * df(0, 0, 0);
+              int oth[2], no = 0;
+              for (int d = 0; d < 3; d++) if (d != a) oth[no++] = d;
+              for (int k = 0; k < 2; k++) {
+                const int b_ = oth[k];
+                if (b_ >= ND) continue;
+                int p[3] = {0, 0, 0}, m[3] = {0, 0, 0};
+                p[b_] = 1; m[b_] = -1;
+                // (f(+a,+b) - f(0,+b) + f(+a,-b)) - f(0,-b), left to right
+                const double t = F(f, e[0] + p[0], e[1] + p[1], e[2] + p[2]) - F(f, p[0], p[1], p[2]) +
+                                 F(f, e[0] + m[0], e[1] + m[1], e[2] + m[2]) - F(f, m[0], m[1], m[2]);
+                v = v + cf.st_beta[2 * a + k] * t;
+              }
+              if (ND == 3) {
+                const int b_ = oth[0], c_ = oth[1];
+                double t = 0.0;
+                bool first = true;
+                for (int sc = -1; sc <= 1; sc += 2)
+                  for (int sb = 1; sb >= -1; sb -= 2) {
+                    int o[3] = {0, 0, 0};
+                    o[b_] = sb; o[c_] = sc;
+                    const double hi = F(f, e[0] + o[0], e[1] + o[1], e[2] + o[2]), lo = F(f, o[0], o[1], o[2]);
+                    if (first) { t = hi - lo; first = false; }
+                    else t = t + hi - lo;
+                  }
+                v = v + cf.st_gamma[a] * t;
+              }
+              v = v + cf.st_delta[a] * (F(f, 2 * e[0], 2 * e[1], 2 * e[2]) - F(f, -e[0], -e[1], -e[2]));
+              return v;
             };
-            bx(ix, iy) = bx(ix, iy) - hdty * ddy(ez);
-            by(ix, iy) = by(ix, iy) + hdtx * ddx(ez);
-            bz(ix, iy) = bz(ix, iy) - hdtx * ddx(ey) + hdty * ddy(ex);
+            if (ND == 1) {
+              by(ix) = by(ix) + hdtx * dd(ez, 0);
+              bz(ix) = bz(ix) - hdtx * dd(ey, 0);
+            } else if (ND == 2) {
+              bx(ix, iy) = bx(ix, iy) - hdty * dd(ez, 1);
+              by(ix, iy) = by(ix, iy) + hdtx * dd(ez, 0);
+              bz(ix, iy) = bz(ix, iy) - hdtx * dd(ey, 0) + hdty * dd(ex, 1);
+            } else {
+              bx(ix, iy, iz) = bx(ix, iy, iz) - hdty * dd(ez, 1) + hdtz * dd(ey, 2);
+              by(ix, iy, iz) = by(ix, iy, iz) - hdtz * dd(ex, 2) + hdtx * dd(ez, 0);
+              bz(ix, iy, iz) = bz(ix, iy, iz) - hdtx * dd(ey, 0) + hdty * dd(ex, 1);
+            }
           } else if (ND == 2) {
             double v = bx(ix, iy);
             for (int k = 0; k < nt; k++) v = v - cy[k] * dyf(ez, k);

@@ -21,8 +21,8 @@ class _Config(C.Structure):
         ("xmin", C.c_double * 3), ("xmax", C.c_double * 3), ("bc_field", C.c_int * 6),
         ("dt", C.c_double), ("n_species", C.c_int), ("seed", C.c_int),
         ("field_order", C.c_int), ("maxwell_solver", C.c_int),
-        ("alphax", C.c_double), ("alphay", C.c_double), ("betaxy", C.c_double), ("betayx", C.c_double),
-        ("deltax", C.c_double), ("deltay", C.c_double),
+        ("st_alpha", C.c_double * 3), ("st_beta", C.c_double * 6), ("st_gamma", C.c_double * 3),
+        ("st_delta", C.c_double * 3),
         ("smooth_its", C.c_int), ("smooth_comp_its", C.c_int), ("smooth_nstrides", C.c_int),
         ("smooth_strides", C.c_int * 4),
     ]
@@ -101,8 +101,13 @@ class Oracle:
         cfg.seed = deck.seed
         cfg.field_order = int(getattr(deck, "field_order", 2))
         cfg.maxwell_solver = deck.maxwell_solver_code() if hasattr(deck, "maxwell_solver_code") else 0
-        for k, v in (deck.stencil() if hasattr(deck, "stencil") else {}).items():
-            setattr(cfg, k, v)
+        st = deck.stencil()
+        for i, ax in enumerate("xyz"):
+            cfg.st_alpha[i] = st["alpha" + ax]
+            cfg.st_gamma[i] = st["gamma" + ax]
+            cfg.st_delta[i] = st["delta" + ax]
+        for i, k in enumerate(("betaxy", "betaxz", "betayx", "betayz", "betazx", "betazy")):
+            cfg.st_beta[i] = st[k]
         if getattr(deck, "smooth_currents", False):
             cfg.smooth_its = int(deck.smooth_iterations)
             cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0

@@ -134,6 +134,14 @@ CASES = [
     (2, (40, 24), dict(maxwell_solver="pukhov")),
     (2, (40, 24), dict(maxwell_solver="custom",
                        stencil_custom=dict(betaxy=0.1, betayx=0.05, deltax=0.02, deltay=0.01, dt=1.0e-16))),
+    (1, (48,), dict(maxwell_solver="lehe_x")),
+    (3, (12, 10, 9), dict(maxwell_solver="lehe_x")), (3, (12, 10, 9), dict(maxwell_solver="lehe_y")),
+    (3, (12, 10, 9), dict(maxwell_solver="lehe_z")), (3, (12, 10, 9), dict(maxwell_solver="cowan")),
+    (3, (12, 10, 9), dict(maxwell_solver="pukhov")),
+    (3, (12, 10, 9), dict(maxwell_solver="custom",
+                          stencil_custom=dict(betaxy=0.05, betaxz=0.04, betayx=0.03, betayz=0.02, betazx=0.06,
+                                              betazy=0.01, gammax=0.01, gammay=0.02, gammaz=0.005,
+                                              deltax=0.01, deltay=0.02, deltaz=0.015, dt=5.0e-17))),
 ]
 
 
@@ -197,6 +205,58 @@ def test_binomial_filter_properties(ndims, n):
 
 
 def test_unsupported_solver_combinations_are_refused():
-    dk = D.Deck(3, [8, 8, 8], [0.0] * 3, [1.0] * 3, ["periodic"] * 6, maxwell_solver="lehe_x")
+    dk = D.Deck(2, [8, 8], [0.0] * 2, [1.0] * 2, ["periodic"] * 4, maxwell_solver="cowan")   # epoch3d only
     with pytest.raises(NotImplementedError):
         dk.stencil()
+
+
+def test_cowan_and_lehe_z_group_velocity_3d():
+    """3D solvers along their favoured axis on a thin periodic box: Cowan / Pukhov reduce to the 1D Yee
+    dispersion at c dt / dx = 0.95 for a wave that is uniform in the two other directions, Lehe_z follows
+    the Lehe dispersion along z."""
+    lam = 0.5e-6
+    for solver, axis in (("cowan", 0), ("pukhov", 0), ("lehe_z", 2)):
+        n = [6, 6, 6]
+        n[axis] = 240
+        L = [0.6e-6] * 3
+        L[axis] = 24e-6
+        dk = D.Deck(3, n, [-l / 2 for l in L], [l / 2 for l in L], ["periodic"] * 6, maxwell_solver=solver)
+        dx, dt = dk.dx(axis), dk.dt()
+        k_l = 2 * np.pi / lam
+        S = c * dt / dx
+        st = dk.stencil()
+        delta = st["delta" + "xyz"[axis]]
+
+        def w_of(k):
+            s = np.sin(k * dx / 2) * ((1 - 3 * delta) * np.sin(k * dx / 2) + delta * np.sin(3 * k * dx / 2))
+            return 2 / dt * np.arcsin(S * np.sqrt(s))
+        vg = (w_of(k_l * 1.0001) - w_of(k_l * 0.9999)) / (k_l * 0.0002)
+        o = Oracle(dk)
+        ng = 5
+        idx = np.arange(1 - ng, n[axis] + ng + 1)
+        x_c = dk.grid_min(axis) + (idx - 1) * dx
+        x0, width = -6e-6, 1.2e-6
+        env_c = np.exp(-((x_c - x0) / width) ** 2) * np.sin(k_l * (x_c - x0))
+        xs = x_c + dx / 2
+        env_s = np.exp(-((xs - x0) / width) ** 2) * np.sin(k_l * (xs - x0))
+        # propagation along +axis: (E_b, B_c) = (E, E/c) with (a, b, c) cyclic
+        eb, bc = ("ey", "bz") if axis == 0 else ("ex", "by")
+        shape = [1, 1, 1]
+        shape[2 - axis] = -1                              # arrays are (z, y, x)
+        o.field(0, eb)[...] = 1e9 * env_c.reshape(shape)
+        o.field(0, bc)[...] = 1e9 / c * env_s.reshape(shape)
+        o.init()
+        ts, xcs = [], []
+        for s_ in range(int(30e-15 / dt)):
+            o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+            if s_ % 5 == 4 and (s_ + 1) * dt > 12e-15:
+                a = o.field(0, eb)
+                line = a[ng:-ng, ng, ng] if axis == 2 else a[ng, ng, ng:-ng]
+                Fq = np.fft.fft(line); m = line.size
+                Fq[m // 2 + 1:] = 0.0; Fq[1:m // 2] *= 2.0
+                e2 = np.abs(np.fft.ifft(Fq)) ** 2
+                x = x_c[ng:-ng]
+                sel = np.abs(x - x[np.argmax(e2)]) <= 3e-6
+                ts.append((s_ + 1) * dt); xcs.append(float((x[sel] * e2[sel]).sum() / e2[sel].sum()))
+        vg_sim = np.polyfit(ts, xcs, 1)[0]
+        assert np.isclose(vg_sim, vg, rtol=0.005), (solver, vg_sim, vg)
