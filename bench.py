@@ -157,7 +157,12 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(b["wall_s"] for b in vals) / len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "epoch2d uniform thermal plasma (BASELINE C2 physics), bounded CPU sample"},
+            # the same workload the CUDA arm reports; the CPU arm advances a bounded sample of it per step
+            # (cpu_baseline.sample), there being no way to hold 1.07e9 particles x 10 steps in a few minutes of CPU
+            "config": {"workload": f"epoch2d uniform thermal plasma, periodic, {args.n}x{args.n} cells per GPU, "
+                                   f"{args.ppc} ppc ({args.n * args.n * args.ppc} particles per GPU), triangle shape, "
+                                   "Yee order 2 (BASELINE C2)",
+                       "sampled": True},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
