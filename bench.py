@@ -268,7 +268,7 @@ def main():
     # source planes, laser.f90:347-352; zero for this periodic deck but copied all the same)
     # from pinned memory, and reads back the step's results: the global particle count
     # (update_particle_count), the field energies (calc_total_energy_sum) and the Ey array as
-    # a field dump would.  The particle state itself stays device-resident by design.
+    # a field dump would (asynchronously: epb_download_field_async).  The particle state itself stays device-resident by design.
     ny1 = (sim.geo["n"][1] + 1) * (sim.geo["n"][2] + 1 if args.workload == "c4" else 1)
     src = torch.zeros(2, ny1, dtype=torch.float64).pin_memory()
     ey_host = torch.empty(sim.shape, dtype=torch.float64).pin_memory()
@@ -282,7 +282,14 @@ def main():
         sim.step()
         sim.global_count(0)
         sim.field_energy()
-        sim.download_field_into("ey", ey_host.data_ptr())
+        # the Ey dump of this step leaves the device while the next step runs (device-side snapshot +
+        # second stream); the host owns the previous step's array from here on
+        if os.environ.get("EPB_BENCH_SYNC_DUMP"):
+            sim.download_field_into("ey", ey_host.data_ptr())
+        else:
+            sim.wait_downloads()
+            sim.download_field_async("ey", ey_host.data_ptr())
+    sim.wait_downloads()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -1094,6 +1094,7 @@ int epb_destroy(epb_handle *h) {
   epb_comm_destroy(h);
   cudaFree(h->fields); cudaFree(h->snap); cudaFree(h->src);
   for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
   cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
@@ -1135,6 +1136,36 @@ int epb_download_field(epb_handle *h, int field, double *host) {
   if (!h || field < 0 || field >= 9) return EPB_ERR_ARG;
   EPB_CUDA(h, cudaMemcpyAsync(host, h->f(field), h->fsize * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPB_OK;
+}
+// Field dump that overlaps the following steps: the array is snapshotted on the device in stream
+// order (so later kernels may overwrite it at once) and copied to the host on a second stream.
+int epb_download_field_async(epb_handle *h, int field, double *host) {
+  if (!h || field < 0 || field >= 9 || !host) return EPB_ERR_ARG;
+  if (!h->copy_stream) {
+    EPB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    EPB_CUDA(h, cudaMalloc(&h->dump_stage, h->fsize * sizeof(double)));
+    EPB_CUDA(h, cudaEventCreateWithFlags(&h->dump_ready, cudaEventDisableTiming));
+    EPB_CUDA(h, cudaEventCreateWithFlags(&h->dump_done, cudaEventDisableTiming));
+  }
+  if (h->dump_pending) {  // one staging buffer: the previous dump must have left the device
+    EPB_CUDA(h, cudaStreamWaitEvent(h->stream, h->dump_done, 0));
+  }
+  EPB_CUDA(h, cudaMemcpyAsync(h->dump_stage, h->f(field), h->fsize * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  EPB_CUDA(h, cudaEventRecord(h->dump_ready, h->stream));
+  EPB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->dump_ready, 0));
+  EPB_CUDA(h, cudaMemcpyAsync(host, h->dump_stage, h->fsize * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+  EPB_CUDA(h, cudaEventRecord(h->dump_done, h->copy_stream));
+  h->dump_pending = true;
+  return EPB_OK;
+}
+// blocks until the host buffers of all asynchronous dumps are complete
+int epb_wait_downloads(epb_handle *h) {
+  if (!h) return EPB_ERR_ARG;
+  if (h->dump_pending) {
+    EPB_CUDA(h, cudaEventSynchronize(h->dump_done));
+    h->dump_pending = false;
+  }
   return EPB_OK;
 }
 int epb_field_device_ptr(epb_handle *h, int field, void **dptr) {

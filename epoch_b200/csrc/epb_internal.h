@@ -126,6 +126,11 @@ struct epb_handle {
   int *h_counts = nullptr;      // pinned [64]
   int *d_scratch = nullptr;     // device ints
   int *movers = nullptr;        // exchange: tail survivors that fill holes (27*out_cap+1)
+  // asynchronous field dump: device staging copy + second stream (epb_download_field_async)
+  cudaStream_t copy_stream = nullptr;
+  double *dump_stage = nullptr;
+  cudaEvent_t dump_ready = nullptr, dump_done = nullptr;
+  bool dump_pending = false;
   double *sendbuf = nullptr, *recvbuf = nullptr;  // halo + particle staging
   size_t sendbuf_elems = 0, recvbuf_elems = 0;
   void *nccl = nullptr;         // ncclComm_t

@@ -264,6 +264,14 @@ class Simulation:
         """D2H of one field array (with ghosts) into caller-owned (e.g. pinned) host memory."""
         self._chk(self.L.epb_download_field(self._h, _lib.FIELD_NAMES.index(name), C.c_void_p(host_ptr)))
 
+    def download_field_async(self, name: str, host_ptr: int):
+        """Field dump that overlaps the following steps; host_ptr must be page-locked and must not be read
+        before wait_downloads() returns."""
+        self._chk(self.L.epb_download_field_async(self._h, _lib.FIELD_NAMES.index(name), C.c_void_p(host_ptr)))
+
+    def wait_downloads(self):
+        self._chk(self.L.epb_wait_downloads(self._h))
+
     def launch_count(self) -> int:
         return int(self.L.epb_launch_count(self._h))
 

@@ -121,6 +121,11 @@ int epb_set_comm(epb_handle *h, const void *id128);
 /* -- state transfer ------------------------------------------------------------ */
 int epb_upload_field(epb_handle *h, int field, const double *host);
 int epb_download_field(epb_handle *h, int field, double *host);
+/* the same as a dump that overlaps the following steps (io/diagnostics.F90 writes field dumps while
+ * nothing else runs; here the array is snapshotted on the device and leaves over a second stream):
+ * host must be page-locked and stay untouched until epb_wait_downloads returns */
+int epb_download_field_async(epb_handle *h, int field, double *host);
+int epb_wait_downloads(epb_handle *h);
 int epb_upload_species(epb_handle *h, int ispecies, int64_t n, const double *packed);
 int epb_download_species(epb_handle *h, int ispecies, int64_t n, double *packed);
 int epb_species_count(epb_handle *h, int ispecies, int64_t *n);   /* attached_list%count */

@@ -188,3 +188,22 @@ def test_full_size_properties_2d():
     assert int(sim.cell_counts(0).sum()) == n0
     jx = sim.interior("jx")
     assert np.isfinite(jx).all() and np.abs(jx).max() > 0
+
+
+def test_async_field_dump_equals_sync_dump():
+    """epb_download_field_async: the snapshot is taken in stream order, so the array that arrives is the
+    one of the step it was requested in even though later steps overwrite the device copy meanwhile."""
+    import torch
+    dk = decks.thermal(2, (48, 32), ppc=6, temp_k=3.0e8)
+    o, sim = make_pair(dk, strict=True)
+    sim.init()
+    for _ in range(2):
+        sim.step()
+    ref = sim.download_field("ey").copy()
+    host = torch.empty(ref.size, dtype=torch.float64).pin_memory()
+    sim.download_field_async("ey", host.data_ptr())
+    for _ in range(3):           # keep computing while the dump is in flight
+        sim.step()
+    sim.wait_downloads()
+    assert np.array_equal(host.numpy().reshape(ref.shape), ref)
+    assert not np.array_equal(sim.download_field("ey"), ref)
