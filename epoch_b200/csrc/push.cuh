@@ -1299,6 +1299,66 @@ constexpr size_t PUSH3D_SMEM =
     sizeof(double) * ((size_t)3 * JT3 + (size_t)P3_WARPS * SROWS * SPITCH + (size_t)P3_WARPS * Q3DBL * Q3CAP) +
     sizeof(int) * ((size_t)P3_WARPS * Q3CAP + (size_t)P3_WARPS * 32 + SLOW3CAP + 2);
 
+// Edge deposit of a queued particle whose nearest cell moved by one cell along exactly one axis a
+// (dc = +-1): its 3x3x3 core joined the transposed reduction with shifted new weights; what is left is
+// J_a on the plane the core has no row for (a-index -2 when dc < 0, else +1: 9 values) and J_b, J_c on
+// the outer plane at a-index +-2 (6 + 6 values).  Every weight of the reference's loop (epoch3d
+// particles.F90:603-648) is h_a * S(g_b, h_b, g_c, h_c) with the bilinear form
+// S = g_b g_c + (g_b h_c + h_b g_c) / 2 + h_b h_c / 3, cyclically in (a, b, c): 21 updates, not ~108.
+__device__ __noinline__ void drain_edge_3d(const PushParams &P, double *sJ, const double *Qd, int slot, int key, int a,
+                                           int dc, double fja, double fjb, double fjc) {
+  const int b = (a + 1) % 3, c = (a + 2) % 3;
+  const double third = P.third;
+  double g[3][3], n[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    tri(Qd[(2 * d) * Q3CAP + slot], g[d][0], g[d][1], g[d][2]);
+    tri(Qd[(2 * d + 1) * Q3CAP + slot], n[d][0], n[d][1], n[d][2]);
+  }
+  // axis a: new weights shifted by dc onto the core; the outer cell only carries a new weight
+  double hCs, hE;
+  if (dc > 0) { hCs = (0.0 - g[a][0]) + (n[a][0] - g[a][1]) + (n[a][1] - g[a][2]); hE = n[a][2]; }
+  else { hCs = (n[a][1] - g[a][0]) + (n[a][2] - g[a][1]) + (0.0 - g[a][2]); hE = n[a][0]; }
+  double gb[3], hb[3], gc[3], hc[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) { gb[q] = g[b][q]; hb[q] = n[b][q] - g[b][q]; gc[q] = g[c][q]; hc[q] = n[c][q] - g[c][q]; }
+  const int str[3] = {1, JW3, JW3 * JW3};
+  const int sa = str[a], sb = str[b], sc = str[c];
+  const int oe = key + 2 * dc * sa;                    // outer plane
+  const int oa = dc < 0 ? oe : key + sa;               // plane of the J_a values the core has no row for
+  const double ha = dc < 0 ? hE : hCs;
+  // J_a: - fj_a * ha * S(b, c)
+#pragma unroll
+  for (int ic = 0; ic < 3; ic++)
+#pragma unroll
+    for (int ib = 0; ib < 3; ib++) {
+      const double S = gb[ib] * gc[ic] + 0.5 * (gb[ib] * hc[ic] + hb[ib] * gc[ic]) + third * (hb[ib] * hc[ic]);
+      smem_add(&sJ[a * JT3 + oa + (ib - 1) * sb + (ic - 1) * sc], -(fja * (ha * S)));
+    }
+  // J_b on the outer plane: running sum along b of - fj_b * h_b * S(a = outer cell, c); last row cancels
+#pragma unroll
+  for (int ic = 0; ic < 3; ic++) {
+    const double Sac = hE * (0.5 * gc[ic] + third * hc[ic]);
+    double run = 0.0;
+#pragma unroll
+    for (int ib = 0; ib < 2; ib++) {
+      run = run - fjb * (hb[ib] * Sac);
+      smem_add(&sJ[b * JT3 + oe + (ib - 1) * sb + (ic - 1) * sc], run);
+    }
+  }
+  // J_c on the outer plane: running sum along c
+#pragma unroll
+  for (int ib = 0; ib < 3; ib++) {
+    const double Sab = hE * (0.5 * gb[ib] + third * hb[ib]);
+    double run = 0.0;
+#pragma unroll
+    for (int ic = 0; ic < 2; ic++) {
+      run = run - fjc * (hc[ic] * Sab);
+      smem_add(&sJ[c * JT3 + oe + (ib - 1) * sb + (ic - 1) * sc], run);
+    }
+  }
+}
+
 // General deposit of queued particles on the shared tile: epoch3d particles.F90:603-648.
 __device__ __noinline__ void drain_extras_3d(const PushParams &P, double *sJ, const double *Qd, const int *Qk, int n,
                                              int lane) {
@@ -1307,6 +1367,12 @@ __device__ __noinline__ void drain_extras_3d(const PushParams &P, double *sJ, co
   const int key = pk & 4095;
   int dcell[3] = {((pk >> 12) & 3) - 1, ((pk >> 14) & 3) - 1, ((pk >> 16) & 3) - 1};
   const double fjx = Qd[6 * Q3CAP + lane], fjy = Qd[7 * Q3CAP + lane], fjz = Qd[8 * Q3CAP + lane];
+  if (pk & (1 << 18)) {  // core already reduced with the batch: only the outer values are left
+    const int a = dcell[0] != 0 ? 0 : dcell[1] != 0 ? 1 : 2;
+    const double fj[3] = {fjx, fjy, fjz};
+    drain_edge_3d(P, sJ, Qd, lane, key, a, dcell[a], fj[a], fj[(a + 1) % 3], fj[(a + 2) % 3]);
+    return;
+  }
   double G[3][5], H[3][5];
   int mn[3], mx[3];
 #pragma unroll
@@ -1403,25 +1469,18 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
     off0 = comp * JT3 + ((0 - 1) * JW3 + (diy - 1)) * JW3 + (dix - 1);
   }
 
-  long long i = start + warp * 32 + lane;
-  double n_x = 0, n_y = 0, n_z = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
-  if (i < end) {
-    n_w = P.w[i]; n_x = P.x[0][i]; n_y = P.x[1][i]; n_z = P.x[2][i];
-    n_px = P.p[0][i]; n_py = P.p[1][i]; n_pz = P.p[2][i];
-  }
-  for (; i - lane < end; i += P3_THREADS) {
+  // no software prefetch here: 16 warps per SM hide the load latency and the kernel is short of registers
+  for (long long i = start + warp * 32 + lane; i - lane < end; i += P3_THREADS) {
     const bool active = i < end;
-    const double part_weight = n_w;
-    double pp[3] = {n_x - P.grid_min_local[0], n_y - P.grid_min_local[1], n_z - P.grid_min_local[2]};
-    double part_ux = n_px * P.ipart_mc;
-    double part_uy = n_py * P.ipart_mc;
-    double part_uz = n_pz * P.ipart_mc;
-    {
-      const long long in = i + P3_THREADS;
-      if (in < end) {
-        n_w = P.w[in]; n_x = P.x[0][in]; n_y = P.x[1][in]; n_z = P.x[2][in];
-        n_px = P.p[0][in]; n_py = P.p[1][in]; n_pz = P.p[2][in];
-      }
+    double part_weight = 0.0, pp[3] = {0.0, 0.0, 0.0}, part_ux = 0.0, part_uy = 0.0, part_uz = 0.0;
+    if (active) {
+      part_weight = P.w[i];
+      pp[0] = P.x[0][i] - P.grid_min_local[0];
+      pp[1] = P.x[1][i] - P.grid_min_local[1];
+      pp[2] = P.x[2][i] - P.grid_min_local[2];
+      part_ux = P.p[0][i] * P.ipart_mc;
+      part_uy = P.p[1][i] * P.ipart_mc;
+      part_uz = P.p[2][i] * P.ipart_mc;
     }
     // ---- phase A: half-step move and nearest cell (epoch3d particles.F90:320-370) ---------
     int key = -1;
@@ -1467,8 +1526,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
       }
     }
     // ---- phase B: gather, Boris rotation, move, store ------------------------------------
-    bool regular = false, extras = false;
+    bool regular = false, extras = false, edge = false;
     int dc[3] = {0, 0, 0};
+    double hfold[3] = {0.0, 0.0, 0.0};
     double G[3][3], H[3][3];  // g weights at t+dt/2; H: staggered weights, later (new weights - g)
     double fo[3] = {0, 0, 0}, fn[3] = {0, 0, 0};
     double fjx = 0, fjy = 0, fjz = 0;
@@ -1540,14 +1600,25 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
         fjx = fcx * P.part_q;
         fjy = fcy * P.part_q;
         fjz = fcz * P.part_q;
-        if ((dc[0] | dc[1] | dc[2]) != 0) {
-          extras = true;
+        const int nmove = (dc[0] != 0) + (dc[1] != 0) + (dc[2] != 0);
+        if (nmove >= 2) {
+          extras = true;  // moved along two or three axes: general loop
         } else {
+          // nearest cell unchanged, or moved by one cell along one axis: new weights shifted onto the
+          // 3x3x3 core; the running prefix of that axis' own component enters the core with the value
+          // of the outer cell at -2 (hfold); the outer values are queued (drain_edge_3d)
           regular = true;
 #pragma unroll
-          for (int d = 0; d < 3; d++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) H[d][q] = W[d][q] - G[d][q];
+          for (int d = 0; d < 3; d++) {
+            const double n0 = dc[d] == 0 ? W[d][0] : dc[d] > 0 ? 0.0 : W[d][1];
+            const double n1 = dc[d] == 0 ? W[d][1] : dc[d] > 0 ? W[d][0] : W[d][2];
+            const double n2 = dc[d] == 0 ? W[d][2] : dc[d] > 0 ? W[d][1] : 0.0;
+            H[d][0] = n0 - G[d][0];
+            H[d][1] = n1 - G[d][1];
+            H[d][2] = n2 - G[d][2];
+            hfold[d] = H[d][0] + (dc[d] < 0 ? W[d][0] : 0.0);
+          }
+          if (nmove == 1) { extras = true; edge = true; }
         }
       }
     }
@@ -1566,7 +1637,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
       const int myslot = qcount + __popc(em & lt_mask);
       if (extras) {
         if (myslot < Q3CAP) {
-          Qk[myslot] = key | ((dc[0] + 1) << 12) | ((dc[1] + 1) << 14) | ((dc[2] + 1) << 16);
+          Qk[myslot] = key | ((dc[0] + 1) << 12) | ((dc[1] + 1) << 14) | ((dc[2] + 1) << 16) | (edge ? 1 << 18 : 0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { Qd[(2 * d) * Q3CAP + myslot] = fo[d]; Qd[(2 * d + 1) * Q3CAP + myslot] = fn[d]; }
           Qd[6 * Q3CAP + myslot] = fjx; Qd[7 * Q3CAP + myslot] = fjy; Qd[8 * Q3CAP + myslot] = fjz;
@@ -1581,7 +1652,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
         qcount = 0;
         if (extras && myslot >= Q3CAP) {
           const int s2 = myslot - Q3CAP;
-          Qk[s2] = key | ((dc[0] + 1) << 12) | ((dc[1] + 1) << 14) | ((dc[2] + 1) << 16);
+          Qk[s2] = key | ((dc[0] + 1) << 12) | ((dc[1] + 1) << 14) | ((dc[2] + 1) << 16) | (edge ? 1 << 18 : 0);
 #pragma unroll
           for (int d = 0; d < 3; d++) { Qd[(2 * d) * Q3CAP + s2] = fo[d]; Qd[(2 * d + 1) * Q3CAP + s2] = fn[d]; }
           Qd[6 * Q3CAP + s2] = fjx; Qd[7 * Q3CAP + s2] = fjy; Qd[8 * Q3CAP + s2] = fjz;
@@ -1605,22 +1676,24 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
           const double zfac1 = gz[iz] + 0.5 * hz[iz];
           const double zfac2 = third * hz[iz] + 0.5 * gz[iz];
           const double gz_iz = gz[iz], hz_iz = hz[iz];
+          const double hzw = iz == 0 ? hfold[2] : hz_iz;   // jz prefix along z
           double jyh[3] = {0.0, 0.0, 0.0};
 #pragma unroll
           for (int iy = 0; iy < 3; iy++) {
             const double yfac1 = gy[iy] + 0.5 * hy[iy];
             const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
-            const double hygz = hy[iy] * gz_iz;
-            const double hyhz = hy[iy] * hz_iz;
+            const double hyw = iy == 0 ? hfold[1] : hy[iy];  // jy prefix along y
+            const double hygz = hyw * gz_iz;
+            const double hyhz = hyw * hz_iz;
             const double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
-            const double hzyfac1 = hz_iz * yfac1;
-            const double hzyfac2 = hz_iz * yfac2;
+            const double hzyfac1 = hzw * yfac1;
+            const double hzyfac2 = hzw * yfac2;
             double jxh = 0.0;
 #pragma unroll
             for (int ix = 0; ix < 3; ix++) {
               const double xfac1 = gx[ix] + 0.5 * hx[ix];
               const double xfac2 = third * hx[ix] + 0.5 * gx[ix];
-              const double wx = hx[ix] * yzfac;
+              const double wx = (ix == 0 ? hfold[0] : hx[ix]) * yzfac;
               const double wy = xfac1 * hygz + xfac2 * hyhz;
               const double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
               jxh = jxh - fjx * wx;
