@@ -1281,8 +1281,8 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
 // ---------------------------------------------------------------------------
 // Tiled 3D kernel
 // ---------------------------------------------------------------------------
-// One CTA (16 warps) per 8x8x8-cell tile of the cell-sorted layout, one CTA per SM.  J is
-// accumulated in a shared tile (+3 halo cells, 66 KB) and flushed once with global reductions;
+// One CTA (8 warps) per 8x8x4-cell tile of the cell-sorted layout, two CTAs per SM.  J is
+// accumulated in a shared tile (+3 halo cells, 47 KB) and flushed once with global reductions;
 // E/B are gathered through the read-only path (a 14^3 x 6 tile does not fit beside the J tile
 // and the reduction scratch; the tile's fields stay L1/L2 resident).  The deposit uses the
 // transposition of push_tiled_2d, generalised to any number of cells per warp (8 particles per
@@ -1292,11 +1292,13 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
 // its values in its column and lane q sums row q run by run, one shared update per (cell, value).
 // Particles whose nearest cell changed (wider stencil) are queued per warp and deposited with
 // the reference's general loop (epoch3d particles.F90:603-648) on the shared tile.
-constexpr int T3 = 8, HALO3 = 3, JW3 = T3 + 2 * HALO3, JT3 = JW3 * JW3 * JW3;
-constexpr int P3_THREADS = 512, P3_WARPS = P3_THREADS / 32;
-constexpr int Q3CAP = 16, Q3DBL = 9, SLOW3CAP = 254;
+// tile = 8 x 8 x 4 cells (T3 x T3 x T3Z), 8 warps, two CTAs per SM so that one CTA's J-tile prologue /
+// epilogue overlaps the other's particle loop
+constexpr int T3 = 8, T3Z = 4, HALO3 = 3, JW3 = T3 + 2 * HALO3, JD3 = T3Z + 2 * HALO3, JT3 = JW3 * JW3 * JD3;
+constexpr int P3_THREADS = 256, P3_WARPS = P3_THREADS / 32;
+constexpr int Q3CAP = 16, Q3DBL = 9, SLOW3CAP = 254, S3ROWS = 21;
 constexpr size_t PUSH3D_SMEM =
-    sizeof(double) * ((size_t)3 * JT3 + (size_t)P3_WARPS * SROWS * SPITCH + (size_t)P3_WARPS * Q3DBL * Q3CAP) +
+    sizeof(double) * ((size_t)3 * JT3 + (size_t)P3_WARPS * S3ROWS * SPITCH + (size_t)P3_WARPS * Q3DBL * Q3CAP) +
     sizeof(int) * ((size_t)P3_WARPS * Q3CAP + (size_t)P3_WARPS * 32 + SLOW3CAP + 2);
 
 // Edge deposit of a queued particle whose nearest cell moved by one cell along exactly one axis a
@@ -1428,11 +1430,11 @@ __device__ __noinline__ void drain_extras_3d(const PushParams &P, double *sJ, co
   }
 }
 
-__global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_constant__ PushParams P) {
+__global__ void __launch_bounds__(P3_THREADS, 2) push_tiled_3d(const __grid_constant__ PushParams P) {
   extern __shared__ double sm[];
   double *sJ = sm;                                       // [3][JW3][JW3][JW3]
   double *sS_all = sJ + 3 * JT3;                         // [warps][27][33]
-  double *sQd_all = sS_all + P3_WARPS * SROWS * SPITCH;  // [warps][9][Q3CAP]
+  double *sQd_all = sS_all + P3_WARPS * S3ROWS * SPITCH;  // [warps][9][Q3CAP]
   int *sQk_all = reinterpret_cast<int *>(sQd_all + P3_WARPS * Q3DBL * Q3CAP);
   int *sRK_all = sQk_all + P3_WARPS * Q3CAP;
   int *sSlow = sRK_all + P3_WARPS * 32;
@@ -1441,7 +1443,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
   const int ttx = tile % P.tg.nt[0], tty = (tile / P.tg.nt[0]) % P.tg.nt[1], ttz = tile / (P.tg.nt[0] * P.tg.nt[1]);
   const int ox = ttx * T3 + 1 - HALO3;  // cell index of shared column 0
   const int oy = tty * T3 + 1 - HALO3;
-  const int oz = ttz * T3 + 1 - HALO3;
+  const int oz = ttz * T3Z + 1 - HALO3;
   const long long start = P.tile_start[tile];
   long long end = P.tile_start[tile + 1];
   if (end > P.n_sorted_clip) end = P.n_sorted_clip;
@@ -1453,7 +1455,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
 
   const double c = EPB_C;
   const double third = P.third;
-  double *S = sS_all + warp * SROWS * SPITCH;
+  double *S = sS_all + warp * S3ROWS * SPITCH;
   double *Qd = sQd_all + warp * Q3DBL * Q3CAP;
   int *Qk = sQk_all + warp * Q3CAP;
   int *RK = sRK_all + warp * 32;
@@ -1498,7 +1500,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) push_tiled_3d(const __grid_cons
       for (int d = 0; d < 3; d++) {
         cell_r[d] = pp[d] * P.idx[d];
         cell1[d] = __double2int_rd(cell_r[d] + 0.5) + 1;
-        fast = fast && (cell1[d] - 2 >= org[d]) && (cell1[d] + 2 <= org[d] + JW3 - 1);
+        fast = fast && (cell1[d] - 2 >= org[d]) && (cell1[d] + 2 <= org[d] + (d == 2 ? JD3 : JW3) - 1);
       }
       if (!fast) {
         const int slot = atomicAdd(sSlowCount, 1);

@@ -212,7 +212,7 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   int T[3] = {1, 1, 1};
   if (nd == 1) T[0] = 256;
   else if (nd == 2) { T[0] = 16; T[1] = 16; }  // must match T2X/T2Y in push.cuh
-  else { T[0] = 8; T[1] = 8; T[2] = 8; }
+  else { T[0] = 8; T[1] = 8; T[2] = 4; }  // must match T3 / T3Z in push.cuh
   const int variant = epb_push_variant();
   if (nd == 2 && variant == 3) T[1] = 8;      // push_cell_2d<8,3>: 16x8-cell tiles
   tg.cpt = 1;
