@@ -180,8 +180,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU")
     variant = int(os.environ.get("EPB_PUSH_VARIANT", "3"))
-    ap.add_argument("--sort-interval", type=int,
-                    default=int(os.environ.get("EPB_SORT_INTERVAL", "3" if variant in (2, 3, 4) else "8")))
+    ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "0")),
+                    help="0 = the library default: 3 for the cell-owner 2D kernel, 8 otherwise")
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -190,6 +190,8 @@ def main():
             args.n = 384
         args.ppc = args.ppc or 8
     args.ppc = args.ppc or 64
+    if args.sort_interval <= 0:
+        args.sort_interval = 3 if (args.workload == "c2" and variant in (2, 3, 4)) else 8
     if args.impl == "reference":
         return run_reference(args)
     # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
