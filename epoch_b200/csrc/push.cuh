@@ -993,7 +993,9 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
   // (fused gather after a sort) the source index of the round after that is already being fetched
   const int *perm = P.perm;
   long long i, i2;      // slot of the current/next round, slot of the round after
-  long long si2 = 0;    // source index of slot i2 (perm[i2], or i2 itself without a pending permutation)
+  // source index of slot i2 (perm[i2], or i2 itself without a pending permutation).  Kept as the raw
+  // 32-bit value: widening it here would make the warp wait for the perm load in the round that issues it
+  int si2 = 0;
   bool act, act2;
   {
     const bool na = my_cnt > 0;
@@ -1014,7 +1016,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
     i2 = rbase + __popc(bal & lt_mask);
     rbase += __popc(bal);
     act2 = na && i2 < clip;
-    if (act2) si2 = perm ? (long long)perm[i2] : i2;
+    if (act2) si2 = perm ? perm[i2] : (int)i2;
   }
   for (int r = 0; r < maxcnt; r++) {
     const bool active = act;
@@ -1031,8 +1033,9 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
       i = i2;
       act = act2;
       if (act) {
-        n_w = P.ws[si2]; n_x = P.xs[0][si2]; n_y = P.xs[1][si2];
-        n_px = P.ps[0][si2]; n_py = P.ps[1][si2]; n_pz = P.ps[2][si2];
+        const long long sl = si2;
+        n_w = P.ws[sl]; n_x = P.xs[0][sl]; n_y = P.xs[1][sl];
+        n_px = P.ps[0][sl]; n_py = P.ps[1][sl]; n_pz = P.ps[2][sl];
       }
       // slot and source index of round r+2
       const bool na = my_cnt > r + 2;
@@ -1040,7 +1043,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
       i2 = rbase + __popc(bal & lt_mask);
       rbase += __popc(bal);
       act2 = na && i2 < clip;
-      if (act2) si2 = perm ? (long long)perm[i2] : i2;
+      if (act2) si2 = perm ? perm[i2] : (int)i2;
     }
     bool extras = false;
     int key = 0, dcx = 0, dcy = 0;
@@ -1140,6 +1143,8 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
           if (dir >= 0) outbox_put(P, ci, dir);
         }
         if (P.deposit) {
+          bool emit_do = false, emit_arr = false;
+          int emit_rank = 0;
           px_ = px_ + delta_x;
           py_ = py_ + delta_y;
           const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
@@ -1157,7 +1162,11 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
             // record for the next sort: (cx3, cy3) is the cell the next push gathers in
             const int nkey = ((cy3 / T2Y) * P.tg.nt[0] + (cx3 >> 4)) * (T2X * T2Y) + (cy3 % T2Y) * T2X + (cx3 & 15);
             P.key_out[ci] = nkey;
-            P.rank_out[ci] = (nkey == my_key) ? stay++ : (atomicAdd(&P.arr_cnt[nkey], 1) | EPB_RANK_ARRIVAL);
+            // the arrival counter's reply is only consumed after the deposit arithmetic below, so the
+            // round trip of the global atomic is hidden instead of stalling the warp here
+            emit_do = true;
+            emit_arr = nkey != my_key;
+            emit_rank = emit_arr ? atomicAdd(&P.arr_cnt[nkey], 1) : stay++;
           }
           key = (cy1 - oy) * TW + (cx1 - ox);
           q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
@@ -1206,6 +1215,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
             }
             if ((dcx | dcy) != 0) { extras = true; key |= 1 << 14; }
           }
+          if (emit_do) P.rank_out[ci] = emit_arr ? (emit_rank | EPB_RANK_ARRIVAL) : emit_rank;
         }
       }
     }
