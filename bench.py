@@ -181,7 +181,7 @@ def main():
                     help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU")
     variant = int(os.environ.get("EPB_PUSH_VARIANT", "3"))
     ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "0")),
-                    help="0 = the library default: 3 for the cell-owner 2D kernel, 8 otherwise")
+                    help="0 = the library default: 2 for the cell-owner 2D kernel, 8 otherwise")
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -191,7 +191,7 @@ def main():
         args.ppc = args.ppc or 8
     args.ppc = args.ppc or 64
     if args.sort_interval <= 0:
-        args.sort_interval = 3 if (args.workload == "c2" and variant in (2, 3, 4)) else 8
+        args.sort_interval = 2 if (args.workload == "c2" and variant in (2, 3, 4)) else 8
     if args.impl == "reference":
         return run_reference(args)
     # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
@@ -313,9 +313,11 @@ def main():
         achieved = (n_local * bytes_per_update / (push_ms * 1e-3)) / 1e9 if push_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "push_traffic_bytes.json")
-        if os.path.exists(tpath) and not is3d and variant in (2, 3, 4) and args.sort_interval == 3:
-            try:  # ncu dram bytes per particle (mean over the fused / plain / emitting launch cycle) x particles per launch
-                traffic = json.load(open(tpath))["dram_bytes_per_particle"]["cycle_mean"] * n_local
+        if os.path.exists(tpath) and not is3d and variant in (2, 3, 4) and args.sort_interval >= 2:
+            try:  # ncu DRAM bytes per particle of the launch mix of one sort cycle x particles per launch
+                bpp = json.load(open(tpath))["dram_bytes_per_particle"]
+                k = args.sort_interval
+                traffic = (bpp["fused_gather"] + (k - 2) * bpp["plain"] + bpp["emitting"]) / k * n_local
             except Exception:
                 traffic = None
         line = {

@@ -1029,7 +1029,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   epb_make_tiles(h->cfg, h->tg);
   // 0 = library default: the cell-owner kernel wants a fresh order (its sort is cheap), the
   // transposition kernel tolerates a stale one
-  if (h->cfg.sort_interval < 1) h->cfg.sort_interval = (h->tg.layout == 1) ? 3 : 8;
+  if (h->cfg.sort_interval < 1) h->cfg.sort_interval = (h->tg.layout == 1) ? 2 : 8;
   EPB_CUDA(h, cudaMalloc(&h->cell_count, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   EPB_CUDA(h, cudaMalloc(&h->cell_start, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   long long maxcap = 0;

@@ -70,7 +70,7 @@ typedef struct epb_config {
   int32_t rank, nranks;
   int32_t n_species;
   int32_t strict_fp;        /* 1: kernels built without FMA contraction (bit-level parity build) */
-  int32_t sort_interval;    /* steps between on-GPU counting sorts; 0 = library default (3 or 8, by kernel) */
+  int32_t sort_interval;    /* steps between on-GPU counting sorts; 0 = library default (2 or 8, by kernel) */
   int32_t field_order;      /* 0 or 2, 4, 6: finite-difference order of the Yee solver (fields.f90:32-46) */
   int32_t maxwell_solver;   /* c_maxwell_solver_* (constants.F90:173-180): 0 yee; -1 custom, 2..4 lehe_x/y/z, 5 cowan, 6 pukhov: extended B stencil, order 2 (fields.f90:51-100, epoch3d :53-162, epoch1d :48-62) */
   int32_t smooth_its;       /* smooth_currents: smooth_its passes (0 = off), current_smooth.F90:50-141 */
