@@ -1459,7 +1459,7 @@ __global__ void __launch_bounds__(P3_THREADS, 2) push_tiled_3d(const __grid_cons
   if (end > P.n_sorted_clip) end = P.n_sorted_clip;
   if (start >= end) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) *sSlowCount = 0;
+  if (tid == 0) { *sSlowCount = 0; sSlowCount[1] = 0; }  // [1]: next batch of the tile (dynamic distribution)
   for (int q = tid; q < 3 * JT3; q += P3_THREADS) sJ[q] = 0.0;
   __syncthreads();
 
@@ -1482,7 +1482,14 @@ __global__ void __launch_bounds__(P3_THREADS, 2) push_tiled_3d(const __grid_cons
   }
 
   // no software prefetch here: 16 warps per SM hide the load latency and the kernel is short of registers
-  for (long long i = start + warp * 32 + lane; i - lane < end; i += P3_THREADS) {
+  // batches are handed out dynamically: a warp that ran the wide-stencil drain takes fewer of them, so the
+  // warps of a CTA reach the final barrier together (the static split left 19 % of the samples there)
+  for (;;) {
+    int bidx = 0;
+    if (lane == 0) bidx = atomicAdd(&sSlowCount[1], 1);
+    bidx = __shfl_sync(FULL, bidx, 0);
+    const long long i = start + (long long)bidx * 32 + lane;
+    if (i - lane >= end) break;
     const bool active = i < end;
     double part_weight = 0.0, pp[3] = {0.0, 0.0, 0.0}, part_ux = 0.0, part_uy = 0.0, part_uz = 0.0;
     if (active) {
