@@ -179,6 +179,8 @@ class Deck:
         dtl = self.dt_laser()
         if dtl > 1e-50:
             dt = min(dt, dtl)
+        if self.maxwell_solver == "custom" and self.dt_multiplier < 1.0:
+            return dt          # setup.F90:657-668: dt_multiplier is overridden to 1 for the custom solver
         return self.dt_multiplier * dt
 
     def maxwell_solver_code(self) -> int:

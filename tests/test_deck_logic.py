@@ -1,0 +1,108 @@
+"""Host-side arithmetic of epoch_b200/deck.py against the reference's formulas, evaluated by hand here:
+set_dt (setup.F90:633-711; epoch1d :566-620; epoch3d :694-760), set_maxwell_solver (fields.f90 of the three
+trees), laser source planes on every face (laser.f90:338-357, :479-500)."""
+import math
+
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+
+c = D.c
+
+
+def _deck(nd, n, L, **kw):
+    return D.Deck(nd, list(n), [0.0] * nd, list(L), ["periodic"] * (2 * nd), **kw)
+
+
+@pytest.mark.parametrize("order,cfl", [(2, 1.0), (4, 6.0 / 7.0), (6, 120.0 / 149.0)])
+def test_dt_yee_orders(order, cfl):
+    dk = _deck(1, [100], [1e-5], field_order=order)
+    assert dk.dt() == 0.95 * (cfl * (1e-5 / 100) / c)
+    dk = _deck(2, [100, 50], [1e-5, 1e-5], field_order=order)
+    dx, dy = 1e-7, 2e-7
+    assert math.isclose(dk.dt(), 0.95 * cfl * dx * dy / math.sqrt(dx ** 2 + dy ** 2) / c, rel_tol=1e-15)
+    dk = _deck(3, [10, 20, 40], [1e-6] * 3, field_order=order)
+    dx, dy, dz = 1e-7, 5e-8, 2.5e-8
+    ref = 0.95 * cfl * dx * dy * dz / math.sqrt((dx * dy) ** 2 + (dy * dz) ** 2 + (dz * dx) ** 2) / c
+    assert math.isclose(dk.dt(), ref, rel_tol=1e-15)
+
+
+def test_dt_extended_solvers():
+    # epoch2d setup.F90:645-649: dt = MIN(dx, dy) / c; epoch3d :707-721
+    dk = _deck(2, [100, 50], [1e-5, 1e-5], maxwell_solver="lehe_x")
+    assert math.isclose(dk.dt(), 0.95 * 1e-7 / c, rel_tol=1e-15)
+    dk = _deck(3, [10, 20, 40], [1e-6] * 3, maxwell_solver="lehe_x")
+    dx, dy, dz = 1e-7, 5e-8, 2.5e-8
+    assert math.isclose(dk.dt(), 0.95 * min(dx, dy * dz / math.sqrt(dy ** 2 + dz ** 2)) / c, rel_tol=1e-15)
+    dk = _deck(3, [10, 20, 40], [1e-6] * 3, maxwell_solver="cowan")
+    assert math.isclose(dk.dt(), 0.95 * dz / c, rel_tol=1e-15)
+    # any_open caps dt at the Yee CFL (setup.F90:651-654)
+    dk = D.Deck(2, [100, 100], [0, 0], [1e-5, 1e-5], ["simple_laser", "open", "periodic", "periodic"],
+                maxwell_solver="pukhov")
+    assert math.isclose(dk.dt(), 0.95 * 1e-7 / math.sqrt(2.0) / c, rel_tol=1e-15)
+
+
+def test_stencil_lehe_x_2d():
+    dk = _deck(2, [100, 50], [1e-5, 1e-5], maxwell_solver="lehe_x")
+    st = dk.stencil()
+    dx, dy, dt = 1e-7, 2e-7, dk.dt()
+    r = dx / (c * dt)
+    deltax = 0.25 * (1.0 - r ** 2 * math.sin(0.5 * math.pi / r) ** 2)
+    assert st["betaxy"] == 0.125 * (dx / dy) ** 2 and st["betayx"] == 0.125
+    assert math.isclose(st["deltax"], deltax, rel_tol=1e-14)
+    assert math.isclose(st["alphax"], 1.0 - 2.0 * st["betaxy"] - 3.0 * deltax, rel_tol=1e-15)
+    assert st["alphay"] == 1.0 - 2.0 * 0.125 and st["deltay"] == 0.0 and st["alphaz"] == 1.0
+
+
+def test_stencil_pukhov_and_cowan_3d_reduce_to_yee_on_axis():
+    """alpha + 2 beta + 2 beta' + 4 gamma + 3 delta = 1 for every axis: a wave that is uniform in the two
+    other directions sees the plain Yee derivative."""
+    for solver in ("pukhov", "cowan", "lehe_x", "lehe_y", "lehe_z"):
+        dk = _deck(3, [10, 20, 40], [1e-6, 1.5e-6, 2.2e-6], maxwell_solver=solver)
+        st = dk.stencil()
+        for a, (b1, b2) in (("x", ("xy", "xz")), ("y", ("yx", "yz")), ("z", ("zx", "zy"))):
+            tot = st["alpha" + a] + 2 * st["beta" + b1] + 2 * st["beta" + b2] + 4 * st["gamma" + a] + 3 * st["delta" + a]
+            assert math.isclose(tot, 1.0, rel_tol=1e-14), (solver, a)
+
+
+def test_solver_availability_per_tree():
+    with pytest.raises(NotImplementedError):
+        _deck(1, [10], [1.0], maxwell_solver="pukhov").stencil()
+    with pytest.raises(NotImplementedError):
+        _deck(2, [10, 10], [1.0, 1.0], maxwell_solver="lehe_z").stencil()
+    assert _deck(1, [10], [1.0], maxwell_solver="lehe_x").stencil()["deltax"] != 0.0
+
+
+@pytest.mark.parametrize("side", [0, 1, 2, 3, 4, 5])
+def test_laser_source_planes(side):
+    """source1/source2 = amp * profile * sin(omega t + phase) * (cos, sin)(pol) on the plane of the face: the two
+    transverse axes in axis order, (0:n) each, lower axis fastest."""
+    n = [6, 5, 4]
+    name = ("x", "y", "z")[side // 2] + ("_min" if side % 2 == 0 else "_max")
+    las = D.Laser(name, 2.0, 3.0e15, pol_angle=0.3, profile=lambda u, v: 1.0 + u * 1e5 + 10.0 * v * 1e5,
+                  phase=lambda u, v: 0.5 * u * 1e5)
+    bcs = ["periodic"] * 6
+    bcs[side] = "simple_laser"
+    dk = D.Deck(3, n, [0.0] * 3, [6e-6, 5e-6, 4e-6], bcs, lasers=[las], t_end=1e-12)
+    assert dk.has_boundary_source(side) and not dk.has_boundary_source((side + 2) % 6)
+    s1, s2 = dk.laser_sources(0, side, 1.0e-15)
+    tr = [d for d in range(3) if d != side // 2]
+    assert s1.size == (n[tr[0]] + 1) * (n[tr[1]] + 1)
+    # element (iu, iv): coordinates x_global(i) = x_min + dx/2 + (i - 1) dx for i = 0..n
+    iu, iv = 2, 3
+    u = dk.x_global(tr[0], iu)
+    v = dk.x_global(tr[1], iv)
+    base = 2.0 * (1.0 + u * 1e5 + 10.0 * v * 1e5) * math.sin(3.0e15 * 1.0e-15 + 0.5 * u * 1e5)
+    k = iv * (n[tr[0]] + 1) + iu
+    assert math.isclose(s1[k], base * math.cos(0.3), rel_tol=1e-12)
+    assert math.isclose(s2[k], base * math.sin(0.3), rel_tol=1e-12)
+
+
+def test_smoothing_and_solver_codes():
+    dk = _deck(2, [8, 8], [1.0, 1.0], maxwell_solver="custom",
+               stencil_custom=dict(betaxy=0.1, betayx=0.05, deltax=0.02, deltay=0.01, dt=1e-10))
+    assert dk.maxwell_solver_code() == -1 and dk.dt() == 1e-10   # constants.F90:173; setup.F90:657-668
+    st = dk.stencil()
+    assert math.isclose(st["alphax"], 1.0 - 0.2 - 0.06, rel_tol=1e-15)
+    assert _deck(3, [8, 8, 8], [1.0] * 3, maxwell_solver="cowan").maxwell_solver_code() == 5
