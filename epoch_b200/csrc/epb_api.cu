@@ -829,7 +829,7 @@ int bfield_final_bcs(epb_handle *h, double dt) {
 
 int bc_allspecies(const epb_handle *h, int i) {  // deck_species_block.F90:182-199
   if (h->sp.empty()) return h->cfg.bc_field[i] == EPB_BC_PERIODIC ? EPB_BC_PERIODIC : EPB_BC_OPEN;
-  int b = h->sp[0].cfg.bc_particle[i];
+  int b = h->sp[h->bc_species >= 0 ? h->bc_species : 0].cfg.bc_particle[i];
   if (b != EPB_BC_REFLECT && b != EPB_BC_PERIODIC) b = EPB_BC_OPEN;
   return b;
 }
@@ -989,15 +989,17 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
       int b = species[s].bc_particle[i];
       if (!(b == EPB_BC_PERIODIC || b == EPB_BC_REFLECT || b == EPB_BC_OPEN))
         return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "particle boundary code %d not implemented on the device path", b);
-      if (s > 0) {
-        int a0 = species[0].bc_particle[i], a1 = b;
-        if ((a0 == EPB_BC_REFLECT) != (a1 == EPB_BC_REFLECT) || (a0 == EPB_BC_PERIODIC) != (a1 == EPB_BC_PERIODIC))
-          return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "per-species mixed particle boundaries (c_bc_mixed) not implemented");
-      }
     }
   }
   epb_handle *h = new epb_handle;
   h->cfg = *cfg;
+  {  // c_bc_mixed: do the species disagree on a particle boundary?
+    auto norm = [](int b) { return (b == EPB_BC_REFLECT || b == EPB_BC_PERIODIC) ? b : EPB_BC_OPEN; };
+    for (int s = 1; s < cfg->n_species; s++)
+      for (int i = 0; i < 2 * cfg->ndims; i++)
+        if (norm(species[s].bc_particle[i]) != norm(species[0].bc_particle[i])) h->bc_mixed = true;
+    if (cfg->n_species > 0 && getenv("EPB_FORCE_MIXED") && atoi(getenv("EPB_FORCE_MIXED"))) h->bc_mixed = true;
+  }
   const int nd = cfg->ndims;
   h->fsize = 1;
   for (int d = 0; d < 3; d++) {
@@ -1361,6 +1363,8 @@ int epb_sort(epb_handle *h) {
   return EPB_OK;
 }
 
+static int current_bcs_species(epb_handle *h, int is);
+
 int epb_push(epb_handle *h) {
   if (!h) return EPB_ERR_ARG;
   const epb_config &c = h->cfg;
@@ -1373,7 +1377,11 @@ int epb_push(epb_handle *h) {
   for (int is = 0; is < (int)h->sp.size(); is++) {
     SpeciesDev &S = h->sp[is];
     if (S.cfg.immobile) continue;
-    if (S.n == 0) {  // nothing to push, but neighbours may still send us particles
+    if (S.n == 0) {  // nothing to push, but neighbours may still send us particles (and, mixed: current)
+      if (h->bc_mixed) {
+        int rcm = current_bcs_species(h, is);
+        if (rcm) return rcm;
+      }
       int rc0 = epb_particle_exchange(h, is);
       if (rc0) return rc0;
       continue;
@@ -1436,6 +1444,10 @@ int epb_push(epb_handle *h) {
       h->ev_pool.push_back({e0, e1});
     }
     EPB_CUDA(h, cudaGetLastError());
+    if (h->bc_mixed) {  // current_bcs(species = ispecies), particles.F90:645
+      int rcm = current_bcs_species(h, is);
+      if (rcm) return rcm;
+    }
     // particle_bcs (particles.F90:648) for this species.  The outbox is shared by all
     // species, so it is drained before the next species is pushed; the reference runs
     // particle_bcs after the species loop, which is equivalent because a species' push
@@ -1447,10 +1459,10 @@ int epb_push(epb_handle *h) {
   return EPB_OK;
 }
 
-int epb_current_finish(epb_handle *h) {
-  if (!h) return EPB_ERR_ARG;
+// current_bcs -> processor_summation_bcs (boundary.F90:783-804): reflection fold, then periodic / neighbour
+// sum, per component, with the boundary codes bc_allspecies() currently answers with
+static int current_sum_bcs(epb_handle *h) {
   const epb_config &c = h->cfg;
-  // current_bcs -> processor_summation_bcs: reflection fold then periodic/neighbour sum, per component
   for (int q = 0; q < 3; q++) {
     for (int d = 0; d < c.ndims; d++)
       for (int side = 0; side < 2; side++) {
@@ -1473,8 +1485,44 @@ int epb_current_finish(epb_handle *h) {
         }
       }
   }
-  int rc = epb_halo_exchange(h, EPB_JX, 3, true);
+  return epb_halo_exchange(h, EPB_JX, 3, true);
+}
+
+// particle_clear_bcs (boundary.F90:755-779): zero everything outside 1..n of the three current arrays
+struct ClearOp { double *a[3]; int nd, n[3], sz[3]; };
+__global__ void __launch_bounds__(256) k_clear_ghosts(const __grid_constant__ ClearOp C) {
+  const size_t total = (size_t)C.sz[0] * C.sz[1] * C.sz[2];
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % C.sz[0]) + 1 - NG;
+    const int j = C.nd >= 2 ? (int)((t / C.sz[0]) % C.sz[1]) + 1 - NG : 1;
+    const int k = C.nd >= 3 ? (int)(t / ((size_t)C.sz[0] * C.sz[1])) + 1 - NG : 1;
+    const bool in = i >= 1 && i <= C.n[0] && (C.nd < 2 || (j >= 1 && j <= C.n[1])) && (C.nd < 3 || (k >= 1 && k <= C.n[2]));
+    if (!in) { C.a[0][t] = 0.0; C.a[1][t] = 0.0; C.a[2][t] = 0.0; }
+  }
+}
+// current_bcs(species) of a c_bc_mixed run, called after that species was pushed
+static int current_bcs_species(epb_handle *h, int is) {
+  h->bc_species = is;
+  int rc = current_sum_bcs(h);
+  h->bc_species = -1;
   if (rc) return rc;
+  ClearOp C;
+  for (int q = 0; q < 3; q++) C.a[q] = h->f(EPB_JX + q);
+  C.nd = h->cfg.ndims;
+  for (int k = 0; k < 3; k++) { C.n[k] = h->cfg.n[k]; C.sz[k] = h->sz[k]; }
+  k_clear_ghosts<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(C);
+  h->launches++;
+  return EPB_OK;
+}
+
+int epb_current_finish(epb_handle *h) {
+  if (!h) return EPB_ERR_ARG;
+  const epb_config &c = h->cfg;
+  int rc = EPB_OK;
+  if (!h->bc_mixed) {  // with c_bc_mixed the sums were done per species inside epb_push
+    rc = current_sum_bcs(h);
+    if (rc) return rc;
+  }
   rc = epb_halo_exchange(h, EPB_JX, 3, false);  // field_bc(jx|jy|jz, jng)
   if (rc) return rc;
   if (c.smooth_its + c.smooth_comp_its > 0) {  // smooth_current (current_smooth.F90:50-141)

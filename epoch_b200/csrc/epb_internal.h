@@ -131,6 +131,10 @@ struct epb_handle {
   double *dump_stage = nullptr;
   cudaEvent_t dump_ready = nullptr, dump_done = nullptr;
   bool dump_pending = false;
+  // c_bc_mixed (deck_species_block.F90:182-199): the species disagree on some particle boundary, so J is
+  // folded / summed / cleared after every species with that species' boundary codes (particles.F90:645)
+  bool bc_mixed = false;
+  int bc_species = -1;          // species whose codes the current exchange uses (-1: bc_allspecies)
   double *sendbuf = nullptr, *recvbuf = nullptr;  // halo + particle staging
   size_t sendbuf_elems = 0, recvbuf_elems = 0;
   void *nccl = nullptr;         // ncclComm_t

@@ -61,7 +61,7 @@ inline int nbr1(const epb_config &c, int d, int s) {
 }
 int bc_allspecies(const epb_handle *h, int i) {
   if (h->sp.empty()) return h->cfg.bc_field[i] == EPB_BC_PERIODIC ? EPB_BC_PERIODIC : EPB_BC_OPEN;
-  int b = h->sp[0].cfg.bc_particle[i];
+  int b = h->sp[h->bc_species >= 0 ? h->bc_species : 0].cfg.bc_particle[i];
   if (b != EPB_BC_REFLECT && b != EPB_BC_PERIODIC) b = EPB_BC_OPEN;
   return b;
 }

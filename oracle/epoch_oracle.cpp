@@ -114,6 +114,7 @@ struct Config {
   double st_alpha[3], st_beta[6], st_gamma[3], st_delta[3];
   // current_smooth.F90:50-141: smooth_currents with smooth_its (+ smooth_comp_its) passes over strides
   int smooth_its, smooth_comp_its, smooth_nstrides, smooth_strides[4];
+  int force_mixed;  // test hook: take the per-species current_bcs path even if all species agree
 };
 
 // random_generator.f90:23-78 (KISS), :112-173 (polar Box-Muller)
@@ -201,6 +202,7 @@ struct World {
   bool periods[3] = {false, false, false};
   int bc_field[6];
   int bc_allspecies[6];
+  bool bc_mixed = false;   // c_bc_mixed on some boundary: J is folded per species (boundary.F90:547-556, 790-796)
   double dt;
   std::vector<Rank> r;
 };
@@ -240,8 +242,9 @@ void setup_world(World &w) {
       int b = w.sp[is].bc_particle[i];
       if (b != c_bc_reflect && b != c_bc_periodic) b = c_bc_open;
       if (is == 0) w.bc_allspecies[i] = b;
-      else if (w.bc_allspecies[i] != b) w.bc_allspecies[i] = -99;  // c_bc_mixed: unsupported
+      else if (w.bc_allspecies[i] != b) { w.bc_allspecies[i] = -99; w.bc_mixed = true; }  // c_bc_mixed
     }
+  if (cf.force_mixed && !w.sp.empty()) w.bc_mixed = true;
   if (w.sp.empty())
     for (int i = 0; i < 2 * nd; i++)
       w.bc_allspecies[i] = (cf.bc_field[i] == c_bc_periodic) ? c_bc_periodic : c_bc_open;
@@ -948,10 +951,10 @@ inline double gather(const Arr &F, const double *wx, int cx, const double *wy, i
 }
 
 template <int ND>
-void push_particles(World &w) {
+void push_particles(World &w, int only = -1, bool zero_j = true) {
   const double dt = w.dt;
   for (Rank &R : w.r) {
-    for (int q = JX; q <= JZ; q++) std::fill(R.f[q].v.begin(), R.f[q].v.end(), 0.0);
+    if (zero_j) for (int q = JX; q <= JZ; q++) std::fill(R.f[q].v.begin(), R.f[q].v.end(), 0.0);
     // particles.F90:128-136, 155-167
     double fac = 1.0;
     for (int d = 0; d < ND; d++) fac *= 0.5;
@@ -974,6 +977,7 @@ void push_particles(World &w) {
     Arr &jx = R.f[JX], &jy = R.f[JY], &jz = R.f[JZ];
 
     for (size_t is = 0; is < w.sp.size(); is++) {
+      if (only >= 0 && (int)is != only) continue;
       const SpeciesCfg &S = w.sp[is];
       R.bnd_cand[is].clear();
       if (S.immobile) continue;
@@ -1291,7 +1295,8 @@ void particle_bcs(World &w) {
 }
 
 // boundary.F90:534-630: reflecting fold of J ghost cells
-void particle_reflection_bcs(World &w, int which, int flip_dir) {
+void particle_reflection_bcs(World &w, int which, int flip_dir, const int *bcs = nullptr) {
+  if (!bcs) bcs = w.bc_allspecies;
   for (Rank &R : w.r) {
     Arr &a = R.f[which];
     for (int d = 0; d < w.nd; d++) {
@@ -1309,11 +1314,11 @@ void particle_reflection_bcs(World &w, int which, int flip_dir) {
               a(s[0], s[1], s[2]) = 0.0;
             }
       };
-      if (R.is_bnd[2 * d] && w.bc_allspecies[2 * d] == c_bc_reflect) {
+      if (R.is_bnd[2 * d] && bcs[2 * d] == c_bc_reflect) {
         if (flip_dir == d) for (int i = 1; i <= NG - 1; i++) fold(i, -i, -1.0);
         else for (int i = 1; i <= NG - 1; i++) fold(i, 1 - i, +1.0);
       }
-      if (R.is_bnd[2 * d + 1] && w.bc_allspecies[2 * d + 1] == c_bc_reflect) {
+      if (R.is_bnd[2 * d + 1] && bcs[2 * d + 1] == c_bc_reflect) {
         if (flip_dir == d) for (int i = 1; i <= NG; i++) fold(nn - i, nn + i, -1.0);
         else for (int i = 1; i <= NG; i++) fold(nn + 1 - i, nn + i, +1.0);
       }
@@ -1322,7 +1327,8 @@ void particle_reflection_bcs(World &w, int which, int flip_dir) {
 }
 
 // boundary.F90:634-751: send ghost layers, add into the neighbour's interior
-void particle_periodic_bcs(World &w, int which) {
+void particle_periodic_bcs(World &w, int which, const int *bcs = nullptr) {
+  if (!bcs) bcs = w.bc_allspecies;
   std::vector<std::vector<double>> temp(w.nranks);
   for (int d = 0; d < w.nd; d++) {
     for (int pass = 0; pass < 2; pass++) {
@@ -1332,15 +1338,15 @@ void particle_periodic_bcs(World &w, int which) {
         Rank &R = w.r[rk];
         temp[rk].clear();
         int nl[2] = {nbr(R, d, -1), nbr(R, d, +1)};
-        if (R.is_bnd[2 * d] && w.bc_allspecies[2 * d] != c_bc_periodic) nl[0] = -1;
-        if (R.is_bnd[2 * d + 1] && w.bc_allspecies[2 * d + 1] != c_bc_periodic) nl[1] = -1;
+        if (R.is_bnd[2 * d] && bcs[2 * d] != c_bc_periodic) nl[0] = -1;
+        if (R.is_bnd[2 * d + 1] && bcs[2 * d + 1] != c_bc_periodic) nl[1] = -1;
         int src = pass == 0 ? nl[0] : nl[1];
         if (src < 0) continue;
         const Rank &S = w.r[src];
         // the sender must also be willing to send towards us
         int snl = pass == 0 ? nbr(S, d, +1) : nbr(S, d, -1);
         int sb = pass == 0 ? 2 * d + 1 : 2 * d;
-        if (S.is_bnd[sb] && w.bc_allspecies[sb] != c_bc_periodic) snl = -1;
+        if (S.is_bnd[sb] && bcs[sb] != c_bc_periodic) snl = -1;
         if (snl != rk) continue;
         const Arr &a = S.f[which];
         Box b = full_box(a);
@@ -1413,8 +1419,33 @@ void smooth_array(World &w, int which) {
 }
 
 // current_smooth.F90:29-45 with boundary.F90:1466-1475, 783-804
-void current_finish(World &w) {
+// current_bcs(species) with c_bc_mixed (particles.F90:645; boundary.F90:783-804, :749 particle_clear_bcs):
+// the ghost cells hold this species' current only (they are cleared after every species)
+void current_bcs_species(World &w, int is) {
+  int bcs[6];
+  for (int i = 0; i < 6; i++) {
+    int b = i < 2 * w.nd ? w.sp[is].bc_particle[i] : c_bc_open;
+    if (b != c_bc_reflect && b != c_bc_periodic) b = c_bc_open;
+    bcs[i] = b;
+  }
   for (int q = 0; q < 3; q++) {
+    particle_reflection_bcs(w, JX + q, q, bcs);
+    particle_periodic_bcs(w, JX + q, bcs);
+    for (Rank &R : w.r) {  // particle_clear_bcs: everything outside 1..n
+      Arr &a = R.f[JX + q];
+      for (int k = a.lo[2]; k < a.lo[2] + a.sz[2]; k++)
+        for (int j = a.lo[1]; j < a.lo[1] + a.sz[1]; j++)
+          for (int i = a.lo[0]; i < a.lo[0] + a.sz[0]; i++) {
+            const bool in = (i >= 1 && i <= R.n[0]) && (w.nd < 2 || (j >= 1 && j <= R.n[1])) &&
+                            (w.nd < 3 || (k >= 1 && k <= R.n[2]));
+            if (!in) a(i, j, k) = 0.0;
+          }
+    }
+  }
+}
+
+void current_finish(World &w) {
+  for (int q = 0; q < 3 && !w.bc_mixed; q++) {
     particle_reflection_bcs(w, JX + q, q);
     particle_periodic_bcs(w, JX + q);
   }
@@ -1711,19 +1742,29 @@ void orc_fields_final(void *h) {
   else update_eb_fields_final<3>(w);
 }
 // push_particles = zero J + push + deposit (+ current_bcs(species) no-op) + particle_bcs
+// push_particles with the per-species current_bcs of c_bc_mixed (particles.F90:169-646)
+static void push_all(World &w) {
+  auto one = [&](int only, bool zero) {
+    if (w.nd == 1) push_particles<1>(w, only, zero);
+    else if (w.nd == 2) push_particles<2>(w, only, zero);
+    else push_particles<3>(w, only, zero);
+  };
+  if (!w.bc_mixed) { one(-1, true); return; }
+  if (w.sp.empty()) { one(-1, true); return; }
+  for (size_t is = 0; is < w.sp.size(); is++) {
+    one((int)is, is == 0);
+    current_bcs_species(w, (int)is);
+  }
+}
 void orc_push(void *h) {
   World &w = *(World *)h;
-  if (w.nd == 1) push_particles<1>(w);
-  else if (w.nd == 2) push_particles<2>(w);
-  else push_particles<3>(w);
+  push_all(w);
   particle_bcs(w);
 }
 // push without the trailing particle_bcs (for kernel-level parity checks)
 void orc_push_only(void *h) {
   World &w = *(World *)h;
-  if (w.nd == 1) push_particles<1>(w);
-  else if (w.nd == 2) push_particles<2>(w);
-  else push_particles<3>(w);
+  push_all(w);
 }
 void orc_particle_bcs(void *h) { particle_bcs(*(World *)h); }
 void orc_setup_bc_lists(void *h) { setup_bc_lists(*(World *)h); }

@@ -41,6 +41,10 @@ def make_deck(name, world):
         dk.field_order = 4
         dk.smooth_currents, dk.smooth_iterations, dk.smooth_compensation, dk.smooth_strides = True, 2, True, (1, 2)
         return dk, 8, 1e-12
+    if name == "mixed2d":    # c_bc_mixed: electrons reflect, protons leave (per-species current sums across ranks)
+        dk = decks.thermal(2, (48, 40), ppc=5, temp_k=4.0e8, nproc=(world, 1, 1), bc="reflect", two_species=True)
+        dk.species[1].bc_particle = ["open"] * 4
+        return dk, 8, 1e-12
     if name == "laser2d_y":   # laser on y_min, decomposed along y and x
         return decks.laser2d_y(nproc=(1, world, 1) if world < 4 else (2, world // 2, 1)), 40, 1e-12
     if name == "laser2d":

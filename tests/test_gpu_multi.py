@@ -36,7 +36,7 @@ def _run(name, world):
         assert p.returncode == 0, f"rank {r} failed:\n{out[-3000:]}"
 
 
-@pytest.mark.parametrize("name", ["thermal2d_x", "thermal2d_y", "thermal1d", "thermal3d", "reflect2d", "foil2d", "laser2d", "solver2d", "laser2d_y"])
+@pytest.mark.parametrize("name", ["thermal2d_x", "thermal2d_y", "thermal1d", "thermal3d", "reflect2d", "foil2d", "laser2d", "solver2d", "laser2d_y", "mixed2d"])
 def test_two_ranks(name):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")

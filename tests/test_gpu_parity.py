@@ -226,3 +226,20 @@ def test_relativistic_plasma_many_movers(ndims, n, sort_interval):
         # J differs from the oracle at the 1e-16 level after the first deposit (summation order), so the
         # state is compared to 1e-9 of each column's scale, as in test_ten_steps_thermal
         assert np.all(np.abs(a - b) <= 1e-9 * np.max(np.abs(b), axis=0))
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (32, 24)), (3, (10, 9, 8))])
+def test_mixed_species_boundaries(ndims, n):
+    """c_bc_mixed (deck_species_block.F90:182-199): electrons are reflected, protons leave through open
+    boundaries, so J is folded / summed / cleared after every species with that species' codes
+    (particles.F90:645, boundary.F90:547-556, :749, :790-796)."""
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=4.0e8, bc="reflect", two_species=True)
+    dk.species[1].bc_particle = ["open"] * (2 * ndims)
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 8)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+    for isp in range(2):
+        assert sim.count(isp) == o.count(0, isp)
+        assert np.array_equal(sim.cell_counts(isp), o.cell_counts(0, isp))
+    assert sim.count(1) < o.get_particles(0, 1).shape[0] + 1 and sim.count(0) == dk.species[0].npart_per_cell * int(np.prod(n))

@@ -115,3 +115,26 @@ def test_decomposed_matches_single_rank_fields():
         loc = o4.interior(r, "ey")[0]
         ref = full[y0:y0 + loc.shape[0], x0:x0 + loc.shape[1]]
         assert np.allclose(loc, ref, rtol=0, atol=1e-9 * np.abs(full).max())
+
+
+@pytest.mark.parametrize("bc", ["reflect", "periodic"])
+@pytest.mark.parametrize("nproc", [(1, 1, 1), (2, 2, 1)])
+def test_per_species_current_bcs_are_consistent(bc, nproc):
+    """c_bc_mixed path (current_bcs per species + particle_clear_bcs, particles.F90:645, boundary.F90:783-804):
+    forced on a deck whose species agree, it must give the fields of the ordinary path (interior cells; the
+    ghost cells of J are cleared in the mixed path only) to summation-order round-off."""
+    from epoch_b200 import deck as D
+    from tests import decks
+
+    def run(force):
+        dk = decks.thermal(2, (24, 20), ppc=5, temp_k=4.0e8, bc=bc, two_species=True, nproc=nproc)
+        dk.force_mixed_bc = force
+        o = Oracle(dk)
+        o.auto_load()
+        D.run(dk, o, list(range(o.nranks)), None, max_steps=6)
+        return o
+    a, b = run(False), run(True)
+    for f in ("ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz"):
+        for r in range(a.nranks):
+            x, y = a.interior(r, f), b.interior(r, f)
+            assert np.max(np.abs(x - y)) <= 1e-13 * max(np.max(np.abs(x)), 1e-300), (f, r)
