@@ -8,19 +8,25 @@
 // src/include/triangle/{gx,hx_dcell,e_part,b_part}.inc; boundary classification
 // follows boundary.F90:1064-1433 (no thermal / CPML).
 //
-// Two kernels:
-//  * push_generic<ND>: any particle range; gathers E/B through the read-only path
-//    and deposits with native global FP64 reductions (RED.E.ADD.F64).  Used for 1D
-//    and 3D, for the unsorted tail (arrivals since the last sort) and as the
-//    per-particle fallback of the tiled kernel.
-//  * push_tiled_2d: one CTA per 16x16-cell tile of the cell-sorted layout.  The
-//    E/B tile (+3 halo cells) is staged in shared memory, J is accumulated in a
-//    shared tile and flushed once with global reductions.  Because the particle
-//    range is cell-ordered, the 32 lanes of a warp mostly sit in one or two cells:
-//    their 3x3x3 deposit values are summed across the warp with a transposing
-//    butterfly (31 shuffles) and only 27 lanes issue one shared-memory update
-//    each, instead of 27 CAS loops per particle (shared FP64 atomicAdd is an
-//    ATOMS.CAST.SPIN loop on sm_100a).
+// Kernels:
+//  * push_cell_2d<CTY,MINB> (default in 2D): one CTA per 16xCTY-cell tile, one warp per 16x2-cell
+//    group, one LANE per CELL.  The particles of a group are stored interleaved by their rank in
+//    the cell (sort.cu), so a round of a warp is one coalesced load; a lane keeps the 21
+//    non-cancelling deposit sums of its cell's 3x3 stencil in registers for the whole tile and
+//    touches shared memory for the deposit only when it flushes them.  It also emits the records
+//    the next sort is built from and applies the previous sort's permutation (fused gather).
+//  * push_tiled_2d<V21> (EPB_PUSH_VARIANT=0/1): one CTA per 16x16-cell tile of the cell-major
+//    layout, one lane per particle; the 27 (21) deposit values of the lanes that share a cell are
+//    summed through a per-warp transposition scratch, one shared update per (cell, value).
+//  * push_tiled_3d: one CTA per 8x8x4-cell tile, J in shared memory, E/B through the read-only
+//    path; lanes grouped by cell, plane-by-plane transposed reduction of the 54 values.
+//  * push_generic<ND>: any particle range, fields through the read-only path, deposit with
+//    global FP64 reductions (RED.E.ADD.F64).  1D, the unsorted tail (arrivals since the last
+//    sort) and the per-particle fallback of the tiled kernels (push_one).
+// In all tiled kernels a particle whose nearest cell moved by one cell along one axis keeps its
+// core in the fast path (shifted weights) and only the values outside the core are queued
+// (drain_edge / drain_edge_3d); shared FP64 atomicAdd is an ATOMS.CAST.SPIN loop on sm_100a, so
+// shared updates per particle are what every kernel here avoids.
 #pragma once
 #include <cstdlib>
 
