@@ -243,3 +243,39 @@ def test_mixed_species_boundaries(ndims, n):
         assert sim.count(isp) == o.count(0, isp)
         assert np.array_equal(sim.cell_counts(isp), o.cell_counts(0, isp))
     assert sim.count(1) < o.get_particles(0, 1).shape[0] + 1 and sim.count(0) == dk.species[0].npart_per_cell * int(np.prod(n))
+
+
+@pytest.mark.parametrize("n,axis", [((64, 16), 0), ((16, 64), 1)])
+def test_plasma_oscillation_frequency_gpu(n, axis):
+    """The CUDA path alone over 600 steps (300 emitted sorts, performance build): a cold plasma rings at
+    w_p within 0.5 % (tests/test_plasma_oscillation.py pins the oracle on the same physics)."""
+    import math
+    from epoch_b200.pic import Simulation
+    from tests.test_plasma_oscillation import DENSITY, WP
+    dx = 8.0e-8
+    sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=40, density=DENSITY, temp=(0.0, 0.0, 0.0))]
+    dk = D.Deck(2, list(n), [0.0, 0.0], [dx * n[0], dx * n[1]], ["periodic"] * 4, species=sp)
+    from oracle.oracle import Oracle
+    o = Oracle(dk)
+    o.auto_load()                                   # the loader only; the run below is CUDA alone
+    p = o.get_particles(0, 0)
+    kw = 2.0 * math.pi / (dx * n[axis])
+    p[:, 2 + axis] = D.m0 * 1.0e-3 * D.c * np.sin(kw * p[:, axis])
+    sim = Simulation(dk, strict_fp=False, sort_interval=0, capacity_factor=1.5)
+    sim.upload_species(0, p)
+    sim.init()
+    dt = dk.dt()
+    ng = 5
+    basis = np.sin(kw * (dk.grid_min(axis) + np.arange(n[axis]) * dx + dx / 2))
+    amp, ts = [], []
+    for s_ in range(600):
+        sim.step()
+        e = sim.download_field(("ex", "ey")[axis])[0, ng:-ng, ng:-ng]
+        amp.append(float(np.sum(e * (basis[None, :] if axis == 0 else basis[:, None]))))
+        ts.append((s_ + 1) * dt)
+    amp, ts = np.array(amp), np.array(ts)
+    zc = np.where(np.sign(amp[:-1]) != np.sign(amp[1:]))[0]
+    tz = ts[zc] + (ts[zc + 1] - ts[zc]) * amp[zc] / (amp[zc] - amp[zc + 1])
+    w = math.pi / float(np.mean(np.diff(tz)))
+    assert len(tz) >= 4 and abs(w / WP - 1.0) < 5.0e-3, (w, WP)
+    assert sim.count(0) == p.shape[0]

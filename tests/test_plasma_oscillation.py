@@ -1,0 +1,59 @@
+"""Physics pin of the particle half of the oracle (push + gather + Esirkepov deposit + field solve):
+a cold uniform electron plasma with a small sinusoidal velocity perturbation rings at the plasma
+frequency w_p = sqrt(n e^2 / (eps0 m)), whatever the direction of the wave.  The reference's own
+particle tests only draw plots (epoch1d/tests/test_landau.py:83-86, test_twostream.py:84-87); BASELINE's
+north star asks for "linear growth rates within 1 %" as the long-run criterion, and this is the simplest
+member of that family: the measured frequency must lie within 0.5 % of w_p (the finite time step shifts
+it by (w_p dt)^2 / 24 ~ 1e-4, the triangle shape function by ~ -(k dx)^2 / 8 ~ -1e-3)."""
+import math
+
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from oracle.oracle import Oracle
+
+DENSITY = 1.0e25
+WP = math.sqrt(DENSITY * D.q0 ** 2 / (D.epsilon0 * D.m0))
+
+
+def _run(ndims, n, axis, nsteps=440, ppc=40):
+    dx = 8.0e-8
+    sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=ppc, density=DENSITY, temp=(0.0, 0.0, 0.0))]
+    dk = D.Deck(ndims, list(n), [0.0] * ndims, [dx * k for k in n], ["periodic"] * (2 * ndims), species=sp)
+    o = Oracle(dk)
+    o.auto_load()
+    L = dx * n[axis]
+    kw = 2.0 * math.pi / L
+    p = o.get_particles(0, 0)
+    v0 = 1.0e-3 * D.c
+    p[:, ndims + axis] = D.m0 * v0 * np.sin(kw * p[:, axis])     # columns: pos(ndims), px, py, pz, w
+    o.set_particles(0, 0, p)
+    o.init()
+    dt = dk.dt()
+    ng = 5
+    comp = ("ex", "ey", "ez")[axis]
+    x_c = dk.grid_min(axis) + np.arange(n[axis]) * dx
+    # E_axis sits half a cell up along its own axis (setup.F90:124-134)
+    basis = np.sin(kw * (x_c + dx / 2))
+    shape = [1, 1, 1]
+    shape[2 - axis] = -1
+    amp, ts = [], []
+    nsteps = int(nsteps * math.sqrt(ndims)) + 1    # dt shrinks with the Yee CFL of the dimensionality
+    for s in range(nsteps):
+        o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+        e = o.interior(0, comp)
+        amp.append(float(np.sum(e * basis.reshape(shape))))
+        ts.append((s + 1) * dt)
+    amp, ts = np.array(amp), np.array(ts)
+    zc = np.where(np.sign(amp[:-1]) != np.sign(amp[1:]))[0]
+    tz = ts[zc] + (ts[zc + 1] - ts[zc]) * amp[zc] / (amp[zc] - amp[zc + 1])
+    assert len(tz) >= 4, "not enough oscillations"
+    return math.pi / float(np.mean(np.diff(tz))), dt
+
+
+@pytest.mark.parametrize("ndims,n,axis", [(1, (64,), 0), (2, (64, 6), 0), (2, (6, 64), 1), (3, (6, 6, 48), 2)])
+def test_cold_plasma_oscillation_frequency(ndims, n, axis):
+    w, dt = _run(ndims, n, axis, ppc=40 if ndims < 3 else 8)
+    assert WP * dt < 0.08
+    assert abs(w / WP - 1.0) < 5.0e-3, (w, WP, w / WP)
