@@ -871,6 +871,8 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
   P.cmratio = P.part_q * dtfac * P.ipart_mc;
   P.ccmratio = cc * P.cmratio;
   P.deposit = !S.cfg.zero_current;
+  P.hc_push = c.hc_push ? 1 : 0;
+  P.hc_alpha = 0.5 * P.part_q * dt / S.cfg.mass;
   P.tile_start = S.tile_start;
   P.cell_start = S.cell_start;
   P.emit = 0;
@@ -1390,7 +1392,9 @@ int epb_push(epb_handle *h) {
     fill_push_params(h, is, P);
     auto launch = c.strict_fp ? epb_launch_push_strict : epb_launch_push_fast;
     static const int no3d = getenv("EPB_NO_TILED_3D") ? atoi(getenv("EPB_NO_TILED_3D")) : 0;
-    const bool tiled = (c.ndims == 2) || (c.ndims == 3 && !no3d);
+    // HC_PUSH builds of the reference: the tiled kernels hold the Boris gamma only, every particle takes
+    // push_generic<ND, true>
+    const bool tiled = !c.hc_push && ((c.ndims == 2) || (c.ndims == 3 && !no3d));
     long long sorted = S.n_sorted < S.n ? S.n_sorted : S.n;
     // layout 1: the last push before a sort also records every particle's place in the next
     // order, so that sort needs neither a key pass nor rank atomics (sort.cu)

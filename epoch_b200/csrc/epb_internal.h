@@ -42,7 +42,9 @@ struct PushParams {
   double kfc[3];           // idty/idtx/idxy (2D), idtyz/idtxz/idtxy (3D), idtf/idxf (1D)
   // species (particles.F90:251-256)
   double part_q, part_mc, ipart_mc, cmratio, ccmratio;
+  double hc_alpha;         // HC_PUSH: alpha = 0.5 * part_q * dt / part_m (particles.F90:390)
   int deposit;
+  int hc_push;             // Higuera-Cary rotation: every particle goes through push_generic<ND, true>
   // particle SoA
   double *x[3];
   double *p[3];

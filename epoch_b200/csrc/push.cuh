@@ -152,7 +152,7 @@ __device__ __forceinline__ double gather_g(const PushParams &P, const double *__
 
 // One particle, everything through global memory.  Mirrors the oracle routine
 // push_particles<ND> line by line.
-template <int ND>
+template <int ND, bool HC = false>
 __device__ __noinline__ void push_one(const PushParams &P, long long i) {
   const double c = EPB_C;
   const double part_weight = P.w[i];
@@ -203,7 +203,19 @@ __device__ __noinline__ void push_one(const PushParams &P, long long i) {
   double uxm = part_ux + cmratio * ex_part;
   double uym = part_uy + cmratio * ey_part;
   double uzm = part_uz + cmratio * ez_part;
-  gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+  if (HC) {  // particles.F90:386-398 (-DHC_PUSH), Higuera & Cary, Phys. Plasmas 24, 052104
+    gamma_rel = uxm * uxm + uym * uym + uzm * uzm + 1.0;
+    const double beta_x = P.hc_alpha * bx_part;
+    const double beta_y = P.hc_alpha * by_part;
+    const double beta_z = P.hc_alpha * bz_part;
+    const double beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z;
+    const double sigma = gamma_rel - beta2;
+    const double beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm;
+    gamma_rel = sigma + sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u));
+    gamma_rel = sqrt(0.5 * gamma_rel);
+  } else {
+    gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+  }
   root = P.ccmratio / gamma_rel;
   double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
   double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
@@ -356,11 +368,11 @@ __device__ __noinline__ void push_one(const PushParams &P, long long i) {
   }
 }
 
-template <int ND>
+template <int ND, bool HC = false>
 __global__ void __launch_bounds__(256) push_generic(const __grid_constant__ PushParams P) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = P.first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.last; i += stride)
-    push_one<ND>(P, i);
+    push_one<ND, HC>(P, i);
 }
 
 // ---------------------------------------------------------------------------
@@ -1820,7 +1832,11 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
   if (cnt <= 0) return;
   long long blocks = (cnt + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
-  if (nd == 1) push_generic<1><<<(int)blocks, 256, 0, s>>>(P);
+  if (P.hc_push) {
+    if (nd == 1) push_generic<1, true><<<(int)blocks, 256, 0, s>>>(P);
+    else if (nd == 2) push_generic<2, true><<<(int)blocks, 256, 0, s>>>(P);
+    else push_generic<3, true><<<(int)blocks, 256, 0, s>>>(P);
+  } else if (nd == 1) push_generic<1><<<(int)blocks, 256, 0, s>>>(P);
   else if (nd == 2) push_generic<2><<<(int)blocks, 256, 0, s>>>(P);
   else push_generic<3><<<(int)blocks, 256, 0, s>>>(P);
   (*launches)++;

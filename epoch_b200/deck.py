@@ -100,6 +100,7 @@ class Deck:
     smooth_iterations: int = 1
     smooth_compensation: bool = False
     smooth_strides: Sequence[int] = (1,)    # 'auto' = (1, 2, 3, 4)
+    hc_push: bool = False                   # build flag -DHC_PUSH (Makefile:264): Higuera-Cary rotation, particles.F90:386-398
 
     # -- grid (setup.F90:162-204) ------------------------------------------
     def dx(self, d: int) -> float:

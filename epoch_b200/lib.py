@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32), ("n_species", C.c_int32),
         ("strict_fp", C.c_int32), ("sort_interval", C.c_int32), ("field_order", C.c_int32),
         ("maxwell_solver", C.c_int32), ("smooth_its", C.c_int32), ("smooth_comp_its", C.c_int32),
-        ("smooth_strides", C.c_int32),
+        ("smooth_strides", C.c_int32), ("hc_push", C.c_int32),
         ("dx", C.c_double * 3), ("dt", C.c_double), ("grid_min_local", C.c_double * 3),
         ("min_local", C.c_double * 3), ("max_local", C.c_double * 3),
         ("gmin", C.c_double * 3), ("gmax", C.c_double * 3),

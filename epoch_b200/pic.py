@@ -120,6 +120,7 @@ class Simulation:
         cfg.dt = deck.dt()
         cfg.field_order = int(deck.field_order)
         cfg.maxwell_solver = deck.maxwell_solver_code()
+        cfg.hc_push = int(getattr(deck, "hc_push", False))
         if deck.smooth_currents:
             cfg.smooth_its = int(deck.smooth_iterations)
             cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0

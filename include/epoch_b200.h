@@ -76,6 +76,8 @@ typedef struct epb_config {
   int32_t smooth_its;       /* smooth_currents: smooth_its passes (0 = off), current_smooth.F90:50-141 */
   int32_t smooth_comp_its;  /* smooth_compensation: 0 or 1 */
   int32_t smooth_strides;   /* up to 4 strides (1..5), one per nibble, low nibble first; 0 = stride 1 */
+  int32_t hc_push;          /* -DHC_PUSH: Higuera-Cary gamma in the momentum rotation (particles.F90:386-398); fills the
+                               former padding word before dx, sizeof(epb_config) is unchanged */
   double dx[3];             /* dx, dy, dz */
   double dt;
   double grid_min_local[3]; /* x_grid_min_local ... (cell centre of local cell 1) */

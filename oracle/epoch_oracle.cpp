@@ -115,6 +115,7 @@ struct Config {
   // current_smooth.F90:50-141: smooth_currents with smooth_its (+ smooth_comp_its) passes over strides
   int smooth_its, smooth_comp_its, smooth_nstrides, smooth_strides[4];
   int force_mixed;  // test hook: take the per-species current_bcs path even if all species agree
+  int hc_push;      // -DHC_PUSH: Higuera-Cary gamma in the rotation (particles.F90:386-398)
 };
 
 // random_generator.f90:23-78 (KISS), :112-173 (polar Box-Muller)
@@ -1039,7 +1040,20 @@ void push_particles(World &w, int only = -1, bool zero_j = true) {
         double uxm = part_ux + cmratio * ex_part;
         double uym = part_uy + cmratio * ey_part;
         double uzm = part_uz + cmratio * ez_part;
-        gamma_rel = std::sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+        if (w.cfg.hc_push) {  // :386-398 (1D :345-357, 3D :423-435), Higuera & Cary, Phys. Plasmas 24, 052104
+          gamma_rel = uxm * uxm + uym * uym + uzm * uzm + 1.0;
+          const double alpha = 0.5 * part_q * dt / S.mass;
+          const double beta_x = alpha * bx_part;
+          const double beta_y = alpha * by_part;
+          const double beta_z = alpha * bz_part;
+          const double beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z;
+          const double sigma = gamma_rel - beta2;
+          const double beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm;
+          gamma_rel = sigma + std::sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u));
+          gamma_rel = std::sqrt(0.5 * gamma_rel);
+        } else {
+          gamma_rel = std::sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+        }
         root = ccmratio / gamma_rel;
         double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
         double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;

@@ -24,7 +24,7 @@ class _Config(C.Structure):
         ("st_alpha", C.c_double * 3), ("st_beta", C.c_double * 6), ("st_gamma", C.c_double * 3),
         ("st_delta", C.c_double * 3),
         ("smooth_its", C.c_int), ("smooth_comp_its", C.c_int), ("smooth_nstrides", C.c_int),
-        ("smooth_strides", C.c_int * 4), ("force_mixed", C.c_int),
+        ("smooth_strides", C.c_int * 4), ("force_mixed", C.c_int), ("hc_push", C.c_int),
     ]
 
 
@@ -109,6 +109,7 @@ class Oracle:
         for i, k in enumerate(("betaxy", "betaxz", "betayx", "betayz", "betazx", "betazy")):
             cfg.st_beta[i] = st[k]
         cfg.force_mixed = int(getattr(deck, "force_mixed_bc", False))
+        cfg.hc_push = int(getattr(deck, "hc_push", False))
         if getattr(deck, "smooth_currents", False):
             cfg.smooth_its = int(deck.smooth_iterations)
             cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
