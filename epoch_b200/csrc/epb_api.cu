@@ -394,6 +394,55 @@ __global__ void __launch_bounds__(256) k_cell_counts(const __grid_constant__ Cou
   }
 }
 
+// Diagnostics moments: io/calc_df.F90 calc_number_density :689-757, calc_charge_density :608-685,
+// calc_mass_density :35-110 (1D/3D trees alike).  particle_to_grid.inc (division by dx, not *idx) with the
+// normalised triangle weights of include/triangle/gxfac.inc; data(cell+ix, ...) += gx*gy*gz*wdata.
+struct MomentOp {
+  const double *x[3], *w;
+  long long n;
+  int nd, sz[3];
+  double gmin[3], dx[3];
+  double scale;    // part_q (charge density), part_m (mass density)
+  int use_scale;   // 0: number density, wdata = weight
+  double *out;
+};
+__global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp M) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (long long)gridDim.x * blockDim.x) {
+    int cell[3] = {1, 1, 1};
+    double g[3][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
+    bool ok = true;
+    for (int d = 0; d < M.nd; d++) {
+      const double cell_r = (M.x[d][i] - M.gmin[d]) / M.dx[d];
+      const int cx = __double2int_rd(cell_r + 0.5);
+      const double cf = (double)cx - cell_r;
+      cell[d] = cx + 1;
+      const double c2 = cf * cf;
+      g[d][0] = 0.5 * (0.25 + c2 + cf);
+      g[d][1] = 0.75 - c2;
+      g[d][2] = 0.5 * (0.25 + c2 - cf);
+      if (cell[d] - 1 < 1 - NG || cell[d] + 1 > M.sz[d] - NG) ok = false;  // outside the allocated extent
+    }
+    if (!ok) continue;
+    const double wdata = M.use_scale ? M.scale * M.w[i] : M.w[i];
+    if (M.nd == 1) {
+      for (int ix = -1; ix <= 1; ix++) atomicAdd(M.out + fofs(M.sz, 1, cell[0] + ix, 1, 1), g[0][ix + 1] * wdata);
+    } else if (M.nd == 2) {
+      for (int iy = -1; iy <= 1; iy++)
+        for (int ix = -1; ix <= 1; ix++)
+          atomicAdd(M.out + fofs(M.sz, 2, cell[0] + ix, cell[1] + iy, 1), g[0][ix + 1] * g[1][iy + 1] * wdata);
+    } else {
+      for (int iz = -1; iz <= 1; iz++)
+        for (int iy = -1; iy <= 1; iy++)
+          for (int ix = -1; ix <= 1; ix++)
+            atomicAdd(M.out + fofs(M.sz, 3, cell[0] + ix, cell[1] + iy, cell[2] + iz),
+                      g[0][ix + 1] * g[1][iy + 1] * g[2][iz + 1] * wdata);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_scale(double *a, size_t n, double s) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) a[t] = a[t] * s;
+}
+
 // Device-side uniform thermal loader (stands in for auto_load on benchmark-size runs).
 struct LoadOp {
   double *x[3], *p[3], *w;
@@ -1012,8 +1061,8 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   h->plane = (size_t)h->sz[1] * h->sz[2];
   EPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
-  // ex..jz, plus the three work arrays of smooth_current when smoothing is on (field ids 9..11)
-  const int nfields = cfg->smooth_its + cfg->smooth_comp_its > 0 ? 12 : 9;
+  // ex..jz, one work array (field id 9: epb_calc_moment), plus two more when smooth_current is on (ids 9..11)
+  const int nfields = cfg->smooth_its + cfg->smooth_comp_its > 0 ? 12 : 10;
   EPB_CUDA(h, cudaMalloc(&h->fields, nfields * h->fsize * sizeof(double)));
   EPB_CUDA(h, cudaMemsetAsync(h->fields, 0, nfields * h->fsize * sizeof(double), h->stream));
   EPB_CUDA(h, cudaMalloc(&h->snap, 12 * h->plane * sizeof(double)));
@@ -1602,6 +1651,111 @@ int epb_kinetic_energy(epb_handle *h, int is, double *out) {
   }
   EPB_CUDA(h, cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPB_OK;
+}
+
+// calc_boundary (io/calc_df.F90:24-31) = processor_summation_bcs without flip_direction on the work array:
+// reflecting fold (no sign change), then the periodic / neighbour sum (boundary.F90:783-804)
+static int moment_sum_bcs(epb_handle *h, int f) {
+  const epb_config &c = h->cfg;
+  for (int d = 0; d < c.ndims; d++)
+    for (int side = 0; side < 2; side++) {
+      const int bd = 2 * d + side;
+      if (c.is_boundary[bd] && bc_allspecies(h, bd) == EPB_BC_REFLECT) {
+        FoldOp M;
+        M.a = h->f(f);
+        M.nd = c.ndims;
+        size_t total = 1;
+        for (int k = 0; k < 3; k++) {
+          M.sz[k] = h->sz[k];
+          M.n[k] = c.n[k];
+          if (k < c.ndims && k != d) total *= h->sz[k];
+        }
+        M.d = d;
+        M.is_max = side;
+        M.flip = 0;
+        k_jfold<<<nblocks(total), 256, 0, h->stream>>>(M);
+        h->launches++;
+      }
+    }
+  return epb_halo_exchange(h, f, 1, true);
+}
+
+int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
+  if (!h || !host || kind < 0 || kind > 2 || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
+  const epb_config &c = h->cfg;
+  const int WK = 9;
+  double *wk = h->f(WK);
+  EPB_CUDA(h, cudaMemsetAsync(wk, 0, h->fsize * sizeof(double), h->stream));
+  double idx;
+  if (kind == EPB_MOMENT_NUMBER_DENSITY) {  // vol = dx * dy; idx = 1 / vol
+    double vol = c.dx[0];
+    for (int d = 1; d < c.ndims; d++) vol = vol * c.dx[d];
+    idx = 1.0 / vol;
+  } else {                                  // idx = 1 / dx / dy
+    idx = 1.0 / c.dx[0];
+    for (int d = 1; d < c.ndims; d++) idx = idx / c.dx[d];
+  }
+  const bool spec_sum = ispecies < 0;
+  for (int is = spec_sum ? 0 : ispecies; is < (spec_sum ? (int)h->sp.size() : ispecies + 1); is++) {
+    SpeciesDev &S = h->sp[is];
+    if (spec_sum && S.cfg.zero_current) continue;  // tracers are left out of a species sum
+    if (S.n > 0) {
+      MomentOp M;
+      for (int d = 0; d < 3; d++) {
+        M.x[d] = S.buf[S.cur][d];
+        M.sz[d] = h->sz[d];
+        M.gmin[d] = c.grid_min_local[d];
+        M.dx[d] = c.dx[d];
+      }
+      M.w = S.buf[S.cur][6];
+      M.n = S.n;
+      M.nd = c.ndims;
+      M.use_scale = kind != EPB_MOMENT_NUMBER_DENSITY;
+      M.scale = kind == EPB_MOMENT_CHARGE_DENSITY ? S.cfg.charge : S.cfg.mass;
+      M.out = wk;
+      k_moment<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
+      h->launches++;
+    }
+    if (h->bc_mixed) {  // calc_boundary(data_array, ispecies) + particle_clear_bcs
+      h->bc_species = is;
+      int rc = moment_sum_bcs(h, WK);
+      h->bc_species = -1;
+      if (rc) return rc;
+      ClearOp C;
+      for (int q = 0; q < 3; q++) C.a[q] = wk;
+      C.nd = c.ndims;
+      for (int k = 0; k < 3; k++) { C.n[k] = c.n[k]; C.sz[k] = h->sz[k]; }
+      k_clear_ghosts<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(C);
+      h->launches++;
+    }
+  }
+  if (!h->bc_mixed) {  // calc_boundary(data_array)
+    int rc = moment_sum_bcs(h, WK);
+    if (rc) return rc;
+  }
+  k_scale<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(wk, h->fsize, idx);
+  h->launches++;
+  for (int bd = 0; bd < 2 * c.ndims; bd++) {  // field_zero_gradient(data_array, c_stagger_centre, bd)
+    if (c.bc_field[bd] == EPB_BC_PERIODIC || !c.is_boundary[bd]) continue;
+    MirrorOp M;
+    M.nd = c.ndims;
+    M.d = bd / 2;
+    M.is_max = bd & 1;
+    M.sign = 1.0;
+    size_t total = 1;
+    for (int d = 0; d < 3; d++) {
+      M.sz[d] = h->sz[d];
+      M.n[d] = c.n[d];
+      if (d < c.ndims && d != M.d) total *= h->sz[d];
+    }
+    for (int q = 0; q < 3; q++) { M.f[q] = wk; M.stag[q] = 0; }  // one array: the copy is idempotent
+    k_mirror<<<nblocks(total), 256, 0, h->stream>>>(M);
+    h->launches++;
+  }
+  EPB_CUDA(h, cudaMemcpyAsync(host, wk, h->fsize * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  EPB_CUDA(h, cudaGetLastError());
   return EPB_OK;
 }
 

@@ -261,6 +261,15 @@ class Simulation:
         self._chk(self.L.epb_kinetic_energy(self._h, isp, C.byref(out)))
         return out.value
 
+    MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2}
+
+    def moment(self, kind: str, isp: int = -1):
+        """calc_number_density / calc_charge_density / calc_mass_density (io/calc_df.F90) computed on the device;
+        isp = -1 sums all species.  Returns the array with ghost cells, like download_field."""
+        a = np.empty(self.shape, dtype=np.float64)
+        self._chk(self.L.epb_calc_moment(self._h, self.MOMENTS[kind], isp, a.ctypes.data))
+        return a
+
     def download_field_into(self, name: str, host_ptr: int):
         """D2H of one field array (with ghosts) into caller-owned (e.g. pinned) host memory."""
         self._chk(self.L.epb_download_field(self._h, _lib.FIELD_NAMES.index(name), C.c_void_p(host_ptr)))

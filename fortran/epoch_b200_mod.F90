@@ -45,6 +45,7 @@ MODULE epoch_b200_mod
     INTEGER(C_INT32_T) :: smooth_its
     INTEGER(C_INT32_T) :: smooth_comp_its
     INTEGER(C_INT32_T) :: smooth_strides
+    INTEGER(C_INT32_T) :: hc_push
     REAL(C_DOUBLE) :: dx(3)
     REAL(C_DOUBLE) :: dt
     REAL(C_DOUBLE) :: grid_min_local(3)
@@ -182,6 +183,14 @@ MODULE epoch_b200_mod
       TYPE(C_PTR), VALUE :: handle
       INTEGER(C_INT) :: rc
     END FUNCTION
+    ! kind: 0 number density, 1 charge density, 2 mass density; ispecies = -1: all species
+    FUNCTION epb_calc_moment(handle, kind, ispecies, host) BIND(C, NAME='epb_calc_moment') RESULT(rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: kind, ispecies
+      TYPE(C_PTR), VALUE :: host
+      INTEGER(C_INT) :: rc
+    END FUNCTION
   END INTERFACE
 
   TYPE(C_PTR), SAVE :: b200 = C_NULL_PTR
@@ -243,6 +252,11 @@ CONTAINS
     cfg%smooth_its = 0
     cfg%smooth_comp_its = 0
     cfg%smooth_strides = 0
+#ifdef HC_PUSH
+    cfg%hc_push = 1
+#else
+    cfg%hc_push = 0
+#endif
     IF (smooth_currents) THEN
       cfg%smooth_its = smooth_its
       cfg%smooth_comp_its = smooth_comp_its
@@ -449,6 +463,11 @@ END MODULE epoch_b200_mod
 !     SUBROUTINE current_finish
 !       CALL b200_check(epb_current_finish(b200))
 !     END SUBROUTINE
+!
+!   MODULE calc_df                               ! io/calc_df.F90:608-757: no particle download for a density dump
+!     SUBROUTINE calc_number_density(data_array, current_species, direction)
+!       CALL b200_check(epb_calc_moment(b200, 0, MAX(current_species, 0) - 1, C_LOC(data_array)))
+!     END SUBROUTINE                             ! calc_charge_density: kind 1, calc_mass_density: kind 2
 !
 !   MODULE partlist
 !     SUBROUTINE update_particle_count           ! partlist.F90:984-1003

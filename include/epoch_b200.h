@@ -172,6 +172,12 @@ int epb_global_count(epb_handle *h, int ispecies, int64_t *n);
  * out[1] = 0.5/mu0*sum(B^2)*dV over the local interior; kinetic: sum w*(gamma-1)*m*c^2 */
 int epb_field_energy(epb_handle *h, double out[2]);
 int epb_kinetic_energy(epb_handle *h, int ispecies, double *out);
+/* calc_number_density (io/calc_df.F90:689-757), calc_charge_density (:608-685), calc_mass_density (:35-110)
+ * of species ispecies (-1: sum over all species, tracers left out) incl. calc_boundary (ghost-cell sums with
+ * the particle boundary codes, across ranks) and the zero-gradient ghost fill: host receives the array at
+ * full extent (1-ng:nx+ng, ...), like the data_array the reference's output routines pass */
+enum { EPB_MOMENT_NUMBER_DENSITY = 0, EPB_MOMENT_CHARGE_DENSITY = 1, EPB_MOMENT_MASS_DENSITY = 2 };
+int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host);
 
 /* -- instrumentation ---------------------------------------------------------------
  * kernel launch counter since creation (bench.py's gpu_launches), and CUDA-event

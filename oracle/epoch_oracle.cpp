@@ -1488,6 +1488,81 @@ inline void particle_to_grid(const World &w, const Rank &R, const Particle &P, i
   for (int d = w.nd; d < 3; d++) { cell[d] = 1; g[d][0] = g[d][2] = 0.0; g[d][1] = 1.0; }
 }
 
+// io/calc_df.F90: calc_number_density :689-757 (kind 0), calc_charge_density :608-685 (kind 1),
+// calc_mass_density :35-110 (kind 2) into the work array WK (1D/3D trees: same routines, gx*wdata resp.
+// gx*gy*gz*wdata).  species < 0 sums all species (tracers skipped, :647-649); calc_boundary = processor_
+// summation_bcs without a sign flip, per species under c_bc_mixed, once otherwise (boundary.F90:783-804);
+// then the scaling (number: 1/(dx*dy), the others 1/dx/dy) and field_zero_gradient(c_stagger_centre) on
+// every boundary.  Ghost cells of periodic / inter-rank edges keep their deposits, as in the reference.
+void calc_moment(World &w, int kind, int species) {
+  const int nd = w.nd;
+  for (Rank &R : w.r) std::fill(R.f[WK].v.begin(), R.f[WK].v.end(), 0.0);
+  double idx;
+  if (kind == 0) {
+    double vol = w.d[0];
+    for (int d = 1; d < nd; d++) vol = vol * w.d[d];
+    idx = 1.0 / vol;
+  } else {
+    idx = 1.0 / w.d[0];
+    for (int d = 1; d < nd; d++) idx = idx / w.d[d];
+  }
+  const bool spec_sum = species < 0;
+  const int no_flip = nd + 3;  // flip_direction absent: no axis matches
+  for (int is = spec_sum ? 0 : species; is < (spec_sum ? (int)w.sp.size() : species + 1); is++) {
+    const SpeciesCfg &S = w.sp[is];
+    if (spec_sum && S.zero_current) continue;
+    for (Rank &R : w.r) {
+      Arr &a = R.f[WK];
+      for (const Particle &P : R.part[is]) {
+        const double wdata = kind == 0 ? P.w : (kind == 1 ? S.charge : S.mass) * P.w;
+        int cell[3];
+        double g[3][3];
+        particle_to_grid(w, R, P, cell, g);
+        if (nd == 1) {
+          for (int ix = -1; ix <= 1; ix++) a(cell[0] + ix) = a(cell[0] + ix) + g[0][ix + 1] * wdata;
+        } else if (nd == 2) {
+          for (int iy = -1; iy <= 1; iy++)
+            for (int ix = -1; ix <= 1; ix++)
+              a(cell[0] + ix, cell[1] + iy) = a(cell[0] + ix, cell[1] + iy) + g[0][ix + 1] * g[1][iy + 1] * wdata;
+        } else {
+          for (int iz = -1; iz <= 1; iz++)
+            for (int iy = -1; iy <= 1; iy++)
+              for (int ix = -1; ix <= 1; ix++)
+                a(cell[0] + ix, cell[1] + iy, cell[2] + iz) =
+                    a(cell[0] + ix, cell[1] + iy, cell[2] + iz) + g[0][ix + 1] * g[1][iy + 1] * g[2][iz + 1] * wdata;
+        }
+      }
+    }
+    if (w.bc_mixed) {  // calc_boundary(data_array, ispecies)
+      int bcs[6];
+      for (int i = 0; i < 6; i++) {
+        int b = i < 2 * nd ? S.bc_particle[i] : c_bc_open;
+        if (b != c_bc_reflect && b != c_bc_periodic) b = c_bc_open;
+        bcs[i] = b;
+      }
+      particle_reflection_bcs(w, WK, no_flip, bcs);
+      particle_periodic_bcs(w, WK, bcs);
+      for (Rank &R : w.r) {  // particle_clear_bcs
+        Arr &a = R.f[WK];
+        for (int k = a.lo[2]; k < a.lo[2] + a.sz[2]; k++)
+          for (int j = a.lo[1]; j < a.lo[1] + a.sz[1]; j++)
+            for (int i = a.lo[0]; i < a.lo[0] + a.sz[0]; i++) {
+              const bool in = (i >= 1 && i <= R.n[0]) && (nd < 2 || (j >= 1 && j <= R.n[1])) &&
+                              (nd < 3 || (k >= 1 && k <= R.n[2]));
+              if (!in) a(i, j, k) = 0.0;
+            }
+      }
+    }
+  }
+  if (!w.bc_mixed) {  // calc_boundary(data_array)
+    particle_reflection_bcs(w, WK, no_flip);
+    particle_periodic_bcs(w, WK);
+  }
+  for (Rank &R : w.r)
+    for (double &v : R.f[WK].v) v = v * idx;
+  for (int i = 0; i < 2 * nd; i++) field_mirror(w, WK, i, +1.0);
+}
+
 void auto_load(World &w) {
   const int nd = w.nd;
   for (size_t is = 0; is < w.sp.size(); is++) {
@@ -1802,6 +1877,8 @@ void orc_cell_counts(void *h, int rk, int is, int32_t *out) {
     if (ok) out[(size_t)(cell[0] - 1) + (size_t)R.n[0] * ((size_t)(cell[1] - 1) + (size_t)R.n[1] * (cell[2] - 1))]++;
   }
 }
+
+void orc_calc_moment(void *h, int kind, int species) { calc_moment(*(World *)h, kind, species); }
 
 // KISS stream check hook: fills out[n] with successive random() values for `seed`
 void orc_kiss(int seed, int n, double *out) {

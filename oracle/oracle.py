@@ -74,6 +74,8 @@ def lib():
         L.orc_rank_info.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         L.orc_outer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_kiss.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.orc_calc_moment.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_calc_moment.restype = None
         _LIB = L
     return _LIB
 
@@ -181,6 +183,17 @@ class Oracle:
     def set_particles(self, rk, isp, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         lib().orc_set_particles(self._h, rk, isp, arr.shape[0], arr.ctypes.data)
+
+    MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2}
+
+    def moment(self, rk, kind, isp=-1):
+        """calc_number_density / calc_charge_density / calc_mass_density (io/calc_df.F90) of species isp
+        (-1: all species); returns a copy of the work array of rank rk, ghost cells included."""
+        L = lib()
+        L.orc_calc_moment(self._h, self.MOMENTS[kind], isp)
+        sz = L.orc_field_size(self._h, rk)
+        p = L.orc_field(self._h, rk, 9)
+        return np.ctypeslib.as_array(p, shape=(sz,)).reshape(self.field_shape(rk)).copy()
 
     def cell_counts(self, rk, isp):
         n = self.rank_info(rk)["n"]

@@ -1,0 +1,163 @@
+"""Device-side diagnostics moments: calc_number_density, calc_charge_density,
+calc_mass_density of io/calc_df.F90 (:689-757, :608-685, :35-110).
+
+The reference holds no numbers for them.  The oracle restatement is pinned on (1) an independent numpy
+deposit of the triangle weights (include/triangle/gxfac.inc), (2) the conservation the routines are built
+for: sum(n) dV = sum of weights inside the domain, for periodic and reflecting boundaries, on one rank and
+decomposed, (3) 1-rank vs 2x2-rank consistency.  The CUDA path (epb_calc_moment) is held to the oracle."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from tests import decks
+
+KINDS = ("number_density", "charge_density", "mass_density")
+
+
+def _interior(a):
+    sl = tuple(slice(5, -5) if a.shape[ax] > 1 else slice(None) for ax in range(3))
+    return a[sl]
+
+
+def _numpy_density(dk, p, periodic=True):
+    """Triangle-shape number density at cell centres on the global periodic grid."""
+    nd = dk.ndims
+    n = [dk.n[d] for d in range(nd)]
+    out = np.zeros(n[::-1])
+    cells, gs = [], []
+    for d in range(nd):
+        r = (p[:, d] - dk.grid_min(d)) / dk.dx(d)
+        cx = np.floor(r + 0.5)
+        f = cx - r
+        cells.append(cx.astype(np.int64))
+        gs.append([0.5 * (0.25 + f * f + f), 0.75 - f * f, 0.5 * (0.25 + f * f - f)])
+    vol = np.prod([dk.dx(d) for d in range(nd)])
+    for offs in itertools.product((-1, 0, 1), repeat=nd):
+        wgt = p[:, -1] / vol
+        idx = []
+        for d in range(nd):
+            wgt = wgt * gs[d][offs[d] + 1]
+            idx.append((cells[d] + offs[d]) % n[d])
+        np.add.at(out, tuple(idx[::-1]), wgt)
+    return out
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 7, 6))])
+def test_number_density_against_numpy(ndims, n):
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=1.0e8)
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    for _ in range(2):
+        o.push()
+    got = _interior(o.moment(0, "number_density", 0)).reshape(n[::-1])
+    ref = _numpy_density(dk, o.get_particles(0, 0))
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    s = dk.species[0]
+    rho = _interior(o.moment(0, "charge_density", 0)).reshape(n[::-1])
+    assert np.abs(rho - s.charge * ref).max() <= 1e-12 * np.abs(s.charge * ref).max()
+    rm = _interior(o.moment(0, "mass_density", 0)).reshape(n[::-1])
+    assert np.abs(rm - s.mass * ref).max() <= 1e-12 * np.abs(s.mass * ref).max()
+
+
+@pytest.mark.parametrize("bc", ["periodic", "reflect"])
+@pytest.mark.parametrize("nproc", [(1, 1, 1), (2, 2, 1)])
+def test_total_weight_is_conserved(bc, nproc):
+    dk = decks.thermal(2, (16, 12), ppc=5, temp_k=3.0e9, bc=bc, nproc=nproc, two_species=True)
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    for _ in range(4):
+        o.push()
+    vol = dk.dx(0) * dk.dx(1)
+    for isp in (0, 1):
+        total = sum(_interior(o.moment(rk, "number_density", isp)).sum() for rk in range(o.nranks)) * vol
+        wsum = sum(o.get_particles(rk, isp)[:, -1].sum() for rk in range(o.nranks))
+        assert abs(total - wsum) <= 1e-12 * wsum
+    # all species: charge density of electrons + protons of equal density cancels in the mean
+    rho = np.concatenate([_interior(o.moment(rk, "charge_density", -1)).ravel() for rk in range(o.nranks)])
+    rho_e = np.concatenate([_interior(o.moment(rk, "charge_density", 0)).ravel() for rk in range(o.nranks)])
+    assert abs(rho.sum()) <= 1e-9 * np.abs(rho_e).sum()
+
+
+@pytest.mark.parametrize("bc", ["periodic", "reflect"])
+def test_decomposed_equals_single_rank(bc):
+    """The same particles (the loader seeds every rank differently, so they are handed over) on 1 and 2x2 ranks."""
+    dk1 = decks.thermal(2, (16, 12), ppc=4, temp_k=1.0e9, bc=bc)
+    o1 = Oracle(dk1)
+    o1.auto_load()
+    o1.init()
+    p = o1.get_particles(0, 0)
+    ref = _interior(o1.moment(0, "number_density", 0)).reshape(12, 16)
+    dk4 = decks.thermal(2, (16, 12), ppc=4, temp_k=1.0e9, bc=bc, nproc=(2, 2, 1))
+    o4 = Oracle(dk4)
+    o4.init()
+    full = np.zeros((12, 16))
+    taken = 0
+    for rk in range(o4.nranks):
+        info = o4.rank_info(rk)
+        sel = np.ones(len(p), dtype=bool)
+        for d in range(2):
+            sel &= (p[:, d] >= info["min_local"][d]) & (p[:, d] < info["max_local"][d])
+        o4.set_particles(rk, 0, p[sel])
+        taken += int(sel.sum())
+    assert taken == len(p)
+    for rk in range(o4.nranks):
+        info = o4.rank_info(rk)
+        a = _interior(o4.moment(rk, "number_density", 0)).reshape(info["n"][1], info["n"][0])
+        x0, y0 = info["gmin"][0] - 1, info["gmin"][1] - 1
+        full[y0:y0 + a.shape[0], x0:x0 + a.shape[1]] = a
+    assert np.abs(full - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_mixed_boundaries_and_tracers():
+    """c_bc_mixed takes the per-species calc_boundary path; a tracer species is left out of the species sum."""
+    dk = decks.thermal(2, (16, 12), ppc=4, temp_k=3.0e9, bc="reflect", two_species=True)
+    dk.species[1].bc_particle = ["open"] * 4
+    dk.species[1].zero_current = True
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    for _ in range(3):
+        o.push()
+    both = o.moment(0, "number_density", -1)
+    only_e = o.moment(0, "number_density", 0)
+    assert np.array_equal(both, only_e)
+    vol = dk.dx(0) * dk.dx(1)
+    assert abs(_interior(only_e).sum() * vol - o.get_particles(0, 0)[:, -1].sum()) <= 1e-12 * o.get_particles(0, 0)[:, -1].sum()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CUDA path against the oracle
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n,bc", [(1, (64,), "periodic"), (2, (32, 24), "periodic"), (2, (32, 24), "reflect"),
+                                        (3, (10, 9, 8), "periodic"), (3, (10, 9, 8), "reflect")])
+def test_moments_match_oracle_gpu(ndims, n, bc):
+    from tests.gpu_util import make_pair, rel_l2, run_both
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=2.0e9, bc=bc, two_species=True)
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 3)
+    for kind in KINDS:
+        for isp in (-1, 0, 1):
+            ref = o.moment(0, kind, isp)
+            got = sim.moment(kind, isp)
+            assert got.shape == ref.shape
+            assert rel_l2(got, ref) <= 1e-13, (kind, isp)
+            assert rel_l2(_interior(got), _interior(ref)) <= 1e-13, (kind, isp)
+    # the diagnostic leaves the state alone: the next steps still match
+    run_both(dk, o, sim, 2)
+    assert rel_l2(sim.download_field("jx"), o.field(0, "jx")) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_moments_mixed_boundaries_gpu():
+    from tests.gpu_util import make_pair, rel_l2, run_both
+    dk = decks.thermal(2, (32, 24), ppc=5, temp_k=2.0e9, bc="reflect", two_species=True)
+    dk.species[1].bc_particle = ["open"] * 4
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 4)
+    for isp in (-1, 0, 1):
+        assert rel_l2(sim.moment("charge_density", isp), o.moment(0, "charge_density", isp)) <= 1e-13, isp
