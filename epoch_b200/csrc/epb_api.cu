@@ -439,6 +439,97 @@ __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp
     }
   }
 }
+// calc_ekbar (io/calc_df.F90:116-221) and the two passes of calc_temperature (:877-1128)
+struct Moment2Op {
+  const double *x[3], *p[3], *w;
+  long long n;
+  int nd, sz[3];
+  double gmin[3], dx[3];
+  int mode;        // 3: ekbar (a0 += g wdata, a1 += g w); 4: temperature pass 1 (mean[q] += g w p/sqrt(m), cnt += g w);
+                   // 5: pass 2 (sig += g sum_q (p/sqrt(m) - mean[q])^2, cnt += g)
+  int dir;         // temperature: -1 all components, else one
+  double part_mc, sqrt_part_m;
+  double *a0, *a1;           // ekbar: data, wt; temperature: sigma, count
+  double *mean[3];
+};
+__global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2Op M) {
+  const double c = EPB_C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (long long)gridDim.x * blockDim.x) {
+    int cell[3] = {1, 1, 1};
+    double g[3][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
+    bool ok = true;
+    for (int d = 0; d < M.nd; d++) {
+      const double cell_r = (M.x[d][i] - M.gmin[d]) / M.dx[d];
+      const int cx = __double2int_rd(cell_r + 0.5);
+      const double cf = (double)cx - cell_r;
+      cell[d] = cx + 1;
+      const double c2 = cf * cf;
+      g[d][0] = 0.5 * (0.25 + c2 + cf);
+      g[d][1] = 0.75 - c2;
+      g[d][2] = 0.5 * (0.25 + c2 - cf);
+      if (cell[d] - 1 < 1 - NG || cell[d] + 1 > M.sz[d] - NG) ok = false;
+    }
+    if (!ok) continue;
+    const double part_w = M.w[i];
+    double wdata = 0.0, pm[3] = {0.0, 0.0, 0.0};
+    if (M.mode == 3) {
+      const double fac = M.part_mc * part_w * c;
+      const double part_ux = M.p[0][i] / M.part_mc, part_uy = M.p[1][i] / M.part_mc, part_uz = M.p[2][i] / M.part_mc;
+      const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+      const double gamma_rel = sqrt(part_u2 + 1.0);
+      const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
+      wdata = gamma_rel_m1 * fac;
+    } else {
+      for (int q = 0; q < 3; q++) pm[q] = M.p[q][i] / M.sqrt_part_m;
+    }
+    const int z0 = M.nd >= 3 ? -1 : 0, z1 = M.nd >= 3 ? 1 : 0;
+    const int y0 = M.nd >= 2 ? -1 : 0, y1 = M.nd >= 2 ? 1 : 0;
+    for (int iz = z0; iz <= z1; iz++)
+      for (int iy = y0; iy <= y1; iy++)
+        for (int ix = -1; ix <= 1; ix++) {
+          // gx(ix) * gy(iy) * gz(iz), left to right
+          double gg = g[0][ix + 1];
+          if (M.nd >= 2) gg = gg * g[1][iy + 1];
+          if (M.nd >= 3) gg = gg * g[2][iz + 1];
+          const size_t o = fofs(M.sz, M.nd, cell[0] + ix, cell[1] + iy, cell[2] + iz);
+          if (M.mode == 3) {
+            atomicAdd(M.a0 + o, gg * wdata);
+            atomicAdd(M.a1 + o, gg * part_w);
+          } else if (M.mode == 4) {
+            const double gf = gg * part_w;
+            for (int q = 0; q < 3; q++)
+              if (M.dir < 0 || M.dir == q) atomicAdd(M.mean[q] + o, gf * pm[q]);
+            atomicAdd(M.a1 + o, gf);
+          } else {
+            double wd;
+            if (M.dir < 0) {
+              const double d0 = pm[0] - M.mean[0][o], d1 = pm[1] - M.mean[1][o], d2 = pm[2] - M.mean[2][o];
+              wd = d0 * d0 + d1 * d1 + d2 * d2;
+            } else {
+              const double d0 = pm[M.dir] - M.mean[M.dir][o];
+              wd = d0 * d0;
+            }
+            atomicAdd(M.a0 + o, gg * wd);
+            atomicAdd(M.a1 + o, gg);
+          }
+        }
+  }
+}
+// element-wise tails of calc_ekbar / calc_temperature
+struct MomentPostOp { int op; size_t n; double *a, *b, *m[3]; double k1, k2; };
+__global__ void __launch_bounds__(256) k_moment_post(const __grid_constant__ MomentPostOp P) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < P.n; t += (size_t)gridDim.x * blockDim.x) {
+    if (P.op == 0) {         // data_array = data_array / MAX(wt, c_tiny)
+      P.a[t] = P.a[t] / fmax(P.b[t], P.k1);
+    } else if (P.op == 1) {  // part_count = MAX(part_count, 1.e-6); mean = mean / part_count
+      const double pc = fmax(P.b[t], 1.e-6);
+      P.b[t] = pc;
+      for (int q = 0; q < 3; q++) P.m[q][t] = P.m[q][t] / pc;
+    } else {                 // sigma = sigma / MAX(part_count, 1.e-6) / kb / dof
+      P.a[t] = P.a[t] / fmax(P.b[t], 1.e-6) / P.k1 / P.k2;
+    }
+  }
+}
 __global__ void __launch_bounds__(256) k_scale(double *a, size_t n, double s) {
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) a[t] = a[t] * s;
 }
@@ -1061,8 +1152,8 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   h->plane = (size_t)h->sz[1] * h->sz[2];
   EPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
-  // ex..jz, one work array (field id 9: epb_calc_moment), plus two more when smooth_current is on (ids 9..11)
-  const int nfields = cfg->smooth_its + cfg->smooth_comp_its > 0 ? 12 : 10;
+  // ex..jz, plus five work arrays (field ids 9..13): smooth_current uses 9..11, epb_calc_moment 9..13
+  const int nfields = 14;
   EPB_CUDA(h, cudaMalloc(&h->fields, nfields * h->fsize * sizeof(double)));
   EPB_CUDA(h, cudaMemsetAsync(h->fields, 0, nfields * h->fsize * sizeof(double), h->stream));
   EPB_CUDA(h, cudaMalloc(&h->snap, 12 * h->plane * sizeof(double)));
@@ -1681,8 +1772,179 @@ static int moment_sum_bcs(epb_handle *h, int f) {
   return epb_halo_exchange(h, f, 1, true);
 }
 
+// field_zero_gradient(array, c_stagger_centre, bd) on every boundary (boundary.F90:416-469)
+static int moment_zero_gradient(epb_handle *h, int f) {
+  const epb_config &c = h->cfg;
+  for (int bd = 0; bd < 2 * c.ndims; bd++) {
+    if (c.bc_field[bd] == EPB_BC_PERIODIC || !c.is_boundary[bd]) continue;
+    MirrorOp M;
+    M.nd = c.ndims;
+    M.d = bd / 2;
+    M.is_max = bd & 1;
+    M.sign = 1.0;
+    size_t total = 1;
+    for (int d = 0; d < 3; d++) {
+      M.sz[d] = h->sz[d];
+      M.n[d] = c.n[d];
+      if (d < c.ndims && d != M.d) total *= h->sz[d];
+    }
+    for (int q = 0; q < 3; q++) { M.f[q] = h->f(f); M.stag[q] = 0; }  // one array: the copy is idempotent
+    k_mirror<<<nblocks(total), 256, 0, h->stream>>>(M);
+    h->launches++;
+  }
+  return EPB_OK;
+}
+
+// calc_boundary(array, ispecies): only under c_bc_mixed, followed by particle_clear_bcs (boundary.F90:749, :790-792)
+static int moment_bcs_species(epb_handle *h, int f, int is) {
+  if (!h->bc_mixed) return EPB_OK;
+  h->bc_species = is;
+  int rc = moment_sum_bcs(h, f);
+  h->bc_species = -1;
+  if (rc) return rc;
+  ClearOp C;
+  for (int q = 0; q < 3; q++) C.a[q] = h->f(f);
+  C.nd = h->cfg.ndims;
+  for (int k = 0; k < 3; k++) { C.n[k] = h->cfg.n[k]; C.sz[k] = h->sz[k]; }
+  k_clear_ghosts<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(C);
+  h->launches++;
+  return EPB_OK;
+}
+// calc_boundary(array): only without c_bc_mixed (boundary.F90:794-796)
+static int moment_bcs_all(epb_handle *h, int f) { return h->bc_mixed ? EPB_OK : moment_sum_bcs(h, f); }
+
+static void moment2_fill(epb_handle *h, int is, Moment2Op &M) {
+  const epb_config &c = h->cfg;
+  SpeciesDev &S = h->sp[is];
+  for (int d = 0; d < 3; d++) {
+    M.x[d] = S.buf[S.cur][d];
+    M.p[d] = S.buf[S.cur][3 + d];
+    M.sz[d] = h->sz[d];
+    M.gmin[d] = c.grid_min_local[d];
+    M.dx[d] = c.dx[d];
+  }
+  M.w = S.buf[S.cur][6];
+  M.n = S.n;
+  M.nd = c.ndims;
+  M.part_mc = EPB_C * S.cfg.mass;
+  M.sqrt_part_m = sqrt(S.cfg.mass);
+}
+
+// calc_ekbar (io/calc_df.F90:116-221): result in work array 9
+static int calc_ekbar_dev(epb_handle *h, int ispecies) {
+  const epb_config &c = h->cfg;
+  const int A = 9, WT = 10;
+  EPB_CUDA(h, cudaMemsetAsync(h->f(A), 0, 2 * h->fsize * sizeof(double), h->stream));
+  const bool spec_sum = ispecies < 0;
+  for (int is = spec_sum ? 0 : ispecies; is < (spec_sum ? (int)h->sp.size() : ispecies + 1); is++) {
+    SpeciesDev &S = h->sp[is];
+    if (spec_sum && S.cfg.zero_current) continue;
+    if (S.n > 0) {
+      Moment2Op M;
+      moment2_fill(h, is, M);
+      M.mode = 3;
+      M.dir = -1;
+      M.a0 = h->f(A);
+      M.a1 = h->f(WT);
+      for (int q = 0; q < 3; q++) M.mean[q] = nullptr;
+      k_moment2<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
+      h->launches++;
+    }
+    int rc = moment_bcs_species(h, A, is);
+    if (!rc) rc = moment_bcs_species(h, WT, is);
+    if (rc) return rc;
+  }
+  int rc = moment_bcs_all(h, A);
+  if (!rc) rc = moment_bcs_all(h, WT);
+  if (rc) return rc;
+  MomentPostOp P;
+  P.op = 0; P.n = h->fsize; P.a = h->f(A); P.b = h->f(WT);
+  for (int q = 0; q < 3; q++) P.m[q] = nullptr;
+  P.k1 = 2.2250738585072014e-308;  // c_tiny = TINY(1.0_num), constants.F90:29
+  P.k2 = 0.0;
+  k_moment_post<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(P);
+  h->launches++;
+  (void)c;
+  return EPB_OK;
+}
+
+// calc_temperature (io/calc_df.F90:877-1128): sigma in work array 9, means 10..12, part_count 13
+static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
+  const int SIG = 9, MEAN0 = 10, CNT = 13;
+  EPB_CUDA(h, cudaMemsetAsync(h->f(SIG), 0, 5 * h->fsize * sizeof(double), h->stream));
+  const bool spec_sum = ispecies < 0;
+  const int s0 = spec_sum ? 0 : ispecies, s1 = spec_sum ? (int)h->sp.size() : ispecies + 1;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int is = s0; is < s1; is++) {
+      SpeciesDev &S = h->sp[is];
+      if (spec_sum && S.cfg.zero_current) continue;
+      if (S.n > 0) {
+        Moment2Op M;
+        moment2_fill(h, is, M);
+        M.mode = pass == 0 ? 4 : 5;
+        M.dir = dir;
+        M.a0 = h->f(SIG);
+        M.a1 = h->f(CNT);
+        for (int q = 0; q < 3; q++) M.mean[q] = h->f(MEAN0 + q);
+        k_moment2<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
+        h->launches++;
+      }
+      int rc = EPB_OK;
+      if (pass == 0) {
+        for (int q = 0; q < 3 && !rc; q++)
+          if (dir < 0 || dir == q) rc = moment_bcs_species(h, MEAN0 + q, is);
+      } else {
+        rc = moment_bcs_species(h, SIG, is);
+      }
+      if (!rc) rc = moment_bcs_species(h, CNT, is);
+      if (rc) return rc;
+    }
+    int rc = EPB_OK;
+    if (pass == 0) {
+      for (int q = 0; q < 3 && !rc; q++)
+        if (dir < 0 || dir == q) rc = moment_bcs_all(h, MEAN0 + q);
+    } else {
+      rc = moment_bcs_all(h, SIG);
+    }
+    if (!rc) rc = moment_bcs_all(h, CNT);
+    if (rc) return rc;
+    MomentPostOp P;
+    P.n = h->fsize; P.a = h->f(SIG); P.b = h->f(CNT);
+    for (int q = 0; q < 3; q++) P.m[q] = h->f(MEAN0 + q);
+    if (pass == 0) {
+      P.op = 1; P.k1 = 0.0; P.k2 = 0.0;
+    } else {
+      P.op = 2; P.k1 = EPB_KB; P.k2 = dir < 0 ? 3.0 : 1.0;
+    }
+    k_moment_post<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(P);
+    h->launches++;
+    if (pass == 0) {
+      // restore the ghost cells of the means (field_bc), then part_count = 0
+      for (int q = 0; q < 3; q++)
+        if (dir < 0 || dir == q) {
+          rc = epb_halo_exchange(h, MEAN0 + q, 1, false);
+          if (rc) return rc;
+        }
+      EPB_CUDA(h, cudaMemsetAsync(h->f(CNT), 0, h->fsize * sizeof(double), h->stream));
+    }
+  }
+  return EPB_OK;
+}
+
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
-  if (!h || !host || kind < 0 || kind > 2 || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
+  if (!h || !host || kind < 0 || kind > 7 || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
+  if (kind >= EPB_MOMENT_EKBAR) {
+    int rc = kind == EPB_MOMENT_EKBAR ? calc_ekbar_dev(h, ispecies) : calc_temperature_dev(h, ispecies, kind - 5);
+    if (rc) return rc;
+    if (kind == EPB_MOMENT_EKBAR) {  // field_zero_gradient(data_array, c_stagger_centre, bd); none for the temperature
+      int rcz = moment_zero_gradient(h, 9);
+      if (rcz) return rcz;
+    }
+    EPB_CUDA(h, cudaMemcpyAsync(host, h->f(9), h->fsize * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    EPB_CUDA(h, cudaGetLastError());
+    return EPB_OK;
+  }
   const epb_config &c = h->cfg;
   const int WK = 9;
   double *wk = h->f(WK);
@@ -1736,22 +1998,9 @@ int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
   }
   k_scale<<<nblocks(h->fsize, 148 * 16), 256, 0, h->stream>>>(wk, h->fsize, idx);
   h->launches++;
-  for (int bd = 0; bd < 2 * c.ndims; bd++) {  // field_zero_gradient(data_array, c_stagger_centre, bd)
-    if (c.bc_field[bd] == EPB_BC_PERIODIC || !c.is_boundary[bd]) continue;
-    MirrorOp M;
-    M.nd = c.ndims;
-    M.d = bd / 2;
-    M.is_max = bd & 1;
-    M.sign = 1.0;
-    size_t total = 1;
-    for (int d = 0; d < 3; d++) {
-      M.sz[d] = h->sz[d];
-      M.n[d] = c.n[d];
-      if (d < c.ndims && d != M.d) total *= h->sz[d];
-    }
-    for (int q = 0; q < 3; q++) { M.f[q] = wk; M.stag[q] = 0; }  // one array: the copy is idempotent
-    k_mirror<<<nblocks(total), 256, 0, h->stream>>>(M);
-    h->launches++;
+  {
+    int rcz = moment_zero_gradient(h, WK);
+    if (rcz) return rcz;
   }
   EPB_CUDA(h, cudaMemcpyAsync(host, wk, h->fsize * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -261,7 +261,8 @@ class Simulation:
         self._chk(self.L.epb_kinetic_energy(self._h, isp, C.byref(out)))
         return out.value
 
-    MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2}
+    MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2, "ekbar": 3, "temperature": 4,
+               "temperature_x": 5, "temperature_y": 6, "temperature_z": 7}
 
     def moment(self, kind: str, isp: int = -1):
         """calc_number_density / calc_charge_density / calc_mass_density (io/calc_df.F90) computed on the device;

@@ -183,7 +183,8 @@ MODULE epoch_b200_mod
       TYPE(C_PTR), VALUE :: handle
       INTEGER(C_INT) :: rc
     END FUNCTION
-    ! kind: 0 number density, 1 charge density, 2 mass density; ispecies = -1: all species
+    ! kind: 0 number density, 1 charge density, 2 mass density, 3 ekbar, 4 temperature, 5..7 temperature x/y/z;
+    ! ispecies = -1: all species
     FUNCTION epb_calc_moment(handle, kind, ispecies, host) BIND(C, NAME='epb_calc_moment') RESULT(rc)
       IMPORT :: C_INT, C_PTR
       TYPE(C_PTR), VALUE :: handle

@@ -176,7 +176,11 @@ int epb_kinetic_energy(epb_handle *h, int ispecies, double *out);
  * of species ispecies (-1: sum over all species, tracers left out) incl. calc_boundary (ghost-cell sums with
  * the particle boundary codes, across ranks) and the zero-gradient ghost fill: host receives the array at
  * full extent (1-ng:nx+ng, ...), like the data_array the reference's output routines pass */
-enum { EPB_MOMENT_NUMBER_DENSITY = 0, EPB_MOMENT_CHARGE_DENSITY = 1, EPB_MOMENT_MASS_DENSITY = 2 };
+enum { EPB_MOMENT_NUMBER_DENSITY = 0, EPB_MOMENT_CHARGE_DENSITY = 1, EPB_MOMENT_MASS_DENSITY = 2,
+       /* calc_ekbar (io/calc_df.F90:116-221): mean kinetic energy per cell, J */
+       EPB_MOMENT_EKBAR = 3,
+       /* calc_temperature (:877-1128), K: all momentum components (dof 3), or direction x / y / z (dof 1) */
+       EPB_MOMENT_TEMPERATURE = 4, EPB_MOMENT_TEMPERATURE_X = 5, EPB_MOMENT_TEMPERATURE_Y = 6, EPB_MOMENT_TEMPERATURE_Z = 7 };
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host);
 
 /* -- instrumentation ---------------------------------------------------------------

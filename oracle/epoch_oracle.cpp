@@ -30,6 +30,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 namespace {
@@ -59,7 +60,7 @@ enum {
 // constants.F90:549-559 (triangle): sf_min=-1, sf_max=1, png=3, ng=png+2
 constexpr int sf_min = -1, sf_max = 1, png = 3, NG = png + 2;
 
-enum { EX, EY, EZ, BX, BY, BZ, JX, JY, JZ, WK, NFIELD };  // WK: work array of smooth_array
+enum { EX, EY, EZ, BX, BY, BZ, JX, JY, JZ, WK, WK1, WK2, WK3, WK4, NFIELD };  // WK: work array of smooth_array; WK..WK4: calc_df
 
 // Fortran-style array  a(1-g:n1+g [, 1-g:n2+g [, 1-g:n3+g]])
 struct Arr {
@@ -1563,6 +1564,175 @@ void calc_moment(World &w, int kind, int species) {
   for (int i = 0; i < 2 * nd; i++) field_mirror(w, WK, i, +1.0);
 }
 
+// calc_boundary(array, ispecies) / calc_boundary(array) of io/calc_df.F90:24-31 on a work array
+static void calc_boundary_species(World &w, int which, const SpeciesCfg &S) {
+  if (!w.bc_mixed) return;  // boundary.F90:790-792
+  const int nd = w.nd;
+  int bcs[6];
+  for (int i = 0; i < 6; i++) {
+    int b = i < 2 * nd ? S.bc_particle[i] : c_bc_open;
+    if (b != c_bc_reflect && b != c_bc_periodic) b = c_bc_open;
+    bcs[i] = b;
+  }
+  particle_reflection_bcs(w, which, nd + 3, bcs);
+  particle_periodic_bcs(w, which, bcs);
+  for (Rank &R : w.r) {  // particle_clear_bcs
+    Arr &a = R.f[which];
+    for (int k = a.lo[2]; k < a.lo[2] + a.sz[2]; k++)
+      for (int j = a.lo[1]; j < a.lo[1] + a.sz[1]; j++)
+        for (int i = a.lo[0]; i < a.lo[0] + a.sz[0]; i++) {
+          const bool in = (i >= 1 && i <= R.n[0]) && (nd < 2 || (j >= 1 && j <= R.n[1])) &&
+                          (nd < 3 || (k >= 1 && k <= R.n[2]));
+          if (!in) a(i, j, k) = 0.0;
+        }
+  }
+}
+static void calc_boundary_all(World &w, int which) {
+  if (w.bc_mixed) return;  // boundary.F90:794-796
+  particle_reflection_bcs(w, which, w.nd + 3);
+  particle_periodic_bcs(w, which);
+}
+// data(cell + offsets) += gx*gy*gz * wdata for up to 4 (array, wdata) pairs; the weight product is formed
+// first, left to right, as in the reference's `gx(ix) * gy(iy) * wdata`
+template <class F>
+static inline void stencil3(int nd, const int cell[3], const double g[3][3], F &&f) {
+  if (nd == 1) {
+    for (int ix = -1; ix <= 1; ix++) f(cell[0] + ix, 1, 1, g[0][ix + 1]);
+  } else if (nd == 2) {
+    for (int iy = -1; iy <= 1; iy++)
+      for (int ix = -1; ix <= 1; ix++) f(cell[0] + ix, cell[1] + iy, 1, g[0][ix + 1] * g[1][iy + 1]);
+  } else {
+    for (int iz = -1; iz <= 1; iz++)
+      for (int iy = -1; iy <= 1; iy++)
+        for (int ix = -1; ix <= 1; ix++)
+          f(cell[0] + ix, cell[1] + iy, cell[2] + iz, g[0][ix + 1] * g[1][iy + 1] * g[2][iz + 1]);
+  }
+}
+
+// calc_ekbar, io/calc_df.F90:116-221: mean kinetic energy per cell = sum(g (gamma-1) m c^2 w) / MAX(sum(g w), c_tiny)
+void calc_ekbar(World &w, int species) {
+  const int nd = w.nd;
+  for (Rank &R : w.r) {
+    std::fill(R.f[WK].v.begin(), R.f[WK].v.end(), 0.0);
+    std::fill(R.f[WK1].v.begin(), R.f[WK1].v.end(), 0.0);
+  }
+  const bool spec_sum = species < 0;
+  for (int is = spec_sum ? 0 : species; is < (spec_sum ? (int)w.sp.size() : species + 1); is++) {
+    const SpeciesCfg &S = w.sp[is];
+    if (spec_sum && S.zero_current) continue;
+    const double part_mc = c * S.mass;
+    for (Rank &R : w.r) {
+      Arr &a = R.f[WK], &wt = R.f[WK1];
+      for (const Particle &P : R.part[is]) {
+        const double part_w = P.w;
+        const double fac = part_mc * part_w * c;
+        const double part_ux = P.p[0] / part_mc, part_uy = P.p[1] / part_mc, part_uz = P.p[2] / part_mc;
+        const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+        const double gamma_rel = std::sqrt(part_u2 + 1.0);
+        const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
+        const double wdata = gamma_rel_m1 * fac;
+        int cell[3];
+        double g[3][3];
+        particle_to_grid(w, R, P, cell, g);
+        stencil3(nd, cell, g, [&](int i, int j, int k, double gg) {
+          a(i, j, k) = a(i, j, k) + gg * wdata;
+          wt(i, j, k) = wt(i, j, k) + gg * part_w;
+        });
+      }
+    }
+    calc_boundary_species(w, WK, S);
+    calc_boundary_species(w, WK1, S);
+  }
+  calc_boundary_all(w, WK);
+  calc_boundary_all(w, WK1);
+  const double c_tiny = std::numeric_limits<double>::min();
+  for (Rank &R : w.r)
+    for (size_t q = 0; q < R.f[WK].v.size(); q++) R.f[WK].v[q] = R.f[WK].v[q] / std::max(R.f[WK1].v[q], c_tiny);
+  for (int i = 0; i < 2 * nd; i++) field_mirror(w, WK, i, +1.0);
+}
+
+// calc_temperature, io/calc_df.F90:877-1128: dir < 0: all three momentum components (dof 3), else one
+// (dof 1).  Pass 1: weighted mean of p/sqrt(m) per cell (ghosts restored with field_bc); pass 2: un-weighted
+// spread around the mean of the cell each stencil point lies in; sigma / MAX(count, 1e-6) / kb / dof.
+void calc_temperature(World &w, int species, int dir) {
+  const int nd = w.nd;
+  const int MEAN[3] = {WK1, WK2, WK3}, CNT = WK4, SIG = WK;
+  for (Rank &R : w.r)
+    for (int q : {WK, WK1, WK2, WK3, WK4}) std::fill(R.f[q].v.begin(), R.f[q].v.end(), 0.0);
+  const double dof = dir < 0 ? 3.0 : 1.0;
+  const bool spec_sum = species < 0;
+  const int s0 = spec_sum ? 0 : species, s1 = spec_sum ? (int)w.sp.size() : species + 1;
+  auto use = [&](int q) { return dir < 0 || dir == q; };
+  for (int is = s0; is < s1; is++) {
+    const SpeciesCfg &S = w.sp[is];
+    if (spec_sum && S.zero_current) continue;
+    const double sqrt_part_m = std::sqrt(S.mass);
+    for (Rank &R : w.r) {
+      for (const Particle &P : R.part[is]) {
+        const double part_w = P.w;
+        const double pm[3] = {P.p[0] / sqrt_part_m, P.p[1] / sqrt_part_m, P.p[2] / sqrt_part_m};
+        int cell[3];
+        double g[3][3];
+        particle_to_grid(w, R, P, cell, g);
+        stencil3(nd, cell, g, [&](int i, int j, int k, double gg) {
+          const double gf = gg * part_w;
+          for (int q = 0; q < 3; q++)
+            if (use(q)) R.f[MEAN[q]](i, j, k) = R.f[MEAN[q]](i, j, k) + gf * pm[q];
+          R.f[CNT](i, j, k) = R.f[CNT](i, j, k) + gf;
+        });
+      }
+    }
+    for (int q = 0; q < 3; q++)
+      if (use(q)) calc_boundary_species(w, MEAN[q], S);
+    calc_boundary_species(w, CNT, S);
+  }
+  for (int q = 0; q < 3; q++)
+    if (use(q)) calc_boundary_all(w, MEAN[q]);
+  calc_boundary_all(w, CNT);
+  for (Rank &R : w.r) {
+    std::vector<double> &pc = R.f[CNT].v;
+    for (size_t t = 0; t < pc.size(); t++) pc[t] = std::max(pc[t], 1.e-6);
+    for (int q = 0; q < 3; q++)  // the reference divides all three, also the unused (zero) ones
+      for (size_t t = 0; t < pc.size(); t++) R.f[MEAN[q]].v[t] = R.f[MEAN[q]].v[t] / pc[t];
+  }
+  for (int q = 0; q < 3; q++)
+    if (use(q)) field_bc(w, MEAN[q]);
+  for (Rank &R : w.r) std::fill(R.f[CNT].v.begin(), R.f[CNT].v.end(), 0.0);
+  for (int is = s0; is < s1; is++) {
+    const SpeciesCfg &S = w.sp[is];
+    if (spec_sum && S.zero_current) continue;
+    const double sqrt_part_m = std::sqrt(S.mass);
+    for (Rank &R : w.r) {
+      for (const Particle &P : R.part[is]) {
+        const double pm[3] = {P.p[0] / sqrt_part_m, P.p[1] / sqrt_part_m, P.p[2] / sqrt_part_m};
+        int cell[3];
+        double g[3][3];
+        particle_to_grid(w, R, P, cell, g);
+        stencil3(nd, cell, g, [&](int i, int j, int k, double gf) {
+          double wdata;
+          if (dir < 0) {
+            const double dx_ = pm[0] - R.f[MEAN[0]](i, j, k), dy_ = pm[1] - R.f[MEAN[1]](i, j, k),
+                         dz_ = pm[2] - R.f[MEAN[2]](i, j, k);
+            wdata = dx_ * dx_ + dy_ * dy_ + dz_ * dz_;
+          } else {
+            const double d_ = pm[dir] - R.f[MEAN[dir]](i, j, k);
+            wdata = d_ * d_;
+          }
+          R.f[SIG](i, j, k) = R.f[SIG](i, j, k) + gf * wdata;
+          R.f[CNT](i, j, k) = R.f[CNT](i, j, k) + gf;
+        });
+      }
+    }
+    calc_boundary_species(w, SIG, S);
+    calc_boundary_species(w, CNT, S);
+  }
+  calc_boundary_all(w, SIG);
+  calc_boundary_all(w, CNT);
+  for (Rank &R : w.r)
+    for (size_t t = 0; t < R.f[SIG].v.size(); t++)
+      R.f[SIG].v[t] = R.f[SIG].v[t] / std::max(R.f[CNT].v[t], 1.e-6) / kb / dof;
+}
+
 void auto_load(World &w) {
   const int nd = w.nd;
   for (size_t is = 0; is < w.sp.size(); is++) {
@@ -1878,7 +2048,13 @@ void orc_cell_counts(void *h, int rk, int is, int32_t *out) {
   }
 }
 
-void orc_calc_moment(void *h, int kind, int species) { calc_moment(*(World *)h, kind, species); }
+// kind 0..2: number / charge / mass density; 3: ekbar; 4: temperature; 5..7: temperature_x/y/z.  Result in WK.
+void orc_calc_moment(void *h, int kind, int species) {
+  World &w = *(World *)h;
+  if (kind <= 2) calc_moment(w, kind, species);
+  else if (kind == 3) calc_ekbar(w, species);
+  else calc_temperature(w, species, kind - 5);
+}
 
 // KISS stream check hook: fills out[n] with successive random() values for `seed`
 void orc_kiss(int seed, int n, double *out) {

@@ -184,7 +184,8 @@ class Oracle:
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         lib().orc_set_particles(self._h, rk, isp, arr.shape[0], arr.ctypes.data)
 
-    MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2}
+    MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2, "ekbar": 3, "temperature": 4,
+               "temperature_x": 5, "temperature_y": 6, "temperature_z": 7}
 
     def moment(self, rk, kind, isp=-1):
         """calc_number_density / calc_charge_density / calc_mass_density (io/calc_df.F90) of species isp

@@ -161,3 +161,140 @@ def test_moments_mixed_boundaries_gpu():
     run_both(dk, o, sim, 4)
     for isp in (-1, 0, 1):
         assert rel_l2(sim.moment("charge_density", isp), o.moment(0, "charge_density", isp)) <= 1e-13, isp
+
+
+# ---------------------------------------------------------------------------------------------------------
+# calc_ekbar (:116-221) and calc_temperature (:877-1128)
+# ---------------------------------------------------------------------------------------------------------
+def _numpy_weights(dk, p):
+    nd = dk.ndims
+    cells, gs = [], []
+    for d in range(nd):
+        r = (p[:, d] - dk.grid_min(d)) / dk.dx(d)
+        cx = np.floor(r + 0.5)
+        f = cx - r
+        cells.append(cx.astype(np.int64))
+        gs.append([0.5 * (0.25 + f * f + f), 0.75 - f * f, 0.5 * (0.25 + f * f - f)])
+    return cells, gs
+
+
+def _numpy_deposit(dk, p, values):
+    """sum over particles of (triangle weight) * values on the periodic grid, no volume factor."""
+    nd = dk.ndims
+    n = [dk.n[d] for d in range(nd)]
+    out = np.zeros(n[::-1])
+    cells, gs = _numpy_weights(dk, p)
+    for offs in itertools.product((-1, 0, 1), repeat=nd):
+        wgt = np.array(values, dtype=np.float64, copy=True)
+        idx = []
+        for d in range(nd):
+            wgt = wgt * gs[d][offs[d] + 1]
+            idx.append((cells[d] + offs[d]) % n[d])
+        np.add.at(out, tuple(idx[::-1]), wgt)
+    return out
+
+
+def _numpy_gather(dk, p, grid):
+    """value of `grid` at each particle's 3^nd stencil points: list of (weight, grid value)."""
+    nd = dk.ndims
+    n = [dk.n[d] for d in range(nd)]
+    cells, gs = _numpy_weights(dk, p)
+    out = []
+    for offs in itertools.product((-1, 0, 1), repeat=nd):
+        wgt = np.ones(len(p))
+        idx = []
+        for d in range(nd):
+            wgt = wgt * gs[d][offs[d] + 1]
+            idx.append((cells[d] + offs[d]) % n[d])
+        out.append((wgt, grid[tuple(idx[::-1])], tuple(idx[::-1])))
+    return out
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 7, 6))])
+def test_ekbar_and_temperature_against_numpy(ndims, n):
+    from epoch_b200 import deck as D
+    temp_k = 5.0e8
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=temp_k)
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    o.push()
+    p = o.get_particles(0, 0)
+    s = dk.species[0]
+    w = p[:, -1]
+    mom = p[:, ndims:ndims + 3]
+    u2 = ((mom / (s.mass * D.c)) ** 2).sum(axis=1)
+    ek = u2 / (np.sqrt(u2 + 1.0) + 1.0) * s.mass * D.c ** 2
+    ref = _numpy_deposit(dk, p, ek * w) / _numpy_deposit(dk, p, w)
+    got = _interior(o.moment(0, "ekbar", 0)).reshape(n[::-1])
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    # temperature: weighted mean per cell, then un-weighted spread around the mean of each stencil cell
+    pm = mom / np.sqrt(s.mass)
+    cnt = _numpy_deposit(dk, p, w)
+    for name, comps in (("temperature", (0, 1, 2)), ("temperature_x", (0,)), ("temperature_y", (1,)), ("temperature_z", (2,))):
+        sig = np.zeros(n[::-1])
+        for q in comps:
+            mean = _numpy_deposit(dk, p, w * pm[:, q]) / cnt
+            for wgt, mval, idx in _numpy_gather(dk, p, mean):
+                np.add.at(sig, idx, wgt * (pm[:, q] - mval) ** 2)
+        ref_t = sig / _numpy_deposit(dk, p, np.ones(len(p))) / D.kb / len(comps)
+        got_t = _interior(o.moment(0, name, 0)).reshape(n[::-1])
+        assert np.abs(got_t - ref_t).max() <= 1e-11 * np.abs(ref_t).max(), name
+    # physics: the loader's Maxwellian has the deck temperature (6 ppc: cell values scatter, the mean does not)
+    t_mean = _interior(o.moment(0, "temperature", 0)).mean()
+    assert abs(t_mean - temp_k) <= 0.12 * temp_k
+
+
+@pytest.mark.parametrize("bc", ["periodic", "reflect"])
+def test_ekbar_temperature_decomposed_equals_single_rank(bc):
+    dk1 = decks.thermal(2, (16, 12), ppc=4, temp_k=1.0e9, bc=bc)
+    o1 = Oracle(dk1)
+    o1.auto_load()
+    o1.init()
+    p = o1.get_particles(0, 0)
+    dk4 = decks.thermal(2, (16, 12), ppc=4, temp_k=1.0e9, bc=bc, nproc=(2, 2, 1))
+    o4 = Oracle(dk4)
+    o4.init()
+    for rk in range(o4.nranks):
+        info = o4.rank_info(rk)
+        sel = np.ones(len(p), dtype=bool)
+        for d in range(2):
+            sel &= (p[:, d] >= info["min_local"][d]) & (p[:, d] < info["max_local"][d])
+        o4.set_particles(rk, 0, p[sel])
+    for kind in ("ekbar", "temperature", "temperature_y"):
+        ref = _interior(o1.moment(0, kind, 0)).reshape(12, 16)
+        full = np.zeros((12, 16))
+        for rk in range(o4.nranks):
+            info = o4.rank_info(rk)
+            a = _interior(o4.moment(rk, kind, 0)).reshape(info["n"][1], info["n"][0])
+            x0, y0 = info["gmin"][0] - 1, info["gmin"][1] - 1
+            full[y0:y0 + a.shape[0], x0:x0 + a.shape[1]] = a
+        assert np.abs(full - ref).max() <= 1e-12 * np.abs(ref).max(), kind
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n,bc", [(1, (64,), "periodic"), (2, (32, 24), "periodic"), (2, (32, 24), "reflect"),
+                                        (3, (10, 9, 8), "periodic"), (3, (10, 9, 8), "reflect")])
+def test_ekbar_temperature_match_oracle_gpu(ndims, n, bc):
+    from tests.gpu_util import make_pair, rel_l2, run_both
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=2.0e9, bc=bc, two_species=True)
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 3)
+    for kind in ("ekbar", "temperature", "temperature_x", "temperature_y", "temperature_z"):
+        for isp in (-1, 0, 1):
+            ref = o.moment(0, kind, isp)
+            got = sim.moment(kind, isp)
+            assert rel_l2(_interior(got), _interior(ref)) <= 1e-12, (kind, isp)
+            assert rel_l2(got, ref) <= 1e-12, (kind, isp)
+
+
+@pytest.mark.gpu
+def test_ekbar_temperature_mixed_boundaries_gpu():
+    from tests.gpu_util import make_pair, rel_l2, run_both
+    dk = decks.thermal(2, (32, 24), ppc=5, temp_k=2.0e9, bc="reflect", two_species=True)
+    dk.species[1].bc_particle = ["open"] * 4
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 4)
+    for kind in ("ekbar", "temperature"):
+        for isp in (-1, 0, 1):
+            assert rel_l2(sim.moment(kind, isp), o.moment(0, kind, isp)) <= 1e-12, (kind, isp)
