@@ -103,6 +103,14 @@ def main():
         if tot != want:
             res["ok"] = False
             res["msgs"].append(f"species {isp}: global count {tot} != {want}")
+    # device-side diagnostics moments (collective: every rank takes part in the ghost-cell sums)
+    if dk.species:
+        for kind in ("number_density", "charge_density", "ekbar", "temperature", "temperature_y"):
+            for isp in [-1] + list(range(len(dk.species))):
+                e = rel_l2(sim.moment(kind, isp), o.moment(rank, kind, isp))
+                if not e <= 1e-12:
+                    res["ok"] = False
+                    res["msgs"].append(f"moment {kind} species {isp}: rel_l2 {e:.3e}")
     res["counts"] = [sim.count(i) for i in range(len(dk.species))]
     sim.close()
     dist.barrier()
