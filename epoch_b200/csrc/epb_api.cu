@@ -402,8 +402,12 @@ struct MomentOp {
   long long n;
   int nd, sz[3];
   double gmin[3], dx[3];
-  double scale;    // part_q (charge density), part_m (mass density)
-  int use_scale;   // 0: number density, wdata = weight
+  double scale;    // part_q (charge density, current), part_m (mass density)
+  int use_scale;   // 0: number density, wdata = weight; 1: scale * weight; 2: calc_per_species_current (:1132-1235),
+                   // wdata = part_q * weight * p(dir) / sqrt((m c)^2 + p^2)
+  int dir;
+  double part_mc;
+  const double *p[3];
   double *out;
 };
 __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp M) {
@@ -423,7 +427,12 @@ __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp
       if (cell[d] - 1 < 1 - NG || cell[d] + 1 > M.sz[d] - NG) ok = false;  // outside the allocated extent
     }
     if (!ok) continue;
-    const double wdata = M.use_scale ? M.scale * M.w[i] : M.w[i];
+    double wdata = M.use_scale ? M.scale * M.w[i] : M.w[i];
+    if (M.use_scale == 2) {
+      const double part_px = M.p[0][i], part_py = M.p[1][i], part_pz = M.p[2][i];
+      const double root = 1.0 / sqrt(M.part_mc * M.part_mc + part_px * part_px + part_py * part_py + part_pz * part_pz);
+      wdata = wdata * (M.dir == 0 ? part_px : M.dir == 1 ? part_py : part_pz) * root;
+    }
     if (M.nd == 1) {
       for (int ix = -1; ix <= 1; ix++) atomicAdd(M.out + fofs(M.sz, 1, cell[0] + ix, 1, 1), g[0][ix + 1] * wdata);
     } else if (M.nd == 2) {
@@ -448,6 +457,8 @@ struct Moment2Op {
   int mode;        // 3: ekbar (a0 += g wdata, a1 += g w); 4: temperature pass 1 (mean[q] += g w p/sqrt(m), cnt += g w);
                    // 5: pass 2 (sig += g sum_q (p/sqrt(m) - mean[q])^2, cnt += g)
   int dir;         // temperature: -1 all components, else one
+  int sub;         // mode 3: 0 ekbar; 1..6 ekflux -x,+x,-y,+y,-z,+z (:415-557); 7..9 average momentum px,py,pz (:1239-1317)
+  double flux_fac; // ekflux: xfac / yfac / zfac of the direction
   double part_mc, sqrt_part_m;
   double *a0, *a1;           // ekbar: data, wt; temperature: sigma, count
   double *mean[3];
@@ -472,13 +483,27 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
     if (!ok) continue;
     const double part_w = M.w[i];
     double wdata = 0.0, pm[3] = {0.0, 0.0, 0.0};
-    if (M.mode == 3) {
+    if (M.mode == 6) {  // calc_average_weight (:811-873): nearest cell only
+      const size_t o = fofs(M.sz, M.nd, cell[0], cell[1], cell[2]);
+      atomicAdd(M.a0 + o, part_w);
+      atomicAdd(M.a1 + o, 1.0);
+      continue;
+    }
+    if (M.mode == 3 && M.sub >= 7) {
+      wdata = part_w * M.p[M.sub - 7][i];
+    } else if (M.mode == 3) {
       const double fac = M.part_mc * part_w * c;
       const double part_ux = M.p[0][i] / M.part_mc, part_uy = M.p[1][i] / M.part_mc, part_uz = M.p[2][i] / M.part_mc;
       const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
       const double gamma_rel = sqrt(part_u2 + 1.0);
       const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
       wdata = gamma_rel_m1 * fac;
+      if (M.sub >= 1) {
+        const int a = (M.sub - 1) / 2;
+        const double part_flux = M.flux_fac * (a == 0 ? part_ux : a == 1 ? part_uy : part_uz) / gamma_rel;
+        if ((M.sub - 1) % 2 == 0) wdata = -wdata * fmin(part_flux, 0.0);
+        else wdata = wdata * fmax(part_flux, 0.0);
+      }
     } else {
       for (int q = 0; q < 3; q++) pm[q] = M.p[q][i] / M.sqrt_part_m;
     }
@@ -1830,10 +1855,20 @@ static void moment2_fill(epb_handle *h, int is, Moment2Op &M) {
   M.sqrt_part_m = sqrt(S.cfg.mass);
 }
 
-// calc_ekbar (io/calc_df.F90:116-221): result in work array 9
-static int calc_ekbar_dev(epb_handle *h, int ispecies) {
+// calc_ekbar (io/calc_df.F90:116-221, sub 0), calc_ekflux (:415-557, sub 1..6), calc_average_momentum (:1239-1317,
+// sub 7..9), calc_average_weight (:811-873, sub 10: nearest cell, no ghost-cell sums or fill): result in work array 9
+static int calc_ratio_dev(epb_handle *h, int ispecies, int sub) {
   const epb_config &c = h->cfg;
   const int A = 9, WT = 10;
+  const bool avg_weight = sub == 10;
+  double flux_fac = 0.0;
+  if (sub >= 1 && sub <= 6) {
+    const int a = (sub - 1) / 2, nd = c.ndims;
+    const double cc = EPB_C, dx = c.dx[0], dy = c.dx[1], dz = c.dx[2];
+    if (nd == 1) flux_fac = a == 0 ? cc : cc * dx;
+    else if (nd == 2) flux_fac = a == 0 ? cc * dy : a == 1 ? cc * dx : cc * dx * dy;
+    else flux_fac = a == 0 ? cc * dy * dz : a == 1 ? cc * dx * dz : cc * dx * dy;
+  }
   EPB_CUDA(h, cudaMemsetAsync(h->f(A), 0, 2 * h->fsize * sizeof(double), h->stream));
   const bool spec_sum = ispecies < 0;
   for (int is = spec_sum ? 0 : ispecies; is < (spec_sum ? (int)h->sp.size() : ispecies + 1); is++) {
@@ -1842,20 +1877,26 @@ static int calc_ekbar_dev(epb_handle *h, int ispecies) {
     if (S.n > 0) {
       Moment2Op M;
       moment2_fill(h, is, M);
-      M.mode = 3;
+      M.mode = avg_weight ? 6 : 3;
       M.dir = -1;
+      M.sub = sub;
+      M.flux_fac = flux_fac;
       M.a0 = h->f(A);
       M.a1 = h->f(WT);
       for (int q = 0; q < 3; q++) M.mean[q] = nullptr;
       k_moment2<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
       h->launches++;
     }
+    if (avg_weight) continue;
     int rc = moment_bcs_species(h, A, is);
     if (!rc) rc = moment_bcs_species(h, WT, is);
     if (rc) return rc;
   }
-  int rc = moment_bcs_all(h, A);
-  if (!rc) rc = moment_bcs_all(h, WT);
+  int rc = EPB_OK;
+  if (!avg_weight) {
+    rc = moment_bcs_all(h, A);
+    if (!rc) rc = moment_bcs_all(h, WT);
+  }
   if (rc) return rc;
   MomentPostOp P;
   P.op = 0; P.n = h->fsize; P.a = h->f(A); P.b = h->f(WT);
@@ -1883,6 +1924,8 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
         moment2_fill(h, is, M);
         M.mode = pass == 0 ? 4 : 5;
         M.dir = dir;
+        M.sub = 0;
+        M.flux_fac = 0.0;
         M.a0 = h->f(SIG);
         M.a1 = h->f(CNT);
         for (int q = 0; q < 3; q++) M.mean[q] = h->f(MEAN0 + q);
@@ -1932,11 +1975,17 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
 }
 
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
-  if (!h || !host || kind < 0 || kind > 7 || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
-  if (kind >= EPB_MOMENT_EKBAR) {
-    int rc = kind == EPB_MOMENT_EKBAR ? calc_ekbar_dev(h, ispecies) : calc_temperature_dev(h, ispecies, kind - 5);
+  if (!h || !host || kind < 0 || kind > EPB_MOMENT_AVERAGE_WEIGHT || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
+  const bool density_like = kind <= EPB_MOMENT_MASS_DENSITY || (kind >= EPB_MOMENT_JX && kind <= EPB_MOMENT_JZ);
+  if (!density_like) {
+    int rc;
+    bool fill = true;  // field_zero_gradient(data_array, c_stagger_centre, bd): not for temperature / average weight
+    if (kind == EPB_MOMENT_EKBAR) rc = calc_ratio_dev(h, ispecies, 0);
+    else if (kind <= EPB_MOMENT_TEMPERATURE_Z) { rc = calc_temperature_dev(h, ispecies, kind - 5); fill = false; }
+    else if (kind <= EPB_MOMENT_AVERAGE_PZ) rc = calc_ratio_dev(h, ispecies, kind - 7);  // ekflux 1..6, momentum 7..9
+    else { rc = calc_ratio_dev(h, ispecies, 10); fill = false; }
     if (rc) return rc;
-    if (kind == EPB_MOMENT_EKBAR) {  // field_zero_gradient(data_array, c_stagger_centre, bd); none for the temperature
+    if (fill) {
       int rcz = moment_zero_gradient(h, 9);
       if (rcz) return rcz;
     }
@@ -1949,6 +1998,7 @@ int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
   const int WK = 9;
   double *wk = h->f(WK);
   EPB_CUDA(h, cudaMemsetAsync(wk, 0, h->fsize * sizeof(double), h->stream));
+  const bool current = kind >= EPB_MOMENT_JX;
   double idx;
   if (kind == EPB_MOMENT_NUMBER_DENSITY) {  // vol = dx * dy; idx = 1 / vol
     double vol = c.dx[0];
@@ -1957,6 +2007,7 @@ int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
   } else {                                  // idx = 1 / dx / dy
     idx = 1.0 / c.dx[0];
     for (int d = 1; d < c.ndims; d++) idx = idx / c.dx[d];
+    if (current) idx = EPB_C * idx;       // calc_per_species_current: idx = c * idx
   }
   const bool spec_sum = ispecies < 0;
   for (int is = spec_sum ? 0 : ispecies; is < (spec_sum ? (int)h->sp.size() : ispecies + 1); is++) {
@@ -1973,8 +2024,11 @@ int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
       M.w = S.buf[S.cur][6];
       M.n = S.n;
       M.nd = c.ndims;
-      M.use_scale = kind != EPB_MOMENT_NUMBER_DENSITY;
-      M.scale = kind == EPB_MOMENT_CHARGE_DENSITY ? S.cfg.charge : S.cfg.mass;
+      M.use_scale = current ? 2 : kind != EPB_MOMENT_NUMBER_DENSITY;
+      M.scale = (kind == EPB_MOMENT_CHARGE_DENSITY || current) ? S.cfg.charge : S.cfg.mass;
+      M.dir = current ? kind - EPB_MOMENT_JX : 0;
+      M.part_mc = EPB_C * S.cfg.mass;
+      for (int d = 0; d < 3; d++) M.p[d] = S.buf[S.cur][3 + d];
       M.out = wk;
       k_moment<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
       h->launches++;

@@ -180,7 +180,16 @@ enum { EPB_MOMENT_NUMBER_DENSITY = 0, EPB_MOMENT_CHARGE_DENSITY = 1, EPB_MOMENT_
        /* calc_ekbar (io/calc_df.F90:116-221): mean kinetic energy per cell, J */
        EPB_MOMENT_EKBAR = 3,
        /* calc_temperature (:877-1128), K: all momentum components (dof 3), or direction x / y / z (dof 1) */
-       EPB_MOMENT_TEMPERATURE = 4, EPB_MOMENT_TEMPERATURE_X = 5, EPB_MOMENT_TEMPERATURE_Y = 6, EPB_MOMENT_TEMPERATURE_Z = 7 };
+       EPB_MOMENT_TEMPERATURE = 4, EPB_MOMENT_TEMPERATURE_X = 5, EPB_MOMENT_TEMPERATURE_Y = 6, EPB_MOMENT_TEMPERATURE_Z = 7,
+       /* calc_ekflux (:415-557), W/m^2-like flux of kinetic energy through -x, +x, -y, +y, -z, +z */
+       EPB_MOMENT_EKFLUX_XM = 8, EPB_MOMENT_EKFLUX_XP = 9, EPB_MOMENT_EKFLUX_YM = 10, EPB_MOMENT_EKFLUX_YP = 11,
+       EPB_MOMENT_EKFLUX_ZM = 12, EPB_MOMENT_EKFLUX_ZP = 13,
+       /* calc_average_momentum (:1239-1317), direction x / y / z */
+       EPB_MOMENT_AVERAGE_PX = 14, EPB_MOMENT_AVERAGE_PY = 15, EPB_MOMENT_AVERAGE_PZ = 16,
+       /* calc_per_species_current (:1132-1235), direction x / y / z */
+       EPB_MOMENT_JX = 17, EPB_MOMENT_JY = 18, EPB_MOMENT_JZ = 19,
+       /* calc_average_weight (:811-873): nearest cell, no ghost-cell sums */
+       EPB_MOMENT_AVERAGE_WEIGHT = 20 };
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host);
 
 /* -- instrumentation ---------------------------------------------------------------

@@ -1609,12 +1609,25 @@ static inline void stencil3(int nd, const int cell[3], const double g[3][3], F &
   }
 }
 
-// calc_ekbar, io/calc_df.F90:116-221: mean kinetic energy per cell = sum(g (gamma-1) m c^2 w) / MAX(sum(g w), c_tiny)
-void calc_ekbar(World &w, int species) {
+// The "ratio" family of io/calc_df.F90: sum(g wdata) / MAX(sum(g w), c_tiny), zero-gradient ghosts.
+//   sub 0      calc_ekbar :116-221            wdata = (gamma - 1) m c^2 w
+//   sub 1..6   calc_ekflux :415-557           direction -x, +x, -y, +y, -z, +z: wdata = -/+ wdata * MIN/MAX(flux, 0),
+//                                             flux = xfac u_x / gamma (xfac = c dy, yfac = c dx, zfac = c dx dy in 2D;
+//                                             1D: c, c dx, c dx; 3D: c dy dz, c dx dz, c dx dy)
+//   sub 7..9   calc_average_momentum :1239-1317  wdata = w p(direction)
+void calc_ratio(World &w, int species, int sub) {
   const int nd = w.nd;
   for (Rank &R : w.r) {
     std::fill(R.f[WK].v.begin(), R.f[WK].v.end(), 0.0);
     std::fill(R.f[WK1].v.begin(), R.f[WK1].v.end(), 0.0);
+  }
+  double flux_fac = 0.0;
+  if (sub >= 1 && sub <= 6) {
+    const int a = (sub - 1) / 2;
+    const double dx = w.d[0], dy = nd >= 2 ? w.d[1] : 0.0, dz = nd >= 3 ? w.d[2] : 0.0;
+    if (nd == 1) flux_fac = a == 0 ? c : c * dx;
+    else if (nd == 2) flux_fac = a == 0 ? c * dy : a == 1 ? c * dx : c * dx * dy;
+    else flux_fac = a == 0 ? c * dy * dz : a == 1 ? c * dx * dz : c * dx * dy;
   }
   const bool spec_sum = species < 0;
   for (int is = spec_sum ? 0 : species; is < (spec_sum ? (int)w.sp.size() : species + 1); is++) {
@@ -1625,12 +1638,23 @@ void calc_ekbar(World &w, int species) {
       Arr &a = R.f[WK], &wt = R.f[WK1];
       for (const Particle &P : R.part[is]) {
         const double part_w = P.w;
-        const double fac = part_mc * part_w * c;
-        const double part_ux = P.p[0] / part_mc, part_uy = P.p[1] / part_mc, part_uz = P.p[2] / part_mc;
-        const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
-        const double gamma_rel = std::sqrt(part_u2 + 1.0);
-        const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
-        const double wdata = gamma_rel_m1 * fac;
+        double wdata;
+        if (sub <= 6) {
+          const double fac = part_mc * part_w * c;
+          const double part_ux = P.p[0] / part_mc, part_uy = P.p[1] / part_mc, part_uz = P.p[2] / part_mc;
+          const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+          const double gamma_rel = std::sqrt(part_u2 + 1.0);
+          const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
+          wdata = gamma_rel_m1 * fac;
+          if (sub >= 1) {
+            const double u[3] = {part_ux, part_uy, part_uz};
+            const double part_flux = flux_fac * u[(sub - 1) / 2] / gamma_rel;
+            if ((sub - 1) % 2 == 0) wdata = -wdata * std::min(part_flux, 0.0);
+            else wdata = wdata * std::max(part_flux, 0.0);
+          }
+        } else {
+          wdata = part_w * P.p[sub - 7];
+        }
         int cell[3];
         double g[3][3];
         particle_to_grid(w, R, P, cell, g);
@@ -1649,6 +1673,63 @@ void calc_ekbar(World &w, int species) {
   for (Rank &R : w.r)
     for (size_t q = 0; q < R.f[WK].v.size(); q++) R.f[WK].v[q] = R.f[WK].v[q] / std::max(R.f[WK1].v[q], c_tiny);
   for (int i = 0; i < 2 * nd; i++) field_mirror(w, WK, i, +1.0);
+}
+
+// calc_per_species_current, io/calc_df.F90:1132-1235: q w c p_dir / sqrt((m c)^2 + p^2) on the triangle stencil,
+// scaled by c / dx / dy
+void calc_species_current(World &w, int species, int dir) {
+  const int nd = w.nd;
+  for (Rank &R : w.r) std::fill(R.f[WK].v.begin(), R.f[WK].v.end(), 0.0);
+  double idx = 1.0 / w.d[0];
+  for (int d = 1; d < nd; d++) idx = idx / w.d[d];
+  const bool spec_sum = species < 0;
+  for (int is = spec_sum ? 0 : species; is < (spec_sum ? (int)w.sp.size() : species + 1); is++) {
+    const SpeciesCfg &S = w.sp[is];
+    if (spec_sum && S.zero_current) continue;
+    const double part_mc = c * S.mass;
+    for (Rank &R : w.r) {
+      Arr &a = R.f[WK];
+      for (const Particle &P : R.part[is]) {
+        double wdata = S.charge * P.w;
+        const double root = 1.0 / std::sqrt(part_mc * part_mc + P.p[0] * P.p[0] + P.p[1] * P.p[1] + P.p[2] * P.p[2]);
+        wdata = wdata * P.p[dir] * root;
+        int cell[3];
+        double g[3][3];
+        particle_to_grid(w, R, P, cell, g);
+        stencil3(nd, cell, g, [&](int i, int j, int k, double gg) { a(i, j, k) = a(i, j, k) + gg * wdata; });
+      }
+    }
+    calc_boundary_species(w, WK, S);
+  }
+  calc_boundary_all(w, WK);
+  idx = c * idx;
+  for (Rank &R : w.r)
+    for (double &v : R.f[WK].v) v = v * idx;
+  for (int i = 0; i < 2 * nd; i++) field_mirror(w, WK, i, +1.0);
+}
+
+// calc_average_weight, io/calc_df.F90:811-873: nearest cell, no ghost-cell sums, no ghost fill
+void calc_average_weight(World &w, int species) {
+  const int nd = w.nd;
+  for (Rank &R : w.r) {
+    std::fill(R.f[WK].v.begin(), R.f[WK].v.end(), 0.0);
+    std::fill(R.f[WK1].v.begin(), R.f[WK1].v.end(), 0.0);
+  }
+  const bool spec_sum = species < 0;
+  for (int is = spec_sum ? 0 : species; is < (spec_sum ? (int)w.sp.size() : species + 1); is++) {
+    if (spec_sum && w.sp[is].zero_current) continue;
+    for (Rank &R : w.r)
+      for (const Particle &P : R.part[is]) {
+        int cell[3] = {1, 1, 1};
+        for (int d = 0; d < nd; d++)
+          cell[d] = (int)std::floor((P.pos[d] - R.grid_min_local[d]) / w.d[d] + 0.5) + 1;
+        R.f[WK](cell[0], cell[1], cell[2]) = R.f[WK](cell[0], cell[1], cell[2]) + P.w;
+        R.f[WK1](cell[0], cell[1], cell[2]) = R.f[WK1](cell[0], cell[1], cell[2]) + 1.0;
+      }
+  }
+  const double c_tiny = std::numeric_limits<double>::min();
+  for (Rank &R : w.r)
+    for (size_t q = 0; q < R.f[WK].v.size(); q++) R.f[WK].v[q] = R.f[WK].v[q] / std::max(R.f[WK1].v[q], c_tiny);
 }
 
 // calc_temperature, io/calc_df.F90:877-1128: dir < 0: all three momentum components (dof 3), else one
@@ -2048,12 +2129,17 @@ void orc_cell_counts(void *h, int rk, int is, int32_t *out) {
   }
 }
 
-// kind 0..2: number / charge / mass density; 3: ekbar; 4: temperature; 5..7: temperature_x/y/z.  Result in WK.
+// kind 0..2: number / charge / mass density; 3: ekbar; 4: temperature; 5..7: temperature_x/y/z; 8..13: ekflux -x,+x,
+// -y,+y,-z,+z; 14..16: average px,py,pz; 17..19: per-species current jx,jy,jz; 20: average weight.  Result in WK.
 void orc_calc_moment(void *h, int kind, int species) {
   World &w = *(World *)h;
   if (kind <= 2) calc_moment(w, kind, species);
-  else if (kind == 3) calc_ekbar(w, species);
-  else calc_temperature(w, species, kind - 5);
+  else if (kind == 3) calc_ratio(w, species, 0);
+  else if (kind <= 7) calc_temperature(w, species, kind - 5);
+  else if (kind <= 13) calc_ratio(w, species, kind - 7);      // ekflux -x, +x, -y, +y, -z, +z
+  else if (kind <= 16) calc_ratio(w, species, kind - 7);      // average momentum px, py, pz (sub 7..9)
+  else if (kind <= 19) calc_species_current(w, species, kind - 17);
+  else calc_average_weight(w, species);
 }
 
 // KISS stream check hook: fills out[n] with successive random() values for `seed`

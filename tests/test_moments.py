@@ -298,3 +298,99 @@ def test_ekbar_temperature_mixed_boundaries_gpu():
     for kind in ("ekbar", "temperature"):
         for isp in (-1, 0, 1):
             assert rel_l2(sim.moment(kind, isp), o.moment(0, kind, isp)) <= 1e-12, (kind, isp)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# calc_ekflux (:415-557), calc_average_momentum (:1239-1317), calc_per_species_current (:1132-1235),
+# calc_average_weight (:811-873)
+# ---------------------------------------------------------------------------------------------------------
+EXTRA_KINDS = ("ekflux_xm", "ekflux_xp", "ekflux_ym", "ekflux_yp", "ekflux_zm", "ekflux_zp",
+               "average_px", "average_py", "average_pz", "jx", "jy", "jz", "average_weight")
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 7, 6))])
+def test_flux_momentum_current_weight_against_numpy(ndims, n):
+    from epoch_b200 import deck as D
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=2.0e9, drift=(3.0e-23, -1.0e-23, 2.0e-23))
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    o.push()
+    p = o.get_particles(0, 0)
+    s = dk.species[0]
+    w = p[:, -1]
+    mom = p[:, ndims:ndims + 3]
+    u = mom / (s.mass * D.c)
+    u2 = (u ** 2).sum(axis=1)
+    gamma = np.sqrt(u2 + 1.0)
+    ek = u2 / (gamma + 1.0) * s.mass * D.c ** 2
+    wt = _numpy_deposit(dk, p, w)
+    d = [dk.dx(q) for q in range(ndims)] + [1.0] * (3 - ndims)
+    if ndims == 1:
+        area = [1.0, d[0], d[0]]
+    elif ndims == 2:
+        area = [d[1], d[0], d[0] * d[1]]
+    else:
+        area = [d[1] * d[2], d[0] * d[2], d[0] * d[1]]
+    for a, ax in enumerate("xyz"):
+        flux = D.c * area[a] * u[:, a] / gamma
+        for sign, tag in ((-1, "m"), (+1, "p")):
+            ref = _numpy_deposit(dk, p, ek * w * np.maximum(sign * flux, 0.0)) / wt
+            got = _interior(o.moment(0, f"ekflux_{ax}{tag}", 0)).reshape(n[::-1])
+            assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (ax, tag)
+        ref = _numpy_deposit(dk, p, w * mom[:, a]) / wt
+        got = _interior(o.moment(0, f"average_p{ax}", 0)).reshape(n[::-1])
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), ax
+        vol = np.prod(d[:ndims])
+        ref = _numpy_deposit(dk, p, s.charge * w * D.c * mom[:, a] / np.sqrt((s.mass * D.c) ** 2 + (mom ** 2).sum(axis=1))) / vol
+        got = _interior(o.moment(0, f"j{ax}", 0)).reshape(n[::-1])
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), ax
+    # weighted back with the cell weights, the mean momentum per cell sums to the particles' total momentum
+    tot = (_interior(o.moment(0, "average_px", 0)).reshape(n[::-1]) * wt).sum()
+    assert abs(tot / (w * mom[:, 0]).sum() - 1.0) < 1e-12
+    # average weight: every particle of this deck has the same weight
+    aw = _interior(o.moment(0, "average_weight", 0))
+    cnt = o.cell_counts(0, 0)
+    assert np.allclose(aw[cnt.reshape(aw.shape) > 0], w[0], rtol=1e-14)
+    assert np.all(aw[cnt.reshape(aw.shape) == 0] == 0.0)
+
+
+def test_species_current_sums_to_deposited_current_scale():
+    """jx of calc_per_species_current is the instantaneous q n v; summed over the box it equals sum(q w v) / dV."""
+    from epoch_b200 import deck as D
+    dk = decks.thermal(2, (16, 12), ppc=6, temp_k=1.0e9, drift=(5.0e-23, 0.0, 0.0))
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    p = o.get_particles(0, 0)
+    s = dk.species[0]
+    v = D.c * p[:, 2] / np.sqrt((s.mass * D.c) ** 2 + (p[:, 2:5] ** 2).sum(axis=1))
+    total = _interior(o.moment(0, "jx", 0)).sum() * dk.dx(0) * dk.dx(1)
+    assert abs(total / (s.charge * (p[:, -1] * v).sum()) - 1.0) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n,bc", [(1, (64,), "periodic"), (2, (32, 24), "reflect"), (3, (10, 9, 8), "periodic")])
+def test_flux_momentum_current_weight_match_oracle_gpu(ndims, n, bc):
+    from tests.gpu_util import make_pair, rel_l2, run_both
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=2.0e9, bc=bc, two_species=True, drift=(3.0e-23, -1.0e-23, 2.0e-23))
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 3)
+    for kind in EXTRA_KINDS:
+        for isp in (-1, 0, 1):
+            ref = o.moment(0, kind, isp)
+            got = sim.moment(kind, isp)
+            assert rel_l2(got, ref) <= 1e-12, (kind, isp)
+            assert rel_l2(_interior(got), _interior(ref)) <= 1e-12, (kind, isp)
+
+
+@pytest.mark.gpu
+def test_flux_momentum_current_weight_mixed_boundaries_gpu():
+    from tests.gpu_util import make_pair, rel_l2, run_both
+    dk = decks.thermal(2, (32, 24), ppc=5, temp_k=2.0e9, bc="reflect", two_species=True)
+    dk.species[1].bc_particle = ["open"] * 4
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, 4)
+    for kind in ("ekflux_xp", "ekflux_ym", "average_pz", "jy", "average_weight"):
+        for isp in (-1, 0, 1):
+            assert rel_l2(sim.moment(kind, isp), o.moment(0, kind, isp)) <= 1e-12, (kind, isp)
