@@ -540,6 +540,50 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
         }
   }
 }
+// calc_poynt_flux (io/calc_df.F90:561-604, epoch1d :441-474, epoch3d :585-650): E x B / mu0 at the cell centres
+struct PoyntOp {
+  const double *f[6];
+  int nd, n[3], sz[3], dir;
+  double *out;
+};
+__device__ __forceinline__ double cell_centred(const PoyntOp &P, int field, int i, int j, int k) {
+  // the active axes the component is staggered along (setup.F90:124-134); lower axis first
+  int ax[2], na = 0;
+  for (int d = 0; d < P.nd; d++) {
+    const bool st = field < 3 ? (d == field) : (d != field - 3);
+    if (st) ax[na++] = d;
+  }
+  const double *a = P.f[field];
+  int q[3] = {i, j, k};
+  if (na == 0) return a[fofs(P.sz, P.nd, q[0], q[1], q[2])];
+  if (na == 1) {
+    const double hi = a[fofs(P.sz, P.nd, q[0], q[1], q[2])];
+    q[ax[0]] -= 1;
+    const double lo = a[fofs(P.sz, P.nd, q[0], q[1], q[2])];
+    return 0.5 * (lo + hi);
+  }
+  double v[4];
+  for (int s = 0; s < 4; s++) {  // (lo,lo), (hi,lo), (lo,hi), (hi,hi)
+    int r[3] = {i, j, k};
+    if (!(s & 1)) r[ax[0]] -= 1;
+    if (!(s & 2)) r[ax[1]] -= 1;
+    v[s] = a[fofs(P.sz, P.nd, r[0], r[1], r[2])];
+  }
+  return 0.25 * (v[0] + v[1] + v[2] + v[3]);
+}
+__global__ void __launch_bounds__(256) k_poynt_flux(const __grid_constant__ PoyntOp P) {
+  const double mu0 = 4.e-7 * 3.141592653589793238462643383279503;
+  const size_t total = (size_t)P.n[0] * P.n[1] * P.n[2];
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % P.n[0]) + 1;
+    const int iy = (int)((t / P.n[0]) % P.n[1]) + 1;
+    const int iz = (int)(t / ((size_t)P.n[0] * P.n[1])) + 1;
+    const int e1 = (P.dir + 1) % 3, e2 = (P.dir + 2) % 3;
+    const double e1c = cell_centred(P, e1, ix, iy, iz), e2c = cell_centred(P, e2, ix, iy, iz);
+    const double b1c = cell_centred(P, 3 + e1, ix, iy, iz), b2c = cell_centred(P, 3 + e2, ix, iy, iz);
+    P.out[fofs(P.sz, P.nd, ix, iy, iz)] = (e1c * b2c - e2c * b1c) / mu0;
+  }
+}
 // element-wise tails of calc_ekbar / calc_temperature
 struct MomentPostOp { int op; size_t n; double *a, *b, *m[3]; double k1, k2; };
 __global__ void __launch_bounds__(256) k_moment_post(const __grid_constant__ MomentPostOp P) {
@@ -1975,7 +2019,23 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
 }
 
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
-  if (!h || !host || kind < 0 || kind > EPB_MOMENT_AVERAGE_WEIGHT || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
+  if (!h || !host || kind < 0 || kind > EPB_MOMENT_POYNT_FLUX_Z || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;
+  if (kind >= EPB_MOMENT_POYNT_FLUX_X) {  // field-only: ghost cells of the result are zero
+    EPB_CUDA(h, cudaMemsetAsync(h->f(9), 0, h->fsize * sizeof(double), h->stream));
+    PoyntOp P;
+    for (int q = 0; q < 6; q++) P.f[q] = h->f(q);
+    P.nd = h->cfg.ndims;
+    for (int q = 0; q < 3; q++) { P.n[q] = h->cfg.n[q]; P.sz[q] = h->sz[q]; }
+    P.dir = kind - EPB_MOMENT_POYNT_FLUX_X;
+    P.out = h->f(9);
+    const size_t total = (size_t)P.n[0] * P.n[1] * P.n[2];
+    k_poynt_flux<<<nblocks(total, 148 * 16), 256, 0, h->stream>>>(P);
+    h->launches++;
+    EPB_CUDA(h, cudaMemcpyAsync(host, h->f(9), h->fsize * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    EPB_CUDA(h, cudaGetLastError());
+    return EPB_OK;
+  }
   const bool density_like = kind <= EPB_MOMENT_MASS_DENSITY || (kind >= EPB_MOMENT_JX && kind <= EPB_MOMENT_JZ);
   if (!density_like) {
     int rc;

@@ -264,7 +264,8 @@ class Simulation:
     MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2, "ekbar": 3, "temperature": 4,
                "temperature_x": 5, "temperature_y": 6, "temperature_z": 7,
                "ekflux_xm": 8, "ekflux_xp": 9, "ekflux_ym": 10, "ekflux_yp": 11, "ekflux_zm": 12, "ekflux_zp": 13,
-               "average_px": 14, "average_py": 15, "average_pz": 16, "jx": 17, "jy": 18, "jz": 19, "average_weight": 20}
+               "average_px": 14, "average_py": 15, "average_pz": 16, "jx": 17, "jy": 18, "jz": 19, "average_weight": 20,
+               "poynt_flux_x": 21, "poynt_flux_y": 22, "poynt_flux_z": 23}
 
     def moment(self, kind: str, isp: int = -1):
         """calc_number_density / calc_charge_density / calc_mass_density (io/calc_df.F90) computed on the device;

@@ -184,7 +184,8 @@ MODULE epoch_b200_mod
       INTEGER(C_INT) :: rc
     END FUNCTION
     ! kind: 0 number density, 1 charge density, 2 mass density, 3 ekbar, 4 temperature, 5..7 temperature x/y/z,
-    ! 8..13 ekflux -x,+x,-y,+y,-z,+z, 14..16 average px,py,pz, 17..19 species current jx,jy,jz, 20 average weight;
+    ! 8..13 ekflux -x,+x,-y,+y,-z,+z, 14..16 average px,py,pz, 17..19 species current jx,jy,jz, 20 average weight,
+    ! 21..23 Poynting flux x,y,z;
     ! ispecies = -1: all species
     FUNCTION epb_calc_moment(handle, kind, ispecies, host) BIND(C, NAME='epb_calc_moment') RESULT(rc)
       IMPORT :: C_INT, C_PTR

@@ -189,7 +189,10 @@ enum { EPB_MOMENT_NUMBER_DENSITY = 0, EPB_MOMENT_CHARGE_DENSITY = 1, EPB_MOMENT_
        /* calc_per_species_current (:1132-1235), direction x / y / z */
        EPB_MOMENT_JX = 17, EPB_MOMENT_JY = 18, EPB_MOMENT_JZ = 19,
        /* calc_average_weight (:811-873): nearest cell, no ghost-cell sums */
-       EPB_MOMENT_AVERAGE_WEIGHT = 20 };
+       EPB_MOMENT_AVERAGE_WEIGHT = 20,
+       /* calc_poynt_flux (:561-604): (E x B) / mu0 at the cell centres, direction x / y / z; ispecies ignored,
+        * ghost cells of the result are zero (the reference leaves them undefined) */
+       EPB_MOMENT_POYNT_FLUX_X = 21, EPB_MOMENT_POYNT_FLUX_Y = 22, EPB_MOMENT_POYNT_FLUX_Z = 23 };
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host);
 
 /* -- instrumentation ---------------------------------------------------------------

@@ -1814,6 +1814,42 @@ void calc_temperature(World &w, int species, int dir) {
       R.f[SIG].v[t] = R.f[SIG].v[t] / std::max(R.f[CNT].v[t], 1.e-6) / kb / dof;
 }
 
+// calc_poynt_flux, io/calc_df.F90:561-604 (epoch1d :441-474, epoch3d :585-650): E x B / mu0 at the cell centre of
+// the interior cells.  Every component is averaged over the active axes it is staggered along (setup.F90:124-134):
+// two-point means, four-point means in the order (lo,lo) + (hi,lo) + (lo,hi) + (hi,hi) with the lower axis first.
+// data_array is INTENT(OUT) and only 1..n is written: the ghost cells are returned as zero here.
+static double cell_centred(const Arr &a, int nd, int field, int i, int j, int k) {
+  int ax[2], na = 0;
+  for (int d = 0; d < nd; d++)
+    if (stagger(d, field)) ax[na++] = d;
+  auto at = [&](int s0, int s1) {
+    int q[3] = {i, j, k};
+    if (na >= 1) q[ax[0]] -= s0;
+    if (na >= 2) q[ax[1]] -= s1;
+    return a(q[0], q[1], q[2]);
+  };
+  if (na == 0) return at(0, 0);
+  if (na == 1) return 0.5 * (at(1, 0) + at(0, 0));
+  return 0.25 * (at(1, 1) + at(0, 1) + at(1, 0) + at(0, 0));
+}
+void calc_poynt_flux(World &w, int dir) {
+  const int nd = w.nd;
+  const double mu0 = 4.e-7 * pi;
+  for (Rank &R : w.r) {
+    Arr &out = R.f[WK];
+    std::fill(out.v.begin(), out.v.end(), 0.0);
+    for (int k = 1; k <= R.n[2]; k++)
+      for (int j = 1; j <= R.n[1]; j++)
+        for (int i = 1; i <= R.n[0]; i++) {
+          const int e1 = EX + (dir + 1) % 3, e2 = EX + (dir + 2) % 3;
+          const int b1 = BX + (dir + 1) % 3, b2 = BX + (dir + 2) % 3;
+          const double e1c = cell_centred(R.f[e1], nd, e1, i, j, k), e2c = cell_centred(R.f[e2], nd, e2, i, j, k);
+          const double b1c = cell_centred(R.f[b1], nd, b1, i, j, k), b2c = cell_centred(R.f[b2], nd, b2, i, j, k);
+          out(i, j, k) = (e1c * b2c - e2c * b1c) / mu0;  // x: ey bz - ez by; y: ez bx - ex bz; z: ex by - ey bx
+        }
+  }
+}
+
 void auto_load(World &w) {
   const int nd = w.nd;
   for (size_t is = 0; is < w.sp.size(); is++) {
@@ -2130,7 +2166,7 @@ void orc_cell_counts(void *h, int rk, int is, int32_t *out) {
 }
 
 // kind 0..2: number / charge / mass density; 3: ekbar; 4: temperature; 5..7: temperature_x/y/z; 8..13: ekflux -x,+x,
-// -y,+y,-z,+z; 14..16: average px,py,pz; 17..19: per-species current jx,jy,jz; 20: average weight.  Result in WK.
+// -y,+y,-z,+z; 14..16: average px,py,pz; 17..19: per-species current jx,jy,jz; 20: average weight; 21..23: Poynting flux x,y,z.  Result in WK.
 void orc_calc_moment(void *h, int kind, int species) {
   World &w = *(World *)h;
   if (kind <= 2) calc_moment(w, kind, species);
@@ -2139,7 +2175,8 @@ void orc_calc_moment(void *h, int kind, int species) {
   else if (kind <= 13) calc_ratio(w, species, kind - 7);      // ekflux -x, +x, -y, +y, -z, +z
   else if (kind <= 16) calc_ratio(w, species, kind - 7);      // average momentum px, py, pz (sub 7..9)
   else if (kind <= 19) calc_species_current(w, species, kind - 17);
-  else calc_average_weight(w, species);
+  else if (kind == 20) calc_average_weight(w, species);
+  else calc_poynt_flux(w, kind - 21);
 }
 
 // KISS stream check hook: fills out[n] with successive random() values for `seed`

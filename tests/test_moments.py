@@ -394,3 +394,69 @@ def test_flux_momentum_current_weight_mixed_boundaries_gpu():
     for kind in ("ekflux_xp", "ekflux_ym", "average_pz", "jy", "average_weight"):
         for isp in (-1, 0, 1):
             assert rel_l2(sim.moment(kind, isp), o.moment(0, kind, isp)) <= 1e-12, (kind, isp)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# calc_poynt_flux (:561-604; epoch1d :441-474; epoch3d :585-650)
+# ---------------------------------------------------------------------------------------------------------
+def _cc(a, ndims, stag_axes):
+    """Cell-centred value on the interior: mean over the active axes the component is staggered along.
+    a is indexed [k][j][i] with 5 ghost cells on active axes; axis d lives in numpy axis 2 - d."""
+    out = a
+    n_avg = 0
+    for d in stag_axes:
+        if d < ndims:
+            out = out + np.roll(out, 1, axis=2 - d)
+            n_avg += 1
+    return _interior(out * (0.5 ** n_avg))
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 7, 6))])
+def test_poynt_flux_against_numpy(ndims, n):
+    dk = decks.thermal(ndims, n, ppc=1)
+    o = Oracle(dk)
+    o.init()
+    rng = np.random.default_rng(11)
+    f = {}
+    for name in ("ex", "ey", "ez", "bx", "by", "bz"):
+        a = o.field(0, name)
+        a[...] = rng.normal(size=a.shape) * (1e9 if name[0] == "e" else 3.0)
+        f[name] = a.copy()
+    mu0 = 4.0e-7 * np.pi
+    cc = {"ex": _cc(f["ex"], ndims, (0,)), "ey": _cc(f["ey"], ndims, (1,)), "ez": _cc(f["ez"], ndims, (2,)),
+          "bx": _cc(f["bx"], ndims, (1, 2)), "by": _cc(f["by"], ndims, (0, 2)), "bz": _cc(f["bz"], ndims, (0, 1))}
+    ref = {"x": (cc["ey"] * cc["bz"] - cc["ez"] * cc["by"]) / mu0,
+           "y": (cc["ez"] * cc["bx"] - cc["ex"] * cc["bz"]) / mu0,
+           "z": (cc["ex"] * cc["by"] - cc["ey"] * cc["bx"]) / mu0}
+    for ax in "xyz":
+        full = o.moment(0, f"poynt_flux_{ax}", -1)
+        got = _interior(full)
+        assert np.abs(got - ref[ax]).max() <= 1e-13 * np.abs(ref[ax]).max(), ax
+        assert np.abs(full).sum() == np.abs(got).sum()          # ghost cells zero
+
+
+def test_poynt_flux_of_a_plane_wave():
+    """E = E0 y, B = E0/c z  =>  S = E0^2 / (mu0 c) along +x, nothing along y and z."""
+    from epoch_b200 import deck as D
+    dk = decks.thermal(2, (16, 12), ppc=1)
+    o = Oracle(dk)
+    o.init()
+    e0 = 2.0e9
+    o.field(0, "ey")[...] = e0
+    o.field(0, "bz")[...] = e0 / D.c
+    sx = _interior(o.moment(0, "poynt_flux_x", -1))
+    assert np.allclose(sx, e0 ** 2 / (4.0e-7 * np.pi * D.c), rtol=1e-14)
+    assert np.all(_interior(o.moment(0, "poynt_flux_y", -1)) == 0.0)
+    assert np.all(_interior(o.moment(0, "poynt_flux_z", -1)) == 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (32, 24)), (3, (10, 9, 8))])
+def test_poynt_flux_matches_oracle_gpu(ndims, n):
+    """No atomics on this path: bit-exact."""
+    from tests.gpu_util import make_pair, set_random_fields
+    dk = decks.thermal(ndims, n, ppc=2)
+    o, sim = make_pair(dk, strict=True)
+    set_random_fields(o, sim, dk, seed=4)
+    for ax in "xyz":
+        assert np.array_equal(sim.moment(f"poynt_flux_{ax}", -1), o.moment(0, f"poynt_flux_{ax}", -1)), ax
