@@ -405,3 +405,113 @@ def run(deck: Deck, backend, local_ranks: Sequence[int], on_dump: Optional[Calla
     if on_dump is not None:
         on_dump(step, time)
     return step, time
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Load balancing, host half: the slab boundaries EPOCH's balancer chooses from a load profile.
+# The device half (histogram of the resident particles, remap of fields and particles) is not built yet; these
+# functions are what it will call, restated from housekeeping/balance.F90 so that a re-cut domain matches EPOCH's.
+# ---------------------------------------------------------------------------------------------------------
+PUSH_PER_FIELD = 5          # shared_data.F90:821
+NCELL_MIN = (3 + 1) // 2 + 1  # constants.F90:562 with png = 3 (triangle shape)
+
+
+def load_profile(cell_index, n_global: int, n_other_global: int, ng: int = NG):
+    """get_load_x / get_load_y (balance.F90:1766-1844) from the particles' global cell indices along one axis.
+
+    cell_index: FLOOR((pos - x_grid_min) / dx + 1.5) of every particle of every species (1-based global cell, ghost
+    cells of an open boundary included), already summed over the ranks.  Returns load(1-ng : n_global+ng) as a
+    numpy int64 array: push_per_field particles' worth per particle, plus one field column (n_other_global cells)
+    per interior cell."""
+    load = np.zeros(n_global + 2 * ng, dtype=np.int64)
+    idx = np.asarray(cell_index, dtype=np.int64) + ng - 1     # Fortran index `cell + ng` of load(1:), 0-based here
+    np.add.at(load, idx, 1)
+    load *= PUSH_PER_FIELD
+    load[ng:ng + n_global] += n_other_global
+    return load
+
+
+def calculate_breaks(load, nproc: int, ng: int = NG, ncell_min: int = NCELL_MIN):
+    """calculate_breaks (balance.F90:1948-2091): split a load profile load(1-ng : sz+ng) into nproc slabs.
+
+    Returns (mins, maxs), 1-based inclusive cell ranges like cell_x_min / cell_x_max.  Control flow as in the
+    reference: ideal load per slab, greedy cuts at the nearer side of the cell that crosses it, at least
+    ncell_min cells per slab, then single-cell perturbations of every cut while the max-min spread improves
+    (the EXITs leave the loop over the cuts, not the iteration), then the two sanity sweeps."""
+    load = np.asarray(load, dtype=np.int64)
+    sz = load.shape[0] - 2 * ng
+    ld = lambda i: int(load[i + ng - 1])                       # load(i), Fortran index
+    seg = lambda i0, i1: int(load[i0 + ng - 1:i1 + ng].sum())  # SUM(load(i0:i1))
+    mins = [1] * nproc
+    maxs = [sz] * nproc            # maxs[proc - 1] = maxs(proc)
+    if nproc < 2:
+        return mins, maxs
+    ideal = int(math.floor(float(seg(1, sz)) / nproc + 0.5))
+    proc, old, total = 0, 1, 0
+    for idim in range(1, sz + 1):
+        total_old = total
+        total = total + ld(idim)
+        if total >= ideal:
+            proc += 1
+            maxs[proc - 1] = idim - 1 if ideal - total_old < total - ideal else idim
+            nextra = old - maxs[proc - 1] + ncell_min
+            if nextra > 0:
+                maxs[proc - 1] += nextra
+            if proc == nproc - 1:
+                break
+            old = maxs[proc - 1]
+            total = total - ideal
+
+    def sweep_back():
+        o = sz
+        for p in range(nproc - 1, 0, -1):
+            if o - maxs[p - 1] < ncell_min:
+                maxs[p - 1] = o - ncell_min
+            o = maxs[p - 1]
+
+    def spread():
+        lmax, lmin, i0 = -1, None, 1
+        for p in range(1, nproc + 1):
+            i1 = maxs[p - 1]
+            v = seg(i0, i1) if i1 >= i0 else 0
+            lmax = max(lmax, v)
+            lmin = v if lmin is None else min(lmin, v)
+            i0 = i1 + 1
+        return lmax, lmin
+
+    sweep_back()
+    best = None                    # load_var_best = HUGE(1)
+    lmax = lmin = None             # undefined in the reference until a perturbation was possible
+    for _ in range(1000):
+        for i in range(1, nproc):
+            left = False
+            for sign in (-1, +1):
+                old_maxs = maxs[i - 1]
+                if sign < 0:
+                    o = 0 if i == 1 else maxs[i - 2]
+                    ok = old_maxs - o - 1 >= ng
+                else:
+                    o = maxs[i]
+                    ok = o - old_maxs - 1 >= ng
+                if ok:
+                    maxs[i - 1] = old_maxs + sign
+                    lmax, lmin = spread()
+                    if best is None or lmax - lmin < best:
+                        left = True
+                        break
+                    maxs[i - 1] = old_maxs
+            if left:
+                break
+        if lmax is not None and (best is None or lmax - lmin < best):
+            best = lmax - lmin
+        else:
+            break
+    sweep_back()
+    o = 0
+    for p in range(1, nproc):
+        if maxs[p - 1] - o < ncell_min:
+            maxs[p - 1] = o + ncell_min
+        o = maxs[p - 1]
+    for p in range(2, nproc + 1):
+        mins[p - 1] = maxs[p - 2] + 1
+    return mins, maxs
