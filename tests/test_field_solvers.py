@@ -260,3 +260,35 @@ def test_cowan_and_lehe_z_group_velocity_3d():
                 ts.append((s_ + 1) * dt); xcs.append(float((x[sel] * e2[sel]).sum() / e2[sel].sum()))
         vg_sim = np.polyfit(ts, xcs, 1)[0]
         assert np.isclose(vg_sim, vg, rtol=0.005), (solver, vg_sim, vg)
+
+
+@pytest.mark.parametrize("solver", ["yee", "lehe_x"])
+def test_group_velocity_1d_matches_reference_formulas(solver):
+    """epoch1d/tests/test_maxwell_solvers.py:35-36, :111-126: the packet of the 1D deck (nx = 240 over 24 um,
+    lambda = 0.5 um) moves with vg_lehe resp. vg_yee; the reference asserts rtol 0.022 (its recorded runs: yee
+    0.0211, lehe_x 0.0049 - through CPML lasers, which are outside the path; here a periodic box)."""
+    L, nx, lam, ng = 24e-6, 240, 0.5e-6, 5
+    dk = D.Deck(1, [nx], [-L / 2], [L / 2], ["periodic"] * 2, dt_multiplier=0.95, maxwell_solver=solver)
+    dx, dt = dk.dx(0), dk.dt()
+    k_l = 2 * np.pi / lam
+    dt_yee = 0.95 * dx / c
+    vg = {"lehe_x": c * (1.0 + 2.0 * (1.0 - c * dt_yee / dx) * (k_l * dx / 2.0) ** 2),
+          "yee": c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt_yee / dx * np.sin(k_l * dx / 2.0)) ** 2)}[solver]
+    assert np.isclose(dt, dt_yee, rtol=1e-14)          # epoch1d set_dt: both solvers run at 0.95 dx / c
+    o = Oracle(dk)
+    x_c = _packet(dk, o)
+    o.init()
+    ts, xs = [], []
+    for n in range(int(30e-15 / dt)):
+        o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+        if n % 5 == 4 and (n + 1) * dt > 12e-15:
+            ey = o.field(0, "ey").reshape(-1)[ng:-ng]
+            x = x_c[ng:-ng]
+            F = np.fft.fft(ey); m = ey.size
+            F[m // 2 + 1:] = 0.0; F[1:m // 2] *= 2.0
+            e2 = np.abs(np.fft.ifft(F)) ** 2
+            sel = np.abs(x - x[np.argmax(e2)]) <= 3.0e-6
+            ts.append((n + 1) * dt)
+            xs.append(float((x[sel] * e2[sel]).sum() / e2[sel].sum()))
+    vg_sim = np.polyfit(ts, xs, 1)[0]
+    assert np.isclose(vg_sim, vg, rtol=0.012), (solver, vg_sim, vg)
