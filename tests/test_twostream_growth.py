@@ -78,7 +78,7 @@ def mode_amplitude(e_interior, ndims, axis, k, xc):
 
 @pytest.mark.parametrize("ndims,axis", [(1, 0), (2, 1)])
 def test_twostream_growth_rate_oracle(ndims, axis):
-    dk, q, k, wbr, xc = setup(ndims, axis, ppc_axis=64 if ndims == 1 else 16)
+    dk, q, k, wbr, xc = setup(ndims, axis, **(dict(ppc_axis=64) if ndims == 1 else dict(ppc_axis=8, ntrans=5)))
     o = Oracle(dk)
     o.set_particles(0, 0, q)
     o.init()
