@@ -227,6 +227,16 @@ CONTAINS
 
     CALL b200_check(epb_abi_info(info))
     IF (info(1) /= C_SIZEOF(cfg)) CALL b200_check(1_C_INT)
+    ! The device layout is pos(1..ndims), p(1..3), weight: builds whose pack_particle carries anything else
+    ! (-DPER_SPECIES_WEIGHT, -DPER_PARTICLE_CHARGE_MASS, -DPARTICLE_ID, ..., partlist.F90:43-85) are refused
+    IF (nvar /= c_ndims + 4) THEN
+      IF (rank == 0) PRINT *, '*** ERROR *** epoch_b200: unsupported particle layout, nvar =', nvar
+      CALL abort_code(c_err_generic_error)
+    END IF
+#if defined(PARTICLE_SHAPE_TOPHAT) || defined(PARTICLE_SHAPE_BSPLINE3)
+    IF (rank == 0) PRINT *, '*** ERROR *** epoch_b200: only the default (triangle) particle shape is supported'
+    CALL abort_code(c_err_generic_error)
+#endif
 
     cfg%ndims = c_ndims
     cfg%n = (/ nx, ny, 1 /)
