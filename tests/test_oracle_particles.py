@@ -138,3 +138,54 @@ def test_per_species_current_bcs_are_consistent(bc, nproc):
         for r in range(a.nranks):
             x, y = a.interior(r, f), b.interior(r, f)
             assert np.max(np.abs(x - y)) <= 1e-13 * max(np.max(np.abs(x)), 1e-300), (f, r)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Exact identities of the Boris scheme (particles.F90:382-428): independent of any restatement
+# ---------------------------------------------------------------------------------------------------------
+def _one_push_uniform(ndims, e, b, temp_k=2.0e9):
+    n = {1: (16,), 2: (12, 10), 3: (8, 7, 6)}[ndims]
+    dk = decks.thermal(ndims, n, ppc=4, temp_k=temp_k)
+    dk.species[0].zero_current = True          # the fields stay uniform
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    for k, name in enumerate(("ex", "ey", "ez")):
+        o.field(0, name)[...] = e[k]
+    for k, name in enumerate(("bx", "by", "bz")):
+        o.field(0, name)[...] = b[k]
+    p0 = o.get_particles(0, 0)[:, ndims:ndims + 3]
+    o.push_only()
+    p1 = o.get_particles(0, 0)[:, ndims:ndims + 3]
+    return dk, p0, p1
+
+
+@pytest.mark.parametrize("ndims", [1, 2, 3])
+def test_boris_uniform_e_is_exact(ndims):
+    """B = 0: the two half kicks add up to p(t + dt) = p(t) + q E dt, whatever gamma is."""
+    e = np.array([3.0e10, -2.0e10, 1.0e10])
+    dk, p0, p1 = _one_push_uniform(ndims, e, np.zeros(3))
+    dp = dk.species[0].charge * e * dk.dt()
+    assert np.abs(p1 - p0 - dp).max() <= 2e-14 * np.abs(p1).max()
+
+
+@pytest.mark.parametrize("ndims", [1, 2, 3])
+def test_boris_rotation_angle_is_exact(ndims):
+    """E = 0: |p| is conserved to round-off and p_perp turns about B by exactly 2 atan(q B dt / (2 gamma m)),
+    p_parallel stays (Birdsall & Langdon's tan(theta/2) identity of the rotation :413-423)."""
+    b = np.array([120.0, -260.0, 310.0])
+    dk, p0, p1 = _one_push_uniform(ndims, np.zeros(3), b)
+    s = dk.species[0]
+    bn = b / np.linalg.norm(b)
+    assert np.abs(np.linalg.norm(p1, axis=1) / np.linalg.norm(p0, axis=1) - 1.0).max() <= 1e-14
+    par0, par1 = p0 @ bn, p1 @ bn
+    assert np.abs(par1 - par0).max() <= 2e-14 * np.abs(p0).max()
+    perp0, perp1 = p0 - np.outer(par0, bn), p1 - np.outer(par1, bn)
+    gamma = np.sqrt(1.0 + (p0 ** 2).sum(axis=1) / (s.mass * D.c) ** 2)
+    theta = 2.0 * np.arctan(s.charge * np.linalg.norm(b) * dk.dt() / (2.0 * gamma * s.mass))
+    # signed angle from perp0 to perp1 about bn; dp/dt = q v x B turns p about B by -q|B|/(gamma m) t
+    sin_a = np.einsum("ij,ij->i", np.cross(perp0, perp1), bn[None, :])
+    cos_a = np.einsum("ij,ij->i", perp0, perp1)
+    ang = np.arctan2(sin_a, cos_a)
+    assert np.abs(ang + theta).max() <= 1e-12
+    assert np.abs(theta).min() > 1e-3          # a visible turn, not a null test
