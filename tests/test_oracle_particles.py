@@ -189,3 +189,37 @@ def test_boris_rotation_angle_is_exact(ndims):
     ang = np.arctan2(sin_a, cos_a)
     assert np.abs(ang + theta).max() <= 1e-12
     assert np.abs(theta).min() > 1e-3          # a visible turn, not a null test
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (32,)), (2, (16, 12)), (3, (8, 7, 6))])
+def test_total_current_identity(ndims, n):
+    """The box total of the deposited current, which the continuity equation cannot see (it fixes div J only):
+    along a gridded axis  sum(J_a) dV = sum_p q w (x_a(t + 3dt/2) - x_a(t + dt/2)) / dt  (Esirkepov's weights
+    telescope), along an ignorable axis  sum(J_a) dV = sum_p q w v_a  (particles.F90:573, epoch1d :489-506)."""
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=5.0e8, drift=(4.0e-23, -2.0e-23, 3.0e-23))
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    s = dk.species[0]
+    rng = np.random.default_rng(2)
+    for name in ("ex", "ey", "ez", "bx", "by", "bz"):
+        a = o.field(0, name)
+        a[...] = rng.normal(size=a.shape) * (1e9 if name[0] == "e" else 3.0)
+    before = o.get_particles(0, 0)
+    o.push_only()
+    after = o.get_particles(0, 0)
+    o.current_finish()
+    dv = np.prod([dk.dx(d) for d in range(ndims)])
+    w = after[:, -1]
+    mom = after[:, ndims:ndims + 3]
+    gamma = np.sqrt(1.0 + (mom ** 2).sum(axis=1) / (s.mass * D.c) ** 2)
+    x_a = _half_positions(dk, before, s.mass, +1)      # x(t + dt/2) from the old state
+    x_b = _half_positions(dk, after, s.mass, +1)       # x(t + 3dt/2) from the new state
+    # `after` positions are wrapped into the box by particle_bcs only later (push_only): no unwrapping needed
+    for a, name in enumerate(("jx", "jy", "jz")):
+        total = o.interior(0, name).sum() * dv
+        if a < ndims:
+            want = s.charge * (w * (x_b[:, a] - x_a[:, a])).sum() / dk.dt()
+        else:
+            want = s.charge * (w * mom[:, a] / (gamma * s.mass)).sum()
+        assert abs(total / want - 1.0) <= 1e-11, (name, total, want)
