@@ -223,3 +223,77 @@ def test_total_current_identity(ndims, n):
         else:
             want = s.charge * (w * mom[:, a] / (gamma * s.mass)).sum()
         assert abs(total / want - 1.0) <= 1e-11, (name, total, want)
+
+
+def _coords(dk, o, name):
+    """Coordinates of every array element (ghost cells included) of field `name`, Yee-staggered as in
+    setup.F90:124-134; arrays are indexed [k][j][i]."""
+    stag = {"ex": (0,), "ey": (1,), "ez": (2,), "bx": (1, 2), "by": (0, 2), "bz": (0, 1)}[name]
+    shape = o.field(0, name).shape
+    out = []
+    for d in range(3):
+        m = shape[2 - d]
+        if d < dk.ndims:
+            x = dk.grid_min(d) + (np.arange(m) - 5) * dk.dx(d) + (0.5 * dk.dx(d) if d in stag else 0.0)
+        else:
+            x = np.zeros(m)
+        sh = [1, 1, 1]
+        sh[2 - d] = m
+        out.append(x.reshape(sh))
+    return out
+
+
+@pytest.mark.parametrize("ndims,n", [(1, (24,)), (2, (12, 10)), (3, (8, 7, 6))])
+def test_gather_is_exact_for_linear_fields(ndims, n):
+    """The quadratic B-spline gather (e_part.inc / b_part.inc) reproduces a field that is linear in space exactly,
+    at the position x(t + dt/2) and with each component's own Yee staggering: with B = 0 the push must give
+    dp = q E(x_half) dt per particle; with E = 0 and one linear B component the turn about that axis must be
+    2 atan(q B(x_half) dt / 2 gamma m)."""
+    dk = decks.thermal(ndims, n, ppc=3, temp_k=1.0e9)
+    s = dk.species[0]
+    s.zero_current = True
+    L = [dk.xmax[d] - dk.xmin[d] for d in range(ndims)]
+    rng = np.random.default_rng(5)
+
+    def linear(o, name, a, b):
+        X = _coords(dk, o, name)
+        v = a + sum(b[d] * X[d] / L[d] for d in range(ndims))
+        o.field(0, name)[...] = np.broadcast_to(v, o.field(0, name).shape)
+
+    def at(pos, a, b):
+        return a + sum(b[d] * pos[:, d] / L[d] for d in range(ndims))
+
+    # E
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    coef = {}
+    for name in ("ex", "ey", "ez"):
+        coef[name] = (rng.normal() * 1e10, rng.normal(size=3) * 1e10)
+        linear(o, name, *coef[name])
+    before = o.get_particles(0, 0)
+    o.push_only()
+    after = o.get_particles(0, 0)
+    xh = _half_positions(dk, before, s.mass, +1)
+    for k, name in enumerate(("ex", "ey", "ez")):
+        dp = after[:, ndims + k] - before[:, ndims + k]
+        want = s.charge * at(xh, *coef[name]) * dk.dt()
+        assert np.abs(dp - want).max() <= 1e-12 * np.abs(want).max(), name
+    # B, one component at a time
+    for m, name in enumerate(("bx", "by", "bz")):
+        o = Oracle(dk)
+        o.auto_load()
+        o.init()
+        a, b = 200.0, rng.normal(size=3) * 60.0
+        linear(o, name, a, b)
+        before = o.get_particles(0, 0)
+        o.push_only()
+        after = o.get_particles(0, 0)
+        xh = _half_positions(dk, before, s.mass, +1)
+        p0, p1 = before[:, ndims:ndims + 3], after[:, ndims:ndims + 3]
+        gamma = np.sqrt(1.0 + (p0 ** 2).sum(axis=1) / (s.mass * D.c) ** 2)
+        theta = 2.0 * np.arctan(s.charge * at(xh, a, b) * dk.dt() / (2.0 * gamma * s.mass))
+        i, j = (m + 1) % 3, (m + 2) % 3
+        ang = np.arctan2(p0[:, i] * p1[:, j] - p0[:, j] * p1[:, i], p0[:, i] * p1[:, i] + p0[:, j] * p1[:, j])
+        assert np.abs(ang + theta).max() <= 1e-11, name
+        assert np.abs(p1[:, m] - p0[:, m]).max() <= 1e-14 * np.abs(p0).max()
