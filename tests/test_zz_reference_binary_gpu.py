@@ -1,6 +1,7 @@
-"""Runs last (file name): the reference's custom-stencil decks replayed on the CUDA path against the numbers the
-reference binary printed.  Added after the round's GPU minutes were spent, hence xfail(strict=False) until it has
-been seen to pass on a B200; tests/test_oracle_golden.py pins the oracle on the same numbers."""
+"""Runs last (file name).  Tests added after the round's GPU minutes were spent, hence xfail(strict=False) until they
+have been seen to pass on a B200: the reference's custom-stencil decks replayed on the CUDA path against the numbers
+the reference binary printed (tests/test_oracle_golden.py pins the oracle on the same numbers), and the device's
+energy diagnostics / total energy history (tests/test_energy_history.py does it for the oracle)."""
 import numpy as np
 import pytest
 
@@ -34,3 +35,33 @@ def test_custom_stencil_decks_reproduce_the_reference_binary_gpu(tree):
     tx = np.array(tx)
     vg_sim = np.polyfit(tx[:, 0], tx[:, 1], 1)[0]
     assert np.isclose(vg_sim, recorded, rtol=1e-9, atol=0), vg_sim
+
+
+@pytest.mark.xfail(reason="added after the round's GPU minutes were spent: not yet run on a B200", strict=False)
+def test_energy_diagnostics_and_history_gpu():
+    """epb_field_energy / epb_kinetic_energy (calc_total_energy_sum, io/calc_df.F90:1321-1417) against numpy on the
+    same device state, and the total energy of the CUDA path alone over 300 steps (performance build)."""
+    from epoch_b200.pic import Simulation
+    from oracle.oracle import Oracle
+    from tests import decks
+    from tests.test_energy_history import energies
+    dk = decks.thermal(2, (24, 24), ppc=16, temp_k=1.0e7, two_species=True)
+    o = Oracle(dk)
+    o.auto_load()                                   # the loader only
+    sim = Simulation(dk, strict_fp=False, sort_interval=0, capacity_factor=1.5)
+    for isp in range(2):
+        sim.upload_species(isp, o.get_particles(0, isp))
+    sim.init()
+    tot = []
+    for s in range(300):
+        sim.step()
+        if s % 30 == 29:
+            fe, fb = sim.field_energy()
+            ke = [sim.kinetic_energy(isp) for isp in range(2)]
+            rfe, rfb, rke = energies(dk, {f: sim.interior(f) for f in ("ex", "ey", "ez", "bx", "by", "bz")},
+                                     [sim.download_species(isp) for isp in range(2)])
+            assert np.isclose(fe, rfe, rtol=1e-12) and np.isclose(fb, rfb, rtol=1e-12)
+            assert np.allclose(ke, rke, rtol=1e-12)
+            tot.append(fe + fb + sum(ke))
+    tot = np.array(tot)
+    assert np.abs(tot / tot[0] - 1.0).max() < 1.0e-4
