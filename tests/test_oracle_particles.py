@@ -297,3 +297,72 @@ def test_gather_is_exact_for_linear_fields(ndims, n):
         ang = np.arctan2(p0[:, i] * p1[:, j] - p0[:, j] * p1[:, i], p0[:, i] * p1[:, i] + p0[:, j] * p1[:, j])
         assert np.abs(ang + theta).max() <= 1e-11, name
         assert np.abs(p1[:, m] - p0[:, m]).max() <= 1e-14 * np.abs(p0).max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# particle_bcs (boundary.F90:1029-1462) on hand-placed particles
+# ---------------------------------------------------------------------------------------------------------
+def _bc_deck(bc):
+    dk = decks.thermal(1, (16,), ppc=1, temp_k=0.0, bc=bc, length=16.0e-6)
+    dk.species[0].zero_current = True
+    return dk
+
+
+def _place(o, xs, pxs):
+    p = o.get_particles(0, 0)[:len(xs)].copy()
+    p[:, 0] = xs
+    p[:, 1] = pxs
+    p[:, 2:4] = 0.0
+    o.set_particles(0, 0, p)
+    return p
+
+
+def test_reflecting_wall_mirrors_position_and_momentum():
+    dk = _bc_deck("reflect")
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    dx, dt = dk.dx(0), dk.dt()
+    v = 0.5 * D.c
+    px = D.m0 * v / np.sqrt(1 - 0.25)
+    # 0.3 dx from either wall, moving towards it: crosses by v dt - 0.3 dx
+    p = _place(o, [0.3 * dx, 16e-6 - 0.3 * dx, 8e-6], [-px, +px, px])
+    o.push()
+    q = o.get_particles(0, 0)
+    assert q.shape[0] == 3
+    q = q[np.argsort(q[:, 0])]
+    over = v * dt - 0.3 * dx
+    assert over > 0
+    assert np.isclose(q[0, 0], over, rtol=1e-12) and np.isclose(q[0, 1], +px, rtol=1e-14)              # 2 x_min - pos
+    assert np.isclose(q[2, 0], 16e-6 - over, rtol=1e-12) and np.isclose(q[2, 1], -px, rtol=1e-14)      # 2 x_max - pos
+    assert np.isclose(q[1, 0], 8e-6 + v * dt, rtol=1e-13)
+
+
+def test_periodic_wrap_and_open_deletion_threshold():
+    # periodic: leaves through x_max, re-enters at x_min + overshoot
+    dk = _bc_deck("periodic")
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    dx, dt = dk.dx(0), dk.dt()
+    v = 0.5 * D.c
+    px = D.m0 * v / np.sqrt(1 - 0.25)
+    _place(o, [16e-6 - 0.3 * dx], [px])
+    o.push()
+    q = o.get_particles(0, 0)
+    assert q.shape[0] == 1 and np.isclose(q[0, 0], v * dt - 0.3 * dx, rtol=1e-10)
+    # open: a particle stays alive (and on this rank) until it is beyond x_min_outer = x_min - ((1 + png) / 2) dx
+    # = x_min - 2 dx (utilities.f90:367-369, integer division), then it is deleted
+    dk = _bc_deck("open")
+    o = Oracle(dk)
+    o.auto_load()
+    o.init()
+    dx, dt = dk.dx(0), dk.dt()
+    _place(o, [0.3 * dx], [-px])
+    steps_inside = int(np.floor((0.3 * dx + 2.0 * dx) / (v * dt)))   # pushes after which it is still >= x_min_outer
+    for s in range(steps_inside):
+        o.push()
+        assert o.count(0, 0) == 1, s
+    assert o.get_particles(0, 0)[0, 0] < 0.0                         # outside the domain, not yet deleted
+    o.push()
+    assert o.count(0, 0) == 0
