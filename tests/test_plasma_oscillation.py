@@ -57,3 +57,46 @@ def test_cold_plasma_oscillation_frequency(ndims, n, axis):
     w, dt = _run(ndims, n, axis, ppc=40 if ndims < 3 else 8)
     assert WP * dt < 0.08
     assert abs(w / WP - 1.0) < 5.0e-3, (w, WP, w / WP)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Transverse branch: w^2 = w_p^2 + c^2 k^2 (couples the transverse current deposit to the Yee solver)
+# ---------------------------------------------------------------------------------------------------------
+def _run_transverse(ndims, n, axis, pol, nsteps=500, ppc=40):
+    """Wave vector along `axis`, particle velocity and E along `pol` != axis.  pol may be an ignorable axis (its
+    current is then q w v, particles.F90:573 / epoch1d :489-506) or a gridded one (Esirkepov along pol)."""
+    dx = 8.0e-8
+    sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=ppc, density=DENSITY, temp=(0.0, 0.0, 0.0))]
+    dk = D.Deck(ndims, list(n), [0.0] * ndims, [dx * k for k in n], ["periodic"] * (2 * ndims), species=sp)
+    o = Oracle(dk)
+    o.auto_load()
+    kw = 2.0 * math.pi / (dx * n[axis])
+    p = o.get_particles(0, 0)
+    p[:, ndims + pol] = D.m0 * 1.0e-3 * D.c * np.sin(kw * p[:, axis])
+    o.set_particles(0, 0, p)
+    o.init()
+    dt = dk.dt()
+    comp = ("ex", "ey", "ez")[pol]
+    x_c = dk.grid_min(axis) + np.arange(n[axis]) * dx       # E_pol is not staggered along the wave axis
+    shape = [1, 1, 1]
+    shape[2 - axis] = -1
+    basis = np.sin(kw * x_c).reshape(shape)
+    amp, ts = [], []
+    for s in range(int(nsteps * math.sqrt(ndims)) + 1):
+        o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+        amp.append(float(np.sum(o.interior(0, comp) * basis)))
+        ts.append((s + 1) * dt)
+    amp, ts = np.array(amp), np.array(ts)
+    zc = np.where(np.sign(amp[:-1]) != np.sign(amp[1:]))[0]
+    tz = ts[zc] + (ts[zc + 1] - ts[zc]) * amp[zc] / (amp[zc] - amp[zc + 1])
+    assert len(tz) >= 6, "not enough oscillations"
+    return math.pi / float(np.mean(np.diff(tz))), kw, dt
+
+
+@pytest.mark.parametrize("ndims,n,axis,pol", [(1, (64,), 0, 1), (1, (64,), 0, 2), (2, (64, 6), 0, 1), (2, (64, 6), 0, 2),
+                                              (2, (6, 64), 1, 0)])
+def test_transverse_plasma_wave_dispersion(ndims, n, axis, pol):
+    w, kw, dt = _run_transverse(ndims, n, axis, pol, ppc=40 if ndims == 1 else 16)
+    w_theory = math.sqrt(WP ** 2 + (D.c * kw) ** 2)
+    assert D.c * kw > WP                       # both terms matter: c k = 2.1 w_p
+    assert abs(w / w_theory - 1.0) < 5.0e-3, (w, w_theory, w / w_theory)
