@@ -185,6 +185,55 @@ extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
   return epb_comm_init(h, id128);
 }
 
+// get_load_x / get_load_y (balance.F90:1766-1844; epoch3d :2247-2362; epoch1d :980-1006): histogram of the
+// particles of all species over the GLOBAL cells of one axis, cell = FLOOR((pos - x_grid_min) / dx + 1.5) + ng
+namespace {
+__global__ void __launch_bounds__(256) k_load_profile(const double *x, long long n, double grid_min, double dx, int len,
+                                                      unsigned long long *load) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cell = __double2int_rd((x[i] - grid_min) / dx + 1.5) + NG;   // index into load(1:len)
+    if (cell >= 1 && cell <= len) atomicAdd(load + (cell - 1), 1ULL);
+  }
+}
+}  // namespace
+
+extern "C" int epb_load_profile(epb_handle *h, int axis, int64_t *load) {
+  if (!h || !load || axis < 0 || axis >= h->cfg.ndims) return EPB_ERR_ARG;
+  const epb_config &c = h->cfg;
+  const int len = c.n_global[axis] + 2 * NG;
+  unsigned long long *d = nullptr;
+  EPB_CUDA(h, cudaMalloc(&d, 2 * (size_t)len * sizeof(unsigned long long)));
+  cudaMemsetAsync(d, 0, 2 * (size_t)len * sizeof(unsigned long long), h->stream);
+  const double grid_min = c.gmin[axis] + c.dx[axis] / 2.0;   // x_grid_min (setup.F90:169,180; no CPML)
+  for (size_t is = 0; is < h->sp.size(); is++) {
+    SpeciesDev &S = h->sp[is];
+    if (S.n <= 0) continue;
+    long long blocks = (S.n + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    k_load_profile<<<(int)blocks, 256, 0, h->stream>>>(S.buf[S.cur][axis], S.n, grid_min, c.dx[axis], len, d);
+    h->launches++;
+  }
+  unsigned long long *res = d;
+  if (c.nranks > 1 && h->nccl) {   // MPI_ALLREDUCE(MPI_IN_PLACE, load, st, MPI_INTEGER8, MPI_SUM)
+    ncclResult_t r = ncclAllReduce(d, d + len, len, ncclInt64, ncclSum, (ncclComm_t)h->nccl, h->stream);
+    if (r != ncclSuccess) { cudaFree(d); return epb_fail(h, EPB_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r)); }
+    res = d + len;
+  }
+  cudaError_t e = cudaMemcpyAsync(load, res, (size_t)len * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return epb_fail(h, EPB_ERR_CUDA, "epb_load_profile: %s", cudaGetErrorString(e));
+  // load = push_per_field * load; load(ng+1:st-ng) += cells of one slab across the other axes
+  int64_t other = 1;
+  for (int q = 0; q < c.ndims; q++)
+    if (q != axis) other *= c.n_global[q];
+  for (int i = 0; i < len; i++) {
+    load[i] *= 5;   // push_per_field, shared_data.F90:821
+    if (i >= NG && i < len - NG) load[i] += other;
+  }
+  return EPB_OK;
+}
+
 extern "C" int epb_global_count(epb_handle *h, int is, int64_t *n) {
   if (!h || is < 0 || is >= (int)h->sp.size() || !n) return EPB_ERR_ARG;
   long long local = h->sp[is].n;

@@ -22,7 +22,7 @@ SYMBOLS = (
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
     "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy",
-    "epb_kinetic_energy", "epb_calc_moment",
+    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile",
 )
 
 
@@ -106,6 +106,7 @@ def load():
     L.epb_field_energy.argtypes = [vp, dp]
     L.epb_kinetic_energy.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.epb_calc_moment.argtypes = [vp, i32, i32, dp]
+    L.epb_load_profile.argtypes = [vp, i32, dp]
     L.epb_launch_count.argtypes = [vp]; L.epb_launch_count.restype = i64
     L.epb_push_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), i32]
     _lib = L

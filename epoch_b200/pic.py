@@ -261,6 +261,13 @@ class Simulation:
         self._chk(self.L.epb_kinetic_energy(self._h, isp, C.byref(out)))
         return out.value
 
+    def load_profile(self, axis: int):
+        """get_load_x/y/z (balance.F90:1766-1844) over the global cells of `axis`, summed over the ranks; feed it to
+        deck.calculate_breaks."""
+        out = np.zeros(self.deck.n[axis] + 2 * NG, dtype=np.int64)
+        self._chk(self.L.epb_load_profile(self._h, axis, out.ctypes.data))
+        return out
+
     MOMENTS = {"number_density": 0, "charge_density": 1, "mass_density": 2, "ekbar": 3, "temperature": 4,
                "temperature_x": 5, "temperature_y": 6, "temperature_z": 7,
                "ekflux_xm": 8, "ekflux_xp": 9, "ekflux_ym": 10, "ekflux_yp": 11, "ekflux_zm": 12, "ekflux_zp": 13,

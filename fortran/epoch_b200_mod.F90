@@ -183,6 +183,14 @@ MODULE epoch_b200_mod
       TYPE(C_PTR), VALUE :: handle
       INTEGER(C_INT) :: rc
     END FUNCTION
+    ! load(1-ng : n_global+ng) of get_load_x/y/z (balance.F90:1766-1844); axis = 0, 1, 2
+    FUNCTION epb_load_profile(handle, axis, load) BIND(C, NAME='epb_load_profile') RESULT(rc)
+      IMPORT :: C_INT, C_PTR, C_INT64_T
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: axis
+      INTEGER(C_INT64_T), INTENT(OUT) :: load(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     ! kind: 0 number density, 1 charge density, 2 mass density, 3 ekbar, 4 temperature, 5..7 temperature x/y/z,
     ! 8..13 ekflux -x,+x,-y,+y,-z,+z, 14..16 average px,py,pz, 17..19 species current jx,jy,jz, 20 average weight,
     ! 21..23 Poynting flux x,y,z;

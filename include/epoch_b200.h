@@ -195,6 +195,12 @@ enum { EPB_MOMENT_NUMBER_DENSITY = 0, EPB_MOMENT_CHARGE_DENSITY = 1, EPB_MOMENT_
        EPB_MOMENT_POYNT_FLUX_X = 21, EPB_MOMENT_POYNT_FLUX_Y = 22, EPB_MOMENT_POYNT_FLUX_Z = 23 };
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host);
 
+/* -- load balancing (host half in the binding: calculate_breaks, balance.F90:1948-2091) ---------------
+ * get_load_x / get_load_y / get_load_z (balance.F90:1766-1844, epoch3d :2247-2362): the load profile of one axis
+ * over the GLOBAL cells, load(1-ng : n_global+ng) as int64: push_per_field (5) per particle of any species in
+ * that cell column, summed over the ranks, plus one field column per interior cell */
+int epb_load_profile(epb_handle *h, int axis, int64_t *load);
+
 /* -- instrumentation ---------------------------------------------------------------
  * kernel launch counter since creation (bench.py's gpu_launches), and CUDA-event
  * timing of the push/deposit kernel alone: average ms per launch since the last reset */
