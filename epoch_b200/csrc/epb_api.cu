@@ -133,7 +133,7 @@ struct MirrorOp {
   int nd, sz[3], n[3];
   int d;         // axis
   int is_max;
-  double sign;   // -1 clamp, +1 zero gradient
+  double sign[3]; // per component: -1 clamp, +1 zero gradient
 };
 __global__ void __launch_bounds__(256) k_mirror(const __grid_constant__ MirrorOp M) {
   // threads cover the full transverse extent (incl. ghosts), as the Fortran ':' slices do
@@ -150,21 +150,22 @@ __global__ void __launch_bounds__(256) k_mirror(const __grid_constant__ MirrorOp
     const int nn = M.n[M.d];
     for (int q = 0; q < 3; q++) {
       double *a = M.f[q] + base;
+      const double sgn = M.sign[q];
       // Fortran index i along axis d lives at offset (i + NG - 1) * s
 #define AT(i) a[(size_t)((i) + NG - 1) * s]
       if (!M.is_max) {
         if (M.stag[q]) {
-          for (int i = 1; i <= NG - 1; i++) AT(i - NG) = M.sign * AT(NG - i);
-          if (M.sign < 0) AT(0) = 0.0;
+          for (int i = 1; i <= NG - 1; i++) AT(i - NG) = sgn * AT(NG - i);
+          if (sgn < 0) AT(0) = 0.0;
         } else {
-          for (int i = 1; i <= NG; i++) AT(i - NG) = M.sign * AT(NG + 1 - i);
+          for (int i = 1; i <= NG; i++) AT(i - NG) = sgn * AT(NG + 1 - i);
         }
       } else {
         if (M.stag[q]) {
-          if (M.sign < 0) AT(nn) = 0.0;
-          for (int i = 1; i <= NG - 1; i++) AT(nn + i) = M.sign * AT(nn - i);
+          if (sgn < 0) AT(nn) = 0.0;
+          for (int i = 1; i <= NG - 1; i++) AT(nn + i) = sgn * AT(nn - i);
         } else {
-          for (int i = 1; i <= NG; i++) AT(nn + i) = M.sign * AT(nn + 1 - i);
+          for (int i = 1; i <= NG; i++) AT(nn + i) = sgn * AT(nn + 1 - i);
         }
       }
 #undef AT
@@ -927,7 +928,7 @@ inline bool stagger(int dir, int field) {  // setup.F90:124-134
   return false;
 }
 
-int mirror3(epb_handle *h, int f0, int boundary, double sign) {
+int mirror3(epb_handle *h, int f0, int boundary, double sign, int conduct = 0) {
   const epb_config &c = h->cfg;
   if (c.bc_field[boundary] == EPB_BC_PERIODIC) return EPB_OK;
   if (!c.is_boundary[boundary]) return EPB_OK;
@@ -935,7 +936,15 @@ int mirror3(epb_handle *h, int f0, int boundary, double sign) {
   M.nd = c.ndims;
   M.d = boundary / 2;
   M.is_max = boundary & 1;
-  M.sign = sign;
+  // conduct: c_bc_conduct (boundary.F90:817-832, :870-885) clamps the E component normal to the wall and the
+  // B components along it, and gives the others a zero gradient
+  for (int q = 0; q < 3; q++) {
+    M.sign[q] = sign;
+    if (conduct) {
+      const bool normal = (q == M.d);
+      M.sign[q] = (f0 == EPB_EX) ? (normal ? -1.0 : +1.0) : (normal ? +1.0 : -1.0);
+    }
+  }
   size_t total = 1;
   for (int d = 0; d < 3; d++) {
     M.sz[d] = h->sz[d];
@@ -953,6 +962,8 @@ int field_bcs3(epb_handle *h, int f0, bool mpi_only) {
   int rc = epb_halo_exchange(h, f0, 3, false);
   if (rc) return rc;
   if (mpi_only) return EPB_OK;
+  for (int i = 0; i < 2 * h->cfg.ndims; i++)
+    if (h->cfg.bc_field[i] == EPB_BC_CONDUCT) mirror3(h, f0, i, 0.0, 1);
   for (int i = 0; i < 2 * h->cfg.ndims; i++) {
     int b = h->cfg.bc_field[i];
     if (b == EPB_BC_CLAMP || b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW) mirror3(h, f0, i, -1.0);
@@ -1192,7 +1203,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   for (int i = 0; i < 2 * cfg->ndims; i++) {
     int b = cfg->bc_field[i];
     bool ok = b == EPB_BC_PERIODIC || b == EPB_BC_CLAMP || b == EPB_BC_ZERO_GRADIENT ||
-              b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW;
+              b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW || b == EPB_BC_CONDUCT;
     if (!ok) return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "field boundary code %d on boundary %d not implemented on the device path", b, i);
   }
   for (int s = 0; s < cfg->n_species; s++) {
@@ -1850,7 +1861,7 @@ static int moment_zero_gradient(epb_handle *h, int f) {
     M.nd = c.ndims;
     M.d = bd / 2;
     M.is_max = bd & 1;
-    M.sign = 1.0;
+    M.sign[0] = M.sign[1] = M.sign[2] = 1.0;
     size_t total = 1;
     for (int d = 0; d < 3; d++) {
       M.sz[d] = h->sz[d];

@@ -480,7 +480,9 @@ def calculate_breaks(load, nproc: int, ng: int = NG, ncell_min: int = NCELL_MIN)
         return lmax, lmin
 
     sweep_back()
-    best = None                    # load_var_best = HUGE(1)
+    # load_var_best = HUGE(1): the default-INTEGER huge (2^31 - 1) assigned to an INTEGER(i8), balance.F90:2006 --
+    # a spread of 2^31 - 1 or more therefore rejects every perturbation and the loop exits after one iteration
+    best = 2 ** 31 - 1
     lmax = lmin = None             # undefined in the reference until a perturbation was possible
     for _ in range(1000):
         for i in range(1, nproc):
@@ -496,13 +498,13 @@ def calculate_breaks(load, nproc: int, ng: int = NG, ncell_min: int = NCELL_MIN)
                 if ok:
                     maxs[i - 1] = old_maxs + sign
                     lmax, lmin = spread()
-                    if best is None or lmax - lmin < best:
+                    if lmax - lmin < best:
                         left = True
                         break
                     maxs[i - 1] = old_maxs
             if left:
                 break
-        if lmax is not None and (best is None or lmax - lmin < best):
+        if lmax is not None and lmax - lmin < best:
             best = lmax - lmin
         else:
             break

@@ -485,6 +485,16 @@ void field_mirror(World &w, int which, int boundary, double sign) {
 void field_bcs3(World &w, int f0, bool mpi_only) {
   for (int i = 0; i < 3; i++) field_bc(w, f0 + i);
   if (mpi_only) return;
+  // perfectly conducting boundaries (boundary.F90:817-832 efield, :870-885 bfield; epoch3d adds the z pair,
+  // epoch1d has the x pair only): E normal to the wall and B along it are clamped, the others zero-gradient
+  for (int i = 0; i < 2 * w.nd; i++) {
+    if (w.bc_field[i] != c_bc_conduct) continue;
+    for (int q = 0; q < 3; q++) {
+      const bool normal = (q == i / 2);
+      const double sgn = (f0 == EX) ? (normal ? -1.0 : +1.0) : (normal ? +1.0 : -1.0);
+      field_mirror(w, f0 + q, i, sgn);
+    }
+  }
   for (int i = 0; i < 2 * w.nd; i++) {
     int b = w.bc_field[i];
     if (b == c_bc_clamp || b == c_bc_simple_laser || b == c_bc_simple_outflow)

@@ -9,47 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from epoch_b200 import deck as D  # noqa: E402
-from epoch_b200.pic import Simulation  # noqa: E402
-from oracle.oracle import Oracle  # noqa: E402
-from tests import decks  # noqa: E402
-from tests.gpu_util import FIELDS, rel_l2  # noqa: E402
-
-
-def make_deck(name, world):
-    if name == "thermal2d_x":
-        return decks.thermal(2, (48, 40), ppc=6, temp_k=3.0e8, nproc=(world, 1, 1), two_species=True), 10, 1e-12
-    if name == "thermal2d_y":
-        return decks.thermal(2, (40, 48), ppc=6, temp_k=3.0e8, nproc=(1, world, 1)), 10, 1e-12
-    if name == "thermal2d_xy":
-        return decks.thermal(2, (48, 48), ppc=5, temp_k=3.0e8, nproc=(2, world // 2, 1)), 10, 1e-12
-    if name == "thermal3d":
-        npz = (2, 2, world // 4) if world >= 4 else (world, 1, 1)
-        return decks.thermal(3, (20, 16, 12), ppc=4, temp_k=3.0e8, nproc=npz), 8, 1e-12
-    if name == "thermal1d":
-        return decks.thermal(1, (128,), ppc=8, temp_k=3.0e8, nproc=(world, 1, 1)), 10, 1e-12
-    if name == "reflect2d":
-        return decks.thermal(2, (48, 40), ppc=5, temp_k=4.0e8, nproc=(world, 1, 1), bc="reflect"), 10, 1e-12
-    if name == "foil2d":
-        return decks.foil2d(n=(96, 64), nproc=(world, 1, 1), nsteps=30), 30, 1e-11
-    if name == "solver2d":   # order-4 field solver + strided compensated current smoothing across ranks
-        dk = decks.thermal(2, (48, 40), ppc=5, temp_k=3.0e8, nproc=(world, 1, 1))
-        dk.field_order = 4
-        dk.smooth_currents, dk.smooth_iterations, dk.smooth_compensation, dk.smooth_strides = True, 2, True, (1, 2)
-        return dk, 8, 1e-12
-    if name == "mixed2d":    # c_bc_mixed: electrons reflect, protons leave (per-species current sums across ranks)
-        dk = decks.thermal(2, (48, 40), ppc=5, temp_k=4.0e8, nproc=(world, 1, 1), bc="reflect", two_species=True)
-        dk.species[1].bc_particle = ["open"] * 4
-        return dk, 8, 1e-12
-    if name == "laser2d_y":   # laser on y_min, decomposed along y and x
-        return decks.laser2d_y(nproc=(1, world, 1) if world < 4 else (2, world // 2, 1)), 40, 1e-12
-    if name == "laser2d":
-        return decks.laser2d(nproc=(world, 1, 1), n=64), 40, 1e-12
-    raise KeyError(name)
+from tests.parity_check import make_deck, run_case  # noqa: E402,F401
 
 
 def main():
@@ -58,61 +21,13 @@ def main():
     world = int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("gloo")
-    dk, nsteps, tol = make_deck(name, world)
-    assert dk.nranks() == world
-    o = Oracle(dk)
-    if dk.species:
-        o.auto_load()
-    sim = Simulation(dk, rank=rank, strict_fp=True, sort_interval=2, capacity_factor=3.0)
-    ids = [Simulation.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, 0)
-    sim.set_comm(ids[0])
-    for isp in range(len(dk.species)):
-        sim.upload_species(isp, o.get_particles(rank, isp))
 
-    ranks = list(range(world))
+    def share_id(uid):
+        ids = [uid]
+        dist.broadcast_object_list(ids, 0)
+        return ids[0]
 
-    class Both:
-        def set_laser_source(self, lr, side, s1, s2):
-            o.set_laser_source(ranks[lr], side, s1, s2)
-            if ranks[lr] == rank:
-                sim.set_laser_source(0, side, s1, s2)
-        def init(self): o.init(); sim.init()
-        def fields_half(self): o.fields_half(); sim.fields_half()
-        def push(self): o.push(); sim.push()
-        def current_finish(self): o.current_finish(); sim.current_finish()
-        def fields_final(self): o.fields_final(); sim.fields_final()
-
-    D.run(dk, Both(), ranks, None, max_steps=nsteps)
-    res = {"rank": rank, "ok": True, "msgs": []}
-    for f in FIELDS:
-        e = rel_l2(sim.download_field(f), o.field(rank, f))
-        if not e <= tol:
-            res["ok"] = False
-            res["msgs"].append(f"{f}: rel_l2 {e:.3e}")
-    for isp in range(len(dk.species)):
-        a, b = sim.count(isp), o.count(rank, isp)
-        if a != b:
-            res["ok"] = False
-            res["msgs"].append(f"species {isp}: count {a} != oracle {b}")
-        elif not np.array_equal(sim.cell_counts(isp), o.cell_counts(rank, isp)):
-            res["ok"] = False
-            res["msgs"].append(f"species {isp}: per-cell counts differ")
-        tot = sim.global_count(isp)
-        want = sum(o.count(r, isp) for r in range(world))
-        if tot != want:
-            res["ok"] = False
-            res["msgs"].append(f"species {isp}: global count {tot} != {want}")
-    # device-side diagnostics moments (collective: every rank takes part in the ghost-cell sums)
-    if dk.species:
-        for kind in ("number_density", "charge_density", "ekbar", "temperature", "temperature_y"):
-            for isp in [-1] + list(range(len(dk.species))):
-                e = rel_l2(sim.moment(kind, isp), o.moment(rank, kind, isp))
-                if not e <= 1e-12:
-                    res["ok"] = False
-                    res["msgs"].append(f"moment {kind} species {isp}: rel_l2 {e:.3e}")
-    res["counts"] = [sim.count(i) for i in range(len(dk.species))]
-    sim.close()
+    res = run_case(name, rank, world, share_id)
     dist.barrier()
     dist.destroy_process_group()
     print("RESULT " + json.dumps(res), flush=True)

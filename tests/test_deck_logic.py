@@ -160,3 +160,14 @@ def test_load_profile():
     assert load[5 + 0] == 2 * PUSH + 16 and load[5 + 1] == PUSH + 16 and load[5 + 7] == 3 * PUSH + 16
     assert load[4] == PUSH and load[13] == PUSH and load[:4].sum() == 0 and load[14:].sum() == 0
     assert load.sum() == len(cells) * PUSH + 8 * 16
+
+
+def test_calculate_breaks_huge_quirk():
+    """load_var_best starts at HUGE(1) = 2^31 - 1 (a default INTEGER stored in an i8, balance.F90:2006): when the
+    max-min spread of the slabs is >= 2^31 - 1 no perturbation is ever accepted and the greedy cuts stand
+    (one hot column of 4e10 over 3 ranks -> maxs [5, 8, 40], not [5, 9, 40])."""
+    ng = 5
+    load = np.ones(40 + 2 * ng, dtype=np.int64)
+    load[ng + 6 - 1] = 4 * 10 ** 10    # cell 6
+    mins, maxs = D.calculate_breaks(load, 3)
+    assert maxs == [5, 8, 40] and mins == [1, 6, 9]

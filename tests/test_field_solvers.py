@@ -292,3 +292,51 @@ def test_group_velocity_1d_matches_reference_formulas(solver):
             xs.append(float((x[sel] * e2[sel]).sum() / e2[sel].sum()))
     vg_sim = np.polyfit(ts, xs, 1)[0]
     assert np.isclose(vg_sim, vg, rtol=0.012), (solver, vg_sim, vg)
+
+
+def test_conducting_walls_oracle():
+    """c_bc_conduct as the reference codes it (boundary.F90:817-832 efield_bcs, :870-885 bfield_bcs): on an x wall
+    ex, by, bz are clamped (odd about the wall; zero on the wall plane where the component is staggered in x) and
+    ey, ez, bx get a zero gradient (even); likewise on the y walls with the roles permuted."""
+    from oracle.oracle import Oracle
+    n = (24, 20)
+    dk = D.Deck(2, list(n), [0.0, 0.0], [1.0e-5, 1.0e-5], ["conduct"] * 4)
+    o = Oracle(dk)
+    rng = np.random.default_rng(3)
+    for f in ("ex", "ey", "ez", "bx", "by", "bz"):
+        a = o.field(0, f)
+        a[...] = rng.normal(size=a.shape) * (1e9 if f[0] == "e" else 3.0)
+    o.init()
+    for _ in range(3):
+        o.fields_half(); o.current_finish(); o.fields_final()
+    ng = 5
+    stag_x = {"ex": True, "ey": False, "ez": False, "bx": False, "by": True, "bz": True}
+    stag_y = {"ex": False, "ey": True, "ez": False, "bx": True, "by": False, "bz": True}
+    odd_x = {"ex": True, "ey": False, "ez": False, "bx": False, "by": True, "bz": True}
+    odd_y = {"ex": False, "ey": True, "ez": False, "bx": True, "by": False, "bz": True}
+    for f in odd_x:
+        a = o.field(0, f)[0]            # [y, x], Fortran index i at i + ng - 1
+        at = lambda i: a[ng:-ng, i + ng - 1]
+        sg = -1.0 if odd_x[f] else 1.0
+        if stag_x[f]:
+            for i in range(1, ng):
+                assert np.array_equal(at(-i), sg * at(i)), (f, i)
+                assert np.array_equal(at(n[0] + i), sg * at(n[0] - i)), (f, i)
+            if odd_x[f]:
+                assert not at(0).any() and not at(n[0]).any(), f
+        else:
+            for i in range(1, ng + 1):
+                assert np.array_equal(at(1 - i), sg * at(i)), (f, i)
+                assert np.array_equal(at(n[0] + i), sg * at(n[0] + 1 - i)), (f, i)
+        at = lambda j: a[j + ng - 1, ng:-ng]
+        sg = -1.0 if odd_y[f] else 1.0
+        if stag_y[f]:
+            for j in range(1, ng):
+                assert np.array_equal(at(-j), sg * at(j)), (f, j)
+                assert np.array_equal(at(n[1] + j), sg * at(n[1] - j)), (f, j)
+            if odd_y[f]:
+                assert not at(0).any() and not at(n[1]).any(), f
+        else:
+            for j in range(1, ng + 1):
+                assert np.array_equal(at(1 - j), sg * at(j)), (f, j)
+                assert np.array_equal(at(n[1] + j), sg * at(n[1] + 1 - j)), (f, j)

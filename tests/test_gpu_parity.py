@@ -245,6 +245,20 @@ def test_mixed_species_boundaries(ndims, n):
     assert sim.count(1) < o.get_particles(0, 1).shape[0] + 1 and sim.count(0) == dk.species[0].npart_per_cell * int(np.prod(n))
 
 
+@pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (32, 24)), (3, (10, 9, 8))])
+def test_conducting_walls(ndims, n):
+    """c_bc_conduct on every face (boundary.F90:817-832, :870-885; epoch3d :1159-1241): E normal to a wall and
+    B along it are clamped, the other components get a zero gradient; the particles are reflected."""
+    dk = decks.thermal(ndims, n, ppc=5, temp_k=4.0e8, bc="conduct")
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    set_random_fields(o, sim, dk, e_amp=1e8, b_amp=0.3)
+    run_both(dk, o, sim, 8)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= TOL, name
+    assert sim.count(0) == o.count(0, 0)
+    assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+
+
 @pytest.mark.parametrize("n,axis", [((64, 16), 0), ((16, 64), 1)])
 def test_plasma_oscillation_frequency_gpu(n, axis):
     """The CUDA path alone over 600 steps (300 emitted sorts, performance build): a cold plasma rings at

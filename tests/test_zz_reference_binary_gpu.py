@@ -1,5 +1,5 @@
-"""Runs last (file name).  Tests added after the round's GPU minutes were spent, hence xfail(strict=False) until they
-have been seen to pass on a B200: the reference's custom-stencil decks replayed on the CUDA path against the numbers
+"""Runs last (file name).  All of these passed on the driver's B200 box in round 1 (GPUTEST_r01: xpassed), so they
+are plain tests now: the reference's custom-stencil decks replayed on the CUDA path against the numbers
 the reference binary printed (tests/test_oracle_golden.py pins the oracle on the same numbers), and the device's
 energy diagnostics / total energy history (tests/test_energy_history.py does it for the oracle)."""
 import numpy as np
@@ -10,7 +10,6 @@ from epoch_b200 import deck as D
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(reason="added after the round's GPU minutes were spent: not yet run on a B200", strict=False)
 @pytest.mark.parametrize("tree", ["1d_optimized", "1d_lehe_x", "2d_optimized"])
 def test_custom_stencil_decks_reproduce_the_reference_binary_gpu(tree):
     """The reference's custom-stencil decks (simple_laser + open) on the CUDA path: the group velocities the
@@ -37,7 +36,6 @@ def test_custom_stencil_decks_reproduce_the_reference_binary_gpu(tree):
     assert np.isclose(vg_sim, recorded, rtol=1e-9, atol=0), vg_sim
 
 
-@pytest.mark.xfail(reason="added after the round's GPU minutes were spent: not yet run on a B200", strict=False)
 def test_energy_diagnostics_and_history_gpu():
     """epb_field_energy / epb_kinetic_energy (calc_total_energy_sum, io/calc_df.F90:1321-1417) against numpy on the
     same device state, and the total energy of the CUDA path alone over 300 steps (performance build)."""
@@ -67,7 +65,6 @@ def test_energy_diagnostics_and_history_gpu():
     assert np.abs(tot / tot[0] - 1.0).max() < 1.0e-4
 
 
-@pytest.mark.xfail(reason="added after the round's GPU minutes were spent: not yet run on a B200", strict=False)
 @pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (48, 32)), (3, (12, 10, 9))])
 def test_load_profile_gpu(ndims, n):
     """epb_load_profile (get_load_x/y/z, balance.F90:1766-1844) against the numpy restatement in deck.py on the
