@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--ppc", type=int, default=None)
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU")
-    variant = int(os.environ.get("EPB_PUSH_VARIANT", "3"))
+    variant = int(os.environ.get("EPB_PUSH_VARIANT", "5"))
     ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "0")),
                     help="0 = the library default: 2 for the cell-owner 2D kernel, 8 otherwise")
     ap.add_argument("--strict", type=int, default=0)
@@ -339,7 +339,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "kernel": "push_tiled_3d (push+deposit)" if is3d else
-                                   ("push_cell_2d (push+deposit)" if variant in (2, 3, 4) else "push_tiled_2d (push+deposit)"),
+                                   ("push_slots_2d (push+deposit, in-place slot columns)" if variant == 5 else
+                                    "push_cell_2d (push+deposit)" if variant in (2, 3, 4) else "push_tiled_2d (push+deposit)"),
                          "bytes_per_update": bytes_per_update,
                          "kernel_ms": push_ms, "kernel_launches": push_n,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},

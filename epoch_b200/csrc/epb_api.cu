@@ -7,6 +7,8 @@
 #include <cstring>
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "epb_internal.h"
 
 int epb_fail(epb_handle *h, int code, const char *fmt, ...) {
@@ -378,13 +380,15 @@ __global__ void __launch_bounds__(256) k_outflow_face(const __grid_constant__ Fa
 // calc_ppc (io/calc_df.F90:761-808): cell = FLOOR((pos - x_grid_min_local)/dx + 0.5) + 1
 struct CountOp {
   const double *x[3];
-  long long n;
+  PRange r;
   int nd, nloc[3];
   double gmin[3], dx[3];
   int *out;
 };
 __global__ void __launch_bounds__(256) k_cell_counts(const __grid_constant__ CountOp C) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < C.n; i += (long long)gridDim.x * blockDim.x) {
+  const long long nn = prange_n(C.r);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
+    if (!prange_valid(C.r, i)) continue;
     int cell[3] = {1, 1, 1};
     bool ok = true;
     for (int d = 0; d < C.nd; d++) {
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(256) k_cell_counts(const __grid_constant__ Cou
 // normalised triangle weights of include/triangle/gxfac.inc; data(cell+ix, ...) += gx*gy*gz*wdata.
 struct MomentOp {
   const double *x[3], *w;
-  long long n;
+  PRange r;
   int nd, sz[3];
   double gmin[3], dx[3];
   double scale;    // part_q (charge density, current), part_m (mass density)
@@ -412,7 +416,9 @@ struct MomentOp {
   double *out;
 };
 __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp M) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (long long)gridDim.x * blockDim.x) {
+  const long long nn = prange_n(M.r);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
+    if (!prange_valid(M.r, i)) continue;
     int cell[3] = {1, 1, 1};
     double g[3][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
     bool ok = true;
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp
 // calc_ekbar (io/calc_df.F90:116-221) and the two passes of calc_temperature (:877-1128)
 struct Moment2Op {
   const double *x[3], *p[3], *w;
-  long long n;
+  PRange r;
   int nd, sz[3];
   double gmin[3], dx[3];
   int mode;        // 3: ekbar (a0 += g wdata, a1 += g w); 4: temperature pass 1 (mean[q] += g w p/sqrt(m), cnt += g w);
@@ -466,7 +472,9 @@ struct Moment2Op {
 };
 __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2Op M) {
   const double c = EPB_C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += (long long)gridDim.x * blockDim.x) {
+  const long long nn = prange_n(M.r);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
+    if (!prange_valid(M.r, i)) continue;
     int cell[3] = {1, 1, 1};
     double g[3][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
     bool ok = true;
@@ -614,6 +622,7 @@ struct LoadOp {
   double stdev[3], drift[3];
   unsigned long long seed;
   int mixed;  // 1: cell drawn at random per particle (Poisson counts, the long-time state of a thermal plasma)
+  long long i0, i1;  // particles [i0, i1) of the species are generated, written at index i - i0
 };
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long &s) {
   unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
@@ -627,14 +636,16 @@ __device__ __forceinline__ double u01(unsigned long long &s) {
 __global__ void __launch_bounds__(256) k_load_uniform(const __grid_constant__ LoadOp L) {
   const long long ncell = (long long)L.nloc[0] * L.nloc[1] * L.nloc[2];
   const long long total = ncell * L.ppc;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long last = L.i1 < total ? L.i1 : total;
+  for (long long i = L.i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < last; i += (long long)gridDim.x * blockDim.x) {
+    const long long o = i - L.i0;
     unsigned long long s = L.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(i + 1));
     long long cellid = i / L.ppc;
     if (L.mixed) cellid = (long long)(u01(s) * (double)ncell) % ncell;
     int cell[3] = {(int)(cellid % L.nloc[0]), (int)((cellid / L.nloc[0]) % L.nloc[1]),
                    (int)(cellid / ((long long)L.nloc[0] * L.nloc[1]))};
     for (int d = 0; d < L.nd; d++)
-      L.x[d][i] = (L.gmin_local[d] + (double)cell[d] * L.dx[d]) + (u01(s) - 0.5) * L.dx[d];
+      L.x[d][o] = (L.gmin_local[d] + (double)cell[d] * L.dx[d]) + (u01(s) - 0.5) * L.dx[d];
     double g[4];
     for (int q = 0; q < 2; q++) {
       double r1, r2, ww;
@@ -647,8 +658,8 @@ __global__ void __launch_bounds__(256) k_load_uniform(const __grid_constant__ Lo
       g[2 * q] = r1 * ww;
       g[2 * q + 1] = r2 * ww;
     }
-    for (int d = 0; d < 3; d++) L.p[d][i] = g[d] * L.stdev[d] + L.drift[d];
-    L.w[i] = L.weight;
+    for (int d = 0; d < 3; d++) L.p[d][o] = g[d] * L.stdev[d] + L.drift[d];
+    L.w[o] = L.weight;
   }
 }
 
@@ -676,9 +687,11 @@ __global__ void __launch_bounds__(256) k_field_energy(const __grid_constant__ En
   if ((threadIdx.x & 31) == 0) { atomicAdd(&E.out[0], se); atomicAdd(&E.out[1], sb); }
 }
 __global__ void __launch_bounds__(256) k_kinetic_energy(const double *px, const double *py, const double *pz,
-                                                        const double *w, long long n, double mc, double mc2, double *out) {
+                                                        const double *w, const __grid_constant__ PRange R, double mc, double mc2, double *out) {
   double s = 0.0;
+  const long long n = prange_n(R);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (!prange_valid(R, i)) continue;
     const double ux = px[i] / mc, uy = py[i] / mc, uz = pz[i] / mc;
     const double u2 = ux * ux + uy * uy + uz * uz;
     const double gamma = sqrt(u2 + 1.0);
@@ -1253,7 +1266,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   epb_make_tiles(h->cfg, h->tg);
   // 0 = library default: the cell-owner kernel wants a fresh order (its sort is cheap), the
   // transposition kernel tolerates a stale one
-  if (h->cfg.sort_interval < 1) h->cfg.sort_interval = (h->tg.layout == 1) ? 2 : 8;
+  if (h->cfg.sort_interval < 1) h->cfg.sort_interval = (h->tg.layout == 1) ? 2 : 8;   // layout 2 never sorts
   EPB_CUDA(h, cudaMalloc(&h->cell_count, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   EPB_CUDA(h, cudaMalloc(&h->cell_start, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
   long long maxcap = 0;
@@ -1264,6 +1277,16 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     S.cap = species[s].capacity > 0 ? species[s].capacity : 1024;
     if (S.cap >= (1LL << 31) - 1024) return epb_fail(h, EPB_ERR_CAPACITY, "species capacity must be < 2^31");
     maxcap = S.cap > maxcap ? S.cap : maxcap;
+    if (h->tg.layout == 2) {  // slot columns: the arena is sized at the first upload / load (slots.cu)
+      int rcs = epb_slots_alloc(h, s);
+      if (!rcs) {  // a first arena from the mean occupancy the capacity implies; re-sized by upload / load if denser
+        long long ncell = 1;
+        for (int d = 0; d < nd; d++) ncell *= cfg->n[d];
+        rcs = epb_slots_reset(h, s, 0, (int)std::min<long long>(S.cap / std::max<long long>(1, ncell), 4096));
+      }
+      if (rcs) { epb_destroy(h); return rcs; }
+      continue;
+    }
     for (int b = 0; b < 2; b++)
       for (int q = 0; q < 7; q++) {
         if (q < 3 && q >= nd) continue;
@@ -1320,11 +1343,12 @@ int epb_destroy(epb_handle *h) {
   for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
-  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch);
+  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
     for (int b = 0; b < 2; b++)
       for (int q = 0; q < 7; q++) cudaFree(S.buf[b][q]);
+    if (S.slots) epb_slots_free(S);
     cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.cell_start); cudaFree(S.rank); cudaFree(S.perm); cudaFree(S.stay_cnt); cudaFree(S.arr_cnt); cudaFree(S.gone);
   }
   if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -1403,6 +1427,7 @@ int epb_upload_species(epb_handle *h, int is, int64_t n, const double *packed) {
   if (!h || is < 0 || is >= (int)h->sp.size() || n < 0) return EPB_ERR_ARG;
   SpeciesDev &S = h->sp[is];
   if (n > S.cap) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %lld particles > capacity %lld", is, (long long)n, S.cap);
+  if (S.slots) return epb_slots_upload(h, is, n, packed);
   const int nd = h->cfg.ndims, nv = nd + 4;
   std::vector<double> tmp((size_t)n);
   for (int q = 0; q < nv; q++) {
@@ -1422,6 +1447,7 @@ int epb_upload_species(epb_handle *h, int is, int64_t n, const double *packed) {
 int epb_download_species(epb_handle *h, int is, int64_t n, double *packed) {
   if (!h || is < 0 || is >= (int)h->sp.size()) return EPB_ERR_ARG;
   SpeciesDev &S = h->sp[is];
+  if (S.slots) return epb_slots_download(h, is, n, packed);
   if (n > S.n) n = S.n;
   const int nd = h->cfg.ndims, nv = nd + 4;
   std::vector<double> tmp((size_t)n);
@@ -1435,6 +1461,12 @@ int epb_download_species(epb_handle *h, int is, int64_t n, double *packed) {
 }
 int epb_species_count(epb_handle *h, int is, int64_t *n) {
   if (!h || is < 0 || is >= (int)h->sp.size() || !n) return EPB_ERR_ARG;
+  if (h->sp[is].slots) {
+    long long v = 0;
+    int rc = epb_slots_count(h, is, &v);
+    *n = v;
+    return rc;
+  }
   *n = h->sp[is].n;
   return EPB_OK;
 }
@@ -1449,22 +1481,55 @@ int epb_load_uniform(epb_handle *h, int is, int32_t ppc, double density, const d
   LoadOp L;
   memset(&L, 0, sizeof L);
   for (int d = 0; d < 3; d++) {
-    L.x[d] = S.buf[S.cur][d];
-    L.p[d] = S.buf[S.cur][3 + d];
+    if (!S.slots) {
+      L.x[d] = S.buf[S.cur][d];
+      L.p[d] = S.buf[S.cur][3 + d];
+    }
     L.nloc[d] = c.n[d];
     L.gmin_local[d] = c.grid_min_local[d];
     L.dx[d] = c.dx[d];
     L.stdev[d] = sqrt(temp_k[d] * EPB_KB * S.cfg.mass);
     L.drift[d] = drift[d];
   }
-  L.w = S.buf[S.cur][6];
+  if (!S.slots) L.w = S.buf[S.cur][6];
   L.nd = c.ndims;
   L.ppc = ppc;
+  L.i0 = 0;
+  L.i1 = total;
   L.mixed = getenv("EPB_LOAD_MIXED") ? atoi(getenv("EPB_LOAD_MIXED")) : 0;
   double vol = 1.0;
   for (int d = 0; d < c.ndims; d++) vol *= c.dx[d];
   L.weight = density * vol / ppc;
   L.seed = seed + 0x632BE59BD9B4E019ull * (unsigned long long)(c.rank + 1);
+  if (S.slots) {
+    // slot columns: generated chunk by chunk into the mover buffer and inserted by k_deliver (slots.cu); the
+    // mixed state has Poisson counts, so its densest cell is ~6 sigma above the mean
+    const int hint = L.mixed ? ppc + (int)ceil(6.0 * sqrt((double)ppc)) : ppc;
+    int rc = epb_slots_reset(h, is, total, hint);
+    if (rc) return rc;
+    long long i0 = 0;
+    while (i0 < total) {
+      int waiting = 0;
+      rc = epb_slots_waiting(h, is, &waiting);
+      if (rc) return rc;
+      const long long mm = std::min<long long>(total - i0, S.mcap - waiting);
+      if (mm <= 0) return epb_fail(h, EPB_ERR_CAPACITY, "load_uniform: the mover buffer is full of particles that do not fit their columns");
+      for (int d = 0; d < 3; d++) {
+        L.x[d] = S.mbuf[S.mcur][d] ? S.mbuf[S.mcur][d] + waiting : nullptr;
+        L.p[d] = S.mbuf[S.mcur][3 + d] + waiting;
+      }
+      L.w = S.mbuf[S.mcur][6] + waiting;
+      L.i0 = i0;
+      L.i1 = i0 + mm;
+      k_load_uniform<<<nblocks((size_t)mm, 148 * 32), 256, 0, h->stream>>>(L);
+      h->launches++;
+      rc = epb_slots_commit(h, is, waiting, mm);
+      if (rc) return rc;
+      i0 += mm;
+    }
+    EPB_CUDA(h, cudaGetLastError());
+    return epb_slots_check(h);
+  }
   k_load_uniform<<<nblocks((size_t)total, 148 * 32), 256, 0, h->stream>>>(L);
   h->launches++;
   EPB_CUDA(h, cudaMemsetAsync(S.gone, 0, (size_t)S.cap, h->stream));
@@ -1487,15 +1552,21 @@ int epb_cell_counts(epb_handle *h, int is, int32_t *out) {
   EPB_CUDA(h, cudaMemsetAsync(d_out, 0, ncell * sizeof(int), h->stream));
   CountOp C;
   for (int d = 0; d < 3; d++) {
-    C.x[d] = S.buf[S.cur][d];
     C.nloc[d] = c.n[d];
     C.gmin[d] = c.grid_min_local[d];
     C.dx[d] = c.dx[d];
   }
-  C.n = S.n;
   C.nd = c.ndims;
   C.out = d_out;
-  if (S.n > 0) { k_cell_counts<<<nblocks((size_t)S.n), 256, 0, h->stream>>>(C); h->launches++; }
+  SlotView V[2];
+  const int nv = epb_species_views(h, is, V);
+  for (int v = 0; v < nv; v++) {
+    for (int d = 0; d < 3; d++) C.x[d] = V[v].a[d];
+    C.r = V[v].r;
+    k_cell_counts<<<nblocks((size_t)V[v].r.n), 256, 0, h->stream>>>(C);
+    h->launches++;
+  }
+  (void)S;
   EPB_CUDA(h, cudaMemcpyAsync(out, d_out, ncell * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_out);
@@ -1578,6 +1649,7 @@ int epb_fields_final(epb_handle *h) {
 int epb_sort(epb_handle *h) {
   if (!h) return EPB_ERR_ARG;
   for (int is = 0; is < (int)h->sp.size(); is++) {
+    if (h->sp[is].slots) continue;   // slot columns are always in order
     int rc = h->sp[is].info_valid ? epb_sort_species_emitted(h, is) : epb_sort_species(h, is);
     if (rc) return rc;
   }
@@ -1599,7 +1671,7 @@ int epb_push(epb_handle *h) {
   for (int is = 0; is < (int)h->sp.size(); is++) {
     SpeciesDev &S = h->sp[is];
     if (S.cfg.immobile) continue;
-    if (S.n == 0) {  // nothing to push, but neighbours may still send us particles (and, mixed: current)
+    if (S.n == 0 && !S.slots) {  // nothing to push, but neighbours may still send us particles (and, mixed: current)
       if (h->bc_mixed) {
         int rcm = current_bcs_species(h, is);
         if (rcm) return rcm;
@@ -1611,6 +1683,38 @@ int epb_push(epb_handle *h) {
     PushParams P;
     fill_push_params(h, is, P);
     auto launch = c.strict_fp ? epb_launch_push_strict : epb_launch_push_fast;
+    if (S.slots) {
+      // slot columns (layout 2): the lanes walk their columns and compact them in place; movers, leavers and
+      // arrivals go through the mover buffer and are inserted by k_deliver after the exchange.  No sort.
+      epb_slots_fill_push(h, is, P);
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (h->time_push) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+      }
+      launch(P, c.ndims, true, h->stream, &h->launches);
+      {  // entries of the mover buffer that still have to be pushed (column full / stencil outside the tile)
+        PushParams Pm = P;
+        for (int d = 0; d < 3; d++) { Pm.x[d] = P.mx[d]; Pm.p[d] = P.mp[d]; }
+        Pm.w = P.mw;
+        Pm.gone = P.mflag;
+        (c.strict_fp ? epb_launch_push_m_strict : epb_launch_push_m_fast)(Pm, h->stream, &h->launches);
+      }
+      if (h->time_push) {
+        cudaEventRecord(e1, h->stream);
+        h->ev_pool.push_back({e0, e1});
+      }
+      EPB_CUDA(h, cudaGetLastError());
+      if (h->bc_mixed) {
+        int rcm = current_bcs_species(h, is);
+        if (rcm) return rcm;
+      }
+      int rc = epb_particle_exchange(h, is);
+      if (rc) return rc;
+      rc = epb_slots_deliver(h, is);
+      if (rc) return rc;
+      continue;
+    }
     static const int no3d = getenv("EPB_NO_TILED_3D") ? atoi(getenv("EPB_NO_TILED_3D")) : 0;
     // HC_PUSH builds of the reference: the tiled kernels hold the Boris gamma only, every particle takes
     // push_generic<ND, true>
@@ -1815,9 +1919,11 @@ int epb_kinetic_energy(epb_handle *h, int is, double *out) {
   double *d = (double *)(h->d_scratch + 256);
   EPB_CUDA(h, cudaMemsetAsync(d, 0, sizeof(double), h->stream));
   const double mc = EPB_C * S.cfg.mass;
-  if (S.n > 0) {
-    k_kinetic_energy<<<nblocks((size_t)S.n, 148 * 8), 256, 0, h->stream>>>(S.buf[S.cur][3], S.buf[S.cur][4], S.buf[S.cur][5],
-                                                                    S.buf[S.cur][6], S.n, mc, mc * EPB_C, d);
+  SlotView V[2];
+  const int nv = epb_species_views(h, is, V);
+  for (int v = 0; v < nv; v++) {
+    k_kinetic_energy<<<nblocks((size_t)V[v].r.n, 148 * 8), 256, 0, h->stream>>>(V[v].a[3], V[v].a[4], V[v].a[5], V[v].a[6], V[v].r,
+                                                                          mc, mc * EPB_C, d);
     h->launches++;
   }
   EPB_CUDA(h, cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1893,18 +1999,18 @@ static int moment_bcs_species(epb_handle *h, int f, int is) {
 // calc_boundary(array): only without c_bc_mixed (boundary.F90:794-796)
 static int moment_bcs_all(epb_handle *h, int f) { return h->bc_mixed ? EPB_OK : moment_sum_bcs(h, f); }
 
-static void moment2_fill(epb_handle *h, int is, Moment2Op &M) {
+static void moment2_fill(epb_handle *h, int is, const SlotView &V, Moment2Op &M) {
   const epb_config &c = h->cfg;
   SpeciesDev &S = h->sp[is];
   for (int d = 0; d < 3; d++) {
-    M.x[d] = S.buf[S.cur][d];
-    M.p[d] = S.buf[S.cur][3 + d];
+    M.x[d] = V.a[d];
+    M.p[d] = V.a[3 + d];
     M.sz[d] = h->sz[d];
     M.gmin[d] = c.grid_min_local[d];
     M.dx[d] = c.dx[d];
   }
-  M.w = S.buf[S.cur][6];
-  M.n = S.n;
+  M.w = V.a[6];
+  M.r = V.r;
   M.nd = c.ndims;
   M.part_mc = EPB_C * S.cfg.mass;
   M.sqrt_part_m = sqrt(S.cfg.mass);
@@ -1929,9 +2035,11 @@ static int calc_ratio_dev(epb_handle *h, int ispecies, int sub) {
   for (int is = spec_sum ? 0 : ispecies; is < (spec_sum ? (int)h->sp.size() : ispecies + 1); is++) {
     SpeciesDev &S = h->sp[is];
     if (spec_sum && S.cfg.zero_current) continue;
-    if (S.n > 0) {
+    SlotView V[2];
+    const int nv = epb_species_views(h, is, V);
+    for (int v = 0; v < nv; v++) {
       Moment2Op M;
-      moment2_fill(h, is, M);
+      moment2_fill(h, is, V[v], M);
       M.mode = avg_weight ? 6 : 3;
       M.dir = -1;
       M.sub = sub;
@@ -1939,7 +2047,7 @@ static int calc_ratio_dev(epb_handle *h, int ispecies, int sub) {
       M.a0 = h->f(A);
       M.a1 = h->f(WT);
       for (int q = 0; q < 3; q++) M.mean[q] = nullptr;
-      k_moment2<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
+      k_moment2<<<nblocks((size_t)V[v].r.n, 148 * 32), 256, 0, h->stream>>>(M);
       h->launches++;
     }
     if (avg_weight) continue;
@@ -1974,9 +2082,11 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
     for (int is = s0; is < s1; is++) {
       SpeciesDev &S = h->sp[is];
       if (spec_sum && S.cfg.zero_current) continue;
-      if (S.n > 0) {
+      SlotView V[2];
+      const int nv = epb_species_views(h, is, V);
+      for (int v = 0; v < nv; v++) {
         Moment2Op M;
-        moment2_fill(h, is, M);
+        moment2_fill(h, is, V[v], M);
         M.mode = pass == 0 ? 4 : 5;
         M.dir = dir;
         M.sub = 0;
@@ -1984,7 +2094,7 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
         M.a0 = h->f(SIG);
         M.a1 = h->f(CNT);
         for (int q = 0; q < 3; q++) M.mean[q] = h->f(MEAN0 + q);
-        k_moment2<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
+        k_moment2<<<nblocks((size_t)V[v].r.n, 148 * 32), 256, 0, h->stream>>>(M);
         h->launches++;
       }
       int rc = EPB_OK;
@@ -2084,24 +2194,26 @@ int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
   for (int is = spec_sum ? 0 : ispecies; is < (spec_sum ? (int)h->sp.size() : ispecies + 1); is++) {
     SpeciesDev &S = h->sp[is];
     if (spec_sum && S.cfg.zero_current) continue;  // tracers are left out of a species sum
-    if (S.n > 0) {
+    SlotView V[2];
+    const int nv = epb_species_views(h, is, V);
+    for (int v = 0; v < nv; v++) {
       MomentOp M;
       for (int d = 0; d < 3; d++) {
-        M.x[d] = S.buf[S.cur][d];
+        M.x[d] = V[v].a[d];
         M.sz[d] = h->sz[d];
         M.gmin[d] = c.grid_min_local[d];
         M.dx[d] = c.dx[d];
       }
-      M.w = S.buf[S.cur][6];
-      M.n = S.n;
+      M.w = V[v].a[6];
+      M.r = V[v].r;
       M.nd = c.ndims;
       M.use_scale = current ? 2 : kind != EPB_MOMENT_NUMBER_DENSITY;
       M.scale = (kind == EPB_MOMENT_CHARGE_DENSITY || current) ? S.cfg.charge : S.cfg.mass;
       M.dir = current ? kind - EPB_MOMENT_JX : 0;
       M.part_mc = EPB_C * S.cfg.mass;
-      for (int d = 0; d < 3; d++) M.p[d] = S.buf[S.cur][3 + d];
+      for (int d = 0; d < 3; d++) M.p[d] = V[v].a[3 + d];
       M.out = wk;
-      k_moment<<<nblocks((size_t)S.n, 148 * 32), 256, 0, h->stream>>>(M);
+      k_moment<<<nblocks((size_t)V[v].r.n, 148 * 32), 256, 0, h->stream>>>(M);
       h->launches++;
     }
     if (h->bc_mixed) {  // calc_boundary(data_array, ispecies) + particle_clear_bcs

@@ -25,7 +25,44 @@ struct TileGeom {
   int cpt;     // cells per tile
   int ntiles;
   int nkeys;   // ntiles * cpt
-  int layout;  // 0: cell-major inside a tile; 1 (2D): 8x4-cell warp groups, particles of a group interleaved by rank (see push_cell_2d)
+  int layout;  // 0: cell-major inside a tile; 1 (2D): 8x4-cell warp groups, particles of a group interleaved by rank (see push_cell_2d);
+               // 2 (2D, default): slot columns, one fixed-capacity column per cell, no sort at all (see push_slots_2d)
+};
+
+// Layout 2 ("slot columns", 2D): the particles of cell key k = group * 32 + lane live in rows 0 .. cnt[k]-1 of
+// column k; row r of a group's 32 columns is 32 consecutive, 256-byte aligned doubles per array
+// (slot = (group * R + r) * 32 + lane), so a round of the owning warp is one aligned, coalesced access and a
+// particle that stays in its cell is never moved by anything but its own lane.  Particles that change cell
+// ("movers"), leave the rank, or whose stencil leaves the tile go through the mover buffer M (SoA + a flag
+// byte per entry) and are inserted into their next column by k_deliver; what does not fit its column (or M)
+// waits in the other M buffer and is pushed by the generic kernel.
+// A range of particle slots a diagnostic kernel walks: the classic contiguous [0, n) (cnt == nullptr,
+// n_dev == nullptr), the slot arena (cnt != nullptr: slot i is a particle iff its row < cnt[its column]), or a
+// mover buffer (n_dev != nullptr: the count lives on the device, R holds the buffer's capacity, entries with
+// flag == 1 have left).
+struct PRange {
+  long long n;             // contiguous: count; arena: nkeys * R slots
+  const int *cnt;
+  int R;
+  const int *n_dev;
+  const unsigned char *flag;
+};
+__device__ __forceinline__ long long prange_n(const PRange &V) {
+  if (V.cnt || !V.n_dev) return V.n;
+  const long long n = (long long)*V.n_dev;
+  return n > V.R ? V.R : n;
+}
+__device__ __forceinline__ bool prange_valid(const PRange &V, long long i) {
+  if (!V.cnt) return !V.flag || V.flag[i] != 1;
+  const long long rowslot = i >> 5;            // group * R + r
+  const int lane = (int)(i & 31);
+  const long long g = rowslot / V.R;
+  const int r = (int)(rowslot - g * V.R);
+  return r < V.cnt[g * 32 + lane];
+}
+struct SlotView {
+  double *a[7];            // x, y, (z), px, py, pz, w
+  PRange r;
 };
 
 // Everything the push kernels need, passed by value (__grid_constant__).
@@ -79,6 +116,17 @@ struct PushParams {
   unsigned char *gone;     // per particle flag
   int out_cap;
   int experiment;          // profiling only (EPB_PUSH_EXPERIMENT): disables parts of the tiled kernel
+  // layout 2 (slot columns): x/p/w above are the arena; cnt = particles per column, R = rows per column
+  int *cnt;
+  int R;
+  // mover buffer the kernel appends to: entry m holds a particle that must be (re)inserted by k_deliver
+  // (mflag 0), one that left this rank (1, listed in the outbox by its M index) or one that still has to be
+  // pushed by the generic kernel (2: stencil outside the tile, or no room in its column)
+  double *mx[3], *mp[3], *mw;
+  unsigned char *mflag;
+  int *mcount;             // device counter (may run past mcap: readers clamp)
+  int mcap;
+  int *err;                // device error word: bit 0 = mover buffer overflow lost a particle
 };
 
 struct SpeciesDev {
@@ -97,6 +145,16 @@ struct SpeciesDev {
   bool info_valid = false;    // key/rank/stay_cnt/arr_cnt describe the current particle set
   bool pending_perm = false;  // the sort left the data in place: perm[new slot] = old index, applied by the next push
   unsigned char *gone = nullptr;
+  // layout 2 (slot columns): buf[0] is the arena of nkeys * R slots; n / n_sorted / key / rank / perm are unused
+  bool slots = false;
+  int R = 0;                  // rows per column
+  int *cnt = nullptr;         // [nkeys] particles per column
+  double *mbuf[2][7] = {{0}}; // mover buffers (SoA), mcur = the one the push appends to
+  unsigned char *mflag[2] = {nullptr, nullptr};
+  int *mcount = nullptr;      // device [2]
+  int mcur = 0;
+  long long mcap = 0;
+  bool arena_ready = false;   // R chosen and the arena allocated (at the first upload / load, when the density is known)
 };
 
 // opaque storage of a CUtensorMap (128 bytes, 64-byte aligned), see fdtd_tma.cu
@@ -127,6 +185,7 @@ struct epb_handle {
   int out_cap = 0;
   int *h_counts = nullptr;      // pinned [64]
   int *d_scratch = nullptr;     // device ints
+  int *d_err = nullptr;         // device error word (layout 2), checked at the synchronising entry points
   int *movers = nullptr;        // exchange: tail survivors that fill holes (27*out_cap+1)
   // asynchronous field dump: device staging copy + second stream (epb_download_field_async)
   cudaStream_t copy_stream = nullptr;
@@ -156,13 +215,14 @@ struct epb_handle {
   double *f(int which) const { return fields + (size_t)which * fsize; }
 };
 
-// 2D push kernel (EPB_PUSH_VARIANT): 3 (default) = push_cell_2d<8,3>: one lane per cell, register-resident
-// deposit sums, rank-interleaved layout, 16x8-cell tiles, 168 registers; 2 / 4 = the same kernel on
+// 2D push kernel (EPB_PUSH_VARIANT): 5 (default) = push_slots_2d<8,3>: one lane per cell, register-resident
+// deposit sums, slot-column layout (no sort), 16x8-cell tiles; 3 = push_cell_2d<8,3>: the same deposit on the
+// rank-interleaved sorted layout (emitted sort every 2 steps), 168 registers; 2 / 4 = the same kernel on
 // 16x16-cell tiles with 128 / 255 registers; 0 = push_tiled_2d (lane per particle, 27-value
 // transposed reduction, cell-major layout); 1 = its 21-value form.
 inline int epb_push_variant() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 3; }
+  if (v < 0) { const char *e = getenv("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 5; }
   return v;
 }
 
@@ -173,6 +233,23 @@ void epb_launch_push_fast(const PushParams &P, int nd, bool tiled, cudaStream_t 
 // fdtd_tma.cu
 bool epb_fdtd_tma_setup(epb_handle *h);
 void epb_fdtd_tma_launch(epb_handle *h, bool is_e, double cx, double cy, double cz, double fac);
+
+// slots.cu (layout 2)
+int epb_slots_alloc(epb_handle *h, int is);                       // mover buffers + counts (at create)
+void epb_slots_free(SpeciesDev &S);
+int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hint);  // empty the species; (re)size the arena
+int epb_slots_deliver(epb_handle *h, int is);                     // insert the mover buffer's particles into their columns
+int epb_slots_waiting(epb_handle *h, int is, int *waiting);       // entries of the current mover buffer that found their column full
+int epb_slots_commit(epb_handle *h, int is, int waiting, long long m);  // m staged particles behind them: flags, count, deliver
+int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed);
+int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed);
+int epb_slots_count(epb_handle *h, int is, long long *n);         // synchronises
+int epb_slots_check(epb_handle *h);                               // device error word -> EPB_ERR_CAPACITY (synchronises)
+void epb_slots_views(epb_handle *h, int is, SlotView V[2]);       // [0] arena, [1] waiting entries of the mover buffer
+int epb_species_views(epb_handle *h, int is, SlotView V[2]);      // any layout: the ranges that hold the species' particles; returns how many
+void epb_slots_fill_push(epb_handle *h, int is, PushParams &P);
+void epb_launch_push_m_strict(const PushParams &P, cudaStream_t s, long long *launches);
+void epb_launch_push_m_fast(const PushParams &P, cudaStream_t s, long long *launches);
 
 // sort.cu
 int epb_sort_species(epb_handle *h, int is);

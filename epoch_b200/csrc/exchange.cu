@@ -11,6 +11,9 @@
 // handle's stream.  The three components of E, B or J travel in one message.
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstring>
+
 #include "epb_internal.h"
 
 int epb_halo_local(epb_handle *h, int f0, int nf, bool add, int d, int pass);
@@ -117,11 +120,22 @@ struct PUnpackOp {
   long long first;
   int count;
   const double *buf;
+  // layout 2: arrivals are appended to the mover buffer, whose count lives on the device
+  const int *first_dev;
+  unsigned char *flag;
+  int cap;
+  int *err;
 };
+__global__ void k_bump_count(int *count_dev, int n) { *count_dev += n; }
 __global__ void __launch_bounds__(256) k_punpack(const __grid_constant__ PUnpackOp O) {
+  const long long first = O.first_dev ? (long long)*O.first_dev : O.first;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < O.count; t += gridDim.x * blockDim.x) {
     const double *o = O.buf + (size_t)t * O.nv;
-    const long long i = O.first + t;
+    const long long i = first + t;
+    if (O.first_dev) {
+      if (i >= O.cap) { atomicOr(O.err, 2); continue; }
+      O.flag[i] = 0;
+    }
     int q = 0;
     for (int d = 0; d < O.nd; d++) O.dst[d][i] = o[q++];
     for (int d = 3; d < 7; d++) O.dst[d][i] = o[q++];
@@ -188,9 +202,11 @@ extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
 // get_load_x / get_load_y (balance.F90:1766-1844; epoch3d :2247-2362; epoch1d :980-1006): histogram of the
 // particles of all species over the GLOBAL cells of one axis, cell = FLOOR((pos - x_grid_min) / dx + 1.5) + ng
 namespace {
-__global__ void __launch_bounds__(256) k_load_profile(const double *x, long long n, double grid_min, double dx, int len,
+__global__ void __launch_bounds__(256) k_load_profile(const double *x, const __grid_constant__ PRange R, double grid_min, double dx, int len,
                                                       unsigned long long *load) {
+  const long long n = prange_n(R);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (!prange_valid(R, i)) continue;
     const int cell = __double2int_rd((x[i] - grid_min) / dx + 1.5) + NG;   // index into load(1:len)
     if (cell >= 1 && cell <= len) atomicAdd(load + (cell - 1), 1ULL);
   }
@@ -206,12 +222,12 @@ extern "C" int epb_load_profile(epb_handle *h, int axis, int64_t *load) {
   cudaMemsetAsync(d, 0, 2 * (size_t)len * sizeof(unsigned long long), h->stream);
   const double grid_min = c.gmin[axis] + c.dx[axis] / 2.0;   // x_grid_min (setup.F90:169,180; no CPML)
   for (size_t is = 0; is < h->sp.size(); is++) {
-    SpeciesDev &S = h->sp[is];
-    if (S.n <= 0) continue;
-    long long blocks = (S.n + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    k_load_profile<<<(int)blocks, 256, 0, h->stream>>>(S.buf[S.cur][axis], S.n, grid_min, c.dx[axis], len, d);
-    h->launches++;
+    SlotView V[2];
+    const int nv = epb_species_views(h, (int)is, V);
+    for (int v = 0; v < nv; v++) {
+      k_load_profile<<<nblk((size_t)V[v].r.n), 256, 0, h->stream>>>(V[v].a[axis], V[v].r, grid_min, c.dx[axis], len, d);
+      h->launches++;
+    }
   }
   unsigned long long *res = d;
   if (c.nranks > 1 && h->nccl) {   // MPI_ALLREDUCE(MPI_IN_PLACE, load, st, MPI_INTEGER8, MPI_SUM)
@@ -237,6 +253,10 @@ extern "C" int epb_load_profile(epb_handle *h, int axis, int64_t *load) {
 extern "C" int epb_global_count(epb_handle *h, int is, int64_t *n) {
   if (!h || is < 0 || is >= (int)h->sp.size() || !n) return EPB_ERR_ARG;
   long long local = h->sp[is].n;
+  if (h->sp[is].slots) {
+    int rcs = epb_slots_count(h, is, &local);
+    if (rcs) return rcs;
+  }
   if (h->cfg.nranks <= 1 || !h->nccl) { *n = local; return EPB_OK; }
   long long *d = (long long *)h->d_scratch;
   EPB_CUDA(h, cudaMemcpyAsync(d, &local, sizeof local, cudaMemcpyHostToDevice, h->stream));
@@ -319,9 +339,12 @@ int epb_particle_exchange(epb_handle *h, int is) {
   EPB_CUDA(h, cudaMemcpyAsync(cnt, h->out_count, 27 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   long long gone_total = 0;
+  // An overflowing outbox is reported AFTER the exchange has completed with what fits: the neighbours have
+  // already posted their sends / receives against this rank, and an early return here would leave them
+  // blocked for ever; the error then surfaces on this rank while the others stay consistent.
+  int overflow_q = -1, overflow_n = 0;
   for (int q = 0; q < 27; q++) {
-    if (cnt[q] > h->out_cap)
-      return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %d particles leave in direction %d > outbox capacity %d", is, cnt[q], q, h->out_cap);
+    if (cnt[q] > h->out_cap) { overflow_q = q; overflow_n = cnt[q]; cnt[q] = h->out_cap; }
     gone_total += cnt[q];
   }
   const bool remote = c.nranks > 1 && h->nccl;
@@ -354,9 +377,11 @@ int epb_particle_exchange(epb_handle *h, int is) {
   }
   const long long n_recv = (long long)(recv_tot / nv);
   if (gone_total == 0 && n_recv == 0) return EPB_OK;
-  if (S.n - gone_total + n_recv > S.cap)
-    return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %lld particles after migration > capacity %lld", is, S.n - gone_total + n_recv, S.cap);
-  double *const *arr = S.buf[S.cur];
+  // the receive side cannot refuse either (the senders are committed): arrivals beyond the capacity are dropped
+  // by the unpack below and the error is returned once the exchange is complete
+  bool cap_fail = false;
+  if (!S.slots && S.n - gone_total + n_recv > S.cap) cap_fail = true;
+  double *const *arr = S.slots ? S.mbuf[S.mcur] : S.buf[S.cur];
   if (remote && (send_tot || recv_tot)) {
     int rc = ensure_buf(h, &h->sendbuf, &h->sendbuf_elems, send_tot);
     if (rc) return rc;
@@ -387,7 +412,8 @@ int epb_particle_exchange(epb_handle *h, int is) {
     h->launches++;
   }
   // compaction: holes below n_new are filled with the survivors of the tail [n_new, n_old)
-  if (gone_total > 0) {
+  // (slot columns: the leavers sit in the mover buffer, flagged, and k_deliver skips them)
+  if (gone_total > 0 && !S.slots) {
     const long long n_old = S.n, n_new = S.n - gone_total;
     int *ctr = h->d_scratch;  // [0] mover count, [1] fill cursor
     EPB_CUDA(h, cudaMemsetAsync(ctr, 0, 2 * sizeof(int), h->stream));
@@ -415,17 +441,32 @@ int epb_particle_exchange(epb_handle *h, int is) {
   for (int q = 0; q < 27; q++) {
     if (!recvc[q]) continue;
     PUnpackOp O;
+    memset(&O, 0, sizeof O);
     for (int k = 0; k < 7; k++) O.dst[k] = arr[k];
     O.nv = nv; O.nd = nd;
     O.first = S.n;
-    O.key = S.info_valid ? S.key : nullptr;
+    O.key = (!S.slots && S.info_valid) ? S.key : nullptr;
     O.count = recvc[q];
+    if (!S.slots && S.n + recvc[q] > S.cap) O.count = (int)std::max<long long>(0, S.cap - S.n);
     O.buf = h->recvbuf + recv_off[q];
-    k_punpack<<<nblk((size_t)recvc[q]), 256, 0, h->stream>>>(O);
-    h->launches++;
-    S.n += recvc[q];
+    if (S.slots) {
+      O.first_dev = S.mcount + S.mcur;
+      O.flag = S.mflag[S.mcur];
+      O.cap = (int)S.mcap;
+      O.err = h->d_err;
+    }
+    if (O.count > 0) {
+      k_punpack<<<nblk((size_t)O.count), 256, 0, h->stream>>>(O);
+      h->launches++;
+    }
+    if (S.slots) { k_bump_count<<<1, 1, 0, h->stream>>>(S.mcount + S.mcur, recvc[q]); h->launches++; }
+    else S.n += O.count;
   }
   EPB_CUDA(h, cudaMemsetAsync(h->out_count, 0, 27 * sizeof(int), h->stream));
   EPB_CUDA(h, cudaGetLastError());
+  if (overflow_q >= 0)
+    return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %d particles leave in direction %d > outbox capacity %d", is, overflow_n, overflow_q, h->out_cap);
+  if (cap_fail)
+    return epb_fail(h, EPB_ERR_CAPACITY, "species %d: more particles after migration than the capacity %lld", is, S.cap);
   return EPB_OK;
 }

@@ -1307,6 +1307,388 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
 
 
 // ---------------------------------------------------------------------------
+// Slot-column 2D kernel (layout 2, the default): push_cell_2d's lane-per-cell register deposit on a
+// particle store that needs no sort
+// ---------------------------------------------------------------------------
+// Every cell owns a column of R slots (epb_internal.h, slots.cu); row r of a warp's 32 columns is 32
+// consecutive, 256-byte aligned doubles, so round r is one aligned coalesced access with no index
+// arithmetic, no permutation and no prefix sums.  The lane walks its column; a particle whose next gather
+// cell is still the lane's cell is written back into the column at the lane's write cursor (in-place
+// compaction: the cursor never passes the read row), all others -- ~4 % per step in the C2 plasma -- leave
+// through the mover buffer M:
+//   * movers: pushed, next gather cell differs (or a boundary condition touched them): M entry, flag 0
+//   * leavers: pushed, classified for another rank by particle_bc: M entry, flag 1, M index in the outbox
+//   * particles whose stencil is not inside the tile's halo (only arrivals the prediction got wrong, or
+//     columns left stale by a full M): unpushed M entry, flag 2, pushed by push_generic_m
+//   * deleted particles (open boundary, beyond x_min_outer): dropped
+// k_deliver (slots.cu) then inserts the flag-0 entries into their new columns.  A mover that finds M full
+// simply stays where it is and is deposited through the general path next step: placement is an
+// optimisation, never a correctness condition.  Deposit exactly as push_cell_2d (21 register sums per
+// cell, core/edge split for one-axis movers, drain_extras for the rest).
+template <int CTY>
+constexpr size_t pushslots_smem() {
+  return sizeof(double) * ((size_t)9 * CPITCH * (CTY + 2 * HALO) + (size_t)(CTY / 2) * QDBL * QCAP) +
+         sizeof(int) * ((size_t)(CTY / 2) * QCAP + 2);
+}
+
+template <int CTY, int MINB>
+__global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_constant__ PushParams P) {
+  constexpr int T2Y = CTY, TH = CTY + 2 * HALO, TW = CPITCH, TWU = T2X + 2 * HALO, TILE_ELEMS = TW * TH;
+  constexpr int PUSH2D_THREADS = CTY * 16, PUSH2D_WARPS = CTY / 2;
+  extern __shared__ double sm[];
+  double *sF = sm;                                   // [6][TH][TW]
+  double *sJ = sF + 6 * TILE_ELEMS;                  // [3][TH][TW]
+  double *sQd_all = sJ + 3 * TILE_ELEMS;
+  int *sQk_all = reinterpret_cast<int *>(sQd_all + PUSH2D_WARPS * QDBL * QCAP);
+  const int tile = blockIdx.x;
+  const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
+  const int ox = ttx * T2X + 1 - HALO;  // cell index of shared column 0
+  const int oy = tty * T2Y + 1 - HALO;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int my_key = tile * (T2X * T2Y) + warp * 32 + lane;
+  int my_cnt = P.cnt[my_key];
+  if (my_cnt > P.R) my_cnt = P.R;
+  if (!__syncthreads_or(my_cnt > 0)) return;
+  for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
+    const int lx = q % TW, ly = q / TW;
+    const int cx = ox + lx, cy = oy + ly;
+    const bool ok = (lx < TWU) && (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
+    const size_t o = ok ? gofs<2>(P, cx, cy, 1) : 0;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      sF[f * TILE_ELEMS + q] = ok ? __ldg(P.e[f] + o) : 0.0;
+      sF[(3 + f) * TILE_ELEMS + q] = ok ? __ldg(P.b[f] + o) : 0.0;
+      sJ[f * TILE_ELEMS + q] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  const double c = EPB_C;
+  const double third = P.third;
+  const double *sEx = sF, *sEy = sF + TILE_ELEMS, *sEz = sF + 2 * TILE_ELEMS;
+  const double *sBx = sF + 3 * TILE_ELEMS, *sBy = sF + 4 * TILE_ELEMS, *sBz = sF + 5 * TILE_ELEMS;
+  double *Qd = sQd_all + warp * QDBL * QCAP;
+  int *Qk = sQk_all + warp * QCAP;
+  int qcount = 0;  // warp-uniform
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // this lane's cell (1-based cell indices as in the reference)
+  const int hcx = ttx * T2X + (lane & 15) + 1;
+  const int hcy = tty * T2Y + warp * 2 + (lane >> 4) + 1;
+  const int maxcnt = __reduce_max_sync(FULL, my_cnt);
+  const size_t gbase = ((size_t)(my_key >> 5) * (size_t)P.R) * 32 + lane;  // slot of row 0 of this lane's column
+  int wcur = 0;  // write cursor: rows 0 .. wcur-1 hold the particles that stay in this column
+
+  // raw deposit sums of this lane's cell: AX[iy][ix<2], AY[iy<2][ix], AZ[iy][ix]
+  double AX[3][2], AY[2][3], AZ[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      AZ[a][b] = 0.0;
+      if (b < 2) AX[a][b] = 0.0;
+      if (a < 2) AY[a][b] = 0.0;
+    }
+  }
+
+  // software pipeline: the next row's loads are in flight while this one computes
+  double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
+  if (my_cnt > 0) {
+    n_w = P.w[gbase]; n_x = P.x[0][gbase]; n_y = P.x[1][gbase];
+    n_px = P.p[0][gbase]; n_py = P.p[1][gbase]; n_pz = P.p[2][gbase];
+  }
+  for (int r = 0; r < maxcnt; r++) {
+    const bool active = r < my_cnt;
+    const double part_weight = n_w;
+    const double raw_x = n_x, raw_y = n_y, raw_px = n_px, raw_py = n_py, raw_pz = n_pz;
+    double px_ = n_x - P.grid_min_local[0];
+    double py_ = n_y - P.grid_min_local[1];
+    double part_ux = n_px * P.ipart_mc;
+    double part_uy = n_py * P.ipart_mc;
+    double part_uz = n_pz * P.ipart_mc;
+    if (r + 1 < my_cnt) {
+      const size_t sl = gbase + (size_t)(r + 1) * 32;
+      n_w = P.w[sl]; n_x = P.x[0][sl]; n_y = P.x[1][sl];
+      n_px = P.p[0][sl]; n_py = P.p[1][sl]; n_pz = P.p[2][sl];
+    }
+    // what happens to the particle: 0 stays in this column, 1 pushed and leaves through M (flag 0, or 1 with
+    // dir >= 0), 2 unpushed through M (flag 2), 3 deleted
+    int disp = 0, dir = -1;
+    double o_x = raw_x, o_y = raw_y, o_px = raw_px, o_py = raw_py, o_pz = raw_pz;
+    bool extras = false;
+    int key = 0, dcx = 0, dcy = 0;
+    double q_fxo = 0, q_fxn = 0, q_fyo = 0, q_fyn = 0, fjx = 0, fjy = 0, fjz = 0;
+    if (active) {
+      double root;
+      gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
+      px_ = px_ + part_ux * root;
+      py_ = py_ + part_uy * root;
+      const double cell_x_r = px_ * P.idx[0];
+      const double cell_y_r = py_ * P.idx[1];
+      const int cx1 = __double2int_rd(cell_x_r + 0.5) + 1;
+      const int cy1 = __double2int_rd(cell_y_r + 0.5) + 1;
+      // the gather reads cell1-2..cell1+1, the deposit writes cell1-2..cell1+2
+      const bool fast = (cx1 - 2 >= ox) && (cx1 + 2 <= ox + TWU - 1) && (cy1 - 2 >= oy) && (cy1 + 2 <= oy + TH - 1);
+      if (!fast) {
+        disp = 2;
+      } else {
+        double gx[3], gy[3], hx[3], hy[3];
+        const double fxo = (double)(cx1 - 1) - cell_x_r, fyo = (double)(cy1 - 1) - cell_y_r;
+        tri(fxo, gx[0], gx[1], gx[2]);
+        tri(fyo, gy[0], gy[1], gy[2]);
+        int cx2 = __double2int_rd(cell_x_r);
+        tri((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
+        cx2 += 1;
+        int cy2 = __double2int_rd(cell_y_r);
+        tri((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
+        cy2 += 1;
+        // shared-tile offsets of (cell-1, cell-1)
+        const int o11 = (cy1 - 1 - oy) * TW + (cx1 - 1 - ox);
+        const int o21 = (cy1 - 1 - oy) * TW + (cx2 - 1 - ox);
+        const int o12 = (cy2 - 1 - oy) * TW + (cx1 - 1 - ox);
+        const int o22 = (cy2 - 1 - oy) * TW + (cx2 - 1 - ox);
+        auto gat = [&](const double *F, int o, const double *wx, const double *wy) {
+          double r0 = wx[0] * F[o] + wx[1] * F[o + 1] + wx[2] * F[o + 2];
+          double r1 = wx[0] * F[o + TW] + wx[1] * F[o + TW + 1] + wx[2] * F[o + TW + 2];
+          double r2 = wx[0] * F[o + 2 * TW] + wx[1] * F[o + 2 * TW + 1] + wx[2] * F[o + 2 * TW + 2];
+          return wy[0] * r0 + wy[1] * r1 + wy[2] * r2;
+        };
+        const double ex_part = gat(sEx, o21, hx, gy);
+        const double ey_part = gat(sEy, o12, gx, hy);
+        const double ez_part = gat(sEz, o11, gx, gy);
+        const double bx_part = gat(sBx, o12, gx, hy);
+        const double by_part = gat(sBy, o21, hx, gy);
+        const double bz_part = gat(sBz, o22, hx, hy);
+        const double cmratio = P.cmratio;
+        const double uxm = part_ux + cmratio * ex_part;
+        const double uym = part_uy + cmratio * ey_part;
+        const double uzm = part_uz + cmratio * ez_part;
+        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+        const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+        const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+#ifdef EPB_FAST_MATH
+        const double tau = rcp_ge1(1.0 + taux2 + tauy2 + tauz2);
+#else
+        const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+#endif
+        const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                            2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+        const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                            2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+        const double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                            2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+        part_ux = uxp + cmratio * ex_part;
+        part_uy = uyp + cmratio * ey_part;
+        part_uz = uzp + cmratio * ez_part;
+        const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+#ifdef EPB_FAST_MATH
+        const double igamma = rsqrt_ge1(part_u2 + 1.0);
+#else
+        const double igamma = 1.0 / sqrt(part_u2 + 1.0);
+#endif
+        root = P.dtco2 * igamma;
+        const double delta_x = part_ux * root;
+        const double delta_y = part_uy * root;
+        const double part_vz = part_uz * c * igamma;
+        px_ = px_ + delta_x;
+        py_ = py_ + delta_y;
+        bool touched;  // a particle boundary condition looked at this particle (it is outside the local domain)
+        {
+          double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
+          double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
+          touched = (pos[0] < P.bnd_min[0]) || (pos[0] > P.bnd_max[0]) || (pos[1] < P.bnd_min[1]) || (pos[1] > P.bnd_max[1]);
+          dir = particle_bc<2>(P, pos, mom);
+          o_x = pos[0]; o_y = pos[1];
+          o_px = mom[0]; o_py = mom[1]; o_pz = mom[2];
+        }
+        // the cell the next push gathers this particle in (its half step, particles.F90:289-322)
+        px_ = px_ + delta_x;
+        py_ = py_ + delta_y;
+        const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
+        const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
+        {
+          const int kx = cx3 < 0 ? 0 : (cx3 > P.n[0] - 1 ? P.n[0] - 1 : cx3);
+          const int ky = cy3 < 0 ? 0 : (cy3 > P.n[1] - 1 ? P.n[1] - 1 : cy3);
+          const bool stays = !touched && (kx + 1 == hcx) && (ky + 1 == hcy);
+          disp = (dir == 13) ? 3 : (stays ? 0 : 1);
+        }
+        if (P.deposit) {
+          const double fxn = (double)cx3 - cxr, fyn = (double)cy3 - cyr;
+          dcx = cx3 + 1 - cx1;
+          dcy = cy3 + 1 - cy1;
+          const double fcx = P.kfc[0] * part_weight;
+          const double fcy = P.kfc[1] * part_weight;
+          const double fcz = P.kfc[2] * part_weight;
+          fjx = fcx * P.part_q;
+          fjy = fcy * P.part_q;
+          fjz = fcz * P.part_q * part_vz;
+          key = (cy1 - oy) * TW + (cx1 - ox);
+          q_fxo = fxo; q_fxn = fxn; q_fyo = fyo; q_fyn = fyn;
+          if (cx1 != hcx || cy1 != hcy || (dcx != 0 && dcy != 0)) {
+            extras = true;  // not this lane's cell, or moved diagonally
+            if ((dcx | dcy) == 0) key |= 1 << 15;  // 3x3 stencil: 21-update drain
+          } else {
+            // This lane's own cell, nearest cell unchanged or moved by one cell along one axis.
+            // New weights on the 3x3 core (particles.F90:521-538 with the shift by dcell); the
+            // part of a moved particle's stencil outside the core is queued (drain_edge).
+            double wm, w0, wp;
+            tri(fxn, wm, w0, wp);
+            hx[0] = (dcx == 0 ? wm : dcx > 0 ? 0.0 : w0) - gx[0];
+            hx[1] = (dcx == 0 ? w0 : dcx > 0 ? wm : wp) - gx[1];
+            hx[2] = (dcx == 0 ? wp : dcx > 0 ? w0 : 0.0) - gx[2];
+            const double hxa = hx[0] + (dcx < 0 ? wm : 0.0);  // running jx prefix enters the core with column -2
+            tri(fyn, wm, w0, wp);
+            hy[0] = (dcy == 0 ? wm : dcy > 0 ? 0.0 : w0) - gy[0];
+            hy[1] = (dcy == 0 ? w0 : dcy > 0 ? wm : wp) - gy[1];
+            hy[2] = (dcy == 0 ? wp : dcy > 0 ? w0 : 0.0) - gy[2];
+            const double hya = hy[0] + (dcy < 0 ? wm : 0.0);
+            double xfac1[3], yfac1[3], yfac2[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              xfac1[q] = gx[q] + 0.5 * hx[q];
+              yfac1[q] = gy[q] + 0.5 * hy[q];
+              yfac2[q] = third * hy[q] + 0.5 * gy[q];
+            }
+            const double fhx0 = fjx * hxa, fhx1 = fjx * hx[1];
+            const double fhy0 = fjy * hya, fhy1 = fjy * hy[1];
+#pragma unroll
+            for (int iy = 0; iy < 3; iy++) {
+              AX[iy][0] += fhx0 * yfac1[iy];
+              AX[iy][1] += fhx1 * yfac1[iy];
+            }
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) {
+              AY[0][ix] += fhy0 * xfac1[ix];
+              AY[1][ix] += fhy1 * xfac1[ix];
+            }
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) {
+              const double zg = fjz * gx[ix], zh = fjz * hx[ix];
+#pragma unroll
+              for (int iy = 0; iy < 3; iy++) AZ[iy][ix] += zg * yfac1[iy] + zh * yfac2[iy];
+            }
+            if ((dcx | dcy) != 0) { extras = true; key |= 1 << 14; }
+          }
+        }
+      }
+    }
+    // ---- particles that leave this column: one warp-aggregated reservation in the mover buffer ----
+    {
+      const bool mv = (disp == 1) || (disp == 2);
+      const unsigned bal = __ballot_sync(FULL, mv);
+      if (bal) {
+        int base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(P.mcount, __popc(bal));
+        base = __shfl_sync(FULL, base, __ffs(bal) - 1);
+        if (mv) {
+          const int m = base + __popc(bal & lt_mask);
+          if (m < P.mcap) {
+            P.mx[0][m] = o_x; P.mx[1][m] = o_y;
+            P.mp[0][m] = o_px; P.mp[1][m] = o_py; P.mp[2][m] = o_pz;
+            P.mw[m] = part_weight;
+            P.mflag[m] = (disp == 2) ? 2 : (dir >= 0 ? 1 : 0);
+            if (disp == 1 && dir >= 0) {
+              const int slot = atomicAdd(&P.out_count[dir], 1);
+              if (slot < P.out_cap) P.out_idx[(size_t)dir * P.out_cap + slot] = m;
+            }
+          } else if (disp == 1 && dir < 0) {
+            disp = 0;  // no room in M: the particle stays in this column and is deposited the general way next step
+          } else {
+            atomicOr(P.err, 1);  // a leaver or an unpushed particle cannot stay: reported as a capacity error
+          }
+        }
+      }
+    }
+    if (active && disp == 0) {
+      const size_t ow = gbase + (size_t)wcur * 32;
+      P.x[0][ow] = o_x;
+      P.x[1][ow] = o_y;
+      P.p[0][ow] = o_px;
+      P.p[1][ow] = o_py;
+      P.p[2][ow] = o_pz;
+      if (wcur != r) P.w[ow] = part_weight;
+      wcur++;
+    }
+    if (!P.deposit) continue;
+    // ---- queue the particles that are not regular for their lane ---------------------------
+    const unsigned em = __ballot_sync(FULL, extras);
+    if (em) {
+      const int ne = __popc(em);
+      if (qcount + ne > QCAP) {
+        __syncwarp();
+        drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
+        __syncwarp();
+        qcount = 0;
+      }
+      if (extras) {
+        const int slot = qcount + __popc(em & lt_mask);
+        Qk[slot] = key | ((dcx + 1) << 10) | ((dcy + 1) << 12);
+        Qd[0 * QCAP + slot] = q_fxo; Qd[1 * QCAP + slot] = q_fxn;
+        Qd[2 * QCAP + slot] = q_fyo; Qd[3 * QCAP + slot] = q_fyn;
+        Qd[4 * QCAP + slot] = fjx; Qd[5 * QCAP + slot] = fjy; Qd[6 * QCAP + slot] = fjz;
+      }
+      qcount += ne;
+    }
+  }
+  if (qcount) {
+    __syncwarp();
+    drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
+  }
+  if (my_cnt > 0) P.cnt[my_key] = wcur;
+  // ---- flush this lane's cell sums: prefixes of particles.F90:563-571, one update per point ----
+  if (P.deposit && my_cnt > 0) {
+    const int hb = (hcy - oy) * TW + (hcx - ox);
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++) {
+      const double v0 = -AX[iy][0];
+      const double v1 = v0 - AX[iy][1];
+      smem_add(&sJ[hb + (iy - 1) * TW - 1], v0);
+      smem_add(&sJ[hb + (iy - 1) * TW], v1);
+    }
+#pragma unroll
+    for (int ix = 0; ix < 3; ix++) {
+      const double v0 = -AY[0][ix];
+      const double v1 = v0 - AY[1][ix];
+      smem_add(&sJ[TILE_ELEMS + hb - TW + (ix - 1)], v0);
+      smem_add(&sJ[TILE_ELEMS + hb + (ix - 1)], v1);
+    }
+#pragma unroll
+    for (int iy = 0; iy < 3; iy++)
+#pragma unroll
+      for (int ix = 0; ix < 3; ix++) smem_add(&sJ[2 * TILE_ELEMS + hb + (iy - 1) * TW + (ix - 1)], AZ[iy][ix]);
+  }
+  __syncthreads();
+  if (!P.deposit) return;
+  for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
+    const int lx = q % TW, ly = q / TW;
+    const int cx = ox + lx, cy = oy + ly;
+    const bool ok = (lx < TWU) && (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG);
+    if (!ok) continue;
+    const size_t o = gofs<2>(P, cx, cy, 1);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double val = sJ[f * TILE_ELEMS + q];
+      if (val != 0.0) atomicAdd(P.j[f] + o, val);
+    }
+  }
+}
+
+// The mover buffer's unpushed entries (flag 2: no room in their column, or stencil outside their tile):
+// push_one on the buffer itself.  A particle that leaves the rank is flagged 1 by outbox_put (P.gone is the
+// flag array here), everything else becomes an ordinary flag-0 entry for k_deliver.
+template <int ND>
+__global__ void __launch_bounds__(256) push_generic_m(const __grid_constant__ PushParams P) {
+  int n = *P.mcount;
+  if (n > P.mcap) n = P.mcap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (P.gone[i] != 2) continue;
+    P.gone[i] = 0;
+    push_one<ND>(P, i);
+  }
+}
+
+
+// ---------------------------------------------------------------------------
 // Tiled 3D kernel
 // ---------------------------------------------------------------------------
 // One CTA (8 warps) per 8x8x4-cell tile of the cell-sorted layout, two CTAs per SM.  J is
@@ -1805,7 +2187,19 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
       attr_set = true;
     }
     if (P.tg.ntiles > 0) {
-      if (P.tg.layout == 1) {
+      if (P.tg.layout == 2) {
+        static bool attr_s = false;
+        static int minb = 3;
+        if (!attr_s) {
+          cudaFuncSetAttribute(push_slots_2d<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
+          cudaFuncSetAttribute(push_slots_2d<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
+          const char *e = getenv("EPB_SLOTS_MINB");
+          if (e) minb = atoi(e);
+          attr_s = true;
+        }
+        if (minb == 4) push_slots_2d<8, 4><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+        else push_slots_2d<8, 3><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+      } else if (P.tg.layout == 1) {
         if (P.tg.T[1] == 8) push_cell_2d<8, 3><<<P.tg.ntiles, 128, pushcell_smem<8>(), s>>>(P);
         else if (variant == 4) push_cell_2d<16, 1><<<P.tg.ntiles, 256, pushcell_smem<16>(), s>>>(P);
         else push_cell_2d<16, 2><<<P.tg.ntiles, 256, pushcell_smem<16>(), s>>>(P);
@@ -1839,6 +2233,14 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
   } else if (nd == 1) push_generic<1><<<(int)blocks, 256, 0, s>>>(P);
   else if (nd == 2) push_generic<2><<<(int)blocks, 256, 0, s>>>(P);
   else push_generic<3><<<(int)blocks, 256, 0, s>>>(P);
+  (*launches)++;
+}
+
+// layout 2: the unpushed entries of the mover buffer (P.x/p/w/gone point into it)
+inline void launch_push_m(const PushParams &P, cudaStream_t s, long long *launches) {
+  int blocks = (P.mcap + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  push_generic_m<2><<<blocks, 256, 0, s>>>(P);
   (*launches)++;
 }
 

@@ -5,3 +5,6 @@
 void epb_launch_push_strict(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
   epb_strict::launch_push(P, nd, tiled, s, launches);
 }
+void epb_launch_push_m_strict(const PushParams &P, cudaStream_t s, long long *launches) {
+  epb_strict::launch_push_m(P, s, launches);
+}

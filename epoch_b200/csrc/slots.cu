@@ -1,0 +1,463 @@
+// slots.cu — layout 2 ("slot columns") of the 2D particle store: everything around push_slots_2d.
+//
+// Replaces, for 2D species, the cell-sorted contiguous arrays + periodic counting sort (sort.cu) that stood in
+// for the reference's linked lists (TYPE particle_list, shared_data.F90:159-171; reorder_particles_to_grid,
+// housekeeping/split_particle.F90:29-77): every cell owns a fixed-capacity column of slots, the push keeps a
+// particle that stays in its cell where it is, and only the few per cent that change cell are moved -- through
+// the mover buffer, by k_deliver below.  There is no sort and no second copy of the particle state.
+//
+//   arena  : 7 SoA arrays of nkeys * R slots; slot of (key k, row r) = ((k >> 5) * R + r) * 32 + (k & 31)
+//   cnt    : particles per column (rows 0 .. cnt-1 are particles, packed)
+//   M, M'  : mover buffers (SoA + flag byte + device counter).  After a push M holds the step's movers
+//            (flag 0), the particles that left the rank (flag 1, indexed by the outbox) and arrivals from the
+//            neighbours (flag 0); k_deliver inserts the flag-0 entries into their columns, what finds its
+//            column full goes to M' with flag 2 and is pushed by the generic kernel next step.  M and M' swap.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "epb_internal.h"
+
+namespace {
+
+constexpr int NG = EPB_NG;
+
+inline int nblk(size_t n, int cap = 148 * 16) {
+  size_t b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+
+struct DeliverOp {
+  // source: mover buffer
+  const double *sx[3], *sp[3], *sw;
+  const unsigned char *sflag;
+  const int *scount;
+  int scap;
+  // destination: arena + counts
+  double *ax[3], *ap[3], *aw;
+  int *cnt;
+  int R;
+  // overflow: the other mover buffer
+  double *ox[3], *op[3], *ow;
+  unsigned char *oflag;
+  int *ocount;
+  int ocap;
+  int *err;
+  // predicted gather cell (particles.F90:289-322, the top of the next push)
+  int nd, nloc[3];
+  double gmin[3], idx[3], ipart_mc, dtco2;
+  TileGeom tg;
+};
+
+// The cell the NEXT push gathers this particle in: position advanced by half a step with the stored
+// momentum, operation for operation what push_slots_2d does at the top of its round, so the particle meets
+// the lane that owns its stencil.  Clamped into the interior (a particle within half a step of the rank's
+// edge can gather in the first ghost cell: it lives in the edge column and takes the general deposit there).
+__device__ __forceinline__ int predicted_key(const DeliverOp &D, double x, double y, double px, double py, double pz) {
+  const double ux = px * D.ipart_mc, uy = py * D.ipart_mc, uz = pz * D.ipart_mc;
+  const double root = D.dtco2 / sqrt(ux * ux + uy * uy + uz * uz + 1.0);
+  double part_x = x - D.gmin[0];
+  double part_y = y - D.gmin[1];
+  part_x = part_x + ux * root;
+  part_y = part_y + uy * root;
+  int cx = __double2int_rd(part_x * D.idx[0] + 0.5);
+  int cy = __double2int_rd(part_y * D.idx[1] + 0.5);
+  cx = cx < 0 ? 0 : (cx > D.nloc[0] - 1 ? D.nloc[0] - 1 : cx);
+  cy = cy < 0 ? 0 : (cy > D.nloc[1] - 1 ? D.nloc[1] - 1 : cy);
+  const int tx = cx / D.tg.T[0], ty = cy / D.tg.T[1];
+  return (ty * D.tg.nt[0] + tx) * D.tg.cpt + (cy - ty * D.tg.T[1]) * D.tg.T[0] + (cx - tx * D.tg.T[0]);
+}
+
+__global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ DeliverOp D) {
+  int n = *D.scount;
+  if (n > D.scap) n = D.scap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (D.sflag[i] == 1) continue;   // left this rank or the system
+    const double x = D.sx[0][i], y = D.sx[1][i];
+    const double px = D.sp[0][i], py = D.sp[1][i], pz = D.sp[2][i], w = D.sw[i];
+    const int key = predicted_key(D, x, y, px, py, pz);
+    const int r = atomicAdd(&D.cnt[key], 1);
+    if (r < D.R) {
+      const size_t o = ((size_t)(key >> 5) * D.R + r) * 32 + (key & 31);
+      D.ax[0][o] = x; D.ax[1][o] = y;
+      D.ap[0][o] = px; D.ap[1][o] = py; D.ap[2][o] = pz;
+      D.aw[o] = w;
+    } else {
+      // column full: every thread that saw r >= R takes its increment back, so the count settles at R
+      atomicSub(&D.cnt[key], 1);
+      const int m = atomicAdd(D.ocount, 1);
+      if (m < D.ocap) {
+        D.ox[0][m] = x; D.ox[1][m] = y;
+        D.op[0][m] = px; D.op[1][m] = py; D.op[2][m] = pz;
+        D.ow[m] = w;
+        D.oflag[m] = 2;
+      } else {
+        atomicOr(D.err, 1);
+      }
+    }
+  }
+}
+
+// arena -> contiguous SoA staging (download): columns [k0, k1), offsets from the scanned counts
+struct CompactOp {
+  const double *a[7];
+  double *dst[7];
+  const int *cnt, *start;
+  int R, k0, k1;
+  long long base;   // start[k0]
+};
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ CompactOp C) {
+  // one warp per group of 32 columns, row by row (coalesced reads)
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int g = (C.k0 >> 5) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < (C.k1 >> 5); g += warps) {
+    const int key = g * 32 + lane;
+    const int c = min(C.cnt[key], C.R);
+    const long long st = (long long)C.start[key] - C.base;
+    const int mx = __reduce_max_sync(0xffffffffu, c);
+    for (int r = 0; r < mx; r++) {
+      if (r < c) {
+        const size_t o = ((size_t)g * C.R + r) * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < 7; q++)
+          if (C.a[q]) C.dst[q][st + r] = C.a[q][o];
+      }
+    }
+  }
+}
+
+__global__ void k_clamp_counts(const int *cnt, int *out, int n, int R) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = min(cnt[i], R);
+}
+__global__ void k_set_flags(unsigned char *f, const int *count_dev, int base_is_count, int n, unsigned char v) {
+  // flags of n entries appended at *count_dev (read before k_bump runs on the same stream)
+  const int base = base_is_count ? *count_dev : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f[base + i] = v;
+}
+__global__ void k_bump(int *count_dev, int n) { *count_dev += n; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int epb_slots_alloc(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  const int nd = h->cfg.ndims;
+  S.slots = true;
+  S.mcap = std::max<long long>(65536, S.cap / 8);
+  if (S.mcap > S.cap && S.cap >= 4096) S.mcap = S.cap;
+  for (int b = 0; b < 2; b++) {
+    for (int q = 0; q < 7; q++) {
+      if (q < 3 && q >= nd) continue;
+      EPB_CUDA(h, cudaMalloc(&S.mbuf[b][q], (size_t)S.mcap * sizeof(double)));
+    }
+    EPB_CUDA(h, cudaMalloc(&S.mflag[b], (size_t)S.mcap));
+    EPB_CUDA(h, cudaMemsetAsync(S.mflag[b], 0, (size_t)S.mcap, h->stream));
+  }
+  EPB_CUDA(h, cudaMalloc(&S.mcount, 2 * sizeof(int)));
+  EPB_CUDA(h, cudaMemsetAsync(S.mcount, 0, 2 * sizeof(int), h->stream));
+  EPB_CUDA(h, cudaMalloc(&S.cnt, ((size_t)h->tg.nkeys + 1) * sizeof(int)));
+  EPB_CUDA(h, cudaMemsetAsync(S.cnt, 0, ((size_t)h->tg.nkeys + 1) * sizeof(int), h->stream));
+  if (!h->d_err) {
+    EPB_CUDA(h, cudaMalloc(&h->d_err, sizeof(int)));
+    EPB_CUDA(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+  }
+  return EPB_OK;
+}
+
+void epb_slots_free(SpeciesDev &S) {
+  for (int b = 0; b < 2; b++) {
+    for (int q = 0; q < 7; q++) cudaFree(S.mbuf[b][q]);
+    cudaFree(S.mflag[b]);
+  }
+  cudaFree(S.mcount);
+  cudaFree(S.cnt);
+}
+
+// Empty the species and make sure the arena fits what is about to be loaded: rows per column R from the
+// densest cell expected (max_ppc_hint) and the mean of the occupied ones, capped by the memory the host
+// reserved (2 x capacity slots: what the sorted layout's double buffer took).
+int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hint) {
+  SpeciesDev &S = h->sp[is];
+  const int nd = h->cfg.ndims;
+  const long long nkeys = h->tg.nkeys;
+  long long want = max_ppc_hint + (long long)std::ceil(5.0 * std::sqrt((double)std::max(1, max_ppc_hint))) + 4;
+  if (want < 8) want = 8;
+  long long budget = (2 * S.cap) / std::max<long long>(1, nkeys);
+  if (budget < 8) budget = 8;
+  long long R = std::min(want, budget);
+  if ((size_t)R * (size_t)nkeys >= ((size_t)1 << 36)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
+  (void)n_expected;
+  // keep an arena that is large enough and not grossly oversized
+  if (S.arena_ready && S.R >= R && S.R <= 2 * R + 16) R = S.R;
+  if (!S.arena_ready || S.R != (int)R) {
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < 7; q++) {
+      if (q < 3 && q >= nd) continue;
+      cudaFree(S.buf[0][q]);
+      S.buf[0][q] = nullptr;
+      EPB_CUDA(h, cudaMalloc(&S.buf[0][q], (size_t)R * nkeys * sizeof(double)));
+    }
+    S.R = (int)R;
+    S.arena_ready = true;
+  }
+  S.cur = 0;
+  S.mcur = 0;
+  EPB_CUDA(h, cudaMemsetAsync(S.cnt, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
+  EPB_CUDA(h, cudaMemsetAsync(S.mcount, 0, 2 * sizeof(int), h->stream));
+  S.n = 0;
+  S.n_sorted = 0;
+  return EPB_OK;
+}
+
+static void fill_deliver(epb_handle *h, int is, DeliverOp &D) {
+  SpeciesDev &S = h->sp[is];
+  const epb_config &c = h->cfg;
+  memset(&D, 0, sizeof D);
+  const int m = S.mcur, o = S.mcur ^ 1;
+  for (int d = 0; d < 3; d++) {
+    D.sx[d] = S.mbuf[m][d]; D.sp[d] = S.mbuf[m][3 + d];
+    D.ax[d] = S.buf[0][d]; D.ap[d] = S.buf[0][3 + d];
+    D.ox[d] = S.mbuf[o][d]; D.op[d] = S.mbuf[o][3 + d];
+    D.nloc[d] = c.n[d];
+    D.gmin[d] = c.grid_min_local[d];
+    D.idx[d] = d < c.ndims ? 1.0 / c.dx[d] : 0.0;
+  }
+  D.sw = S.mbuf[m][6]; D.aw = S.buf[0][6]; D.ow = S.mbuf[o][6];
+  D.sflag = S.mflag[m]; D.oflag = S.mflag[o];
+  D.scount = S.mcount + m; D.ocount = S.mcount + o;
+  D.scap = D.ocap = (int)S.mcap;
+  D.cnt = S.cnt;
+  D.R = S.R;
+  D.err = h->d_err;
+  D.nd = c.ndims;
+  D.ipart_mc = 1.0 / (EPB_C * S.cfg.mass);
+  D.dtco2 = EPB_C * (c.dt / 2.0);
+  D.tg = h->tg;
+}
+
+// Insert the current mover buffer's particles into their columns; the buffers swap.
+int epb_slots_deliver(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  DeliverOp D;
+  fill_deliver(h, is, D);
+  k_deliver<<<nblk((size_t)S.mcap, 148 * 8), 256, 0, h->stream>>>(D);
+  h->launches++;
+  EPB_CUDA(h, cudaMemsetAsync(S.mcount + S.mcur, 0, sizeof(int), h->stream));
+  S.mcur ^= 1;
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
+void epb_slots_views(epb_handle *h, int is, SlotView V[2]) {
+  SpeciesDev &S = h->sp[is];
+  memset(V, 0, 2 * sizeof(SlotView));
+  for (int q = 0; q < 7; q++) { V[0].a[q] = S.buf[0][q]; V[1].a[q] = S.mbuf[S.mcur][q]; }
+  V[0].r.cnt = S.cnt;
+  V[0].r.R = S.R;
+  V[0].r.n = S.arena_ready ? (long long)h->tg.nkeys * S.R : 0;
+  V[1].r.n_dev = S.mcount + S.mcur;
+  V[1].r.R = (int)S.mcap;
+  V[1].r.n = S.mcap;       // upper bound, for sizing the grid
+  V[1].r.flag = S.mflag[S.mcur];
+}
+
+int epb_species_views(epb_handle *h, int is, SlotView V[2]) {
+  SpeciesDev &S = h->sp[is];
+  if (S.slots) {
+    if (!S.arena_ready) return 0;
+    epb_slots_views(h, is, V);
+    return 2;
+  }
+  memset(V, 0, 2 * sizeof(SlotView));
+  if (S.n <= 0) return 0;
+  for (int q = 0; q < 7; q++) V[0].a[q] = S.buf[S.cur][q];
+  V[0].r.n = S.n;
+  return 1;
+}
+
+void epb_slots_fill_push(epb_handle *h, int is, PushParams &P) {
+  SpeciesDev &S = h->sp[is];
+  P.cnt = S.cnt;
+  P.R = S.R;
+  for (int d = 0; d < 3; d++) { P.mx[d] = S.mbuf[S.mcur][d]; P.mp[d] = S.mbuf[S.mcur][3 + d]; }
+  P.mw = S.mbuf[S.mcur][6];
+  P.mflag = S.mflag[S.mcur];
+  P.mcount = S.mcount + S.mcur;
+  P.mcap = (int)S.mcap;
+  P.err = h->d_err;
+}
+
+int epb_slots_check(epb_handle *h) {
+  if (!h->d_err) return EPB_OK;
+  int e = 0;
+  EPB_CUDA(h, cudaMemcpyAsync(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (e) return epb_fail(h, EPB_ERR_CAPACITY, "slot layout: a mover buffer overflowed and particles were lost (error word %d); raise the species capacity", e);
+  return EPB_OK;
+}
+
+int epb_slots_count(epb_handle *h, int is, long long *n) {
+  SpeciesDev &S = h->sp[is];
+  *n = 0;
+  if (!S.arena_ready) return EPB_OK;
+  const int nkeys = h->tg.nkeys;
+  size_t need = 0;
+  long long *d_out = (long long *)(h->d_scratch + 512);
+  int *tmp = h->cell_count;   // [nkeys + 1] scratch: clamped counts
+  k_clamp_counts<<<nblk((size_t)nkeys), 256, 0, h->stream>>>(S.cnt, tmp, nkeys, S.R);
+  cub::DeviceReduce::Sum(nullptr, need, tmp, d_out, nkeys, h->stream);
+  if (need > h->cub_tmp_bytes) {
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->cub_tmp);
+    EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
+    h->cub_tmp_bytes = need;
+  }
+  cub::DeviceReduce::Sum(h->cub_tmp, need, tmp, d_out, nkeys, h->stream);
+  h->launches += 2;
+  long long arena = 0;
+  int mc[2] = {0, 0};
+  EPB_CUDA(h, cudaMemcpyAsync(&arena, d_out, sizeof arena, cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaMemcpyAsync(mc, S.mcount, sizeof mc, cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long waiting = std::min<long long>(mc[S.mcur], S.mcap);   // between steps: flag-2 entries only
+  *n = arena + waiting;
+  return epb_slots_check(h);
+}
+
+// Staging through the mover buffer (upload, device loader): the caller writes m particles behind the `waiting`
+// entries of the current buffer (particles that found their column full), then commits: flags, count, k_deliver.
+int epb_slots_waiting(epb_handle *h, int is, int *waiting) {
+  SpeciesDev &S = h->sp[is];
+  EPB_CUDA(h, cudaMemcpyAsync(waiting, S.mcount + S.mcur, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (*waiting > S.mcap) *waiting = (int)S.mcap;
+  return EPB_OK;
+}
+int epb_slots_commit(epb_handle *h, int is, int waiting, long long m) {
+  SpeciesDev &S = h->sp[is];
+  EPB_CUDA(h, cudaMemsetAsync(S.mflag[S.mcur] + waiting, 0, (size_t)m, h->stream));
+  k_bump<<<1, 1, 0, h->stream>>>(S.mcount + S.mcur, (int)m);
+  h->launches++;
+  // the waiting entries (flag 2) are offered to their columns again as well: harmless
+  return epb_slots_deliver(h, is);
+}
+
+// Host block (pack_particle order, partlist.F90:414-486) -> mover buffer chunk -> k_deliver.
+int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed) {
+  SpeciesDev &S = h->sp[is];
+  const epb_config &c = h->cfg;
+  const int nd = c.ndims, nv = nd + 4;
+  // densest cell (nearest cell of the stored position, io/calc_df.F90:795-796): sizes the columns
+  int max_ppc = 0;
+  {
+    std::vector<int> hist((size_t)c.n[0] * c.n[1], 0);
+    for (int64_t i = 0; i < n; i++) {
+      int cx = (int)std::floor((packed[i * nv + 0] - c.grid_min_local[0]) / c.dx[0] + 0.5);
+      int cy = (int)std::floor((packed[i * nv + 1] - c.grid_min_local[1]) / c.dx[1] + 0.5);
+      cx = cx < 0 ? 0 : (cx > c.n[0] - 1 ? c.n[0] - 1 : cx);
+      cy = cy < 0 ? 0 : (cy > c.n[1] - 1 ? c.n[1] - 1 : cy);
+      const int v = ++hist[(size_t)cy * c.n[0] + cx];
+      if (v > max_ppc) max_ppc = v;
+    }
+  }
+  int rc = epb_slots_reset(h, is, n, max_ppc);
+  if (rc) return rc;
+  std::vector<double> tmp((size_t)std::min<int64_t>(S.mcap, std::max<int64_t>(n, 1)));
+  int64_t i0 = 0;
+  while (i0 < n) {
+    int waiting = 0;
+    rc = epb_slots_waiting(h, is, &waiting);
+    if (rc) return rc;
+    const int64_t mm = std::min<int64_t>(n - i0, S.mcap - waiting);
+    if (mm <= 0) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %d particles fit neither their columns (R = %d) nor the mover buffer", is, waiting, S.R);
+    for (int q = 0; q < nv; q++) {
+      for (int64_t i = 0; i < mm; i++) tmp[i] = packed[(i0 + i) * nv + q];
+      const int comp = q < nd ? q : 3 + (q - nd);
+      EPB_CUDA(h, cudaMemcpyAsync(S.mbuf[S.mcur][comp] + waiting, tmp.data(), (size_t)mm * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    rc = epb_slots_commit(h, is, waiting, mm);
+    if (rc) return rc;
+    i0 += mm;
+  }
+  return epb_slots_check(h);
+}
+
+int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed) {
+  SpeciesDev &S = h->sp[is];
+  const epb_config &c = h->cfg;
+  const int nd = c.ndims, nv = nd + 4;
+  if (!S.arena_ready || n <= 0) return EPB_OK;
+  const int nkeys = h->tg.nkeys;
+  // scan of the clamped counts -> start[nkeys + 1]
+  int *tmpc = h->cell_count, *start = h->cell_start;
+  k_clamp_counts<<<nblk((size_t)nkeys), 256, 0, h->stream>>>(S.cnt, tmpc, nkeys, S.R);
+  EPB_CUDA(h, cudaMemsetAsync(tmpc + nkeys, 0, sizeof(int), h->stream));
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, tmpc, start, nkeys + 1, h->stream);
+  if (need > h->cub_tmp_bytes) {
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->cub_tmp);
+    EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
+    h->cub_tmp_bytes = need;
+  }
+  cub::DeviceScan::ExclusiveSum(h->cub_tmp, need, tmpc, start, nkeys + 1, h->stream);
+  h->launches += 2;
+  std::vector<int> hstart((size_t)nkeys + 1);
+  EPB_CUDA(h, cudaMemcpyAsync(hstart.data(), start, ((size_t)nkeys + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int mc = 0;
+  EPB_CUDA(h, cudaMemcpyAsync(&mc, S.mcount + S.mcur, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (mc > S.mcap) mc = (int)S.mcap;
+  // staging: the idle mover buffer
+  const int stg = S.mcur ^ 1;
+  const int64_t chunk = S.mcap;
+  std::vector<double> tmp((size_t)std::min<int64_t>(chunk, n));
+  int64_t done = 0;
+  int k0 = 0;
+  while (k0 < nkeys && done < n) {
+    // largest group-aligned key range whose particles fit the staging buffer
+    int k1 = k0;
+    while (k1 < nkeys) {
+      const int kn = std::min(nkeys, k1 + 32);
+      if ((int64_t)hstart[kn] - hstart[k0] > chunk) break;
+      k1 = kn;
+    }
+    if (k1 == k0) return epb_fail(h, EPB_ERR_CAPACITY, "download: one group of columns exceeds the staging buffer");
+    const int64_t m = (int64_t)hstart[k1] - hstart[k0];
+    if (m > 0) {
+      CompactOp C;
+      for (int q = 0; q < 7; q++) { C.a[q] = S.buf[0][q]; C.dst[q] = S.mbuf[stg][q]; }
+      C.cnt = S.cnt; C.start = start; C.R = S.R; C.k0 = k0; C.k1 = k1; C.base = hstart[k0];
+      k_compact<<<nblk((size_t)(k1 - k0), 148 * 8), 256, 0, h->stream>>>(C);
+      h->launches++;
+      const int64_t take = std::min<int64_t>(m, n - done);
+      for (int q = 0; q < nv; q++) {
+        const int comp = q < nd ? q : 3 + (q - nd);
+        EPB_CUDA(h, cudaMemcpyAsync(tmp.data(), S.mbuf[stg][comp], (size_t)take * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < take; i++) packed[(done + i) * nv + q] = tmp[i];
+      }
+      done += take;
+    }
+    k0 = k1;
+  }
+  // the entries waiting in the mover buffer (no room in their column)
+  if (mc > 0 && done < n) {
+    const int64_t take = std::min<int64_t>(mc, n - done);
+    std::vector<double> t2((size_t)take);
+    for (int q = 0; q < nv; q++) {
+      const int comp = q < nd ? q : 3 + (q - nd);
+      EPB_CUDA(h, cudaMemcpyAsync(t2.data(), S.mbuf[S.mcur][comp], (size_t)take * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+      for (int64_t i = 0; i < take; i++) packed[(done + i) * nv + q] = t2[i];
+    }
+    done += take;
+  }
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}

@@ -214,7 +214,7 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   else if (nd == 2) { T[0] = 16; T[1] = 16; }  // must match T2X/T2Y in push.cuh
   else { T[0] = 8; T[1] = 8; T[2] = 4; }  // must match T3 / T3Z in push.cuh
   const int variant = epb_push_variant();
-  if (nd == 2 && variant == 3) T[1] = 8;      // push_cell_2d<8,3>: 16x8-cell tiles
+  if (nd == 2 && (variant == 3 || variant == 5)) T[1] = 8;      // push_cell_2d<8,3> / push_slots_2d<8,3>: 16x8-cell tiles
   tg.cpt = 1;
   tg.ntiles = 1;
   for (int d = 0; d < 3; d++) {
@@ -225,6 +225,8 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   }
   tg.nkeys = tg.ntiles * tg.cpt;
   tg.layout = (nd == 2 && variant >= 2 && variant <= 4) ? 1 : 0;
+  // slot columns; the Higuera-Cary build pushes every particle through the generic kernel (contiguous layout)
+  if (nd == 2 && variant == 5) tg.layout = cfg.hc_push ? 0 : 2;
 }
 
 static void fill_keyop(epb_handle *h, SpeciesDev &S, KeyOp &K) {
