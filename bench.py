@@ -184,6 +184,8 @@ def main():
                     help="0 = the library default: 2 for the cell-owner 2D kernel, 8 otherwise")
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the untimed pre-phase that checks this decomposition against the multi-rank CPU oracle")
     args = ap.parse_args()
     if args.workload == "c4":
         if args.n == 4096:
@@ -219,6 +221,38 @@ def main():
     else:
         nproc = split_2d(world)
         dk = c2_deck(args.n, args.ppc, nproc)
+    # ---- untimed pre-phase: parity of THIS decomposition (every rank checks its own share of small decomposed
+    # decks against the multi-rank CPU oracle: per-cell / per-rank / global counts bit-exact, E/B/J and the
+    # moments within 1e-12 relative L2; tests/parity_check.py).  The oracle is the checker here, nothing of
+    # it is timed.  The verdict travels in the JSON line so that the scaling runs carry it.
+    parity = "skipped"
+    if not args.no_parity_check:
+        from tests.parity_check import run_case
+
+        def share_id(uid):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+            if world > 1:
+                dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+
+        cases = ["thermal3d_bench"] if args.workload == "c4" else ["thermal2d_bench", "foil2d_xy"]
+        msgs = []
+        for name in cases:
+            for strict in (True, False):
+                try:
+                    r = run_case(name, rank, world, share_id, strict=strict, moments=strict)
+                    if not r["ok"]:
+                        msgs.append(f"{name}[strict={int(strict)}] rank {rank}: " + "; ".join(r["msgs"]))
+                except Exception as e:  # a failing check must not hide behind a crash
+                    msgs.append(f"{name}[strict={int(strict)}] rank {rank}: {type(e).__name__}: {e}")
+        bad = torch.tensor([len(msgs)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(bad)
+        parity = "ok" if int(bad.item()) == 0 else ("FAILED: " + " | ".join(msgs) if msgs else "FAILED on another rank")
+        if msgs:
+            print("parity_check:", msgs, file=sys.stderr, flush=True)
     stream = torch.cuda.Stream()
     sim = Simulation(dk, rank=rank, strict_fp=bool(args.strict), sort_interval=args.sort_interval,
                      capacity_factor=1.02 if world == 1 else 1.15, stream=stream.cuda_stream)
@@ -335,6 +369,9 @@ def main():
                        "l2_policy": "inputs (51.5 GB of particle state per GPU) far exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
+            "parity_check": parity,
+            "parity_cases": ("thermal3d_bench" if is3d else "thermal2d_bench, foil2d_xy") +
+                            f" on {world} rank(s), parity and performance builds (tests/parity_check.py)",
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,

@@ -1343,7 +1343,7 @@ int epb_destroy(epb_handle *h) {
   for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
-  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err);
+  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
     for (int b = 0; b < 2; b++)

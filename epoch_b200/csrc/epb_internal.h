@@ -185,6 +185,7 @@ struct epb_handle {
   int out_cap = 0;
   int *h_counts = nullptr;      // pinned [64]
   int *d_scratch = nullptr;     // device ints
+  double *aos_stage = nullptr;  // 2 Mi particles in the pack_particle wire layout (upload / download staging)
   int *d_err = nullptr;         // device error word (layout 2), checked at the synchronising entry points
   int *movers = nullptr;        // exchange: tail survivors that fill holes (27*out_cap+1)
   // asynchronous field dump: device staging copy + second stream (epb_download_field_async)

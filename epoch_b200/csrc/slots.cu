@@ -130,6 +130,28 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
   }
 }
 
+// pack_particle wire layout (partlist.F90:414-486: pos(1:ndims), p(1:3), weight) <-> the SoA arrays
+struct AosOp {
+  double *soa[7];
+  double *aos;
+  long long n;
+  int nd, nv;
+  int to_soa;
+};
+__global__ void __launch_bounds__(256) k_aos(const __grid_constant__ AosOp A) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (long long)gridDim.x * blockDim.x) {
+    double *o = A.aos + i * A.nv;
+    int q = 0;
+    if (A.to_soa) {
+      for (int d = 0; d < A.nd; d++) A.soa[d][i] = o[q++];
+      for (int d = 3; d < 7; d++) A.soa[d][i] = o[q++];
+    } else {
+      for (int d = 0; d < A.nd; d++) o[q++] = A.soa[d][i];
+      for (int d = 3; d < 7; d++) o[q++] = A.soa[d][i];
+    }
+  }
+}
+
 __global__ void k_clamp_counts(const int *cnt, int *out, int n, int R) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = min(cnt[i], R);
 }
@@ -366,20 +388,25 @@ int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed) {
   }
   int rc = epb_slots_reset(h, is, n, max_ppc);
   if (rc) return rc;
-  std::vector<double> tmp((size_t)std::min<int64_t>(S.mcap, std::max<int64_t>(n, 1)));
+  // the packed block goes to the device as it is (chunks of <= 2 Mi particles through a staging buffer) and
+  // is taken apart into the SoA mover buffer there
+  const int64_t CH = std::min<int64_t>(S.mcap, 2 << 20);
+  if (!h->aos_stage) {
+    EPB_CUDA(h, cudaMalloc(&h->aos_stage, (size_t)(2 << 20) * 7 * sizeof(double)));
+  }
   int64_t i0 = 0;
   while (i0 < n) {
     int waiting = 0;
     rc = epb_slots_waiting(h, is, &waiting);
     if (rc) return rc;
-    const int64_t mm = std::min<int64_t>(n - i0, S.mcap - waiting);
+    const int64_t mm = std::min<int64_t>(std::min<int64_t>(n - i0, CH), S.mcap - waiting);
     if (mm <= 0) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %d particles fit neither their columns (R = %d) nor the mover buffer", is, waiting, S.R);
-    for (int q = 0; q < nv; q++) {
-      for (int64_t i = 0; i < mm; i++) tmp[i] = packed[(i0 + i) * nv + q];
-      const int comp = q < nd ? q : 3 + (q - nd);
-      EPB_CUDA(h, cudaMemcpyAsync(S.mbuf[S.mcur][comp] + waiting, tmp.data(), (size_t)mm * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
+    EPB_CUDA(h, cudaMemcpyAsync(h->aos_stage, packed + i0 * nv, (size_t)mm * nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    AosOp A;
+    for (int q = 0; q < 7; q++) A.soa[q] = S.mbuf[S.mcur][q] ? S.mbuf[S.mcur][q] + waiting : nullptr;
+    A.aos = h->aos_stage; A.n = mm; A.nd = nd; A.nv = nv; A.to_soa = 1;
+    k_aos<<<nblk((size_t)mm), 256, 0, h->stream>>>(A);
+    h->launches++;
     rc = epb_slots_commit(h, is, waiting, mm);
     if (rc) return rc;
     i0 += mm;
@@ -413,18 +440,30 @@ int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed) {
   EPB_CUDA(h, cudaMemcpyAsync(&mc, S.mcount + S.mcur, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (mc > S.mcap) mc = (int)S.mcap;
-  // staging: the idle mover buffer
+  // staging: columns -> the idle mover buffer (SoA, contiguous) -> wire layout -> host, <= 2 Mi particles a time
   const int stg = S.mcur ^ 1;
-  const int64_t chunk = S.mcap;
-  std::vector<double> tmp((size_t)std::min<int64_t>(chunk, n));
+  const int64_t CH = std::min<int64_t>(S.mcap, 2 << 20);
+  if (!h->aos_stage) {
+    EPB_CUDA(h, cudaMalloc(&h->aos_stage, (size_t)(2 << 20) * 7 * sizeof(double)));
+  }
+  auto ship = [&](double *const *soa, int64_t off, int64_t take, int64_t done) -> int {
+    AosOp A;
+    for (int q = 0; q < 7; q++) A.soa[q] = soa[q] ? soa[q] + off : nullptr;
+    A.aos = h->aos_stage; A.n = take; A.nd = nd; A.nv = nv; A.to_soa = 0;
+    k_aos<<<nblk((size_t)take), 256, 0, h->stream>>>(A);
+    h->launches++;
+    EPB_CUDA(h, cudaMemcpyAsync(packed + done * nv, h->aos_stage, (size_t)take * nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EPB_OK;
+  };
   int64_t done = 0;
   int k0 = 0;
   while (k0 < nkeys && done < n) {
-    // largest group-aligned key range whose particles fit the staging buffer
+    // largest group-aligned key range whose particles fit one chunk
     int k1 = k0;
     while (k1 < nkeys) {
       const int kn = std::min(nkeys, k1 + 32);
-      if ((int64_t)hstart[kn] - hstart[k0] > chunk) break;
+      if ((int64_t)hstart[kn] - hstart[k0] > CH) break;
       k1 = kn;
     }
     if (k1 == k0) return epb_fail(h, EPB_ERR_CAPACITY, "download: one group of columns exceeds the staging buffer");
@@ -436,27 +475,20 @@ int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed) {
       k_compact<<<nblk((size_t)(k1 - k0), 148 * 8), 256, 0, h->stream>>>(C);
       h->launches++;
       const int64_t take = std::min<int64_t>(m, n - done);
-      for (int q = 0; q < nv; q++) {
-        const int comp = q < nd ? q : 3 + (q - nd);
-        EPB_CUDA(h, cudaMemcpyAsync(tmp.data(), S.mbuf[stg][comp], (size_t)take * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-        for (int64_t i = 0; i < take; i++) packed[(done + i) * nv + q] = tmp[i];
-      }
+      int rcs = ship(S.mbuf[stg], 0, take, done);
+      if (rcs) return rcs;
       done += take;
     }
     k0 = k1;
   }
   // the entries waiting in the mover buffer (no room in their column)
-  if (mc > 0 && done < n) {
-    const int64_t take = std::min<int64_t>(mc, n - done);
-    std::vector<double> t2((size_t)take);
-    for (int q = 0; q < nv; q++) {
-      const int comp = q < nd ? q : 3 + (q - nd);
-      EPB_CUDA(h, cudaMemcpyAsync(t2.data(), S.mbuf[S.mcur][comp], (size_t)take * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-      for (int64_t i = 0; i < take; i++) packed[(done + i) * nv + q] = t2[i];
-    }
+  int64_t woff = 0;
+  while (woff < mc && done < n) {
+    const int64_t take = std::min<int64_t>(std::min<int64_t>(mc - woff, CH), n - done);
+    int rcs = ship(S.mbuf[S.mcur], woff, take, done);
+    if (rcs) return rcs;
     done += take;
+    woff += take;
   }
   EPB_CUDA(h, cudaGetLastError());
   return EPB_OK;

@@ -147,6 +147,7 @@ class Simulation:
         if rc != 0:
             raise EpbError(f"epb_create failed with code {rc} (see stderr)")
         self.cfg = cfg
+        self.species_cfg = sp
         self.nd = nd
         self.shape = tuple((geo["n"][d] + 2 * NG) if d < nd else 1 for d in (2, 1, 0))
         if stream is not None:
@@ -292,6 +293,39 @@ class Simulation:
 
     def wait_downloads(self):
         self._chk(self.L.epb_wait_downloads(self._h))
+
+    def write_replay_state(self, path: str, nsteps: int, fields: dict, particles: Sequence):
+        """State file for host/replay.cpp (the compiled host that replays EPOCH's call sequence through the C ABI):
+        this rank's epb_config / epb_species structs as raw bytes, the step count, ex..bz and the packed particles."""
+        with open(path, "wb") as f:
+            f.write(b"EPBRPLY1")
+            f.write(np.array([C.sizeof(self.cfg), C.sizeof(_lib.SpeciesCfg), len(self.deck.species), nsteps],
+                             dtype=np.int32).tobytes())
+            f.write(bytes(self.cfg))
+            for i in range(len(self.deck.species)):
+                f.write(bytes(self.species_cfg[i]))
+            for name in _lib.FIELD_NAMES[:6]:
+                a = fields.get(name)
+                a = np.zeros(self.shape) if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(self.shape)
+                f.write(a.tobytes())
+            for p in particles:
+                p = np.ascontiguousarray(p, dtype=np.float64)
+                f.write(np.array([p.shape[0]], dtype=np.int64).tobytes())
+                f.write(p.tobytes())
+
+    def read_replay_result(self, path: str):
+        """(fields dict incl. jx..jz, [packed particles per species]) written by host/replay.cpp"""
+        nvar = self.nd + 4
+        with open(path, "rb") as f:
+            assert f.read(8) == b"EPBRSLT1"
+            n = int(np.prod(self.shape))
+            fields = {name: np.frombuffer(f.read(8 * n), dtype=np.float64).reshape(self.shape)
+                      for name in _lib.FIELD_NAMES}
+            parts = []
+            for _ in self.deck.species:
+                k = int(np.frombuffer(f.read(8), dtype=np.int64)[0])
+                parts.append(np.frombuffer(f.read(8 * k * nvar), dtype=np.float64).reshape(k, nvar))
+        return fields, parts
 
     def launch_count(self) -> int:
         return int(self.L.epb_launch_count(self._h))

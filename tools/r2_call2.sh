@@ -5,7 +5,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_call2_pytest.log
 tail -15 gpurun_out/r2_call2_pytest.log
 for cfg in "5 3 0" "5 4 0" "3 3 0" "5 3 1" "3 3 1"; do
   set -- $cfg
-  EPB_PUSH_VARIANT=$1 EPB_SLOTS_MINB=$2 EPB_LOAD_MIXED=$3 timeout 600 python bench.py --steps 10 --warmup 4 --no-cpu-baseline \
+  EPB_PUSH_VARIANT=$1 EPB_SLOTS_MINB=$2 EPB_LOAD_MIXED=$3 timeout 600 python bench.py --steps 10 --warmup 4 --no-cpu-baseline $( [ "$cfg" = "5 3 0" ] || echo --no-parity-check ) \
     > gpurun_out/r2_call2_bench_v$1_m$2_mix$3.json 2> gpurun_out/r2_call2_bench_v$1_m$2_mix$3.err
   echo "variant=$1 minb=$2 mixed=$3"; python - <<PY
 import json
