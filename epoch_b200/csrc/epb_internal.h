@@ -239,12 +239,22 @@ void epb_fdtd_tma_launch(epb_handle *h, bool is_e, double cx, double cy, double 
 int epb_slots_alloc(epb_handle *h, int is);                       // mover buffers + counts (at create)
 void epb_slots_free(SpeciesDev &S);
 int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hint);  // empty the species; (re)size the arena
+int epb_slots_ensure_rows(epb_handle *h, int is, int R);          // empty species: at least R rows per column
 int epb_slots_deliver(epb_handle *h, int is);                     // insert the mover buffer's particles into their columns
 int epb_slots_waiting(epb_handle *h, int is, int *waiting);       // entries of the current mover buffer that found their column full
 int epb_slots_commit(epb_handle *h, int is, int waiting, long long m);  // m staged particles behind them: flags, count, deliver
 int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed);
 int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed);
 int epb_slots_count(epb_handle *h, int is, long long *n);         // synchronises
+// chunked walk over a species' particles as contiguous SoA device arrays, any layout (slots.cu)
+struct SpeciesIter {
+  std::vector<int> hstart;   // slot columns: scanned column counts
+  int k0 = 0, mc = 0;
+  long long woff = 0, lin = 0;
+};
+int epb_species_iter_begin(epb_handle *h, int is, SpeciesIter &I);
+int epb_species_iter_next(epb_handle *h, int is, SpeciesIter &I, long long CH, double *st[7], long long *m);
+int epb_species_insert_aos(epb_handle *h, int is, const double *aos_dev, long long n);   // device block in the wire layout
 int epb_slots_check(epb_handle *h);                               // device error word -> EPB_ERR_CAPACITY (synchronises)
 void epb_slots_views(epb_handle *h, int is, SlotView V[2]);       // [0] arena, [1] waiting entries of the mover buffer
 int epb_species_views(epb_handle *h, int is, SlotView V[2]);      // any layout: the ranges that hold the species' particles; returns how many

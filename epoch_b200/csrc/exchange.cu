@@ -470,3 +470,328 @@ int epb_particle_exchange(epb_handle *h, int is) {
     return epb_fail(h, EPB_ERR_CAPACITY, "species %d: more particles after migration than the capacity %lld", is, S.cap);
   return EPB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Dynamic load balancing, device half: the data movement of balance_workload
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Box { int lo[3], hi[3]; };   // global cell indices, inclusive
+
+// the cells rank `r` owns in decomposition D, widened by the ghost cells at the physical domain edges
+// (redistribute_field_2d: ng0 / ng1, balance.F90:1357-1362)
+Box owned_box(const epb_decomp &D, const epb_config &c, int r) {
+  Box b;
+  const int npx = D.nproc[0], npy = c.ndims >= 2 ? D.nproc[1] : 1;
+  const int co[3] = {r % npx, (r / npx) % npy, r / (npx * npy)};
+  for (int d = 0; d < 3; d++) {
+    if (d >= c.ndims) { b.lo[d] = b.hi[d] = 1; continue; }
+    b.lo[d] = D.cell_min[d][co[d]];
+    b.hi[d] = D.cell_max[d][co[d]];
+    if (b.lo[d] == 1) b.lo[d] -= NG;
+    if (b.hi[d] == c.n_global[d]) b.hi[d] += NG;
+  }
+  return b;
+}
+bool intersect(const Box &a, const Box &b, Box &o) {
+  for (int d = 0; d < 3; d++) {
+    o.lo[d] = std::max(a.lo[d], b.lo[d]);
+    o.hi[d] = std::min(a.hi[d], b.hi[d]);
+    if (o.lo[d] > o.hi[d]) return false;
+  }
+  return true;
+}
+size_t box_cells(const Box &b) {
+  size_t n = 1;
+  for (int d = 0; d < 3; d++) n *= (size_t)(b.hi[d] - b.lo[d] + 1);
+  return n;
+}
+// pack / unpack of a global box on a handle's arrays (local index = global index - (first owned cell - 1))
+void run_box(epb_handle *h, const int gmin[3], int f0, int nf, const Box &b, double *buf, int mode, cudaStream_t st) {
+  PackOp B;
+  B.nf = nf;
+  B.nd = h->cfg.ndims;
+  for (int q = 0; q < nf; q++) B.f[q] = h->f(f0 + q);
+  for (int q = 0; q < 3; q++) {
+    B.sz[q] = h->sz[q];
+    B.lo[q] = q < h->cfg.ndims ? b.lo[q] - (gmin[q] - 1) : 1;
+    B.ext[q] = b.hi[q] - b.lo[q] + 1;
+  }
+  B.buf = buf;
+  B.mode = mode;
+  k_pack<<<nblk(box_cells(b)), 256, 0, st>>>(B);
+  h->launches++;
+}
+
+// get_particle_processor (balance.F90:2095-2151): the processor coordinate whose [minpos, maxpos) holds the position
+struct DestOp {
+  const double *x[3];
+  long long n;
+  int nd, nproc[3];
+  double minpos[3][32], maxpos[3][32];
+  int *dest;
+  int *count;      // [nranks]
+  int *err;
+};
+__global__ void __launch_bounds__(256) k_dest(const __grid_constant__ DestOp D) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < D.n; i += (long long)gridDim.x * blockDim.x) {
+    int co[3] = {0, 0, 0};
+    bool ok = true;
+    for (int d = 0; d < D.nd; d++) {
+      const double p = D.x[d][i];
+      int found = -1;
+      for (int ip = 0; ip < D.nproc[d]; ip++)
+        if (p >= D.minpos[d][ip] && p < D.maxpos[d][ip]) { found = ip; break; }
+      if (found < 0) ok = false;
+      co[d] = found;
+    }
+    int r = -1;
+    if (ok) {
+      r = (co[2] * (D.nd >= 2 ? D.nproc[1] : 1) + co[1]) * D.nproc[0] + co[0];
+      atomicAdd(&D.count[r], 1);
+    } else {
+      atomicOr(D.err, 4);   // "Unlocatable particle"
+    }
+    D.dest[i] = r;
+  }
+}
+struct RouteOp {
+  const double *src[7];
+  const int *dest;
+  const int *offset;   // [nranks] first slot of every destination in buf
+  int *cursor;         // [nranks]
+  long long n;
+  int nd, nv;
+  double *buf;         // AoS, pack_particle order, grouped by destination rank
+};
+__global__ void __launch_bounds__(256) k_route(const __grid_constant__ RouteOp R) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R.n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = R.dest[i];
+    if (r < 0) continue;
+    const int slot = R.offset[r] + atomicAdd(&R.cursor[r], 1);
+    double *o = R.buf + (size_t)slot * R.nv;
+    int q = 0;
+    for (int d = 0; d < R.nd; d++) o[q++] = R.src[d][i];
+    for (int d = 3; d < 7; d++) o[q++] = R.src[d][i];
+  }
+}
+__global__ void k_absmax(const double *a, size_t n, unsigned long long *out) {
+  double m = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmax(m, fabs(a[i]));
+  if (m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+}  // namespace
+
+extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd_, const epb_config *ncfg,
+                                const epb_species *nsp, epb_handle **out) {
+  if (!oh || !od || !nd_ || !ncfg || !out) return EPB_ERR_ARG;
+  *out = nullptr;
+  const epb_config &oc = oh->cfg;
+  const int nd = oc.ndims, nranks = oc.nranks, me = oc.rank;
+  if (ncfg->ndims != nd || ncfg->nranks != nranks || ncfg->rank != me || ncfg->n_species != oc.n_species)
+    return epb_fail(oh, EPB_ERR_ARG, "epb_redistribute: the new config describes another run");
+  int nprod = 1;
+  for (int d = 0; d < nd; d++) {
+    if (od->nproc[d] != nd_->nproc[d] || od->nproc[d] > 32)
+      return epb_fail(oh, EPB_ERR_ARG, "epb_redistribute: processor grid must stay the same (<= 32 per axis)");
+    nprod *= od->nproc[d];
+  }
+  if (nprod != nranks || nranks > 64) return epb_fail(oh, EPB_ERR_ARG, "epb_redistribute: nproc does not match nranks (<= 64)");
+  if (nranks > 1 && !oh->nccl) return epb_fail(oh, EPB_ERR_NCCL, "epb_redistribute: epb_set_comm was not called");
+  EPB_CUDA(oh, cudaStreamSynchronize(oh->stream));
+  // The snapshots setup_field_boundaries took of the initial fields on laser / outflow faces are not moved: refuse
+  // the (rare) deck that has non-zero ones instead of silently zeroing them
+  {
+    unsigned long long *d_m = (unsigned long long *)(oh->d_scratch + 768);
+    EPB_CUDA(oh, cudaMemsetAsync(d_m, 0, sizeof *d_m, oh->stream));
+    k_absmax<<<nblk(12 * oh->plane), 256, 0, oh->stream>>>(oh->snap, 12 * oh->plane, d_m);
+    for (int a = 1; a < nd; a++)
+      if (oh->snapA[a]) k_absmax<<<nblk(12 * oh->planeA[a]), 256, 0, oh->stream>>>(oh->snapA[a], 12 * oh->planeA[a], d_m);
+    unsigned long long m = 0;
+    EPB_CUDA(oh, cudaMemcpyAsync(&m, d_m, sizeof m, cudaMemcpyDeviceToHost, oh->stream));
+    EPB_CUDA(oh, cudaStreamSynchronize(oh->stream));
+    if (m != 0)
+      return epb_fail(oh, EPB_ERR_UNSUPPORTED, "epb_redistribute: non-zero initial fields on a laser / outflow boundary (their snapshots are not re-cut)");
+  }
+  epb_handle *nh = nullptr;
+  int rc = epb_create(ncfg, nsp, &nh);
+  if (rc) return epb_fail(oh, rc, "epb_redistribute: epb_create for the new decomposition failed");
+  for (int is = 0; is < (int)oh->sp.size() && !rc; is++)   // columns as deep as the ones they replace
+    if (oh->sp[is].slots && nh->sp[is].slots) rc = epb_slots_ensure_rows(nh, is, oh->sp[is].R);
+  if (rc) { oh->err = nh->err; epb_destroy(nh); return rc; }
+  nh->nccl = oh->nccl;   // the communicator moves to the new state (same ranks, same Cartesian topology)
+  nh->time_push = oh->time_push;
+  ncclComm_t comm = (ncclComm_t)nh->nccl;
+  cudaStream_t st = nh->stream;
+  auto fail = [&](int code) { nh->nccl = nullptr; oh->err = nh->err; epb_destroy(nh); return code; };
+
+  // ---- fields: every cell goes from its old owner to its new owner --------------------------------------------
+  {
+    int omin[3] = {1, 1, 1}, nmin[3] = {1, 1, 1};
+    {
+      const int npx = od->nproc[0], npy = nd >= 2 ? od->nproc[1] : 1;
+      const int co[3] = {me % npx, (me / npx) % npy, me / (npx * npy)};
+      for (int d = 0; d < nd; d++) { omin[d] = od->cell_min[d][co[d]]; nmin[d] = nd_->cell_min[d][co[d]]; }
+    }
+    const Box my_old = owned_box(*od, oc, me), my_new = owned_box(*nd_, oc, me);
+    std::vector<Box> sbox(nranks), rbox(nranks);
+    std::vector<char> shas(nranks, 0), rhas(nranks, 0);
+    std::vector<size_t> soff(nranks + 1, 0), roff(nranks + 1, 0);
+    for (int p = 0; p < nranks; p++) {
+      shas[p] = intersect(my_old, owned_box(*nd_, oc, p), sbox[p]);
+      rhas[p] = intersect(my_new, owned_box(*od, oc, p), rbox[p]);
+      soff[p + 1] = soff[p] + (shas[p] ? 3 * box_cells(sbox[p]) : 0);
+      roff[p + 1] = roff[p] + (rhas[p] ? 3 * box_cells(rbox[p]) : 0);
+    }
+    rc = ensure_buf(nh, &nh->sendbuf, &nh->sendbuf_elems, soff[nranks]);
+    if (!rc) rc = ensure_buf(nh, &nh->recvbuf, &nh->recvbuf_elems, roff[nranks]);
+    if (rc) return fail(rc);
+    for (int f0 = 0; f0 < 9; f0 += 3) {   // E, B, J: three components per message
+      for (int p = 0; p < nranks; p++)
+        if (shas[p]) run_box(oh, omin, f0, 3, sbox[p], nh->sendbuf + soff[p], 0, st);
+      if (nranks > 1) {
+        ncclGroupStart();
+        for (int p = 0; p < nranks; p++) {
+          if (p == me) continue;
+          if (shas[p]) ncclSend(nh->sendbuf + soff[p], soff[p + 1] - soff[p], ncclDouble, p, comm, st);
+          if (rhas[p]) ncclRecv(nh->recvbuf + roff[p], roff[p + 1] - roff[p], ncclDouble, p, comm, st);
+        }
+        ncclResult_t r = ncclGroupEnd();
+        if (r != ncclSuccess) { epb_fail(nh, EPB_ERR_NCCL, "epb_redistribute (fields): %s", ncclGetErrorString(r)); return fail(EPB_ERR_NCCL); }
+        nh->launches++;
+      }
+      for (int p = 0; p < nranks; p++) {
+        if (!rhas[p]) continue;
+        // what stays on this rank is copied through the send buffer (same box on both sides)
+        const double *src = (p == me) ? nh->sendbuf + soff[p] : nh->recvbuf + roff[p];
+        run_box(nh, nmin, f0, 3, rbox[p], const_cast<double *>(src), 1, st);
+      }
+      rc = epb_halo_exchange(nh, f0, 3, false);   // do_field_mpi_with_lengths (remap_field, balance.F90:1082)
+      if (rc) return fail(rc);
+    }
+  }
+
+  // ---- particles: distribute_particles ------------------------------------------------------------------------
+  const int nv = nd + 4;
+  const long long CH = 4 << 20;
+  int *d_dest = nullptr, *d_cnt = nullptr;   // d_cnt: [nranks + 1] counts + "more chunks" flag, then [nranks][nranks + 1], offsets, cursors
+  if (cudaMalloc(&d_dest, (size_t)CH * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&d_cnt, (size_t)(nranks + 1) * (nranks + 4) * sizeof(int)) != cudaSuccess) {
+    cudaFree(d_dest);
+    epb_fail(nh, EPB_ERR_CUDA, "epb_redistribute: scratch allocation failed");
+    return fail(EPB_ERR_CUDA);
+  }
+  int *d_all = d_cnt + (nranks + 1), *d_off = d_all + (nranks + 1) * nranks, *d_cur = d_off + (nranks + 1);
+  auto cleanup = [&]() { cudaFree(d_dest); cudaFree(d_cnt); };
+  DestOp D;
+  memset(&D, 0, sizeof D);
+  D.nd = nd;
+  for (int d = 0; d < nd; d++) {
+    D.nproc[d] = nd_->nproc[d];
+    const double dx = oc.dx[d];
+    const double x_grid_min = oc.gmin[d] + dx / 2.0;   // setup.F90:169,180
+    const int np = nd_->nproc[d];
+    for (int ip = 0; ip < np; ip++) {
+      const double gmin_ip = x_grid_min + (double)(nd_->cell_min[d][ip] - 1) * dx;   // x_grid_mins(iproc)
+      const double gmax_ip = x_grid_min + (double)(nd_->cell_max[d][ip] - 1) * dx;   // x_grid_maxs(iproc)
+      D.minpos[d][ip] = ip == 0 ? gmin_ip - dx * (0.5 + 3.0) : gmin_ip - dx * 0.5;    // png = 3
+      D.maxpos[d][ip] = ip == np - 1 ? gmax_ip + dx * (0.5 + 3.0) : gmax_ip + dx * 0.5;
+    }
+  }
+  D.dest = d_dest;
+  D.count = d_cnt;
+  if (!nh->d_err) {
+    if (cudaMalloc(&nh->d_err, sizeof(int)) != cudaSuccess) { cleanup(); return fail(EPB_ERR_CUDA); }
+    cudaMemsetAsync(nh->d_err, 0, sizeof(int), st);
+  }
+  D.err = nh->d_err;
+  std::vector<int> hall((size_t)(nranks + 1) * nranks);
+  for (int is = 0; is < (int)oh->sp.size(); is++) {
+    SpeciesIter I;
+    rc = epb_species_iter_begin(oh, is, I);
+    if (rc) { cleanup(); return fail(rc); }
+    bool mine_done = false;
+    for (;;) {
+      double *sa[7];
+      long long m = 0;
+      if (!mine_done) {
+        rc = epb_species_iter_next(oh, is, I, CH, sa, &m);   // gathers on oh->stream
+        if (rc) { cleanup(); return fail(rc); }
+        if (m == 0) mine_done = true;
+        cudaStreamSynchronize(oh->stream);
+      }
+      cudaMemsetAsync(d_cnt, 0, (size_t)(nranks + 1) * sizeof(int), st);
+      if (m > 0) {
+        for (int d = 0; d < 3; d++) D.x[d] = sa[d];
+        D.n = m;
+        k_dest<<<nblk((size_t)m), 256, 0, st>>>(D);
+        nh->launches++;
+      }
+      const int more = mine_done ? 0 : 1;
+      cudaMemcpyAsync(d_cnt + nranks, &more, sizeof(int), cudaMemcpyHostToDevice, st);
+      if (nranks > 1) {
+        ncclResult_t r = ncclAllGather(d_cnt, d_all, nranks + 1, ncclInt32, comm, st);
+        if (r != ncclSuccess) { cleanup(); epb_fail(nh, EPB_ERR_NCCL, "epb_redistribute (counts): %s", ncclGetErrorString(r)); return fail(EPB_ERR_NCCL); }
+      } else {
+        cudaMemcpyAsync(d_all, d_cnt, (size_t)(nranks + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st);
+      }
+      cudaMemcpyAsync(hall.data(), d_all, hall.size() * sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); epb_fail(nh, EPB_ERR_CUDA, "epb_redistribute: %s", cudaGetErrorString(cudaGetLastError())); return fail(EPB_ERR_CUDA); }
+      bool any_more = false;
+      for (int p = 0; p < nranks; p++) any_more = any_more || hall[(size_t)p * (nranks + 1) + nranks];
+      // send counts = my row, receive counts = my column
+      std::vector<int> hoff(nranks + 1, 0), roffp(nranks + 1, 0);
+      for (int p = 0; p < nranks; p++) {
+        hoff[p + 1] = hoff[p] + hall[(size_t)me * (nranks + 1) + p];
+        roffp[p + 1] = roffp[p] + (p == me ? 0 : hall[(size_t)p * (nranks + 1) + me]);
+      }
+      if (hoff[nranks] > 0 || roffp[nranks] > 0) {
+        rc = ensure_buf(nh, &nh->sendbuf, &nh->sendbuf_elems, (size_t)hoff[nranks] * nv);
+        if (!rc) rc = ensure_buf(nh, &nh->recvbuf, &nh->recvbuf_elems, (size_t)roffp[nranks] * nv);
+        if (rc) { cleanup(); return fail(rc); }
+        if (m > 0) {
+          cudaMemcpyAsync(d_off, hoff.data(), (size_t)(nranks + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+          cudaMemsetAsync(d_cur, 0, (size_t)(nranks + 1) * sizeof(int), st);
+          RouteOp R;
+          for (int q = 0; q < 7; q++) R.src[q] = sa[q];
+          R.dest = d_dest; R.offset = d_off; R.cursor = d_cur; R.n = m; R.nd = nd; R.nv = nv; R.buf = nh->sendbuf;
+          k_route<<<nblk((size_t)m), 256, 0, st>>>(R);
+          nh->launches++;
+        }
+        if (nranks > 1) {
+          ncclGroupStart();
+          for (int p = 0; p < nranks; p++) {
+            if (p == me) continue;
+            const int sc = hoff[p + 1] - hoff[p], rcnt = roffp[p + 1] - roffp[p];
+            if (sc) ncclSend(nh->sendbuf + (size_t)hoff[p] * nv, (size_t)sc * nv, ncclDouble, p, comm, st);
+            if (rcnt) ncclRecv(nh->recvbuf + (size_t)roffp[p] * nv, (size_t)rcnt * nv, ncclDouble, p, comm, st);
+          }
+          ncclResult_t r = ncclGroupEnd();
+          if (r != ncclSuccess) { cleanup(); epb_fail(nh, EPB_ERR_NCCL, "epb_redistribute (particles): %s", ncclGetErrorString(r)); return fail(EPB_ERR_NCCL); }
+          nh->launches++;
+        }
+        // what stays here, then what arrived
+        rc = epb_species_insert_aos(nh, is, nh->sendbuf + (size_t)hoff[me] * nv, hoff[me + 1] - hoff[me]);
+        if (!rc) rc = epb_species_insert_aos(nh, is, nh->recvbuf, roffp[nranks]);
+        if (rc) { cleanup(); return fail(rc); }
+        // the staging arrays of the old handle are reused by the next chunk: finish with them first
+        cudaStreamSynchronize(st);
+      }
+      if (!any_more) break;
+    }
+  }
+  cleanup();
+  {
+    int e = 0;
+    cudaMemcpyAsync(&e, nh->d_err, sizeof e, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || e) {
+      epb_fail(nh, e ? EPB_ERR_CAPACITY : EPB_ERR_CUDA, e & 4 ? "epb_redistribute: unlocatable particle (balance.F90:2145)" : "epb_redistribute: device error %d", e);
+      return fail(e ? EPB_ERR_CAPACITY : EPB_ERR_CUDA);
+    }
+  }
+  oh->nccl = nullptr;   // moved
+  epb_destroy(oh);
+  *out = nh;
+  return EPB_OK;
+}

@@ -202,29 +202,46 @@ void epb_slots_free(SpeciesDev &S) {
 // Empty the species and make sure the arena fits what is about to be loaded: rows per column R from the
 // densest cell expected (max_ppc_hint) and the mean of the occupied ones, capped by the memory the host
 // reserved (2 x capacity slots: what the sorted layout's double buffer took).
-int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hint) {
+static int slots_set_rows(epb_handle *h, int is, long long R) {
   SpeciesDev &S = h->sp[is];
   const int nd = h->cfg.ndims;
   const long long nkeys = h->tg.nkeys;
+  if ((size_t)R * (size_t)nkeys >= ((size_t)1 << 36)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < 7; q++) {
+    if (q < 3 && q >= nd) continue;
+    cudaFree(S.buf[0][q]);
+    S.buf[0][q] = nullptr;
+    EPB_CUDA(h, cudaMalloc(&S.buf[0][q], (size_t)R * nkeys * sizeof(double)));
+  }
+  S.R = (int)R;
+  S.arena_ready = true;
+  return EPB_OK;
+}
+// memory a species' arena may take: what the sorted layout's double buffer took for the capacity the host
+// reserved (2 x capacity slots), or 32 GiB, whichever is larger (non-uniform decks: few dense cells, many empty)
+static long long slots_row_budget(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  const long long nkeys = std::max<long long>(1, h->tg.nkeys);
+  const long long by_cap = (2 * S.cap) / nkeys;
+  const long long by_mem = (long long)((32ull << 30) / (56ull * (unsigned long long)nkeys));
+  return std::max<long long>(8, std::max(by_cap, by_mem));
+}
+
+// Empty the species and make sure the arena fits what is about to be loaded: rows per column R from the
+// densest cell expected (max_ppc_hint), capped by slots_row_budget.
+int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hint) {
+  SpeciesDev &S = h->sp[is];
+  const long long nkeys = h->tg.nkeys;
   long long want = max_ppc_hint + (long long)std::ceil(5.0 * std::sqrt((double)std::max(1, max_ppc_hint))) + 4;
   if (want < 8) want = 8;
-  long long budget = (2 * S.cap) / std::max<long long>(1, nkeys);
-  if (budget < 8) budget = 8;
-  long long R = std::min(want, budget);
-  if ((size_t)R * (size_t)nkeys >= ((size_t)1 << 36)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
+  long long R = std::min(want, slots_row_budget(h, is));
   (void)n_expected;
   // keep an arena that is large enough and not grossly oversized
   if (S.arena_ready && S.R >= R && S.R <= 2 * R + 16) R = S.R;
   if (!S.arena_ready || S.R != (int)R) {
-    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int q = 0; q < 7; q++) {
-      if (q < 3 && q >= nd) continue;
-      cudaFree(S.buf[0][q]);
-      S.buf[0][q] = nullptr;
-      EPB_CUDA(h, cudaMalloc(&S.buf[0][q], (size_t)R * nkeys * sizeof(double)));
-    }
-    S.R = (int)R;
-    S.arena_ready = true;
+    int rc = slots_set_rows(h, is, R);
+    if (rc) return rc;
   }
   S.cur = 0;
   S.mcur = 0;
@@ -233,6 +250,13 @@ int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hin
   S.n = 0;
   S.n_sorted = 0;
   return EPB_OK;
+}
+
+// an EMPTY species gets at least R rows per column (redistribution: as many as the state it replaces)
+int epb_slots_ensure_rows(epb_handle *h, int is, int R) {
+  SpeciesDev &S = h->sp[is];
+  if (!S.slots || (S.arena_ready && S.R >= R)) return EPB_OK;
+  return slots_set_rows(h, is, std::min<long long>(R, slots_row_budget(h, is)));
 }
 
 static void fill_deliver(epb_handle *h, int is, DeliverOp &D) {
@@ -414,11 +438,15 @@ int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed) {
   return epb_slots_check(h);
 }
 
-int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed) {
+// ---- walking a species chunk by chunk (download, redistribution): any layout ---------------------------------
+// Every call to epb_species_iter_next hands out the next <= CH particles as contiguous SoA device arrays
+// (slot columns: gathered into the idle mover buffer by k_compact; the waiting entries of the current mover
+// buffer and the classic contiguous layout are handed out in place).  The species must not change meanwhile.
+int epb_species_iter_begin(epb_handle *h, int is, SpeciesIter &I) {
   SpeciesDev &S = h->sp[is];
-  const epb_config &c = h->cfg;
-  const int nd = c.ndims, nv = nd + 4;
-  if (!S.arena_ready || n <= 0) return EPB_OK;
+  I = SpeciesIter();
+  if (!S.slots) return EPB_OK;
+  if (!S.arena_ready) return EPB_OK;
   const int nkeys = h->tg.nkeys;
   // scan of the clamped counts -> start[nkeys + 1]
   int *tmpc = h->cell_count, *start = h->cell_start;
@@ -434,62 +462,126 @@ int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed) {
   }
   cub::DeviceScan::ExclusiveSum(h->cub_tmp, need, tmpc, start, nkeys + 1, h->stream);
   h->launches += 2;
-  std::vector<int> hstart((size_t)nkeys + 1);
-  EPB_CUDA(h, cudaMemcpyAsync(hstart.data(), start, ((size_t)nkeys + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  int mc = 0;
-  EPB_CUDA(h, cudaMemcpyAsync(&mc, S.mcount + S.mcur, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  I.hstart.resize((size_t)nkeys + 1);
+  EPB_CUDA(h, cudaMemcpyAsync(I.hstart.data(), start, ((size_t)nkeys + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaMemcpyAsync(&I.mc, S.mcount + S.mcur, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (mc > S.mcap) mc = (int)S.mcap;
-  // staging: columns -> the idle mover buffer (SoA, contiguous) -> wire layout -> host, <= 2 Mi particles a time
+  if (I.mc > S.mcap) I.mc = (int)S.mcap;
+  return EPB_OK;
+}
+
+int epb_species_iter_next(epb_handle *h, int is, SpeciesIter &I, long long CH, double *st[7], long long *m) {
+  SpeciesDev &S = h->sp[is];
+  *m = 0;
+  for (int q = 0; q < 7; q++) st[q] = nullptr;
+  if (!S.slots) {
+    if (I.lin >= S.n) return EPB_OK;
+    *m = std::min<long long>(CH, S.n - I.lin);
+    for (int q = 0; q < 7; q++) st[q] = S.buf[S.cur][q] ? S.buf[S.cur][q] + I.lin : nullptr;
+    I.lin += *m;
+    return EPB_OK;
+  }
+  if (!S.arena_ready) return EPB_OK;
+  const int nkeys = h->tg.nkeys;
+  if (CH > S.mcap) CH = S.mcap;
   const int stg = S.mcur ^ 1;
-  const int64_t CH = std::min<int64_t>(S.mcap, 2 << 20);
+  while (I.k0 < nkeys) {
+    // largest group-aligned key range whose particles fit one chunk
+    int k1 = I.k0;
+    while (k1 < nkeys) {
+      const int kn = std::min(nkeys, k1 + 32);
+      if ((long long)I.hstart[kn] - I.hstart[I.k0] > CH) break;
+      k1 = kn;
+    }
+    if (k1 == I.k0) return epb_fail(h, EPB_ERR_CAPACITY, "one group of slot columns exceeds the staging buffer");
+    const long long mm = (long long)I.hstart[k1] - I.hstart[I.k0];
+    const int k0 = I.k0;
+    I.k0 = k1;
+    if (mm > 0) {
+      CompactOp C;
+      for (int q = 0; q < 7; q++) { C.a[q] = S.buf[0][q]; C.dst[q] = S.mbuf[stg][q]; }
+      C.cnt = S.cnt; C.start = h->cell_start; C.R = S.R; C.k0 = k0; C.k1 = k1; C.base = I.hstart[k0];
+      k_compact<<<nblk((size_t)(k1 - k0), 148 * 8), 256, 0, h->stream>>>(C);
+      h->launches++;
+      for (int q = 0; q < 7; q++) st[q] = S.mbuf[stg][q];
+      *m = mm;
+      return EPB_OK;
+    }
+  }
+  // the entries waiting in the current mover buffer (no room in their column): all are live between steps
+  if (I.woff < I.mc) {
+    *m = std::min<long long>(I.mc - I.woff, CH);
+    for (int q = 0; q < 7; q++) st[q] = S.mbuf[S.mcur][q] ? S.mbuf[S.mcur][q] + I.woff : nullptr;
+    I.woff += *m;
+  }
+  return EPB_OK;
+}
+
+int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed) {
+  SpeciesDev &S = h->sp[is];
+  const epb_config &c = h->cfg;
+  const int nd = c.ndims, nv = nd + 4;
+  if (!S.arena_ready || n <= 0) return EPB_OK;
+  const long long CH = std::min<long long>(S.mcap, 2 << 20);
   if (!h->aos_stage) {
     EPB_CUDA(h, cudaMalloc(&h->aos_stage, (size_t)(2 << 20) * 7 * sizeof(double)));
   }
-  auto ship = [&](double *const *soa, int64_t off, int64_t take, int64_t done) -> int {
+  SpeciesIter I;
+  int rc = epb_species_iter_begin(h, is, I);
+  if (rc) return rc;
+  int64_t done = 0;
+  while (done < n) {
+    double *st[7];
+    long long m = 0;
+    rc = epb_species_iter_next(h, is, I, CH, st, &m);
+    if (rc) return rc;
+    if (m == 0) break;
+    const long long take = std::min<long long>(m, n - done);
     AosOp A;
-    for (int q = 0; q < 7; q++) A.soa[q] = soa[q] ? soa[q] + off : nullptr;
+    for (int q = 0; q < 7; q++) A.soa[q] = st[q];
     A.aos = h->aos_stage; A.n = take; A.nd = nd; A.nv = nv; A.to_soa = 0;
     k_aos<<<nblk((size_t)take), 256, 0, h->stream>>>(A);
     h->launches++;
     EPB_CUDA(h, cudaMemcpyAsync(packed + done * nv, h->aos_stage, (size_t)take * nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-    return EPB_OK;
-  };
-  int64_t done = 0;
-  int k0 = 0;
-  while (k0 < nkeys && done < n) {
-    // largest group-aligned key range whose particles fit one chunk
-    int k1 = k0;
-    while (k1 < nkeys) {
-      const int kn = std::min(nkeys, k1 + 32);
-      if ((int64_t)hstart[kn] - hstart[k0] > CH) break;
-      k1 = kn;
-    }
-    if (k1 == k0) return epb_fail(h, EPB_ERR_CAPACITY, "download: one group of columns exceeds the staging buffer");
-    const int64_t m = (int64_t)hstart[k1] - hstart[k0];
-    if (m > 0) {
-      CompactOp C;
-      for (int q = 0; q < 7; q++) { C.a[q] = S.buf[0][q]; C.dst[q] = S.mbuf[stg][q]; }
-      C.cnt = S.cnt; C.start = start; C.R = S.R; C.k0 = k0; C.k1 = k1; C.base = hstart[k0];
-      k_compact<<<nblk((size_t)(k1 - k0), 148 * 8), 256, 0, h->stream>>>(C);
-      h->launches++;
-      const int64_t take = std::min<int64_t>(m, n - done);
-      int rcs = ship(S.mbuf[stg], 0, take, done);
-      if (rcs) return rcs;
-      done += take;
-    }
-    k0 = k1;
-  }
-  // the entries waiting in the mover buffer (no room in their column)
-  int64_t woff = 0;
-  while (woff < mc && done < n) {
-    const int64_t take = std::min<int64_t>(std::min<int64_t>(mc - woff, CH), n - done);
-    int rcs = ship(S.mbuf[S.mcur], woff, take, done);
-    if (rcs) return rcs;
     done += take;
-    woff += take;
   }
   EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
+// Particles that are already on the device in the wire layout (redistribution): appended to the species.
+int epb_species_insert_aos(epb_handle *h, int is, const double *aos_dev, long long n) {
+  SpeciesDev &S = h->sp[is];
+  const int nd = h->cfg.ndims, nv = nd + 4;
+  if (n <= 0) return EPB_OK;
+  if (!S.slots) {
+    if (S.n + n > S.cap) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %lld particles > capacity %lld", is, S.n + n, S.cap);
+    AosOp A;
+    for (int q = 0; q < 7; q++) A.soa[q] = S.buf[S.cur][q] ? S.buf[S.cur][q] + S.n : nullptr;
+    A.aos = const_cast<double *>(aos_dev); A.n = n; A.nd = nd; A.nv = nv; A.to_soa = 1;
+    k_aos<<<nblk((size_t)n), 256, 0, h->stream>>>(A);
+    h->launches++;
+    S.n += n;
+    S.info_valid = false;
+    h->pushes_since_sort = 1 << 30;   // sort before the next push
+    return EPB_OK;
+  }
+  long long i0 = 0;
+  while (i0 < n) {
+    int waiting = 0;
+    int rc = epb_slots_waiting(h, is, &waiting);
+    if (rc) return rc;
+    const long long mm = std::min<long long>(n - i0, S.mcap - waiting);
+    if (mm <= 0) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: %d particles fit neither their columns (R = %d) nor the mover buffer", is, waiting, S.R);
+    AosOp A;
+    for (int q = 0; q < 7; q++) A.soa[q] = S.mbuf[S.mcur][q] ? S.mbuf[S.mcur][q] + waiting : nullptr;
+    A.aos = const_cast<double *>(aos_dev) + i0 * nv; A.n = mm; A.nd = nd; A.nv = nv; A.to_soa = 1;
+    k_aos<<<nblk((size_t)mm), 256, 0, h->stream>>>(A);
+    h->launches++;
+    rc = epb_slots_commit(h, is, waiting, mm);
+    if (rc) return rc;
+    i0 += mm;
+  }
   return EPB_OK;
 }

@@ -101,6 +101,7 @@ class Deck:
     smooth_compensation: bool = False
     smooth_strides: Sequence[int] = (1,)    # 'auto' = (1, 2, 3, 4)
     hc_push: bool = False                   # build flag -DHC_PUSH (Makefile:264): Higuera-Cary rotation, particles.F90:386-398
+    cuts: Optional[dict] = None             # axis -> (mins, maxs): slabs re-cut by the load balancer (balance.F90:383-436)
 
     # -- grid (setup.F90:162-204) ------------------------------------------
     def dx(self, d: int) -> float:
@@ -263,6 +264,8 @@ class Deck:
 
     # -- decomposition (mpi_routines.F90:317-351) ---------------------------
     def cell_ranges(self, d: int):
+        if self.cuts and d in self.cuts:
+            return list(self.cuts[d][0]), list(self.cuts[d][1])
         npd = max(1, self.nproc[d]) if d < self.ndims else 1
         ng_ = self.n[d] if d < self.ndims else 1
         n0 = ng_ // npd

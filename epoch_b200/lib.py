@@ -22,7 +22,7 @@ SYMBOLS = (
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
     "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy",
-    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile",
+    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute",
 )
 
 
@@ -46,6 +46,11 @@ class SpeciesCfg(C.Structure):
         ("charge", C.c_double), ("mass", C.c_double), ("bc_particle", C.c_int32 * 6),
         ("zero_current", C.c_int32), ("immobile", C.c_int32), ("capacity", C.c_int64),
     ]
+
+
+class Decomp(C.Structure):
+    """struct epb_decomp: cell_x_min(1:nprocx) ... of a tensor-product decomposition (mpi_routines.F90:317-351)"""
+    _fields_ = [("nproc", C.c_int32 * 3), ("cell_min", C.POINTER(C.c_int32) * 3), ("cell_max", C.POINTER(C.c_int32) * 3)]
 
 
 _lib = None
@@ -106,6 +111,8 @@ def load():
     L.epb_field_energy.argtypes = [vp, dp]
     L.epb_kinetic_energy.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.epb_calc_moment.argtypes = [vp, i32, i32, dp]
+    L.epb_redistribute.argtypes = [vp, C.POINTER(Decomp), C.POINTER(Decomp), C.POINTER(Config), C.POINTER(SpeciesCfg),
+                                   C.POINTER(vp)]
     L.epb_load_profile.argtypes = [vp, i32, dp]
     L.epb_launch_count.argtypes = [vp]; L.epb_launch_count.restype = i64
     L.epb_push_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), i32]

@@ -70,6 +70,95 @@ def rank_geometry(deck: Deck, rank: int):
     return geo
 
 
+def build_config(deck: Deck, rank: int, strict_fp: bool, sort_interval: int, capacity_factor: float,
+                 min_capacity: int, capacities: Optional[Sequence[int]] = None):
+    """(epb_config, epb_species[], geometry) of one rank: the mirror of the shared_data globals b200_attach copies
+    (fortran/epoch_b200_mod.F90), from the deck and its decomposition (incl. slabs re-cut by the balancer)."""
+    nd = deck.ndims
+    geo = rank_geometry(deck, rank)
+    bcf = deck.bc_codes()
+    # setup_boundaries normalisation (boundary.F90:44-57)
+    for i in range(6):
+        if bcf[i] in (2, 9):
+            bcf[i] = 8
+        if bcf[i] == 5:
+            bcf[i] = 4
+    periods = []
+    for d in range(3):
+        per = d < nd and bcf[2 * d] == 1
+        for s in deck.species:
+            if d < nd and deck.species_bc_codes(s)[2 * d] == 1:
+                per = True
+        periods.append(per)
+    cfg = _lib.Config()
+    cfg.ndims = nd
+    for d in range(3):
+        cfg.n[d] = geo["n"][d]
+        cfg.n_global[d] = deck.n[d] if d < nd else 1
+        cfg.dx[d] = deck.dx(d) if d < nd else 1.0
+        cfg.grid_min_local[d] = geo["grid_min_local"][d]
+        cfg.min_local[d] = geo["min_local"][d]
+        cfg.max_local[d] = geo["max_local"][d]
+        cfg.gmin[d] = deck.xmin[d] if d < nd else 0.0
+        cfg.gmax[d] = deck.xmax[d] if d < nd else 0.0
+        cfg.min_outer[d] = geo["min_outer"][d]
+        cfg.max_outer[d] = geo["max_outer"][d]
+    cfg.ng = NG
+    for i in range(6):
+        cfg.bc_field[i] = bcf[i]
+        cfg.is_boundary[i] = geo["is_bnd"][i]
+    for i, v in enumerate(_neighbour_table(deck, rank, periods)):
+        cfg.neighbour[i] = v
+    cfg.rank = rank
+    cfg.nranks = deck.nranks()
+    cfg.n_species = len(deck.species)
+    cfg.strict_fp = int(strict_fp)
+    cfg.sort_interval = sort_interval
+    cfg.dt = deck.dt()
+    cfg.field_order = int(deck.field_order)
+    cfg.maxwell_solver = deck.maxwell_solver_code()
+    cfg.hc_push = int(getattr(deck, "hc_push", False))
+    if deck.smooth_currents:
+        cfg.smooth_its = int(deck.smooth_iterations)
+        cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
+        cfg.smooth_strides = sum(int(v) << (4 * i) for i, v in enumerate(deck.smooth_strides))
+    st = deck.stencil()
+    for i, k in enumerate(deck.STENCIL_KEYS):
+        cfg.stencil[i] = st[k]
+    ncell = geo["n"][0] * geo["n"][1] * geo["n"][2]
+    sp = (_lib.SpeciesCfg * max(1, len(deck.species)))()
+    for i, s in enumerate(deck.species):
+        sp[i].charge, sp[i].mass = s.charge, s.mass
+        for k, b in enumerate(deck.species_bc_codes(s)):
+            # setup_particle_boundary (boundary.F90:108-122)
+            if b in (2, 10):
+                b = 9
+            if b in (3, 4):
+                b = 5
+            sp[i].bc_particle[k] = b
+        sp[i].zero_current = int(s.zero_current)
+        sp[i].immobile = int(s.immobile)
+        sp[i].capacity = max(min_capacity, int(capacity_factor * s.npart_per_cell * ncell))
+        if capacities is not None:
+            sp[i].capacity = max(min_capacity, int(capacities[i]))
+    return cfg, sp, geo
+
+
+def _decomp(deck: Deck):
+    """struct epb_decomp of a deck's decomposition (keeps the int arrays alive on the returned object)."""
+    d = _lib.Decomp()
+    keep = []
+    for a in range(3):
+        d.nproc[a] = max(1, deck.nproc[a]) if a < deck.ndims else 1
+        mins, maxs = deck.cell_ranges(a) if a < deck.ndims else ([1], [1])
+        amin, amax = (C.c_int32 * len(mins))(*mins), (C.c_int32 * len(maxs))(*maxs)
+        keep += [amin, amax]
+        d.cell_min[a] = C.cast(amin, C.POINTER(C.c_int32))
+        d.cell_max[a] = C.cast(amax, C.POINTER(C.c_int32))
+    d._keep = keep
+    return d
+
+
 class Simulation:
     def __init__(self, deck: Deck, rank: int = 0, strict_fp: bool = True, sort_interval: int = 1,
                  capacity_factor: float = 1.5, min_capacity: int = 4096, stream: Optional[int] = None):
@@ -77,71 +166,10 @@ class Simulation:
         self.rank = rank
         self.L = _lib.load()
         nd = deck.ndims
-        geo = rank_geometry(deck, rank)
+        self._build_args = dict(strict_fp=strict_fp, sort_interval=sort_interval, capacity_factor=capacity_factor,
+                                min_capacity=min_capacity)
+        cfg, sp, geo = build_config(deck, rank, **self._build_args)
         self.geo = geo
-        bcf = deck.bc_codes()
-        # setup_boundaries normalisation (boundary.F90:44-57)
-        for i in range(6):
-            if bcf[i] in (2, 9):
-                bcf[i] = 8
-            if bcf[i] == 5:
-                bcf[i] = 4
-        periods = []
-        for d in range(3):
-            per = d < nd and bcf[2 * d] == 1
-            for s in deck.species:
-                if d < nd and deck.species_bc_codes(s)[2 * d] == 1:
-                    per = True
-            periods.append(per)
-        cfg = _lib.Config()
-        cfg.ndims = nd
-        for d in range(3):
-            cfg.n[d] = geo["n"][d]
-            cfg.n_global[d] = deck.n[d] if d < nd else 1
-            cfg.dx[d] = deck.dx(d) if d < nd else 1.0
-            cfg.grid_min_local[d] = geo["grid_min_local"][d]
-            cfg.min_local[d] = geo["min_local"][d]
-            cfg.max_local[d] = geo["max_local"][d]
-            cfg.gmin[d] = deck.xmin[d] if d < nd else 0.0
-            cfg.gmax[d] = deck.xmax[d] if d < nd else 0.0
-            cfg.min_outer[d] = geo["min_outer"][d]
-            cfg.max_outer[d] = geo["max_outer"][d]
-        cfg.ng = NG
-        for i in range(6):
-            cfg.bc_field[i] = bcf[i]
-            cfg.is_boundary[i] = geo["is_bnd"][i]
-        for i, v in enumerate(_neighbour_table(deck, rank, periods)):
-            cfg.neighbour[i] = v
-        cfg.rank = rank
-        cfg.nranks = deck.nranks()
-        cfg.n_species = len(deck.species)
-        cfg.strict_fp = int(strict_fp)
-        cfg.sort_interval = sort_interval
-        cfg.dt = deck.dt()
-        cfg.field_order = int(deck.field_order)
-        cfg.maxwell_solver = deck.maxwell_solver_code()
-        cfg.hc_push = int(getattr(deck, "hc_push", False))
-        if deck.smooth_currents:
-            cfg.smooth_its = int(deck.smooth_iterations)
-            cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
-            cfg.smooth_strides = sum(int(v) << (4 * i) for i, v in enumerate(deck.smooth_strides))
-        st = deck.stencil()
-        for i, k in enumerate(deck.STENCIL_KEYS):
-            cfg.stencil[i] = st[k]
-        ncell = geo["n"][0] * geo["n"][1] * geo["n"][2]
-        sp = (_lib.SpeciesCfg * max(1, len(deck.species)))()
-        for i, s in enumerate(deck.species):
-            sp[i].charge, sp[i].mass = s.charge, s.mass
-            for k, b in enumerate(deck.species_bc_codes(s)):
-                # setup_particle_boundary (boundary.F90:108-122)
-                if b in (2, 10):
-                    b = 9
-                if b in (3, 4):
-                    b = 5
-                sp[i].bc_particle[k] = b
-            sp[i].zero_current = int(s.zero_current)
-            sp[i].immobile = int(s.immobile)
-            sp[i].capacity = max(min_capacity, int(capacity_factor * s.npart_per_cell * ncell))
         self._h = C.c_void_p()
         rc = self.L.epb_create(C.byref(cfg), sp, C.byref(self._h))
         if rc != 0:
@@ -150,8 +178,31 @@ class Simulation:
         self.species_cfg = sp
         self.nd = nd
         self.shape = tuple((geo["n"][d] + 2 * NG) if d < nd else 1 for d in (2, 1, 0))
+        self._stream = stream
         if stream is not None:
             self._chk(self.L.epb_set_stream(self._h, C.c_void_p(stream)))
+
+    def rebalance(self, cuts: dict, capacities: Optional[Sequence[int]] = None):
+        """balance_workload's data movement (balance.F90:93-300) for slabs the host has re-cut: `cuts` maps an axis
+        to (mins, maxs) as calculate_breaks returns them.  Collective: every rank calls it with the same cuts.
+        Fields and particles move to their new owners on the device (epb_redistribute); this object then describes
+        the rank's new sub-domain."""
+        import copy
+        new_deck = copy.copy(self.deck)
+        new_cuts = dict(self.deck.cuts or {})
+        new_cuts.update({int(a): (list(v[0]), list(v[1])) for a, v in cuts.items()})
+        new_deck.cuts = new_cuts
+        cfg, sp, geo = build_config(new_deck, self.rank, capacities=capacities, **self._build_args)
+        od, nd_ = _decomp(self.deck), _decomp(new_deck)
+        out = C.c_void_p()
+        rc = self.L.epb_redistribute(self._h, C.byref(od), C.byref(nd_), C.byref(cfg), sp, C.byref(out))
+        if rc != 0:
+            self._chk(rc)
+        self._h = out
+        self.deck, self.cfg, self.species_cfg, self.geo = new_deck, cfg, sp, geo
+        self.shape = tuple((geo["n"][d] + 2 * NG) if d < self.nd else 1 for d in (2, 1, 0))
+        if self._stream is not None:
+            self._chk(self.L.epb_set_stream(self._h, C.c_void_p(self._stream)))
 
     # ------------------------------------------------------------------
     def _chk(self, rc):

@@ -201,6 +201,23 @@ int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host);
  * that cell column, summed over the ranks, plus one field column per interior cell */
 int epb_load_profile(epb_handle *h, int axis, int64_t *load);
 
+/* balance_workload's data movement (housekeeping/balance.F90:93-300): redistribute_domain / redistribute_fields
+ * (:383-436, :436-1060; redistribute_field_2d :1282) and distribute_particles (:2156-2211).  Collective over the ranks.
+ * The host has re-cut the slabs (calculate_breaks on epb_load_profile) and describes the old and the new tensor-product
+ * decomposition -- cell_min / cell_max are cell_x_min(1:nprocx) ... of mpi_routines.F90:317-351, 1-based inclusive global
+ * cells per processor coordinate; rank = (cz * nprocy + cy) * nprocx + cx -- together with the config of THIS rank in the
+ * new decomposition.  The library builds the new device state, sends every field cell (interior, plus the ghost cells of
+ * the physical domain edges, as redistribute_field_2d does; the other ghost cells are refilled by the halo exchange) and
+ * every particle (get_particle_processor, balance.F90:2095-2151) to the rank that owns it now, hands the communicator
+ * over and destroys the old handle.  *out replaces old_h, which must not be used again. */
+typedef struct epb_decomp {
+  int32_t nproc[3];
+  const int32_t *cell_min[3];
+  const int32_t *cell_max[3];
+} epb_decomp;
+int epb_redistribute(epb_handle *old_h, const epb_decomp *old_d, const epb_decomp *new_d, const epb_config *new_cfg,
+                     const epb_species *new_species, epb_handle **out);
+
 /* -- instrumentation ---------------------------------------------------------------
  * kernel launch counter since creation (bench.py's gpu_launches), and CUDA-event
  * timing of the push/deposit kernel alone: average ms per launch since the last reset */

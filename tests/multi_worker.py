@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from tests.parity_check import make_deck, run_case  # noqa: E402,F401
+from tests.parity_check import make_deck, run_case, run_rebalance_case  # noqa: E402,F401
 
 
 def main():
@@ -27,7 +27,15 @@ def main():
         dist.broadcast_object_list(ids, 0)
         return ids[0]
 
-    res = run_case(name, rank, world, share_id)
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    if name == "rebalance2d":
+        res = run_rebalance_case(rank, world, share_id, allgather)
+    else:
+        res = run_case(name, rank, world, share_id)
     dist.barrier()
     dist.destroy_process_group()
     print("RESULT " + json.dumps(res), flush=True)

@@ -112,3 +112,136 @@ def run_case(name, rank, world, share_id, strict=True, sort_interval=2, moments=
     res["counts"] = [sim.count(i) for i in range(len(dk.species))]
     sim.close()
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Load balancing (SURVEY.md 8 f2 / BASELINE C3): the slabs are re-cut in mid-run and fields and particles are
+# redistributed on the device (epb_redistribute = balance_workload's data movement, balance.F90:93-300).
+# ---------------------------------------------------------------------------------------------------------
+def _assemble(deck, pieces, name=None):
+    """Global interior array from per-rank interiors [(rank, array[z,y,x])] of `deck`'s decomposition."""
+    shape = [deck.n[d] if d < deck.ndims else 1 for d in (2, 1, 0)]
+    out = np.zeros(shape, dtype=pieces[0][1].dtype)
+    for r, a in pieces:
+        n, g = deck.local_extent(r)
+        sl = tuple(slice(g[d] - 1, g[d] - 1 + n[d]) for d in (2, 1, 0))
+        out[sl] = a
+    return out
+
+
+def _interior(a):
+    sl = tuple(slice(5, -5) if a.shape[ax] > 1 else slice(None) for ax in range(3))
+    return a[sl]
+
+
+def run_rebalance_case(rank, world, share_id, allgather, k1=12, k2=10, strict=True, n=(96, 64)):
+    """Foil deck (laser on x_min, particles only in the slab), `world` ranks along x.  After k1 steps the x
+    slabs are re-cut with EPOCH's rule (epb_load_profile -> calculate_breaks) and the state is redistributed.
+    Checks: the move loses / changes nothing (global particle multiset and global fields bit-identical, every
+    particle on the rank get_particle_processor names, per-rank counts as numpy computes them from the
+    positions); then k2 more steps agree with the CPU oracle, which keeps the ORIGINAL decomposition -- the
+    physics does not depend on where the cuts are -- to 1e-11 on the assembled global E/B/J, with bit-exact
+    global per-cell counts."""
+    from epoch_b200.pic import Simulation
+    from oracle.oracle import Oracle
+    dk = decks.foil2d(n=n, nproc=(world, 1, 1), nsteps=k1 + k2)
+    res = {"case": "rebalance2d", "rank": rank, "ok": True, "msgs": []}
+
+    def bad(msg):
+        res["ok"] = False
+        res["msgs"].append(msg)
+
+    o = Oracle(dk)
+    o.auto_load()
+    sim = Simulation(dk, rank=rank, strict_fp=strict, sort_interval=2, capacity_factor=3.0)
+    if world > 1:
+        sim.set_comm(share_id(Simulation.nccl_unique_id() if rank == 0 else None))
+    nsp = len(dk.species)
+    for isp in range(nsp):
+        sim.upload_species(isp, o.get_particles(rank, isp))
+    dt = dk.dt()
+    ranks = list(range(world))
+    state = {"time": 0.0}
+
+    def sources(t):
+        for side in range(2 * dk.ndims):
+            if dk.has_boundary_source(side):
+                for r in ranks:
+                    s1, s2 = dk.laser_sources(r, side, t)
+                    o.set_laser_source(r, side, s1, s2)
+                s1, s2 = sim.deck.laser_sources(rank, side, t)   # the rank's CURRENT sub-domain
+                sim.set_laser_source(0, side, s1, s2)
+
+    state["time"] += dt / 2.0
+    sources(state["time"])
+    o.init(); sim.init()
+
+    def step():
+        o.fields_half(); sim.fields_half()
+        o.push(); sim.push()
+        o.current_finish(); sim.current_finish()
+        state["time"] += dt
+        sources(state["time"])
+        o.fields_final(); sim.fields_final()
+
+    for _ in range(k1):
+        step()
+    # ---- re-cut ----
+    before_p = [sim.download_species(i) for i in range(nsp)]
+    before_f = {f: _interior(sim.download_field(f)) for f in FIELDS}
+    old_deck = sim.deck
+    load = sim.load_profile(0)
+    mins, maxs = D.calculate_breaks(load, world)
+    res["cuts"] = [list(mins), list(maxs)]
+    old_counts = [sim.count(i) for i in range(nsp)]
+    sim.rebalance({0: (mins, maxs)}, capacities=[3 * sum(allgather(c)) // max(1, world) + 4096 for c in old_counts])
+    after_p = [sim.download_species(i) for i in range(nsp)]
+    after_f = {f: _interior(sim.download_field(f)) for f in FIELDS}
+    allb = allgather((before_p, before_f))
+    alla = allgather((after_p, after_f))
+    from tests.gpu_util import sorted_rows
+    for isp in range(nsp):
+        b = sorted_rows(np.concatenate([x[0][isp] for x in allb]))
+        a = sorted_rows(np.concatenate([x[0][isp] for x in alla]))
+        if a.shape != b.shape or not np.array_equal(a, b):
+            bad(f"species {isp}: the redistribution changed the global particle set")
+        # get_particle_processor (balance.F90:2095-2151) on this rank's particles
+        p = after_p[isp]
+        dx = dk.dx(0)
+        lo = dk.x_global(0, mins[rank]) - dx * (0.5 + (3.0 if rank == 0 else 0.0))
+        hi = dk.x_global(0, maxs[rank]) + dx * (0.5 + (3.0 if rank == world - 1 else 0.0))
+        if p.shape[0] and not np.all((p[:, 0] >= lo) & (p[:, 0] < hi)):
+            bad(f"species {isp}: a particle sits on the wrong rank after the redistribution")
+        allp = np.concatenate([x[0][isp] for x in allb])
+        want = int(np.sum((allp[:, 0] >= lo) & (allp[:, 0] < hi)))
+        if sim.count(isp) != want:
+            bad(f"species {isp}: count {sim.count(isp)} after the re-cut, expected {want}")
+    for f in FIELDS[:6]:
+        gb = _assemble(old_deck, [(r, x[1][f]) for r, x in enumerate(allb)])
+        ga = _assemble(sim.deck, [(r, x[1][f]) for r, x in enumerate(alla)])
+        if not np.array_equal(ga, gb):
+            bad(f"{f}: the redistribution changed the global field")
+    # ---- carry on ----
+    for _ in range(k2):
+        step()
+    mine = ({f: _interior(sim.download_field(f)) for f in FIELDS}, [sim.cell_counts(i) for i in range(nsp)],
+            [sim.count(i) for i in range(nsp)])
+    allm = allgather(mine)
+    for f in FIELDS:
+        g_sim = _assemble(sim.deck, [(r, x[0][f]) for r, x in enumerate(allm)])
+        g_orc = _assemble(dk, [(r, _interior(o.field(r, f))) for r in ranks])
+        e = rel_l2(g_sim, g_orc)
+        if not e <= 1e-11:
+            bad(f"{f} after the re-cut: rel_l2 {e:.3e}")
+    for isp in range(nsp):
+        g_sim = _assemble(sim.deck, [(r, x[1][isp]) for r, x in enumerate(allm)])
+        g_orc = _assemble(dk, [(r, o.cell_counts(r, isp)) for r in ranks])
+        if not np.array_equal(g_sim, g_orc):
+            bad(f"species {isp}: global per-cell counts differ after the re-cut")
+        tot = sim.global_count(isp)
+        if tot != sum(o.count(r, isp) for r in ranks):
+            bad(f"species {isp}: global count {tot}")
+    res["counts_after"] = [x[2] for x in allm]
+    res["counts_before"] = allgather(old_counts)
+    sim.close()
+    return res

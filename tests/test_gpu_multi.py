@@ -43,7 +43,21 @@ def test_two_ranks(name):
     _run(name, 2)
 
 
-@pytest.mark.parametrize("name", ["thermal2d_xy", "foil2d"])
+def test_rebalance_two_ranks():
+    """epb_redistribute (balance_workload's data movement): re-cut slabs in mid-run, nothing lost, physics unchanged"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("rebalance2d", 2)
+
+
+def test_rebalance_single_rank():
+    """the same machinery on one rank (every cell and particle 'moves' to the same rank through the new state)"""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    _run("rebalance2d", 1)
+
+
+@pytest.mark.parametrize("name", ["thermal2d_xy", "foil2d", "rebalance2d", "foil2d_xy"])
 def test_four_ranks(name):
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs")
