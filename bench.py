@@ -169,6 +169,190 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def c3_deck(n_local, ppc, nproc):
+    """epoch2d laser-solid interaction (after epoch2d/example_decks/ramp.deck): simple_laser on
+    x_min, simple_outflow on x_max, y periodic; an overdense electron + proton slab in the middle fifth of the
+    box, nothing elsewhere -- so a plain nprocx x nprocy split leaves the outer x slabs without particles."""
+    from epoch_b200 import deck as D
+    lam = 1 * D.micron
+    omega = 2 * D.pi * D.c / lam
+    ncrit = omega ** 2 * D.epsilon0 * D.m0 / D.q0 ** 2
+    n = [n_local * nproc[0], n_local * nproc[1]]
+    dx = lam / 32.0
+    L = [n[0] * dx, n[1] * dx]
+    las = D.Laser("x_min", D.Laser.amp_from_intensity_w_cm2(1.0e19), omega,
+                  profile=lambda y, z: D.gauss(y, 0, 0.25 * L[1]),
+                  t_profile=lambda t: D.gauss(t, 30 * D.femto, 12 * D.femto) if t < 30 * D.femto else 1.0)
+    box_lo, box_hi = (0.4 * L[0], -1e300, -1e300), (0.6 * L[0], 1e300, 1e300)
+    bcp = ["open", "open", "periodic", "periodic"]
+    sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=ppc, density=10 * ncrit, temp=(1.0e6,) * 3,
+                    box_lo=box_lo, box_hi=box_hi, bc_particle=bcp),
+          D.Species("proton", D.q0, 1836.2 * D.m0, npart_per_cell=ppc, density=10 * ncrit, temp=(1.0e6,) * 3,
+                    box_lo=box_lo, box_hi=box_hi, bc_particle=bcp)]
+    return D.Deck(2, n, [0.0, -L[1] / 2], [L[0], L[1] / 2], ["simple_laser", "simple_outflow", "periodic", "periodic"],
+                  species=sp, lasers=[las], nproc=(nproc[0], nproc[1], 1), t_end=1.0)
+
+
+def run_c3(args, world, rank, local_rank, parity, torch, dist):
+    """--workload c3: K steps with EPOCH's plain split, then the slabs are re-cut (epb_load_profile ->
+    calculate_breaks -> epb_redistribute) and K steps are timed again.  `value` is the balanced run."""
+    import numpy as np
+    from epoch_b200 import deck as D
+    from epoch_b200.pic import Simulation
+    nproc = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
+    dk = c3_deck(args.n, args.ppc, nproc)
+    stream = torch.cuda.Stream()
+    ncell_foil = 0.2 * dk.n[0] * dk.n[1]
+    cap = int(1.6 * ncell_foil * args.ppc / world) + (1 << 20)       # per species; every rank can take an equal share
+    n_loc, g_loc = dk.local_extent(rank)
+    # before the re-cut the two middle x slabs hold everything
+    frac = max(0.0, min(0.6 * dk.n[0], g_loc[0] - 1 + n_loc[0]) - max(0.4 * dk.n[0], g_loc[0] - 1)) / max(1, n_loc[0])
+    cap0 = max(cap, int(1.1 * frac * n_loc[0] * n_loc[1] * args.ppc) + (1 << 20))
+    sim = Simulation(dk, rank=rank, strict_fp=bool(args.strict), sort_interval=args.sort_interval,
+                     capacity_factor=cap0 / max(1.0, args.ppc * n_loc[0] * n_loc[1]), stream=stream.cuda_stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(Simulation.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        sim.set_comm(bytes(idt.cpu().tolist()))
+    # loader (stands in for auto_load, helper.F90:95): ppc particles in every foil cell of this rank
+    rng = np.random.default_rng(20261018 + rank)
+    dx = dk.dx(0)
+    ix = np.arange(g_loc[0], g_loc[0] + n_loc[0])
+    xc = dk.x_global(0, ix)
+    in_foil = ix[(xc >= dk.species[0].box_lo[0]) & (xc < dk.species[0].box_hi[0])]
+    for isp, spc in enumerate(dk.species):
+        npart = len(in_foil) * n_loc[1] * args.ppc
+        p = np.empty((npart, 6))
+        if npart:
+            cx = np.repeat(in_foil, n_loc[1] * args.ppc)
+            cy = np.tile(np.repeat(np.arange(g_loc[1], g_loc[1] + n_loc[1]), args.ppc), len(in_foil))
+            p[:, 0] = dk.x_global(0, cx) + (rng.random(npart) - 0.5) * dx
+            p[:, 1] = dk.x_global(1, cy) + (rng.random(npart) - 0.5) * dx
+            sd = math.sqrt(spc.temp[0] * D.kb * spc.mass)
+            p[:, 2:5] = rng.normal(size=(npart, 3)) * sd
+            p[:, 5] = spc.density * dx * dx / args.ppc
+        sim.upload_species(isp, p)
+        del p
+    dt = dk.dt()
+    state = {"t": dt / 2.0}
+
+    def sources():
+        for side in (0, 1):
+            if sim.geo["is_bnd"][side]:
+                s1, s2 = sim.deck.laser_sources(rank, side, state["t"])
+                sim.set_laser_source(0, side, s1, s2)
+
+    sources()
+    sim.init()
+
+    def step():
+        sim.fields_half(); sim.push(); sim.current_finish()
+        state["t"] += dt
+        sources()
+        sim.fields_final()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k):
+        barrier()
+        sim.push_kernel_ms(reset=1)
+        l0 = sim.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(k):
+                step()
+            e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        pm, pn = sim.push_kernel_ms(reset=2)
+        t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item()), sim.launch_count() - l0, pm, pn
+
+    def counts():
+        loc = sum(sim.count(i) for i in range(2))
+        t = torch.tensor([loc], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allc, t)
+        else:
+            allc = [t]
+        return [int(c.item()) for c in allc]
+
+    for _ in range(args.warmup):
+        step()
+    c_before = counts()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_u, wall_u, launches_u, _, _ = timed(args.steps)
+    n_total = sum(c_before)
+    # ---- the balancer: EPOCH's rule on the device histogram, then the device remap ----
+    t0 = time.perf_counter()
+    cuts = {}
+    for axis in (0, 1):
+        if nproc[axis] > 1:
+            cuts[axis] = D.calculate_breaks(sim.load_profile(axis), nproc[axis])
+    if cuts:
+        sim.rebalance(cuts, capacities=[cap, cap])
+    barrier()
+    rebalance_s = time.perf_counter() - t0
+    c_after = counts()
+    for _ in range(2):
+        step()
+    ms_b, wall_b, launches_b, push_ms, push_n = timed(args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    n_end = sum(counts())
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bpu = 88.0 + 120.0 / (2 * args.ppc)
+        # the fullest rank's kernel: its particles x bytes / its push time (rank 0's own timing is reported)
+        achieved = (c_after[0] * bpu / (push_ms * 2 * 1e-3)) / 1e9 if push_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": n_total * args.steps / (ms_b * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_b / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"epoch2d laser-solid: simple_laser on x_min (1e19 W/cm^2, 1 um), simple_outflow on x_max, "
+                                   f"y periodic, 10 n_crit e-/p+ foil in the middle fifth of x, {args.ppc} ppc per species, "
+                                   f"{dk.n[0]}x{dk.n[1]} cells, pinned {nproc[0]}x{nproc[1]} decomposition (BASELINE C3)",
+                       "decomposition": f"{nproc[0]}x{nproc[1]}", "strict_fp": int(args.strict), "particles_total": n_total,
+                       "particles_end": n_end, "load_balancer": "calculate_breaks (balance.F90:1948) on epb_load_profile, "
+                                                                "epb_redistribute", "cuts": {str(k): v for k, v in cuts.items()},
+                       "l2_policy": "particle state per GPU exceeds the 126 MB L2"},
+            "c3": {"unbalanced_value": n_total * args.steps / (ms_u * 1e-3), "unbalanced_ms_per_step": ms_u / args.steps,
+                   "balanced_ms_per_step": ms_b / args.steps, "rebalance_s": rebalance_s,
+                   "particles_per_rank_before": c_before, "particles_per_rank_after": c_after},
+            "e2e": {"value": n_total * args.steps / wall_b, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * 2 * (sim.geo["n"][1] + 1) * 8, "d2h_bytes_per_step": 0,
+                    "note": "wall clock of the same steps through the C ABI incl. the per-step laser source planes from the host"},
+            "gpu_launches": launches_b, "parity_check": parity,
+            "parity_cases": f"thermal2d_bench, foil2d_xy on {world} rank(s) (tests/parity_check.py)",
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "kernel": "push_slots_2d (push+deposit), two species, rank 0 after the re-cut",
+                         "bytes_per_update": bpu, "kernel_ms": push_ms, "kernel_launches": push_n,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,8 +361,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", dest="n", type=int, default=4096, help="cells per side per GPU")
     ap.add_argument("--ppc", type=int, default=None)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU; "
+                         "c3: 2D laser-solid (laser on x_min, overdense e-/p+ foil), pinned nprocx x nprocy, load "
+                         "balancer off and on")
     variant = int(os.environ.get("EPB_PUSH_VARIANT", "5"))
     ap.add_argument("--sort-interval", type=int, default=int(os.environ.get("EPB_SORT_INTERVAL", "0")),
                     help="0 = the library default: 2 for the cell-owner 2D kernel, 8 otherwise")
@@ -191,6 +377,10 @@ def main():
         if args.n == 4096:
             args.n = 384
         args.ppc = args.ppc or 8
+    if args.workload == "c3":
+        if args.n == 4096:
+            args.n = 2048
+        args.ppc = args.ppc or 32
     args.ppc = args.ppc or 64
     if args.sort_interval <= 0:
         args.sort_interval = 2 if (args.workload == "c2" and variant in (2, 3, 4)) else 8
@@ -218,6 +408,8 @@ def main():
     if args.workload == "c4":
         nproc = split_3d(world)
         dk = c4_deck(args.n, args.ppc, nproc)
+    elif args.workload == "c3":
+        nproc, dk = None, None
     else:
         nproc = split_2d(world)
         dk = c2_deck(args.n, args.ppc, nproc)
@@ -253,6 +445,11 @@ def main():
         parity = "ok" if int(bad.item()) == 0 else ("FAILED: " + " | ".join(msgs) if msgs else "FAILED on another rank")
         if msgs:
             print("parity_check:", msgs, file=sys.stderr, flush=True)
+    if args.workload == "c3":
+        run_c3(args, world, rank, local_rank, parity, torch, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     stream = torch.cuda.Stream()
     sim = Simulation(dk, rank=rank, strict_fp=bool(args.strict), sort_interval=args.sort_interval,
                      capacity_factor=1.02 if world == 1 else 1.15, stream=stream.cuda_stream)

@@ -1709,7 +1709,9 @@ int epb_push(epb_handle *h) {
         int rcm = current_bcs_species(h, is);
         if (rcm) return rcm;
       }
-      int rc = epb_particle_exchange(h, is);
+      int rc = epb_slots_after_push(h, is);
+      if (rc) return rc;
+      rc = epb_particle_exchange(h, is);
       if (rc) return rc;
       rc = epb_slots_deliver(h, is);
       if (rc) return rc;

@@ -127,6 +127,15 @@ struct PushParams {
   int *mcount;             // device counter (may run past mcap: readers clamp)
   int mcap;
   int *err;                // device error word: bit 0 = mover buffer overflow lost a particle
+  // group inboxes (layout 2): a mover whose next column is known goes straight into the inbox of that column's
+  // group (64-byte entries: x, y, px, py, pz, w, destination lane, pad -- two full sectors, written by one lane),
+  // and the NEXT push reads it from there in the rounds after the column's own rows; ib_in / ic_in are the
+  // inbox this push consumes, ib_out / ic_out the one it fills.  nullptr: every mover takes the M path.
+  const double *ib_in;
+  const int *ic_in;
+  double *ib_out;
+  int *ic_out;
+  int IC;                  // entries per group inbox (<= 256)
 };
 
 struct SpeciesDev {
@@ -155,6 +164,11 @@ struct SpeciesDev {
   int mcur = 0;
   long long mcap = 0;
   bool arena_ready = false;   // R chosen and the arena allocated (at the first upload / load, when the density is known)
+  double *inbox[2] = {nullptr, nullptr};   // [ngroups][IC][8] group inboxes (see PushParams), ping-pong
+  int *icnt[2] = {nullptr, nullptr};       // [ngroups] entries per inbox (may run past IC: readers clamp)
+  int icur = 0;                            // the inbox the next push consumes
+  int IC = 0;
+  bool inbox_dirty = false;                // inbox[icur] may hold particles (between two pushes)
 };
 
 // opaque storage of a CUtensorMap (128 bytes, 64-byte aligned), see fdtd_tma.cu
@@ -245,6 +259,8 @@ int epb_slots_waiting(epb_handle *h, int is, int *waiting);       // entries of 
 int epb_slots_commit(epb_handle *h, int is, int waiting, long long m);  // m staged particles behind them: flags, count, deliver
 int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed);
 int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed);
+int epb_slots_settle(epb_handle *h, int is);                      // group inboxes -> columns (before anything but a push walks the species)
+int epb_slots_after_push(epb_handle *h, int is);                  // the consumed inbox is emptied, the filled one becomes current
 int epb_slots_count(epb_handle *h, int is, long long *n);         // synchronises
 // chunked walk over a species' particles as contiguous SoA device arrays, any layout (slots.cu)
 struct SpeciesIter {

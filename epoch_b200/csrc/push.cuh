@@ -45,6 +45,19 @@ __device__ __forceinline__ void tri(double f, double &gm, double &g0, double &gp
   gp = 0.25 + cf2 - f;
 }
 
+// The same weights for the performance build in four FP64 instructions (a = f^2 + 1/4 fused, g0 = 2 - 2a);
+// the parity build keeps the reference's expression tree.
+__device__ __forceinline__ void tri_s(double f, double &gm, double &g0, double &gp) {
+#ifdef EPB_FAST_MATH
+  const double a = fma(f, f, 0.25);
+  gm = a + f;
+  gp = a - f;
+  g0 = fma(-2.0, a, 2.0);
+#else
+  tri(f, gm, g0, gp);
+#endif
+}
+
 // boundary.F90:1064-1433 for one particle.  Returns -1 if the particle stays on
 // this rank, else the outbox slot: direction index (iz+1)*9+(iy+1)*3+(ix+1), or 13
 // for a particle that left the system (open boundary, beyond x_min_outer).
@@ -1325,10 +1338,11 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_cell_2d(const __grid_cons
 // simply stays where it is and is deposited through the general path next step: placement is an
 // optimisation, never a correctness condition.  Deposit exactly as push_cell_2d (21 register sums per
 // cell, core/edge split for one-axis movers, drain_extras for the rest).
+constexpr int SLOT_LK = 16;   // arrivals one column takes from its group's inbox per step (more: through M)
 template <int CTY>
 constexpr size_t pushslots_smem() {
   return sizeof(double) * ((size_t)9 * CPITCH * (CTY + 2 * HALO) + (size_t)(CTY / 2) * QDBL * QCAP) +
-         sizeof(int) * ((size_t)(CTY / 2) * QCAP + 2);
+         sizeof(int) * ((size_t)(CTY / 2) * QCAP + 2 + (size_t)(CTY / 2) * 32) + (size_t)(CTY / 2) * 32 * SLOT_LK;
 }
 
 template <int CTY, int MINB>
@@ -1340,6 +1354,8 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   double *sJ = sF + 6 * TILE_ELEMS;                  // [3][TH][TW]
   double *sQd_all = sJ + 3 * TILE_ELEMS;
   int *sQk_all = reinterpret_cast<int *>(sQd_all + PUSH2D_WARPS * QDBL * QCAP);
+  int *sAcnt_all = sQk_all + PUSH2D_WARPS * QCAP + 2;                               // [warp][32] arrivals per lane
+  unsigned char *sAlist_all = reinterpret_cast<unsigned char *>(sAcnt_all + PUSH2D_WARPS * 32);  // [warp][32][SLOT_LK]
   const int tile = blockIdx.x;
   const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
   const int ox = ttx * T2X + 1 - HALO;  // cell index of shared column 0
@@ -1348,7 +1364,11 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   const int my_key = tile * (T2X * T2Y) + warp * 32 + lane;
   int my_cnt = P.cnt[my_key];
   if (my_cnt > P.R) my_cnt = P.R;
-  if (!__syncthreads_or(my_cnt > 0)) return;
+  // entries waiting in this warp's group inbox (filled by the previous push)
+  const int grp = my_key >> 5;
+  int inA = P.ic_in ? P.ic_in[grp] : 0;
+  if (inA > P.IC) inA = P.IC;
+  if (!__syncthreads_or(my_cnt > 0 || inA > 0)) return;
   for (int q = tid; q < TILE_ELEMS; q += PUSH2D_THREADS) {
     const int lx = q % TW, ly = q / TW;
     const int cx = ox + lx, cy = oy + ly;
@@ -1372,10 +1392,43 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   int qcount = 0;  // warp-uniform
   const unsigned lt_mask = (1u << lane) - 1u;
 
+  // ---- this warp's inbox: which entries are for which lane (entry = 8 doubles, [6] = destination lane) ----
+  int *sAcnt = sAcnt_all + warp * 32;
+  unsigned char *sAlist = sAlist_all + warp * 32 * SLOT_LK;
+  const double *ibg = P.ib_in ? P.ib_in + (size_t)grp * (size_t)P.IC * 8 : nullptr;
+  sAcnt[lane] = 0;
+  __syncwarp();
+  for (int j0 = 0; j0 < inA; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < inA) {
+      const int ml = (int)__double_as_longlong(ibg[(size_t)j * 8 + 6]) & 31;
+      const int pos = atomicAdd(&sAcnt[ml], 1);
+      if (pos < SLOT_LK) {
+        sAlist[ml * SLOT_LK + pos] = (unsigned char)j;
+      } else {
+        // more arrivals than one column takes per step: the entry goes on through the mover buffer (flag 0)
+        const int m = atomicAdd(P.mcount, 1);
+        if (m < P.mcap) {
+          const double *e = ibg + (size_t)j * 8;
+          P.mx[0][m] = e[0]; P.mx[1][m] = e[1];
+          P.mp[0][m] = e[2]; P.mp[1][m] = e[3]; P.mp[2][m] = e[4];
+          P.mw[m] = e[5];
+          P.mflag[m] = 0;
+        } else {
+          atomicOr(P.err, 1);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  int my_a = sAcnt[lane];
+  if (my_a > SLOT_LK) my_a = SLOT_LK;
+  const int my_tot = my_cnt + my_a;
+
   // this lane's cell (1-based cell indices as in the reference)
   const int hcx = ttx * T2X + (lane & 15) + 1;
   const int hcy = tty * T2Y + warp * 2 + (lane >> 4) + 1;
-  const int maxcnt = __reduce_max_sync(FULL, my_cnt);
+  const int maxcnt = __reduce_max_sync(FULL, my_tot);
   const size_t gbase = ((size_t)(my_key >> 5) * (size_t)P.R) * 32 + lane;  // slot of row 0 of this lane's column
   int wcur = 0;  // write cursor: rows 0 .. wcur-1 hold the particles that stay in this column
 
@@ -1392,13 +1445,22 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   }
 
   // software pipeline: the next row's loads are in flight while this one computes
+  // (rounds 0 .. my_cnt-1 walk the column, rounds my_cnt .. my_tot-1 take the lane's arrivals from the inbox)
   double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
-  if (my_cnt > 0) {
-    n_w = P.w[gbase]; n_x = P.x[0][gbase]; n_y = P.x[1][gbase];
-    n_px = P.p[0][gbase]; n_py = P.p[1][gbase]; n_pz = P.p[2][gbase];
-  }
+  auto fetch = [&](int rn) {
+    if (rn < my_cnt) {
+      const size_t sl = gbase + (size_t)rn * 32;
+      n_w = P.w[sl]; n_x = P.x[0][sl]; n_y = P.x[1][sl];
+      n_px = P.p[0][sl]; n_py = P.p[1][sl]; n_pz = P.p[2][sl];
+    } else if (rn < my_tot) {
+      const double2 *e = reinterpret_cast<const double2 *>(ibg + (size_t)sAlist[lane * SLOT_LK + (rn - my_cnt)] * 8);
+      const double2 v0 = e[0], v1 = e[1], v2 = e[2];
+      n_x = v0.x; n_y = v0.y; n_px = v1.x; n_py = v1.y; n_pz = v2.x; n_w = v2.y;
+    }
+  };
+  fetch(0);
   for (int r = 0; r < maxcnt; r++) {
-    const bool active = r < my_cnt;
+    const bool active = r < my_tot;
     const double part_weight = n_w;
     const double raw_x = n_x, raw_y = n_y, raw_px = n_px, raw_py = n_py, raw_pz = n_pz;
     double px_ = n_x - P.grid_min_local[0];
@@ -1406,18 +1468,17 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
     double part_ux = n_px * P.ipart_mc;
     double part_uy = n_py * P.ipart_mc;
     double part_uz = n_pz * P.ipart_mc;
-    if (r + 1 < my_cnt) {
-      const size_t sl = gbase + (size_t)(r + 1) * 32;
-      n_w = P.w[sl]; n_x = P.x[0][sl]; n_y = P.x[1][sl];
-      n_px = P.p[0][sl]; n_py = P.p[1][sl]; n_pz = P.p[2][sl];
-    }
+    fetch(r + 1);
     // what happens to the particle: 0 stays in this column, 1 pushed and leaves through M (flag 0, or 1 with
     // dir >= 0), 2 unpushed through M (flag 2), 3 deleted
-    int disp = 0, dir = -1;
+    int disp = 0, dir = -1, nkx, nky;
+    bool touched = false;
     double o_x = raw_x, o_y = raw_y, o_px = raw_px, o_py = raw_py, o_pz = raw_pz;
     bool extras = false;
-    int key = 0, dcx = 0, dcy = 0;
-    double q_fxo = 0, q_fxn = 0, q_fyo = 0, q_fyn = 0, fjx = 0, fjy = 0, fjz = 0;
+    // only read where `extras` (resp. a mover's disp) says they were set: deliberately not initialised, zeroing
+    // them every round costs ~20 instructions
+    int key, dcx, dcy, ib_slot = -1;
+    double q_fxo, q_fxn, q_fyo, q_fyn, fjx, fjy, fjz;
     if (active) {
       double root;
       gamma_root(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0, P.dtco2, root);
@@ -1434,13 +1495,13 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
       } else {
         double gx[3], gy[3], hx[3], hy[3];
         const double fxo = (double)(cx1 - 1) - cell_x_r, fyo = (double)(cy1 - 1) - cell_y_r;
-        tri(fxo, gx[0], gx[1], gx[2]);
-        tri(fyo, gy[0], gy[1], gy[2]);
+        tri_s(fxo, gx[0], gx[1], gx[2]);
+        tri_s(fyo, gy[0], gy[1], gy[2]);
         int cx2 = __double2int_rd(cell_x_r);
-        tri((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
+        tri_s((double)cx2 - cell_x_r + 0.5, hx[0], hx[1], hx[2]);
         cx2 += 1;
         int cy2 = __double2int_rd(cell_y_r);
-        tri((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
+        tri_s((double)cy2 - cell_y_r + 0.5, hy[0], hy[1], hy[2]);
         cy2 += 1;
         // shared-tile offsets of (cell-1, cell-1)
         const int o11 = (cy1 - 1 - oy) * TW + (cx1 - 1 - ox);
@@ -1492,8 +1553,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
         const double part_vz = part_uz * c * igamma;
         px_ = px_ + delta_x;
         py_ = py_ + delta_y;
-        bool touched;  // a particle boundary condition looked at this particle (it is outside the local domain)
-        {
+        {  // touched: a particle boundary condition looked at this particle (it is outside the local domain)
           double pos[3] = {px_ + P.grid_min_local[0], py_ + P.grid_min_local[1], 0.0};
           double mom[3] = {P.part_mc * part_ux, P.part_mc * part_uy, P.part_mc * part_uz};
           touched = (pos[0] < P.bnd_min[0]) || (pos[0] > P.bnd_max[0]) || (pos[1] < P.bnd_min[1]) || (pos[1] > P.bnd_max[1]);
@@ -1507,10 +1567,23 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
         const double cxr = px_ * P.idx[0], cyr = py_ * P.idx[1];
         const int cx3 = __double2int_rd(cxr + 0.5), cy3 = __double2int_rd(cyr + 0.5);
         {
-          const int kx = cx3 < 0 ? 0 : (cx3 > P.n[0] - 1 ? P.n[0] - 1 : cx3);
-          const int ky = cy3 < 0 ? 0 : (cy3 > P.n[1] - 1 ? P.n[1] - 1 : cy3);
-          const bool stays = !touched && (kx + 1 == hcx) && (ky + 1 == hcy);
+          // (a particle predicted to gather in the first ghost cell belongs to the edge column: the clamp is
+          // only paid by the particles that are about to move)
+          const bool stays = !touched && (cx3 + 1 == hcx) && (cy3 + 1 == hcy);
           disp = (dir == 13) ? 3 : (stays ? 0 : 1);
+          if (disp == 1 && dir < 0 && !touched) {
+            nkx = cx3 < 0 ? 0 : (cx3 > P.n[0] - 1 ? P.n[0] - 1 : cx3);
+            nky = cy3 < 0 ? 0 : (cy3 > P.n[1] - 1 ? P.n[1] - 1 : cy3);
+            if (nkx + 1 == hcx && nky + 1 == hcy) {
+              disp = 0;   // edge column after all
+            } else if (P.ic_out) {
+              // reserve the entry in the destination group's inbox NOW; the reply is only looked at after the
+              // deposit arithmetic below, so the round trip of the atomic is hidden
+              const int nkey = ((nky / T2Y) * P.tg.nt[0] + (nkx >> 4)) * (T2X * T2Y) + (nky % T2Y) * T2X + (nkx & 15);
+              nkx = nkey;
+              ib_slot = atomicAdd(&P.ic_out[nkey >> 5], 1);
+            }
+          }
         }
         if (P.deposit) {
           const double fxn = (double)cx3 - cxr, fyn = (double)cy3 - cyr;
@@ -1532,12 +1605,12 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
             // New weights on the 3x3 core (particles.F90:521-538 with the shift by dcell); the
             // part of a moved particle's stencil outside the core is queued (drain_edge).
             double wm, w0, wp;
-            tri(fxn, wm, w0, wp);
+            tri_s(fxn, wm, w0, wp);
             hx[0] = (dcx == 0 ? wm : dcx > 0 ? 0.0 : w0) - gx[0];
             hx[1] = (dcx == 0 ? w0 : dcx > 0 ? wm : wp) - gx[1];
             hx[2] = (dcx == 0 ? wp : dcx > 0 ? w0 : 0.0) - gx[2];
             const double hxa = hx[0] + (dcx < 0 ? wm : 0.0);  // running jx prefix enters the core with column -2
-            tri(fyn, wm, w0, wp);
+            tri_s(fyn, wm, w0, wp);
             hy[0] = (dcy == 0 ? wm : dcy > 0 ? 0.0 : w0) - gy[0];
             hy[1] = (dcy == 0 ? w0 : dcy > 0 ? wm : wp) - gy[1];
             hy[2] = (dcy == 0 ? wp : dcy > 0 ? w0 : 0.0) - gy[2];
@@ -1565,22 +1638,43 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
             for (int ix = 0; ix < 3; ix++) {
               const double zg = fjz * gx[ix], zh = fjz * hx[ix];
 #pragma unroll
-              for (int iy = 0; iy < 3; iy++) AZ[iy][ix] += zg * yfac1[iy] + zh * yfac2[iy];
+              for (int iy = 0; iy < 3; iy++) {
+#ifdef EPB_FAST_MATH
+                AZ[iy][ix] = fma(zh, yfac2[iy], fma(zg, yfac1[iy], AZ[iy][ix]));   // two FMAs instead of mul + FMA + add
+#else
+                AZ[iy][ix] += zg * yfac1[iy] + zh * yfac2[iy];
+#endif
+              }
             }
             if ((dcx | dcy) != 0) { extras = true; key |= 1 << 14; }
           }
         }
       }
     }
-    // ---- particles that leave this column: one warp-aggregated reservation in the mover buffer ----
+    // ---- particles that leave this column -----------------------------------------------------------
+    // a mover whose next column is known goes straight into that column's group inbox: one 64-byte entry
+    // (two full sectors, no read-modify-write), consumed by the next push
+    bool toM = (disp == 2) || (disp == 1 && (dir >= 0 || touched));
+    if (disp == 1 && !toM) {
+      if (ib_slot >= 0 && ib_slot < P.IC) {
+        const int nkey = nkx;
+        double2 *e = reinterpret_cast<double2 *>(P.ib_out + ((size_t)(nkey >> 5) * (size_t)P.IC + ib_slot) * 8);
+        e[0] = make_double2(o_x, o_y);
+        e[1] = make_double2(o_px, o_py);
+        e[2] = make_double2(o_pz, part_weight);
+        e[3] = make_double2(__longlong_as_double((long long)(nkey & 31)), 0.0);
+      } else {
+        toM = true;   // inbox full (or switched off): through the mover buffer, k_deliver finds the column
+      }
+    }
+    if (active && disp == 0 && wcur >= P.R) toM = true;   // no row left in this column: on through M (flag 0)
     {
-      const bool mv = (disp == 1) || (disp == 2);
-      const unsigned bal = __ballot_sync(FULL, mv);
+      const unsigned bal = __ballot_sync(FULL, toM);
       if (bal) {
         int base = 0;
         if (lane == __ffs(bal) - 1) base = atomicAdd(P.mcount, __popc(bal));
         base = __shfl_sync(FULL, base, __ffs(bal) - 1);
-        if (mv) {
+        if (toM) {
           const int m = base + __popc(bal & lt_mask);
           if (m < P.mcap) {
             P.mx[0][m] = o_x; P.mx[1][m] = o_y;
@@ -1591,10 +1685,12 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
               const int slot = atomicAdd(&P.out_count[dir], 1);
               if (slot < P.out_cap) P.out_idx[(size_t)dir * P.out_cap + slot] = m;
             }
-          } else if (disp == 1 && dir < 0) {
+            if (disp == 0) disp = 1;   // left through M after all
+          } else if (disp == 1 && dir < 0 && wcur < P.R) {
             disp = 0;  // no room in M: the particle stays in this column and is deposited the general way next step
           } else {
-            atomicOr(P.err, 1);  // a leaver or an unpushed particle cannot stay: reported as a capacity error
+            atomicOr(P.err, 1);  // a leaver, an unpushed particle or a full column cannot keep it: capacity error
+            disp = 3;
           }
         }
       }
@@ -1606,7 +1702,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
       P.p[0][ow] = o_px;
       P.p[1][ow] = o_py;
       P.p[2][ow] = o_pz;
-      if (wcur != r) P.w[ow] = part_weight;
+      if (wcur != r || r >= my_cnt) P.w[ow] = part_weight;
       wcur++;
     }
     if (!P.deposit) continue;
@@ -1634,9 +1730,9 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
     __syncwarp();
     drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
   }
-  if (my_cnt > 0) P.cnt[my_key] = wcur;
+  if (my_tot > 0) P.cnt[my_key] = wcur;
   // ---- flush this lane's cell sums: prefixes of particles.F90:563-571, one update per point ----
-  if (P.deposit && my_cnt > 0) {
+  if (P.deposit && my_tot > 0) {
     const int hb = (hcy - oy) * TW + (hcx - ox);
 #pragma unroll
     for (int iy = 0; iy < 3; iy++) {

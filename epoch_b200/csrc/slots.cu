@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "epb_internal.h"
@@ -97,6 +98,51 @@ __global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ Deliver
         D.oflag[m] = 2;
       } else {
         atomicOr(D.err, 1);
+      }
+    }
+  }
+}
+
+struct SettleOp {
+  const double *ib;
+  const int *ic;
+  int IC, ngroups;
+  double *ax[3], *ap[3], *aw;
+  int *cnt;
+  int R;
+  double *ox[3], *op[3], *ow;
+  unsigned char *oflag;
+  int *ocount;
+  int ocap;
+  int *err;
+};
+__global__ void __launch_bounds__(256) k_settle(const __grid_constant__ SettleOp O) {
+  // one warp per group inbox
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < O.ngroups; g += warps) {
+    int n = O.ic[g];
+    if (n > O.IC) n = O.IC;
+    for (int j = lane; j < n; j += 32) {
+      const double *e = O.ib + ((size_t)g * O.IC + j) * 8;
+      const int key = g * 32 + ((int)__double_as_longlong(e[6]) & 31);
+      const int r = atomicAdd(&O.cnt[key], 1);
+      if (r < O.R) {
+        const size_t o = ((size_t)g * O.R + r) * 32 + (key & 31);
+        O.ax[0][o] = e[0]; O.ax[1][o] = e[1];
+        O.ap[0][o] = e[2]; O.ap[1][o] = e[3]; O.ap[2][o] = e[4];
+        O.aw[o] = e[5];
+      } else {
+        atomicSub(&O.cnt[key], 1);
+        const int m = atomicAdd(O.ocount, 1);
+        if (m < O.ocap) {
+          O.ox[0][m] = e[0]; O.ox[1][m] = e[1];
+          O.op[0][m] = e[2]; O.op[1][m] = e[3]; O.op[2][m] = e[4];
+          O.ow[m] = e[5];
+          O.oflag[m] = 2;
+        } else {
+          atomicOr(O.err, 1);
+        }
       }
     }
   }
@@ -187,6 +233,17 @@ int epb_slots_alloc(epb_handle *h, int is) {
     EPB_CUDA(h, cudaMalloc(&h->d_err, sizeof(int)));
     EPB_CUDA(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
   }
+  // group inboxes (EPB_SLOTS_INBOX=0 sends every mover through the mover buffer and k_deliver instead)
+  static const int use_inbox = getenv("EPB_SLOTS_INBOX") ? atoi(getenv("EPB_SLOTS_INBOX")) : 1;
+  if (use_inbox) {
+    const size_t ngroups = (size_t)h->tg.nkeys / 32;
+    S.IC = 192;
+    for (int b = 0; b < 2; b++) {
+      EPB_CUDA(h, cudaMalloc(&S.inbox[b], ngroups * (size_t)S.IC * 8 * sizeof(double)));
+      EPB_CUDA(h, cudaMalloc(&S.icnt[b], (ngroups + 1) * sizeof(int)));
+      EPB_CUDA(h, cudaMemsetAsync(S.icnt[b], 0, (ngroups + 1) * sizeof(int), h->stream));
+    }
+  }
   return EPB_OK;
 }
 
@@ -197,6 +254,7 @@ void epb_slots_free(SpeciesDev &S) {
   }
   cudaFree(S.mcount);
   cudaFree(S.cnt);
+  for (int b = 0; b < 2; b++) { cudaFree(S.inbox[b]); cudaFree(S.icnt[b]); }
 }
 
 // Empty the species and make sure the arena fits what is about to be loaded: rows per column R from the
@@ -247,6 +305,11 @@ int epb_slots_reset(epb_handle *h, int is, long long n_expected, int max_ppc_hin
   S.mcur = 0;
   EPB_CUDA(h, cudaMemsetAsync(S.cnt, 0, ((size_t)nkeys + 1) * sizeof(int), h->stream));
   EPB_CUDA(h, cudaMemsetAsync(S.mcount, 0, 2 * sizeof(int), h->stream));
+  if (S.icnt[0]) {
+    for (int b = 0; b < 2; b++) EPB_CUDA(h, cudaMemsetAsync(S.icnt[b], 0, ((size_t)nkeys / 32 + 1) * sizeof(int), h->stream));
+    S.icur = 0;
+    S.inbox_dirty = false;
+  }
   S.n = 0;
   S.n_sorted = 0;
   return EPB_OK;
@@ -315,6 +378,7 @@ int epb_species_views(epb_handle *h, int is, SlotView V[2]) {
   SpeciesDev &S = h->sp[is];
   if (S.slots) {
     if (!S.arena_ready) return 0;
+    epb_slots_settle(h, is);
     epb_slots_views(h, is, V);
     return 2;
   }
@@ -335,6 +399,51 @@ void epb_slots_fill_push(epb_handle *h, int is, PushParams &P) {
   P.mcount = S.mcount + S.mcur;
   P.mcap = (int)S.mcap;
   P.err = h->d_err;
+  P.ib_in = S.inbox[S.icur];
+  P.ic_in = S.icnt[S.icur];
+  P.ib_out = S.inbox[S.icur ^ 1];
+  P.ic_out = S.icnt[S.icur ^ 1];
+  P.IC = S.IC;
+}
+
+int epb_slots_after_push(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  if (!S.icnt[0]) return EPB_OK;
+  EPB_CUDA(h, cudaMemsetAsync(S.icnt[S.icur], 0, ((size_t)h->tg.nkeys / 32 + 1) * sizeof(int), h->stream));
+  S.icur ^= 1;
+  S.inbox_dirty = true;
+  return EPB_OK;
+}
+
+// Group inboxes -> columns: what the next push would do on the fly, done now because something else (a
+// diagnostic, a download, the balancer) is about to walk the species.  An entry that finds its column full waits in
+// the current mover buffer like any other (flag 2).
+int epb_slots_settle(epb_handle *h, int is) {
+  SpeciesDev &S = h->sp[is];
+  if (!S.slots || !S.icnt[0] || !S.inbox_dirty) return EPB_OK;
+  SettleOp O;
+  memset(&O, 0, sizeof O);
+  for (int d = 0; d < 3; d++) {
+    O.ax[d] = S.buf[0][d]; O.ap[d] = S.buf[0][3 + d];
+    O.ox[d] = S.mbuf[S.mcur][d]; O.op[d] = S.mbuf[S.mcur][3 + d];
+  }
+  O.aw = S.buf[0][6]; O.ow = S.mbuf[S.mcur][6];
+  O.oflag = S.mflag[S.mcur];
+  O.ocount = S.mcount + S.mcur;
+  O.ocap = (int)S.mcap;
+  O.cnt = S.cnt;
+  O.R = S.R;
+  O.err = h->d_err;
+  O.ib = S.inbox[S.icur];
+  O.ic = S.icnt[S.icur];
+  O.IC = S.IC;
+  O.ngroups = h->tg.nkeys / 32;
+  k_settle<<<nblk((size_t)O.ngroups * 32, 148 * 8), 256, 0, h->stream>>>(O);
+  h->launches++;
+  EPB_CUDA(h, cudaMemsetAsync(S.icnt[S.icur], 0, ((size_t)O.ngroups + 1) * sizeof(int), h->stream));
+  S.inbox_dirty = false;
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
 }
 
 int epb_slots_check(epb_handle *h) {
@@ -364,13 +473,20 @@ int epb_slots_count(epb_handle *h, int is, long long *n) {
   }
   cub::DeviceReduce::Sum(h->cub_tmp, need, tmp, d_out, nkeys, h->stream);
   h->launches += 2;
-  long long arena = 0;
+  long long arena = 0, inbox = 0;
   int mc[2] = {0, 0};
   EPB_CUDA(h, cudaMemcpyAsync(&arena, d_out, sizeof arena, cudaMemcpyDeviceToHost, h->stream));
+  if (S.icnt[0] && S.inbox_dirty) {   // particles on their way between two columns
+    const int ng = nkeys / 32;
+    k_clamp_counts<<<nblk((size_t)ng), 256, 0, h->stream>>>(S.icnt[S.icur], tmp, ng, S.IC);
+    cub::DeviceReduce::Sum(h->cub_tmp, need, tmp, d_out + 1, ng, h->stream);
+    h->launches += 2;
+    EPB_CUDA(h, cudaMemcpyAsync(&inbox, d_out + 1, sizeof inbox, cudaMemcpyDeviceToHost, h->stream));
+  }
   EPB_CUDA(h, cudaMemcpyAsync(mc, S.mcount, sizeof mc, cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   long long waiting = std::min<long long>(mc[S.mcur], S.mcap);   // between steps: flag-2 entries only
-  *n = arena + waiting;
+  *n = arena + waiting + inbox;
   return epb_slots_check(h);
 }
 
@@ -447,6 +563,10 @@ int epb_species_iter_begin(epb_handle *h, int is, SpeciesIter &I) {
   I = SpeciesIter();
   if (!S.slots) return EPB_OK;
   if (!S.arena_ready) return EPB_OK;
+  {
+    int rcs = epb_slots_settle(h, is);
+    if (rcs) return rcs;
+  }
   const int nkeys = h->tg.nkeys;
   // scan of the clamped counts -> start[nkeys + 1]
   int *tmpc = h->cell_count, *start = h->cell_start;
