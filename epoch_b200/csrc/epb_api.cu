@@ -389,10 +389,11 @@ __global__ void __launch_bounds__(256) k_cell_counts(const __grid_constant__ Cou
   const long long nn = prange_n(C.r);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
     if (!prange_valid(C.r, i)) continue;
+    const long long e = prange_at(C.r, i);
     int cell[3] = {1, 1, 1};
     bool ok = true;
     for (int d = 0; d < C.nd; d++) {
-      cell[d] = __double2int_rd((C.x[d][i] - C.gmin[d]) / C.dx[d] + 0.5) + 1;
+      cell[d] = __double2int_rd((C.x[d][e] - C.gmin[d]) / C.dx[d] + 0.5) + 1;
       if (cell[d] < 1 || cell[d] > C.nloc[d]) ok = false;
     }
     if (ok) atomicAdd(&C.out[(size_t)(cell[0] - 1) + (size_t)C.nloc[0] * ((size_t)(cell[1] - 1) + (size_t)C.nloc[1] * (cell[2] - 1))], 1);
@@ -419,11 +420,12 @@ __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp
   const long long nn = prange_n(M.r);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
     if (!prange_valid(M.r, i)) continue;
+    const long long e = prange_at(M.r, i);
     int cell[3] = {1, 1, 1};
     double g[3][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
     bool ok = true;
     for (int d = 0; d < M.nd; d++) {
-      const double cell_r = (M.x[d][i] - M.gmin[d]) / M.dx[d];
+      const double cell_r = (M.x[d][e] - M.gmin[d]) / M.dx[d];
       const int cx = __double2int_rd(cell_r + 0.5);
       const double cf = (double)cx - cell_r;
       cell[d] = cx + 1;
@@ -434,9 +436,9 @@ __global__ void __launch_bounds__(256) k_moment(const __grid_constant__ MomentOp
       if (cell[d] - 1 < 1 - NG || cell[d] + 1 > M.sz[d] - NG) ok = false;  // outside the allocated extent
     }
     if (!ok) continue;
-    double wdata = M.use_scale ? M.scale * M.w[i] : M.w[i];
+    double wdata = M.use_scale ? M.scale * M.w[e] : M.w[e];
     if (M.use_scale == 2) {
-      const double part_px = M.p[0][i], part_py = M.p[1][i], part_pz = M.p[2][i];
+      const double part_px = M.p[0][e], part_py = M.p[1][e], part_pz = M.p[2][e];
       const double root = 1.0 / sqrt(M.part_mc * M.part_mc + part_px * part_px + part_py * part_py + part_pz * part_pz);
       wdata = wdata * (M.dir == 0 ? part_px : M.dir == 1 ? part_py : part_pz) * root;
     }
@@ -475,11 +477,12 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
   const long long nn = prange_n(M.r);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
     if (!prange_valid(M.r, i)) continue;
+    const long long e = prange_at(M.r, i);
     int cell[3] = {1, 1, 1};
     double g[3][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
     bool ok = true;
     for (int d = 0; d < M.nd; d++) {
-      const double cell_r = (M.x[d][i] - M.gmin[d]) / M.dx[d];
+      const double cell_r = (M.x[d][e] - M.gmin[d]) / M.dx[d];
       const int cx = __double2int_rd(cell_r + 0.5);
       const double cf = (double)cx - cell_r;
       cell[d] = cx + 1;
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
       if (cell[d] - 1 < 1 - NG || cell[d] + 1 > M.sz[d] - NG) ok = false;
     }
     if (!ok) continue;
-    const double part_w = M.w[i];
+    const double part_w = M.w[e];
     double wdata = 0.0, pm[3] = {0.0, 0.0, 0.0};
     if (M.mode == 6) {  // calc_average_weight (:811-873): nearest cell only
       const size_t o = fofs(M.sz, M.nd, cell[0], cell[1], cell[2]);
@@ -499,10 +502,10 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
       continue;
     }
     if (M.mode == 3 && M.sub >= 7) {
-      wdata = part_w * M.p[M.sub - 7][i];
+      wdata = part_w * M.p[M.sub - 7][e];
     } else if (M.mode == 3) {
       const double fac = M.part_mc * part_w * c;
-      const double part_ux = M.p[0][i] / M.part_mc, part_uy = M.p[1][i] / M.part_mc, part_uz = M.p[2][i] / M.part_mc;
+      const double part_ux = M.p[0][e] / M.part_mc, part_uy = M.p[1][e] / M.part_mc, part_uz = M.p[2][e] / M.part_mc;
       const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
       const double gamma_rel = sqrt(part_u2 + 1.0);
       const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
         else wdata = wdata * fmax(part_flux, 0.0);
       }
     } else {
-      for (int q = 0; q < 3; q++) pm[q] = M.p[q][i] / M.sqrt_part_m;
+      for (int q = 0; q < 3; q++) pm[q] = M.p[q][e] / M.sqrt_part_m;
     }
     const int z0 = M.nd >= 3 ? -1 : 0, z1 = M.nd >= 3 ? 1 : 0;
     const int y0 = M.nd >= 2 ? -1 : 0, y1 = M.nd >= 2 ? 1 : 0;
@@ -692,10 +695,11 @@ __global__ void __launch_bounds__(256) k_kinetic_energy(const double *px, const 
   const long long n = prange_n(R);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (!prange_valid(R, i)) continue;
-    const double ux = px[i] / mc, uy = py[i] / mc, uz = pz[i] / mc;
+    const long long e = prange_at(R, i);
+    const double ux = px[e] / mc, uy = py[e] / mc, uz = pz[e] / mc;
     const double u2 = ux * ux + uy * uy + uz * uz;
     const double gamma = sqrt(u2 + 1.0);
-    s += w[i] * (u2 / (gamma + 1.0)) * mc2;  // (gamma-1) m c^2 without cancellation
+    s += w[e] * (u2 / (gamma + 1.0)) * mc2;  // (gamma-1) m c^2 without cancellation
   }
   for (int q = 16; q >= 1; q >>= 1) s += __shfl_xor_sync(0xffffffffu, s, q);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
@@ -1346,9 +1350,10 @@ int epb_destroy(epb_handle *h) {
   cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
+    // slot columns first: their buf[0][*] point INTO the arena and are cleared by epb_slots_free
+    if (S.slots) epb_slots_free(S);
     for (int b = 0; b < 2; b++)
       for (int q = 0; q < 7; q++) cudaFree(S.buf[b][q]);
-    if (S.slots) epb_slots_free(S);
     cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.cell_start); cudaFree(S.rank); cudaFree(S.perm); cudaFree(S.stay_cnt); cudaFree(S.arr_cnt); cudaFree(S.gone);
   }
   if (h->h_counts) cudaFreeHost(h->h_counts);

@@ -30,9 +30,10 @@ struct TileGeom {
 };
 
 // Layout 2 ("slot columns", 2D): the particles of cell key k = group * 32 + lane live in rows 0 .. cnt[k]-1 of
-// column k; row r of a group's 32 columns is 32 consecutive, 256-byte aligned doubles per array
-// (slot = (group * R + r) * 32 + lane), so a round of the owning warp is one aligned, coalesced access and a
-// particle that stays in its cell is never moved by anything but its own lane.  Particles that change cell
+// column k; row r of a group's 32 columns is one ROW BLOCK of NC x 32 doubles -- x[32] y[32] px[32] py[32] pz[32]
+// w[32], 256-byte aligned each -- at block index group * R + r of ONE allocation, so a round of the owning warp is
+// NC aligned, coalesced accesses off a single pointer with immediate offsets, and a particle that stays in its
+// cell is never moved by anything but its own lane.  (S.buf[0][q] point at component q of block 0.)  Particles that change cell
 // ("movers"), leave the rank, or whose stencil leaves the tile go through the mover buffer M (SoA + a flag
 // byte per entry) and are inserted into their next column by k_deliver; what does not fit its column (or M)
 // waits in the other M buffer and is pushed by the generic kernel.
@@ -46,7 +47,12 @@ struct PRange {
   int R;
   const int *n_dev;
   const unsigned char *flag;
+  int K;                   // arena: components per row block (the arrays are interleaved row by row, see below); else 0
 };
+// element offset of slot i inside a component array of the range (arena: row blocks of K x 32 doubles)
+__device__ __forceinline__ long long prange_at(const PRange &V, long long i) {
+  return V.K ? (((i >> 5) * V.K) << 5) + (i & 31) : i;
+}
 __device__ __forceinline__ long long prange_n(const PRange &V) {
   if (V.cnt || !V.n_dev) return V.n;
   const long long n = (long long)*V.n_dev;
@@ -163,6 +169,7 @@ struct SpeciesDev {
   int *mcount = nullptr;      // device [2]
   int mcur = 0;
   long long mcap = 0;
+  double *arena = nullptr;    // the one allocation behind buf[0][*]
   bool arena_ready = false;   // R chosen and the arena allocated (at the first upload / load, when the density is known)
   double *inbox[2] = {nullptr, nullptr};   // [ngroups][IC][8] group inboxes (see PushParams), ping-pong
   int *icnt[2] = {nullptr, nullptr};       // [ngroups] entries per inbox (may run past IC: readers clamp)

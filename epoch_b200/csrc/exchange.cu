@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_load_profile(const double *x, const __g
   const long long n = prange_n(R);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (!prange_valid(R, i)) continue;
-    const int cell = __double2int_rd((x[i] - grid_min) / dx + 1.5) + NG;   // index into load(1:len)
+    const int cell = __double2int_rd((x[prange_at(R, i)] - grid_min) / dx + 1.5) + NG;   // index into load(1:len)
     if (cell >= 1 && cell <= len) atomicAdd(load + (cell - 1), 1ULL);
   }
 }

@@ -1429,7 +1429,10 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   const int hcx = ttx * T2X + (lane & 15) + 1;
   const int hcy = tty * T2Y + warp * 2 + (lane >> 4) + 1;
   const int maxcnt = __reduce_max_sync(FULL, my_tot);
-  const size_t gbase = ((size_t)(my_key >> 5) * (size_t)P.R) * 32 + lane;  // slot of row 0 of this lane's column
+  // row 0 of this lane's column: rows are blocks of 6 x 32 doubles (x y px py pz w), so every access below is
+  // this pointer + row * ROWD + an immediate component offset
+  constexpr int ROWD = 6 * 32, OX = 0, OY = 32, OPX = 64, OPY = 96, OPZ = 128, OW = 160;
+  double *const col = P.x[0] + ((size_t)(my_key >> 5) * (size_t)P.R) * ROWD + lane;
   int wcur = 0;  // write cursor: rows 0 .. wcur-1 hold the particles that stay in this column
 
   // raw deposit sums of this lane's cell: AX[iy][ix<2], AY[iy<2][ix], AZ[iy][ix]
@@ -1449,9 +1452,9 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
   auto fetch = [&](int rn) {
     if (rn < my_cnt) {
-      const size_t sl = gbase + (size_t)rn * 32;
-      n_w = P.w[sl]; n_x = P.x[0][sl]; n_y = P.x[1][sl];
-      n_px = P.p[0][sl]; n_py = P.p[1][sl]; n_pz = P.p[2][sl];
+      const double *row = col + (size_t)rn * ROWD;
+      n_w = row[OW]; n_x = row[OX]; n_y = row[OY];
+      n_px = row[OPX]; n_py = row[OPY]; n_pz = row[OPZ];
     } else if (rn < my_tot) {
       const double2 *e = reinterpret_cast<const double2 *>(ibg + (size_t)sAlist[lane * SLOT_LK + (rn - my_cnt)] * 8);
       const double2 v0 = e[0], v1 = e[1], v2 = e[2];
@@ -1696,13 +1699,13 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
       }
     }
     if (active && disp == 0) {
-      const size_t ow = gbase + (size_t)wcur * 32;
-      P.x[0][ow] = o_x;
-      P.x[1][ow] = o_y;
-      P.p[0][ow] = o_px;
-      P.p[1][ow] = o_py;
-      P.p[2][ow] = o_pz;
-      if (wcur != r || r >= my_cnt) P.w[ow] = part_weight;
+      double *row = col + (size_t)wcur * ROWD;
+      row[OX] = o_x;
+      row[OY] = o_y;
+      row[OPX] = o_px;
+      row[OPY] = o_py;
+      row[OPZ] = o_pz;
+      if (wcur != r || r >= my_cnt) row[OW] = part_weight;
       wcur++;
     }
     if (!P.deposit) continue;

@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int NG = EPB_NG;
+constexpr int SLOT_NC = 6;   // components of a 2D particle: x, y, px, py, pz, w (layout 2 is 2D only)
 
 inline int nblk(size_t n, int cap = 148 * 16) {
   size_t b = (n + 255) / 256;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ Deliver
     const int key = predicted_key(D, x, y, px, py, pz);
     const int r = atomicAdd(&D.cnt[key], 1);
     if (r < D.R) {
-      const size_t o = ((size_t)(key >> 5) * D.R + r) * 32 + (key & 31);
+      const size_t o = ((size_t)(key >> 5) * D.R + r) * (32 * SLOT_NC) + (key & 31);
       D.ax[0][o] = x; D.ax[1][o] = y;
       D.ap[0][o] = px; D.ap[1][o] = py; D.ap[2][o] = pz;
       D.aw[o] = w;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_settle(const __grid_constant__ SettleOp
       const int key = g * 32 + ((int)__double_as_longlong(e[6]) & 31);
       const int r = atomicAdd(&O.cnt[key], 1);
       if (r < O.R) {
-        const size_t o = ((size_t)g * O.R + r) * 32 + (key & 31);
+        const size_t o = ((size_t)g * O.R + r) * (32 * SLOT_NC) + (key & 31);
         O.ax[0][o] = e[0]; O.ax[1][o] = e[1];
         O.ap[0][o] = e[2]; O.ap[1][o] = e[3]; O.ap[2][o] = e[4];
         O.aw[o] = e[5];
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
     const int mx = __reduce_max_sync(0xffffffffu, c);
     for (int r = 0; r < mx; r++) {
       if (r < c) {
-        const size_t o = ((size_t)g * C.R + r) * 32 + lane;
+        const size_t o = ((size_t)g * C.R + r) * (32 * SLOT_NC) + lane;
 #pragma unroll
         for (int q = 0; q < 7; q++)
           if (C.a[q]) C.dst[q][st + r] = C.a[q][o];
@@ -254,6 +254,8 @@ void epb_slots_free(SpeciesDev &S) {
   }
   cudaFree(S.mcount);
   cudaFree(S.cnt);
+  cudaFree(S.arena);
+  for (int q = 0; q < 7; q++) S.buf[0][q] = nullptr;   // they pointed into the arena
   for (int b = 0; b < 2; b++) { cudaFree(S.inbox[b]); cudaFree(S.icnt[b]); }
 }
 
@@ -264,13 +266,19 @@ static int slots_set_rows(epb_handle *h, int is, long long R) {
   SpeciesDev &S = h->sp[is];
   const int nd = h->cfg.ndims;
   const long long nkeys = h->tg.nkeys;
-  if ((size_t)R * (size_t)nkeys >= ((size_t)1 << 36)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
+  if ((size_t)R * (size_t)nkeys * SLOT_NC >= ((size_t)1 << 38)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  for (int q = 0; q < 7; q++) {
-    if (q < 3 && q >= nd) continue;
-    cudaFree(S.buf[0][q]);
-    S.buf[0][q] = nullptr;
-    EPB_CUDA(h, cudaMalloc(&S.buf[0][q], (size_t)R * nkeys * sizeof(double)));
+  // one allocation of nkeys / 32 * R row blocks of NC x 32 doubles; buf[0][q] = component q of block 0
+  cudaFree(S.arena);
+  S.arena = nullptr;
+  for (int q = 0; q < 7; q++) S.buf[0][q] = nullptr;
+  EPB_CUDA(h, cudaMalloc(&S.arena, (size_t)R * nkeys * SLOT_NC * sizeof(double)));
+  {
+    int cq = 0;
+    for (int q = 0; q < 7; q++) {
+      if (q < 3 && q >= nd) continue;
+      S.buf[0][q] = S.arena + (size_t)32 * cq++;
+    }
   }
   S.R = (int)R;
   S.arena_ready = true;
@@ -366,6 +374,7 @@ void epb_slots_views(epb_handle *h, int is, SlotView V[2]) {
   memset(V, 0, 2 * sizeof(SlotView));
   for (int q = 0; q < 7; q++) { V[0].a[q] = S.buf[0][q]; V[1].a[q] = S.mbuf[S.mcur][q]; }
   V[0].r.cnt = S.cnt;
+  V[0].r.K = SLOT_NC;
   V[0].r.R = S.R;
   V[0].r.n = S.arena_ready ? (long long)h->tg.nkeys * S.R : 0;
   V[1].r.n_dev = S.mcount + S.mcur;
@@ -464,8 +473,8 @@ int epb_slots_count(epb_handle *h, int is, long long *n) {
   long long *d_out = (long long *)(h->d_scratch + 512);
   int *tmp = h->cell_count;   // [nkeys + 1] scratch: clamped counts
   k_clamp_counts<<<nblk((size_t)nkeys), 256, 0, h->stream>>>(S.cnt, tmp, nkeys, S.R);
-  cub::DeviceReduce::Sum(nullptr, need, tmp, d_out, nkeys, h->stream);
-  if (need > h->cub_tmp_bytes) {
+  EPB_CUDA(h, cub::DeviceReduce::Sum(nullptr, need, tmp, d_out, nkeys, h->stream));
+  if (need > h->cub_tmp_bytes || !h->cub_tmp) {
     EPB_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(h->cub_tmp);
     EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
@@ -573,8 +582,8 @@ int epb_species_iter_begin(epb_handle *h, int is, SpeciesIter &I) {
   k_clamp_counts<<<nblk((size_t)nkeys), 256, 0, h->stream>>>(S.cnt, tmpc, nkeys, S.R);
   EPB_CUDA(h, cudaMemsetAsync(tmpc + nkeys, 0, sizeof(int), h->stream));
   size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, tmpc, start, nkeys + 1, h->stream);
-  if (need > h->cub_tmp_bytes) {
+  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, need, tmpc, start, nkeys + 1, h->stream));
+  if (need > h->cub_tmp_bytes || !h->cub_tmp) {
     EPB_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(h->cub_tmp);
     EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));

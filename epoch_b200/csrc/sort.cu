@@ -287,8 +287,8 @@ int epb_sort_species_emitted(epb_handle *h, int is) {
   k_add_counts<<<148 * 8, 256, 0, h->stream>>>(S.stay_cnt, S.arr_cnt, h->cell_count, nkeys + 1);
   h->launches++;
   size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, S.cell_start, nkeys + 1, h->stream);
-  if (need > h->cub_tmp_bytes) {
+  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, S.cell_start, nkeys + 1, h->stream));
+  if (need > h->cub_tmp_bytes || !h->cub_tmp) {
     cudaFree(h->cub_tmp);
     EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
     h->cub_tmp_bytes = need;
@@ -362,8 +362,10 @@ int epb_sort_species(epb_handle *h, int is) {
   }
   int *cstart = (h->tg.layout == 1 && S.cell_start) ? S.cell_start : h->cell_start;
   size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, cstart, nkeys + 1, h->stream);
-  if (need > h->cub_tmp_bytes) {
+  // (checked: a stale error picked up by the size query would leave need = 0 and turn the real call below
+  // into a second size query -- the scan would silently not run)
+  EPB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, need, h->cell_count, cstart, nkeys + 1, h->stream));
+  if (need > h->cub_tmp_bytes || !h->cub_tmp) {
     cudaFree(h->cub_tmp);
     EPB_CUDA(h, cudaMalloc(&h->cub_tmp, need));
     h->cub_tmp_bytes = need;
