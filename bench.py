@@ -183,7 +183,7 @@ def c3_deck(n_local, ppc, nproc):
     las = D.Laser("x_min", D.Laser.amp_from_intensity_w_cm2(1.0e19), omega,
                   profile=lambda y, z: D.gauss(y, 0, 0.25 * L[1]),
                   t_profile=lambda t: D.gauss(t, 30 * D.femto, 12 * D.femto) if t < 30 * D.femto else 1.0)
-    box_lo, box_hi = (0.4 * L[0], -1e300, -1e300), (0.6 * L[0], 1e300, 1e300)
+    box_lo, box_hi = (0.55 * L[0], -1e300, -1e300), (0.75 * L[0], 1e300, 1e300)
     bcp = ["open", "open", "periodic", "periodic"]
     sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=ppc, density=10 * ncrit, temp=(1.0e6,) * 3,
                     box_lo=box_lo, box_hi=box_hi, bc_particle=bcp),
@@ -206,7 +206,7 @@ def run_c3(args, world, rank, local_rank, parity, torch, dist):
     cap = int(1.6 * ncell_foil * args.ppc / world) + (1 << 20)       # per species; every rank can take an equal share
     n_loc, g_loc = dk.local_extent(rank)
     # before the re-cut the two middle x slabs hold everything
-    frac = max(0.0, min(0.6 * dk.n[0], g_loc[0] - 1 + n_loc[0]) - max(0.4 * dk.n[0], g_loc[0] - 1)) / max(1, n_loc[0])
+    frac = max(0.0, min(0.75 * dk.n[0], g_loc[0] - 1 + n_loc[0]) - max(0.55 * dk.n[0], g_loc[0] - 1)) / max(1, n_loc[0])
     cap0 = max(cap, int(1.1 * frac * n_loc[0] * n_loc[1] * args.ppc) + (1 << 20))
     sim = Simulation(dk, rank=rank, strict_fp=bool(args.strict), sort_interval=args.sort_interval,
                      capacity_factor=cap0 / max(1.0, args.ppc * n_loc[0] * n_loc[1]), stream=stream.cuda_stream)
@@ -328,7 +328,7 @@ def run_c3(args, world, rank, local_rank, parity, torch, dist):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_b / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"epoch2d laser-solid: simple_laser on x_min (1e19 W/cm^2, 1 um), simple_outflow on x_max, "
-                                   f"y periodic, 10 n_crit e-/p+ foil in the middle fifth of x, {args.ppc} ppc per species, "
+                                   f"y periodic, 10 n_crit e-/p+ foil over x in [0.55, 0.75] of the box, {args.ppc} ppc per species, "
                                    f"{dk.n[0]}x{dk.n[1]} cells, pinned {nproc[0]}x{nproc[1]} decomposition (BASELINE C3)",
                        "decomposition": f"{nproc[0]}x{nproc[1]}", "strict_fp": int(args.strict), "particles_total": n_total,
                        "particles_end": n_end, "load_balancer": "calculate_breaks (balance.F90:1948) on epb_load_profile, "

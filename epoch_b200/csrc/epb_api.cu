@@ -1347,7 +1347,7 @@ int epb_destroy(epb_handle *h) {
   for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
-  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage);
+  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage); cudaFree(h->coll_work);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
     // slot columns first: their buf[0][*] point INTO the arena and are cleared by epb_slots_free
@@ -2145,6 +2145,24 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
   }
   return EPB_OK;
 }
+
+}  // extern "C"
+
+// calc_coll_ekbar (what = 0; collisions.F90:1487-1575, J) / calc_coll_temperature_ev (what = 1; :1367-1483, left in K)
+// of one species into a device array: the same grid quantities as calc_ekbar / calc_temperature, whose device
+// versions are reused (collide.cu turns the temperature into eV where it uses it)
+int epb_coll_moment_dev(epb_handle *h, int what, int ispecies, double *dst) {
+  int rc = what == 0 ? calc_ratio_dev(h, ispecies, 0) : calc_temperature_dev(h, ispecies, -1);
+  if (rc) return rc;
+  if (what == 0) {
+    rc = moment_zero_gradient(h, 9);
+    if (rc) return rc;
+  }
+  EPB_CUDA(h, cudaMemcpyAsync(dst, h->f(9), h->fsize * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return EPB_OK;
+}
+
+extern "C" {
 
 int epb_calc_moment(epb_handle *h, int kind, int ispecies, double *host) {
   if (!h || !host || kind < 0 || kind > EPB_MOMENT_POYNT_FLUX_Z || ispecies >= (int)h->sp.size()) return EPB_ERR_ARG;

@@ -206,6 +206,8 @@ struct epb_handle {
   int out_cap = 0;
   int *h_counts = nullptr;      // pinned [64]
   int *d_scratch = nullptr;     // device ints
+  double *coll_work = nullptr;  // collisions with coulomb_log_auto: ekbar of species 1, temperature of species 2 (2 x fsize)
+  long long coll_calls = 0;     // epb_collide calls so far (feeds the pair streams' seed)
   double *aos_stage = nullptr;  // 2 Mi particles in the pack_particle wire layout (upload / download staging)
   int *d_err = nullptr;         // device error word (layout 2), checked at the synchronising entry points
   int *movers = nullptr;        // exchange: tail survivors that fill holes (27*out_cap+1)

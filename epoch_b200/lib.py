@@ -22,7 +22,7 @@ SYMBOLS = (
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
     "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy",
-    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute",
+    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute", "epb_collide", "epb_collide_pairs_test",
 )
 
 
@@ -51,6 +51,12 @@ class SpeciesCfg(C.Structure):
 class Decomp(C.Structure):
     """struct epb_decomp: cell_x_min(1:nprocx) ... of a tensor-product decomposition (mpi_routines.F90:317-351)"""
     _fields_ = [("nproc", C.c_int32 * 3), ("cell_min", C.POINTER(C.c_int32) * 3), ("cell_max", C.POINTER(C.c_int32) * 3)]
+
+
+class Collisions(C.Structure):
+    """struct epb_collisions (the collisions block of the deck, deck/deck_collision_block.F90)"""
+    _fields_ = [("n_species", C.c_int32), ("coll_n_step", C.c_int32), ("use_nanbu", C.c_int32), ("reserved", C.c_int32),
+                ("coulomb_log", C.c_double), ("seed", C.c_uint64), ("coll_pairs", C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -111,6 +117,8 @@ def load():
     L.epb_field_energy.argtypes = [vp, dp]
     L.epb_kinetic_energy.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.epb_calc_moment.argtypes = [vp, i32, i32, dp]
+    L.epb_collide.argtypes = [vp, C.POINTER(Collisions)]
+    L.epb_collide_pairs_test.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
     L.epb_redistribute.argtypes = [vp, C.POINTER(Decomp), C.POINTER(Decomp), C.POINTER(Config), C.POINTER(SpeciesCfg),
                                    C.POINTER(vp)]
     L.epb_load_profile.argtypes = [vp, i32, dp]

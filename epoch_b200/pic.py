@@ -295,6 +295,19 @@ class Simulation:
     def sort(self): self._chk(self.L.epb_sort(self._h))
     def synchronize(self): self._chk(self.L.epb_synchronize(self._h))
 
+    def collide(self, coll_pairs, coulomb_log: float = 0.0, use_nanbu: bool = True, coll_n_step: int = 1,
+                seed: int = 7842432):
+        """particle_collisions (physics_packages/collisions.F90:86-214): coll_pairs[i][j] = user_factor of the species
+        pair (<= 0: no collisions); coulomb_log <= 0 means coulomb_log = auto.  PROGRAM pic calls it after
+        push_particles on collision steps (epoch2d.F90:219-236)."""
+        n = len(self.deck.species)
+        cp = np.ascontiguousarray(np.asarray(coll_pairs, dtype=np.float64).reshape(n, n))
+        c = _lib.Collisions()
+        c.n_species, c.coll_n_step, c.use_nanbu = n, int(coll_n_step), int(use_nanbu)
+        c.coulomb_log, c.seed = float(coulomb_log), int(seed)
+        c.coll_pairs = cp.ctypes.data_as(C.POINTER(C.c_double))
+        self._chk(self.L.epb_collide(self._h, C.byref(c)))
+
     def step(self):
         """One pass of the hot path with no boundary sources (uniform-plasma benchmark step)."""
         self.fields_half()

@@ -218,6 +218,28 @@ typedef struct epb_decomp {
 int epb_redistribute(epb_handle *old_h, const epb_decomp *old_d, const epb_decomp *new_d, const epb_config *new_cfg,
                      const epb_species *new_species, epb_handle **out);
 
+/* -- binary collisions ---------------------------------------------------------------------------------------
+ * particle_collisions (physics_packages/collisions.F90:86-214), called by PROGRAM pic after push_particles on the
+ * steps where MODULO(step, coll_n_step) == coll_n_step - 1 (epoch2d.F90:219-236).  The per-cell lists the reference
+ * builds with reorder_particles_to_grid are the device's own cell-resident layout, so nothing is re-sorted.
+ * coll_pairs(n_species, n_species): the deck's user_factor for every species pair (row-major, upper triangle read;
+ * <= 0: the pair does not collide).  coulomb_log > 0: fixed value; <= 0: coulomb_log_auto (calc_coulomb_log :1288).
+ * use_nanbu: 1 Nanbu / Perez (the reference's default), 0 Sentoku-Kemp.  The random numbers come from counter-based
+ * per-pair streams derived from seed (the reference's single KISS stream is inherently serial). */
+typedef struct epb_collisions {
+  int32_t n_species;
+  int32_t coll_n_step;
+  int32_t use_nanbu;
+  int32_t reserved;
+  double coulomb_log;
+  uint64_t seed;
+  const double *coll_pairs;
+} epb_collisions;
+int epb_collide(epb_handle *h, const epb_collisions *c);
+/* test hook: the pair operator alone on explicit pairs and random numbers (tests/test_collisions.py) */
+int epb_collide_pairs_test(int n, double *p1, double *p2, const double *w1, const double *w2, const double *ran,
+                           const double *env, int *done);
+
 /* -- instrumentation ---------------------------------------------------------------
  * kernel launch counter since creation (bench.py's gpu_launches), and CUDA-event
  * timing of the push/deposit kernel alone: average ms per launch since the last reset */

@@ -2197,3 +2197,6 @@ void orc_kiss(int seed, int n, double *out) {
 }
 
 }  // extern "C"
+
+// binary collisions (physics_packages/collisions.F90): SURVEY.md 8 f1
+#include "collisions_oracle.inc"

@@ -76,6 +76,10 @@ def lib():
         L.orc_kiss.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.orc_calc_moment.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_calc_moment.restype = None
+        L.orc_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.orc_collide.restype = None
+        L.orc_collide_pairs_test.argtypes = [C.c_int] + [C.c_void_p] * 7
+        L.orc_collide_pairs_test.restype = None
         _LIB = L
     return _LIB
 
@@ -215,6 +219,12 @@ class Oracle:
     def init(self): lib().orc_init(self._h)
     def fields_half(self): lib().orc_fields_half(self._h)
     def fields_final(self): lib().orc_fields_final(self._h)
+    def collide(self, coll_pairs, coulomb_log=0.0, use_nanbu=True, coll_n_step=1):
+        """particle_collisions (physics_packages/collisions.F90:86-214) on every rank, with the rank's KISS stream"""
+        n = len(self.deck.species)
+        cp = np.ascontiguousarray(np.asarray(coll_pairs, dtype=np.float64).reshape(n, n))
+        lib().orc_collide(self._h, int(coll_n_step), int(use_nanbu), float(coulomb_log), cp.ctypes.data)
+
     def push(self): lib().orc_push(self._h)
     def push_only(self): lib().orc_push_only(self._h)
     def particle_bcs(self): lib().orc_particle_bcs(self._h)

@@ -1,0 +1,244 @@
+"""Binary collisions (BASELINE config 5): physics_packages/collisions.F90 on the device's cell-resident
+layout (epb_collide) and in the CPU oracle (oracle/collisions_oracle.inc).
+
+The reference holds no numbers for collisions (no test deck switches them on), so the pins are what the operators must
+satisfy -- momentum and energy conservation pair by pair, the classical isotropisation rate of a temperature
+anisotropy -- and, between device and oracle, pair-by-pair agreement on identical random numbers."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from oracle import oracle as O
+
+M0, Q0, CL = D.m0, D.q0, D.c
+
+
+def _pairs(n, m1, m2, t_ev, seed):
+    rng = np.random.default_rng(seed)
+    p1 = rng.normal(size=(n, 3)) * math.sqrt(m1 * t_ev * Q0)
+    p2 = rng.normal(size=(n, 3)) * math.sqrt(m2 * t_ev * Q0)
+    return p1, p2, rng.random((n, 4))
+
+
+def _env(m1, m2, q1, q2, nanbu, inter, dens=1e28, loglam=10.0, dt=1e-16, factor=1.0 / 64e28 * 64, np_=1.0):
+    # SK: nu * factor * np * dt; NP: s_fac = cell_fac * loglam / (4 pi eps0^2 c^4) with cell_fac = n^2 dt factor dV
+    dv = 1e-16
+    fac = 1.0 / (32.0 * dens * dv / 64.0)        # ~ user_factor / sum(min(w)) for 32 pairs of weight n dV / 64
+    cell_fac = dens * dens * dt * fac * dv
+    s_fac = cell_fac * loglam / (4.0 * math.pi * D.epsilon0 ** 2 * CL ** 4)
+    pi_fac = (4.0 * math.pi / 3.0) ** (1.0 / 3.0)
+    if inter:
+        s_fac_prime, sp_den = cell_fac * pi_fac, max(m1, m2) * dens ** (2.0 / 3.0)
+    else:
+        s_fac_prime, sp_den = cell_fac * pi_fac / dens ** (2.0 / 3.0), max(m1, m2)
+    npart = dens * dv
+    return np.array([m1, m2, q1, q2, dens, loglam, fac / (1.0 if inter else 2.0), npart, dt, s_fac, s_fac_prime, sp_den,
+                     float(inter), float(nanbu)])
+
+
+def _run_pairs(fn, p1, p2, w1, w2, ran, env):
+    a, b = p1.copy(), p2.copy()
+    done = np.zeros(p1.shape[0], dtype=np.int32)
+    fn(p1.shape[0], a.ctypes.data, b.ctypes.data, w1.ctypes.data, w2.ctypes.data, ran.ctypes.data, env.ctypes.data,
+       done.ctypes.data)
+    return a, b, done
+
+
+@pytest.mark.parametrize("nanbu", [0, 1])
+@pytest.mark.parametrize("inter", [0, 1])
+def test_pair_operators_conserve_momentum_and_energy(nanbu, inter):
+    """Every scattered pair of equal weights keeps its total momentum and energy (the scattering is a rotation of
+    the relative momentum in the centre-of-momentum frame): to 1e-12 for both operators, like and unlike masses."""
+    O.build()
+    m1, m2 = M0, (1836.2 * M0 if inter else M0)
+    q1, q2 = -Q0, (Q0 if inter else -Q0)
+    n = 4096
+    p1, p2, ran = _pairs(n, m1, m2, 5000.0, 11)          # 5 keV: mildly relativistic
+    w = np.full(n, 3.0e10)
+    a, b, done = _run_pairs(O.lib().orc_collide_pairs_test, p1, p2, w, w, ran, _env(m1, m2, q1, q2, nanbu, inter))
+    assert done.all()
+    e = lambda p, m: CL * np.sqrt(np.sum(p * p, axis=1) + (m * CL) ** 2)
+    scale = np.abs(p1).max() + np.abs(p2).max()
+    assert np.abs((a + b) - (p1 + p2)).max() <= 1e-12 * scale
+    et0, et1 = e(p1, m1) + e(p2, m2), e(a, m1) + e(b, m2)
+    assert np.abs(et1 / et0 - 1.0).max() <= 1e-13
+    moved = np.abs(a - p1).max(axis=1) > 1e-6 * np.abs(p1).max()
+    assert moved.mean() > 0.9                             # and it does scatter
+
+
+def _aniso_deck(n=(16, 16), ppc=200, dens=1.0e28):
+    dx = 1.0e-8
+    sp = [D.Species("electron", -Q0, M0, npart_per_cell=ppc, density=dens, temp=(0.0, 0.0, 0.0))]
+    return D.Deck(2, list(n), [0.0, 0.0], [dx * n[0], dx * n[1]], ["periodic"] * 4, species=sp)
+
+
+def _aniso_particles(o, t_par_ev=150.0, t_perp_ev=75.0, seed=5):
+    p = o.get_particles(0, 0)
+    rng = np.random.default_rng(seed)
+    p[:, 2] = rng.normal(size=p.shape[0]) * math.sqrt(M0 * t_par_ev * Q0)
+    p[:, 3] = rng.normal(size=p.shape[0]) * math.sqrt(M0 * t_perp_ev * Q0)
+    p[:, 4] = rng.normal(size=p.shape[0]) * math.sqrt(M0 * t_perp_ev * Q0)
+    return p
+
+
+def _temps_ev(p):
+    t = (p[:, 2:5] ** 2).mean(axis=0) / M0 / Q0
+    return t[0], 0.5 * (t[1] + t[2])
+
+
+def _nu_iso(dens, t_ev, loglam):
+    """small-anisotropy limit of the NRL isotropisation rate (SI): dT_perp/dt = -nu (T_perp - T_par)"""
+    e2 = Q0 ** 2 / (4.0 * math.pi * D.epsilon0)
+    return 8.0 * math.sqrt(math.pi) / 15.0 * e2 ** 2 * dens * loglam / (math.sqrt(M0) * (t_ev * Q0) ** 1.5)
+
+
+@pytest.mark.parametrize("nanbu", [1, 0])
+def test_temperature_isotropisation_oracle(nanbu):
+    """A bi-Maxwellian electron plasma relaxes towards isotropy at the classical rate: d(T_par - T_perp)/dt =
+    -3 nu (T_par - T_perp).  Collisions only (no push); total momentum and energy are kept to round-off."""
+    dk = _aniso_deck()
+    o = O.Oracle(dk)
+    o.auto_load()
+    p = _aniso_particles(o)
+    o.set_particles(0, 0, p)
+    loglam, dens = 10.0, dk.species[0].density
+    tpar0, tperp0 = _temps_ev(p)
+    tmean = (tpar0 + 2 * tperp0) / 3.0
+    nu = _nu_iso(dens, tmean, loglam)
+    nsteps = int(0.5 / (3.0 * nu * dk.dt()))
+    pt0, e0 = p[:, 2:5].sum(axis=0), np.sqrt((p[:, 2:5] ** 2).sum(axis=1) + (M0 * CL) ** 2).sum()
+    for _ in range(nsteps):
+        o.collide([[1.0]], coulomb_log=loglam, use_nanbu=bool(nanbu))
+    q = o.get_particles(0, 0)
+    assert np.array_equal(q[:, :2], p[:, :2]) and np.array_equal(q[:, 5], p[:, 5])
+    pt1, e1 = q[:, 2:5].sum(axis=0), np.sqrt((q[:, 2:5] ** 2).sum(axis=1) + (M0 * CL) ** 2).sum()
+    assert np.abs(pt1 - pt0).max() <= 1e-9 * np.abs(q[:, 2:5]).sum() and abs(e1 / e0 - 1.0) < 1e-12
+    tpar1, tperp1 = _temps_ev(q)
+    decay = (tpar1 - tperp1) / (tpar0 - tperp0)
+    want = math.exp(-3.0 * nu * nsteps * dk.dt())
+    assert 0.0 < decay < 1.0
+    if nanbu:
+        # finite anisotropy (A = -1/2) and the operator's own accuracy: within 25 % of the small-anisotropy e-folding
+        assert abs(math.log(decay) / math.log(want) - 1.0) < 0.25, (decay, want)
+    else:
+        # Sentoku-Kemp as the reference codes it relaxes like particles several times faster than the classical rate
+        # (measured here: ~5x) -- the "unusual behaviour" its own deck reader warns about when it announces that Nanbu
+        # is the default now (deck_collision_block.F90:120-131).  Restated as it is; only the direction is asserted.
+        assert decay < want, (decay, want)
+
+
+def test_coulomb_log_auto_oracle():
+    """coulomb_log = auto (calc_coulomb_log, collisions.F90:1288-1316) on a hot dense plasma: ln(Lambda) of a few,
+    and the run relaxes; two species so that inter-species pairs are exercised too."""
+    dk = _aniso_deck(n=(8, 8), ppc=60)
+    dk.species.append(D.Species("proton", Q0, 1836.2 * M0, npart_per_cell=60, density=1.0e28, temp=(1.0e6,) * 3))
+    o = O.Oracle(dk)
+    o.auto_load()
+    p = _aniso_particles(o)
+    o.set_particles(0, 0, p)
+    e = lambda: sum(np.sqrt((o.get_particles(0, i)[:, 2:5] ** 2).sum(axis=1) + (m * CL) ** 2).sum() * CL
+                    for i, m in ((0, M0), (1, 1836.2 * M0)))
+    e0 = e()
+    t0 = _temps_ev(p)
+    for _ in range(40):
+        o.collide([[1.0, 1.0], [0.0, 1.0]], coulomb_log=0.0, use_nanbu=True)
+    t1 = _temps_ev(o.get_particles(0, 0))
+    assert abs(e() / e0 - 1.0) < 1e-12
+    assert (t1[0] - t1[1]) < 0.97 * (t0[0] - t0[1])    # ln(Lambda) ~ 2.5 here: four times slower than with the fixed 10
+
+
+# ---- device ---------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("nanbu", [0, 1])
+@pytest.mark.parametrize("inter", [0, 1])
+def test_pair_operators_match_oracle_gpu(nanbu, inter):
+    """The device's pair operator against the oracle's on identical pairs and random numbers: the arithmetic is the
+    same expression tree (both built without FMA contraction); the math-library calls (log, sin, cos, exp, sinh,
+    acos, pow) may differ in the last place, hence 1e-12 of the momentum scale instead of bit equality."""
+    from epoch_b200 import lib as L
+    lib = L.load()
+    m1, m2 = M0, (1836.2 * M0 if inter else M0)
+    q1, q2 = -Q0, (Q0 if inter else -Q0)
+    n = 20000
+    p1, p2, ran = _pairs(n, m1, m2, 2000.0, 23)
+    rng = np.random.default_rng(2)
+    w1 = np.where(rng.random(n) < 0.5, 3.0e10, 1.0e10)     # unequal weights: SK correction / NP rejection paths
+    w2 = np.full(n, 3.0e10)
+    env = _env(m1, m2, q1, q2, nanbu, inter)
+    a0, b0, d0 = _run_pairs(O.lib().orc_collide_pairs_test, p1, p2, w1, w2, ran, env)
+    a1, b1, d1 = _run_pairs(lib.epb_collide_pairs_test, p1, p2, w1, w2, ran, env)
+    assert np.array_equal(d0, d1)
+    assert np.abs(a1 - a0).max() <= 1e-12 * np.abs(p1).max()
+    assert np.abs(b1 - b0).max() <= 1e-12 * np.abs(p2).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nanbu", [1, 0])
+def test_temperature_isotropisation_gpu(nanbu):
+    """The same relaxation on the device (epb_collide on the slot columns, per-pair counter-based streams): conserved
+    totals, the classical rate, and the oracle's decay within the statistical scatter of two independent runs."""
+    from epoch_b200.pic import Simulation
+    dk = _aniso_deck()
+    o = O.Oracle(dk)
+    o.auto_load()
+    p = _aniso_particles(o)
+    o.set_particles(0, 0, p)
+    sim = Simulation(dk, strict_fp=True, sort_interval=2, capacity_factor=2.0)
+    sim.upload_species(0, p)
+    loglam, dens = 10.0, dk.species[0].density
+    tpar0, tperp0 = _temps_ev(p)
+    nu = _nu_iso(dens, (tpar0 + 2 * tperp0) / 3.0, loglam)
+    nsteps = int(0.5 / (3.0 * nu * dk.dt()))
+    for _ in range(nsteps):
+        o.collide([[1.0]], coulomb_log=loglam, use_nanbu=bool(nanbu))
+        sim.collide([[1.0]], coulomb_log=loglam, use_nanbu=bool(nanbu), seed=99)
+    q = sim.download_species(0)
+    assert q.shape == p.shape
+    srt = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]
+    assert np.array_equal(srt(q)[:, :2], srt(p)[:, :2])                      # positions untouched
+    pt0, pt1 = p[:, 2:5].sum(axis=0), q[:, 2:5].sum(axis=0)
+    e = lambda a: np.sqrt((a[:, 2:5] ** 2).sum(axis=1) + (M0 * CL) ** 2).sum()
+    assert np.abs(pt1 - pt0).max() <= 1e-9 * np.abs(q[:, 2:5]).sum() and abs(e(q) / e(p) - 1.0) < 1e-12
+    tpar1, tperp1 = _temps_ev(q)
+    decay = (tpar1 - tperp1) / (tpar0 - tperp0)
+    want = math.exp(-3.0 * nu * nsteps * dk.dt())
+    assert 0.0 < decay < 1.0
+    if nanbu:
+        assert abs(math.log(decay) / math.log(want) - 1.0) < 0.25, (decay, want)
+    to = _temps_ev(o.get_particles(0, 0))
+    decay_o = (to[0] - to[1]) / (tpar0 - tperp0)
+    # two independent random streams over 51 200 particles: the remaining anisotropies agree to a few per cent of
+    # the initial one
+    assert abs(decay - decay_o) < 0.03, (decay, decay_o)
+
+
+@pytest.mark.gpu
+def test_collisions_inside_the_pic_loop_gpu():
+    """PROGRAM pic's order (epoch2d.F90:211-250): fields_half, push, collide, current_finish, fields_final -- two
+    species, coulomb_log = auto, both operators' inter-species pairs; the particle count and the total energy
+    (kinetic + field) are kept while the electron anisotropy relaxes."""
+    from epoch_b200.pic import Simulation
+    dk = _aniso_deck(n=(32, 16), ppc=40)
+    dk.species.append(D.Species("proton", Q0, 1836.2 * M0, npart_per_cell=40, density=1.0e28, temp=(1.0e6,) * 3))
+    o = O.Oracle(dk)
+    o.auto_load()
+    p = _aniso_particles(o)
+    sim = Simulation(dk, strict_fp=False, sort_interval=2, capacity_factor=2.0)
+    sim.upload_species(0, p)
+    sim.upload_species(1, o.get_particles(0, 1))
+    sim.init()
+    n0 = [sim.count(0), sim.count(1)]
+    tot = lambda: sum(sim.field_energy()) + sim.kinetic_energy(0) + sim.kinetic_energy(1)
+    e0 = tot()
+    for _ in range(30):
+        sim.fields_half(); sim.push()
+        sim.collide([[1.0, 1.0], [0.0, 1.0]], coulomb_log=0.0, use_nanbu=True)
+        sim.current_finish(); sim.fields_final()
+    assert [sim.count(0), sim.count(1)] == n0
+    assert abs(tot() / e0 - 1.0) < 2e-2
+    t1 = _temps_ev(sim.download_species(0))
+    t0 = _temps_ev(p)
+    assert (t1[0] - t1[1]) < 0.98 * (t0[0] - t0[1])
