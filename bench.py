@@ -141,6 +141,51 @@ def cpu_baseline(n=192, ppc=64, steps=4, procs=1):
             "wall_s": time.perf_counter() - t0}
 
 
+def e2e_full(n=512, ppc=64, steps=10):
+    """The drop-in cost an EPOCH user pays around the resident loop: host/replay.cpp -- a
+    compiled host that keeps the particles in EPOCH-style linked lists -- attaches (list -> pack_particle buffer ->
+    device), runs `steps` steps and takes a full particle dump back into fresh lists, on a bounded C2-physics
+    sample (n x n cells).  Reported per phase; `value` is updates/s with attach and dump inside the clock."""
+    import tempfile
+    import numpy as np
+    from epoch_b200 import deck as D
+    from epoch_b200.pic import Simulation
+    exe = os.path.join(ROOT, "host", "replay")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
+    dk = c2_deck(n, ppc, (1, 1))
+    sim = Simulation(dk, strict_fp=False, sort_interval=0, capacity_factor=1.5)   # for its config structs
+    rng = np.random.default_rng(7)
+    npart = n * n * ppc
+    spc = dk.species[0]
+    dx = dk.dx(0)
+    p = np.empty((npart, 6))
+    cell = np.repeat(np.arange(n * n), ppc)
+    p[:, 0] = dk.x_global(0, cell % n + 1) + (rng.random(npart) - 0.5) * dx
+    p[:, 1] = dk.x_global(1, cell // n + 1) + (rng.random(npart) - 0.5) * dx
+    p[:, 2:5] = rng.normal(size=(npart, 3)) * math.sqrt(spc.temp[0] * D.kb * spc.mass)
+    p[:, 5] = spc.density * dx * dx / ppc
+    with tempfile.TemporaryDirectory() as td:
+        state = os.path.join(td, "state.bin")
+        sim.write_replay_state(state, steps, {}, [p])
+        sim.close()
+        del p
+        r = subprocess.run([exe, state, "-"], capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        return {"error": r.stderr[-300:]}
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    tot = info["attach_s"] + info["steps_s"] + info["download_s"]
+    nbytes = info["particles"] * info["bytes_per_particle"]
+    return {"value": info["particles"] * steps / tot, "unit": UNIT, "particles": info["particles"], "steps": steps,
+            "attach_s": info["attach_s"], "list_to_packed_s": info["list_to_packed_s"], "upload_api_s": info["upload_api_s"],
+            "upload_api_GBps": nbytes / max(info["upload_api_s"], 1e-9) / 1e9, "steps_s": info["steps_s"],
+            "download_s": info["download_s"], "download_api_s": info["download_api_s"],
+            "download_api_GBps": nbytes / max(info["download_api_s"], 1e-9) / 1e9,
+            "packed_to_list_s": info["packed_to_list_s"],
+            "host": "host/replay.cpp (C++, linked lists of heap nodes; the Fortran shim's call sequence)",
+            "sample": f"C2 physics at {n}x{n} cells, {ppc} ppc"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -370,6 +415,8 @@ def main():
                     help="0 = the library default: 2 for the cell-owner 2D kernel, 8 otherwise")
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-full", action="store_true",
+                    help="skip the compiled-host attach / dump measurement (host/replay.cpp) at N = 1")
     ap.add_argument("--no-parity-check", action="store_true",
                     help="skip the untimed pre-phase that checks this decomposition against the multi-rank CPU oracle")
     args = ap.parse_args()
@@ -507,24 +554,45 @@ def main():
     ey_host = torch.empty(sim.shape, dtype=torch.float64).pin_memory()
     h2d = 2 * 2 * ny1 * 8
     d2h = ey_host.numel() * 8 + 8 + 16
+    # one untimed pass of the same calls: first-use allocations (dump staging buffer, copy stream, scratch of the
+    # count reduction) belong to start-up, not to a step
+    sim.global_count(0)
+    sim.field_energy()
+    sim.download_field_async("ey", ey_host.data_ptr())
+    sim.wait_downloads()
     barrier()
+    prof = {} if os.environ.get("EPB_BENCH_E2E_BREAKDOWN") else None   # host wall time of every call of the loop
+
+    def timed_call(name, fn, *a):
+        if prof is None:
+            return fn(*a)
+        t1 = time.perf_counter()
+        r = fn(*a)
+        prof[name] = prof.get(name, 0.0) + time.perf_counter() - t1
+        return r
+
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for side in (0, 1):
-            sim.L.epb_set_laser_source(sim._h, side, src[0].data_ptr(), src[1].data_ptr())
-        sim.step()
-        sim.global_count(0)
-        sim.field_energy()
+            timed_call("set_laser_source", sim.L.epb_set_laser_source, sim._h, side, src[0].data_ptr(), src[1].data_ptr())
+        timed_call("step (enqueue)", sim.step)
+        if prof is not None:
+            timed_call("synchronize (the step on the GPU)", sim.synchronize)
+        timed_call("global_count", sim.global_count, 0)
+        timed_call("field_energy", sim.field_energy)
         # the Ey dump of this step leaves the device while the next step runs (device-side snapshot +
         # second stream); the host owns the previous step's array from here on
         if os.environ.get("EPB_BENCH_SYNC_DUMP"):
-            sim.download_field_into("ey", ey_host.data_ptr())
+            timed_call("download_field", sim.download_field_into, "ey", ey_host.data_ptr())
         else:
-            sim.wait_downloads()
-            sim.download_field_async("ey", ey_host.data_ptr())
+            timed_call("wait_downloads", sim.wait_downloads)
+            timed_call("download_field_async", sim.download_field_async, "ey", ey_host.data_ptr())
     sim.wait_downloads()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if prof is not None and rank == 0:
+        print("e2e breakdown (ms per step): " + ", ".join(f"{k} {1e3 * v / args.steps:.3f}" for k, v in prof.items()) +
+              f"; total {1e3 * e2e_s / args.steps:.3f}", file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -583,6 +651,12 @@ def main():
             b = cpu_baseline()
             b.pop("wall_s", None)
             line["cpu_baseline"] = b
+        if not args.no_e2e_full and world == 1 and not is3d:
+            sim.close()   # give the device memory back before the compiled host attaches its own state
+            try:
+                line["e2e_full"] = e2e_full()
+            except Exception as e:
+                line["e2e_full"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

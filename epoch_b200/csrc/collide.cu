@@ -481,7 +481,7 @@ extern "C" int epb_collide(epb_handle *h, const epb_collisions *c) {
       for (int d = 0; d < 3; d++) { O.p1[d] = S1.buf[0][3 + d]; O.p2[d] = S2.buf[0][3 + d]; }
       O.w1 = S1.buf[0][6]; O.w2 = S2.buf[0][6];
       O.cnt1 = S1.cnt; O.cnt2 = S2.cnt;
-      O.R1 = S1.R; O.R2 = S2.R; O.rowd = 6 * 32;
+      O.R1 = S1.R; O.R2 = S2.R; O.rowd = S1.rowd;
       O.ngroups = ngroups;
       O.intra = (is == js);
       O.nanbu = c->use_nanbu ? 1 : 0;

@@ -666,6 +666,106 @@ __global__ void __launch_bounds__(256) k_load_uniform(const __grid_constant__ Lo
   }
 }
 
+// Thermal particle boundaries (boundary.F90:1104-1148 and its x_max / y / z copies; epoch3d :1496-1550, epoch1d
+// :728-750), applied right after the push to the particles particle_bc left beyond x_min_outer / x_max_outer of a
+// thermal wall: the wall temperature is interpolated with the triangle weights at the particle's transverse
+// position, the momentum normal to the wall is drawn from the inward flux distribution (flux_momentum_from_
+// temperature with zero drift: SQRT(g1^2 + g2^2) of two normal deviates, particle_temperature.F90:409-460), the other
+// two from Maxwellians (momentum_from_temperature :388-398), and the position is mirrored about the outer edge.
+// The reference draws from the rank's serial KISS stream; here every particle has its own counter-based stream.
+struct ThermalOp {
+  double *x[3], *p[3];
+  PRange r;
+  int nd, n[3];
+  double gmin_local[3], dx[3], min_outer[3], max_outer[3];
+  int th_min[3], th_max[3];      // thermal wall on this rank's boundary face
+  const double *ext_temp[6];     // (plane, 3): the transverse axes in axis order with ghost cells, lower axis fastest
+  double mass;
+  unsigned long long seed;
+};
+__device__ __forceinline__ void normal_pair(unsigned long long &s, double &a, double &b) {
+  double u1 = u01(s), u2 = u01(s);
+  if (u1 < 1e-300) u1 = 1e-300;
+  const double r = sqrt(-2.0 * log(u1));
+  a = r * cos(6.283185307179586476925286766559 * u2);
+  b = r * sin(6.283185307179586476925286766559 * u2);
+}
+template <int ND>
+__global__ void __launch_bounds__(256) k_thermal(const __grid_constant__ ThermalOp T) {
+  const long long nn = prange_n(T.r);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
+    if (!prange_valid(T.r, i)) continue;
+    const long long e = prange_at(T.r, i);
+    double pos[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; d++) pos[d] = T.x[d][e];
+    bool any = false;
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+      any = any || (T.th_min[d] && pos[d] < T.min_outer[d]) || (T.th_max[d] && pos[d] >= T.max_outer[d]);
+    if (!any) continue;
+    unsigned long long s = T.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(i + 1));
+    (void)splitmix(s);
+    double mom[3] = {T.p[0][e], T.p[1][e], T.p[2][e]};
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      const double part_pos = pos[d];
+      for (int side = 0; side < 2; side++) {
+        const bool hit = side == 0 ? (T.th_min[d] && part_pos < T.min_outer[d]) : (T.th_max[d] && part_pos >= T.max_outer[d]);
+        if (!hit) continue;
+        // wall temperature at the particle's transverse position (always the triangle weighting)
+        int tr[2] = {0, 0}, ntr = 0;
+        for (int q = 0; q < ND; q++) if (q != d) tr[ntr++] = q;
+        size_t plane = 1;
+        for (int q = 0; q < ntr; q++) plane *= (size_t)(T.n[tr[q]] + 2 * NG);
+        int cell[2] = {0, 0};
+        double g[2][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
+        for (int q = 0; q < ntr; q++) {
+          const double cell_r = (pos[tr[q]] - T.gmin_local[tr[q]]) / T.dx[tr[q]];
+          const int c = __double2int_rd(cell_r + 0.5);
+          const double cf = (double)c - cell_r;
+          cell[q] = c + 1;
+          const double cf2 = cf * cf;
+          g[q][0] = 0.5 * (0.25 + cf2 + cf);
+          g[q][1] = 0.75 - cf2;
+          g[q][2] = 0.5 * (0.25 + cf2 - cf);
+        }
+        const double *ET = T.ext_temp[2 * d + side];
+        double temp[3];
+        for (int c3 = 0; c3 < 3; c3++) {
+          double t = 0.0;
+          if (ntr == 0) {
+            t = ET[c3];
+          } else if (ntr == 1) {
+            for (int a = -1; a <= 1; a++) t = t + g[0][a + 1] * ET[(size_t)(cell[0] + a + NG - 1) + plane * c3];
+          } else {
+            const size_t e0 = (size_t)(T.n[tr[0]] + 2 * NG);
+            for (int b = -1; b <= 1; b++)
+              for (int a = -1; a <= 1; a++)
+                t = t + g[0][a + 1] * g[1][b + 1] * ET[(size_t)(cell[0] + a + NG - 1) + e0 * (size_t)(cell[1] + b + NG - 1) + plane * c3];
+          }
+          temp[c3] = t;
+        }
+        const double direction = side == 0 ? 1.0 : -1.0;   // -REAL(sgn): into the domain
+        double g1, g2, g3, g4;
+        normal_pair(s, g1, g2);
+        normal_pair(s, g3, g4);
+        const double gq[2] = {g3, g4};
+        int k = 0;
+        for (int c3 = 0; c3 < 3; c3++) {
+          const double stdev = sqrt(temp[c3] * EPB_KB * T.mass);
+          if (c3 == d) mom[c3] = direction * sqrt((g1 * stdev) * (g1 * stdev) + (g2 * stdev) * (g2 * stdev));
+          else mom[c3] = gq[k++] * stdev;
+        }
+        pos[d] = 2.0 * (side == 0 ? T.min_outer[d] : T.max_outer[d]) - part_pos;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) T.x[d][e] = pos[d];
+    T.p[0][e] = mom[0]; T.p[1][e] = mom[1]; T.p[2][e] = mom[2];
+  }
+}
+
 // calc_total_energy_sum (io/calc_df.F90:1321-1417)
 struct EnergyOp {
   const double *f[6];
@@ -1226,7 +1326,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   for (int s = 0; s < cfg->n_species; s++) {
     for (int i = 0; i < 2 * cfg->ndims; i++) {
       int b = species[s].bc_particle[i];
-      if (!(b == EPB_BC_PERIODIC || b == EPB_BC_REFLECT || b == EPB_BC_OPEN))
+      if (!(b == EPB_BC_PERIODIC || b == EPB_BC_REFLECT || b == EPB_BC_OPEN || b == EPB_BC_THERMAL))
         return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "particle boundary code %d not implemented on the device path", b);
     }
   }
@@ -1281,7 +1381,7 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
     S.cap = species[s].capacity > 0 ? species[s].capacity : 1024;
     if (S.cap >= (1LL << 31) - 1024) return epb_fail(h, EPB_ERR_CAPACITY, "species capacity must be < 2^31");
     maxcap = S.cap > maxcap ? S.cap : maxcap;
-    if (h->tg.layout == 2) {  // slot columns: the arena is sized at the first upload / load (slots.cu)
+    if (h->tg.layout >= 2) {  // slot columns / tile bags: the arena is sized at the first upload / load (slots.cu)
       int rcs = epb_slots_alloc(h, s);
       if (!rcs) {  // a first arena from the mean occupancy the capacity implies; re-sized by upload / load if denser
         long long ncell = 1;
@@ -1352,6 +1452,7 @@ int epb_destroy(epb_handle *h) {
   for (auto &S : h->sp) {
     // slot columns first: their buf[0][*] point INTO the arena and are cleared by epb_slots_free
     if (S.slots) epb_slots_free(S);
+    for (int q = 0; q < 6; q++) cudaFree(S.ext_temp[q]);
     for (int b = 0; b < 2; b++)
       for (int q = 0; q < 7; q++) cudaFree(S.buf[b][q]);
     cudaFree(S.key); cudaFree(S.tile_start); cudaFree(S.cell_start); cudaFree(S.rank); cudaFree(S.perm); cudaFree(S.stay_cnt); cudaFree(S.arr_cnt); cudaFree(S.gone);
@@ -1664,6 +1765,63 @@ int epb_sort(epb_handle *h) {
 
 static int current_bcs_species(epb_handle *h, int is);
 
+// thermal walls of this rank for species `is`: re-emission of the particles the push left beyond the outer edge.
+// `views`: the particle ranges to scan (slot columns: only the mover buffer holds boundary-touched particles)
+static int thermal_apply(epb_handle *h, int is, const SlotView *V, int nv) {
+  const epb_config &c = h->cfg;
+  SpeciesDev &S = h->sp[is];
+  ThermalOp T;
+  memset(&T, 0, sizeof T);
+  bool any = false;
+  for (int d = 0; d < c.ndims; d++) {
+    T.th_min[d] = c.is_boundary[2 * d] && S.cfg.bc_particle[2 * d] == EPB_BC_THERMAL;
+    T.th_max[d] = c.is_boundary[2 * d + 1] && S.cfg.bc_particle[2 * d + 1] == EPB_BC_THERMAL;
+    any = any || T.th_min[d] || T.th_max[d];
+  }
+  if (!any) return EPB_OK;
+  for (int side = 0; side < 2 * c.ndims; side++) {
+    const int d = side / 2;
+    if (((side & 1) ? T.th_max[d] : T.th_min[d]) && !S.ext_temp[side])
+      return epb_fail(h, EPB_ERR_ARG, "species %d: thermal boundary %d without epb_set_boundary_temperature", is, side);
+    T.ext_temp[side] = S.ext_temp[side];
+  }
+  T.nd = c.ndims;
+  for (int d = 0; d < 3; d++) {
+    T.n[d] = c.n[d];
+    T.gmin_local[d] = c.grid_min_local[d];
+    T.dx[d] = c.dx[d];
+    T.min_outer[d] = c.min_outer[d];
+    T.max_outer[d] = c.max_outer[d];
+  }
+  T.mass = S.cfg.mass;
+  h->thermal_calls++;
+  T.seed = 0x2545F4914F6CDD1Dull * (unsigned long long)h->thermal_calls + 0x9E3779B97F4A7C15ull * (unsigned long long)(c.rank + 1) + (unsigned long long)is;
+  for (int v = 0; v < nv; v++) {
+    for (int d = 0; d < 3; d++) { T.x[d] = V[v].a[d]; T.p[d] = V[v].a[3 + d]; }
+    T.r = V[v].r;
+    const int nb = nblocks((size_t)V[v].r.n, 148 * 8);
+    if (c.ndims == 1) k_thermal<1><<<nb, 256, 0, h->stream>>>(T);
+    else if (c.ndims == 2) k_thermal<2><<<nb, 256, 0, h->stream>>>(T);
+    else k_thermal<3><<<nb, 256, 0, h->stream>>>(T);
+    h->launches++;
+  }
+  return EPB_OK;
+}
+
+// ext_temp_<side> of a species (shared_data.F90:255-256; set from the deck's temperature by the host): the wall
+// temperature of a thermal particle boundary, (plane, 3) doubles -- the transverse axes in axis order with ghost
+// cells (1-ng:n+ng), lower axis fastest, then the three momentum components
+int epb_set_boundary_temperature(epb_handle *h, int is, int side, const double *temp) {
+  if (!h || is < 0 || is >= (int)h->sp.size() || side < 0 || side >= 2 * h->cfg.ndims || !temp) return EPB_ERR_ARG;
+  SpeciesDev &S = h->sp[is];
+  size_t plane = 1;
+  for (int d = 0; d < h->cfg.ndims; d++) if (d != side / 2) plane *= (size_t)h->sz[d];
+  if (!S.ext_temp[side]) EPB_CUDA(h, cudaMalloc(&S.ext_temp[side], 3 * plane * sizeof(double)));
+  EPB_CUDA(h, cudaMemcpyAsync(S.ext_temp[side], temp, 3 * plane * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPB_OK;
+}
+
 int epb_push(epb_handle *h) {
   if (!h) return EPB_ERR_ARG;
   const epb_config &c = h->cfg;
@@ -1716,6 +1874,12 @@ int epb_push(epb_handle *h) {
       }
       int rc = epb_slots_after_push(h, is);
       if (rc) return rc;
+      {  // thermal walls: the boundary-touched particles sit in the mover buffer
+        SlotView V[2];
+        epb_slots_views(h, is, V);
+        rc = thermal_apply(h, is, V + 1, 1);
+        if (rc) return rc;
+      }
       rc = epb_particle_exchange(h, is);
       if (rc) return rc;
       rc = epb_slots_deliver(h, is);
@@ -1782,6 +1946,12 @@ int epb_push(epb_handle *h) {
     if (h->bc_mixed) {  // current_bcs(species = ispecies), particles.F90:645
       int rcm = current_bcs_species(h, is);
       if (rcm) return rcm;
+    }
+    {  // thermal walls (part of particle_bcs): scan the species for particles beyond the outer edge
+      SlotView V[2];
+      const int nv = epb_species_views(h, is, V);
+      int rct = thermal_apply(h, is, V, nv);
+      if (rct) return rct;
     }
     // particle_bcs (particles.F90:648) for this species.  The outbox is shared by all
     // species, so it is drained before the next species is pushed; the reference runs

@@ -26,7 +26,8 @@ struct TileGeom {
   int ntiles;
   int nkeys;   // ntiles * cpt
   int layout;  // 0: cell-major inside a tile; 1 (2D): 8x4-cell warp groups, particles of a group interleaved by rank (see push_cell_2d);
-               // 2 (2D, default): slot columns, one fixed-capacity column per cell, no sort at all (see push_slots_2d)
+               // 2 (2D, default): slot columns, one fixed-capacity column per cell, no sort at all (see push_slots_2d);
+               // 3 (3D, EPB_PUSH3D_VARIANT=1): slot columns in 3D, 16x4x2-cell tiles (push_bag_3d)
 };
 
 // Layout 2 ("slot columns", 2D): the particles of cell key k = group * 32 + lane live in rows 0 .. cnt[k]-1 of
@@ -125,6 +126,7 @@ struct PushParams {
   // layout 2 (slot columns): x/p/w above are the arena; cnt = particles per column, R = rows per column
   int *cnt;
   int R;
+  int rowd;                // doubles per row block: 32 x components (interleaved rows) or 32 (one plane per component)
   // mover buffer the kernel appends to: entry m holds a particle that must be (re)inserted by k_deliver
   // (mflag 0), one that left this rank (1, listed in the outbox by its M index) or one that still has to be
   // pushed by the generic kernel (2: stencil outside the tile, or no room in its column)
@@ -160,9 +162,11 @@ struct SpeciesDev {
   bool info_valid = false;    // key/rank/stay_cnt/arr_cnt describe the current particle set
   bool pending_perm = false;  // the sort left the data in place: perm[new slot] = old index, applied by the next push
   unsigned char *gone = nullptr;
+  double *ext_temp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // thermal walls: ext_temp_x_min ... (plane, 3)
   // layout 2 (slot columns): buf[0] is the arena of nkeys * R slots; n / n_sorted / key / rank / perm are unused
   bool slots = false;
   int R = 0;                  // rows per column
+  int rowd = 0;               // doubles per row block (see PushParams)
   int *cnt = nullptr;         // [nkeys] particles per column
   double *mbuf[2][7] = {{0}}; // mover buffers (SoA), mcur = the one the push appends to
   unsigned char *mflag[2] = {nullptr, nullptr};
@@ -207,6 +211,7 @@ struct epb_handle {
   int *h_counts = nullptr;      // pinned [64]
   int *d_scratch = nullptr;     // device ints
   double *coll_work = nullptr;  // collisions with coulomb_log_auto: ekbar of species 1, temperature of species 2 (2 x fsize)
+  long long thermal_calls = 0;  // thermal re-emission launches so far (seed of the per-particle streams)
   long long coll_calls = 0;     // epb_collide calls so far (feeds the pair streams' seed)
   double *aos_stage = nullptr;  // 2 Mi particles in the pack_particle wire layout (upload / download staging)
   int *d_err = nullptr;         // device error word (layout 2), checked at the synchronising entry points

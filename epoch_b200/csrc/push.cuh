@@ -83,6 +83,10 @@ __device__ __forceinline__ int particle_bc(const PushParams &P, double *pos, dou
         }
       } else if (bc == EPB_BC_PERIODIC) {
         if (P.is_bnd_min[d]) pos[d] = part_pos + P.shift[d];
+      } else if (bc == EPB_BC_THERMAL) {
+        // boundary.F90:1104-1148: the particle stays on this rank; beyond x_min_outer it is re-emitted from the wall's
+        // thermal distribution by k_thermal right after the push (epb_api.cu), which needs random numbers
+        if (P.is_bnd_min[d]) bd[d] = 0;
       } else {
         if (part_pos < P.min_outer[d]) { bd[d] = 0; oob = true; }
         else if (P.is_bnd_min[d]) bd[d] = 0;
@@ -99,6 +103,8 @@ __device__ __forceinline__ int particle_bc(const PushParams &P, double *pos, dou
         }
       } else if (bc == EPB_BC_PERIODIC) {
         if (P.is_bnd_max[d]) pos[d] = part_pos - P.shift[d];
+      } else if (bc == EPB_BC_THERMAL) {
+        if (P.is_bnd_max[d]) bd[d] = 0;
       } else {
         if (part_pos >= P.max_outer[d]) { bd[d] = 0; oob = true; }
         else if (P.is_bnd_max[d]) bd[d] = 0;
@@ -1345,7 +1351,7 @@ constexpr size_t pushslots_smem() {
          sizeof(int) * ((size_t)(CTY / 2) * QCAP + 2 + (size_t)(CTY / 2) * 32) + (size_t)(CTY / 2) * 32 * SLOT_LK;
 }
 
-template <int CTY, int MINB>
+template <int CTY, int MINB, bool RB>
 __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_constant__ PushParams P) {
   constexpr int T2Y = CTY, TH = CTY + 2 * HALO, TW = CPITCH, TWU = T2X + 2 * HALO, TILE_ELEMS = TW * TH;
   constexpr int PUSH2D_THREADS = CTY * 16, PUSH2D_WARPS = CTY / 2;
@@ -1431,7 +1437,10 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   const int maxcnt = __reduce_max_sync(FULL, my_tot);
   // row 0 of this lane's column: rows are blocks of 6 x 32 doubles (x y px py pz w), so every access below is
   // this pointer + row * ROWD + an immediate component offset
-  constexpr int ROWD = 6 * 32, OX = 0, OY = 32, OPX = 64, OPY = 96, OPZ = 128, OW = 160;
+  // (RB = false: one plane per component, rows of 32 doubles; the component offsets are run-time strides then)
+  constexpr int ROWD = RB ? 6 * 32 : 32;
+  const size_t CS = RB ? (size_t)32 : (size_t)(P.x[1] - P.x[0]);
+  const size_t OX = 0, OY = CS, OPX = 2 * CS, OPY = 3 * CS, OPZ = 4 * CS, OW = 5 * CS;
   double *const col = P.x[0] + ((size_t)(my_key >> 5) * (size_t)P.R) * ROWD + lane;
   int wcur = 0;  // write cursor: rows 0 .. wcur-1 hold the particles that stay in this column
 
@@ -2272,6 +2281,469 @@ __global__ void __launch_bounds__(P3_THREADS, 2) push_tiled_3d(const __grid_cons
 }
 
 
+// ---------------------------------------------------------------------------
+// Slot-column 3D kernel (layout 3, EPB_PUSH3D_VARIANT=1)
+// ---------------------------------------------------------------------------
+// The slot-column store of push_slots_2d in 3D: a column per cell, rows of 7 x 32 doubles (x y z px py pz w),
+// in-place compaction by the owning lane, movers through the group inboxes, boundary-touched / leaving /
+// out-of-tile particles through the mover buffer.  One CTA (4 warps) per 16 x 4 x 2-cell tile; a warp's 32 columns
+// are 16 x 2 cells of one z plane, so a half-warp always works on 16 CONSECUTIVE cells of one x row: every shared-
+// memory access of the gather and of the deposit is then conflict-free whatever the row pitch (the first version,
+// 8 x 8 x 4 tiles with 8 x 4-cell groups, lost half of its shared-memory bandwidth to bank conflicts between the
+// rows of a half-warp: profiles/r02_ncu_push_bag_3d_v1_cells.txt).  Because a particle is always gathered inside
+// its tile (the prediction that places it is the push's own half step), the tile's E/B live in shared memory with
+// a halo of only -2 / +1 cells and the gather never touches global memory -- the step push_tiled_3d could not
+// take, since its sorted order goes stale between sorts.  Deposit: the lanes of a row sit in 32 different cells,
+// so the 54 non-cancelling values of a particle whose nearest cell is unchanged go straight to the shared J tile
+// with shared-memory adds that do not collide inside the warp -- no transposition scratch, no reduction; a
+// particle whose nearest cell moved is queued per warp and drained densely with the reference's general loop.
+constexpr int B3X = 16, B3Y = 4, B3Z = 2, B3N = B3X * B3Y * B3Z;          // tile = 128 cells = 4 warps x 32 columns
+constexpr int B3_THREADS = 128, B3_WARPS = 4;
+constexpr int EB3X = B3X + 3, EB3Y = B3Y + 3, EB3Z = B3Z + 3, EB3N = EB3X * EB3Y * EB3Z;   // E/B: cells origin-2 .. origin+T
+constexpr int EB3P = (EB3N + 1) & ~1;                                      // padded component stride
+constexpr int JB3H = 2, JB3X = B3X + 2 * JB3H, JB3Y = B3Y + 2 * JB3H, JB3Z = B3Z + 2 * JB3H, JB3N = JB3X * JB3Y * JB3Z;
+constexpr size_t PUSHBAG3D_SMEM =
+    sizeof(double) * ((size_t)6 * EB3P + (size_t)3 * JB3N + (size_t)B3_WARPS * Q3DBL * Q3CAP) +
+    sizeof(int) * ((size_t)B3_WARPS * Q3CAP + (size_t)B3_WARPS * 32 + 2) + (size_t)B3_WARPS * 32 * SLOT_LK;
+
+// drain_extras_3d's general loop (epoch3d particles.F90:603-648) on a J tile of any geometry
+__device__ __noinline__ void drain_general_3d(const PushParams &P, double *sJ, const double *Qd, const int *Qk, int n,
+                                              int lane, int sy, int sz, int jt) {
+  if (lane >= n) return;
+  const int pk = Qk[lane];
+  const int key = pk & 4095;
+  const int dcell[3] = {((pk >> 12) & 3) - 1, ((pk >> 14) & 3) - 1, ((pk >> 16) & 3) - 1};
+  const double fjx = Qd[6 * Q3CAP + lane], fjy = Qd[7 * Q3CAP + lane], fjz = Qd[8 * Q3CAP + lane];
+  double G[3][5], H[3][5];
+  int mn[3], mx[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    G[d][0] = G[d][4] = 0.0;
+    tri(Qd[(2 * d) * Q3CAP + lane], G[d][1], G[d][2], G[d][3]);
+    double wm, w0, wp;
+    tri(Qd[(2 * d + 1) * Q3CAP + lane], wm, w0, wp);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      const int r = q - 2 - dcell[d];
+      H[d][q] = ((r == -1) ? wm : (r == 0) ? w0 : (r == 1) ? wp : 0.0) - G[d][q];
+    }
+    mn[d] = -1 + (dcell[d] - 1) / 2;
+    mx[d] = 1 + (dcell[d] + 1) / 2;
+  }
+  const double *gx = &G[0][2], *gy = &G[1][2], *gz = &G[2][2];
+  const double *hx = &H[0][2], *hy = &H[1][2], *hz = &H[2][2];
+  const double third = P.third;
+  double jzh[5][5];
+  for (int a = 0; a < 5; a++)
+    for (int b = 0; b < 5; b++) jzh[a][b] = 0.0;
+  for (int iz = mn[2]; iz <= mx[2]; iz++) {
+    const double zfac1 = gz[iz] + 0.5 * hz[iz];
+    const double zfac2 = third * hz[iz] + 0.5 * gz[iz];
+    const double gz_iz = gz[iz], hz_iz = hz[iz];
+    double jyh[5] = {0, 0, 0, 0, 0};
+    for (int iy = mn[1]; iy <= mx[1]; iy++) {
+      const double yfac1 = gy[iy] + 0.5 * hy[iy];
+      const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+      const double hygz = hy[iy] * gz_iz;
+      const double hyhz = hy[iy] * hz_iz;
+      const double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
+      const double hzyfac1 = hz_iz * yfac1;
+      const double hzyfac2 = hz_iz * yfac2;
+      double jxh = 0.0;
+      for (int ix = mn[0]; ix <= mx[0]; ix++) {
+        const double xfac1 = gx[ix] + 0.5 * hx[ix];
+        const double xfac2 = third * hx[ix] + 0.5 * gx[ix];
+        const double wx = hx[ix] * yzfac;
+        const double wy = xfac1 * hygz + xfac2 * hyhz;
+        const double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
+        jxh = jxh - fjx * wx;
+        jyh[ix + 2] = jyh[ix + 2] - fjy * wy;
+        jzh[iy + 2][ix + 2] = jzh[iy + 2][ix + 2] - fjz * wz;
+        const int o = key + iz * sz + iy * sy + ix;
+        // the last column / row / plane of each running sum cancels structurally (sum of hx = 0)
+        if (ix < mx[0]) smem_add(&sJ[o], jxh);
+        if (iy < mx[1]) smem_add(&sJ[jt + o], jyh[ix + 2]);
+        if (iz < mx[2]) smem_add(&sJ[2 * jt + o], jzh[iy + 2][ix + 2]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_constant__ PushParams P) {
+  extern __shared__ double sm[];
+  double *sF = sm;                                   // [6][EB3P]
+  double *sJ = sF + 6 * EB3P;                        // [3][JB3N]
+  double *sQd_all = sJ + 3 * JB3N;
+  int *sQk_all = reinterpret_cast<int *>(sQd_all + B3_WARPS * Q3DBL * Q3CAP);
+  int *sAcnt_all = sQk_all + B3_WARPS * Q3CAP;       // [warp][32] arrivals per lane
+  unsigned char *sAlist_all = reinterpret_cast<unsigned char *>(sAcnt_all + B3_WARPS * 32 + 2);   // [warp][32][SLOT_LK]
+  const int tile = blockIdx.x;
+  const int ttx = tile % P.tg.nt[0], tty = (tile / P.tg.nt[0]) % P.tg.nt[1], ttz = tile / (P.tg.nt[0] * P.tg.nt[1]);
+  const int cx0 = ttx * B3X + 1, cy0 = tty * B3Y + 1, cz0 = ttz * B3Z + 1;  // first cell of the tile (1-based)
+  const int ex0 = cx0 - 2, ey0 = cy0 - 2, ez0 = cz0 - 2;                   // E/B tile origin
+  const int ox = cx0 - JB3H, oy = cy0 - JB3H, oz = cz0 - JB3H;             // J tile origin
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int my_key = tile * B3N + warp * 32 + lane;
+  int my_cnt = P.cnt[my_key];
+  if (my_cnt > P.R) my_cnt = P.R;
+  const int grp = my_key >> 5;
+  int inA = P.ic_in ? P.ic_in[grp] : 0;
+  if (inA > P.IC) inA = P.IC;
+  if (!__syncthreads_or(my_cnt > 0 || inA > 0)) return;
+  for (int q = tid; q < EB3N; q += B3_THREADS) {
+    const int lx = q % EB3X, ly = (q / EB3X) % EB3Y, lz = q / (EB3X * EB3Y);
+    const int cx = ex0 + lx, cy = ey0 + ly, cz = ez0 + lz;
+    const bool ok = (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG) &&
+                    (cz >= 1 - NG) && (cz <= P.n[2] + NG);
+    const size_t o = ok ? gofs<3>(P, cx, cy, cz) : 0;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      sF[f * EB3P + q] = ok ? __ldg(P.e[f] + o) : 0.0;
+      sF[(3 + f) * EB3P + q] = ok ? __ldg(P.b[f] + o) : 0.0;
+    }
+  }
+  for (int q = tid; q < 3 * JB3N; q += B3_THREADS) sJ[q] = 0.0;
+  // ---- this warp's inbox: which entries are for which lane (entry = 8 doubles, [7] = destination lane) ----
+  int *sAcnt = sAcnt_all + warp * 32;
+  unsigned char *sAlist = sAlist_all + warp * 32 * SLOT_LK;
+  const double *ibg = P.ib_in ? P.ib_in + (size_t)grp * (size_t)P.IC * 8 : nullptr;
+  sAcnt[lane] = 0;
+  __syncwarp();
+  for (int j0 = 0; j0 < inA; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < inA) {
+      const int ml = (int)__double_as_longlong(ibg[(size_t)j * 8 + 7]) & 31;
+      const int pos = atomicAdd(&sAcnt[ml], 1);
+      if (pos < SLOT_LK) {
+        sAlist[ml * SLOT_LK + pos] = (unsigned char)j;
+      } else {
+        const int m = atomicAdd(P.mcount, 1);
+        if (m < P.mcap) {
+          const double *e = ibg + (size_t)j * 8;
+          P.mx[0][m] = e[0]; P.mx[1][m] = e[1]; P.mx[2][m] = e[2];
+          P.mp[0][m] = e[3]; P.mp[1][m] = e[4]; P.mp[2][m] = e[5];
+          P.mw[m] = e[6];
+          P.mflag[m] = 0;
+        } else {
+          atomicOr(P.err, 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  int my_a = sAcnt[lane];
+  if (my_a > SLOT_LK) my_a = SLOT_LK;
+  const int my_tot = my_cnt + my_a;
+  const int maxcnt = __reduce_max_sync(FULL, my_tot);
+
+  const double c = EPB_C;
+  const double third = P.third;
+  double *Qd = sQd_all + warp * Q3DBL * Q3CAP;
+  int *Qk = sQk_all + warp * Q3CAP;
+  int qcount = 0;  // warp-uniform
+  const unsigned lt_mask = (1u << lane) - 1u;
+  constexpr int ROWD = 7 * 32;
+  double *const col = P.x[0] + ((size_t)grp * (size_t)P.R) * ROWD + lane;
+  int wcur = 0;
+
+  double n_v[7] = {0, 0, 0, 0, 0, 0, 0};   // x y z px py pz w of the next round
+  auto fetch = [&](int rn) {
+    if (rn < my_cnt) {
+      const double *row = col + (size_t)rn * ROWD;
+#pragma unroll
+      for (int q = 0; q < 7; q++) n_v[q] = row[q * 32];
+    } else if (rn < my_tot) {
+      const double2 *e = reinterpret_cast<const double2 *>(ibg + (size_t)sAlist[lane * SLOT_LK + (rn - my_cnt)] * 8);
+      const double2 v0 = e[0], v1 = e[1], v2 = e[2], v3 = e[3];
+      n_v[0] = v0.x; n_v[1] = v0.y; n_v[2] = v1.x; n_v[3] = v1.y; n_v[4] = v2.x; n_v[5] = v2.y; n_v[6] = v3.x;
+    }
+  };
+  fetch(0);
+  for (int r = 0; r < maxcnt; r++) {
+    const bool active = r < my_tot;
+    double o_v[6] = {n_v[0], n_v[1], n_v[2], n_v[3], n_v[4], n_v[5]};   // what is written back / sent on
+    const double part_weight = n_v[6];
+    double pp[3] = {n_v[0] - P.grid_min_local[0], n_v[1] - P.grid_min_local[1], n_v[2] - P.grid_min_local[2]};
+    double uu[3] = {n_v[3] * P.ipart_mc, n_v[4] * P.ipart_mc, n_v[5] * P.ipart_mc};
+    fetch(r + 1);
+    int disp = 0, dir = -1, ib_slot = -1, ntile = 0, nlane = 0;
+    bool touched = false, extras = false;
+    int qkey, dcell[3];
+    double q_f[6], fj[3];
+    if (active) {
+      double root;
+      gamma_root(uu[0] * uu[0] + uu[1] * uu[1] + uu[2] * uu[2] + 1.0, P.dtco2, root);
+      int c1[3], c2[3];
+      double G[3][3], H[3][3], cr[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        pp[d] = pp[d] + uu[d] * root;
+        cr[d] = pp[d] * P.idx[d];
+        c1[d] = __double2int_rd(cr[d] + 0.5) + 1;
+      }
+      const bool fast = (c1[0] >= cx0) && (c1[0] < cx0 + B3X) && (c1[1] >= cy0) && (c1[1] < cy0 + B3Y) &&
+                        (c1[2] >= cz0) && (c1[2] < cz0 + B3Z);
+      if (!fast) {
+        disp = 2;
+      } else {
+        double fo[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          fo[d] = (double)(c1[d] - 1) - cr[d];
+          tri_s(fo[d], G[d][0], G[d][1], G[d][2]);
+          const int c2d = __double2int_rd(cr[d]);
+          tri_s((double)c2d - cr[d] + 0.5, H[d][0], H[d][1], H[d][2]);
+          c2[d] = c2d + 1;
+        }
+        // shared E/B tile offsets of (cell - 1) along every axis, for the nearest (1) and the staggered (2) cell
+        const int a1[3] = {c1[0] - 1 - ex0, (c1[1] - 1 - ey0) * EB3X, (c1[2] - 1 - ez0) * EB3X * EB3Y};
+        const int a2[3] = {c2[0] - 1 - ex0, (c2[1] - 1 - ey0) * EB3X, (c2[2] - 1 - ez0) * EB3X * EB3Y};
+        auto gat = [&](const double *F, int o, const double *wx, const double *wy, const double *wz) {
+          double acc = 0.0;
+#pragma unroll
+          for (int iz = 0; iz < 3; iz++) {
+            double pl = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < 3; iy++) {
+              const double *row = F + o + iz * EB3X * EB3Y + iy * EB3X;
+              const double rs = wx[0] * row[0] + wx[1] * row[1] + wx[2] * row[2];
+              pl = (iy == 0) ? wy[iy] * rs : pl + wy[iy] * rs;
+            }
+            acc = (iz == 0) ? wz[iz] * pl : acc + wz[iz] * pl;
+          }
+          return acc;
+        };
+        // include/triangle/e_part.inc, b_part.inc: ex(hx,gy,gz) ey(gx,hy,gz) ez(gx,gy,hz) bx(gx,hy,hz) by(hx,gy,hz) bz(hx,hy,gz)
+        const double ex_part = gat(sF + 0 * EB3P, a2[0] + a1[1] + a1[2], H[0], G[1], G[2]);
+        const double ey_part = gat(sF + 1 * EB3P, a1[0] + a2[1] + a1[2], G[0], H[1], G[2]);
+        const double ez_part = gat(sF + 2 * EB3P, a1[0] + a1[1] + a2[2], G[0], G[1], H[2]);
+        const double bx_part = gat(sF + 3 * EB3P, a1[0] + a2[1] + a2[2], G[0], H[1], H[2]);
+        const double by_part = gat(sF + 4 * EB3P, a2[0] + a1[1] + a2[2], H[0], G[1], H[2]);
+        const double bz_part = gat(sF + 5 * EB3P, a2[0] + a2[1] + a1[2], H[0], H[1], G[2]);
+        const double cmratio = P.cmratio;
+        const double uxm = uu[0] + cmratio * ex_part;
+        const double uym = uu[1] + cmratio * ey_part;
+        const double uzm = uu[2] + cmratio * ez_part;
+        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+        const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
+        const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
+#ifdef EPB_FAST_MATH
+        const double tau = rcp_ge1(1.0 + taux2 + tauy2 + tauz2);
+#else
+        const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+#endif
+        const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm +
+                            2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
+        const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym +
+                            2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
+        const double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm +
+                            2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
+        uu[0] = uxp + cmratio * ex_part;
+        uu[1] = uyp + cmratio * ey_part;
+        uu[2] = uzp + cmratio * ez_part;
+        // epoch3d particles.F90:470-474
+        gamma_root(uu[0] * uu[0] + uu[1] * uu[1] + uu[2] * uu[2] + 1.0, P.dtco2, root);
+        double delta[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          delta[d] = uu[d] * root;
+          pp[d] = pp[d] + delta[d];
+        }
+        {
+          double pos[3] = {pp[0] + P.grid_min_local[0], pp[1] + P.grid_min_local[1], pp[2] + P.grid_min_local[2]};
+          double mom[3] = {P.part_mc * uu[0], P.part_mc * uu[1], P.part_mc * uu[2]};
+          touched = (pos[0] < P.bnd_min[0]) || (pos[0] > P.bnd_max[0]) || (pos[1] < P.bnd_min[1]) || (pos[1] > P.bnd_max[1]) ||
+                    (pos[2] < P.bnd_min[2]) || (pos[2] > P.bnd_max[2]);
+          dir = particle_bc<3>(P, pos, mom);
+#pragma unroll
+          for (int d = 0; d < 3; d++) { o_v[d] = pos[d]; o_v[3 + d] = mom[d]; }
+        }
+        // the cell the next push gathers this particle in, its new shape weights for the deposit
+        int c3[3];
+        double fn[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          pp[d] = pp[d] + delta[d];
+          const double crn = pp[d] * P.idx[d];
+          c3[d] = __double2int_rd(crn + 0.5);
+          fn[d] = (double)c3[d] - crn;
+          dcell[d] = c3[d] + 1 - c1[d];
+        }
+        {
+          int k3[3];
+#pragma unroll
+          for (int d = 0; d < 3; d++) k3[d] = c3[d] < 0 ? 0 : (c3[d] > P.n[d] - 1 ? P.n[d] - 1 : c3[d]);
+          ntile = ((k3[2] / B3Z) * P.tg.nt[1] + (k3[1] / B3Y)) * P.tg.nt[0] + (k3[0] / B3X);
+          // in-tile index of the next gather cell: 32 consecutive ones are 16 x 2 cells of one z plane
+          const int nin = ((k3[2] % B3Z) * B3Y + (k3[1] % B3Y)) * B3X + (k3[0] % B3X);
+          const bool stays = !touched && ntile == tile && nin == warp * 32 + lane;
+          disp = (dir == 13) ? 3 : (stays ? 0 : 1);
+          if (disp == 1 && dir < 0 && !touched && P.ic_out) {
+            // reserve the entry in the destination cell's group inbox now, look at the reply after the deposit
+            ntile = ntile * B3_WARPS + (nin >> 5);
+            nlane = nin & 31;
+            ib_slot = atomicAdd(&P.ic_out[ntile], 1);
+          }
+        }
+        if (P.deposit) {
+          const double fcx = P.kfc[0] * part_weight, fcy = P.kfc[1] * part_weight, fcz = P.kfc[2] * part_weight;
+          fj[0] = fcx * P.part_q;
+          fj[1] = fcy * P.part_q;
+          fj[2] = fcz * P.part_q;
+          const int key = ((c1[2] - oz) * JB3Y + (c1[1] - oy)) * JB3X + (c1[0] - ox);
+          if ((dcell[0] | dcell[1] | dcell[2]) != 0) {
+            extras = true;   // nearest cell moved: wider stencil, drained densely with the general loop
+            qkey = key | ((dcell[0] + 1) << 12) | ((dcell[1] + 1) << 14) | ((dcell[2] + 1) << 16);
+#pragma unroll
+            for (int d = 0; d < 3; d++) { q_f[2 * d] = fo[d]; q_f[2 * d + 1] = fn[d]; }
+          } else {
+            // epoch3d particles.F90:603-648 on the 3x3x3 stencil; the last column / row / plane of each running
+            // sum cancels structurally and is left out (54 shared adds)
+            double hx[3], hy[3], hz[3], wm, w0, wp;
+            tri_s(fn[0], wm, w0, wp); hx[0] = wm - G[0][0]; hx[1] = w0 - G[0][1]; hx[2] = wp - G[0][2];
+            tri_s(fn[1], wm, w0, wp); hy[0] = wm - G[1][0]; hy[1] = w0 - G[1][1]; hy[2] = wp - G[1][2];
+            tri_s(fn[2], wm, w0, wp); hz[0] = wm - G[2][0]; hz[1] = w0 - G[2][1]; hz[2] = wp - G[2][2];
+            const double *gx = G[0], *gy = G[1], *gz = G[2];
+            double xfac1[3], xfac2[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) { xfac1[q] = gx[q] + 0.5 * hx[q]; xfac2[q] = third * hx[q] + 0.5 * gx[q]; }
+            double jzh[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) jzh[a][b] = 0.0;
+            double *j0 = sJ + key - (JB3X * JB3Y + JB3X + 1);   // (cell - 1) along every axis
+#pragma unroll
+            for (int iz = 0; iz < 3; iz++) {
+              const double zfac1 = gz[iz] + 0.5 * hz[iz];
+              const double zfac2 = third * hz[iz] + 0.5 * gz[iz];
+              double jyh[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+              for (int iy = 0; iy < 3; iy++) {
+                const double yfac1 = gy[iy] + 0.5 * hy[iy];
+                const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+                const double hygz = hy[iy] * gz[iz];
+                const double hyhz = hy[iy] * hz[iz];
+                const double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
+                const double hzyfac1 = hz[iz] * yfac1;
+                const double hzyfac2 = hz[iz] * yfac2;
+                double jxh = 0.0;
+                double *jr = j0 + (iz * JB3Y + iy) * JB3X;
+#pragma unroll
+                for (int ix = 0; ix < 3; ix++) {
+                  const double wx = hx[ix] * yzfac;
+                  const double wy = xfac1[ix] * hygz + xfac2[ix] * hyhz;
+                  const double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
+                  jxh = jxh - fj[0] * wx;
+                  jyh[ix] = jyh[ix] - fj[1] * wy;
+                  jzh[iy][ix] = jzh[iy][ix] - fj[2] * wz;
+                  if (ix < 2) smem_add(jr + ix, jxh);
+                  if (iy < 2) smem_add(jr + JB3N + ix, jyh[ix]);
+                  if (iz < 2) smem_add(jr + 2 * JB3N + ix, jzh[iy][ix]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // ---- particles that leave this column (see push_slots_2d) ----
+    bool toM = (disp == 2) || (disp == 1 && (dir >= 0 || touched));
+    if (disp == 1 && !toM) {
+      if (ib_slot >= 0 && ib_slot < P.IC) {
+        double2 *e = reinterpret_cast<double2 *>(P.ib_out + ((size_t)ntile * (size_t)P.IC + ib_slot) * 8);
+        e[0] = make_double2(o_v[0], o_v[1]);
+        e[1] = make_double2(o_v[2], o_v[3]);
+        e[2] = make_double2(o_v[4], o_v[5]);
+        e[3] = make_double2(part_weight, __longlong_as_double((long long)nlane));
+      } else {
+        toM = true;
+      }
+    }
+    if (active && disp == 0 && wcur >= P.R) toM = true;
+    {
+      const unsigned bal = __ballot_sync(FULL, toM);
+      if (bal) {
+        int base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(P.mcount, __popc(bal));
+        base = __shfl_sync(FULL, base, __ffs(bal) - 1);
+        if (toM) {
+          const int m = base + __popc(bal & lt_mask);
+          if (m < P.mcap) {
+            P.mx[0][m] = o_v[0]; P.mx[1][m] = o_v[1]; P.mx[2][m] = o_v[2];
+            P.mp[0][m] = o_v[3]; P.mp[1][m] = o_v[4]; P.mp[2][m] = o_v[5];
+            P.mw[m] = part_weight;
+            P.mflag[m] = (disp == 2) ? 2 : (dir >= 0 ? 1 : 0);
+            if (disp == 1 && dir >= 0) {
+              const int slot = atomicAdd(&P.out_count[dir], 1);
+              if (slot < P.out_cap) P.out_idx[(size_t)dir * P.out_cap + slot] = m;
+            }
+            if (disp == 0) disp = 1;
+          } else if (disp == 1 && dir < 0 && wcur < P.R) {
+            disp = 0;
+          } else {
+            atomicOr(P.err, 1);
+            disp = 3;
+          }
+        }
+      }
+    }
+    if (active && disp == 0) {
+      double *row = col + (size_t)wcur * ROWD;
+#pragma unroll
+      for (int q = 0; q < 6; q++) row[q * 32] = o_v[q];
+      if (wcur != r || r >= my_cnt) row[6 * 32] = part_weight;
+      wcur++;
+    }
+    if (!P.deposit) continue;
+    // ---- queue the particles whose nearest cell moved ----
+    const unsigned em = __ballot_sync(FULL, extras);
+    if (em) {
+      // the queue holds Q3CAP entries: a round's extras go in in two halves if need be
+      for (int half = 0; half < 2; half++) {
+        const unsigned hm = half == 0 ? (em & 0xffffu) : (em & 0xffff0000u);
+        if (!hm) continue;
+        const int ne = __popc(hm);
+        if (qcount + ne > Q3CAP) {
+          __syncwarp();
+          drain_general_3d(P, sJ, Qd, Qk, qcount, lane, JB3X, JB3X * JB3Y, JB3N);
+          __syncwarp();
+          qcount = 0;
+        }
+        if (extras && ((hm >> lane) & 1u)) {
+          const int slot = qcount + __popc(hm & lt_mask);
+          Qk[slot] = qkey;
+#pragma unroll
+          for (int q = 0; q < 6; q++) Qd[q * Q3CAP + slot] = q_f[q];
+          Qd[6 * Q3CAP + slot] = fj[0]; Qd[7 * Q3CAP + slot] = fj[1]; Qd[8 * Q3CAP + slot] = fj[2];
+        }
+        qcount += ne;
+      }
+    }
+  }
+  if (qcount) {
+    __syncwarp();
+    drain_general_3d(P, sJ, Qd, Qk, qcount, lane, JB3X, JB3X * JB3Y, JB3N);
+  }
+  if (my_tot > 0) P.cnt[my_key] = wcur;
+  __syncthreads();
+  if (!P.deposit) return;
+  for (int q = tid; q < JB3N; q += B3_THREADS) {
+    const int lx = q % JB3X, ly = (q / JB3X) % JB3Y, lz = q / (JB3X * JB3Y);
+    const int cx = ox + lx, cy = oy + ly, cz = oz + lz;
+    const bool ok = (cx >= 1 - NG) && (cx <= P.n[0] + NG) && (cy >= 1 - NG) && (cy <= P.n[1] + NG) &&
+                    (cz >= 1 - NG) && (cz <= P.n[2] + NG);
+    if (!ok) continue;
+    const size_t o = gofs<3>(P, cx, cy, cz);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double val = sJ[f * JB3N + q];
+      if (val != 0.0) atomicAdd(P.j[f] + o, val);
+    }
+  }
+}
+
+
 inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s, long long *launches) {
   static bool attr_set = false;
   static int variant = 0;
@@ -2290,14 +2762,13 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
         static bool attr_s = false;
         static int minb = 3;
         if (!attr_s) {
-          cudaFuncSetAttribute(push_slots_2d<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
-          cudaFuncSetAttribute(push_slots_2d<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
-          const char *e = getenv("EPB_SLOTS_MINB");
-          if (e) minb = atoi(e);
+          cudaFuncSetAttribute(push_slots_2d<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
+          cudaFuncSetAttribute(push_slots_2d<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
           attr_s = true;
         }
-        if (minb == 4) push_slots_2d<8, 4><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
-        else push_slots_2d<8, 3><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+        (void)minb;
+        if (P.rowd == 32) push_slots_2d<8, 3, false><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+        else push_slots_2d<8, 3, true><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
       } else if (P.tg.layout == 1) {
         if (P.tg.T[1] == 8) push_cell_2d<8, 3><<<P.tg.ntiles, 128, pushcell_smem<8>(), s>>>(P);
         else if (variant == 4) push_cell_2d<16, 1><<<P.tg.ntiles, 256, pushcell_smem<16>(), s>>>(P);
@@ -2316,7 +2787,16 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
       attr3 = true;
     }
     if (P.tg.ntiles > 0) {
-      push_tiled_3d<<<P.tg.ntiles, P3_THREADS, PUSH3D_SMEM, s>>>(P);
+      if (P.tg.layout == 3) {
+        static bool attrb = false;
+        if (!attrb) {
+          cudaFuncSetAttribute(push_bag_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSHBAG3D_SMEM);
+          attrb = true;
+        }
+        push_bag_3d<<<P.tg.ntiles, B3_THREADS, PUSHBAG3D_SMEM, s>>>(P);
+      } else {
+        push_tiled_3d<<<P.tg.ntiles, P3_THREADS, PUSH3D_SMEM, s>>>(P);
+      }
       (*launches)++;
     }
     return;
@@ -2339,7 +2819,8 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
 inline void launch_push_m(const PushParams &P, cudaStream_t s, long long *launches) {
   int blocks = (P.mcap + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  push_generic_m<2><<<blocks, 256, 0, s>>>(P);
+  if (P.nd == 3) push_generic_m<3><<<blocks, 256, 0, s>>>(P);
+  else push_generic_m<2><<<blocks, 256, 0, s>>>(P);
   (*launches)++;
 }
 

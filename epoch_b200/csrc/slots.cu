@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int SLOT_NC = 6;   // components of a 2D particle: x, y, px, py, pz, w (layout 2 is 2D only)
+// components per particle = nd + 4 (2D: x y px py pz w; 3D: x y z px py pz w): a row block is NC x 32 doubles
 
 inline int nblk(size_t n, int cap = 148 * 16) {
   size_t b = (n + 255) / 256;
@@ -52,25 +52,29 @@ struct DeliverOp {
   int nd, nloc[3];
   double gmin[3], idx[3], ipart_mc, dtco2;
   TileGeom tg;
+  int rowd;        // doubles per row block (32 x components when the arrays are interleaved row by row, else 32)
 };
 
 // The cell the NEXT push gathers this particle in: position advanced by half a step with the stored
 // momentum, operation for operation what push_slots_2d does at the top of its round, so the particle meets
 // the lane that owns its stencil.  Clamped into the interior (a particle within half a step of the rank's
 // edge can gather in the first ghost cell: it lives in the edge column and takes the general deposit there).
-__device__ __forceinline__ int predicted_key(const DeliverOp &D, double x, double y, double px, double py, double pz) {
+__device__ __forceinline__ int predicted_key(const DeliverOp &D, const double *x, double px, double py, double pz) {
   const double ux = px * D.ipart_mc, uy = py * D.ipart_mc, uz = pz * D.ipart_mc;
   const double root = D.dtco2 / sqrt(ux * ux + uy * uy + uz * uz + 1.0);
-  double part_x = x - D.gmin[0];
-  double part_y = y - D.gmin[1];
-  part_x = part_x + ux * root;
-  part_y = part_y + uy * root;
-  int cx = __double2int_rd(part_x * D.idx[0] + 0.5);
-  int cy = __double2int_rd(part_y * D.idx[1] + 0.5);
-  cx = cx < 0 ? 0 : (cx > D.nloc[0] - 1 ? D.nloc[0] - 1 : cx);
-  cy = cy < 0 ? 0 : (cy > D.nloc[1] - 1 ? D.nloc[1] - 1 : cy);
-  const int tx = cx / D.tg.T[0], ty = cy / D.tg.T[1];
-  return (ty * D.tg.nt[0] + tx) * D.tg.cpt + (cy - ty * D.tg.T[1]) * D.tg.T[0] + (cx - tx * D.tg.T[0]);
+  const double u[3] = {ux, uy, uz};
+  int cell[3] = {0, 0, 0};
+  for (int d = 0; d < D.nd; d++) {
+    double part_x = x[d] - D.gmin[d];
+    part_x = part_x + u[d] * root;
+    int c = __double2int_rd(part_x * D.idx[d] + 0.5);
+    cell[d] = c < 0 ? 0 : (c > D.nloc[d] - 1 ? D.nloc[d] - 1 : c);
+  }
+  const int tx = cell[0] / D.tg.T[0], ty = cell[1] / D.tg.T[1], tz = cell[2] / D.tg.T[2];
+  const int tile = (tz * D.tg.nt[1] + ty) * D.tg.nt[0] + tx;
+  // a column per cell: 32 consecutive keys are 16 x 2 cells of one z plane
+  return tile * D.tg.cpt + ((cell[2] - tz * D.tg.T[2]) * D.tg.T[1] + (cell[1] - ty * D.tg.T[1])) * D.tg.T[0] +
+         (cell[0] - tx * D.tg.T[0]);
 }
 
 __global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ DeliverOp D) {
@@ -78,13 +82,14 @@ __global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ Deliver
   if (n > D.scap) n = D.scap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (D.sflag[i] == 1) continue;   // left this rank or the system
-    const double x = D.sx[0][i], y = D.sx[1][i];
+    double x[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < D.nd; d++) x[d] = D.sx[d][i];
     const double px = D.sp[0][i], py = D.sp[1][i], pz = D.sp[2][i], w = D.sw[i];
-    const int key = predicted_key(D, x, y, px, py, pz);
+    const int key = predicted_key(D, x, px, py, pz);
     const int r = atomicAdd(&D.cnt[key], 1);
     if (r < D.R) {
-      const size_t o = ((size_t)(key >> 5) * D.R + r) * (32 * SLOT_NC) + (key & 31);
-      D.ax[0][o] = x; D.ax[1][o] = y;
+      const size_t o = ((size_t)(key >> 5) * D.R + r) * D.rowd + (key & 31);
+      for (int d = 0; d < D.nd; d++) D.ax[d][o] = x[d];
       D.ap[0][o] = px; D.ap[1][o] = py; D.ap[2][o] = pz;
       D.aw[o] = w;
     } else {
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ Deliver
       atomicSub(&D.cnt[key], 1);
       const int m = atomicAdd(D.ocount, 1);
       if (m < D.ocap) {
-        D.ox[0][m] = x; D.ox[1][m] = y;
+        for (int d = 0; d < D.nd; d++) D.ox[d][m] = x[d];
         D.op[0][m] = px; D.op[1][m] = py; D.op[2][m] = pz;
         D.ow[m] = w;
         D.oflag[m] = 2;
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(256) k_deliver(const __grid_constant__ Deliver
 struct SettleOp {
   const double *ib;
   const int *ic;
-  int IC, ngroups;
+  int IC, ngroups, nd, rowd;
   double *ax[3], *ap[3], *aw;
   int *cnt;
   int R;
@@ -116,6 +121,7 @@ struct SettleOp {
   int ocap;
   int *err;
 };
+// inbox entry: nd position components, px, py, pz, w, then the destination lane (as an integer's bits) in double nd + 4
 __global__ void __launch_bounds__(256) k_settle(const __grid_constant__ SettleOp O) {
   // one warp per group inbox
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -125,20 +131,20 @@ __global__ void __launch_bounds__(256) k_settle(const __grid_constant__ SettleOp
     if (n > O.IC) n = O.IC;
     for (int j = lane; j < n; j += 32) {
       const double *e = O.ib + ((size_t)g * O.IC + j) * 8;
-      const int key = g * 32 + ((int)__double_as_longlong(e[6]) & 31);
+      const int key = g * 32 + ((int)__double_as_longlong(e[O.nd + 4]) & 31);
       const int r = atomicAdd(&O.cnt[key], 1);
       if (r < O.R) {
-        const size_t o = ((size_t)g * O.R + r) * (32 * SLOT_NC) + (key & 31);
-        O.ax[0][o] = e[0]; O.ax[1][o] = e[1];
-        O.ap[0][o] = e[2]; O.ap[1][o] = e[3]; O.ap[2][o] = e[4];
-        O.aw[o] = e[5];
+        const size_t o = ((size_t)g * O.R + r) * O.rowd + (key & 31);
+        for (int d = 0; d < O.nd; d++) O.ax[d][o] = e[d];
+        O.ap[0][o] = e[O.nd]; O.ap[1][o] = e[O.nd + 1]; O.ap[2][o] = e[O.nd + 2];
+        O.aw[o] = e[O.nd + 3];
       } else {
         atomicSub(&O.cnt[key], 1);
         const int m = atomicAdd(O.ocount, 1);
         if (m < O.ocap) {
-          O.ox[0][m] = e[0]; O.ox[1][m] = e[1];
-          O.op[0][m] = e[2]; O.op[1][m] = e[3]; O.op[2][m] = e[4];
-          O.ow[m] = e[5];
+          for (int d = 0; d < O.nd; d++) O.ox[d][m] = e[d];
+          O.op[0][m] = e[O.nd]; O.op[1][m] = e[O.nd + 1]; O.op[2][m] = e[O.nd + 2];
+          O.ow[m] = e[O.nd + 3];
           O.oflag[m] = 2;
         } else {
           atomicOr(O.err, 1);
@@ -153,7 +159,7 @@ struct CompactOp {
   const double *a[7];
   double *dst[7];
   const int *cnt, *start;
-  int R, k0, k1;
+  int R, k0, k1, rowd;
   long long base;   // start[k0]
 };
 __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ CompactOp C) {
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
     const int mx = __reduce_max_sync(0xffffffffu, c);
     for (int r = 0; r < mx; r++) {
       if (r < c) {
-        const size_t o = ((size_t)g * C.R + r) * (32 * SLOT_NC) + lane;
+        const size_t o = ((size_t)g * C.R + r) * C.rowd + lane;
 #pragma unroll
         for (int q = 0; q < 7; q++)
           if (C.a[q]) C.dst[q][st + r] = C.a[q][o];
@@ -237,7 +243,14 @@ int epb_slots_alloc(epb_handle *h, int is) {
   static const int use_inbox = getenv("EPB_SLOTS_INBOX") ? atoi(getenv("EPB_SLOTS_INBOX")) : 1;
   if (use_inbox) {
     const size_t ngroups = (size_t)h->tg.nkeys / 32;
-    S.IC = 192;
+    // entries per group inbox: a step's arrivals of 32 columns.  192 covers 64 particles per cell at ~9 % movers;
+    // runs with few particles per cell (3D: 8) get proportionally less (the mover buffer takes what does not fit)
+    {
+      long long ncell = 1;
+      for (int d = 0; d < nd; d++) ncell *= h->cfg.n[d];
+      const long long ppc = S.cap / std::max<long long>(1, ncell);
+      S.IC = (int)std::min<long long>(192, std::max<long long>(48, 4 * ppc));
+    }
     for (int b = 0; b < 2; b++) {
       EPB_CUDA(h, cudaMalloc(&S.inbox[b], ngroups * (size_t)S.IC * 8 * sizeof(double)));
       EPB_CUDA(h, cudaMalloc(&S.icnt[b], (ngroups + 1) * sizeof(int)));
@@ -266,18 +279,25 @@ static int slots_set_rows(epb_handle *h, int is, long long R) {
   SpeciesDev &S = h->sp[is];
   const int nd = h->cfg.ndims;
   const long long nkeys = h->tg.nkeys;
-  if ((size_t)R * (size_t)nkeys * SLOT_NC >= ((size_t)1 << 38)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
+  const int NC = nd + 4;
+  if ((size_t)R * (size_t)nkeys * NC >= ((size_t)1 << 38)) return epb_fail(h, EPB_ERR_CAPACITY, "species %d: slot arena too large", is);
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   // one allocation of nkeys / 32 * R row blocks of NC x 32 doubles; buf[0][q] = component q of block 0
   cudaFree(S.arena);
   S.arena = nullptr;
   for (int q = 0; q < 7; q++) S.buf[0][q] = nullptr;
-  EPB_CUDA(h, cudaMalloc(&S.arena, (size_t)R * nkeys * SLOT_NC * sizeof(double)));
+  EPB_CUDA(h, cudaMalloc(&S.arena, (size_t)R * nkeys * NC * sizeof(double)));
   {
+    // 2D default: the components as separate planes of R * nkeys doubles (measured 0.3 - 2.4 % faster than interleaved
+    // row blocks on the same box, profiles/r02_call12_*); EPB_SLOTS_ROWBLOCK=1 selects the row blocks, which 3D always uses
+    static const int rowblock = getenv("EPB_SLOTS_ROWBLOCK") ? atoi(getenv("EPB_SLOTS_ROWBLOCK")) : 0;
+    const bool rb = rowblock != 0 || nd == 3;
+    S.rowd = rb ? 32 * NC : 32;
+    const size_t cstride = rb ? 32 : (size_t)R * nkeys;
     int cq = 0;
     for (int q = 0; q < 7; q++) {
       if (q < 3 && q >= nd) continue;
-      S.buf[0][q] = S.arena + (size_t)32 * cq++;
+      S.buf[0][q] = S.arena + cstride * cq++;
     }
   }
   S.R = (int)R;
@@ -290,7 +310,7 @@ static long long slots_row_budget(epb_handle *h, int is) {
   SpeciesDev &S = h->sp[is];
   const long long nkeys = std::max<long long>(1, h->tg.nkeys);
   const long long by_cap = (2 * S.cap) / nkeys;
-  const long long by_mem = (long long)((32ull << 30) / (56ull * (unsigned long long)nkeys));
+  const long long by_mem = (long long)((32ull << 30) / (8ull * (h->cfg.ndims + 4) * (unsigned long long)nkeys));
   return std::max<long long>(8, std::max(by_cap, by_mem));
 }
 
@@ -354,6 +374,7 @@ static void fill_deliver(epb_handle *h, int is, DeliverOp &D) {
   D.ipart_mc = 1.0 / (EPB_C * S.cfg.mass);
   D.dtco2 = EPB_C * (c.dt / 2.0);
   D.tg = h->tg;
+  D.rowd = S.rowd;
 }
 
 // Insert the current mover buffer's particles into their columns; the buffers swap.
@@ -374,7 +395,7 @@ void epb_slots_views(epb_handle *h, int is, SlotView V[2]) {
   memset(V, 0, 2 * sizeof(SlotView));
   for (int q = 0; q < 7; q++) { V[0].a[q] = S.buf[0][q]; V[1].a[q] = S.mbuf[S.mcur][q]; }
   V[0].r.cnt = S.cnt;
-  V[0].r.K = SLOT_NC;
+  V[0].r.K = S.rowd / 32;
   V[0].r.R = S.R;
   V[0].r.n = S.arena_ready ? (long long)h->tg.nkeys * S.R : 0;
   V[1].r.n_dev = S.mcount + S.mcur;
@@ -402,6 +423,7 @@ void epb_slots_fill_push(epb_handle *h, int is, PushParams &P) {
   SpeciesDev &S = h->sp[is];
   P.cnt = S.cnt;
   P.R = S.R;
+  P.rowd = S.rowd;
   for (int d = 0; d < 3; d++) { P.mx[d] = S.mbuf[S.mcur][d]; P.mp[d] = S.mbuf[S.mcur][3 + d]; }
   P.mw = S.mbuf[S.mcur][6];
   P.mflag = S.mflag[S.mcur];
@@ -446,6 +468,8 @@ int epb_slots_settle(epb_handle *h, int is) {
   O.ib = S.inbox[S.icur];
   O.ic = S.icnt[S.icur];
   O.IC = S.IC;
+  O.nd = h->cfg.ndims;
+  O.rowd = S.rowd;
   O.ngroups = h->tg.nkeys / 32;
   k_settle<<<nblk((size_t)O.ngroups * 32, 148 * 8), 256, 0, h->stream>>>(O);
   h->launches++;
@@ -525,13 +549,16 @@ int epb_slots_upload(epb_handle *h, int is, int64_t n, const double *packed) {
   // densest cell (nearest cell of the stored position, io/calc_df.F90:795-796): sizes the columns
   int max_ppc = 0;
   {
-    std::vector<int> hist((size_t)c.n[0] * c.n[1], 0);
+    std::vector<int> hist((size_t)c.n[0] * c.n[1] * c.n[2], 0);
     for (int64_t i = 0; i < n; i++) {
-      int cx = (int)std::floor((packed[i * nv + 0] - c.grid_min_local[0]) / c.dx[0] + 0.5);
-      int cy = (int)std::floor((packed[i * nv + 1] - c.grid_min_local[1]) / c.dx[1] + 0.5);
-      cx = cx < 0 ? 0 : (cx > c.n[0] - 1 ? c.n[0] - 1 : cx);
-      cy = cy < 0 ? 0 : (cy > c.n[1] - 1 ? c.n[1] - 1 : cy);
-      const int v = ++hist[(size_t)cy * c.n[0] + cx];
+      size_t o = 0, str = 1;
+      for (int d = 0; d < nd; d++) {
+        int cd = (int)std::floor((packed[i * nv + d] - c.grid_min_local[d]) / c.dx[d] + 0.5);
+        cd = cd < 0 ? 0 : (cd > c.n[d] - 1 ? c.n[d] - 1 : cd);
+        o += str * (size_t)cd;
+        str *= (size_t)c.n[d];
+      }
+      const int v = ++hist[o];
       if (v > max_ppc) max_ppc = v;
     }
   }
@@ -630,6 +657,7 @@ int epb_species_iter_next(epb_handle *h, int is, SpeciesIter &I, long long CH, d
       CompactOp C;
       for (int q = 0; q < 7; q++) { C.a[q] = S.buf[0][q]; C.dst[q] = S.mbuf[stg][q]; }
       C.cnt = S.cnt; C.start = h->cell_start; C.R = S.R; C.k0 = k0; C.k1 = k1; C.base = I.hstart[k0];
+      C.rowd = S.rowd;
       k_compact<<<nblk((size_t)(k1 - k0), 148 * 8), 256, 0, h->stream>>>(C);
       h->launches++;
       for (int q = 0; q < 7; q++) st[q] = S.mbuf[stg][q];

@@ -22,7 +22,7 @@ SYMBOLS = (
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
     "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy",
-    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute", "epb_collide", "epb_collide_pairs_test",
+    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute", "epb_collide", "epb_collide_pairs_test", "epb_set_boundary_temperature",
 )
 
 
@@ -117,6 +117,7 @@ def load():
     L.epb_field_energy.argtypes = [vp, dp]
     L.epb_kinetic_energy.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.epb_calc_moment.argtypes = [vp, i32, i32, dp]
+    L.epb_set_boundary_temperature.argtypes = [vp, i32, i32, dp]
     L.epb_collide.argtypes = [vp, C.POINTER(Collisions)]
     L.epb_collide_pairs_test.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
     L.epb_redistribute.argtypes = [vp, C.POINTER(Decomp), C.POINTER(Decomp), C.POINTER(Config), C.POINTER(SpeciesCfg),

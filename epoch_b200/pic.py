@@ -295,6 +295,19 @@ class Simulation:
     def sort(self): self._chk(self.L.epb_sort(self._h))
     def synchronize(self): self._chk(self.L.epb_synchronize(self._h))
 
+    def set_boundary_temperature(self, isp: int, side: int, temp_k):
+        """species%ext_temp_<side> of a thermal particle boundary: a (3,) temperature [K] applied to the whole face, or
+        the full (3, plane) array (transverse axes with ghost cells, lower axis fastest)."""
+        plane = 1
+        for d in range(self.nd):
+            if d != side // 2:
+                plane *= self.geo["n"][d] + 2 * NG
+        t = np.asarray(temp_k, dtype=np.float64)
+        if t.size == 3:
+            t = np.repeat(t.reshape(3, 1), plane, axis=1)
+        t = np.ascontiguousarray(t.reshape(3, plane))
+        self._chk(self.L.epb_set_boundary_temperature(self._h, isp, side, t.ctypes.data))
+
     def collide(self, coll_pairs, coulomb_log: float = 0.0, use_nanbu: bool = True, coll_n_step: int = 1,
                 seed: int = 7842432):
         """particle_collisions (physics_packages/collisions.F90:86-214): coll_pairs[i][j] = user_factor of the species

@@ -149,6 +149,14 @@ int epb_field_device_ptr(epb_handle *h, int field, void **dptr);
  * expression, laser.f90:159-176). */
 int epb_set_laser_source(epb_handle *h, int side, const double *source1, const double *source2);
 
+/* Thermal particle boundaries (bc_particle = EPB_BC_THERMAL; boundary.F90:1104-1148 and its copies for the other
+ * faces): the wall temperature species%ext_temp_<side> (shared_data.F90:255-256) of boundary `side` (0 x_min .. 5
+ * z_max) as (plane, 3) doubles -- the transverse axes in axis order with their ghost cells (1-ng:n+ng), lower axis
+ * fastest, then the three momentum components; 1D: three numbers.  Must be set before the first push of a rank that
+ * owns such a wall.  Re-emission draws from counter-based per-particle streams (the reference: the rank's serial
+ * KISS stream), so parity with the reference is statistical there. */
+int epb_set_boundary_temperature(epb_handle *h, int ispecies, int side, const double *temp);
+
 /* -- the hot path ---------------------------------------------------------------- */
 /* epoch2d.F90:144-162: setup_field_boundaries snapshots, setup_bc_lists + particle_bcs,
  * efield_bcs, bfield_final_bcs with dt/2 */

@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <stdexcept>
 #include <vector>
 
 namespace {
@@ -186,6 +187,9 @@ struct Rank {
   // (planes with a unit extent along the axis; axis 0 keeps the arrays above)
   Arr snapA[3][2][6], srcA[3][2][2];
   Arr src1[2], src2[2];  // laser sources on x_min / x_max, set by the host each step
+  // thermal particle boundaries: ext_temp_x_min ... (shared_data.F90:255-256), [species][side] = (plane, 3): the two
+  // transverse axes in axis order with ghost cells, lower axis fastest; empty = never set
+  std::vector<std::vector<std::vector<double>>> ext_temp;
   std::vector<std::vector<Particle>> part;       // per species
   std::vector<std::vector<int64_t>> bnd_cand;    // boundary candidate indices per species
   Rng rng;
@@ -1234,6 +1238,60 @@ void setup_bc_lists(World &w) {
 }
 
 // boundary.F90:1029-1462 (2D); 3D/1D identical per axis.  No thermal / CPML.
+// The thermal branch of particle_bcs (boundary.F90:1104-1148 and its x_max / y / z copies; epoch3d :1496-1550,
+// epoch1d :728-750): the boundary temperature is interpolated with the triangle weights at the particle's
+// transverse position, the momentum normal to the wall is drawn from the flux distribution pointing inwards
+// (flux_momentum_from_temperature with zero drift: a Rayleigh deviate, particle_temperature.F90:409-460), the
+// other two from Maxwellians (momentum_from_temperature :388-398), all from the rank's KISS stream.
+void thermal_reemit(World &w, Rank &R, int is, Particle &cur, int d, int side, double direction) {
+  const int nd = w.nd;
+  const double mass = w.sp[is].mass;
+  double temp[3] = {0.0, 0.0, 0.0};
+  const std::vector<double> &T = R.ext_temp[is][2 * d + side];
+  int tr[2], ntr = 0;
+  for (int q = 0; q < nd; q++) if (q != d) tr[ntr++] = q;
+  size_t plane = 1;
+  for (int q = 0; q < ntr; q++) plane *= (size_t)(R.n[tr[q]] + 2 * NG);
+  if (T.empty()) throw std::runtime_error("thermal boundary without ext_temp");
+  int cell[2] = {0, 0};
+  double g[2][3] = {{0.0, 1.0, 0.0}, {0.0, 1.0, 0.0}};
+  for (int q = 0; q < ntr; q++) {
+    const double cell_r = (cur.pos[tr[q]] - R.grid_min_local[tr[q]]) / w.d[tr[q]];
+    int c = (int)std::floor(cell_r + 0.5);
+    const double cell_frac = (double)c - cell_r;
+    cell[q] = c + 1;
+    const double cf2 = cell_frac * cell_frac;
+    g[q][0] = 0.5 * (0.25 + cf2 + cell_frac);
+    g[q][1] = 0.75 - cf2;
+    g[q][2] = 0.5 * (0.25 + cf2 - cell_frac);
+  }
+  for (int i = 0; i < 3; i++) {
+    temp[i] = 0.0;
+    if (ntr == 0) {
+      temp[i] = T[i];
+    } else if (ntr == 1) {
+      for (int a = -1; a <= 1; a++) temp[i] = temp[i] + g[0][a + 1] * T[(size_t)(cell[0] + a + NG - 1) + plane * i];
+    } else {
+      const size_t e0 = (size_t)(R.n[tr[0]] + 2 * NG);
+      for (int b = -1; b <= 1; b++)
+        for (int a = -1; a <= 1; a++)
+          temp[i] = temp[i] + g[0][a + 1] * g[1][b + 1] * T[(size_t)(cell[0] + a + NG - 1) + e0 * (size_t)(cell[1] + b + NG - 1) + plane * i];
+    }
+  }
+  // the wall-normal component first (i = d), then the others in index order -- for an x wall this is the
+  // reference's x, y, z order of draws
+  auto mft = [&](double t) { return R.rng.box_muller(std::sqrt(t * kb * mass), 0.0); };
+  for (int i = 0; i < 3; i++) {
+    const int comp = i == 0 ? d : (i <= d ? i - 1 : i);
+    if (comp == d) {
+      const double mom1 = mft(temp[comp]), mom2 = mft(temp[comp]);
+      cur.p[comp] = direction * std::sqrt(mom1 * mom1 + mom2 * mom2);
+    } else {
+      cur.p[comp] = mft(temp[comp]);
+    }
+  }
+}
+
 void particle_bcs(World &w) {
   const int nd = w.nd;
   double shift[3];
@@ -1264,6 +1322,12 @@ void particle_bcs(World &w) {
               }
             } else if (bc == c_bc_periodic) {
               if (R.is_bnd[2 * d]) cur.pos[d] = part_pos - sgn * shift[d];
+            } else if (bc == c_bc_thermal) {   // boundary.F90:1104-1148
+              if (part_pos < w.min_outer[d]) {
+                bd[d] = 0;
+                thermal_reemit(w, R, (int)is, cur, d, 0, -(double)sgn);
+                cur.pos[d] = 2.0 * w.min_outer[d] - part_pos;
+              } else if (R.is_bnd[2 * d]) bd[d] = 0;
             } else {
               if (part_pos < w.min_outer[d]) { bd[d] = 0; out_of_bounds = true; }
               else if (R.is_bnd[2 * d]) bd[d] = 0;
@@ -1282,6 +1346,12 @@ void particle_bcs(World &w) {
               }
             } else if (bc == c_bc_periodic) {
               if (R.is_bnd[2 * d + 1]) cur.pos[d] = part_pos - sgn * shift[d];
+            } else if (bc == c_bc_thermal) {   // boundary.F90:1189-1233
+              if (part_pos >= w.max_outer[d]) {
+                bd[d] = 0;
+                thermal_reemit(w, R, (int)is, cur, d, 1, -(double)sgn);
+                cur.pos[d] = 2.0 * w.max_outer[d] - part_pos;
+              } else if (R.is_bnd[2 * d + 1]) bd[d] = 0;
             } else {
               if (part_pos >= w.max_outer[d]) { bd[d] = 0; out_of_bounds = true; }
               else if (R.is_bnd[2 * d + 1]) bd[d] = 0;
@@ -2160,6 +2230,14 @@ void orc_bfield_bcs(void *h, int mpi_only) { bfield_bcs(*(World *)h, mpi_only !=
 
 // calc_ppc, io/calc_df.F90:761-808 (triangle): cell = FLOOR((pos-x_grid_min_local)/dx + 0.5) + 1
 // out has the local interior shape (nx,ny,nz), x fastest; out-of-range particles are skipped
+// ext_temp_<side> of one species on one rank: (plane, 3) doubles, see Rank::ext_temp
+void orc_set_boundary_temperature(void *h, int rk, int is, int side, const double *t, int64_t n) {
+  World &w = *(World *)h;
+  Rank &R = w.r[rk];
+  if (R.ext_temp.empty()) R.ext_temp.assign(w.sp.size(), std::vector<std::vector<double>>(6));
+  R.ext_temp[is][side].assign(t, t + n);
+}
+
 void orc_cell_counts(void *h, int rk, int is, int32_t *out) {
   World &w = *(World *)h;
   Rank &R = w.r[rk];

@@ -76,6 +76,8 @@ def lib():
         L.orc_kiss.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.orc_calc_moment.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_calc_moment.restype = None
+        L.orc_set_boundary_temperature.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+        L.orc_set_boundary_temperature.restype = None
         L.orc_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.orc_collide.restype = None
         L.orc_collide_pairs_test.argtypes = [C.c_int] + [C.c_void_p] * 7
@@ -219,6 +221,19 @@ class Oracle:
     def init(self): lib().orc_init(self._h)
     def fields_half(self): lib().orc_fields_half(self._h)
     def fields_final(self): lib().orc_fields_final(self._h)
+    def set_boundary_temperature(self, rk, isp, side, temp_k):
+        """ext_temp_<side> of a thermal particle boundary on rank rk: (3,) or (3, plane) [K]"""
+        n = self.rank_info(rk)["n"]
+        plane = 1
+        for d in range(self.deck.ndims):
+            if d != side // 2:
+                plane *= n[d] + 10
+        t = np.asarray(temp_k, dtype=np.float64)
+        if t.size == 3:
+            t = np.repeat(t.reshape(3, 1), plane, axis=1)
+        t = np.ascontiguousarray(t.reshape(3, plane))
+        lib().orc_set_boundary_temperature(self._h, rk, isp, side, t.ctypes.data, t.size)
+
     def collide(self, coll_pairs, coulomb_log=0.0, use_nanbu=True, coll_n_step=1):
         """particle_collisions (physics_packages/collisions.F90:86-214) on every rank, with the rank's KISS stream"""
         n = len(self.deck.species)

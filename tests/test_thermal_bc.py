@@ -1,0 +1,138 @@
+"""Thermal particle boundaries (boundary.F90:1104-1148 and its copies for the other faces,
+particle_temperature.F90:388-460): a particle that passes the outer edge of a thermal wall comes back with a
+momentum drawn from the wall's temperature -- flux-weighted (Rayleigh) along the normal, Maxwellian along the wall.
+
+The reference draws from the rank's serial KISS stream, the device from counter-based per-particle streams, so oracle
+and device are compared on the distributions they must both produce."""
+import math
+
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from oracle import oracle as O
+from tests import decks
+
+T_WALL = 2.0e7   # K, colder than the 1e8 K plasma so that the walls visibly cool it
+
+
+def _deck(ndims, n, ppc=12):
+    # fields: clamped (a deck writes bc_x_min_field = reflect); particles: thermal walls on every face
+    dk = decks.thermal(ndims, n, ppc=ppc, temp_k=1.0e8, bc="reflect")
+    dk.species[0].bc_particle = ["thermal"] * (2 * ndims)
+    return dk
+
+
+def _walls(dk):
+    return [(s, (T_WALL, 2 * T_WALL, 3 * T_WALL)) for s in range(2 * dk.ndims)]
+
+
+def test_thermal_wall_oracle_distribution():
+    """Oracle, particle_bcs alone (2D): particles placed beyond the outer edges of thermal walls come back mirrored
+    about the edge, moving inwards, with <p_n^2> = 2 m k T_n along the wall normal (flux-weighted: a Rayleigh deviate)
+    and <p_t^2> = m k T_t along the wall; particles that have not reached the outer edge are left alone."""
+    dk = _deck(2, (16, 12), ppc=400)
+    o = O.Oracle(dk)
+    o.auto_load()
+    for side, t in _walls(dk):
+        o.set_boundary_temperature(0, 0, side, t)
+    p = o.get_particles(0, 0).copy()
+    n = p.shape[0]
+    dx = dk.dx(0)
+    rng = np.random.default_rng(4)
+    third = n // 3
+    # first third beyond x_max_outer, second beyond x_min_outer, the rest between x_max and x_max_outer (not re-emitted)
+    p[:third, 0] = dk.xmax[0] + (2.0 + rng.random(third) * 0.3) * dx
+    p[third:2 * third, 0] = dk.xmin[0] - (2.0 + rng.random(third) * 0.3) * dx
+    p[2 * third:, 0] = dk.xmax[0] + rng.random(n - 2 * third) * 1.9 * dx
+    o.set_particles(0, 0, p)
+    O.lib().orc_setup_bc_lists(o._h)
+    o.particle_bcs()
+    q = o.get_particles(0, 0)
+    assert q.shape == p.shape
+    assert np.array_equal(q[2 * third:], p[2 * third:])                      # inside the outer edge: untouched
+    hi, lo = q[:third], q[third:2 * third]
+    assert np.allclose(hi[:, 0], 2 * (dk.xmax[0] + 2 * dx) - p[:third, 0], rtol=0, atol=1e-20)
+    assert np.allclose(lo[:, 0], 2 * (dk.xmin[0] - 2 * dx) - p[third:2 * third, 0], rtol=0, atol=1e-20)
+    assert (hi[:, 2] < 0).all() and (lo[:, 2] > 0).all()
+    mk = D.m0 * D.kb
+    for h in (hi, lo):
+        assert abs(np.mean(h[:, 2] ** 2) / (2 * mk * T_WALL) - 1.0) < 0.05
+        assert abs(np.mean(h[:, 3] ** 2) / (mk * 2 * T_WALL) - 1.0) < 0.05
+        assert abs(np.mean(h[:, 4] ** 2) / (mk * 3 * T_WALL) - 1.0) < 0.05
+        assert abs(np.mean(h[:, 3])) < 0.05 * math.sqrt(mk * 2 * T_WALL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (32, 24)), (3, (16, 8, 6))])
+def test_thermal_walls_gpu(ndims, n):
+    """Device vs oracle with thermal walls on every face: identical particle counts (nobody is lost), all particles
+    inside the outer edges, and the same cooling of the plasma by the colder walls within the statistical scatter of
+    the two random streams; J and the fields stay finite and comparable in size."""
+    from epoch_b200.pic import Simulation
+    dk = _deck(ndims, n)
+    o = O.Oracle(dk)
+    o.auto_load()
+    p0 = o.get_particles(0, 0).copy()
+    sim = Simulation(dk, strict_fp=True, sort_interval=2, capacity_factor=2.0)
+    sim.upload_species(0, p0)
+    for side, t in _walls(dk):
+        o.set_boundary_temperature(0, 0, side, t)
+        sim.set_boundary_temperature(0, side, t)
+    o.init(); sim.init()
+    nsteps = 60
+    for _ in range(nsteps):
+        o.fields_half(); sim.fields_half()
+        o.push(); sim.push()
+        o.current_finish(); sim.current_finish()
+        o.fields_final(); sim.fields_final()
+    a, b = sim.download_species(0), o.get_particles(0, 0)
+    assert a.shape == b.shape == p0.shape
+    shift = 2.0                                           # x_min_outer = x_min - 2 dx (png = 3)
+    for d in range(ndims):
+        lo, hi = dk.xmin[d] - shift * dk.dx(d), dk.xmax[d] + shift * dk.dx(d)
+        for q in (a, b):
+            assert (q[:, d] >= lo - 0.5 * dk.dx(d)).all() and (q[:, d] <= hi + 0.5 * dk.dx(d)).all()
+    ke = lambda q: np.mean(np.sum(q[:, ndims:ndims + 3] ** 2, axis=1))
+    ke0, kea, keb = ke(p0), ke(a), ke(b)
+    assert kea < 0.97 * ke0 and keb < 0.97 * ke0           # the walls are colder than the plasma
+    assert abs(kea / keb - 1.0) < 0.05, (kea / ke0, keb / ke0)
+    for f in ("jx", "ex"):
+        x, y = sim.download_field(f), o.field(0, f)
+        assert np.isfinite(x).all()
+        assert 0.5 < (np.abs(x).mean() + 1e-300) / (np.abs(y).mean() + 1e-300) < 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,n", [(2, (16, 12)), (3, (16, 8, 4))])
+def test_thermal_wall_distribution_gpu(ndims, n):
+    """The device's re-emission alone: particles uploaded beyond the outer edge of the x walls are pushed (they only
+    move further out) and come back with the wall's flux-weighted / Maxwellian momenta, pointing inwards."""
+    from epoch_b200.pic import Simulation
+    dk = _deck(ndims, n, ppc=400 if ndims == 2 else 100)
+    o = O.Oracle(dk)
+    o.auto_load()
+    p = o.get_particles(0, 0).copy()
+    npart = p.shape[0]
+    dx = dk.dx(0)
+    rng = np.random.default_rng(4)
+    half = npart // 2
+    p[:half, 0] = dk.xmax[0] + (2.0 + rng.random(half) * 0.3) * dx
+    p[half:, 0] = dk.xmin[0] - (2.0 + rng.random(npart - half) * 0.3) * dx
+    p[:, ndims:ndims + 3] *= 1e-3                      # nearly at rest: the push barely moves them
+    sim = Simulation(dk, strict_fp=True, sort_interval=2, capacity_factor=2.0)
+    sim.upload_species(0, p)
+    for side, t in _walls(dk):
+        sim.set_boundary_temperature(0, side, t)
+    sim.init()
+    sim.fields_half(); sim.push()
+    q = sim.download_species(0)
+    assert q.shape == p.shape
+    hi, lo = q[q[:, 0] > 0.5 * (dk.xmin[0] + dk.xmax[0])], q[q[:, 0] < 0.5 * (dk.xmin[0] + dk.xmax[0])]
+    assert abs(hi.shape[0] - half) <= 1 and (hi[:, ndims] < 0).all() and (lo[:, ndims] > 0).all()
+    assert (hi[:, 0] <= dk.xmax[0] + 2 * dx).all() and (lo[:, 0] >= dk.xmin[0] - 2 * dx).all()
+    mk = D.m0 * D.kb
+    for h in (hi, lo):
+        assert abs(np.mean(h[:, ndims] ** 2) / (2 * mk * T_WALL) - 1.0) < 0.05
+        assert abs(np.mean(h[:, ndims + 1] ** 2) / (mk * 2 * T_WALL) - 1.0) < 0.05
+        assert abs(np.mean(h[:, ndims + 2] ** 2) / (mk * 3 * T_WALL) - 1.0) < 0.05

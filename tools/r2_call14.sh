@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, GPU call 14: 3D slot columns on 16x4x2 tiles (conflict-free half-warps, no spills) vs the sorted kernel
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_moments.py tests/test_host_replay.py -m gpu -q -x > gpurun_out/r2_call14_pytest.log 2>&1; tail -3 gpurun_out/r2_call14_pytest.log
+for cfg in "1 0" "1 1" "0 0"; do
+  set -- $cfg
+  EPB_PUSH3D_VARIANT=$1 EPB_LOAD_MIXED=$2 timeout 600 python bench.py --workload c4 --steps 6 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r2_call14_c4_v$1_m$2.json 2> gpurun_out/r2_call14_c4_v$1_m$2.err
+  python -c "
+import json
+try:
+    d=json.loads(open('gpurun_out/r2_call14_c4_v$1_m$2.json').read().strip().splitlines()[-1]); print('c4 share variant=$1 mixed=$2:', d['ms_per_step'], d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'])
+except Exception as e:
+    print('failed', e); print(open('gpurun_out/r2_call14_c4_v$1_m$2.err').read()[-1200:])"
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:push_bag_3d -s 4 -c 1 -o gpurun_out/r2_prof_bag3d_v2 -f \
+  python bench.py --workload c4 --cells 192 --steps 3 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r2_call14_prof3d.log 2>&1
