@@ -62,10 +62,10 @@ def test_product_path_fails_loudly_without_gpu():
 
 
 def test_unsupported_configuration_is_refused():
-    """thermal particle boundaries need the host RNG stream (boundary.F90:1104-1148): the
-    device path returns EPB_ERR_UNSUPPORTED instead of silently diverging."""
-    dk = decks.thermal(2, (16, 16), ppc=2, bc="periodic")
-    dk.species[0].bc_particle = ["thermal", "thermal", "periodic", "periodic"]
+    """A FIELD boundary code the device path does not implement (here: `thermal`, which efield_bcs / bfield_bcs give
+    no edge condition at all, boundary.F90:808-907) returns EPB_ERR_UNSUPPORTED instead of silently diverging.
+    (Thermal PARTICLE boundaries are implemented since round 2, tests/test_thermal_bc.py.)"""
+    dk = decks.thermal(2, (16, 16), ppc=2, bc="thermal")
     with pytest.raises(pic.EpbError, match="code 3"):
         pic.Simulation(dk)
 

@@ -104,10 +104,11 @@ def test_thermal_walls_gpu(ndims, n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ndims,n", [(2, (16, 12)), (3, (16, 8, 4))])
+@pytest.mark.parametrize("ndims,n", [(2, (16, 96)), (3, (16, 16, 12))])
 def test_thermal_wall_distribution_gpu(ndims, n):
-    """The device's re-emission alone: particles uploaded beyond the outer edge of the x walls are pushed (they only
-    move further out) and come back with the wall's flux-weighted / Maxwellian momenta, pointing inwards."""
+    """The device's re-emission alone: a tenth of a nearly cold plasma is uploaded beyond the outer edges of the x
+    walls, is pushed (it only moves further out) and comes back with the wall's flux-weighted / Maxwellian momenta,
+    pointing inwards; the rest of the plasma stays cold."""
     from epoch_b200.pic import Simulation
     dk = _deck(ndims, n, ppc=400 if ndims == 2 else 100)
     o = O.Oracle(dk)
@@ -116,9 +117,10 @@ def test_thermal_wall_distribution_gpu(ndims, n):
     npart = p.shape[0]
     dx = dk.dx(0)
     rng = np.random.default_rng(4)
-    half = npart // 2
-    p[:half, 0] = dk.xmax[0] + (2.0 + rng.random(half) * 0.3) * dx
-    p[half:, 0] = dk.xmin[0] - (2.0 + rng.random(npart - half) * 0.3) * dx
+    rng.shuffle(p, axis=0)
+    k = npart // 20
+    p[:k, 0] = dk.xmax[0] + (2.0 + rng.random(k) * 0.3) * dx
+    p[k:2 * k, 0] = dk.xmin[0] - (2.0 + rng.random(k) * 0.3) * dx
     p[:, ndims:ndims + 3] *= 1e-3                      # nearly at rest: the push barely moves them
     sim = Simulation(dk, strict_fp=True, sort_interval=2, capacity_factor=2.0)
     sim.upload_species(0, p)
@@ -128,10 +130,13 @@ def test_thermal_wall_distribution_gpu(ndims, n):
     sim.fields_half(); sim.push()
     q = sim.download_species(0)
     assert q.shape == p.shape
-    hi, lo = q[q[:, 0] > 0.5 * (dk.xmin[0] + dk.xmax[0])], q[q[:, 0] < 0.5 * (dk.xmin[0] + dk.xmax[0])]
-    assert abs(hi.shape[0] - half) <= 1 and (hi[:, ndims] < 0).all() and (lo[:, ndims] > 0).all()
-    assert (hi[:, 0] <= dk.xmax[0] + 2 * dx).all() and (lo[:, 0] >= dk.xmin[0] - 2 * dx).all()
     mk = D.m0 * D.kb
+    hot = np.sum(q[:, ndims:ndims + 3] ** 2, axis=1) > (0.02 ** 2) * mk * 1.0e8     # cold plasma: 1e-3 sqrt(m k 1e8)
+    assert hot.sum() == 2 * k
+    q = q[hot]
+    hi, lo = q[q[:, 0] > 0.5 * (dk.xmin[0] + dk.xmax[0])], q[q[:, 0] < 0.5 * (dk.xmin[0] + dk.xmax[0])]
+    assert hi.shape[0] == k and (hi[:, ndims] < 0).all() and (lo[:, ndims] > 0).all()
+    assert (hi[:, 0] <= dk.xmax[0] + 2 * dx).all() and (lo[:, 0] >= dk.xmin[0] - 2 * dx).all()
     for h in (hi, lo):
         assert abs(np.mean(h[:, ndims] ** 2) / (2 * mk * T_WALL) - 1.0) < 0.05
         assert abs(np.mean(h[:, ndims + 1] ** 2) / (mk * 2 * T_WALL) - 1.0) < 0.05
