@@ -119,8 +119,8 @@ def test_thermal_wall_distribution_gpu(ndims, n):
     rng = np.random.default_rng(4)
     rng.shuffle(p, axis=0)
     k = npart // 20
-    p[:k, 0] = dk.xmax[0] + (2.0 + rng.random(k) * 0.3) * dx
-    p[k:2 * k, 0] = dk.xmin[0] - (2.0 + rng.random(k) * 0.3) * dx
+    p[:k, 0] = dk.xmax[0] + (2.05 + rng.random(k) * 0.25) * dx
+    p[k:2 * k, 0] = dk.xmin[0] - (2.05 + rng.random(k) * 0.25) * dx
     p[:, ndims:ndims + 3] *= 1e-3                      # nearly at rest: the push barely moves them
     sim = Simulation(dk, strict_fp=True, sort_interval=2, capacity_factor=2.0)
     sim.upload_species(0, p)
