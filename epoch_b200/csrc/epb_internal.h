@@ -27,7 +27,7 @@ struct TileGeom {
   int nkeys;   // ntiles * cpt
   int layout;  // 0: cell-major inside a tile; 1 (2D): 8x4-cell warp groups, particles of a group interleaved by rank (see push_cell_2d);
                // 2 (2D, default): slot columns, one fixed-capacity column per cell, no sort at all (see push_slots_2d);
-               // 3 (3D, EPB_PUSH3D_VARIANT=1): slot columns in 3D, 16x4x2-cell tiles (push_bag_3d)
+               // 3 (3D, EPB_PUSH3D_VARIANT=1): slot columns in 3D, 16x4x3-cell tiles (push_bag_3d)
 };
 
 // Layout 2 ("slot columns", 2D): the particles of cell key k = group * 32 + lane live in rows 0 .. cnt[k]-1 of

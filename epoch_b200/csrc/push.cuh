@@ -1348,7 +1348,8 @@ constexpr int SLOT_LK = 16;   // arrivals one column takes from its group's inbo
 template <int CTY>
 constexpr size_t pushslots_smem() {
   return sizeof(double) * ((size_t)9 * CPITCH * (CTY + 2 * HALO) + (size_t)(CTY / 2) * QDBL * QCAP) +
-         sizeof(int) * ((size_t)(CTY / 2) * QCAP + 2 + (size_t)(CTY / 2) * 32) + (size_t)(CTY / 2) * 32 * SLOT_LK;
+         sizeof(int) * ((size_t)(CTY / 2) * QCAP + 2 + (size_t)(CTY / 2) * 32) + (size_t)(CTY / 2) * 32 * SLOT_LK +
+         sizeof(double) * (size_t)(CTY / 2) * 6 * 32;
 }
 
 template <int CTY, int MINB, bool RB>
@@ -1362,6 +1363,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
   int *sQk_all = reinterpret_cast<int *>(sQd_all + PUSH2D_WARPS * QDBL * QCAP);
   int *sAcnt_all = sQk_all + PUSH2D_WARPS * QCAP + 2;                               // [warp][32] arrivals per lane
   unsigned char *sAlist_all = reinterpret_cast<unsigned char *>(sAcnt_all + PUSH2D_WARPS * 32);  // [warp][32][SLOT_LK]
+  double *sPend_all = reinterpret_cast<double *>(sAlist_all + PUSH2D_WARPS * 32 * SLOT_LK);       // [warp][6][32]
   const int tile = blockIdx.x;
   const int ttx = tile % P.tg.nt[0], tty = tile / P.tg.nt[0];
   const int ox = ttx * T2X + 1 - HALO;  // cell index of shared column 0
@@ -1456,6 +1458,42 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
     }
   }
 
+  // A mover's inbox entry is written one round late: the reservation (an atomic round trip to L2) is issued in
+  // the mover's own round, its payload waits in shared memory, and the reply is only looked at when the next
+  // round starts -- a whole round of arithmetic hides the latency that 73 % of the rounds (those with at least
+  // one mover among 32 lanes) used to wait for.
+  double *sPend = sPend_all + warp * 6 * 32 + lane;
+  int pend_key = -1, pend_slot = 0;
+  auto flush_pending = [&]() {
+    if (pend_key >= 0) {
+      const double p_x = sPend[0], p_y = sPend[32], p_px = sPend[64], p_py = sPend[96], p_pz = sPend[128], p_w = sPend[160];
+      if (pend_slot < P.IC) {
+        double2 *e = reinterpret_cast<double2 *>(P.ib_out + ((size_t)(pend_key >> 5) * (size_t)P.IC + pend_slot) * 8);
+        e[0] = make_double2(p_x, p_y);
+        e[1] = make_double2(p_px, p_py);
+        e[2] = make_double2(p_pz, p_w);
+        e[3] = make_double2(__longlong_as_double((long long)(pend_key & 31)), 0.0);
+      } else {
+        // inbox full: on through the mover buffer (k_deliver finds the column); if that is full too the particle
+        // goes back into this column (rows below the read row are free) and is deposited the general way next step
+        const int m = atomicAdd(P.mcount, 1);
+        if (m < P.mcap) {
+          P.mx[0][m] = p_x; P.mx[1][m] = p_y;
+          P.mp[0][m] = p_px; P.mp[1][m] = p_py; P.mp[2][m] = p_pz;
+          P.mw[m] = p_w;
+          P.mflag[m] = 0;
+        } else if (wcur < P.R) {
+          double *row = col + (size_t)wcur * ROWD;
+          row[OX] = p_x; row[OY] = p_y; row[OPX] = p_px; row[OPY] = p_py; row[OPZ] = p_pz; row[OW] = p_w;
+          wcur++;
+        } else {
+          atomicOr(P.err, 1);
+        }
+      }
+      pend_key = -1;
+    }
+  };
+
   // software pipeline: the next row's loads are in flight while this one computes
   // (rounds 0 .. my_cnt-1 walk the column, rounds my_cnt .. my_tot-1 take the lane's arrivals from the inbox)
   double n_x = 0, n_y = 0, n_px = 0, n_py = 0, n_pz = 0, n_w = 0;
@@ -1481,15 +1519,16 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
     double part_uy = n_py * P.ipart_mc;
     double part_uz = n_pz * P.ipart_mc;
     fetch(r + 1);
+    flush_pending();
     // what happens to the particle: 0 stays in this column, 1 pushed and leaves through M (flag 0, or 1 with
-    // dir >= 0), 2 unpushed through M (flag 2), 3 deleted
+    // dir >= 0), 2 unpushed through M (flag 2), 3 deleted, 4 left through its next column's inbox (pending)
     int disp = 0, dir = -1, nkx, nky;
     bool touched = false;
     double o_x = raw_x, o_y = raw_y, o_px = raw_px, o_py = raw_py, o_pz = raw_pz;
     bool extras = false;
     // only read where `extras` (resp. a mover's disp) says they were set: deliberately not initialised, zeroing
     // them every round costs ~20 instructions
-    int key, dcx, dcy, ib_slot = -1;
+    int key, dcx, dcy;
     double q_fxo, q_fxn, q_fyo, q_fyn, fjx, fjy, fjz;
     if (active) {
       double root;
@@ -1589,11 +1628,14 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
             if (nkx + 1 == hcx && nky + 1 == hcy) {
               disp = 0;   // edge column after all
             } else if (P.ic_out) {
-              // reserve the entry in the destination group's inbox NOW; the reply is only looked at after the
-              // deposit arithmetic below, so the round trip of the atomic is hidden
+              // a mover whose next column is known goes straight into that column's group inbox: one 64-byte
+              // entry (two full sectors, no read-modify-write), consumed by the next push.  Reserve the entry
+              // now, park the payload, write it when the next round starts (flush_pending)
               const int nkey = ((nky / T2Y) * P.tg.nt[0] + (nkx >> 4)) * (T2X * T2Y) + (nky % T2Y) * T2X + (nkx & 15);
-              nkx = nkey;
-              ib_slot = atomicAdd(&P.ic_out[nkey >> 5], 1);
+              pend_key = nkey;
+              pend_slot = atomicAdd(&P.ic_out[nkey >> 5], 1);
+              sPend[0] = o_x; sPend[32] = o_y; sPend[64] = o_px; sPend[96] = o_py; sPend[128] = o_pz; sPend[160] = part_weight;
+              disp = 4;
             }
           }
         }
@@ -1663,22 +1705,9 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
         }
       }
     }
-    // ---- particles that leave this column -----------------------------------------------------------
-    // a mover whose next column is known goes straight into that column's group inbox: one 64-byte entry
-    // (two full sectors, no read-modify-write), consumed by the next push
-    bool toM = (disp == 2) || (disp == 1 && (dir >= 0 || touched));
-    if (disp == 1 && !toM) {
-      if (ib_slot >= 0 && ib_slot < P.IC) {
-        const int nkey = nkx;
-        double2 *e = reinterpret_cast<double2 *>(P.ib_out + ((size_t)(nkey >> 5) * (size_t)P.IC + ib_slot) * 8);
-        e[0] = make_double2(o_x, o_y);
-        e[1] = make_double2(o_px, o_py);
-        e[2] = make_double2(o_pz, part_weight);
-        e[3] = make_double2(__longlong_as_double((long long)(nkey & 31)), 0.0);
-      } else {
-        toM = true;   // inbox full (or switched off): through the mover buffer, k_deliver finds the column
-      }
-    }
+    // ---- particles that leave this column through the mover buffer -------------------------------------
+    // (boundary-touched or leaving particles, unpushed ones, movers when the inboxes are switched off)
+    bool toM = (disp == 2) || (disp == 1);
     if (active && disp == 0 && wcur >= P.R) toM = true;   // no row left in this column: on through M (flag 0)
     {
       const unsigned bal = __ballot_sync(FULL, toM);
@@ -1742,6 +1771,7 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
     __syncwarp();
     drain_extras(P, sJ, Qd, Qk, qcount, lane, TILE_ELEMS, TW);
   }
+  flush_pending();
   if (my_tot > 0) P.cnt[my_key] = wcur;
   // ---- flush this lane's cell sums: prefixes of particles.F90:563-571, one update per point ----
   if (P.deposit && my_tot > 0) {
@@ -2286,31 +2316,43 @@ __global__ void __launch_bounds__(P3_THREADS, 2) push_tiled_3d(const __grid_cons
 // ---------------------------------------------------------------------------
 // The slot-column store of push_slots_2d in 3D: a column per cell, rows of 7 x 32 doubles (x y z px py pz w),
 // in-place compaction by the owning lane, movers through the group inboxes, boundary-touched / leaving /
-// out-of-tile particles through the mover buffer.  One CTA (4 warps) per 16 x 4 x 2-cell tile; a warp's 32 columns
+// out-of-tile particles through the mover buffer.  One CTA (6 warps) per 16 x 4 x 3-cell tile; a warp's 32 columns
 // are 16 x 2 cells of one z plane, so a half-warp always works on 16 CONSECUTIVE cells of one x row: every shared-
 // memory access of the gather and of the deposit is then conflict-free whatever the row pitch (the first version,
 // 8 x 8 x 4 tiles with 8 x 4-cell groups, lost half of its shared-memory bandwidth to bank conflicts between the
 // rows of a half-warp: profiles/r02_ncu_push_bag_3d_v1_cells.txt).  Because a particle is always gathered inside
 // its tile (the prediction that places it is the push's own half step), the tile's E/B live in shared memory with
 // a halo of only -2 / +1 cells and the gather never touches global memory -- the step push_tiled_3d could not
-// take, since its sorted order goes stale between sorts.  Deposit: the lanes of a row sit in 32 different cells,
-// so the 54 non-cancelling values of a particle whose nearest cell is unchanged go straight to the shared J tile
-// with shared-memory adds that do not collide inside the warp -- no transposition scratch, no reduction; a
-// particle whose nearest cell moved is queued per warp and drained densely with the reference's general loop.
-constexpr int B3X = 16, B3Y = 4, B3Z = 2, B3N = B3X * B3Y * B3Z;          // tile = 128 cells = 4 warps x 32 columns
-constexpr int B3_THREADS = 128, B3_WARPS = 4;
+// take, since its sorted order goes stale between sorts.
+// Deposit.  Shared memory has no FP64 add: atomicAdd on it is an ATOMS.CAST.SPIN loop, and 54 of those per
+// particle were 36 % of the stall samples and a quarter of the instructions of the second version
+// (profiles/r02_ncu_push_bag_3d_v2_16x4x2.txt).  So every warp owns a PRIVATE 18 x 4 x 3-point J tile (its 16 x 2
+// cells and the 3x3x3 stencil's halo of one).  The lanes of a warp sit in 32 different cells, so for a particle
+// whose nearest cell is unchanged (88 % of a thermal plasma's) each of the 54 non-cancelling values of the
+// reference's loop lands on a different address in every lane: plain load / add / store, no atomics, no loops, and
+// the 54 updates are independent so their latencies overlap.  A particle whose nearest cell moved (wider stencil)
+// is queued per warp and drained densely with the reference's general loop into the CTA's J tile (halo 2, shared
+// atomics); the private tiles are added to it once at the end, and the CTA tile goes to global memory as before.
+constexpr int B3X = 16, B3Y = 4, B3Z = 3, B3N = B3X * B3Y * B3Z;          // tile = 192 cells = 6 warps x 32 columns
+constexpr int B3_THREADS = 192, B3_WARPS = 6;
 constexpr int EB3X = B3X + 3, EB3Y = B3Y + 3, EB3Z = B3Z + 3, EB3N = EB3X * EB3Y * EB3Z;   // E/B: cells origin-2 .. origin+T
 constexpr int EB3P = (EB3N + 1) & ~1;                                      // padded component stride
 constexpr int JB3H = 2, JB3X = B3X + 2 * JB3H, JB3Y = B3Y + 2 * JB3H, JB3Z = B3Z + 2 * JB3H, JB3N = JB3X * JB3Y * JB3Z;
+constexpr int PV3X = B3X + 2, PV3Y = 4, PV3Z = 3, PV3N = PV3X * PV3Y * PV3Z;   // a warp's private J tile (one component)
 constexpr size_t PUSHBAG3D_SMEM =
-    sizeof(double) * ((size_t)6 * EB3P + (size_t)3 * JB3N + (size_t)B3_WARPS * Q3DBL * Q3CAP) +
+    sizeof(double) * ((size_t)6 * EB3P + (size_t)3 * JB3N + (size_t)B3_WARPS * 3 * PV3N + (size_t)B3_WARPS * Q3DBL * Q3CAP) +
     sizeof(int) * ((size_t)B3_WARPS * Q3CAP + (size_t)B3_WARPS * 32 + 2) + (size_t)B3_WARPS * 32 * SLOT_LK;
 
+__device__ __forceinline__ void drain_edge_3d_slots(double *sJ, const double *Qd, int pk, int lane, double third);
 // drain_extras_3d's general loop (epoch3d particles.F90:603-648) on a J tile of any geometry
 __device__ __noinline__ void drain_general_3d(const PushParams &P, double *sJ, const double *Qd, const int *Qk, int n,
                                               int lane, int sy, int sz, int jt) {
   if (lane >= n) return;
   const int pk = Qk[lane];
+  if (pk & (1 << 20)) {   // a one-axis mover whose core went to the private tile: only the 21 values beyond it
+    drain_edge_3d_slots(sJ, Qd, pk, lane, P.third);
+    return;
+  }
   const int key = pk & 4095;
   const int dcell[3] = {((pk >> 12) & 3) - 1, ((pk >> 14) & 3) - 1, ((pk >> 16) & 3) - 1};
   const double fjx = Qd[6 * Q3CAP + lane], fjy = Qd[7 * Q3CAP + lane], fjz = Qd[8 * Q3CAP + lane];
@@ -2369,11 +2411,139 @@ __device__ __noinline__ void drain_general_3d(const PushParams &P, double *sJ, c
   }
 }
 
-__global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_constant__ PushParams P) {
+// One-axis movers (the nearest cell changed along exactly one axis a, by s = +-1): the 3x3x3 core around the old
+// cell is deposited inline with every other particle (deposit_core_3d); what is left of the 4x3x3 stencil -- 21
+// values -- comes here, one particle per lane, in closed form.  With g the old and h = new - old weights,
+// Esirkepov's weight of component a is w_a = h_a S(b,c), S(b,c) = g_b g_c + (h_b g_c + g_b h_c)/2 + h_b h_c/3
+// (epoch3d particles.F90:620-626 for the three components), and the current is the running sum of -fj w along
+// its own axis.  Beyond the core there is one more plane, at 2s along a, where g_a = 0 and h_a = E (the new weight
+// there):
+//   component a: its running sum has one more non-zero point than a particle that stays -- the core's third point
+//     for s = +1 (value +fj_a E S(b,c), since the weights h sum to zero), the plane at -2 for s = -1 (-fj_a E S(b,c));
+//   component b (and c alike) on the plane: w_b = h_b E (g_c/2 + h_c/3), summed along b; the last point cancels.
+__device__ __forceinline__ void drain_edge_3d_slots(double *sJ, const double *Qd, int pk, int lane, double third) {
+  const int key = pk & 4095;
+  const int d0 = ((pk >> 12) & 3) - 1, d1 = ((pk >> 14) & 3) - 1, d2 = ((pk >> 16) & 3) - 1;
+  const int a = d0 != 0 ? 0 : (d1 != 0 ? 1 : 2);
+  const int sgn = d0 + d1 + d2;                     // exactly one of them is non-zero
+  const int b = a == 2 ? 0 : a + 1, c = a == 0 ? 2 : a - 1;
+  double wm, w0, wp;
+  tri(Qd[(2 * a + 1) * Q3CAP + lane], wm, w0, wp);
+  const double E = sgn > 0 ? wp : wm;
+  double Gb[3], Hb[3], Gc[3], Hc[3];
+  tri(Qd[(2 * b) * Q3CAP + lane], Gb[0], Gb[1], Gb[2]);
+  tri(Qd[(2 * b + 1) * Q3CAP + lane], wm, w0, wp);
+  Hb[0] = wm - Gb[0]; Hb[1] = w0 - Gb[1]; Hb[2] = wp - Gb[2];
+  tri(Qd[(2 * c) * Q3CAP + lane], Gc[0], Gc[1], Gc[2]);
+  tri(Qd[(2 * c + 1) * Q3CAP + lane], wm, w0, wp);
+  Hc[0] = wm - Gc[0]; Hc[1] = w0 - Gc[1]; Hc[2] = wp - Gc[2];
+  const double va = Qd[(6 + a) * Q3CAP + lane] * E * (double)sgn;
+  const double vb = -(Qd[(6 + b) * Q3CAP + lane] * E);
+  const double vc = -(Qd[(6 + c) * Q3CAP + lane] * E);
+  const int st0 = 1, st1 = JB3X, st2 = JB3X * JB3Y;
+  const int sa = a == 0 ? st0 : (a == 1 ? st1 : st2);
+  const int sb = b == 0 ? st0 : (b == 1 ? st1 : st2);
+  const int sc = c == 0 ? st0 : (c == 1 ? st1 : st2);
+  double *ja = sJ + a * JB3N + key + (sgn > 0 ? 1 : -2) * sa;   // component a: third core point / the plane at -2
+  double *jb = sJ + b * JB3N + key + 2 * sgn * sa;               // components b, c: the plane at 2s
+  double *jc = sJ + c * JB3N + key + 2 * sgn * sa;
+  double f2b[3], f2c[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    f2b[q] = third * Hb[q] + 0.5 * Gb[q];
+    f2c[q] = third * Hc[q] + 0.5 * Gc[q];
+  }
+#pragma unroll
+  for (int ib = 0; ib < 3; ib++)
+#pragma unroll
+    for (int ic = 0; ic < 3; ic++) {
+      const double S = Gb[ib] * (Gc[ic] + 0.5 * Hc[ic]) + Hb[ib] * f2c[ic];
+      smem_add(ja + (ib - 1) * sb + (ic - 1) * sc, va * S);
+    }
+#pragma unroll
+  for (int ic = 0; ic < 3; ic++) {
+    const double t = vb * f2c[ic];
+    smem_add(jb - sb + (ic - 1) * sc, t * Hb[0]);
+    smem_add(jb + (ic - 1) * sc, t * (Hb[0] + Hb[1]));
+  }
+#pragma unroll
+  for (int ib = 0; ib < 3; ib++) {
+    const double t = vc * f2b[ib];
+    smem_add(jc + (ib - 1) * sb - sc, t * Hc[0]);
+    smem_add(jc + (ib - 1) * sb, t * (Hc[0] + Hc[1]));
+  }
+}
+
+// The 3x3x3 core of the deposit on the warp's private tile (epoch3d particles.F90:603-648 on the core): G the old
+// weights, H = (new weights on the core points) - G, cin the new weight one point below the core (a particle that
+// moved down along that axis; it enters the running sums before the core), fj the current factors.  The last
+// column / row / plane of each running sum is left out: it cancels for a particle that stays and belongs to
+// drain_edge_3d_slots for one that moved up.  Convergent code: the whole warp comes here; `on` says which lanes
+// deposit.  Lanes are different cells, so one (ix, iy) step never hits one address twice, but the lanes of
+// neighbouring cells hit the same address in DIFFERENT steps: the load / add / store of a step must be complete
+// before the next step's loads, hence the __syncwarp() between steps (an ordering point for the compiler; the
+// hardware runs a warp's shared-memory instructions in order).  Inside a step the up to eight updates (three
+// planes x three components) are independent.
+__device__ __forceinline__ void deposit_core_3d(bool on, double *pvb, const double (&G)[3][3], const double (&H)[3][3],
+                                                const double (&cin)[3], const double (&fj)[3], double third) {
+  const double *gx = G[0], *gy = G[1], *gz = G[2];
+  const double *hx = H[0], *hy = H[1], *hz = H[2];
+  double zfac1[3], zfac2[3], xz[3][3], jyh[3][3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    zfac1[q] = gz[q] + 0.5 * hz[q];
+    zfac2[q] = third * hz[q] + 0.5 * gz[q];
+  }
+  const double c0 = -(fj[0] * cin[0]), c1 = -(fj[1] * cin[1]), c2 = -(fj[2] * cin[2]);
+#pragma unroll
+  for (int ix = 0; ix < 3; ix++) {
+    const double xfac1 = gx[ix] + 0.5 * hx[ix];
+    const double xfac2 = third * hx[ix] + 0.5 * gx[ix];
+#pragma unroll
+    for (int iz = 0; iz < 3; iz++) {
+      xz[iz][ix] = xfac1 * gz[iz] + xfac2 * hz[iz];
+      jyh[iz][ix] = c1 * xz[iz][ix];
+    }
+  }
+#pragma unroll
+  for (int iy = 0; iy < 3; iy++) {
+    const double yfac1 = gy[iy] + 0.5 * hy[iy];
+    const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
+    double yz[3], jxh[3];
+#pragma unroll
+    for (int iz = 0; iz < 3; iz++) {
+      yz[iz] = gy[iy] * zfac1[iz] + hy[iy] * zfac2[iz];
+      jxh[iz] = c0 * yz[iz];
+    }
+    const double fhy = fj[1] * hy[iy];
+#pragma unroll
+    for (int ix = 0; ix < 3; ix++) {
+      const double xy = gx[ix] * yfac1 + hx[ix] * yfac2;
+      const double fhx = fj[0] * hx[ix];
+      double jzh = c2 * xy;
+      double *jr = pvb + iy * PV3X + ix;
+#pragma unroll
+      for (int iz = 0; iz < 3; iz++) {
+        jxh[iz] = jxh[iz] - fhx * yz[iz];
+        jyh[iz][ix] = jyh[iz][ix] - fhy * xz[iz][ix];
+        jzh = jzh - (fj[2] * hz[iz]) * xy;
+        if (on) {
+          if (ix < 2) jr[iz * PV3Y * PV3X] += jxh[iz];
+          if (iy < 2) jr[PV3N + iz * PV3Y * PV3X] += jyh[iz][ix];
+          if (iz < 2) jr[2 * PV3N + iz * PV3Y * PV3X] += jzh;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(B3_THREADS, 2) push_bag_3d(const __grid_constant__ PushParams P) {
   extern __shared__ double sm[];
   double *sF = sm;                                   // [6][EB3P]
   double *sJ = sF + 6 * EB3P;                        // [3][JB3N]
-  double *sQd_all = sJ + 3 * JB3N;
+  double *sPV_all = sJ + 3 * JB3N;                   // [warp][3][PV3N] private deposit tiles
+  double *sQd_all = sPV_all + B3_WARPS * 3 * PV3N;
   int *sQk_all = reinterpret_cast<int *>(sQd_all + B3_WARPS * Q3DBL * Q3CAP);
   int *sAcnt_all = sQk_all + B3_WARPS * Q3CAP;       // [warp][32] arrivals per lane
   unsigned char *sAlist_all = reinterpret_cast<unsigned char *>(sAcnt_all + B3_WARPS * 32 + 2);   // [warp][32][SLOT_LK]
@@ -2402,7 +2572,7 @@ __global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_consta
       sF[(3 + f) * EB3P + q] = ok ? __ldg(P.b[f] + o) : 0.0;
     }
   }
-  for (int q = tid; q < 3 * JB3N; q += B3_THREADS) sJ[q] = 0.0;
+  for (int q = tid; q < 3 * JB3N + B3_WARPS * 3 * PV3N; q += B3_THREADS) sJ[q] = 0.0;   // CTA tile and the private tiles
   // ---- this warp's inbox: which entries are for which lane (entry = 8 doubles, [7] = destination lane) ----
   int *sAcnt = sAcnt_all + warp * 32;
   unsigned char *sAlist = sAlist_all + warp * 32 * SLOT_LK;
@@ -2445,6 +2615,10 @@ __global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_consta
   constexpr int ROWD = 7 * 32;
   double *const col = P.x[0] + ((size_t)grp * (size_t)P.R) * ROWD + lane;
   int wcur = 0;
+  // this lane's cell (1-based) and the (cell - 1) corner of its 3x3x3 stencil in the warp's private tile, whose
+  // origin is (cx0 - 1, first row of the warp - 1, plane of the warp - 1)
+  const int hcx = cx0 + (lane & 15), hcy = cy0 + 2 * (warp & 1) + (lane >> 4), hcz = cz0 + (warp >> 1);
+  double *const pvb = sPV_all + warp * 3 * PV3N + (lane >> 4) * PV3X + (lane & 15);
 
   double n_v[7] = {0, 0, 0, 0, 0, 0, 0};   // x y z px py pz w of the next round
   auto fetch = [&](int rn) {
@@ -2467,14 +2641,16 @@ __global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_consta
     double uu[3] = {n_v[3] * P.ipart_mc, n_v[4] * P.ipart_mc, n_v[5] * P.ipart_mc};
     fetch(r + 1);
     int disp = 0, dir = -1, ib_slot = -1, ntile = 0, nlane = 0;
-    bool touched = false, extras = false;
+    bool touched = false, extras = false, inl = false;
     int qkey, dcell[3];
-    double q_f[6], fj[3];
+    double q_f[6], fj[3] = {0.0, 0.0, 0.0};
+    // inputs of the core deposit (deposit_core_3d runs in convergent code after this block)
+    double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Hd[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, cin[3] = {0, 0, 0};
     if (active) {
       double root;
       gamma_root(uu[0] * uu[0] + uu[1] * uu[1] + uu[2] * uu[2] + 1.0, P.dtco2, root);
       int c1[3], c2[3];
-      double G[3][3], H[3][3], cr[3];
+      double H[3][3], cr[3];
 #pragma unroll
       for (int d = 0; d < 3; d++) {
         pp[d] = pp[d] + uu[d] * root;
@@ -2591,62 +2767,35 @@ __global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_consta
           fj[1] = fcy * P.part_q;
           fj[2] = fcz * P.part_q;
           const int key = ((c1[2] - oz) * JB3Y + (c1[1] - oy)) * JB3X + (c1[0] - ox);
-          if ((dcell[0] | dcell[1] | dcell[2]) != 0) {
-            extras = true;   // nearest cell moved: wider stencil, drained densely with the general loop
-            qkey = key | ((dcell[0] + 1) << 12) | ((dcell[1] + 1) << 14) | ((dcell[2] + 1) << 16);
+          const int nmov = (dcell[0] != 0) + (dcell[1] != 0) + (dcell[2] != 0);
+          const bool own = c1[0] == hcx && c1[1] == hcy && c1[2] == hcz;
+          qkey = key | ((dcell[0] + 1) << 12) | ((dcell[1] + 1) << 14) | ((dcell[2] + 1) << 16);
+          if (nmov != 0 || !own) {
+            // nearest cell moved: the stencil is wider than the core.  Along one axis the part beyond the core is
+            // 21 values (drain_edge_3d_slots, bit 20 of the key); anything else (0.5 % of a thermal plasma's
+            // particles, or a particle that is not in this lane's cell) takes the reference's general loop.
+            extras = true;
 #pragma unroll
             for (int d = 0; d < 3; d++) { q_f[2 * d] = fo[d]; q_f[2 * d + 1] = fn[d]; }
-          } else {
-            // epoch3d particles.F90:603-648 on the 3x3x3 stencil; the last column / row / plane of each running
-            // sum cancels structurally and is left out (54 shared adds)
-            double hx[3], hy[3], hz[3], wm, w0, wp;
-            tri_s(fn[0], wm, w0, wp); hx[0] = wm - G[0][0]; hx[1] = w0 - G[0][1]; hx[2] = wp - G[0][2];
-            tri_s(fn[1], wm, w0, wp); hy[0] = wm - G[1][0]; hy[1] = w0 - G[1][1]; hy[2] = wp - G[1][2];
-            tri_s(fn[2], wm, w0, wp); hz[0] = wm - G[2][0]; hz[1] = w0 - G[2][1]; hz[2] = wp - G[2][2];
-            const double *gx = G[0], *gy = G[1], *gz = G[2];
-            double xfac1[3], xfac2[3];
+          }
+          if (nmov <= 1 && own) {
+            inl = true;
+            if (nmov == 1) qkey |= 1 << 20;
+            // new weights on the core points (shifted by the move), the carry from the point below the core
 #pragma unroll
-            for (int q = 0; q < 3; q++) { xfac1[q] = gx[q] + 0.5 * hx[q]; xfac2[q] = third * hx[q] + 0.5 * gx[q]; }
-            double jzh[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-              for (int b = 0; b < 3; b++) jzh[a][b] = 0.0;
-            double *j0 = sJ + key - (JB3X * JB3Y + JB3X + 1);   // (cell - 1) along every axis
-#pragma unroll
-            for (int iz = 0; iz < 3; iz++) {
-              const double zfac1 = gz[iz] + 0.5 * hz[iz];
-              const double zfac2 = third * hz[iz] + 0.5 * gz[iz];
-              double jyh[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-              for (int iy = 0; iy < 3; iy++) {
-                const double yfac1 = gy[iy] + 0.5 * hy[iy];
-                const double yfac2 = third * hy[iy] + 0.5 * gy[iy];
-                const double hygz = hy[iy] * gz[iz];
-                const double hyhz = hy[iy] * hz[iz];
-                const double yzfac = gy[iy] * zfac1 + hy[iy] * zfac2;
-                const double hzyfac1 = hz[iz] * yfac1;
-                const double hzyfac2 = hz[iz] * yfac2;
-                double jxh = 0.0;
-                double *jr = j0 + (iz * JB3Y + iy) * JB3X;
-#pragma unroll
-                for (int ix = 0; ix < 3; ix++) {
-                  const double wx = hx[ix] * yzfac;
-                  const double wy = xfac1[ix] * hygz + xfac2[ix] * hyhz;
-                  const double wz = gx[ix] * hzyfac1 + hx[ix] * hzyfac2;
-                  jxh = jxh - fj[0] * wx;
-                  jyh[ix] = jyh[ix] - fj[1] * wy;
-                  jzh[iy][ix] = jzh[iy][ix] - fj[2] * wz;
-                  if (ix < 2) smem_add(jr + ix, jxh);
-                  if (iy < 2) smem_add(jr + JB3N + ix, jyh[ix]);
-                  if (iz < 2) smem_add(jr + 2 * JB3N + ix, jzh[iy][ix]);
-                }
-              }
+            for (int d = 0; d < 3; d++) {
+              double wm, w0, wp;
+              tri_s(fn[d], wm, w0, wp);
+              Hd[d][0] = (dcell[d] == 0 ? wm : dcell[d] > 0 ? 0.0 : w0) - G[d][0];
+              Hd[d][1] = (dcell[d] == 0 ? w0 : dcell[d] > 0 ? wm : wp) - G[d][1];
+              Hd[d][2] = (dcell[d] == 0 ? wp : dcell[d] > 0 ? w0 : 0.0) - G[d][2];
+              cin[d] = dcell[d] < 0 ? wm : 0.0;
             }
           }
         }
       }
     }
+    if (P.deposit && __any_sync(FULL, inl)) deposit_core_3d(inl, pvb, G, Hd, cin, fj, third);
     // ---- particles that leave this column (see push_slots_2d) ----
     bool toM = (disp == 2) || (disp == 1 && (dir >= 0 || touched));
     if (disp == 1 && !toM) {
@@ -2726,6 +2875,22 @@ __global__ void __launch_bounds__(B3_THREADS, 3) push_bag_3d(const __grid_consta
     drain_general_3d(P, sJ, Qd, Qk, qcount, lane, JB3X, JB3X * JB3Y, JB3N);
   }
   if (my_tot > 0) P.cnt[my_key] = wcur;
+  if (P.deposit && maxcnt > 0) {
+    // the warp's private tile joins the CTA tile: point (px, py, pz) of it is CTA-tile point
+    // (px + JB3H - 1, py + first row of the warp + JB3H - 1, pz + plane of the warp + JB3H - 1)
+    __syncwarp();
+    const double *pv = sPV_all + warp * 3 * PV3N;
+    const int jb = (((warp >> 1) + JB3H - 1) * JB3Y + 2 * (warp & 1) + JB3H - 1) * JB3X + JB3H - 1;
+    for (int q = lane; q < PV3N; q += 32) {
+      const int px = q % PV3X, py = (q / PV3X) % PV3Y, pz = q / (PV3X * PV3Y);
+      const int o = jb + (pz * JB3Y + py) * JB3X + px;
+#pragma unroll
+      for (int f = 0; f < 3; f++) {
+        const double v = pv[f * PV3N + q];
+        if (v != 0.0) smem_add(&sJ[f * JB3N + o], v);
+      }
+    }
+  }
   __syncthreads();
   if (!P.deposit) return;
   for (int q = tid; q < JB3N; q += B3_THREADS) {

@@ -222,7 +222,7 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   static const int v3 = getenv("EPB_PUSH3D_VARIANT") ? atoi(getenv("EPB_PUSH3D_VARIANT")) : 1;
   if (nd == 3 && v3 != 0 && !cfg.hc_push) {
     tg.layout = 3;
-    T[0] = 16; T[1] = 4; T[2] = 2;   // must match B3X / B3Y / B3Z in push.cuh (half-warp = 16 consecutive cells of a row)
+    T[0] = 16; T[1] = 4; T[2] = 3;   // must match B3X / B3Y / B3Z in push.cuh (half-warp = 16 consecutive cells of a row)
   }
   tg.cpt = 1;
   tg.ntiles = 1;
