@@ -1244,7 +1244,7 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
   P.out_idx = h->out_idx;
   P.out_cap = h->out_cap;
   P.gone = S.gone;
-  static int experiment = getenv("EPB_PUSH_EXPERIMENT") ? atoi(getenv("EPB_PUSH_EXPERIMENT")) : 0;
+  static int experiment = epb_env("EPB_PUSH_EXPERIMENT") ? atoi(epb_env("EPB_PUSH_EXPERIMENT")) : 0;
   P.experiment = experiment;
 }
 
@@ -1299,6 +1299,8 @@ int epb_abi_info(int32_t out[4]) {
 const char *epb_last_error(const epb_handle *h) { return h ? h->err.c_str() : "null handle"; }
 int64_t epb_launch_count(const epb_handle *h) { return h ? h->launches : 0; }
 
+static int create_device_state(epb_handle *h, const epb_config *cfg, const epb_species *species);
+
 int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **out) {
   if (!cfg || !out) return EPB_ERR_ARG;
   *out = nullptr;
@@ -1330,14 +1332,27 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
         return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "particle boundary code %d not implemented on the device path", b);
     }
   }
+  // everything that can fail after the handle exists runs in create_device_state, so that a failure there
+  // (out of memory, a CUDA error) releases what was already allocated instead of leaking a half-built handle
   epb_handle *h = new epb_handle;
   h->cfg = *cfg;
+  const int rc = create_device_state(h, cfg, species);
+  if (rc != EPB_OK) {
+    fprintf(stderr, "epoch_b200: epb_create failed: %s\n", h->err.c_str());
+    epb_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return EPB_OK;
+}
+
+static int create_device_state(epb_handle *h, const epb_config *cfg, const epb_species *species) {
   {  // c_bc_mixed: do the species disagree on a particle boundary?
     auto norm = [](int b) { return (b == EPB_BC_REFLECT || b == EPB_BC_PERIODIC) ? b : EPB_BC_OPEN; };
     for (int s = 1; s < cfg->n_species; s++)
       for (int i = 0; i < 2 * cfg->ndims; i++)
         if (norm(species[s].bc_particle[i]) != norm(species[0].bc_particle[i])) h->bc_mixed = true;
-    if (cfg->n_species > 0 && getenv("EPB_FORCE_MIXED") && atoi(getenv("EPB_FORCE_MIXED"))) h->bc_mixed = true;
+    if (cfg->n_species > 0 && epb_env("EPB_FORCE_MIXED") && atoi(epb_env("EPB_FORCE_MIXED"))) h->bc_mixed = true;
   }
   const int nd = cfg->ndims;
   h->fsize = 1;
@@ -1435,7 +1450,6 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   EPB_CUDA(h, cudaEventCreate(&h->ev0));
   EPB_CUDA(h, cudaEventCreate(&h->ev1));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  *out = h;
   return EPB_OK;
 }
 
@@ -1447,7 +1461,7 @@ int epb_destroy(epb_handle *h) {
   for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
-  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage); cudaFree(h->coll_work);
+  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage); cudaFree(h->coll_work); cudaFree(h->prof_scratch);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
     // slot columns first: their buf[0][*] point INTO the arena and are cleared by epb_slots_free
@@ -1577,9 +1591,12 @@ int epb_species_count(epb_handle *h, int is, int64_t *n) {
   return EPB_OK;
 }
 
-int epb_load_uniform(epb_handle *h, int is, int32_t ppc, double density, const double temp_k[3],
+int epb_load_uniform(epb_handle *h, int is, int32_t ppc_arg, double density, const double temp_k[3],
                      const double drift[3], uint64_t seed) {
-  if (!h || is < 0 || is >= (int)h->sp.size()) return EPB_ERR_ARG;
+  if (!h || is < 0 || is >= (int)h->sp.size() || ppc_arg == 0) return EPB_ERR_ARG;
+  // ppc < 0: |ppc| particles per cell on average, every particle's cell drawn at random (Poisson counts: the state a
+  // thermal plasma relaxes to, against the loader's exactly |ppc| per cell)
+  const int32_t ppc = ppc_arg < 0 ? -ppc_arg : ppc_arg;
   const epb_config &c = h->cfg;
   SpeciesDev &S = h->sp[is];
   long long total = (long long)c.n[0] * c.n[1] * c.n[2] * ppc;
@@ -1602,7 +1619,7 @@ int epb_load_uniform(epb_handle *h, int is, int32_t ppc, double density, const d
   L.ppc = ppc;
   L.i0 = 0;
   L.i1 = total;
-  L.mixed = getenv("EPB_LOAD_MIXED") ? atoi(getenv("EPB_LOAD_MIXED")) : 0;
+  L.mixed = ppc_arg < 0 ? 1 : (epb_env("EPB_LOAD_MIXED") ? atoi(epb_env("EPB_LOAD_MIXED")) : 0);
   double vol = 1.0;
   for (int d = 0; d < c.ndims; d++) vol *= c.dx[d];
   L.weight = density * vol / ppc;
@@ -1886,14 +1903,14 @@ int epb_push(epb_handle *h) {
       if (rc) return rc;
       continue;
     }
-    static const int no3d = getenv("EPB_NO_TILED_3D") ? atoi(getenv("EPB_NO_TILED_3D")) : 0;
+    static const int no3d = epb_env("EPB_NO_TILED_3D") ? atoi(epb_env("EPB_NO_TILED_3D")) : 0;
     // HC_PUSH builds of the reference: the tiled kernels hold the Boris gamma only, every particle takes
     // push_generic<ND, true>
     const bool tiled = !c.hc_push && ((c.ndims == 2) || (c.ndims == 3 && !no3d));
     long long sorted = S.n_sorted < S.n ? S.n_sorted : S.n;
     // layout 1: the last push before a sort also records every particle's place in the next
     // order, so that sort needs neither a key pass nor rank atomics (sort.cu)
-    static const int no_emit = getenv("EPB_NO_EMIT") ? atoi(getenv("EPB_NO_EMIT")) : 0;
+    static const int no_emit = epb_env("EPB_NO_EMIT") ? atoi(epb_env("EPB_NO_EMIT")) : 0;
     S.info_valid = false;
     if (tiled && sorted > 0 && h->tg.layout == 1 && P.deposit && !no_emit && h->pushes_since_sort + 1 >= c.sort_interval) {
       const size_t kb = ((size_t)h->tg.nkeys + 1) * sizeof(int);

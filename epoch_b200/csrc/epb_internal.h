@@ -185,6 +185,9 @@ struct SpeciesDev {
 // opaque storage of a CUtensorMap (128 bytes, 64-byte aligned), see fdtd_tma.cu
 struct alignas(64) TmapStorage { unsigned char b[128]; };
 
+// push_per_field (shared_data.F90:821): the weight of a particle against a cell in the balancer's load; deck.PUSH_PER_FIELD
+constexpr int EPB_PUSH_PER_FIELD = 5;
+
 struct epb_handle {
   epb_config cfg;
   std::vector<SpeciesDev> sp;
@@ -200,6 +203,8 @@ struct epb_handle {
   size_t planeA[3] = {0, 0, 0};
   double *snapA[3] = {nullptr, nullptr, nullptr};  // [2 sides][6 fields][planeA]
   double *srcA[3] = {nullptr, nullptr, nullptr};   // [2 sides][2][planeA]
+  unsigned long long *prof_scratch = nullptr;   // epb_load_profile: local + summed histogram
+  size_t prof_cap = 0;
   TileGeom tg;
   int *cell_count = nullptr;    // nkeys + 1
   int *cell_start = nullptr;    // nkeys + 1
@@ -249,9 +254,16 @@ struct epb_handle {
 // rank-interleaved sorted layout (emitted sort every 2 steps), 168 registers; 2 / 4 = the same kernel on
 // 16x16-cell tiles with 128 / 255 registers; 0 = push_tiled_2d (lane per particle, 27-value
 // transposed reduction, cell-major layout); 1 = its 21-value form.
+// Every kernel-selection / experiment switch of the library is read through epb_env: the variables are honoured
+// only when EPB_DEBUG is set to a non-zero value, so a stray variable in a production host's environment cannot
+// change kernels or particle loading.  (EPB_DEBUG=1 EPB_PUSH_VARIANT=3 ... is how the A/B lines under profiles/ were made.)
+inline const char *epb_env(const char *name) {
+  static const int debug = getenv("EPB_DEBUG") ? atoi(getenv("EPB_DEBUG")) : 0;
+  return debug ? getenv(name) : nullptr;
+}
 inline int epb_push_variant() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 5; }
+  if (v < 0) { const char *e = epb_env("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 5; }
   return v;
 }
 

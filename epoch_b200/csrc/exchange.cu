@@ -217,9 +217,17 @@ extern "C" int epb_load_profile(epb_handle *h, int axis, int64_t *load) {
   if (!h || !load || axis < 0 || axis >= h->cfg.ndims) return EPB_ERR_ARG;
   const epb_config &c = h->cfg;
   const int len = c.n_global[axis] + 2 * NG;
-  unsigned long long *d = nullptr;
-  EPB_CUDA(h, cudaMalloc(&d, 2 * (size_t)len * sizeof(unsigned long long)));
-  cudaMemsetAsync(d, 0, 2 * (size_t)len * sizeof(unsigned long long), h->stream);
+  // handle-owned scratch (two histograms: local and summed), grown on demand and released by epb_destroy
+  if (h->prof_cap < 2 * (size_t)len) {
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->prof_scratch);
+    h->prof_scratch = nullptr;
+    h->prof_cap = 0;
+    EPB_CUDA(h, cudaMalloc(&h->prof_scratch, 2 * (size_t)len * sizeof(unsigned long long)));
+    h->prof_cap = 2 * (size_t)len;
+  }
+  unsigned long long *d = h->prof_scratch;
+  EPB_CUDA(h, cudaMemsetAsync(d, 0, 2 * (size_t)len * sizeof(unsigned long long), h->stream));
   const double grid_min = c.gmin[axis] + c.dx[axis] / 2.0;   // x_grid_min (setup.F90:169,180; no CPML)
   for (size_t is = 0; is < h->sp.size(); is++) {
     SlotView V[2];
@@ -229,22 +237,22 @@ extern "C" int epb_load_profile(epb_handle *h, int axis, int64_t *load) {
       h->launches++;
     }
   }
+  EPB_CUDA(h, cudaGetLastError());
   unsigned long long *res = d;
   if (c.nranks > 1 && h->nccl) {   // MPI_ALLREDUCE(MPI_IN_PLACE, load, st, MPI_INTEGER8, MPI_SUM)
     ncclResult_t r = ncclAllReduce(d, d + len, len, ncclInt64, ncclSum, (ncclComm_t)h->nccl, h->stream);
-    if (r != ncclSuccess) { cudaFree(d); return epb_fail(h, EPB_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r)); }
+    if (r != ncclSuccess) return epb_fail(h, EPB_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r));
     res = d + len;
   }
   cudaError_t e = cudaMemcpyAsync(load, res, (size_t)len * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d);
   if (e != cudaSuccess) return epb_fail(h, EPB_ERR_CUDA, "epb_load_profile: %s", cudaGetErrorString(e));
   // load = push_per_field * load; load(ng+1:st-ng) += cells of one slab across the other axes
   int64_t other = 1;
   for (int q = 0; q < c.ndims; q++)
     if (q != axis) other *= c.n_global[q];
   for (int i = 0; i < len; i++) {
-    load[i] *= 5;   // push_per_field, shared_data.F90:821
+    load[i] *= EPB_PUSH_PER_FIELD;   // shared_data.F90:821
     if (i >= NG && i < len - NG) load[i] += other;
   }
   return EPB_OK;

@@ -186,7 +186,7 @@ bool epb_fdtd_tma_setup(epb_handle *h) {
   h->tma_ok = false;
   const int nd = h->cfg.ndims;
   if (nd < 2) return false;
-  if (getenv("EPB_NO_TMA")) return false;
+  if (epb_env("EPB_NO_TMA")) return false;
   if ((h->sz[0] * sizeof(double)) % 16 != 0) return false;
   if (nd == 3 && ((size_t)h->sz[0] * h->sz[1] * sizeof(double)) % 16 != 0) return false;
   void *fn = nullptr;

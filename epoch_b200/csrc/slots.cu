@@ -240,7 +240,7 @@ int epb_slots_alloc(epb_handle *h, int is) {
     EPB_CUDA(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
   }
   // group inboxes (EPB_SLOTS_INBOX=0 sends every mover through the mover buffer and k_deliver instead)
-  static const int use_inbox = getenv("EPB_SLOTS_INBOX") ? atoi(getenv("EPB_SLOTS_INBOX")) : 1;
+  static const int use_inbox = epb_env("EPB_SLOTS_INBOX") ? atoi(epb_env("EPB_SLOTS_INBOX")) : 1;
   if (use_inbox) {
     const size_t ngroups = (size_t)h->tg.nkeys / 32;
     // entries per group inbox: a step's arrivals of 32 columns.  192 covers 64 particles per cell at ~9 % movers;
@@ -290,7 +290,7 @@ static int slots_set_rows(epb_handle *h, int is, long long R) {
   {
     // 2D default: the components as separate planes of R * nkeys doubles (measured 0.3 - 2.4 % faster than interleaved
     // row blocks on the same box, profiles/r02_call12_*); EPB_SLOTS_ROWBLOCK=1 selects the row blocks, which 3D always uses
-    static const int rowblock = getenv("EPB_SLOTS_ROWBLOCK") ? atoi(getenv("EPB_SLOTS_ROWBLOCK")) : 0;
+    static const int rowblock = epb_env("EPB_SLOTS_ROWBLOCK") ? atoi(epb_env("EPB_SLOTS_ROWBLOCK")) : 0;
     const bool rb = rowblock != 0 || nd == 3;
     S.rowd = rb ? 32 * NC : 32;
     const size_t cstride = rb ? 32 : (size_t)R * nkeys;

@@ -219,7 +219,7 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   // slot columns; the Higuera-Cary build pushes every particle through the generic kernel (contiguous layout)
   if (nd == 2 && variant == 5) tg.layout = cfg.hc_push ? 0 : 2;
   // 3D: tile bags (layout 3, push_bag_3d) unless EPB_PUSH3D_VARIANT=0 asks for the sorted layout of push_tiled_3d
-  static const int v3 = getenv("EPB_PUSH3D_VARIANT") ? atoi(getenv("EPB_PUSH3D_VARIANT")) : 1;
+  static const int v3 = epb_env("EPB_PUSH3D_VARIANT") ? atoi(epb_env("EPB_PUSH3D_VARIANT")) : 1;
   if (nd == 3 && v3 != 0 && !cfg.hc_push) {
     tg.layout = 3;
     T[0] = 16; T[1] = 4; T[2] = 3;   // must match B3X / B3Y / B3Z in push.cuh (half-warp = 16 consecutive cells of a row)
@@ -316,7 +316,7 @@ int epb_sort_species_emitted(epb_handle *h, int is) {
     // the gather itself is left to the next push of this species (PushParams::perm), which reads
     // the old order through perm and writes the new one: no separate 100 B/particle pass
     S.pending_perm = true;
-    static const int no_fuse = getenv("EPB_NO_FUSED_GATHER") ? atoi(getenv("EPB_NO_FUSED_GATHER")) : 0;
+    static const int no_fuse = epb_env("EPB_NO_FUSED_GATHER") ? atoi(epb_env("EPB_NO_FUSED_GATHER")) : 0;
     if (no_fuse) {
       int rc = epb_apply_pending_perm(h, is);
       if (rc) return rc;
@@ -353,7 +353,7 @@ int epb_sort_species(epb_handle *h, int is) {
     K.tg = h->tg;
     K.key = S.key;
     K.count = h->cell_count;
-    static const int predict_env = getenv("EPB_SORT_PREDICT") ? atoi(getenv("EPB_SORT_PREDICT")) : 0;
+    static const int predict_env = epb_env("EPB_SORT_PREDICT") ? atoi(epb_env("EPB_SORT_PREDICT")) : 0;
     K.predict = (h->tg.layout == 1) || predict_env;
     for (int d = 0; d < 3; d++) {
       K.p[d] = S.buf[S.cur][3 + d];

@@ -263,11 +263,14 @@ class Simulation:
         self._chk(self.L.epb_cell_counts(self._h, isp, out.ctypes.data))
         return out
 
-    def load_uniform(self, isp: int, seed: int = 12345):
+    def load_uniform(self, isp: int, seed: int = 12345, mixed: bool = False):
+        """Device-side loader.  mixed: every particle's cell is drawn at random (Poisson counts per cell, the state
+        a thermal plasma relaxes to) instead of exactly npart_per_cell per cell."""
         s = self.deck.species[isp]
         t = (C.c_double * 3)(*s.temp)
         d = (C.c_double * 3)(*s.drift)
-        self._chk(self.L.epb_load_uniform(self._h, isp, int(s.npart_per_cell), s.density, t, d, seed))
+        ppc = int(s.npart_per_cell)
+        self._chk(self.L.epb_load_uniform(self._h, isp, -ppc if mixed else ppc, s.density, t, d, seed))
 
     def set_comm(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

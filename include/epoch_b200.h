@@ -133,7 +133,9 @@ int epb_download_species(epb_handle *h, int ispecies, int64_t n, double *packed)
 int epb_species_count(epb_handle *h, int ispecies, int64_t *n);   /* attached_list%count */
 /* device-side loader for the bench: npart_per_cell particles per cell, uniform
  * density, Maxwellian momenta (stands in for auto_load, helper.F90:95, whose
- * KISS stream is host-serial; parity runs upload the oracle's particles instead) */
+ * KISS stream is host-serial; parity runs upload the oracle's particles instead).
+ * npart_per_cell < 0: |npart_per_cell| per cell ON AVERAGE, each particle's cell drawn at random (Poisson counts
+ * per cell: the state a thermal plasma relaxes to; bench.py's "mixed_state" figure) */
 int epb_load_uniform(epb_handle *h, int ispecies, int32_t npart_per_cell, double density,
                      const double temp_k[3], const double drift[3], uint64_t seed);
 /* particles-per-cell as calc_ppc defines it (io/calc_df.F90:761-808); out(nx,ny,nz) int32 */
