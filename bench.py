@@ -358,37 +358,6 @@ def run_c3(args, world, rank, local_rank, parity, torch, dist):
     ms_b, wall_b, launches_b, push_ms, push_n = timed(args.steps)
     clocks = sampler.stop() if rank == 0 else None
     n_end = sum(counts())
-    # ---- the same steps from the relaxed state ("mixed_state") --------------------------
-    # EPOCH's loader puts exactly ppc particles in every cell; a thermal plasma relaxes to Poisson counts, where a
-    # warp runs as many rounds as its fullest column.  The figure above is the deck as loaded (what the reference arm
-    # runs too); this one is the long-time state of the same deck, device-timed the same way.
-    sim.close()   # give the device memory back (also before the compiled host attaches its own state)
-    mixed_state = None
-    if not args.no_mixed:
-        msim = make_sim(True)
-        for _ in range(3):
-            msim.step()
-        msim.push_kernel_ms(reset=1)
-        barrier()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        msteps = min(args.steps, 6)
-        with torch.cuda.stream(stream):
-            m0.record(stream)
-            for _ in range(msteps):
-                msim.step()
-            m1.record(stream)
-        barrier()
-        mms = m0.elapsed_time(m1)
-        mk_ms, _ = msim.push_kernel_ms(reset=2)
-        mtot = msim.global_count(0)
-        if world > 1:
-            t = torch.tensor([mms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            mms = float(t.item())
-        mixed_state = {"value": mtot * msteps / (mms * 1e-3), "unit": UNIT, "ms_per_step": mms / msteps, "steps": msteps,
-                       "kernel_ms": mk_ms, "load": "every particle's cell drawn at random (Poisson counts per cell)"}
-        msim.close()
-
     if rank == 0:
         peaks = {}
         try:
@@ -591,12 +560,14 @@ def main():
     ny1 = (sim.geo["n"][1] + 1) * (sim.geo["n"][2] + 1 if args.workload == "c4" else 1)
     src = torch.zeros(2, ny1, dtype=torch.float64).pin_memory()
     ey_host = torch.empty(sim.shape, dtype=torch.float64).pin_memory()
+    scal = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(2)]
     h2d = 2 * 2 * ny1 * 8
-    d2h = ey_host.numel() * 8 + 8 + 16
+    d2h = ey_host.numel() * 8 + 4 * 8
     # one untimed pass of the same calls: first-use allocations (dump staging buffer, copy stream, scratch of the
-    # count reduction) belong to start-up, not to a step
-    sim.global_count(0)
-    sim.field_energy()
+    # reductions, the source planes' staging ring) belong to start-up, not to a step
+    for side in (0, 1):
+        sim.L.epb_set_laser_source(sim._h, side, src[0].data_ptr(), src[1].data_ptr())
+    sim.wait_scalars(sim.step_scalars_async(scal[0].data_ptr()))
     sim.download_field_async("ey", ey_host.data_ptr())
     sim.wait_downloads()
     barrier()
@@ -610,25 +581,36 @@ def main():
         prof[name] = prof.get(name, 0.0) + time.perf_counter() - t1
         return r
 
+    # The host runs one step ahead of the device, as a production host would: it hands over step k's source planes
+    # and enqueues step k, its scalar diagnostics and its Ey dump, and only then waits for what step k-1 sent back
+    # (counts and energies in page-locked memory, the Ey array of the previous dump).  Every step's inputs and
+    # results cross the bus inside the clock; nothing is skipped, the device just never waits for the host.
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    tickets = []
+    results = []
+    for k in range(args.steps):
         for side in (0, 1):
             timed_call("set_laser_source", sim.L.epb_set_laser_source, sim._h, side, src[0].data_ptr(), src[1].data_ptr())
         timed_call("step (enqueue)", sim.step)
-        if prof is not None:
-            timed_call("synchronize (the step on the GPU)", sim.synchronize)
-        timed_call("global_count", sim.global_count, 0)
-        timed_call("field_energy", sim.field_energy)
-        # the Ey dump of this step leaves the device while the next step runs (device-side snapshot +
-        # second stream); the host owns the previous step's array from here on
-        if os.environ.get("EPB_BENCH_SYNC_DUMP"):
+        tickets.append(timed_call("step_scalars_async", sim.step_scalars_async, scal[k % 2].data_ptr()))
+        if os.environ.get("EPB_BENCH_NO_DUMP"):      # diagnosis only: what the Ey dump costs
+            pass
+        elif os.environ.get("EPB_BENCH_SYNC_DUMP"):
             timed_call("download_field", sim.download_field_into, "ey", ey_host.data_ptr())
         else:
-            timed_call("wait_downloads", sim.wait_downloads)
+            # one host array: the previous dump must have arrived before this one may overwrite it
+            timed_call("wait_downloads (previous dump)", sim.wait_downloads)
             timed_call("download_field_async", sim.download_field_async, "ey", ey_host.data_ptr())
+        if k > 0:
+            timed_call("wait_scalars (previous step)", sim.wait_scalars, tickets[k - 1])
+            results.append(scal[(k - 1) % 2][:4].tolist())
+    sim.wait_scalars(tickets[-1])
+    results.append(scal[(args.steps - 1) % 2][:4].tolist())
     sim.wait_downloads()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if any(r[3] != 0.0 for r in results) or any(int(r[2]) != n_total for r in results):
+        raise RuntimeError(f"e2e: the per-step results are wrong: {results[-1]} (expected {n_total} particles)")
     if prof is not None and rank == 0:
         print("e2e breakdown (ms per step): " + ", ".join(f"{k} {1e3 * v / args.steps:.3f}" for k, v in prof.items()) +
               f"; total {1e3 * e2e_s / args.steps:.3f}", file=sys.stderr, flush=True)
@@ -637,6 +619,37 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n_total * args.steps / e2e_s
+
+    # ---- the same steps from the relaxed state ("mixed_state") --------------------------
+    # EPOCH's loader puts exactly ppc particles in every cell; a thermal plasma relaxes to Poisson counts, where a
+    # warp runs as many rounds as its fullest column.  The figure above is the deck as loaded (what the reference arm
+    # runs too); this one is the long-time state of the same deck, device-timed the same way.
+    sim.close()   # give the device memory back (also before the compiled host attaches its own state)
+    mixed_state = None
+    if not args.no_mixed:
+        msim = make_sim(True)
+        for _ in range(3):
+            msim.step()
+        msim.push_kernel_ms(reset=1)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        msteps = min(args.steps, 6)
+        with torch.cuda.stream(stream):
+            m0.record(stream)
+            for _ in range(msteps):
+                msim.step()
+            m1.record(stream)
+        barrier()
+        mms = m0.elapsed_time(m1)
+        mk_ms, _ = msim.push_kernel_ms(reset=2)
+        mtot = msim.global_count(0)
+        if world > 1:
+            t = torch.tensor([mms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mms = float(t.item())
+        mixed_state = {"value": mtot * msteps / (mms * 1e-3), "unit": UNIT, "ms_per_step": mms / msteps, "steps": msteps,
+                       "kernel_ms": mk_ms, "load": "every particle's cell drawn at random (Poisson counts per cell)"}
+        msim.close()
 
     if rank == 0:
         peaks = {}

@@ -1461,7 +1461,10 @@ int epb_destroy(epb_handle *h) {
   for (int a = 1; a < 3; a++) { cudaFree(h->snapA[a]); cudaFree(h->srcA[a]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
-  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage); cudaFree(h->coll_work); cudaFree(h->prof_scratch);
+  cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage); cudaFree(h->coll_work); cudaFree(h->prof_scratch); cudaFree(h->scal_dev);
+  for (int q = 0; q < 4; q++) if (h->scal_ev[q]) cudaEventDestroy(h->scal_ev[q]);
+  for (int q = 0; q < 8; q++) if (h->src_ev[q]) cudaEventDestroy(h->src_ev[q]);
+  if (h->src_stage) cudaFreeHost(h->src_stage);
   cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   for (auto &S : h->sp) {
     // slot columns first: their buf[0][*] point INTO the arena and are cleared by epb_slots_free
@@ -1705,10 +1708,29 @@ int epb_set_laser_source(epb_handle *h, int side, const double *s1, const double
   double *base = a == 0 ? h->src : h->srcA[a];
   const size_t plane = a == 0 ? h->plane : h->planeA[a];
   if (!base) return EPB_ERR_ARG;
-  EPB_CUDA(h, cudaMemcpyAsync(base + ((size_t)sd * 2 + 0) * plane, s1, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  EPB_CUDA(h, cudaMemcpyAsync(base + ((size_t)sd * 2 + 1) * plane, s2, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  // host buffers may be reused by the caller right after return
-  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  // The caller may reuse its buffers right after return, and the call must not wait for the stream (the host
+  // enqueues step n+1 while step n runs): the planes go through a ring of page-locked staging slots; a slot is
+  // reused eight calls later, after its copy's event.
+  size_t maxn = 1;
+  for (int q = 0; q < c.ndims; q++) {
+    size_t m = 1;
+    for (int d = 0; d < c.ndims; d++) if (d != q) m *= (size_t)(c.n[d] + 1);
+    if (m > maxn) maxn = m;
+  }
+  if (!h->src_stage) {
+    h->src_stage_slot = 2 * maxn;
+    EPB_CUDA(h, cudaMallocHost(&h->src_stage, 8 * h->src_stage_slot * sizeof(double)));
+    for (int q = 0; q < 8; q++) EPB_CUDA(h, cudaEventCreateWithFlags(&h->src_ev[q], cudaEventDisableTiming));
+  }
+  const int slot = (int)(h->src_calls % 8);
+  if (h->src_calls >= 8) EPB_CUDA(h, cudaEventSynchronize(h->src_ev[slot]));
+  double *st = h->src_stage + (size_t)slot * h->src_stage_slot;
+  memcpy(st, s1, n * sizeof(double));
+  memcpy(st + n, s2, n * sizeof(double));
+  EPB_CUDA(h, cudaMemcpyAsync(base + ((size_t)sd * 2 + 0) * plane, st, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPB_CUDA(h, cudaMemcpyAsync(base + ((size_t)sd * 2 + 1) * plane, st + n, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPB_CUDA(h, cudaEventRecord(h->src_ev[slot], h->stream));
+  h->src_calls++;
   return EPB_OK;
 }
 
@@ -1904,8 +1926,8 @@ int epb_push(epb_handle *h) {
       continue;
     }
     static const int no3d = epb_env("EPB_NO_TILED_3D") ? atoi(epb_env("EPB_NO_TILED_3D")) : 0;
-    // HC_PUSH builds of the reference: the tiled kernels hold the Boris gamma only, every particle takes
-    // push_generic<ND, true>
+    // HC_PUSH builds of the reference: the slot-column kernels carry the rotation as a template flag (handled
+    // above); the sorted layouts' tiled kernels hold the Boris gamma only, there every particle takes push_generic<ND, true>
     const bool tiled = !c.hc_push && ((c.ndims == 2) || (c.ndims == 3 && !no3d));
     long long sorted = S.n_sorted < S.n ? S.n_sorted : S.n;
     // layout 1: the last push before a sort also records every particle's place in the next
@@ -2104,6 +2126,104 @@ int epb_field_energy(epb_handle *h, double out[2]) {
   const double mu0 = 4.e-7 * 3.141592653589793238462643383279503;
   out[0] = 0.5 * EPB_EPS0 * v[0] * dv;
   out[1] = 0.5 / mu0 * v[1] * dv;
+  return EPB_OK;
+}
+
+// The scalars EPOCH's host looks at after every step -- update_particle_count's global count of every species
+// (partlist.F90:984-1003) and calc_total_energy_sum's field energies (io/calc_df.F90:1321-1417, summed over the
+// ranks like its MPI_ALLREDUCE) -- evaluated in stream order and copied to page-locked host memory WITHOUT stopping
+// the host, so that it can enqueue the next step while this one runs.  host[0] = 0.5 eps0 sum E^2 dV, host[1] =
+// 0.5/mu0 sum B^2 dV, host[2 + is] = global count of species is (exact: an integer below 2^53), host[2 + n_species]
+// = the device error word (non-zero: a capacity overflow lost particles).  Returns a ticket for epb_wait_scalars.
+namespace {
+struct ScalOp {
+  double *out;
+  double ce, cb;
+  int nsp;
+  const long long *cnt2;          // [2 * is]: columns, inbox
+  const int *mcount[EPB_SCAL_MAXSP];
+  int mcap[EPB_SCAL_MAXSP], slots[EPB_SCAL_MAXSP];
+  long long fixed[EPB_SCAL_MAXSP];
+  const int *err;
+};
+__global__ void k_scalars(const __grid_constant__ ScalOp O) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  O.out[0] *= O.ce;
+  O.out[1] *= O.cb;
+  for (int is = 0; is < O.nsp; is++) {
+    long long v = O.fixed[is];
+    if (O.slots[is]) {
+      const int w = *O.mcount[is];
+      v = O.cnt2[2 * is] + O.cnt2[2 * is + 1] + (w < O.mcap[is] ? w : O.mcap[is]);
+    }
+    O.out[2 + is] = (double)v;
+  }
+  O.out[2 + O.nsp] = O.err ? (double)*O.err : 0.0;
+}
+}  // namespace
+
+int epb_step_scalars_async(epb_handle *h, double *host, int64_t *ticket) {
+  if (!h || !host) return EPB_ERR_ARG;
+  const epb_config &c = h->cfg;
+  const int nsp = (int)h->sp.size();
+  if (nsp > EPB_SCAL_MAXSP) return epb_fail(h, EPB_ERR_UNSUPPORTED, "epb_step_scalars_async: more than %d species", EPB_SCAL_MAXSP);
+  if (!h->scal_dev) {
+    EPB_CUDA(h, cudaMalloc(&h->scal_dev, (size_t)(2 * (3 + EPB_SCAL_MAXSP)) * sizeof(double)));
+    for (int q = 0; q < 4; q++) EPB_CUDA(h, cudaEventCreateWithFlags(&h->scal_ev[q], cudaEventDisableTiming));
+  }
+  double *d = h->scal_dev;
+  const int len = 3 + nsp;
+  EPB_CUDA(h, cudaMemsetAsync(d, 0, 2 * (size_t)(3 + EPB_SCAL_MAXSP) * sizeof(double), h->stream));
+  EnergyOp E;
+  for (int q = 0; q < 6; q++) E.f[q] = h->f(q);
+  E.nd = c.ndims;
+  for (int q = 0; q < 3; q++) { E.n[q] = c.n[q]; E.sz[q] = h->sz[q]; }
+  E.out = d;
+  const size_t total = (size_t)c.n[0] * c.n[1] * c.n[2];
+  k_field_energy<<<nblocks(total, 148 * 8), 256, 0, h->stream>>>(E);
+  ScalOp O;
+  memset(&O, 0, sizeof O);
+  double dv = 1.0;
+  for (int q = 0; q < c.ndims; q++) dv *= c.dx[q];
+  const double mu0 = 4.e-7 * 3.141592653589793238462643383279503;
+  O.out = d;
+  O.ce = 0.5 * EPB_EPS0 * dv;
+  O.cb = 0.5 / mu0 * dv;
+  O.nsp = nsp;
+  long long *cnt2 = (long long *)(h->d_scratch + 512);
+  O.cnt2 = cnt2;
+  O.err = h->d_err;
+  for (int is = 0; is < nsp; is++) {
+    SpeciesDev &S = h->sp[is];
+    O.slots[is] = S.slots ? 1 : 0;
+    O.fixed[is] = S.n;
+    if (S.slots) {
+      int rc = epb_slots_count_enqueue(h, is, cnt2 + 2 * is);
+      if (rc) return rc;
+      O.mcount[is] = S.mcount + S.mcur;
+      O.mcap[is] = S.mcap;
+    }
+  }
+  k_scalars<<<1, 32, 0, h->stream>>>(O);
+  h->launches += 2;
+  EPB_CUDA(h, cudaGetLastError());
+  double *res = d;
+  if (c.nranks > 1 && h->nccl) {
+    int rc = epb_allreduce_sum_f64(h, d, d + (3 + EPB_SCAL_MAXSP), len);
+    if (rc) return rc;
+    res = d + (3 + EPB_SCAL_MAXSP);
+  }
+  EPB_CUDA(h, cudaMemcpyAsync(host, res, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  const long long t = h->scal_ticket++;
+  EPB_CUDA(h, cudaEventRecord(h->scal_ev[t % 4], h->stream));
+  if (ticket) *ticket = t;
+  return EPB_OK;
+}
+
+int epb_wait_scalars(epb_handle *h, int64_t ticket) {
+  if (!h || ticket < 0 || ticket >= h->scal_ticket) return EPB_ERR_ARG;
+  if (h->scal_ticket - ticket > 4) return EPB_OK;   // its event was recorded again since: that request completed long ago
+  EPB_CUDA(h, cudaEventSynchronize(h->scal_ev[ticket % 4]));
   return EPB_OK;
 }
 

@@ -88,7 +88,7 @@ struct PushParams {
   double part_q, part_mc, ipart_mc, cmratio, ccmratio;
   double hc_alpha;         // HC_PUSH: alpha = 0.5 * part_q * dt / part_m (particles.F90:390)
   int deposit;
-  int hc_push;             // Higuera-Cary rotation: every particle goes through push_generic<ND, true>
+  int hc_push;             // Higuera-Cary rotation (template flag of the slot-column kernels; push_generic<ND, true> elsewhere)
   // particle SoA
   double *x[3];
   double *p[3];
@@ -185,6 +185,9 @@ struct SpeciesDev {
 // opaque storage of a CUtensorMap (128 bytes, 64-byte aligned), see fdtd_tma.cu
 struct alignas(64) TmapStorage { unsigned char b[128]; };
 
+constexpr int EPB_SCAL_MAXSP = 16;   // species covered by epb_step_scalars_async
+int epb_allreduce_sum_f64(epb_handle *h, const double *src, double *dst, int n);   // exchange.cu
+
 // push_per_field (shared_data.F90:821): the weight of a particle against a cell in the balancer's load; deck.PUSH_PER_FIELD
 constexpr int EPB_PUSH_PER_FIELD = 5;
 
@@ -226,6 +229,15 @@ struct epb_handle {
   double *dump_stage = nullptr;
   cudaEvent_t dump_ready = nullptr, dump_done = nullptr;
   bool dump_pending = false;
+  // epb_step_scalars_async: device block [EPB_SCAL_MAX doubles], a ring of completion events (ticket % 4)
+  double *scal_dev = nullptr;
+  cudaEvent_t scal_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long scal_ticket = 0;
+  // epb_set_laser_source: page-locked staging ring, so the call neither waits for the stream nor pins the caller's buffer
+  double *src_stage = nullptr;
+  size_t src_stage_slot = 0;     // doubles per slot
+  cudaEvent_t src_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long src_calls = 0;
   // c_bc_mixed (deck_species_block.F90:182-199): the species disagree on some particle boundary, so J is
   // folded / summed / cleared after every species with that species' boundary codes (particles.F90:645)
   bool bc_mixed = false;
@@ -288,6 +300,7 @@ int epb_slots_download(epb_handle *h, int is, int64_t n, double *packed);
 int epb_slots_settle(epb_handle *h, int is);                      // group inboxes -> columns (before anything but a push walks the species)
 int epb_slots_after_push(epb_handle *h, int is);                  // the consumed inbox is emptied, the filled one becomes current
 int epb_slots_count(epb_handle *h, int is, long long *n);         // synchronises
+int epb_slots_count_enqueue(epb_handle *h, int is, long long *d_out);   // d_out[0] columns, d_out[1] inbox; no host round trip
 // chunked walk over a species' particles as contiguous SoA device arrays, any layout (slots.cu)
 struct SpeciesIter {
   std::vector<int> hstart;   // slot columns: scanned column counts

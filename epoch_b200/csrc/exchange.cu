@@ -258,6 +258,11 @@ extern "C" int epb_load_profile(epb_handle *h, int axis, int64_t *load) {
   return EPB_OK;
 }
 
+int epb_allreduce_sum_f64(epb_handle *h, const double *src, double *dst, int n) {
+  EPB_NCCL(h, ncclAllReduce(src, dst, n, ncclDouble, ncclSum, (ncclComm_t)h->nccl, h->stream));
+  return EPB_OK;
+}
+
 extern "C" int epb_global_count(epb_handle *h, int is, int64_t *n) {
   if (!h || is < 0 || is >= (int)h->sp.size() || !n) return EPB_ERR_ARG;
   long long local = h->sp[is].n;

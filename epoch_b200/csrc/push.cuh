@@ -1352,7 +1352,7 @@ constexpr size_t pushslots_smem() {
          sizeof(double) * (size_t)(CTY / 2) * 6 * 32;
 }
 
-template <int CTY, int MINB, bool RB>
+template <int CTY, int MINB, bool RB, bool HC = false>
 __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_constant__ PushParams P) {
   constexpr int T2Y = CTY, TH = CTY + 2 * HALO, TW = CPITCH, TWU = T2X + 2 * HALO, TILE_ELEMS = TW * TH;
   constexpr int PUSH2D_THREADS = CTY * 16, PUSH2D_WARPS = CTY / 2;
@@ -1575,7 +1575,15 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
         const double uxm = part_ux + cmratio * ex_part;
         const double uym = part_uy + cmratio * ey_part;
         const double uzm = part_uz + cmratio * ez_part;
-        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+        double gm2 = uxm * uxm + uym * uym + uzm * uzm + 1.0;
+        if (HC) {  // particles.F90:386-398 (-DHC_PUSH), Higuera & Cary, Phys. Plasmas 24, 052104; the result is >= 1 too
+          const double beta_x = P.hc_alpha * bx_part, beta_y = P.hc_alpha * by_part, beta_z = P.hc_alpha * bz_part;
+          const double beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z;
+          const double sigma = gm2 - beta2;
+          const double beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm;
+          gm2 = 0.5 * (sigma + sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u)));
+        }
+        gamma_root(gm2, P.ccmratio, root);
         const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
         const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
 #ifdef EPB_FAST_MATH
@@ -1814,14 +1822,14 @@ __global__ void __launch_bounds__(CTY * 16, MINB) push_slots_2d(const __grid_con
 // The mover buffer's unpushed entries (flag 2: no room in their column, or stencil outside their tile):
 // push_one on the buffer itself.  A particle that leaves the rank is flagged 1 by outbox_put (P.gone is the
 // flag array here), everything else becomes an ordinary flag-0 entry for k_deliver.
-template <int ND>
+template <int ND, bool HC = false>
 __global__ void __launch_bounds__(256) push_generic_m(const __grid_constant__ PushParams P) {
   int n = *P.mcount;
   if (n > P.mcap) n = P.mcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (P.gone[i] != 2) continue;
     P.gone[i] = 0;
-    push_one<ND>(P, i);
+    push_one<ND, HC>(P, i);
   }
 }
 
@@ -2538,6 +2546,7 @@ __device__ __forceinline__ void deposit_core_3d(bool on, double *pvb, const doub
   }
 }
 
+template <bool HC>
 __global__ void __launch_bounds__(B3_THREADS, 2) push_bag_3d(const __grid_constant__ PushParams P) {
   extern __shared__ double sm[];
   double *sF = sm;                                   // [6][EB3P]
@@ -2700,7 +2709,15 @@ __global__ void __launch_bounds__(B3_THREADS, 2) push_bag_3d(const __grid_consta
         const double uxm = uu[0] + cmratio * ex_part;
         const double uym = uu[1] + cmratio * ey_part;
         const double uzm = uu[2] + cmratio * ez_part;
-        gamma_root(uxm * uxm + uym * uym + uzm * uzm + 1.0, P.ccmratio, root);
+        double gm2 = uxm * uxm + uym * uym + uzm * uzm + 1.0;
+        if (HC) {  // particles.F90:386-398 (-DHC_PUSH), Higuera & Cary, Phys. Plasmas 24, 052104; the result is >= 1 too
+          const double beta_x = P.hc_alpha * bx_part, beta_y = P.hc_alpha * by_part, beta_z = P.hc_alpha * bz_part;
+          const double beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z;
+          const double sigma = gm2 - beta2;
+          const double beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm;
+          gm2 = 0.5 * (sigma + sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u)));
+        }
+        gamma_root(gm2, P.ccmratio, root);
         const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
         const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
 #ifdef EPB_FAST_MATH
@@ -2929,10 +2946,15 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
         if (!attr_s) {
           cudaFuncSetAttribute(push_slots_2d<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
           cudaFuncSetAttribute(push_slots_2d<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
+          cudaFuncSetAttribute(push_slots_2d<8, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
+          cudaFuncSetAttribute(push_slots_2d<8, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
           attr_s = true;
         }
         (void)minb;
-        if (P.rowd == 32) push_slots_2d<8, 3, false><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+        if (P.hc_push) {   // Higuera-Cary rotation: the same kernels with the other gamma (particles.F90:386-398)
+          if (P.rowd == 32) push_slots_2d<8, 3, false, true><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+          else push_slots_2d<8, 3, true, true><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
+        } else if (P.rowd == 32) push_slots_2d<8, 3, false><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
         else push_slots_2d<8, 3, true><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
       } else if (P.tg.layout == 1) {
         if (P.tg.T[1] == 8) push_cell_2d<8, 3><<<P.tg.ntiles, 128, pushcell_smem<8>(), s>>>(P);
@@ -2955,10 +2977,12 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
       if (P.tg.layout == 3) {
         static bool attrb = false;
         if (!attrb) {
-          cudaFuncSetAttribute(push_bag_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSHBAG3D_SMEM);
+          cudaFuncSetAttribute(push_bag_3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSHBAG3D_SMEM);
+          cudaFuncSetAttribute(push_bag_3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PUSHBAG3D_SMEM);
           attrb = true;
         }
-        push_bag_3d<<<P.tg.ntiles, B3_THREADS, PUSHBAG3D_SMEM, s>>>(P);
+        if (P.hc_push) push_bag_3d<true><<<P.tg.ntiles, B3_THREADS, PUSHBAG3D_SMEM, s>>>(P);
+        else push_bag_3d<false><<<P.tg.ntiles, B3_THREADS, PUSHBAG3D_SMEM, s>>>(P);
       } else {
         push_tiled_3d<<<P.tg.ntiles, P3_THREADS, PUSH3D_SMEM, s>>>(P);
       }
@@ -2984,7 +3008,10 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
 inline void launch_push_m(const PushParams &P, cudaStream_t s, long long *launches) {
   int blocks = (P.mcap + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (P.nd == 3) push_generic_m<3><<<blocks, 256, 0, s>>>(P);
+  if (P.hc_push) {
+    if (P.nd == 3) push_generic_m<3, true><<<blocks, 256, 0, s>>>(P);
+    else push_generic_m<2, true><<<blocks, 256, 0, s>>>(P);
+  } else if (P.nd == 3) push_generic_m<3><<<blocks, 256, 0, s>>>(P);
   else push_generic_m<2><<<blocks, 256, 0, s>>>(P);
   (*launches)++;
 }

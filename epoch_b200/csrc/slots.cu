@@ -488,13 +488,14 @@ int epb_slots_check(epb_handle *h) {
   return EPB_OK;
 }
 
-int epb_slots_count(epb_handle *h, int is, long long *n) {
+// The count of a slot-layout species without a host round trip: d_out[0] = particles in the columns, d_out[1] = on
+// their way between two columns (inbox); the caller adds the waiting entries of the mover buffer (S.mcount[S.mcur]).
+int epb_slots_count_enqueue(epb_handle *h, int is, long long *d_out) {
   SpeciesDev &S = h->sp[is];
-  *n = 0;
+  EPB_CUDA(h, cudaMemsetAsync(d_out, 0, 2 * sizeof(long long), h->stream));
   if (!S.arena_ready) return EPB_OK;
   const int nkeys = h->tg.nkeys;
   size_t need = 0;
-  long long *d_out = (long long *)(h->d_scratch + 512);
   int *tmp = h->cell_count;   // [nkeys + 1] scratch: clamped counts
   k_clamp_counts<<<nblk((size_t)nkeys), 256, 0, h->stream>>>(S.cnt, tmp, nkeys, S.R);
   EPB_CUDA(h, cub::DeviceReduce::Sum(nullptr, need, tmp, d_out, nkeys, h->stream));
@@ -506,20 +507,29 @@ int epb_slots_count(epb_handle *h, int is, long long *n) {
   }
   cub::DeviceReduce::Sum(h->cub_tmp, need, tmp, d_out, nkeys, h->stream);
   h->launches += 2;
-  long long arena = 0, inbox = 0;
-  int mc[2] = {0, 0};
-  EPB_CUDA(h, cudaMemcpyAsync(&arena, d_out, sizeof arena, cudaMemcpyDeviceToHost, h->stream));
   if (S.icnt[0] && S.inbox_dirty) {   // particles on their way between two columns
     const int ng = nkeys / 32;
     k_clamp_counts<<<nblk((size_t)ng), 256, 0, h->stream>>>(S.icnt[S.icur], tmp, ng, S.IC);
     cub::DeviceReduce::Sum(h->cub_tmp, need, tmp, d_out + 1, ng, h->stream);
     h->launches += 2;
-    EPB_CUDA(h, cudaMemcpyAsync(&inbox, d_out + 1, sizeof inbox, cudaMemcpyDeviceToHost, h->stream));
   }
+  return EPB_OK;
+}
+
+int epb_slots_count(epb_handle *h, int is, long long *n) {
+  SpeciesDev &S = h->sp[is];
+  *n = 0;
+  if (!S.arena_ready) return EPB_OK;
+  long long *d_out = (long long *)(h->d_scratch + 512);
+  int rc = epb_slots_count_enqueue(h, is, d_out);
+  if (rc) return rc;
+  long long v[2] = {0, 0};
+  int mc[2] = {0, 0};
+  EPB_CUDA(h, cudaMemcpyAsync(v, d_out, sizeof v, cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaMemcpyAsync(mc, S.mcount, sizeof mc, cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
   long long waiting = std::min<long long>(mc[S.mcur], S.mcap);   // between steps: flag-2 entries only
-  *n = arena + waiting + inbox;
+  *n = v[0] + waiting + v[1];
   return epb_slots_check(h);
 }
 

@@ -216,11 +216,11 @@ void epb_make_tiles(const epb_config &cfg, TileGeom &tg) {
   const int variant = epb_push_variant();
   if (nd == 2 && (variant == 3 || variant == 5)) T[1] = 8;      // push_cell_2d<8,3> / push_slots_2d<8,3>: 16x8-cell tiles
   tg.layout = (nd == 2 && variant >= 2 && variant <= 4) ? 1 : 0;
-  // slot columns; the Higuera-Cary build pushes every particle through the generic kernel (contiguous layout)
-  if (nd == 2 && variant == 5) tg.layout = cfg.hc_push ? 0 : 2;
+  // slot columns (the Higuera-Cary rotation is a template flag of the same kernels)
+  if (nd == 2 && variant == 5) tg.layout = 2;
   // 3D: tile bags (layout 3, push_bag_3d) unless EPB_PUSH3D_VARIANT=0 asks for the sorted layout of push_tiled_3d
   static const int v3 = epb_env("EPB_PUSH3D_VARIANT") ? atoi(epb_env("EPB_PUSH3D_VARIANT")) : 1;
-  if (nd == 3 && v3 != 0 && !cfg.hc_push) {
+  if (nd == 3 && v3 != 0) {
     tg.layout = 3;
     T[0] = 16; T[1] = 4; T[2] = 3;   // must match B3X / B3Y / B3Z in push.cuh (half-warp = 16 consecutive cells of a row)
   }

@@ -21,7 +21,7 @@ SYMBOLS = (
     "epb_upload_species", "epb_download_species", "epb_species_count", "epb_load_uniform",
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
-    "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy",
+    "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy", "epb_step_scalars_async", "epb_wait_scalars",
     "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute", "epb_collide", "epb_collide_pairs_test", "epb_set_boundary_temperature",
 )
 
@@ -115,6 +115,8 @@ def load():
         getattr(L, name).argtypes = [vp]
     L.epb_global_count.argtypes = [vp, i32, C.POINTER(i64)]
     L.epb_field_energy.argtypes = [vp, dp]
+    L.epb_step_scalars_async.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+    L.epb_wait_scalars.argtypes = [vp, C.c_int64]
     L.epb_kinetic_energy.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.epb_calc_moment.argtypes = [vp, i32, i32, dp]
     L.epb_set_boundary_temperature.argtypes = [vp, i32, i32, dp]

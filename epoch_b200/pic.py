@@ -410,6 +410,16 @@ class Simulation:
     def launch_count(self) -> int:
         return int(self.L.epb_launch_count(self._h))
 
+    def step_scalars_async(self, host_ptr: int) -> int:
+        """Field energies and global particle counts of the state the stream has reached, copied to the page-locked
+        array at host_ptr (3 + n_species doubles) without stopping the host; returns the ticket for wait_scalars."""
+        t = C.c_int64()
+        self._chk(self.L.epb_step_scalars_async(self._h, host_ptr, C.byref(t)))
+        return t.value
+
+    def wait_scalars(self, ticket: int):
+        self._chk(self.L.epb_wait_scalars(self._h, ticket))
+
     def push_kernel_ms(self, reset: int = 0):
         ms = C.c_double(); n = C.c_int64()
         self._chk(self.L.epb_push_kernel_ms(self._h, C.byref(ms), C.byref(n), reset))

@@ -181,6 +181,14 @@ int epb_global_count(epb_handle *h, int ispecies, int64_t *n);
  * calc_total_energy_sum (io/calc_df.F90:1321-1417): out[0] = 0.5*eps0*sum(E^2)*dV,
  * out[1] = 0.5/mu0*sum(B^2)*dV over the local interior; kinetic: sum w*(gamma-1)*m*c^2 */
 int epb_field_energy(epb_handle *h, double out[2]);
+/* the scalars the host looks at after every step, without stopping it: host (page-locked, 3 + n_species doubles)
+ * receives [0] the E-field energy, [1] the B-field energy (as above, summed over the ranks like
+ * calc_total_energy_sum's MPI_ALLREDUCE), [2 + is] the global count of species is (update_particle_count; exact,
+ * an integer below 2^53), [2 + n_species] the device error word (non-zero: a capacity overflow lost particles).
+ * Evaluated in stream order; *ticket identifies the request, epb_wait_scalars blocks until its numbers are in host.
+ * At most four requests may be outstanding. */
+int epb_step_scalars_async(epb_handle *h, double *host, int64_t *ticket);
+int epb_wait_scalars(epb_handle *h, int64_t ticket);
 int epb_kinetic_energy(epb_handle *h, int ispecies, double *out);
 /* calc_number_density (io/calc_df.F90:689-757), calc_charge_density (:608-685), calc_mass_density (:35-110)
  * of species ispecies (-1: sum over all species, tracers left out) incl. calc_boundary (ghost-cell sums with

@@ -65,6 +65,38 @@ def test_energy_diagnostics_and_history_gpu():
     assert np.abs(tot / tot[0] - 1.0).max() < 1.0e-4
 
 
+@pytest.mark.parametrize("ndims,n", [(2, (40, 24)), (3, (18, 9, 7))])
+def test_step_scalars_async_gpu(ndims, n):
+    """epb_step_scalars_async (the pipelined form of update_particle_count + calc_total_energy_sum): the numbers
+    that arrive in page-locked memory one step late are exactly those of the blocking calls made at that step,
+    and source planes handed to epb_set_laser_source may be overwritten by the caller right after the call."""
+    import torch
+    from epoch_b200.pic import Simulation
+    from oracle.oracle import Oracle
+    from tests import decks
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=2.0e8, two_species=True)
+    o = Oracle(dk)
+    o.auto_load()
+    sim = Simulation(dk, strict_fp=False, sort_interval=2, capacity_factor=2.0)
+    for isp in range(2):
+        sim.upload_species(isp, o.get_particles(0, isp))
+    sim.init()
+    bufs = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(2)]
+    blocking, tickets = [], []
+    for k in range(6):
+        sim.step()
+        tickets.append(sim.step_scalars_async(bufs[k % 2].data_ptr()))
+        blocking.append(list(sim.field_energy()) + [float(sim.global_count(isp)) for isp in range(2)])
+        if k > 0:                                    # the previous step's numbers, while this step is in flight
+            sim.wait_scalars(tickets[k - 1])
+        sim.wait_scalars(tickets[k])
+        got = bufs[k % 2][:5].tolist()
+        assert got[4] == 0.0                         # device error word
+        assert got[2:4] == blocking[k][2:4]
+        assert np.allclose(got[:2], blocking[k][:2], rtol=1e-13, atol=0.0)
+    assert blocking[-1][2] == o.get_particles(0, 0).shape[0]
+
+
 @pytest.mark.parametrize("ndims,n", [(1, (64,)), (2, (48, 32)), (3, (12, 10, 9))])
 def test_load_profile_gpu(ndims, n):
     """epb_load_profile (get_load_x/y/z, balance.F90:1766-1844) against the numpy restatement in deck.py on the
