@@ -37,6 +37,9 @@ struct FieldParams {
   int nt, ext;
   double kx[3], ky[3], kz[3];
   double alpha[3], beta[6], gamma[3], delta[3];  // beta[2a + k]: other axes of a, lower first
+  // CPML (fields.f90:112-204, :306-420): cx1 = c1 * (cnx / cpml_kappa_ex(ix)) ... per cell; kap[a] == nullptr: no CPML
+  const double *kap[3];
+  double ck[3];
 };
 
 __device__ __forceinline__ size_t fofs(const int *sz, int nd, int i, int j, int k) {
@@ -211,6 +214,7 @@ struct SnapOp {
   const double *f[6];
   double *snap;  // [2][6][plane]
   int nd, sz[3], n[3];
+  int i0[2];     // plane of the snapshot per side: 1 / nx, or one outside the laser plane of a cpml_laser face (setup.F90:409-412)
   size_t plane;
 };
 __global__ void __launch_bounds__(256) k_snapshot(const __grid_constant__ SnapOp S) {
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(256) k_snapshot(const __grid_constant__ SnapOp
     const int j = (int)(t % ey_) + 1 - NG, k = (int)(t / ey_) + 1 - NG;
     const int jj = S.nd >= 2 ? j : 1, kk = S.nd >= 3 ? k : 1;
     for (int side = 0; side < 2; side++) {
-      const int i0 = side == 0 ? 1 : S.n[0];
+      const int i0 = S.i0[side];
       const size_t o = fofs(S.sz, S.nd, i0, jj, kk);
       for (int q = 0; q < 6; q++) {
         const bool avg = (q == EPB_EX || q == EPB_BY || q == EPB_BZ);
@@ -239,6 +243,7 @@ struct OutflowOp {
   int nd, sz[3], n[3];
   size_t plane;
   int is_max;
+  int lp;        // laserpos: 1 / nx, or cpml_x_min_laser_idx / cpml_x_max_laser_idx (laser.f90:320-323, :396-399)
   double lx, ly, lz, sum, diff, dt_eps;
 };
 template <int ND>
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(256) k_outflow(const __grid_constant__ Outflow
     const double *ey = O.f[1], *ez = O.f[2], *jy = O.f[7], *jz = O.f[8];
     const double src1 = O.s1[t], src2 = O.s2[t];
     if (!O.is_max) {
-      const size_t o = fofs(O.sz, ND, 1, j, k);  // laserpos = 1
+      const size_t o = fofs(O.sz, ND, O.lp, j, k);
       bx[o - 1] = SN(EPB_BX);
       double tz = 4.0 * src1 + 2.0 * (SN(EPB_EY) + c * SN(EPB_BZ)) - 2.0 * ey[o];
       if (ND == 3) tz = tz - O.lz * (bx[o] - bx[o - szz]);
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(256) k_outflow(const __grid_constant__ Outflow
       bz[o - 1] = O.sum * tz;
       by[o - 1] = O.sum * ty;
     } else {
-      const size_t o = fofs(O.sz, ND, O.n[0], j, k);  // laserpos = nx
+      const size_t o = fofs(O.sz, ND, O.lp, j, k);
       bx[o + 1] = SN(EPB_BX);
       double tz = -4.0 * src1 - 2.0 * (SN(EPB_EY) - c * SN(EPB_BZ)) + 2.0 * ey[o];
       if (ND == 3) tz = tz + O.lz * (bx[o] - bx[o - szz]);
@@ -293,6 +298,7 @@ struct FaceOp {
   double *snap;            // [2][6][plane] of this axis
   const double *s1, *s2;   // sources of this side
   int nd, sz[3], n[3], a, is_max;
+  int lp, snap_i[2];       // laser plane of the update; snapshot planes per side (cpml_laser faces move them inwards)
   size_t plane;
   double l[3], sum, diff, dt_eps;
 };
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(256) k_snapshot_face(const __grid_constant__ F
     for (int d = 0; d < 3; d++) { p[d] = lo[d] + (int)(r % ext[d]); r /= ext[d]; }
     const size_t tp = face_plane_index(O, p);
     for (int side = 0; side < 2; side++) {
-      p[O.a] = side == 0 ? 1 : O.n[O.a];
+      p[O.a] = O.snap_i[side];
       const size_t o = fofs(O.sz, O.nd, p[0], p[1], p[2]);
       for (int q = 0; q < 6; q++) {
         const bool avg = q < 3 ? (q == O.a) : (q - 3 != O.a);
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(256) k_outflow_face(const __grid_constant__ Fa
     const size_t tp = face_plane_index(O, p);
 #define SN(q) snap[(size_t)(q) * O.plane + tp]
     const double src1 = O.s1[t], src2 = O.s2[t];
-    p[a] = O.is_max ? O.n[a] : 1;  // laserpos
+    p[a] = O.lp;  // laserpos
     const ptrdiff_t o = (ptrdiff_t)fofs(O.sz, ND, p[0], p[1], p[2]);
     const ptrdiff_t sa = str[a];
     if (!O.is_max) {
@@ -844,17 +850,24 @@ __global__ void __launch_bounds__(256) k_update_e_gen(const __grid_constant__ Fi
     const double *jx = F.f[6], *jy = F.f[7], *jz = F.f[8];
     // backward difference k along stride s: f(i+k) - f(i-k-1)
     auto db = [&](const double *f, ptrdiff_t s, int k) { return f[o + k * s] - f[o - (k + 1) * s]; };
+    double kx[3] = {F.kx[0], F.kx[1], F.kx[2]}, ky[3] = {F.ky[0], F.ky[1], F.ky[2]}, kz[3] = {F.kz[0], F.kz[1], F.kz[2]};
+    if (F.kap[0]) {   // CPML: the stretching divides every cell's coefficients
+      const double bx_ = F.cx / F.kap[0][ix + NG - 1];
+      const double by_ = ND >= 2 ? F.cy / F.kap[1][iy + NG - 1] : 0.0;
+      const double bz_ = ND >= 3 ? F.cz / F.kap[2][iz + NG - 1] : 0.0;
+      for (int k = 0; k < 3; k++) { kx[k] = F.ck[k] * bx_; ky[k] = F.ck[k] * by_; kz[k] = F.ck[k] * bz_; }
+    }
     double v = ex[o];
-    if (ND >= 2) for (int k = 0; k < nt; k++) v = v + F.ky[k] * db(bz, sy, k);
-    if (ND >= 3) for (int k = 0; k < nt; k++) v = v - F.kz[k] * db(by, szz, k);
+    if (ND >= 2) for (int k = 0; k < nt; k++) v = v + ky[k] * db(bz, sy, k);
+    if (ND >= 3) for (int k = 0; k < nt; k++) v = v - kz[k] * db(by, szz, k);
     ex[o] = v - F.fac * jx[o];
     v = ey[o];
-    if (ND >= 3) for (int k = 0; k < nt; k++) v = v + F.kz[k] * db(bx, szz, k);
-    for (int k = 0; k < nt; k++) v = v - F.kx[k] * db(bz, sx, k);
+    if (ND >= 3) for (int k = 0; k < nt; k++) v = v + kz[k] * db(bx, szz, k);
+    for (int k = 0; k < nt; k++) v = v - kx[k] * db(bz, sx, k);
     ey[o] = v - F.fac * jy[o];
     v = ez[o];
-    for (int k = 0; k < nt; k++) v = v + F.kx[k] * db(by, sx, k);
-    if (ND >= 2) for (int k = 0; k < nt; k++) v = v - F.ky[k] * db(bx, sy, k);
+    for (int k = 0; k < nt; k++) v = v + kx[k] * db(by, sx, k);
+    if (ND >= 2) for (int k = 0; k < nt; k++) v = v - ky[k] * db(bx, sy, k);
     ez[o] = v - F.fac * jz[o];
   }
 }
@@ -874,6 +887,14 @@ __global__ void __launch_bounds__(256) k_update_b_gen(const __grid_constant__ Fi
     double *bx = F.f[3], *by = F.f[4], *bz = F.f[5];
     // forward difference k along stride s: f(i+k+1) - f(i-k)
     auto df = [&](const double *f, ptrdiff_t s, int k) { return f[o + (k + 1) * s] - f[o - k * s]; };
+    double kx[3] = {F.kx[0], F.kx[1], F.kx[2]}, ky[3] = {F.ky[0], F.ky[1], F.ky[2]}, kz[3] = {F.kz[0], F.kz[1], F.kz[2]};
+    double hx_ = F.cx, hy_ = F.cy, hz_ = F.cz;
+    if (F.kap[0]) {   // CPML: cx1 = hdtx / cpml_kappa_bx(ix) (times c1.. for the higher orders), fields.f90:306-420
+      hx_ = F.cx / F.kap[0][ix + NG - 1];
+      hy_ = ND >= 2 ? F.cy / F.kap[1][iy + NG - 1] : 0.0;
+      hz_ = ND >= 3 ? F.cz / F.kap[2][iz + NG - 1] : 0.0;
+      for (int q = 0; q < 3; q++) { kx[q] = F.ck[q] * hx_; ky[q] = F.ck[q] * hy_; kz[q] = F.ck[q] * hz_; }
+    }
     if (F.ext) {
       // fields.f90:441-465, epoch3d fields.f90:655-730, epoch1d fields.f90:304-312: derivative along
       // axis a = alpha + the two betas (lower other axis first; +1 then -1) + gamma (3D; first other
@@ -892,33 +913,33 @@ __global__ void __launch_bounds__(256) k_update_b_gen(const __grid_constant__ Fi
         return v;
       };
       if (ND == 1) {
-        by[o] = by[o] + F.cx * dd(ez, 0);
-        bz[o] = bz[o] - F.cx * dd(ey, 0);
+        by[o] = by[o] + hx_ * dd(ez, 0);
+        bz[o] = bz[o] - hx_ * dd(ey, 0);
       } else if (ND == 2) {
-        bx[o] = bx[o] - F.cy * dd(ez, 1);
-        by[o] = by[o] + F.cx * dd(ez, 0);
-        bz[o] = bz[o] - F.cx * dd(ey, 0) + F.cy * dd(ex, 1);
+        bx[o] = bx[o] - hy_ * dd(ez, 1);
+        by[o] = by[o] + hx_ * dd(ez, 0);
+        bz[o] = bz[o] - hx_ * dd(ey, 0) + hy_ * dd(ex, 1);
       } else {
-        bx[o] = bx[o] - F.cy * dd(ez, 1) + F.cz * dd(ey, 2);
-        by[o] = by[o] - F.cz * dd(ex, 2) + F.cx * dd(ez, 0);
-        bz[o] = bz[o] - F.cx * dd(ey, 0) + F.cy * dd(ex, 1);
+        bx[o] = bx[o] - hy_ * dd(ez, 1) + hz_ * dd(ey, 2);
+        by[o] = by[o] - hz_ * dd(ex, 2) + hx_ * dd(ez, 0);
+        bz[o] = bz[o] - hx_ * dd(ey, 0) + hy_ * dd(ex, 1);
       }
       continue;
     }
     double v;
     if (ND >= 2) {
       v = bx[o];
-      for (int k = 0; k < nt; k++) v = v - F.ky[k] * df(ez, sy, k);
-      if (ND >= 3) for (int k = 0; k < nt; k++) v = v + F.kz[k] * df(ey, szz, k);
+      for (int k = 0; k < nt; k++) v = v - ky[k] * df(ez, sy, k);
+      if (ND >= 3) for (int k = 0; k < nt; k++) v = v + kz[k] * df(ey, szz, k);
       bx[o] = v;
     }
     v = by[o];
-    if (ND >= 3) for (int k = 0; k < nt; k++) v = v - F.kz[k] * df(ex, szz, k);
-    for (int k = 0; k < nt; k++) v = v + F.kx[k] * df(ez, sx, k);
+    if (ND >= 3) for (int k = 0; k < nt; k++) v = v - kz[k] * df(ex, szz, k);
+    for (int k = 0; k < nt; k++) v = v + kx[k] * df(ez, sx, k);
     by[o] = v;
     v = bz[o];
-    for (int k = 0; k < nt; k++) v = v - F.kx[k] * df(ey, sx, k);
-    if (ND >= 2) for (int k = 0; k < nt; k++) v = v + F.ky[k] * df(ex, sy, k);
+    for (int k = 0; k < nt; k++) v = v - kx[k] * df(ey, sx, k);
+    if (ND >= 2) for (int k = 0; k < nt; k++) v = v + ky[k] * df(ex, sy, k);
     bz[o] = v;
   }
 }
@@ -961,6 +982,84 @@ __global__ void __launch_bounds__(256) k_smooth_copyback(const __grid_constant__
   }
 }
 
+// cpml_advance_e_currents / cpml_advance_b_currents (boundary.F90:1813-2023; epoch3d :2365-2790, epoch1d :929-1040)
+// for one layer of axis a, (b, c) its cyclic successors:
+//   E: psi_Eb = bco psi_Eb + cco (B_c(i) - B_c(i-1)), E_b -= fac psi_Eb;  psi_Ec from B_b, E_c += fac psi_Ec
+//   B: psi_Bb = bco psi_Bb + cco (E_c(i+1) - E_c(i)), B_b += tstep psi_Bb; psi_Bc from E_b, B_c -= tstep psi_Bc
+// over the interior of the other axes.  bco / cco are the reference's bcoeff / ccoeff_d per layer position, evaluated
+// on the host (the same libm exp as the CPU oracle) for the half step.
+struct CpmlOp {
+  double *fb, *fc;             // updated components b, c
+  const double *gb, *gc;       // the other field's components b, c
+  double *psb, *psc;
+  const double *bco, *cco;     // indexed i + NG - 1 along the axis
+  int nd, sz[3], n[3], a, i0, i1, efield;
+  double fac;                  // tstep c^2 (E) or tstep (B)
+};
+__global__ void __launch_bounds__(256) k_cpml(const __grid_constant__ CpmlOp O) {
+  int ext[3], lo[3];
+  size_t total = 1;
+  for (int d = 0; d < 3; d++) {
+    if (d == O.a) { ext[d] = O.i1 - O.i0 + 1; lo[d] = O.i0; }
+    else if (d < O.nd) { ext[d] = O.n[d]; lo[d] = 1; }
+    else { ext[d] = 1; lo[d] = 1; }
+    total *= (size_t)ext[d];
+  }
+  const ptrdiff_t str[3] = {1, (ptrdiff_t)O.sz[0], (ptrdiff_t)O.sz[0] * O.sz[1]};
+  const ptrdiff_t sa = str[O.a];
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int p[3];
+    size_t r = t;
+    for (int d = 0; d < 3; d++) { p[d] = lo[d] + (int)(r % ext[d]); r /= ext[d]; }
+    const ptrdiff_t o = (ptrdiff_t)fofs(O.sz, O.nd, p[0], p[1], p[2]);
+    const double bcoeff = O.bco[p[O.a] + NG - 1], ccoeff_d = O.cco[p[O.a] + NG - 1];
+    if (O.efield) {
+      O.psb[o] = bcoeff * O.psb[o] + ccoeff_d * (O.gc[o] - O.gc[o - sa]);
+      O.fb[o] = O.fb[o] - O.fac * O.psb[o];
+      O.psc[o] = bcoeff * O.psc[o] + ccoeff_d * (O.gb[o] - O.gb[o - sa]);
+      O.fc[o] = O.fc[o] + O.fac * O.psc[o];
+    } else {
+      O.psb[o] = bcoeff * O.psb[o] + ccoeff_d * (O.gc[o + sa] - O.gc[o]);
+      O.fb[o] = O.fb[o] + O.fac * O.psb[o];
+      O.psc[o] = bcoeff * O.psc[o] + ccoeff_d * (O.gb[o + sa] - O.gb[o]);
+      O.fc[o] = O.fc[o] - O.fac * O.psc[o];
+    }
+  }
+}
+
+static int cpml_advance(epb_handle *h, double tstep, bool efield) {
+  const epb_config &c = h->cfg;
+  const double cc = EPB_C;
+  for (int a = 0; a < c.ndims; a++) {
+    const int b = (a + 1) % 3, c3 = (a + 2) % 3;
+    for (int sd = 0; sd < 2; sd++) {
+      const int bc = c.bc_field[2 * a + sd];
+      if (bc != EPB_BC_CPML_LASER && bc != EPB_BC_CPML_OUTFLOW) continue;
+      int i0 = h->cp_start[a][sd], i1 = h->cp_end[a][sd];
+      if (!efield && sd == 1) { i0 -= 1; i1 -= 1; }
+      if (i1 < i0) continue;
+      CpmlOp O;
+      O.fb = h->f((efield ? EPB_EX : EPB_BX) + b);
+      O.fc = h->f((efield ? EPB_EX : EPB_BX) + c3);
+      O.gb = h->f((efield ? EPB_BX : EPB_EX) + b);
+      O.gc = h->f((efield ? EPB_BX : EPB_EX) + c3);
+      O.psb = h->cp_psi[a] + (size_t)(efield ? 0 : 2) * h->fsize;
+      O.psc = h->cp_psi[a] + (size_t)(efield ? 1 : 3) * h->fsize;
+      O.bco = h->cp_bco[a][efield ? 0 : 1];
+      O.cco = h->cp_cco[a][efield ? 0 : 1];
+      O.nd = c.ndims;
+      for (int d = 0; d < 3; d++) { O.sz[d] = h->sz[d]; O.n[d] = c.n[d]; }
+      O.a = a; O.i0 = i0; O.i1 = i1; O.efield = efield ? 1 : 0;
+      O.fac = efield ? tstep * (cc * cc) : tstep;
+      size_t total = (size_t)(i1 - i0 + 1);
+      for (int d = 0; d < c.ndims; d++) if (d != a) total *= (size_t)c.n[d];
+      k_cpml<<<nblocks(total, 148 * 8), 256, 0, h->stream>>>(O);
+      h->launches++;
+    }
+  }
+  return EPB_OK;
+}
+
 static void fd_coeffs(int order, double base, double *cc) {
   if (order == 4) { cc[0] = (9.0 / 8.0) * base; cc[1] = (-1.0 / 24.0) * base; cc[2] = 0.0; }
   else if (order == 6) { cc[0] = (75.0 / 64.0) * base; cc[1] = (-25.0 / 384.0) * base; cc[2] = (3.0 / 640.0) * base; }
@@ -977,7 +1076,9 @@ static bool general_solver(const epb_handle *h, FieldParams &F) {
   fd_coeffs(order, F.cz, F.kz);
   for (int q = 0; q < 3; q++) { F.alpha[q] = c.stencil[q]; F.gamma[q] = c.stencil[9 + q]; F.delta[q] = c.stencil[12 + q]; }
   for (int q = 0; q < 6; q++) F.beta[q] = c.stencil[3 + q];
-  return order != 2 || F.ext;
+  fd_coeffs(order, 1.0, F.ck);
+  for (int q = 0; q < 3; q++) F.kap[q] = nullptr;
+  return order != 2 || F.ext || h->cpml;
 }
 
 int update_e(epb_handle *h, double hdt) {
@@ -989,12 +1090,14 @@ int update_e(epb_handle *h, double hdt) {
   F.cz = F.nd >= 3 ? hdt / h->cfg.dx[2] * (c * c) : 0.0;
   F.fac = hdt / EPB_EPS0;
   if (general_solver(h, F)) {
+    if (h->cpml) for (int q = 0; q < F.nd; q++) F.kap[q] = h->cp_kap[q][0];
     size_t tot = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
     int nbg = nblocks(tot, 148 * 32);
     if (F.nd == 1) k_update_e_gen<1><<<nbg, 256, 0, h->stream>>>(F);
     else if (F.nd == 2) k_update_e_gen<2><<<nbg, 256, 0, h->stream>>>(F);
     else k_update_e_gen<3><<<nbg, 256, 0, h->stream>>>(F);
     h->launches++;
+    if (h->cpml) cpml_advance(h, hdt, true);   // fields.f90:204
     return EPB_OK;
   }
   if (h->tma_ok) { epb_fdtd_tma_launch(h, true, F.cx, F.cy, F.cz, F.fac); return EPB_OK; }
@@ -1015,12 +1118,14 @@ int update_b(epb_handle *h, double hdt) {
   F.cz = F.nd >= 3 ? hdt / h->cfg.dx[2] : 0.0;
   F.fac = 0.0;
   if (general_solver(h, F)) {
+    if (h->cpml) for (int q = 0; q < F.nd; q++) F.kap[q] = h->cp_kap[q][1];
     size_t tot = (size_t)(F.n[0] + 1) * (F.nd >= 2 ? F.n[1] + 1 : 1) * (F.nd >= 3 ? F.n[2] + 1 : 1);
     int nbg = nblocks(tot, 148 * 32);
     if (F.nd == 1) k_update_b_gen<1><<<nbg, 256, 0, h->stream>>>(F);
     else if (F.nd == 2) k_update_b_gen<2><<<nbg, 256, 0, h->stream>>>(F);
     else k_update_b_gen<3><<<nbg, 256, 0, h->stream>>>(F);
     h->launches++;
+    if (h->cpml) cpml_advance(h, hdt, false);   // after the B update (fields.f90, end of update_b_field)
     return EPB_OK;
   }
   if (h->tma_ok) { epb_fdtd_tma_launch(h, false, F.cx, F.cy, F.cz, F.fac); return EPB_OK; }
@@ -1084,7 +1189,7 @@ int field_bcs3(epb_handle *h, int f0, bool mpi_only) {
   for (int i = 0; i < 2 * h->cfg.ndims; i++) {
     int b = h->cfg.bc_field[i];
     if (b == EPB_BC_CLAMP || b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW) mirror3(h, f0, i, -1.0);
-    if (b == EPB_BC_ZERO_GRADIENT) mirror3(h, f0, i, +1.0);
+    if (b == EPB_BC_ZERO_GRADIENT || b == EPB_BC_CPML_LASER || b == EPB_BC_CPML_OUTFLOW) mirror3(h, f0, i, +1.0);   // boundary.F90:845-851, :898-904
   }
   return EPB_OK;
 }
@@ -1100,6 +1205,7 @@ int outflow_x(epb_handle *h, int side, double dt) {
   for (int d = 0; d < 3; d++) { O.sz[d] = h->sz[d]; O.n[d] = c.n[d]; }
   O.plane = h->plane;
   O.is_max = side;
+  O.lp = c.bc_field[side] == EPB_BC_CPML_LASER ? h->cp_laser_idx[0][side] : (side ? c.n[0] : 1);
   const double cc = EPB_C;
   const double dtc2 = dt * (cc * cc);
   O.lx = dtc2 / c.dx[0];
@@ -1125,6 +1231,11 @@ static void fill_face_op(epb_handle *h, int a, FaceOp &O) {
   for (int d = 0; d < 3; d++) { O.sz[d] = h->sz[d]; O.n[d] = c.n[d]; }
   O.a = a;
   O.plane = h->planeA[a];
+  for (int sd = 0; sd < 2; sd++) {
+    O.snap_i[sd] = sd ? c.n[a] : 1;
+    if (c.bc_field[2 * a + sd] == EPB_BC_CPML_LASER) O.snap_i[sd] = sd ? h->cp_laser_idx[a][1] + 1 : h->cp_laser_idx[a][0] - 1;
+  }
+  O.lp = 1;
 }
 int outflow_face(epb_handle *h, int boundary, double dt) {
   const epb_config &c = h->cfg;
@@ -1132,6 +1243,7 @@ int outflow_face(epb_handle *h, int boundary, double dt) {
   FaceOp O;
   fill_face_op(h, a, O);
   O.is_max = side;
+  O.lp = c.bc_field[boundary] == EPB_BC_CPML_LASER ? h->cp_laser_idx[a][side] : (side ? c.n[a] : 1);
   O.s1 = h->srcA[a] + ((size_t)side * 2 + 0) * h->planeA[a];
   O.s2 = h->srcA[a] + ((size_t)side * 2 + 1) * h->planeA[a];
   const double cc = EPB_C;
@@ -1153,13 +1265,17 @@ int outflow_face(epb_handle *h, int boundary, double dt) {
 int bfield_final_bcs(epb_handle *h, double dt) {
   int rc = field_bcs3(h, EPB_BX, false);
   if (rc) return rc;
+  // add_laser(i) .OR. simple_outflow (boundary.F90:918-940): a cpml_laser face has add_laser only on the rank that
+  // holds its laser plane (boundary.F90:1572-1577); a cpml_outflow face only absorbs
   for (int side = 0; side < 2; side++) {
     int b = h->cfg.bc_field[side];
-    if (h->cfg.is_boundary[side] && (b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW)) outflow_x(h, side, dt);
+    if (h->cfg.is_boundary[side] && (b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW ||
+                                     (b == EPB_BC_CPML_LASER && h->cp_add_laser[0][side]))) outflow_x(h, side, dt);
   }
   for (int bd = 2; bd < 2 * h->cfg.ndims; bd++) {
     int b = h->cfg.bc_field[bd];
-    if (h->cfg.is_boundary[bd] && (b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW)) outflow_face(h, bd, dt);
+    if (h->cfg.is_boundary[bd] && (b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW ||
+                                   (b == EPB_BC_CPML_LASER && h->cp_add_laser[bd / 2][bd & 1]))) outflow_face(h, bd, dt);
   }
   return field_bcs3(h, EPB_BX, true);
 }
@@ -1228,7 +1344,7 @@ void fill_push_params(epb_handle *h, int is, PushParams &P) {
     P.max_local[d] = c.max_local[d];
     P.gmin[d] = c.gmin[d];
     P.gmax[d] = c.gmax[d];
-    P.shift[d] = (c.gmax[d] - c.gmin[d]) + 2.0 * c.dx[d] * 0.0;  // length_x + 2 dx cpml_thickness
+    P.shift[d] = (c.gmax[d] - c.gmin[d]) + 2.0 * c.dx[d] * (double)c.cpml_thickness;  // length_x + 2 dx cpml_thickness (boundary.F90:1047-1048)
     P.min_outer[d] = c.min_outer[d];
     P.max_outer[d] = c.max_outer[d];
     P.bc_min[d] = S.cfg.bc_particle[2 * d];
@@ -1322,7 +1438,8 @@ int epb_create(const epb_config *cfg, const epb_species *species, epb_handle **o
   for (int i = 0; i < 2 * cfg->ndims; i++) {
     int b = cfg->bc_field[i];
     bool ok = b == EPB_BC_PERIODIC || b == EPB_BC_CLAMP || b == EPB_BC_ZERO_GRADIENT ||
-              b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW || b == EPB_BC_CONDUCT;
+              b == EPB_BC_SIMPLE_LASER || b == EPB_BC_SIMPLE_OUTFLOW || b == EPB_BC_CONDUCT ||
+              b == EPB_BC_CPML_LASER || b == EPB_BC_CPML_OUTFLOW;
     if (!ok) return epb_fail(nullptr, EPB_ERR_UNSUPPORTED, "field boundary code %d on boundary %d not implemented on the device path", b, i);
   }
   for (int s = 0; s < cfg->n_species; s++) {
@@ -1380,6 +1497,81 @@ static int create_device_state(epb_handle *h, const epb_config *cfg, const epb_s
     EPB_CUDA(h, cudaMemsetAsync(h->snapA[a], 0, 12 * pl * sizeof(double), h->stream));
     EPB_CUDA(h, cudaMalloc(&h->srcA[a], 4 * pl * sizeof(double)));
     EPB_CUDA(h, cudaMemsetAsync(h->srcA[a], 0, 4 * pl * sizeof(double), h->stream));
+  }
+  {  // set_cpml_helpers + allocate_cpml_fields (boundary.F90:1479-1794; epoch3d :1891-2330, epoch1d :783-925), per axis
+    const int t = cfg->cpml_thickness;
+    bool any = false;
+    for (int i = 0; i < 2 * nd; i++)
+      if (cfg->bc_field[i] == EPB_BC_CPML_LASER || cfg->bc_field[i] == EPB_BC_CPML_OUTFLOW) any = true;
+    for (int d = 0; d < 3; d++)
+      for (int sd = 0; sd < 2; sd++) { h->cp_start[d][sd] = cfg->n[d] + 1; h->cp_end[d][sd] = 0; }
+    if (any && t <= 0) return epb_fail(h, EPB_ERR_ARG, "a CPML field boundary needs cpml_thickness > 0");
+    if (any) {
+      h->cpml = true;
+      const double cc = EPB_C;
+      const int cpml_m = 3, cpml_ma = 1;
+      const int fng = (cfg->field_order ? cfg->field_order : 2) / 2;   // fields.f90:37
+      const double tstep = 0.5 * cfg->dt;                               // both half steps use hdt
+      auto pw = [](double x, int e) { double r = 1.0; for (int q = 0; q < e; q++) r = r * x; return r; };
+      // dx of the first axis for every axis, as boundary.F90:1517 has it
+      const double sigma_maxval = cfg->cpml_sigma_max * cc * 0.8 * (cpml_m + 1.0) / cfg->dx[0];
+      for (int d = 0; d < nd; d++) {
+        const int n = cfg->n[d], len = n + 2 * NG;
+        std::vector<double> kap[2], sig[2], aa[2];
+        for (int q = 0; q < 2; q++) { kap[q].assign(len, 1.0); sig[q].assign(len, 0.0); aa[q].assign(len, 0.0); }
+        auto at = [&](std::vector<double> &v, int i) -> double & { return v[i + NG - 1]; };
+        const int gmin = cfg->n_global_min[d], gmax = gmin + n - 1, ng_ = cfg->n_global[d];
+        auto profile = [&](int i, int ib, int ig) {   // E point i, B point ib, distance index ig into the layer
+          double x_pos = 1.0 - (double)(ig - 1) / (double)t;
+          at(kap[0], i) = 1.0 + (cfg->cpml_kappa_max - 1.0) * pw(x_pos, cpml_m);
+          at(sig[0], i) = sigma_maxval * pw(x_pos, cpml_m);
+          at(aa[0], i) = cfg->cpml_a_max * pw(1.0 - x_pos, cpml_ma);
+          x_pos = 1.0 - ((double)ig - 0.5) / (double)t;
+          at(kap[1], ib) = 1.0 + (cfg->cpml_kappa_max - 1.0) * pw(x_pos, cpml_m);
+          at(sig[1], ib) = sigma_maxval * pw(x_pos, cpml_m);
+          at(aa[1], ib) = cfg->cpml_a_max * pw(1.0 - x_pos, cpml_ma);
+        };
+        const int bmin = cfg->bc_field[2 * d], bmax = cfg->bc_field[2 * d + 1];
+        if (bmin == EPB_BC_CPML_LASER || bmin == EPB_BC_CPML_OUTFLOW) {
+          if (gmin <= t) {
+            h->cp_start[d][0] = 1;
+            h->cp_end[d][0] = gmax >= t ? t - gmin + 1 : n;
+            for (int i = h->cp_start[d][0]; i <= h->cp_end[d][0]; i++) profile(i, i, i + gmin - 1);
+          }
+          if (gmin <= t + fng + 1 && gmax >= t + fng + 1) { h->cp_add_laser[d][0] = true; h->cp_laser_idx[d][0] = t + fng + 1 - gmin; }
+        }
+        if (bmax == EPB_BC_CPML_LASER || bmax == EPB_BC_CPML_OUTFLOW) {
+          if (gmax >= ng_ - t + 1) {
+            h->cp_end[d][1] = n;
+            h->cp_start[d][1] = gmin <= ng_ - t + 1 ? ng_ - t + 1 - gmin + 1 : 1;
+            for (int i = h->cp_start[d][1]; i <= h->cp_end[d][1]; i++) profile(i, i - 1, ng_ - (i + gmin - 1) + 1);
+          }
+          if (gmin <= ng_ - t - fng + 2 && gmax >= ng_ - t - fng + 2) {
+            h->cp_add_laser[d][1] = true;
+            h->cp_laser_idx[d][1] = ng_ - t - fng + 2 - gmin;
+          }
+        }
+        for (int q = 0; q < 2; q++) {
+          // bcoeff = EXP(-(sigma / kappa + acoeff) * tstep), ccoeff_d = (bcoeff - 1) * sigma / kappa / (sigma + kappa * acoeff) / dx
+          // (boundary.F90:1832-1835); outside the layers (sigma = a = 0) the values are never read
+          std::vector<double> bco(len, 0.0), cco(len, 0.0);
+          for (int i = 0; i < len; i++) {
+            const double kappa = kap[q][i], sigma = sig[q][i], acoeff = aa[q][i];
+            if (sigma == 0.0 && acoeff == 0.0) continue;
+            bco[i] = std::exp(-(sigma / kappa + acoeff) * tstep);
+            cco[i] = (bco[i] - 1.0) * sigma / kappa / (sigma + kappa * acoeff) / cfg->dx[d];
+          }
+          EPB_CUDA(h, cudaMalloc(&h->cp_kap[d][q], len * sizeof(double)));
+          EPB_CUDA(h, cudaMalloc(&h->cp_bco[d][q], len * sizeof(double)));
+          EPB_CUDA(h, cudaMalloc(&h->cp_cco[d][q], len * sizeof(double)));
+          EPB_CUDA(h, cudaMemcpy(h->cp_kap[d][q], kap[q].data(), len * sizeof(double), cudaMemcpyHostToDevice));
+          EPB_CUDA(h, cudaMemcpy(h->cp_bco[d][q], bco.data(), len * sizeof(double), cudaMemcpyHostToDevice));
+          EPB_CUDA(h, cudaMemcpy(h->cp_cco[d][q], cco.data(), len * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        EPB_CUDA(h, cudaMalloc(&h->cp_psi[d], 4 * h->fsize * sizeof(double)));
+        EPB_CUDA(h, cudaMemsetAsync(h->cp_psi[d], 0, 4 * h->fsize * sizeof(double), h->stream));
+      }
+    }
   }
   epb_fdtd_tma_setup(h);
   epb_make_tiles(h->cfg, h->tg);
@@ -1462,6 +1654,10 @@ int epb_destroy(epb_handle *h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaFree(h->dump_stage); cudaEventDestroy(h->dump_ready); cudaEventDestroy(h->dump_done); }
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cub_tmp); cudaFree(h->movers);
   cudaFree(h->out_count); cudaFree(h->out_idx); cudaFree(h->d_scratch); cudaFree(h->d_err); cudaFree(h->aos_stage); cudaFree(h->coll_work); cudaFree(h->prof_scratch); cudaFree(h->scal_dev);
+  for (int d = 0; d < 3; d++) {
+    cudaFree(h->cp_psi[d]);
+    for (int q = 0; q < 2; q++) { cudaFree(h->cp_kap[d][q]); cudaFree(h->cp_bco[d][q]); cudaFree(h->cp_cco[d][q]); }
+  }
   for (int q = 0; q < 4; q++) if (h->scal_ev[q]) cudaEventDestroy(h->scal_ev[q]);
   for (int q = 0; q < 8; q++) if (h->src_ev[q]) cudaEventDestroy(h->src_ev[q]);
   if (h->src_stage) cudaFreeHost(h->src_stage);
@@ -1744,6 +1940,8 @@ int epb_init_boundaries(epb_handle *h) {
   S.nd = c.ndims;
   for (int d = 0; d < 3; d++) { S.sz[d] = h->sz[d]; S.n[d] = c.n[d]; }
   S.plane = h->plane;
+  S.i0[0] = c.bc_field[0] == EPB_BC_CPML_LASER ? h->cp_laser_idx[0][0] - 1 : 1;
+  S.i0[1] = c.bc_field[1] == EPB_BC_CPML_LASER ? h->cp_laser_idx[0][1] + 1 : c.n[0];
   k_snapshot<<<nblocks(h->plane), 256, 0, h->stream>>>(S);
   h->launches++;
   for (int a = 1; a < c.ndims; a++) {

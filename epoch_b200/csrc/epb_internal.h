@@ -229,6 +229,17 @@ struct epb_handle {
   double *dump_stage = nullptr;
   cudaEvent_t dump_ready = nullptr, dump_done = nullptr;
   bool dump_pending = false;
+  // CPML (boundary.F90:1479-2025), built by epb_create when cfg.cpml_thickness > 0: per axis the kappa profiles on the E and
+  // B points and the recursion coefficients bcoeff / ccoeff_d of the half step (device, length n + 2 ng), the layers'
+  // local index ranges [axis][side], the laser plane of a cpml_laser face, four auxiliary arrays per axis (field extent)
+  bool cpml = false;
+  double *cp_kap[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [axis][0 E points, 1 B points]
+  double *cp_bco[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  double *cp_cco[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  int cp_start[3][2], cp_end[3][2];
+  int cp_laser_idx[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  bool cp_add_laser[3][2] = {{false, false}, {false, false}, {false, false}};
+  double *cp_psi[3] = {nullptr, nullptr, nullptr};   // [axis]: 4 x fsize (psi of E_b, E_c, B_b, B_c; (a, b, c) cyclic)
   // epb_step_scalars_async: device block [EPB_SCAL_MAX doubles], a ring of completion events (ticket % 4)
   double *scal_dev = nullptr;
   cudaEvent_t scal_ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -612,6 +612,7 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
   }
   if (nprod != nranks || nranks > 64) return epb_fail(oh, EPB_ERR_ARG, "epb_redistribute: nproc does not match nranks (<= 64)");
   if (nranks > 1 && !oh->nccl) return epb_fail(oh, EPB_ERR_NCCL, "epb_redistribute: epb_set_comm was not called");
+  if (oh->cpml) return epb_fail(oh, EPB_ERR_UNSUPPORTED, "epb_redistribute: the CPML auxiliary arrays are not re-cut (balance.F90:600-700 remaps them)");
   EPB_CUDA(oh, cudaStreamSynchronize(oh->stream));
   // The snapshots setup_field_boundaries took of the initial fields on laser / outflow faces are not moved: refuse
   // the (rare) deck that has non-zero ones instead of silently zeroing them

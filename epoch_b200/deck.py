@@ -34,6 +34,7 @@ femto = 1e-15
 BC = {
     "periodic": 1, "other": 2, "simple_laser": 3, "simple_outflow": 4, "open": 5,
     "zero_gradient": 7, "clamp": 8, "reflect": 9, "conduct": 10, "thermal": 11,
+    "cpml_laser": 12, "cpml_outflow": 13,
 }
 
 NG = 5  # triangle shape: png = 3, ng = png + 2 (constants.F90:549-559)
@@ -102,13 +103,30 @@ class Deck:
     smooth_strides: Sequence[int] = (1,)    # 'auto' = (1, 2, 3, 4)
     hc_push: bool = False                   # build flag -DHC_PUSH (Makefile:264): Higuera-Cary rotation, particles.F90:386-398
     cuts: Optional[dict] = None             # axis -> (mins, maxs): slabs re-cut by the load balancer (balance.F90:383-436)
+    # boundaries block (deck_boundaries_block.f90:143-152; defaults setup.F90:80-83); only read when some field
+    # boundary is cpml_laser / cpml_outflow
+    cpml_thickness: int = 6
+    cpml_kappa_max: float = 20.0
+    cpml_a_max: float = 0.15
+    cpml_sigma_max: float = 0.7
 
     # -- grid (setup.F90:162-204) ------------------------------------------
+    def cpml_t(self) -> int:
+        """cpml_thickness as the code sees it: 0 unless some field boundary is a CPML (mpi_routines.F90:285)."""
+        return int(self.cpml_thickness) if any(b in ("cpml_laser", "cpml_outflow") for b in self.bc_field) else 0
+
+    def ncells(self, d: int) -> int:
+        """nx_global after mpi_routines.F90:295-296: EVERY axis grows by 2 cpml_thickness cells as soon as one
+        boundary is a CPML; `n` keeps the deck's own cell counts."""
+        return int(self.n[d]) + 2 * self.cpml_t()
+
     def dx(self, d: int) -> float:
+        # setup.F90:168: length_x / REAL(nx_global - 2 * cpml_thickness)
         return (self.xmax[d] - self.xmin[d]) / float(self.n[d])
 
     def grid_min(self, d: int) -> float:
-        return self.xmin[d] + self.dx(d) / 2.0
+        # setup.F90:169,180: x_grid_min = x_min - dx * cpml_thickness, then shifted to the cell centre
+        return (self.xmin[d] - self.dx(d) * self.cpml_t()) + self.dx(d) / 2.0
 
     def x_global(self, d: int, i):
         """Cell-centre coordinate of global cell i (1-based), setup.F90:188."""
@@ -129,7 +147,7 @@ class Deck:
 
     def any_open(self) -> bool:
         # boundary.F90:41-57
-        return any(b in ("simple_laser", "simple_outflow", "open") for b in self.bc_field)
+        return any(b in ("simple_laser", "simple_outflow", "open") for b in self.bc_field)   # not the CPML codes
 
     # -- timestep (setup.F90:577-711; 1D :574-606; 3D :700-746) --------------
     def dt_plasma_frequency(self) -> float:
@@ -267,7 +285,7 @@ class Deck:
         if self.cuts and d in self.cuts:
             return list(self.cuts[d][0]), list(self.cuts[d][1])
         npd = max(1, self.nproc[d]) if d < self.ndims else 1
-        ng_ = self.n[d] if d < self.ndims else 1
+        ng_ = self.ncells(d) if d < self.ndims else 1
         n0 = ng_ // npd
         nxp = (n0 + 1) * npd - ng_ if n0 * npd != ng_ else npd
         mins, maxs = [], []
@@ -336,7 +354,7 @@ class Deck:
         return np.ascontiguousarray(s1.ravel()), np.ascontiguousarray(s2.ravel())
 
     def has_boundary_source(self, side: int) -> bool:
-        return side < 2 * self.ndims and self.bc_field[side] in ("simple_laser", "simple_outflow", "open")
+        return side < 2 * self.ndims and self.bc_field[side] in ("simple_laser", "simple_outflow", "open", "cpml_laser")
 
 
 class DumpClock:

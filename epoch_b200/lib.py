@@ -38,6 +38,8 @@ class Config(C.Structure):
         ("min_local", C.c_double * 3), ("max_local", C.c_double * 3),
         ("gmin", C.c_double * 3), ("gmax", C.c_double * 3),
         ("min_outer", C.c_double * 3), ("max_outer", C.c_double * 3), ("stencil", C.c_double * 15),
+        ("cpml_kappa_max", C.c_double), ("cpml_a_max", C.c_double), ("cpml_sigma_max", C.c_double),
+        ("cpml_thickness", C.c_int32), ("n_global_min", C.c_int32 * 3),
     ]
 
 

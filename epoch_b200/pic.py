@@ -54,6 +54,7 @@ def rank_geometry(deck: Deck, rank: int):
     geo = dict(n=n, gmin=g, coords=co, is_bnd=[0] * 6, grid_min_local=[0.0] * 3, min_local=[0.0] * 3,
                max_local=[0.0] * 3, min_outer=[0.0] * 3, max_outer=[0.0] * 3)
     png = 3
+    t = deck.cpml_t()
     for d in range(nd):
         npd = max(1, deck.nproc[d])
         mins, maxs = deck.cell_ranges(d)
@@ -64,10 +65,27 @@ def rank_geometry(deck: Deck, rank: int):
         hdx = 0.5 * dx
         geo["min_local"][d] = geo["grid_min_local"][d] - hdx
         geo["max_local"][d] = float(deck.x_global(d, maxs[co[d]] + 1)) - hdx
-        shift = float((1 + png + 0) // 2)
+        # utilities.f90:364-365: a CPML layer is not part of the particle domain (offsets of boundary.F90:1528-1543,
+        # :1590-1605)
+        off_min, off_max = cpml_offsets(deck, d, mins[co[d]], maxs[co[d]])
+        geo["min_local"][d] = geo["min_local"][d] + off_min * dx
+        geo["max_local"][d] = geo["max_local"][d] - off_max * dx
+        shift = float((1 + png + t) // 2)
         geo["min_outer"][d] = deck.xmin[d] - shift * dx
         geo["max_outer"][d] = deck.xmax[d] + shift * dx
     return geo
+
+
+def cpml_offsets(deck: Deck, d: int, gmin: int, gmax: int):
+    """cpml_x_min_offset / cpml_x_max_offset of a rank that owns global cells gmin..gmax of axis d."""
+    t = deck.cpml_t()
+    ng_ = deck.ncells(d)
+    off_min = off_max = 0
+    if t and deck.bc_field[2 * d] in ("cpml_laser", "cpml_outflow") and gmin <= t:
+        off_min = t - gmin + 1 if gmax >= t else t
+    if t and deck.bc_field[2 * d + 1] in ("cpml_laser", "cpml_outflow") and gmax >= ng_ - t + 1:
+        off_max = t - ng_ + gmax if gmin <= ng_ - t + 1 else t
+    return off_min, off_max
 
 
 def build_config(deck: Deck, rank: int, strict_fp: bool, sort_interval: int, capacity_factor: float,
@@ -94,7 +112,8 @@ def build_config(deck: Deck, rank: int, strict_fp: bool, sort_interval: int, cap
     cfg.ndims = nd
     for d in range(3):
         cfg.n[d] = geo["n"][d]
-        cfg.n_global[d] = deck.n[d] if d < nd else 1
+        cfg.n_global[d] = deck.ncells(d) if d < nd else 1
+        cfg.n_global_min[d] = geo["gmin"][d]
         cfg.dx[d] = deck.dx(d) if d < nd else 1.0
         cfg.grid_min_local[d] = geo["grid_min_local"][d]
         cfg.min_local[d] = geo["min_local"][d]
@@ -118,6 +137,8 @@ def build_config(deck: Deck, rank: int, strict_fp: bool, sort_interval: int, cap
     cfg.field_order = int(deck.field_order)
     cfg.maxwell_solver = deck.maxwell_solver_code()
     cfg.hc_push = int(getattr(deck, "hc_push", False))
+    cfg.cpml_thickness = deck.cpml_t()
+    cfg.cpml_kappa_max, cfg.cpml_a_max, cfg.cpml_sigma_max = deck.cpml_kappa_max, deck.cpml_a_max, deck.cpml_sigma_max
     if deck.smooth_currents:
         cfg.smooth_its = int(deck.smooth_iterations)
         cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0
@@ -133,7 +154,7 @@ def build_config(deck: Deck, rank: int, strict_fp: bool, sort_interval: int, cap
             # setup_particle_boundary (boundary.F90:108-122)
             if b in (2, 10):
                 b = 9
-            if b in (3, 4):
+            if b in (3, 4, 12, 13):
                 b = 5
             sp[i].bc_particle[k] = b
         sp[i].zero_current = int(s.zero_current)
@@ -345,7 +366,7 @@ class Simulation:
     def load_profile(self, axis: int):
         """get_load_x/y/z (balance.F90:1766-1844) over the global cells of `axis`, summed over the ranks; feed it to
         deck.calculate_breaks."""
-        out = np.zeros(self.deck.n[axis] + 2 * NG, dtype=np.int64)
+        out = np.zeros(self.deck.ncells(axis) + 2 * NG, dtype=np.int64)
         self._chk(self.L.epb_load_profile(self._h, axis, out.ctypes.data))
         return out
 

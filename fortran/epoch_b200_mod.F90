@@ -55,6 +55,9 @@ MODULE epoch_b200_mod
     REAL(C_DOUBLE) :: min_outer(3)
     REAL(C_DOUBLE) :: max_outer(3)
     REAL(C_DOUBLE) :: stencil(15)
+    REAL(C_DOUBLE) :: cpml_kappa_max, cpml_a_max, cpml_sigma_max
+    INTEGER(C_INT32_T) :: cpml_thickness
+    INTEGER(C_INT32_T) :: n_global_min(3)
   END TYPE epb_config
 
   ! struct epb_species
@@ -304,6 +307,13 @@ CONTAINS
     cfg%stencil(4) = betaxy
     cfg%stencil(6) = betayx
     cfg%stencil(13:14) = (/ deltax, deltay /)
+    ! CPML: cpml_thickness is already 0 when no field boundary is cpml_laser / cpml_outflow (mpi_routines.F90:285);
+    ! the library restates set_cpml_helpers (boundary.F90:1479-1770) from these numbers
+    cfg%cpml_thickness = cpml_thickness
+    cfg%cpml_kappa_max = cpml_kappa_max
+    cfg%cpml_a_max = cpml_a_max
+    cfg%cpml_sigma_max = cpml_sigma_max
+    cfg%n_global_min = (/ nx_global_min, ny_global_min, 1 /)
 
     ALLOCATE(sp(n_species))
     DO ispecies = 1, n_species

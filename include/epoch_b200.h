@@ -51,6 +51,8 @@ enum {
   EPB_BC_REFLECT = 9,
   EPB_BC_CONDUCT = 10,
   EPB_BC_THERMAL = 11,
+  EPB_BC_CPML_LASER = 12,
+  EPB_BC_CPML_OUTFLOW = 13,
 };
 
 /* field ids for upload/download */
@@ -87,6 +89,12 @@ typedef struct epb_config {
   double min_outer[3];      /* x_min_outer ... (utilities.f90:367-369) */
   double max_outer[3];
   double stencil[15];       /* as set_maxwell_solver leaves them: alphax..z, betaxy, betaxz, betayx, betayz, betazx, betazy, gammax..z, deltax..z */
+  /* CPML boundaries (bc_field 12 cpml_laser / 13 cpml_outflow; boundary.F90:1479-2025).  n, n_global, grid_min_local,
+   * min_local / max_local (with the cpml offsets of utilities.f90:364-365) and min_outer / max_outer are the
+   * caller's as ever; the library restates set_cpml_helpers from these four numbers and n_global_min. */
+  double cpml_kappa_max, cpml_a_max, cpml_sigma_max;   /* shared_data.F90:451 */
+  int32_t cpml_thickness;   /* cells; 0 unless a field boundary is a CPML (mpi_routines.F90:285) */
+  int32_t n_global_min[3];  /* nx_global_min ...: global index of this rank's first cell */
 } epb_config;
 
 /* Mirror of TYPE particle_species (shared_data.F90:194-285), hot-path members only */

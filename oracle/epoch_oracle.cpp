@@ -56,6 +56,8 @@ enum {
   c_bc_reflect = 9,
   c_bc_conduct = 10,
   c_bc_thermal = 11,
+  c_bc_cpml_laser = 12,
+  c_bc_cpml_outflow = 13,
 };
 
 // constants.F90:549-559 (triangle): sf_min=-1, sf_max=1, png=3, ng=png+2
@@ -118,6 +120,10 @@ struct Config {
   int smooth_its, smooth_comp_its, smooth_nstrides, smooth_strides[4];
   int force_mixed;  // test hook: take the per-species current_bcs path even if all species agree
   int hc_push;      // -DHC_PUSH: Higuera-Cary gamma in the rotation (particles.F90:386-398)
+  // CPML boundaries (boundary.F90:1479-2025); defaults of setup.F90:80-83: 6, 20, 0.15, 0.7.  Ignored (thickness 0)
+  // unless some bc_field is cpml_laser / cpml_outflow (mpi_routines.F90:285)
+  int cpml_thickness;
+  double cpml_kappa_max, cpml_a_max, cpml_sigma_max;
 };
 
 // random_generator.f90:23-78 (KISS), :112-173 (polar Box-Muller)
@@ -190,6 +196,15 @@ struct Rank {
   // thermal particle boundaries: ext_temp_x_min ... (shared_data.F90:255-256), [species][side] = (plane, 3): the two
   // transverse axes in axis order with ghost cells, lower axis fastest; empty = never set
   std::vector<std::vector<std::vector<double>>> ext_temp;
+  // CPML (boundary.F90:1479-1770): per axis the stretching profiles on the E and the B points (index i - (1 - NG),
+  // 1.0 / 0.0 outside the layers), the local index range of the two layers [axis][side] (start > end: none here),
+  // the particle-domain offsets, the laser plane of a cpml_laser face, and the four auxiliary arrays of the axis
+  // (psi of E_b, E_c, B_b, B_c for the cyclic (a, b, c))
+  std::vector<double> kap_e[3], kap_b[3], sig_e[3], sig_b[3], a_e[3], a_b[3];
+  int cp_start[3][2], cp_end[3][2], cp_off[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  int laser_idx[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  bool add_laser_cpml[3][2] = {{false, false}, {false, false}, {false, false}};
+  Arr psi[3][4];
   std::vector<std::vector<Particle>> part;       // per species
   std::vector<std::vector<int64_t>> bnd_cand;    // boundary candidate indices per species
   Rng rng;
@@ -208,6 +223,8 @@ struct World {
   bool periods[3] = {false, false, false};
   int bc_field[6];
   int bc_allspecies[6];
+  int cpml_t = 0;          // cpml_thickness, 0 without CPML boundaries
+  int n_ext[3] = {1, 1, 1};  // nx_global after mpi_routines.F90:295-296 (deck value + 2 cpml_thickness)
   bool bc_mixed = false;   // c_bc_mixed on some boundary: J is folded per species (boundary.F90:547-556, 790-796)
   double dt;
   std::vector<Rank> r;
@@ -216,6 +233,79 @@ struct World {
 inline double x_global(const World &w, int d, int i) {
   // setup.F90:188  x_global(ix) = x_grid_min + (ix - 1) * dx
   return w.grid_min[d] + (double)(i - 1) * w.d[d];
+}
+
+// set_cpml_helpers + allocate_cpml_fields (boundary.F90:1479-1794; epoch3d :1891-2330, epoch1d :783-925): the same
+// code per axis.  kappa / sigma / a on the E points (integer positions) and on the B points (half positions), the
+// layer's local index range, the offset that keeps the layer out of the particle domain (utilities.f90:364-365) and
+// the laser plane cpml_thickness + fng + 1 cells in.
+inline bool is_cpml(int b) { return b == c_bc_cpml_laser || b == c_bc_cpml_outflow; }
+void set_cpml_helpers(World &w, Rank &R) {
+  const Config &cf = w.cfg;
+  const int t = w.cpml_t;
+  const int cpml_m = 3, cpml_ma = 1;
+  const int fng = (cf.field_order ? cf.field_order : 2) / 2;   // fields.f90:37
+  for (int d = 0; d < w.nd; d++) {
+    const int n = R.n[d], len = n + 2 * NG;
+    R.kap_e[d].assign(len, 1.0); R.kap_b[d].assign(len, 1.0);
+    R.sig_e[d].assign(len, 0.0); R.sig_b[d].assign(len, 0.0);
+    R.a_e[d].assign(len, 0.0); R.a_b[d].assign(len, 0.0);
+    for (int sd = 0; sd < 2; sd++) { R.cp_start[d][sd] = n + 1; R.cp_end[d][sd] = 0; R.cp_off[d][sd] = 0; }
+    if (t == 0) continue;
+    const int gmin = R.gmin[d], gmax = R.gmin[d] + n - 1, ng_ = w.n_ext[d];
+    // note: dx of the FIRST axis for every axis's sigma (boundary.F90:1517 uses dx for x and y alike)
+    const double sigma_maxval = cf.cpml_sigma_max * c * 0.8 * (cpml_m + 1.0) / w.d[0];
+    auto pw = [](double x, int e) { double r = 1.0; for (int q = 0; q < e; q++) r = r * x; return r; };
+    auto at = [&](std::vector<double> &v, int i) -> double & { return v[i - (1 - NG)]; };
+    if (is_cpml(w.bc_field[2 * d])) {
+      if (gmin <= t) {
+        R.cp_start[d][0] = 1;
+        if (gmax >= t) { R.cp_end[d][0] = t - gmin + 1; R.cp_off[d][0] = t - gmin + 1; }
+        else { R.cp_end[d][0] = n; R.cp_off[d][0] = t; }
+        for (int i = R.cp_start[d][0]; i <= R.cp_end[d][0]; i++) {
+          const int ig = i + gmin - 1;
+          double x_pos = 1.0 - (double)(ig - 1) / (double)t;
+          at(R.kap_e[d], i) = 1.0 + (cf.cpml_kappa_max - 1.0) * pw(x_pos, cpml_m);
+          at(R.sig_e[d], i) = sigma_maxval * pw(x_pos, cpml_m);
+          at(R.a_e[d], i) = cf.cpml_a_max * pw(1.0 - x_pos, cpml_ma);
+          x_pos = 1.0 - ((double)ig - 0.5) / (double)t;
+          at(R.kap_b[d], i) = 1.0 + (cf.cpml_kappa_max - 1.0) * pw(x_pos, cpml_m);
+          at(R.sig_b[d], i) = sigma_maxval * pw(x_pos, cpml_m);
+          at(R.a_b[d], i) = cf.cpml_a_max * pw(1.0 - x_pos, cpml_ma);
+        }
+      }
+      if (gmin <= t + fng + 1 && gmax >= t + fng + 1) {
+        R.add_laser_cpml[d][0] = true;
+        R.laser_idx[d][0] = t + fng + 1 - gmin;
+      }
+    }
+    if (is_cpml(w.bc_field[2 * d + 1])) {
+      if (gmax >= ng_ - t + 1) {
+        R.cp_end[d][1] = n;
+        if (gmin <= ng_ - t + 1) { R.cp_start[d][1] = ng_ - t + 1 - gmin + 1; R.cp_off[d][1] = t - ng_ + gmax; }
+        else { R.cp_start[d][1] = 1; R.cp_off[d][1] = t; }
+        for (int i = R.cp_start[d][1]; i <= R.cp_end[d][1]; i++) {
+          const int ig = ng_ - (i + gmin - 1) + 1;
+          double x_pos = 1.0 - (double)(ig - 1) / (double)t;
+          at(R.kap_e[d], i) = 1.0 + (cf.cpml_kappa_max - 1.0) * pw(x_pos, cpml_m);
+          at(R.sig_e[d], i) = sigma_maxval * pw(x_pos, cpml_m);
+          at(R.a_e[d], i) = cf.cpml_a_max * pw(1.0 - x_pos, cpml_ma);
+          x_pos = 1.0 - ((double)ig - 0.5) / (double)t;
+          at(R.kap_b[d], i - 1) = 1.0 + (cf.cpml_kappa_max - 1.0) * pw(x_pos, cpml_m);
+          at(R.sig_b[d], i - 1) = sigma_maxval * pw(x_pos, cpml_m);
+          at(R.a_b[d], i - 1) = cf.cpml_a_max * pw(1.0 - x_pos, cpml_ma);
+        }
+      }
+      if (gmin <= ng_ - t - fng + 2 && gmax >= ng_ - t - fng + 2) {
+        R.add_laser_cpml[d][1] = true;
+        R.laser_idx[d][1] = ng_ - t - fng + 2 - gmin;
+      }
+    }
+    // utilities.f90:364-365
+    R.min_local[d] = R.min_local[d] + R.cp_off[d][0] * w.d[d];
+    R.max_local[d] = R.max_local[d] - R.cp_off[d][1] * w.d[d];
+    for (int q = 0; q < 4; q++) R.psi[d][q].init(R.n, w.nd);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -239,7 +329,7 @@ void setup_world(World &w) {
       int &b = s.bc_particle[i];
       // boundary.F90:108-122
       if (b == c_bc_other || b == c_bc_conduct) b = c_bc_reflect;
-      if (b == c_bc_simple_laser || b == c_bc_simple_outflow) b = c_bc_open;
+      if (b == c_bc_simple_laser || b == c_bc_simple_outflow || b == c_bc_cpml_laser || b == c_bc_cpml_outflow) b = c_bc_open;
     }
   // deck_species_block.F90:182-199
   for (int i = 0; i < 6; i++) w.bc_allspecies[i] = c_bc_open;
@@ -255,14 +345,19 @@ void setup_world(World &w) {
     for (int i = 0; i < 2 * nd; i++)
       w.bc_allspecies[i] = (cf.bc_field[i] == c_bc_periodic) ? c_bc_periodic : c_bc_open;
 
-  // setup.F90:167-181 (cpml_thickness = 0)
+  // boundary.F90:43-48, mpi_routines.F90:285, :295-296: every axis grows by 2 cpml_thickness cells as soon as one
+  // boundary is a CPML; setup.F90:167-181: dx from the deck's cell count, the grid starts cpml_thickness cells out
+  w.cpml_t = 0;
+  for (int i = 0; i < 2 * nd; i++)
+    if (w.bc_field[i] == c_bc_cpml_laser || w.bc_field[i] == c_bc_cpml_outflow) w.cpml_t = cf.cpml_thickness;
   for (int d = 0; d < nd; d++) {
+    w.n_ext[d] = cf.n_global[d] + 2 * w.cpml_t;
     w.length[d] = cf.xmax[d] - cf.xmin[d];
-    w.d[d] = w.length[d] / (double)cf.n_global[d];
-    double g = cf.xmin[d] - w.d[d] * 0.0;
+    w.d[d] = w.length[d] / (double)(w.n_ext[d] - 2 * w.cpml_t);
+    double g = cf.xmin[d] - w.d[d] * w.cpml_t;
     w.grid_min[d] = g + w.d[d] / 2.0;
     // utilities.f90:367-369
-    double boundary_shift = (double)((1 + png + 0) / 2);
+    double boundary_shift = (double)((1 + png + w.cpml_t) / 2);
     w.min_outer[d] = cf.xmin[d] - boundary_shift * w.d[d];
     w.max_outer[d] = cf.xmax[d] + boundary_shift * w.d[d];
   }
@@ -277,7 +372,7 @@ void setup_world(World &w) {
   int np[3] = {1, 1, 1};
   for (int d = 0; d < nd; d++) {
     np[d] = std::max(1, cf.nproc[d]);
-    int ng_ = cf.n_global[d];
+    int ng_ = w.n_ext[d];
     int n0 = ng_ / np[d];
     int nxp = (n0 * np[d] != ng_) ? (n0 + 1) * np[d] - ng_ : np[d];
     w.cell_min[d].resize(np[d]);
@@ -330,6 +425,7 @@ void setup_world(World &w) {
           R.neighbour[iz + 1][iy + 1][ix + 1] = op ? (t[2] * np[1] + t[1]) * np[0] + t[0] : -1;
         }
     for (int i = 0; i < NFIELD; i++) R.f[i].init(R.n, nd);
+    set_cpml_helpers(w, R);
     int pn[3] = {1, R.n[1], R.n[2]};
     for (int i = 0; i < 6; i++) {
       // planes (1-ng:ny+ng, 1-ng:nz+ng) stored with a unit x extent
@@ -503,7 +599,7 @@ void field_bcs3(World &w, int f0, bool mpi_only) {
     int b = w.bc_field[i];
     if (b == c_bc_clamp || b == c_bc_simple_laser || b == c_bc_simple_outflow)
       for (int q = 0; q < 3; q++) field_mirror(w, f0 + q, i, -1.0);
-    if (b == c_bc_zero_gradient)
+    if (b == c_bc_zero_gradient || b == c_bc_cpml_laser || b == c_bc_cpml_outflow)   // boundary.F90:845-851, :898-904
       for (int q = 0; q < 3; q++) field_mirror(w, f0 + q, i, +1.0);
   }
 }
@@ -524,6 +620,60 @@ static inline void fd_coeffs(int order, double base, double *cc) {
   else { cc[0] = base; cc[1] = 0.0; cc[2] = 0.0; }
 }
 
+// cpml_advance_e_currents / cpml_advance_b_currents (boundary.F90:1813-2023; epoch3d :2365-2790, epoch1d :929-1040),
+// one routine for every axis a with (b, c) the cyclic successors: in the layer
+//   psi_Eb = bcoeff psi_Eb + ccoeff_d (B_c(i) - B_c(i-1)),  E_b -= fac psi_Eb;   psi_Ec likewise from B_b,  E_c += fac psi_Ec
+//   psi_Bb = bcoeff psi_Bb + ccoeff_d (E_c(i+1) - E_c(i)),  B_b += tstep psi_Bb; psi_Bc likewise from E_b,  B_c -= tstep psi_Bc
+// over the interior of the other axes; the B form of a max layer runs one point lower (start-1 .. end-1).
+template <int ND>
+void cpml_advance_currents(World &w, double tstep, bool efield) {
+  const double fac = tstep * (c * c);
+  for (Rank &R : w.r)
+    for (int a = 0; a < ND; a++) {
+      const int b = (a + 1) % 3, cc = (a + 2) % 3;
+      for (int sd = 0; sd < 2; sd++) {
+        if (!is_cpml(w.bc_field[2 * a + sd])) continue;
+        int i0 = R.cp_start[a][sd], i1 = R.cp_end[a][sd];
+        if (!efield && sd == 1) { i0 -= 1; i1 -= 1; }
+        const std::vector<double> &kap = efield ? R.kap_e[a] : R.kap_b[a];
+        const std::vector<double> &sig = efield ? R.sig_e[a] : R.sig_b[a];
+        const std::vector<double> &aa = efield ? R.a_e[a] : R.a_b[a];
+        Arr &Fb = R.f[(efield ? EX : BX) + b], &Fc = R.f[(efield ? EX : BX) + cc];
+        const Arr &Gb = R.f[(efield ? BX : EX) + b], &Gc = R.f[(efield ? BX : EX) + cc];
+        Arr &psb = R.psi[a][efield ? 0 : 2], &psc = R.psi[a][efield ? 1 : 3];
+        int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
+        for (int d = 0; d < ND; d++) if (d != a) hi[d] = R.n[d];
+        int e[3] = {0, 0, 0};
+        e[a] = 1;
+        for (int ipos = i0; ipos <= i1; ipos++) {
+          const double kappa = kap[ipos - (1 - NG)], sigma = sig[ipos - (1 - NG)], acoeff = aa[ipos - (1 - NG)];
+          const double bcoeff = std::exp(-(sigma / kappa + acoeff) * tstep);
+          const double ccoeff_d = (bcoeff - 1.0) * sigma / kappa / (sigma + kappa * acoeff) / w.d[a];
+          for (int k = lo[2]; k <= hi[2]; k++)
+            for (int j = lo[1]; j <= hi[1]; j++)
+              for (int i = lo[0]; i <= hi[0]; i++) {
+                int p[3] = {i, j, k};
+                p[a] = ipos;
+                const int q0 = p[0], q1 = p[1], q2 = p[2];
+                if (efield) {
+                  const int m0 = q0 - e[0], m1 = q1 - e[1], m2 = q2 - e[2];
+                  psb(q0, q1, q2) = bcoeff * psb(q0, q1, q2) + ccoeff_d * (Gc(q0, q1, q2) - Gc(m0, m1, m2));
+                  Fb(q0, q1, q2) = Fb(q0, q1, q2) - fac * psb(q0, q1, q2);
+                  psc(q0, q1, q2) = bcoeff * psc(q0, q1, q2) + ccoeff_d * (Gb(q0, q1, q2) - Gb(m0, m1, m2));
+                  Fc(q0, q1, q2) = Fc(q0, q1, q2) + fac * psc(q0, q1, q2);
+                } else {
+                  const int u0 = q0 + e[0], u1 = q1 + e[1], u2 = q2 + e[2];
+                  psb(q0, q1, q2) = bcoeff * psb(q0, q1, q2) + ccoeff_d * (Gc(u0, u1, u2) - Gc(q0, q1, q2));
+                  Fb(q0, q1, q2) = Fb(q0, q1, q2) + tstep * psb(q0, q1, q2);
+                  psc(q0, q1, q2) = bcoeff * psc(q0, q1, q2) + ccoeff_d * (Gb(u0, u1, u2) - Gb(q0, q1, q2));
+                  Fc(q0, q1, q2) = Fc(q0, q1, q2) - tstep * psc(q0, q1, q2);
+                }
+              }
+        }
+      }
+    }
+}
+
 template <int ND>
 void update_e_field(World &w, double hdt) {
   const double cnx = hdt / w.d[0] * (c * c);
@@ -536,6 +686,7 @@ void update_e_field(World &w, double hdt) {
   fd_coeffs(order, cnx, cx);
   fd_coeffs(order, cny, cy);
   fd_coeffs(order, cnz, cz);
+  const bool cpml = w.cpml_t > 0;
   for (Rank &R : w.r) {
     Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
     const Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
@@ -545,6 +696,11 @@ void update_e_field(World &w, double hdt) {
     for (int iz = k0; iz <= k1; iz++)
       for (int iy = j0; iy <= j1; iy++)
         for (int ix = 0; ix <= R.n[0]; ix++) {
+          if (cpml) {   // fields.f90:112-204: cpml_x = cnx / cpml_kappa_ex(ix), cx1 = c1 * cpml_x, ...
+            fd_coeffs(order, cnx / R.kap_e[0][ix - (1 - NG)], cx);
+            if (ND >= 2) fd_coeffs(order, cny / R.kap_e[1][iy - (1 - NG)], cy);
+            if (ND >= 3) fd_coeffs(order, cnz / R.kap_e[2][iz - (1 - NG)], cz);
+          }
           // backward differences: term k is f(i+k) - f(i-k-1)
           auto dxb = [&](const Arr &f, int k) {
             return ND == 1 ? f(ix + k) - f(ix - k - 1)
@@ -590,6 +746,7 @@ void update_e_field(World &w, double hdt) {
           }
         }
   }
+  if (cpml) cpml_advance_currents<ND>(w, hdt, true);   // fields.f90:204
 }
 
 template <int ND>
@@ -605,6 +762,7 @@ void update_b_field(World &w, double hdt) {
   fd_coeffs(order, hdtz, cz);
   const bool ext = w.cfg.maxwell_solver != 0;  // fields.f90:441-465, epoch3d :655-730, epoch1d :304-312
   const Config &cf = w.cfg;
+  const bool cpml = w.cpml_t > 0;
   for (Rank &R : w.r) {
     const Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ];
     Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
@@ -613,6 +771,13 @@ void update_b_field(World &w, double hdt) {
     for (int iz = k0; iz <= k1; iz++)
       for (int iy = j0; iy <= j1; iy++)
         for (int ix = 0; ix <= R.n[0]; ix++) {
+          double hx_ = hdtx, hy_ = hdty, hz_ = hdtz;
+          if (cpml) {   // fields.f90:306-420: cx1 = hdtx / cpml_kappa_bx(ix) (times c1.. for the higher orders)
+            hx_ = hdtx / R.kap_b[0][ix - (1 - NG)];
+            fd_coeffs(order, hx_, cx);
+            if (ND >= 2) { hy_ = hdty / R.kap_b[1][iy - (1 - NG)]; fd_coeffs(order, hy_, cy); }
+            if (ND >= 3) { hz_ = hdtz / R.kap_b[2][iz - (1 - NG)]; fd_coeffs(order, hz_, cz); }
+          }
           // forward differences: term k is f(i+k+1) - f(i-k)
           auto dxf = [&](const Arr &f, int k) {
             return ND == 1 ? f(ix + k + 1) - f(ix - k)
@@ -672,16 +837,16 @@ void update_b_field(World &w, double hdt) {
               return v;
             };
             if (ND == 1) {
-              by(ix) = by(ix) + hdtx * dd(ez, 0);
-              bz(ix) = bz(ix) - hdtx * dd(ey, 0);
+              by(ix) = by(ix) + hx_ * dd(ez, 0);
+              bz(ix) = bz(ix) - hx_ * dd(ey, 0);
             } else if (ND == 2) {
-              bx(ix, iy) = bx(ix, iy) - hdty * dd(ez, 1);
-              by(ix, iy) = by(ix, iy) + hdtx * dd(ez, 0);
-              bz(ix, iy) = bz(ix, iy) - hdtx * dd(ey, 0) + hdty * dd(ex, 1);
+              bx(ix, iy) = bx(ix, iy) - hy_ * dd(ez, 1);
+              by(ix, iy) = by(ix, iy) + hx_ * dd(ez, 0);
+              bz(ix, iy) = bz(ix, iy) - hx_ * dd(ey, 0) + hy_ * dd(ex, 1);
             } else {
-              bx(ix, iy, iz) = bx(ix, iy, iz) - hdty * dd(ez, 1) + hdtz * dd(ey, 2);
-              by(ix, iy, iz) = by(ix, iy, iz) - hdtz * dd(ex, 2) + hdtx * dd(ez, 0);
-              bz(ix, iy, iz) = bz(ix, iy, iz) - hdtx * dd(ey, 0) + hdty * dd(ex, 1);
+              bx(ix, iy, iz) = bx(ix, iy, iz) - hy_ * dd(ez, 1) + hz_ * dd(ey, 2);
+              by(ix, iy, iz) = by(ix, iy, iz) - hz_ * dd(ex, 2) + hx_ * dd(ez, 0);
+              bz(ix, iy, iz) = bz(ix, iy, iz) - hx_ * dd(ey, 0) + hy_ * dd(ex, 1);
             }
           } else if (ND == 2) {
             double v = bx(ix, iy);
@@ -710,6 +875,7 @@ void update_b_field(World &w, double hdt) {
           }
         }
   }
+  if (cpml) cpml_advance_currents<ND>(w, hdt, false);   // fields.f90:420 region: after the B update
 }
 
 // ---------------------------------------------------------------------------
@@ -727,26 +893,31 @@ void outflow_bcs_x(World &w, bool is_max, double dt) {
   const double sum = 1.0 / (lx + c);
   const double diff = lx - c;
   const double dt_eps = dt / epsilon0;
+  const bool cpml_face = w.bc_field[is_max ? 1 : 0] == c_bc_cpml_laser;
   for (Rank &R : w.r) {
     if (!R.is_bnd[is_max ? 1 : 0]) continue;
+    // a cpml_laser face: only where the laser plane lies on this rank (add_laser, boundary.F90:1572-1577), and the
+    // plane is cpml_x_min_laser_idx / cpml_x_max_laser_idx instead of 1 / nx (laser.f90:320-323, :396-399)
+    if (cpml_face && !R.add_laser_cpml[0][is_max ? 1 : 0]) continue;
     Arr &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
     const Arr &ey = R.f[EY], &ez = R.f[EZ], &jy = R.f[JY], &jz = R.f[JZ];
     const Arr *snap = is_max ? R.snap_max : R.snap_min;
     const Arr &s1 = R.src1[is_max ? 1 : 0], &s2 = R.src2[is_max ? 1 : 0];
     const int k0 = ND >= 3 ? 0 : 1, k1 = ND >= 3 ? R.n[2] : 1;
     const int j0 = ND >= 2 ? 0 : 1, j1 = ND >= 2 ? R.n[1] : 1;
-    const int nx = R.n[0];
+    const int nx = cpml_face ? R.laser_idx[0][1] : R.n[0];
+    const int lp_min = cpml_face ? R.laser_idx[0][0] : 1;
     // all right-hand sides use pre-update values (Fortran array assignment);
     // bz is written before by is evaluated but by's RHS never reads bz.
     for (int k = k0; k <= k1; k++)
       for (int j = j0; j <= j1; j++) {
-        if (!is_max) bx(0, j, k) = snap[BX](1, j, k);
+        if (!is_max) bx(lp_min - 1, j, k) = snap[BX](1, j, k);
         else bx(nx + 1, j, k) = snap[BX](1, j, k);
       }
     for (int k = k0; k <= k1; k++)
       for (int j = j0; j <= j1; j++) {
         if (!is_max) {
-          const int lp = 1;
+          const int lp = lp_min;
           double t = 4.0 * s1(1, j, k) + 2.0 * (snap[EY](1, j, k) + c * snap[BZ](1, j, k)) -
                      2.0 * ey(lp, j, k);
           if (ND == 3) t = t - lz * (bx(lp, j, k) - bx(lp, j, k - 1));
@@ -764,7 +935,7 @@ void outflow_bcs_x(World &w, bool is_max, double dt) {
     for (int k = k0; k <= k1; k++)
       for (int j = j0; j <= j1; j++) {
         if (!is_max) {
-          const int lp = 1;
+          const int lp = lp_min;
           double t = -4.0 * s2(1, j, k) - 2.0 * (snap[EZ](1, j, k) - c * snap[BY](1, j, k)) +
                      2.0 * ez(lp, j, k);
           if (ND >= 2) t = t - ly * (bx(lp, j, k) - bx(lp, j - 1, k));
@@ -785,7 +956,10 @@ void outflow_bcs_x(World &w, bool is_max, double dt) {
 // setup.F90:391-447 (x boundaries only)
 void setup_field_boundaries(World &w) {
   for (Rank &R : w.r) {
-    const int nx0 = 1, nx1 = R.n[0];
+    // setup.F90:409-412: a cpml_laser face takes its snapshot one plane outside the laser plane
+    int nx0 = 1, nx1 = R.n[0];
+    if (w.bc_field[0] == c_bc_cpml_laser) nx0 = R.laser_idx[0][0] - 1;
+    if (w.bc_field[1] == c_bc_cpml_laser) nx1 = R.laser_idx[0][1] + 1;
     for (int f = 0; f < 6; f++) {
       const Arr &a = R.f[f];
       Arr &lo = R.snap_min[f], &hi = R.snap_max[f];
@@ -804,7 +978,8 @@ void setup_field_boundaries(World &w) {
           const Arr &a = R.f[f];
           Arr &q = R.snapA[ax][sd][f];
           const bool avg = f < 3 ? (f == ax) : (f - 3 != ax);
-          const int n0 = sd == 0 ? 1 : R.n[ax];
+          int n0 = sd == 0 ? 1 : R.n[ax];
+          if (w.bc_field[2 * ax + sd] == c_bc_cpml_laser) n0 = sd == 0 ? R.laser_idx[ax][0] - 1 : R.laser_idx[ax][1] + 1;
           int e[3] = {0, 0, 0};
           e[ax] = 1;
           for (int k = q.lo[2]; k < q.lo[2] + q.sz[2]; k++)
@@ -830,15 +1005,17 @@ void outflow_bcs_axis(World &w, int a, bool is_max, double dt) {
   const double sum = 1.0 / (l[a] + c);
   const double diff = l[a] - c;
   const double dt_eps = dt / epsilon0;
+  const bool cpml_face = w.bc_field[2 * a + (is_max ? 1 : 0)] == c_bc_cpml_laser;
   for (Rank &R : w.r) {
     if (!R.is_bnd[2 * a + (is_max ? 1 : 0)]) continue;
+    if (cpml_face && !R.add_laser_cpml[a][is_max ? 1 : 0]) continue;
     Arr &Ba = R.f[BX + a], &Bb = R.f[BX + b], &Bc = R.f[BX + cc];
     const Arr &Eb = R.f[EX + b], &Ec = R.f[EX + cc], &Jb = R.f[JX + b], &Jc = R.f[JX + cc];
     const Arr *snap = R.snapA[a][is_max ? 1 : 0];
     const Arr &s1 = R.srcA[a][is_max ? 1 : 0][0], &s2 = R.srcA[a][is_max ? 1 : 0][1];
     int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
     for (int d = 0; d < ND; d++) if (d != a) { lo[d] = 0; hi[d] = R.n[d]; }
-    const int lp = is_max ? R.n[a] : 1;
+    const int lp = cpml_face ? R.laser_idx[a][is_max ? 1 : 0] : (is_max ? R.n[a] : 1);
     int ea[3] = {0, 0, 0}, eb[3] = {0, 0, 0}, ec[3] = {0, 0, 0};
     ea[a] = 1; eb[b] = 1; ec[cc] = 1;
     auto at = [&](const Arr &A, const int *p, const int *e, int m) {
@@ -894,13 +1071,16 @@ void outflow_bcs_axis(World &w, int a, bool is_max, double dt) {
 template <int ND>
 void bfield_final_bcs(World &w, double dt) {
   bfield_bcs(w, false);
+  // add_laser(i) .OR. simple_outflow (boundary.F90:918-940): a cpml_laser face has add_laser on the rank that holds
+  // the laser plane (the outflow routines skip the others); a cpml_outflow face only absorbs
   for (int s = 0; s < 2; s++) {
     int b = w.bc_field[s];
-    if (b == c_bc_simple_laser || b == c_bc_simple_outflow) outflow_bcs_x<ND>(w, s == 1, dt);
+    if (b == c_bc_simple_laser || b == c_bc_simple_outflow || b == c_bc_cpml_laser) outflow_bcs_x<ND>(w, s == 1, dt);
   }
   for (int s = 2; s < 2 * ND; s++) {
     int b = w.bc_field[s];
-    if (b == c_bc_simple_laser || b == c_bc_simple_outflow) outflow_bcs_axis<ND>(w, s / 2, (s & 1) == 1, dt);
+    if (b == c_bc_simple_laser || b == c_bc_simple_outflow || b == c_bc_cpml_laser)
+      outflow_bcs_axis<ND>(w, s / 2, (s & 1) == 1, dt);
   }
   bfield_bcs(w, true);
 }
@@ -1295,7 +1475,7 @@ void thermal_reemit(World &w, Rank &R, int is, Particle &cur, int d, int side, d
 void particle_bcs(World &w) {
   const int nd = w.nd;
   double shift[3];
-  for (int d = 0; d < nd; d++) shift[d] = w.length[d] + 2.0 * w.d[d] * 0.0;
+  for (int d = 0; d < nd; d++) shift[d] = w.length[d] + 2.0 * w.d[d] * (double)w.cpml_t;   // boundary.F90:1047-1048
   for (size_t is = 0; is < w.sp.size(); is++) {
     const SpeciesCfg &S = w.sp[is];
     // send lists per rank per direction
@@ -1311,7 +1491,11 @@ void particle_bcs(World &w) {
           const double part_pos = cur.pos[d];
           // min side (:1076-1159)
           int sgn = -1;
-          if (part_pos < R.min_local[d]) {
+          if (is_cpml(w.bc_field[2 * d])) {   // boundary.F90:1077-1089: the layer belongs to the boundary rank
+            if (R.is_bnd[2 * d]) {
+              if (part_pos < w.min_outer[d]) { bd[d] = 0; out_of_bounds = true; }
+            } else if (part_pos < R.min_local[d]) bd[d] = sgn;
+          } else if (part_pos < R.min_local[d]) {
             bd[d] = sgn;
             int bc = S.bc_particle[2 * d];
             if (bc == c_bc_reflect) {
@@ -1335,7 +1519,11 @@ void particle_bcs(World &w) {
           }
           // max side (:1161-1244)
           sgn = 1;
-          if (part_pos >= R.max_local[d]) {
+          if (is_cpml(w.bc_field[2 * d + 1])) {   // boundary.F90:1162-1174
+            if (R.is_bnd[2 * d + 1]) {
+              if (part_pos >= w.max_outer[d]) { bd[d] = 0; out_of_bounds = true; }
+            } else if (part_pos >= R.max_local[d]) bd[d] = sgn;
+          } else if (part_pos >= R.max_local[d]) {
             bd[d] = sgn;
             int bc = S.bc_particle[2 * d + 1];
             if (bc == c_bc_reflect) {
@@ -1950,7 +2138,7 @@ void auto_load(World &w) {
               int gi = ii[d] + R.gmin[d] - 1;
               // periodic images of ghost cells map back into the domain
               if (w.bc_field[2 * d] == c_bc_periodic) {
-                int ng_ = w.cfg.n_global[d];
+                int ng_ = w.n_ext[d];
                 gi = ((gi - 1) % ng_ + ng_) % ng_ + 1;
               }
               double xc = x_global(w, d, gi);
@@ -2002,7 +2190,7 @@ void auto_load(World &w) {
             for (int d = 0; d < nd; d++) {
               int gi = ii[d] + R.gmin[d] - 1;
               if (w.bc_field[2 * d] == c_bc_periodic) {
-                int ng_ = w.cfg.n_global[d];
+                int ng_ = w.n_ext[d];
                 gi = ((gi - 1) % ng_ + ng_) % ng_ + 1;
               }
               double xc = x_global(w, d, gi);

@@ -25,6 +25,8 @@ class _Config(C.Structure):
         ("st_delta", C.c_double * 3),
         ("smooth_its", C.c_int), ("smooth_comp_its", C.c_int), ("smooth_nstrides", C.c_int),
         ("smooth_strides", C.c_int * 4), ("force_mixed", C.c_int), ("hc_push", C.c_int),
+        ("cpml_thickness", C.c_int), ("cpml_kappa_max", C.c_double), ("cpml_a_max", C.c_double),
+        ("cpml_sigma_max", C.c_double),
     ]
 
 
@@ -118,6 +120,10 @@ class Oracle:
             cfg.st_beta[i] = st[k]
         cfg.force_mixed = int(getattr(deck, "force_mixed_bc", False))
         cfg.hc_push = int(getattr(deck, "hc_push", False))
+        cfg.cpml_thickness = int(getattr(deck, "cpml_thickness", 6))
+        cfg.cpml_kappa_max = float(getattr(deck, "cpml_kappa_max", 20.0))
+        cfg.cpml_a_max = float(getattr(deck, "cpml_a_max", 0.15))
+        cfg.cpml_sigma_max = float(getattr(deck, "cpml_sigma_max", 0.7))
         if getattr(deck, "smooth_currents", False):
             cfg.smooth_its = int(deck.smooth_iterations)
             cfg.smooth_comp_its = 1 if deck.smooth_compensation else 0

@@ -1,0 +1,231 @@
+"""CPML field boundaries (boundary.F90:1479-2025 set_cpml_helpers / cpml_advance_*_currents,
+fields.f90:112-204 and :306-420 kappa stretching, laser.f90:320-323 laser plane, setup.F90:168-169 / :409-412 and
+mpi_routines.F90:285-296 grid extension, utilities.f90:364-369 particle domain and outer edge).
+
+Pinned on the reference's own CPML decks AS WRITTEN (epoch2d/tests/maxwell_solvers/{yee,lehe_x,pukhov}/input.deck:
+cpml_laser on x_min, cpml_outflow on x_max, periodic in y) and on the number the reference binary printed for one of
+them (epoch2d/tests/test_maxwell_solvers.py:163-165); the CUDA path is then held to the oracle."""
+import numpy as np
+import pytest
+
+from epoch_b200 import deck as D
+from oracle.oracle import Oracle
+from tests import decks
+
+
+def maxwell_deck(solver, nproc=(1, 1, 1), t_end=75 * D.femto):
+    """epoch2d/tests/maxwell_solvers/<solver>/input.deck"""
+    nx = 240
+    ny = nx // 3
+    L = 12 * D.micron
+    las = D.Laser("x_min", D.Laser.amp_from_intensity_w_cm2(1.0e15), 2 * D.pi * D.c / (0.5 * D.micron),
+                  profile=lambda y, z: D.gauss(y, 0.0, 4 * D.micron),
+                  t_profile=lambda t: D.gauss(t, 8 * D.femto, 1.8 * D.femto))
+    return D.Deck(2, [nx, ny], [-L, -L], [L, L], ["cpml_laser", "cpml_outflow", "periodic", "periodic"], lasers=[las],
+                  t_end=t_end, dt_snapshot=25 * D.femto, maxwell_solver=solver, nproc=nproc)
+
+
+def _group_velocity(dk):
+    o = Oracle(dk)
+    nxe, nye = dk.ncells(0), dk.ncells(1)                   # the dump holds the whole grid, CPML cells included
+    x = dk.grid_min(0) + np.arange(nxe) * dk.dx(0)          # grid_mid of Ey along x
+    tx = []
+
+    def dump(step, t):                                      # xt2 of test_maxwell_solvers.py:66-76
+        ey = o.interior(0, "ey").reshape(nye, nxe)
+        b = float(np.sum(ey ** 2))
+        if b > 0 and t > 0:
+            tx.append((t, float(np.sum(x[None, :] * ey ** 2) / b)))
+
+    D.run(dk, o, [0], dump)
+    assert len(tx) == 3
+    tx = np.array(tx)
+    return np.polyfit(tx[:, 0], tx[:, 1], 1)[0]
+
+
+def test_geometry_with_cpml():
+    """mpi_routines.F90:295-296 (both axes grow by 2 x 6 cells although only x has CPML faces), setup.F90:168-169,
+    utilities.f90:364-369 (the layer is outside the particle domain; outer edge (1 + png + 6) / 2 = 5 cells out),
+    boundary.F90:1572-1577 / :1634-1640 (laser planes), one rank and 3 x 2 ranks."""
+    from epoch_b200 import pic
+    dk = maxwell_deck("yee")
+    assert dk.cpml_t() == 6 and dk.ncells(0) == 252 and dk.ncells(1) == 92
+    assert dk.dx(0) == 24 * D.micron / 240
+    assert np.isclose(dk.grid_min(0), -12 * D.micron - 6 * dk.dx(0) + 0.5 * dk.dx(0), rtol=1e-15)
+    geo = pic.rank_geometry(dk, 0)
+    assert np.isclose(geo["min_local"][0], -12 * D.micron, atol=1e-20) and np.isclose(geo["max_local"][0], 12 * D.micron, atol=1e-20)
+    # y is periodic: no offsets there, the box is simply 12 cells longer
+    assert np.isclose(geo["min_local"][1], -12 * D.micron - 6 * dk.dx(1), atol=1e-20)
+    assert np.isclose(geo["min_outer"][0], -12 * D.micron - 5 * dk.dx(0), atol=1e-20)
+    o = Oracle(dk)
+    info = o.rank_info(0)
+    assert info["n"][:2] == [252, 92]
+    for key in ("grid_min_local", "min_local", "max_local"):
+        assert info[key][:2] == geo[key][:2], key
+    dk6 = maxwell_deck("yee", nproc=(3, 2, 1))
+    o6 = Oracle(dk6)
+    lo, hi = o6.outer()
+    for r in range(6):
+        info, geo = o6.rank_info(r), pic.rank_geometry(dk6, r)
+        assert info["n"] == geo["n"] and info["gmin"] == geo["gmin"]
+        for key in ("grid_min_local", "min_local", "max_local"):
+            assert info[key][:2] == geo[key][:2], (r, key)
+        assert lo[:2] == geo["min_outer"][:2] and hi[:2] == geo["max_outer"][:2]
+
+
+def test_reference_cpml_decks_group_velocity():
+    """epoch2d/tests/test_maxwell_solvers.py:150-171 on the decks as written: the slope of the Ey^2 centroid over
+    dumps 1..3 equals the Lehe / Pukhov / Yee group velocity to rtol 0.012.  For the Pukhov deck the oracle also
+    reproduces the number the reference binary printed (:163, "pukhov 292013249.255") in every digit, which pins the
+    CPML restatement -- stretching profiles, auxiliary currents, laser plane, grid extension -- on reference output.
+    (The two other comments, yee 289199289.192 and lehe_x 312016227.758, are not reproduced: 288297786.835 and
+    312148240.814, 3e-3 and 4e-4 away; the same three decks share every line but the solver name, so those comments
+    predate the current solver code, like two of the custom-stencil comments.)"""
+    c = D.c
+    lam = 0.5 * D.micron
+    k_l = 2 * np.pi / lam
+    for solver in ("pukhov", "lehe_x", "yee"):
+        dk = maxwell_deck(solver)
+        dx, dy = dk.dx(0), dk.dx(1)
+        vg_sim = _group_velocity(dk)
+        dt_lehe = 0.95 / np.sqrt(max(1.0 / dx ** 2, 1.0 / dy ** 2)) / c
+        dt_yee = 0.95 * dx * dy / np.sqrt(dx ** 2 + dy ** 2) / c
+        dt_pukhov = 0.95 * min(dx, dy) / c
+        vg = dict(lehe_x=c * (1.0 + 2.0 * (1.0 - c * dt_lehe / dx) * (k_l * dx / 2.0) ** 2),
+                  yee=c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt_yee / dx * np.sin(k_l * dx / 2.0)) ** 2),
+                  pukhov=c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt_pukhov / dx * np.sin(k_l * dx / 2.0)) ** 2))
+        assert np.isclose(vg_sim, vg[solver], rtol=0.012), (solver, vg_sim, vg[solver])
+        if solver == "pukhov":
+            assert np.isclose(vg_sim, 292013249.255, rtol=5e-12, atol=0), vg_sim
+
+
+def test_cpml_decomposed_equals_single_rank():
+    """The layers' index ranges, offsets and laser planes per rank (boundary.F90:1528-1543, :1590-1605): the same
+    deck on 3 x 2 ranks (the x_min layer and the laser plane inside rank 0's 84 cells, the x_max layer in the last)
+    gives the same fields as on one rank."""
+    a = Oracle(maxwell_deck("yee", t_end=30 * D.femto))
+    b = Oracle(maxwell_deck("yee", nproc=(3, 2, 1), t_end=30 * D.femto))
+    D.run(a.deck, a, [0], None)
+    D.run(b.deck, b, list(range(6)), None)
+    for name in ("ey", "bz", "ex"):
+        whole = a.interior(0, name).reshape(92, 252)
+        for r in range(6):
+            info = b.rank_info(r)
+            n, g = info["n"], info["gmin"]
+            part = b.interior(r, name).reshape(n[1], n[0])
+            ref = whole[g[1] - 1:g[1] - 1 + n[1], g[0] - 1:g[0] - 1 + n[0]]
+            assert np.array_equal(part, ref), (name, r)
+
+
+@pytest.mark.parametrize("ndims", [1, 2, 3])
+def test_cpml_absorbs(ndims):
+    """A pulse launched from a cpml_laser face leaves through the cpml_outflow face: once it has crossed the box,
+    less than 1e-4 of the field energy that was in the box is left (1D, 2D with CPML on all four faces; 2e-3 in the
+    narrow 3D box, where the pulse runs at grazing incidence along the four side layers)."""
+    lam = 1.0 * D.micron
+    n = {1: [120], 2: [100, 24], 3: [60, 10, 10]}[ndims]
+    L = [n[0] * lam / 12.0] + [n[d] * lam / 4.0 for d in range(1, ndims)]
+    bcs = ["cpml_laser", "cpml_outflow"] + ["cpml_outflow"] * (2 * (ndims - 1))
+    las = D.Laser("x_min", 1.0e11, 2 * D.pi * D.c / lam, t_profile=lambda t: D.gauss(t, 8 * D.femto, 3 * D.femto),
+                  t_end=16 * D.femto)
+    t_cross = L[0] / D.c
+    dk = D.Deck(ndims, n, [0.0] * ndims, L, bcs, lasers=[las], t_end=16 * D.femto + 2.5 * t_cross)
+    o = Oracle(dk)
+    energy = []
+
+    def dump(step, t):
+        pass
+
+    def total():
+        return sum(float(np.sum(o.interior(0, f) ** 2)) for f in ("ey", "ez")) + \
+            D.c ** 2 * sum(float(np.sum(o.interior(0, f) ** 2)) for f in ("by", "bz"))
+
+    class Probe:
+        def __getattr__(self, k):
+            return getattr(o, k)
+
+        def fields_final(self):
+            o.fields_final()
+            energy.append(total())
+
+        def set_laser_source(self, lr, side, s1, s2):
+            o.set_laser_source(lr, side, s1, s2)
+
+    D.run(dk, Probe(), [0], None)
+    e = np.array(energy)
+    assert np.isfinite(e).all()
+    assert e[-1] < (2.0e-3 if ndims == 3 else 1.0e-4) * e.max(), (e[-1] / e.max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CUDA path against the oracle
+# ---------------------------------------------------------------------------------------------------------
+def _cpml_case(ndims, order=2, solver="yee", particles=False):
+    lam = 1.0 * D.micron
+    n = {1: [96], 2: [64, 40], 3: [36, 14, 12]}[ndims]
+    L = [n[d] * lam / 12.0 for d in range(ndims)]
+    bcs = {1: ["cpml_laser", "cpml_outflow"],
+           2: ["cpml_laser", "cpml_outflow", "cpml_outflow", "cpml_laser"],
+           3: ["cpml_laser", "cpml_outflow", "periodic", "periodic", "cpml_outflow", "cpml_outflow"]}[ndims]
+    las = [D.Laser("x_min", 3.0e11, 2 * D.pi * D.c / lam, t_profile=lambda t: D.gauss(t, 3 * D.femto, 1.5 * D.femto))]
+    if ndims == 2:
+        las.append(D.Laser("y_max", 1.0e11, 2 * D.pi * D.c / lam, pol_angle=0.5))
+    sp = []
+    if particles:
+        lo = tuple(0.3 * L[d] if d < ndims else -1e300 for d in range(3))
+        hi = tuple(0.7 * L[d] if d < ndims else 1e300 for d in range(3))
+        sp = [D.Species("electron", -D.q0, D.m0, npart_per_cell=4, density=1.0e25, temp=(3.0e9,) * 3,
+                        box_lo=lo, box_hi=hi)]
+    return D.Deck(ndims, n, [0.0] * ndims, L, bcs, lasers=las, species=sp, nsteps=40, t_end=1.0,
+                  field_order=order, maxwell_solver=solver)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndims,order,solver,particles", [
+    (1, 2, "yee", False), (2, 2, "yee", False), (3, 2, "yee", False), (2, 4, "yee", False), (1, 6, "yee", False),
+    (2, 2, "pukhov", False), (3, 2, "lehe_x", False), (2, 2, "yee", True), (3, 2, "yee", True), (1, 2, "yee", True)])
+def test_cpml_matches_oracle_gpu(ndims, order, solver, particles):
+    """Device vs oracle with CPML faces (lasers on an x and, in 2D, a y face; field orders 2/4/6; an extended
+    stencil; a hot plasma slab whose particles run into the layers and out through the outer edge): fields to 1e-12,
+    particle bookkeeping exact."""
+    from tests.gpu_util import FIELDS, make_pair, rel_l2, run_both
+    dk = _cpml_case(ndims, order, solver, particles)
+    o, sim = make_pair(dk, strict=True, sort_interval=2)
+    run_both(dk, o, sim, dk.nsteps)
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-12, name
+    assert float(np.abs(o.field(0, "ey")).max()) > 0.0
+    if particles:
+        assert sim.count(0) == o.count(0, 0)
+        assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+        assert o.count(0, 0) < o.get_particles(0, 0).shape[0] + 1
+
+
+@pytest.mark.gpu
+def test_reference_cpml_deck_gpu():
+    """The reference's Pukhov CPML deck as written, on the device: the same group velocity as the reference binary
+    printed (292013249.255) to 1e-9 (the fields follow the oracle to 1e-12; the centroid fit inherits that)."""
+    from epoch_b200.pic import Simulation
+    dk = maxwell_deck("pukhov")
+    sim = Simulation(dk, strict_fp=True)
+    nxe, nye = dk.ncells(0), dk.ncells(1)
+    x = dk.grid_min(0) + np.arange(nxe) * dk.dx(0)
+    tx = []
+
+    def dump(step, t):
+        ey = sim.interior("ey").reshape(nye, nxe)
+        b = float(np.sum(ey ** 2))
+        if b > 0 and t > 0:
+            tx.append((t, float(np.sum(x[None, :] * ey ** 2) / b)))
+
+    class One:
+        def __getattr__(self, k):
+            return getattr(sim, k)
+
+        def set_laser_source(self, lr, side, s1, s2):
+            sim.set_laser_source(0, side, s1, s2)
+
+    D.run(dk, One(), [0], dump)
+    tx = np.array(tx)
+    vg_sim = np.polyfit(tx[:, 0], tx[:, 1], 1)[0]
+    assert np.isclose(vg_sim, 292013249.255, rtol=1e-9, atol=0), vg_sim
