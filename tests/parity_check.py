@@ -51,6 +51,11 @@ def make_deck(name, world):
         return decks.laser2d_y(nproc=(1, world, 1) if world < 4 else (2, world // 2, 1)), 40, 1e-12
     if name == "laser2d":
         return decks.laser2d(nproc=(world, 1, 1), n=64), 40, 1e-12
+    if name in ("cpml2d", "cpml2d_y", "cpml3d"):   # CPML layers, laser planes and particle-domain offsets across ranks
+        from tests.test_cpml import _cpml_case
+        dk = _cpml_case(3 if name == "cpml3d" else 2, particles=True)
+        dk.nproc = (1, world, 1) if name == "cpml2d_y" else (world, 1, 1) if world < 4 else (2, world // 2, 1)
+        return dk, 40, 1e-12
     raise KeyError(name)
 
 
