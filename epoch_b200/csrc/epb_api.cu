@@ -1763,6 +1763,28 @@ int epb_upload_species(epb_handle *h, int is, int64_t n, const double *packed) {
   h->pushes_since_sort = 1 << 30;  // force a sort before the next push
   return EPB_OK;
 }
+// Particles the host creates in mid-run (run_injectors, injectors.F90:150-330; insert_particles of the moving window,
+// window.F90:182-320 -- both evaluate deck expressions and draw from the host's random stream, so they stay EPOCH's):
+// appended to the species in the wire layout, like append_partlist onto attached_list.  The arena of a slot-layout
+// species must exist (epb_upload_species / epb_load_uniform came first).
+int epb_append_species(epb_handle *h, int is, int64_t n, const double *packed) {
+  if (!h || is < 0 || is >= (int)h->sp.size() || n < 0 || (n > 0 && !packed)) return EPB_ERR_ARG;
+  if (n == 0) return EPB_OK;
+  SpeciesDev &S = h->sp[is];
+  if (S.slots && !S.arena_ready) return epb_upload_species(h, is, n, packed);
+  const int nv = h->cfg.ndims + 4;
+  const int64_t CH = 2 << 20;
+  if (!h->aos_stage) EPB_CUDA(h, cudaMalloc(&h->aos_stage, (size_t)CH * 7 * sizeof(double)));
+  for (int64_t i0 = 0; i0 < n; i0 += CH) {
+    const int64_t mm = std::min<int64_t>(CH, n - i0);
+    EPB_CUDA(h, cudaMemcpyAsync(h->aos_stage, packed + i0 * nv, (size_t)mm * nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = epb_species_insert_aos(h, is, h->aos_stage, mm);
+    if (rc) return rc;
+    EPB_CUDA(h, cudaStreamSynchronize(h->stream));   // the staging buffer and the caller's array are free again
+  }
+  return S.slots ? epb_slots_check(h) : EPB_OK;
+}
+
 int epb_download_species(epb_handle *h, int is, int64_t n, double *packed) {
   if (!h || is < 0 || is >= (int)h->sp.size()) return EPB_ERR_ARG;
   SpeciesDev &S = h->sp[is];

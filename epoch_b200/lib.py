@@ -18,7 +18,7 @@ FIELD_NAMES = ("ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz")
 SYMBOLS = (
     "epb_create", "epb_destroy", "epb_last_error", "epb_version", "epb_abi_info", "epb_set_stream", "epb_synchronize",
     "epb_nccl_unique_id", "epb_set_comm", "epb_upload_field", "epb_download_field", "epb_download_field_async", "epb_wait_downloads",
-    "epb_upload_species", "epb_download_species", "epb_species_count", "epb_load_uniform",
+    "epb_upload_species", "epb_download_species", "epb_append_species", "epb_species_count", "epb_load_uniform",
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
     "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy", "epb_step_scalars_async", "epb_wait_scalars",
@@ -107,6 +107,7 @@ def load():
     L.epb_wait_downloads.argtypes = [vp]
     L.epb_upload_species.argtypes = [vp, i32, i64, dp]
     L.epb_download_species.argtypes = [vp, i32, i64, dp]
+    L.epb_append_species.argtypes = [vp, i32, i64, dp]
     L.epb_species_count.argtypes = [vp, i32, C.POINTER(i64)]
     L.epb_load_uniform.argtypes = [vp, i32, C.c_int32, C.c_double, dp, dp, C.c_uint64]
     L.epb_cell_counts.argtypes = [vp, i32, dp]

@@ -261,6 +261,11 @@ class Simulation:
         p = np.ascontiguousarray(packed, dtype=np.float64)
         self._chk(self.L.epb_upload_species(self._h, isp, p.shape[0], p.ctypes.data))
 
+    def append_species(self, isp: int, packed):
+        """Particles the host creates in mid-run (injectors, the moving window's insertions) join the species."""
+        p = np.ascontiguousarray(packed, dtype=np.float64)
+        self._chk(self.L.epb_append_species(self._h, isp, p.shape[0], p.ctypes.data))
+
     def count(self, isp: int) -> int:
         n = C.c_int64()
         self._chk(self.L.epb_species_count(self._h, isp, C.byref(n)))

@@ -138,6 +138,9 @@ int epb_download_field_async(epb_handle *h, int field, double *host);
 int epb_wait_downloads(epb_handle *h);
 int epb_upload_species(epb_handle *h, int ispecies, int64_t n, const double *packed);
 int epb_download_species(epb_handle *h, int ispecies, int64_t n, double *packed);
+/* append_partlist(species%attached_list, ...): particles the host creates in mid-run (run_injectors,
+ * injectors.F90:150-330; the moving window's insert_particles, window.F90:182-320) join the species */
+int epb_append_species(epb_handle *h, int ispecies, int64_t n, const double *packed);
 int epb_species_count(epb_handle *h, int ispecies, int64_t *n);   /* attached_list%count */
 /* device-side loader for the bench: npart_per_cell particles per cell, uniform
  * density, Maxwellian momenta (stands in for auto_load, helper.F90:95, whose

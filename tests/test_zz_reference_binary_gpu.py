@@ -65,6 +65,45 @@ def test_energy_diagnostics_and_history_gpu():
     assert np.abs(tot / tot[0] - 1.0).max() < 1.0e-4
 
 
+@pytest.mark.parametrize("ndims,n", [(1, (96,)), (2, (40, 24)), (3, (18, 9, 7))])
+def test_append_species_gpu(ndims, n):
+    """epb_append_species (what the shim calls after run_injectors / insert_particles): a species uploaded in two
+    halves with some steps in between the appends behaves as the oracle with the same particles -- after the append
+    the device holds exactly the union, and the following steps agree in counts per cell and in the fields."""
+    from epoch_b200.pic import Simulation
+    from oracle.oracle import Oracle
+    from tests import decks
+    from tests.gpu_util import FIELDS, rel_l2, sorted_rows
+    dk = decks.thermal(ndims, n, ppc=6, temp_k=2.0e8)
+    o = Oracle(dk)
+    o.auto_load()
+    p = o.get_particles(0, 0).copy()
+    half = p.shape[0] // 2
+    o.set_particles(0, 0, p[:half])
+    sim = Simulation(dk, strict_fp=True, sort_interval=2, capacity_factor=3.0)
+    sim.upload_species(0, p[:half])
+    o.init(); sim.init()
+
+    def step():
+        o.fields_half(); sim.fields_half()
+        o.push(); sim.push()
+        o.current_finish(); sim.current_finish()
+        o.fields_final(); sim.fields_final()
+
+    for _ in range(3):
+        step()
+    q = o.get_particles(0, 0).copy()
+    o.set_particles(0, 0, np.concatenate([q, p[half:]]))       # append_partlist
+    sim.append_species(0, p[half:])
+    assert sim.count(0) == p.shape[0] == o.count(0, 0)
+    assert np.array_equal(sorted_rows(sim.download_species(0)), sorted_rows(o.get_particles(0, 0)))
+    for _ in range(4):
+        step()
+    assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
+    for name in FIELDS:
+        assert rel_l2(sim.download_field(name), o.field(0, name)) <= 1e-12, name
+
+
 @pytest.mark.parametrize("ndims,n", [(2, (40, 24)), (3, (18, 9, 7))])
 def test_step_scalars_async_gpu(ndims, n):
     """epb_step_scalars_async (the pipelined form of update_particle_count + calc_total_energy_sum): the numbers
