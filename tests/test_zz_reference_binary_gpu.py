@@ -96,7 +96,12 @@ def test_append_species_gpu(ndims, n):
     o.set_particles(0, 0, np.concatenate([q, p[half:]]))       # append_partlist
     sim.append_species(0, p[half:])
     assert sim.count(0) == p.shape[0] == o.count(0, 0)
-    assert np.array_equal(sorted_rows(sim.download_species(0)), sorted_rows(o.get_particles(0, 0)))
+    a, b = sorted_rows(sim.download_species(0)), sorted_rows(o.get_particles(0, 0))
+    # three steps in: the summation order of J differs between the two, so the old half agrees to round-off of each
+    # column's scale; the appended half is on the device exactly as it was handed over
+    assert np.all(np.abs(a - b) <= 1e-9 * np.abs(b).max(axis=0))
+    rows = {r.tobytes() for r in a}
+    assert all(r.tobytes() in rows for r in p[half:])
     for _ in range(4):
         step()
     assert np.array_equal(sim.cell_counts(0), o.cell_counts(0, 0))
