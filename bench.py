@@ -198,6 +198,26 @@ def run_reference(args):
             vals.append(b)
     v = sum(b["value"] for b in vals) / len(vals)
     sample = vals[-1]["sample"]
+    # The samples above are independent periodic domains, one per core: they pay no exchange.  For the record, ONE
+    # domain through the multi-rank oracle (2 x 2 ranks in one process, i.e. with the halo / current-sum / particle
+    # exchange of boundary.F90 but on one core) against the same domain on one rank: what decomposition costs the CPU
+    # algorithm itself.
+    decomposed = None
+    try:
+        from oracle.oracle import Oracle
+        res = {}
+        for name, nproc in (("one_rank", (1, 1)), ("four_ranks_2x2", (2, 2))):
+            dk = c2_deck(256 // nproc[0], 64, nproc)
+            o = Oracle(dk)
+            o.auto_load()
+            o.init()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                o.fields_half(); o.push(); o.current_finish(); o.fields_final()
+            res[name] = 256 * 256 * 64 * 2 / (time.perf_counter() - t0)
+        decomposed = {"unit": UNIT, "cores": 1, "sample": "C2 physics at 256x256 cells, 64 ppc, 2 steps", **res}
+    except Exception as e:
+        decomposed = {"error": f"{type(e).__name__}: {e}"[:200]}
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(b["wall_s"] for b in vals) / len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -209,6 +229,7 @@ def run_reference(args):
                                    "Yee order 2 (BASELINE C2)",
                        "sampled": True},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "decomposed": decomposed,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
