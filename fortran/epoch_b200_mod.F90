@@ -130,6 +130,15 @@ MODULE epoch_b200_mod
       REAL(C_DOUBLE), INTENT(IN) :: packed(*)
       INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION epb_append_species(handle, ispecies, n, packed) &
+        BIND(C, NAME='epb_append_species') RESULT(rc)
+      IMPORT :: C_INT, C_INT64_T, C_PTR, C_DOUBLE
+      TYPE(C_PTR), VALUE :: handle
+      INTEGER(C_INT), VALUE :: ispecies
+      INTEGER(C_INT64_T), VALUE :: n
+      REAL(C_DOUBLE), INTENT(IN) :: packed(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     FUNCTION epb_download_species(handle, ispecies, n, packed) &
         BIND(C, NAME='epb_download_species') RESULT(rc)
       IMPORT :: C_INT, C_INT64_T, C_PTR, C_DOUBLE
@@ -209,6 +218,13 @@ MODULE epoch_b200_mod
 
   TYPE(C_PTR), SAVE :: b200 = C_NULL_PTR
   LOGICAL, SAVE :: b200_fields_on_host = .TRUE.
+  ! device record: pos(1..ndims), p(1..3), weight
+  INTEGER, PARAMETER :: b200_nv = c_ndims + 4
+#ifdef PER_SPECIES_WEIGHT
+  INTEGER, PARAMETER :: b200_has_weight = 0
+#else
+  INTEGER, PARAMETER :: b200_has_weight = 1
+#endif
 
 CONTAINS
 
@@ -240,7 +256,9 @@ CONTAINS
     IF (info(1) /= C_SIZEOF(cfg)) CALL b200_check(1_C_INT)
     ! The device layout is pos(1..ndims), p(1..3), weight: builds whose pack_particle carries anything else
     ! (-DPER_SPECIES_WEIGHT, -DPER_PARTICLE_CHARGE_MASS, -DPARTICLE_ID, ..., partlist.F90:43-85) are refused
-    IF (nvar /= c_ndims + 4) THEN
+    ! -DPER_SPECIES_WEIGHT builds carry no weight per particle (shared_data.F90:101): b200_pack / b200_unpack below
+    ! write species%weight into the device's weight column and drop it again on the way back
+    IF (nvar /= c_ndims + 3 + b200_has_weight) THEN
       IF (rank == 0) PRINT *, '*** ERROR *** epoch_b200: unsupported particle layout, nvar =', nvar
       CALL abort_code(c_err_generic_error)
     END IF
@@ -362,12 +380,11 @@ CONTAINS
 
     DO ispecies = 1, n_species
       npart = species_list(ispecies)%attached_list%count
-      ALLOCATE(buf(MAX(npart * nvar, 1_i8)))
+      ALLOCATE(buf(MAX(npart * b200_nv, 1_i8)))
       cur => species_list(ispecies)%attached_list%head
       ipart = 0
       DO WHILE (ASSOCIATED(cur))
-        ! wire layout of pack_particle (partlist.F90:414-486)
-        CALL pack_particle(buf(ipart*nvar+1:(ipart+1)*nvar), cur)
+        CALL b200_pack(buf(ipart*b200_nv+1:(ipart+1)*b200_nv), cur, species_list(ispecies))
         ipart = ipart + 1
         cur => cur%next
       END DO
@@ -376,6 +393,68 @@ CONTAINS
     END DO
 
   END SUBROUTINE b200_upload
+
+
+
+  ! One particle in the device's record layout: the wire layout of pack_particle (partlist.F90:414-486) for the default
+  ! build; for -DPER_SPECIES_WEIGHT the species' weight fills the weight column.
+  SUBROUTINE b200_pack(rec, cur, species)
+
+    REAL(num), INTENT(OUT) :: rec(:)
+    TYPE(particle), POINTER :: cur
+    TYPE(particle_species), INTENT(IN) :: species
+
+#ifdef PER_SPECIES_WEIGHT
+    rec(1:c_ndims) = cur%part_pos(1:c_ndims)
+    rec(c_ndims+1:c_ndims+3) = cur%part_p(1:3)
+    rec(c_ndims+4) = species%weight
+#else
+    CALL pack_particle(rec, cur)
+#endif
+
+  END SUBROUTINE b200_pack
+
+
+
+  SUBROUTINE b200_unpack(rec, cur)
+
+    REAL(num), INTENT(IN) :: rec(:)
+    TYPE(particle), POINTER :: cur
+
+#ifdef PER_SPECIES_WEIGHT
+    cur%part_pos(1:c_ndims) = rec(1:c_ndims)
+    cur%part_p(1:3) = rec(c_ndims+1:c_ndims+3)
+#else
+    CALL unpack_particle(rec, cur)
+#endif
+
+  END SUBROUTINE b200_unpack
+
+
+
+  ! Particles the host created in mid-run (run_injectors, injectors.F90:150-330; the moving window's insert_particles):
+  ! call with the list that was appended to species_list(ispecies)%attached_list, right after append_partlist.
+  SUBROUTINE b200_append(ispecies, list)
+
+    INTEGER, INTENT(IN) :: ispecies
+    TYPE(particle_list), INTENT(IN) :: list
+    REAL(num), ALLOCATABLE, TARGET :: buf(:)
+    TYPE(particle), POINTER :: cur
+    INTEGER(i8) :: ipart
+
+    IF (list%count <= 0) RETURN
+    ALLOCATE(buf(list%count * b200_nv))
+    cur => list%head
+    ipart = 0
+    DO WHILE (ASSOCIATED(cur) .AND. ipart < list%count)
+      CALL b200_pack(buf(ipart*b200_nv+1:(ipart+1)*b200_nv), cur, species_list(ispecies))
+      ipart = ipart + 1
+      cur => cur%next
+    END DO
+    CALL b200_check(epb_append_species(b200, ispecies - 1, ipart, buf))
+    DEALLOCATE(buf)
+
+  END SUBROUTINE b200_append
 
 
 
@@ -402,14 +481,14 @@ CONTAINS
 
     DO ispecies = 1, n_species
       CALL b200_check(epb_species_count(b200, ispecies - 1, npart))
-      ALLOCATE(buf(MAX(npart * nvar, 1_i8)))
+      ALLOCATE(buf(MAX(npart * b200_nv, 1_i8)))
       CALL b200_check(epb_download_species(b200, ispecies - 1, npart, buf))
       CALL destroy_partlist(species_list(ispecies)%attached_list)
       CALL create_allocated_partlist(species_list(ispecies)%attached_list, npart)
       cur => species_list(ispecies)%attached_list%head
       ipart = 0
       DO WHILE (ASSOCIATED(cur))
-        CALL unpack_particle(buf(ipart*nvar+1:(ipart+1)*nvar), cur)
+        CALL b200_unpack(buf(ipart*b200_nv+1:(ipart+1)*b200_nv), cur)
         ipart = ipart + 1
         cur => cur%next
       END DO
