@@ -427,7 +427,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cells", dest="n", type=int, default=4096, help="cells per side per GPU")
     ap.add_argument("--ppc", type=int, default=None)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 (default, the bench line): 2D 4096^2 x 64 ppc per GPU; c4: 3D 384^3 x 8 ppc per GPU; "
                          "c3: 2D laser-solid (laser on x_min, overdense e-/p+ foil), pinned nprocx x nprocy, load "
                          "balancer off and on")
@@ -452,6 +452,8 @@ def main():
         if args.n == 4096:
             args.n = 2048
         args.ppc = args.ppc or 32
+    if args.workload == "c5" and args.n == 4096:
+        args.n = 2048
     args.ppc = args.ppc or 64
     if args.sort_interval <= 0:
         args.sort_interval = 2 if (args.workload == "c2" and variant in (2, 3, 4)) else 8
@@ -481,6 +483,11 @@ def main():
         dk = c4_deck(args.n, args.ppc, nproc)
     elif args.workload == "c3":
         nproc, dk = None, None
+    elif args.workload == "c5":
+        # BASELINE config 5: a dense plasma with binary collisions every step (collisions.F90): the C2 deck at solid
+        # density and 1e6 K, electron-electron collisions (Nanbu-Perez, coulomb_log = auto) after every push
+        nproc = split_2d(world)
+        dk = c2_deck(args.n, args.ppc, nproc, temp_k=1.0e6, density=1.0e28)
     else:
         nproc = split_2d(world)
         dk = c2_deck(args.n, args.ppc, nproc)
@@ -534,7 +541,24 @@ def main():
             sm.set_comm(bytes(idt.cpu().tolist()))
         sm.load_uniform(0, seed=20261017, mixed=mixed)
         sm.init()
+        if args.workload == "c5":   # PROGRAM pic's collision step: after push_particles, before current_finish
+            def step_with_collisions(sm=sm):
+                sm.fields_half()
+                sm.push()
+                if coll_events is not None:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    sm.collide([[1.0]])
+                    b.record(stream)
+                    coll_events.append((a, b))
+                else:
+                    sm.collide([[1.0]])
+                sm.current_finish()
+                sm.fields_final()
+            sm.step = step_with_collisions
         return sm
+
+    coll_events = None
 
     sim = make_sim(False)
     n_local = sim.count(0)
@@ -555,6 +579,8 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.workload == "c5":
+        coll_events = []
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
@@ -562,6 +588,10 @@ def main():
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    collide_ms = None
+    if coll_events:
+        collide_ms = sum(a.elapsed_time(b) for a, b in coll_events) / len(coll_events)
+    coll_events = None
     clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - launches0
     push_ms, push_n = sim.push_kernel_ms(reset=2)
@@ -725,6 +755,9 @@ def main():
             "config": {"workload": (f"epoch3d uniform thermal plasma, periodic, {args.n}^3 cells per GPU, "
                                     f"{args.ppc} ppc ({n_local} particles per GPU), triangle shape, Yee order 2 "
                                     "(BASELINE C4 per-GPU share)") if is3d else
+                                   (f"epoch2d dense plasma (1e28 m^-3, 1e6 K) with binary collisions every step (electron-electron, "
+                                    f"Nanbu-Perez, coulomb_log = auto), periodic, {args.n}x{args.n} cells per GPU, {args.ppc} ppc "
+                                    f"({n_local} particles per GPU) (BASELINE config 5)") if args.workload == "c5" else
                                    (f"epoch2d uniform thermal plasma, periodic, {args.n}x{args.n} cells per GPU, "
                                     f"{args.ppc} ppc ({n_local} particles per GPU), triangle shape, Yee order 2 "
                                     "(BASELINE C2)"),
@@ -752,6 +785,9 @@ def main():
             line["cpu_baseline"] = b
         if mixed_state is not None:
             line["mixed_state"] = mixed_state
+        if collide_ms is not None:
+            line["collisions"] = {"kernel_ms_per_step": collide_ms, "pairs_per_s": 0.5 * n_local / (collide_ms * 1e-3),
+                                  "note": "epb_collide incl. the inbox settle and the per-cell moments of coulomb_log = auto"}
         if not args.no_e2e_full and world == 1 and not is3d:
             try:
                 line["e2e_full"] = e2e_full()
