@@ -254,6 +254,7 @@ struct epb_handle {
   bool bc_mixed = false;
   int bc_species = -1;          // species whose codes the current exchange uses (-1: bc_allspecies)
   double *sendbuf = nullptr, *recvbuf = nullptr;  // halo + particle staging
+  int xcap[27] = {0};            // records per direction of the fixed-size particle messages (agreed at epb_set_comm)
   size_t sendbuf_elems = 0, recvbuf_elems = 0;
   void *nccl = nullptr;         // ncclComm_t
   std::string err;

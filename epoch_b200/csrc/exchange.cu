@@ -142,6 +142,68 @@ __global__ void __launch_bounds__(256) k_punpack(const __grid_constant__ PUnpack
     if (O.key) O.key[i] = -1;  // no emitted sort record for an arrival
   }
 }
+// ---- the same exchange without a host round trip (slot layout) ------------------------------------------------
+// Every direction's message has a FIXED size agreed at epb_set_comm: a header record whose first double is the
+// number of particles that follow, then room for xcap records.  The counts never visit the host, so the host can
+// enqueue the whole step (and the next one) without waiting for the push kernel.  NVLink makes the padding cheap:
+// at C2 the four face messages are 13 MB each, microseconds per step.
+struct PPackDevOp {
+  const double *src[7];
+  int nv, nd;
+  const int *idx;        // outbox list of this direction
+  const int *count_dev;  // its device counter
+  int xcap, out_cap;
+  double *buf;           // header record + xcap records
+  int *err;
+};
+__global__ void __launch_bounds__(256) k_ppack_dev(const __grid_constant__ PPackDevOp O) {
+  int n = *O.count_dev;
+  if (n > O.out_cap) {                    // the outbox list itself overflowed: those leavers were not recorded
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(O.err, 8);
+    n = O.out_cap;
+  }
+  if (n > O.xcap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(O.err, 4);   // more leavers than the agreed message holds
+    n = O.xcap;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) O.buf[0] = (double)n;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = O.idx[t];
+    double *o = O.buf + (size_t)(t + 1) * O.nv;
+    int q = 0;
+    for (int d = 0; d < O.nd; d++) o[q++] = O.src[d][i];
+    for (int d = 3; d < 7; d++) o[q++] = O.src[d][i];
+  }
+}
+struct PUnpackDevOp {
+  double *dst[7];
+  int nv, nd;
+  const double *buf;     // header record + records
+  int xcap;
+  int *mcount;           // device count of the mover buffer the arrivals are appended to
+  unsigned char *flag;
+  int cap;
+  int *err;
+};
+__global__ void __launch_bounds__(256) k_punpack_dev(const __grid_constant__ PUnpackDevOp O) {
+  int n = (int)O.buf[0];
+  if (n < 0) n = 0;
+  if (n > O.xcap) n = O.xcap;
+  const long long first = (long long)*O.mcount;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const double *o = O.buf + (size_t)(t + 1) * O.nv;
+    const long long i = first + t;
+    if (i >= O.cap) { atomicOr(O.err, 2); continue; }
+    O.flag[i] = 0;
+    int q = 0;
+    for (int d = 0; d < O.nd; d++) O.dst[d][i] = o[q++];
+    for (int d = 3; d < 7; d++) O.dst[d][i] = o[q++];
+  }
+}
+__global__ void k_bump_count_dev(int *count_dev, const double *header) {
+  int n = (int)header[0];
+  if (n > 0) *count_dev += n;
+}
 // survivors in the tail [n_new, n_old) that must move into holes below n_new
 __global__ void __launch_bounds__(256) k_tail_movers(const unsigned char *gone, long long n_new, long long n_old,
                                                      int *movers, int *counter) {
@@ -196,7 +258,35 @@ extern "C" int epb_nccl_unique_id(void *id128) {
 extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
   if (!h || !id128) return EPB_ERR_ARG;
   if (h->cfg.nranks <= 1) return EPB_OK;
-  return epb_comm_init(h, id128);
+  int rc = epb_comm_init(h, id128);
+  if (rc) return rc;
+  // message capacities of the host-round-trip-free particle exchange: per axis, the particles of one cell layer
+  // of the fullest species buffer (what can cross a face in one step at most in a uniform plasma, v dt < dx; a
+  // thermal plasma sends a few per cent of that), at least 64 Ki; edges and corners a 64th of the largest.  Both ends of a message must use the same number: maximum over the ranks.
+  const epb_config &c = h->cfg;
+  long long prop[4] = {0, 0, 0, 0};
+  long long maxcap = 0;
+  for (auto &S : h->sp) maxcap = std::max<long long>(maxcap, S.cap);
+  for (int d = 0; d < c.ndims; d++) {
+    prop[d] = std::max<long long>(65536, maxcap / std::max(1, c.n[d]));
+    prop[d] = std::min<long long>(prop[d], std::max<long long>(h->out_cap, 1));
+    prop[3] = std::max(prop[3], prop[d] / 64);
+  }
+  prop[3] = std::max<long long>(prop[3], 4096);
+  long long *d = (long long *)(h->d_scratch + 896);
+  EPB_CUDA(h, cudaMemcpyAsync(d, prop, sizeof prop, cudaMemcpyHostToDevice, h->stream));
+  EPB_NCCL(h, ncclAllReduce(d, d, 4, ncclInt64, ncclMax, (ncclComm_t)h->nccl, h->stream));
+  EPB_CUDA(h, cudaMemcpyAsync(prop, d, sizeof prop, cudaMemcpyDeviceToHost, h->stream));
+  EPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < 27; q++) {
+    const int o[3] = {q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1};
+    const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
+    h->xcap[q] = 0;
+    if (nz == 1) h->xcap[q] = (int)prop[o[0] != 0 ? 0 : (o[1] != 0 ? 1 : 2)];
+    else if (nz > 1) h->xcap[q] = (int)prop[3];
+    if (h->xcap[q] > h->out_cap) h->xcap[q] = h->out_cap;
+  }
+  return EPB_OK;
 }
 
 // get_load_x / get_load_y (balance.F90:1766-1844; epoch3d :2247-2362; epoch1d :980-1006): histogram of the
@@ -343,11 +433,76 @@ int epb_halo_exchange(epb_handle *h, int f0, int nf, bool add) {
 }
 
 // particle_bcs tail: remove leavers, exchange with up to 26 neighbours, append arrivals
+// Particle migration of a slot-layout species with no host round trip (see k_ppack_dev): the leavers sit in the
+// mover buffer, flagged, the outbox lists their indices per direction; arrivals are appended to the same buffer and
+// placed by k_deliver.  Overflows of any fixed capacity set bits of the device error word, which the next
+// host-visible call (epb_global_count, epb_step_scalars_async, a download) reports as EPB_ERR_CAPACITY.
+static int particle_exchange_async(epb_handle *h, int is) {
+  const epb_config &c = h->cfg;
+  SpeciesDev &S = h->sp[is];
+  const int nd = c.ndims, nv = nd + 4;
+  size_t off[28];
+  off[0] = 0;
+  for (int q = 0; q < 27; q++) off[q + 1] = off[q] + ((size_t)h->xcap[q] + 1) * nv;
+  int rc = ensure_buf(h, &h->sendbuf, &h->sendbuf_elems, off[27]);
+  if (rc) return rc;
+  rc = ensure_buf(h, &h->recvbuf, &h->recvbuf_elems, off[27]);
+  if (rc) return rc;
+  double *const *arr = S.mbuf[S.mcur];
+  for (int q = 0; q < 27; q++) {
+    const int to = c.neighbour[q];
+    if (q == 13 || to < 0 || to == c.rank || h->xcap[q] <= 0) continue;
+    PPackDevOp O;
+    for (int k = 0; k < 7; k++) O.src[k] = arr[k];
+    O.nv = nv; O.nd = nd;
+    O.idx = h->out_idx + (size_t)q * h->out_cap;
+    O.count_dev = h->out_count + q;
+    O.xcap = h->xcap[q]; O.out_cap = h->out_cap;
+    O.buf = h->sendbuf + off[q];
+    O.err = h->d_err;
+    k_ppack_dev<<<nblk((size_t)std::min(h->xcap[q], 1 << 18)), 256, 0, h->stream>>>(O);
+    h->launches++;
+  }
+  ncclComm_t comm = (ncclComm_t)h->nccl;
+  EPB_NCCL(h, ncclGroupStart());
+  for (int q = 0; q < 27; q++) {
+    if (q == 13 || h->xcap[q] <= 0) continue;
+    const int to = c.neighbour[q], from = c.neighbour[26 - q];
+    const size_t len = ((size_t)h->xcap[q] + 1) * nv;
+    if (to >= 0 && to != c.rank) EPB_NCCL(h, ncclSend(h->sendbuf + off[q], len, ncclDouble, to, comm, h->stream));
+    if (from >= 0 && from != c.rank) EPB_NCCL(h, ncclRecv(h->recvbuf + off[q], len, ncclDouble, from, comm, h->stream));
+  }
+  EPB_NCCL(h, ncclGroupEnd());
+  h->launches++;
+  // append arrivals in the reference's direction order (boundary.F90:1436-1446)
+  for (int q = 0; q < 27; q++) {
+    const int from = c.neighbour[26 - q];
+    if (q == 13 || from < 0 || from == c.rank || h->xcap[q] <= 0) continue;
+    PUnpackDevOp O;
+    for (int k = 0; k < 7; k++) O.dst[k] = arr[k];
+    O.nv = nv; O.nd = nd;
+    O.buf = h->recvbuf + off[q];
+    O.xcap = h->xcap[q];
+    O.mcount = S.mcount + S.mcur;
+    O.flag = S.mflag[S.mcur];
+    O.cap = (int)S.mcap;
+    O.err = h->d_err;
+    k_punpack_dev<<<nblk((size_t)std::min(h->xcap[q], 1 << 18)), 256, 0, h->stream>>>(O);
+    k_bump_count_dev<<<1, 1, 0, h->stream>>>(S.mcount + S.mcur, h->recvbuf + off[q]);
+    h->launches += 2;
+  }
+  EPB_CUDA(h, cudaMemsetAsync(h->out_count, 0, 27 * sizeof(int), h->stream));
+  EPB_CUDA(h, cudaGetLastError());
+  return EPB_OK;
+}
+
 int epb_particle_exchange(epb_handle *h, int is) {
   const epb_config &c = h->cfg;
   SpeciesDev &S = h->sp[is];
   if (h->out_cap == 0 || S.cfg.immobile) return EPB_OK;
   const int nd = c.ndims, nv = nd + 4;
+  static const int force_sync = epb_env("EPB_EXCHANGE_SYNC") ? atoi(epb_env("EPB_EXCHANGE_SYNC")) : 0;
+  if (S.slots && c.nranks > 1 && h->nccl && !force_sync) return particle_exchange_async(h, is);
   int *cnt = h->h_counts;
   EPB_CUDA(h, cudaMemcpyAsync(cnt, h->out_count, 27 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
