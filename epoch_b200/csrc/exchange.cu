@@ -255,21 +255,20 @@ extern "C" int epb_nccl_unique_id(void *id128) {
   memcpy(id128, &id, sizeof id);
   return EPB_OK;
 }
-extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
-  if (!h || !id128) return EPB_ERR_ARG;
-  if (h->cfg.nranks <= 1) return EPB_OK;
-  int rc = epb_comm_init(h, id128);
-  if (rc) return rc;
-  // message capacities of the host-round-trip-free particle exchange: per axis, the particles of one cell layer
-  // of the fullest species buffer (what can cross a face in one step at most in a uniform plasma, v dt < dx; a
-  // thermal plasma sends a few per cent of that), at least 64 Ki; edges and corners a 64th of the largest.  Both ends of a message must use the same number: maximum over the ranks.
+// Message capacities of the host-round-trip-free particle exchange (particle_exchange_async): per axis, the particles
+// of one cell layer of the fullest species buffer (what can cross a face in one step at most in a uniform plasma,
+// v dt < dx; a thermal plasma sends a few per cent of that), at least 64 Ki; edges and corners a 64th of the largest.
+// Both ends of a message must use the same number: maximum over the ranks.  Collective; called when the communicator
+// is attached and again when the balancer has re-cut the slabs (new extents, new capacities).
+int epb_agree_exchange_caps(epb_handle *h) {
   const epb_config &c = h->cfg;
+  for (int q = 0; q < 27; q++) h->xcap[q] = 0;
+  if (c.nranks <= 1 || !h->nccl) return EPB_OK;
   long long prop[4] = {0, 0, 0, 0};
-  long long maxcap = 0;
+  long long maxcap = 0, maxout = h->out_cap;
   for (auto &S : h->sp) maxcap = std::max<long long>(maxcap, S.cap);
   for (int d = 0; d < c.ndims; d++) {
     prop[d] = std::max<long long>(65536, maxcap / std::max(1, c.n[d]));
-    prop[d] = std::min<long long>(prop[d], std::max<long long>(h->out_cap, 1));
     prop[3] = std::max(prop[3], prop[d] / 64);
   }
   prop[3] = std::max<long long>(prop[3], 4096);
@@ -281,12 +280,19 @@ extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
   for (int q = 0; q < 27; q++) {
     const int o[3] = {q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1};
     const int nz = (o[0] != 0) + (o[1] != 0) + (o[2] != 0);
-    h->xcap[q] = 0;
     if (nz == 1) h->xcap[q] = (int)prop[o[0] != 0 ? 0 : (o[1] != 0 ? 1 : 2)];
     else if (nz > 1) h->xcap[q] = (int)prop[3];
-    if (h->xcap[q] > h->out_cap) h->xcap[q] = h->out_cap;
   }
+  (void)maxout;
   return EPB_OK;
+}
+
+extern "C" int epb_set_comm(epb_handle *h, const void *id128) {
+  if (!h || !id128) return EPB_ERR_ARG;
+  if (h->cfg.nranks <= 1) return EPB_OK;
+  int rc = epb_comm_init(h, id128);
+  if (rc) return rc;
+  return epb_agree_exchange_caps(h);
 }
 
 // get_load_x / get_load_y (balance.F90:1766-1844; epoch3d :2247-2362; epoch1d :980-1006): histogram of the
@@ -960,6 +966,10 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
     }
   }
   oh->nccl = nullptr;   // moved
+  {
+    int rcx = epb_agree_exchange_caps(nh);
+    if (rcx) return rcx;
+  }
   epb_destroy(oh);
   *out = nh;
   return EPB_OK;

@@ -484,7 +484,10 @@ int epb_slots_check(epb_handle *h) {
   int e = 0;
   EPB_CUDA(h, cudaMemcpyAsync(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
   EPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (e) return epb_fail(h, EPB_ERR_CAPACITY, "slot layout: a mover buffer overflowed and particles were lost (error word %d); raise the species capacity", e);
+  if (e) return epb_fail(h, EPB_ERR_CAPACITY, "slot layout: particles were lost (error word %d:%s%s%s%s); raise the species capacity", e,
+                         (e & 1) ? " a mover buffer overflowed" : "", (e & 2) ? " arrivals from a neighbour did not fit the mover buffer" : "",
+                         (e & 4) ? " more particles left through one face than an exchange message holds" : "",
+                         (e & 8) ? " the outbox list of one direction overflowed" : "");
   return EPB_OK;
 }
 
