@@ -14,7 +14,7 @@ tests)
 testsv)
   # 2D parity tests under the alternative push kernels (EPB_PUSH_VARIANT is read once per process)
   for v in ${TESTVARIANTS:-3 2 4}; do
-    EPB_PUSH_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden_fixtures.py -m gpu -q \
+    EPB_DEBUG=1 EPB_PUSH_VARIANT=$v timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden_fixtures.py -m gpu -q \
       -k "2-n or 2d or sort_interval or open_boundaries or foil or full_size or cuda_path" > gpurun_out/pytest_gpu_v$v.log 2>&1
     echo "variant $v pytest rc=$?" >> gpurun_out/pytest_gpu_v$v.log; tail -4 gpurun_out/pytest_gpu_v$v.log
   done ;;
@@ -47,18 +47,18 @@ benchN)
 variants)
   for v in ${VARIANTS:-0 1 2 3}; do
     for si in ${SORTS:-4}; do
-      EPB_PUSH_VARIANT=$v timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval $si --no-cpu-baseline 2>/dev/null | \
+      EPB_DEBUG=1 EPB_PUSH_VARIANT=$v timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval $si --no-cpu-baseline 2>/dev/null | \
         python -c "import sys,json; d=json.loads(sys.stdin.read()); print('variant $v sort $si: push_ms %.3f step_ms %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step']))" | tee -a gpurun_out/variants.log
     done
   done ;;
 experiments)
   for e in ${EXPS:-0 1 2 3 8 11 4 15}; do
-    EPB_PUSH_EXPERIMENT=$e timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval 4 --no-cpu-baseline 2>/dev/null | \
+    EPB_DEBUG=1 EPB_PUSH_EXPERIMENT=$e timeout 600 python bench.py --cells 2048 --steps 8 --warmup 4 --sort-interval 4 --no-cpu-baseline 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('experiment $e: push_ms %.3f step_ms %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step']))" | tee -a gpurun_out/experiments.log
   done ;;
 bench3d)
   for no3d in ${NO3D:-0 1}; do
-    EPB_NO_TILED_3D=$no3d timeout 900 python bench.py --workload c4 --cells ${CELLS3D:-192} --steps 4 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench3d.err | \
+    EPB_DEBUG=1 EPB_NO_TILED_3D=$no3d timeout 900 python bench.py --workload c4 --cells ${CELLS3D:-192} --steps 4 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench3d.err | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('3d no_tiled=$no3d: push_ms %.3f step_ms %.3f value %.3e frac %.3f'%(d['roofline']['kernel_ms'], d['ms_per_step'], d['value'], d['roofline']['frac']))" | tee -a gpurun_out/bench3d.log
     tail -2 gpurun_out/bench3d.err
   done ;;
