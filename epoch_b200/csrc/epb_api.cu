@@ -1510,7 +1510,9 @@ static int create_device_state(epb_handle *h, const epb_config *cfg, const epb_s
       h->cpml = true;
       const double cc = EPB_C;
       const int cpml_m = 3, cpml_ma = 1;
-      const int fng = (cfg->field_order ? cfg->field_order : 2) / 2;   // fields.f90:37
+      // fng: field_order / 2 (fields.f90:37), but 2 for the Lehe solvers (deck_control_block.F90:117-120)
+      int fng = (cfg->field_order ? cfg->field_order : 2) / 2;
+      if (cfg->maxwell_solver >= 2 && cfg->maxwell_solver <= 4) fng = 2;   // c_maxwell_solver_lehe_x / _y / _z
       const double tstep = 0.5 * cfg->dt;                               // both half steps use hdt
       auto pw = [](double x, int e) { double r = 1.0; for (int q = 0; q < e; q++) r = r * x; return r; };
       // dx of the first axis for every axis, as boundary.F90:1517 has it

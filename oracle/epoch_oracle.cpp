@@ -244,7 +244,10 @@ void set_cpml_helpers(World &w, Rank &R) {
   const Config &cf = w.cfg;
   const int t = w.cpml_t;
   const int cpml_m = 3, cpml_ma = 1;
-  const int fng = (cf.field_order ? cf.field_order : 2) / 2;   // fields.f90:37
+  // fng, "the number of ghost cells needed by the field solver": field_order / 2 (fields.f90:37), but 2 for the Lehe
+  // solvers (deck_control_block.F90:117-120; epoch3d :118-122 adds lehe_z) -- it decides where the laser plane sits
+  int fng = (cf.field_order ? cf.field_order : 2) / 2;
+  if (cf.maxwell_solver >= 2 && cf.maxwell_solver <= 4) fng = 2;   // c_maxwell_solver_lehe_x / _y / _z
   for (int d = 0; d < w.nd; d++) {
     const int n = R.n[d], len = n + 2 * NG;
     R.kap_e[d].assign(len, 1.0); R.kap_b[d].assign(len, 1.0);

@@ -73,14 +73,19 @@ def test_geometry_with_cpml():
         assert lo[:2] == geo["min_outer"][:2] and hi[:2] == geo["max_outer"][:2]
 
 
+# the numbers the reference binary printed for its CPML decks (comments of epoch{1,2,3}d/tests/test_maxwell_solvers.py)
+RECORDED_2D = {"pukhov": 292013249.255, "lehe_x": 312016227.758}     # test_maxwell_solvers.py:163-165
+RECORDED_1D = {"yee": 298540658.530, "lehe_x": 313164075.045}        # epoch1d/tests/test_maxwell_solvers.py:123-124
+
+
 def test_reference_cpml_decks_group_velocity():
     """epoch2d/tests/test_maxwell_solvers.py:150-171 on the decks as written: the slope of the Ey^2 centroid over
-    dumps 1..3 equals the Lehe / Pukhov / Yee group velocity to rtol 0.012.  For the Pukhov deck the oracle also
-    reproduces the number the reference binary printed (:163, "pukhov 292013249.255") in every digit, which pins the
-    CPML restatement -- stretching profiles, auxiliary currents, laser plane, grid extension -- on reference output.
-    (The two other comments, yee 289199289.192 and lehe_x 312016227.758, are not reproduced: 288297786.835 and
-    312148240.814, 3e-3 and 4e-4 away; the same three decks share every line but the solver name, so those comments
-    predate the current solver code, like two of the custom-stencil comments.)"""
+    dumps 1..3 equals the Lehe / Pukhov / Yee group velocity to rtol 0.012.  For the Pukhov and the Lehe deck the
+    oracle also reproduces the numbers the reference binary printed (:163-165, "pukhov 292013249.255", "lehe_x
+    312016227.758") in every digit, which pins the CPML restatement -- stretching profiles, auxiliary currents, laser
+    plane (fng = 2 cells further in for the Lehe solvers, deck_control_block.F90:117-120), grid extension -- on
+    reference output.  (The third comment, yee 289199289.192, is not reproduced: 288297786.835, 3e-3 away; yee is
+    commented out of that test's solver list, and the 1D yee deck below does match.)"""
     c = D.c
     lam = 0.5 * D.micron
     k_l = 2 * np.pi / lam
@@ -95,8 +100,47 @@ def test_reference_cpml_decks_group_velocity():
                   yee=c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt_yee / dx * np.sin(k_l * dx / 2.0)) ** 2),
                   pukhov=c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt_pukhov / dx * np.sin(k_l * dx / 2.0)) ** 2))
         assert np.isclose(vg_sim, vg[solver], rtol=0.012), (solver, vg_sim, vg[solver])
-        if solver == "pukhov":
-            assert np.isclose(vg_sim, 292013249.255, rtol=5e-12, atol=0), vg_sim
+        if solver in RECORDED_2D:
+            assert np.isclose(vg_sim, RECORDED_2D[solver], rtol=5e-12, atol=0), (solver, vg_sim)
+
+
+def maxwell_deck_1d(solver):
+    """epoch1d/tests/maxwell_solvers/<solver>/input.deck: 240 cells over 24 um, cpml_laser / cpml_outflow, the pulse
+    until 14 fs, dumps every 12 fs"""
+    L = 12 * D.micron
+    las = D.Laser("x_min", D.Laser.amp_from_intensity_w_cm2(1.0e15), 2 * D.pi * D.c / (0.5 * D.micron),
+                  t_profile=lambda t: D.gauss(t, 8 * D.femto, 1.8 * D.femto), t_end=14 * D.femto)
+    return D.Deck(1, [240], [-L], [L], ["cpml_laser", "cpml_outflow"], lasers=[las], t_end=75 * D.femto,
+                  dt_snapshot=12 * D.femto, maxwell_solver=solver)
+
+
+@pytest.mark.parametrize("solver", ["yee", "lehe_x"])
+def test_reference_cpml_decks_1d(solver):
+    """epoch1d/tests/test_maxwell_solvers.py:111-129 on the decks as written (dumps 1..7, rtol 0.022 against the
+    dispersion formulas) and the two numbers the reference binary printed (:123-124), reproduced in every digit."""
+    dk = maxwell_deck_1d(solver)
+    o = Oracle(dk)
+    nxe = dk.ncells(0)
+    x = dk.grid_min(0) + np.arange(nxe) * dk.dx(0)
+    tx = []
+
+    def dump(step, t):
+        ey = o.interior(0, "ey").reshape(-1)
+        b = float(np.sum(ey ** 2))
+        if b > 0 and t > 0:
+            tx.append((t, float(np.sum(x * ey ** 2) / b)))
+
+    D.run(dk, o, [0], dump)
+    assert len(tx) == 7
+    tx = np.array(tx)
+    vg_sim = np.polyfit(tx[:, 0], tx[:, 1], 1)[0]
+    assert np.isclose(vg_sim, RECORDED_1D[solver], rtol=5e-12, atol=0), (solver, vg_sim)
+    c, dx = D.c, dk.dx(0)
+    k_l = 2 * np.pi / (0.5 * D.micron)
+    dt_yee = 0.95 * dx / c
+    vg = dict(lehe_x=c * (1.0 + 2.0 * (1.0 - c * dt_yee / dx) * (k_l * dx / 2.0) ** 2),
+              yee=c * np.cos(k_l * dx / 2.0) / np.sqrt(1 - (c * dt_yee / dx * np.sin(k_l * dx / 2.0)) ** 2))
+    assert np.isclose(vg_sim, vg[solver], rtol=0.022)
 
 
 def test_cpml_decomposed_equals_single_rank():
@@ -202,11 +246,12 @@ def test_cpml_matches_oracle_gpu(ndims, order, solver, particles):
 
 
 @pytest.mark.gpu
-def test_reference_cpml_deck_gpu():
-    """The reference's Pukhov CPML deck as written, on the device: the same group velocity as the reference binary
-    printed (292013249.255) to 1e-9 (the fields follow the oracle to 1e-12; the centroid fit inherits that)."""
+@pytest.mark.parametrize("solver", ["pukhov", "lehe_x"])
+def test_reference_cpml_deck_gpu(solver):
+    """The reference's Pukhov and Lehe CPML decks as written, on the device: the same group velocity as the reference
+    binary printed to 1e-9 (the fields follow the oracle to 1e-12; the centroid fit inherits that)."""
     from epoch_b200.pic import Simulation
-    dk = maxwell_deck("pukhov")
+    dk = maxwell_deck(solver)
     sim = Simulation(dk, strict_fp=True)
     nxe, nye = dk.ncells(0), dk.ncells(1)
     x = dk.grid_min(0) + np.arange(nxe) * dk.dx(0)
@@ -228,4 +273,4 @@ def test_reference_cpml_deck_gpu():
     D.run(dk, One(), [0], dump)
     tx = np.array(tx)
     vg_sim = np.polyfit(tx[:, 0], tx[:, 1], 1)[0]
-    assert np.isclose(vg_sim, 292013249.255, rtol=1e-9, atol=0), vg_sim
+    assert np.isclose(vg_sim, RECORDED_2D[solver], rtol=1e-9, atol=0), vg_sim
