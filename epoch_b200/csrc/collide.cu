@@ -203,18 +203,22 @@ __device__ bool pair_sk(const PairEnv &E, double *p1, double *p2, double w1, dou
 __device__ bool pair_np(const PairEnv &E, double *q1p, double *q2p, double w1, double w2, RanSrc &R) {
   const double m1 = E.m1, m2 = E.m2;
   double p1[3], p2[3], p1n[3], p2n[3], vc[3], v1[3], v2[3], p3[3], p4[3];
-  for (int d = 0; d < 3; d++) { p1[d] = q1p[d] / C_; p2[d] = q2p[d] / C_; }
-  for (int d = 0; d < 3; d++) { p1n[d] = p1[d] / M0; p2n[d] = p2[d] / M0; }
+  // the quotients by constants and the three-component quotients by one divisor go through div_rcp (epb_internal.h):
+  // the compiler's division carries a slow-path branch that keeps neighbouring divisions from overlapping
+  const double rc = 1.0 / C_, rm0 = 1.0 / M0, rm1 = 1.0 / m1, rm2 = 1.0 / m2;
+  for (int d = 0; d < 3; d++) { p1[d] = div_rcp(q1p[d], C_, rc); p2[d] = div_rcp(q2p[d], C_, rc); }
+  for (int d = 0; d < 3; d++) { p1n[d] = div_rcp(p1[d], M0, rm0); p2n[d] = div_rcp(p2[d], M0, rm0); }
   if (dot3(p1n, p1n) < EPS && dot3(p2n, p2n) < EPS) return false;
   for (int d = 0; d < 3; d++) vc[d] = p1n[d] - p2n[d];
   if (dot3(vc, vc) < EPS) return false;
-  for (int d = 0; d < 3; d++) p1n[d] = p1[d] / m1;
+  for (int d = 0; d < 3; d++) p1n[d] = div_rcp(p1[d], m1, rm1);
   const double gm1 = sqrt(dot3(p1n, p1n) + 1.0) * m1;
-  for (int d = 0; d < 3; d++) p2n[d] = p2[d] / m2;
+  for (int d = 0; d < 3; d++) p2n[d] = div_rcp(p2[d], m2, rm2);
   const double gm2 = sqrt(dot3(p2n, p2n) + 1.0) * m2;
   const double gm = gm1 + gm2;
-  for (int d = 0; d < 3; d++) { v1[d] = p1[d] / gm1; v2[d] = p2[d] / gm2; }
-  for (int d = 0; d < 3; d++) vc[d] = (p1[d] + p2[d]) / gm;
+  const double rgm1 = 1.0 / gm1, rgm2 = 1.0 / gm2, rgm = 1.0 / gm;
+  for (int d = 0; d < 3; d++) { v1[d] = div_rcp(p1[d], gm1, rgm1); v2[d] = div_rcp(p2[d], gm2, rgm2); }
+  for (int d = 0; d < 3; d++) vc[d] = div_rcp(p1[d] + p2[d], gm, rgm);
   const double vc_sq = dot3(vc, vc);
   const double gamma_rel_inv = sqrt(1.0 - vc_sq);
   const double gc = 1.0 / gamma_rel_inv;

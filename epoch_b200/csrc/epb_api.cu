@@ -478,8 +478,25 @@ struct Moment2Op {
   double *a0, *a1;           // ekbar: data, wt; temperature: sigma, count
   double *mean[3];
 };
-__global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2Op M) {
+// mode 3: what one particle adds to the data array (ekbar, one ekflux direction, one momentum component)
+__device__ __forceinline__ double moment2_wdata(const Moment2Op &M, long long e, double part_w) {
   const double c = EPB_C;
+  if (M.sub >= 7) return part_w * M.p[M.sub - 7][e];
+  const double fac = M.part_mc * part_w * c;
+  const double part_ux = M.p[0][e] / M.part_mc, part_uy = M.p[1][e] / M.part_mc, part_uz = M.p[2][e] / M.part_mc;
+  const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
+  const double gamma_rel = sqrt(part_u2 + 1.0);
+  const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
+  double wdata = gamma_rel_m1 * fac;
+  if (M.sub >= 1) {
+    const int a = (M.sub - 1) / 2;
+    const double part_flux = M.flux_fac * (a == 0 ? part_ux : a == 1 ? part_uy : part_uz) / gamma_rel;
+    if ((M.sub - 1) % 2 == 0) wdata = -wdata * fmin(part_flux, 0.0);
+    else wdata = wdata * fmax(part_flux, 0.0);
+  }
+  return wdata;
+}
+__global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2Op M) {
   const long long nn = prange_n(M.r);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long long)gridDim.x * blockDim.x) {
     if (!prange_valid(M.r, i)) continue;
@@ -507,21 +524,8 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
       atomicAdd(M.a1 + o, 1.0);
       continue;
     }
-    if (M.mode == 3 && M.sub >= 7) {
-      wdata = part_w * M.p[M.sub - 7][e];
-    } else if (M.mode == 3) {
-      const double fac = M.part_mc * part_w * c;
-      const double part_ux = M.p[0][e] / M.part_mc, part_uy = M.p[1][e] / M.part_mc, part_uz = M.p[2][e] / M.part_mc;
-      const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
-      const double gamma_rel = sqrt(part_u2 + 1.0);
-      const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
-      wdata = gamma_rel_m1 * fac;
-      if (M.sub >= 1) {
-        const int a = (M.sub - 1) / 2;
-        const double part_flux = M.flux_fac * (a == 0 ? part_ux : a == 1 ? part_uy : part_uz) / gamma_rel;
-        if ((M.sub - 1) % 2 == 0) wdata = -wdata * fmin(part_flux, 0.0);
-        else wdata = wdata * fmax(part_flux, 0.0);
-      }
+    if (M.mode == 3) {
+      wdata = moment2_wdata(M, e, part_w);
     } else {
       for (int q = 0; q < 3; q++) pm[q] = M.p[q][e] / M.sqrt_part_m;
     }
@@ -556,6 +560,178 @@ __global__ void __launch_bounds__(256) k_moment2(const __grid_constant__ Moment2
             atomicAdd(M.a1 + o, gg);
           }
         }
+  }
+}
+// The same sums on the 2D slot columns (layout 2): one warp per group of 32 columns = 16 x 2 cells, one lane per
+// column.  A column holds the particles that GATHER in its cell at the next push, so nearly all of them also have
+// it as their nearest cell: those accumulate their nine stencil values per output array in registers, the warp
+// folds the lanes' registers into its 18 x 4-cell shared tile (nine conflict-free steps) and adds the tile to the
+// grid once -- 72 atomics per array and group instead of nine per particle.  The few particles whose nearest cell
+// is a neighbour of the column's cell take the per-particle atomics of k_moment2.  The kernel is bound by the
+// latency of one particle's dependent FP64 chain, so the divisions by loop constants go through div_rcp (no
+// slow-path branch: they overlap) and the next row is loaded while the current one is worked on.
+constexpr int MS_WARPS = 4;
+template <int MODE>   // 3: NA = 2 (data, wt); 4: NA = 4 (mean x 3, count); 5: NA = 2 (sigma, count)
+__global__ void __launch_bounds__(MS_WARPS * 32, 4) k_moment2_slots(const __grid_constant__ Moment2Op M, const TileGeom tg) {
+  constexpr int NA = MODE == 4 ? 4 : 2;
+  constexpr int TW = 18, TH = 4;
+  __shared__ double tile_all[MS_WARPS][NA][TW * TH];
+  __shared__ double mean_all[MODE == 5 ? MS_WARPS : 1][3][TW * TH];   // pass 2: the means around the warp's cells
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ngroups = tg.nkeys / 32, gpt = tg.cpt / 32;
+  double (*tile)[TW * TH] = tile_all[wib];
+  double (*mean_s)[TW * TH] = mean_all[MODE == 5 ? wib : 0];
+  double *out[NA];
+  if (MODE == 4) { out[0] = M.mean[0]; out[1] = M.mean[1]; out[NA - 2] = M.mean[2]; out[NA - 1] = M.a1; }
+  else { out[0] = M.a0; out[1] = M.a1; }
+  const double rdx[2] = {1.0 / M.dx[0], 1.0 / M.dx[1]};
+  const double pdiv = MODE == 3 ? M.part_mc : M.sqrt_part_m, rpdiv = 1.0 / pdiv;
+  const int lx = lane & 15, ly = lane >> 4;
+  const int home_o = (ly + 1) * TW + lx + 1;   // the column's cell inside the warp's tile
+  for (int g = blockIdx.x * MS_WARPS + wib; g < ngroups; g += gridDim.x * MS_WARPS) {
+    const int t = g / gpt, gi = g - t * gpt;
+    const int ty = t / tg.nt[0], tx = t - ty * tg.nt[0];
+    const int x0 = tx * tg.T[0], y0 = ty * tg.T[1] + gi * 2;   // Fortran index of tile cell (0, 0), the halo corner; the lane's column is tile cell (lx + 1, ly + 1)
+    const int n = M.r.cnt[g * 32 + lane];
+    if (MODE == 5) {
+      for (int i = lane; i < TW * TH; i += 32) {
+        const int cx = x0 + i % TW, cy = y0 + i / TW;
+        const bool in = cx <= M.sz[0] - NG && cy <= M.sz[1] - NG;
+        const size_t o = in ? fofs(M.sz, 2, cx, cy, 1) : 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) mean_s[q][i] = (in && (M.dir < 0 || M.dir == q)) ? M.mean[q][o] : 0.0;
+      }
+      __syncwarp();
+    }
+    double acc[NA][9];
+#pragma unroll
+    for (int a = 0; a < NA; a++)
+#pragma unroll
+      for (int k = 0; k < 9; k++) acc[a][k] = 0.0;
+    // row r of the lane's column: element e0 + r * rstride of every component array (planes, or row blocks of K x 32)
+    const long long e0 = ((((long long)g * M.r.R) * M.r.K) << 5) + lane, rstride = (long long)M.r.K << 5;
+    const double *comp[6] = {M.x[0], M.x[1], M.p[0], M.p[1], M.p[2], M.w};
+    double nxt[6];
+    if (n > 0) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) nxt[q] = comp[q][e0];
+    }
+    for (int r = 0; r < n; r++) {
+      double cur[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) cur[q] = nxt[q];
+      if (r + 1 < n) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) nxt[q] = comp[q][e0 + (r + 1) * rstride];
+      }
+      int cell[2];
+      double gw[2][3];
+      bool ok = true;
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        const double cell_r = div_rcp(cur[d] - M.gmin[d], M.dx[d], rdx[d]);
+        const int cx = __double2int_rd(cell_r + 0.5);
+        const double cf = (double)cx - cell_r;
+        cell[d] = cx + 1;
+        const double c2 = cf * cf;
+        gw[d][0] = 0.5 * (0.25 + c2 + cf);
+        gw[d][1] = 0.75 - c2;
+        gw[d][2] = 0.5 * (0.25 + c2 - cf);
+        if (cell[d] - 1 < 1 - NG || cell[d] + 1 > M.sz[d] - NG) ok = false;
+      }
+      if (!ok) continue;
+      const double part_w = cur[5];
+      double wdata = 0.0, pm[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) pm[q] = div_rcp(cur[2 + q], pdiv, rpdiv);   // mode 3: u = p / (m c); else p / sqrt(m)
+      if (MODE == 3) {
+        if (M.sub >= 7) {
+          wdata = part_w * (M.sub == 7 ? cur[2] : M.sub == 8 ? cur[3] : cur[4]);
+        } else {
+          const double fac = M.part_mc * part_w * EPB_C;
+          const double part_u2 = pm[0] * pm[0] + pm[1] * pm[1] + pm[2] * pm[2];
+          const double gamma_rel = sqrt(part_u2 + 1.0);
+          const double gamma_rel_m1 = part_u2 / (gamma_rel + 1.0);
+          wdata = gamma_rel_m1 * fac;
+          if (M.sub >= 1) {
+            const int a = (M.sub - 1) / 2;
+            const double part_flux = M.flux_fac * (a == 0 ? pm[0] : a == 1 ? pm[1] : pm[2]) / gamma_rel;
+            if ((M.sub - 1) % 2 == 0) wdata = -wdata * fmin(part_flux, 0.0);
+            else wdata = wdata * fmax(part_flux, 0.0);
+          }
+        }
+      }
+      const bool home = cell[0] == x0 + lx + 1 && cell[1] == y0 + ly + 1;
+      // what the particle adds at stencil point k = (iy + 1) * 3 + ix + 1; mean_k: the means there (pass 2)
+      auto value = [&](int k, const double *mean_k, double *v) {
+        const double gg = gw[0][k % 3] * gw[1][k / 3];
+        if (MODE == 3) {
+          v[0] = gg * wdata;
+          v[1] = gg * part_w;
+        } else if (MODE == 4) {
+          const double gf = gg * part_w;
+          v[0] = gf * pm[0]; v[1] = gf * pm[1]; v[NA - 2] = gf * pm[2];
+          v[NA - 1] = gf;
+        } else {
+          double wd = 0.0;
+#pragma unroll
+          for (int q = 0; q < 3; q++)
+            if (M.dir < 0 || M.dir == q) { const double dq = pm[q] - mean_k[q]; wd += dq * dq; }
+          v[0] = gg * wd;
+          v[1] = gg;
+        }
+      };
+      if (home) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          double mk[3] = {0.0, 0.0, 0.0}, v[NA];
+          if (MODE == 5) {
+            const int o = home_o + (k / 3 - 1) * TW + (k % 3 - 1);
+#pragma unroll
+            for (int q = 0; q < 3; q++) mk[q] = mean_s[q][o];
+          }
+          value(k, mk, v);
+#pragma unroll
+          for (int a = 0; a < NA; a++) acc[a][k] += v[a];
+        }
+      } else {
+        for (int k = 0; k < 9; k++) {
+          const size_t o = fofs(M.sz, 2, cell[0] + (k % 3 - 1), cell[1] + (k / 3 - 1), 1);
+          double mk[3] = {0.0, 0.0, 0.0}, v[NA];
+          if (MODE == 5) {
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              if (M.dir < 0 || M.dir == q) mk[q] = M.mean[q][o];
+          }
+          value(k, mk, v);
+#pragma unroll
+          for (int a = 0; a < NA; a++)
+            if (MODE != 4 || a == NA - 1 || M.dir < 0 || M.dir == a) atomicAdd(out[a] + o, v[a]);
+        }
+      }
+    }
+    // fold the lanes' registers into the warp's tile: in step k every lane adds to a different cell
+    for (int i = lane; i < NA * TW * TH; i += 32) (&tile[0][0])[i] = 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const int o = home_o + (k / 3 - 1) * TW + (k % 3 - 1);
+#pragma unroll
+      for (int a = 0; a < NA; a++) tile[a][o] += acc[a][k];
+      __syncwarp();
+    }
+    for (int i = lane; i < TW * TH; i += 32) {
+      const int cx = x0 + i % TW, cy = y0 + i / TW;
+      if (cx > M.sz[0] - NG || cy > M.sz[1] - NG) continue;   // padding columns past the rank's extent hold no particle
+      const size_t o = fofs(M.sz, 2, cx, cy, 1);
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        if (MODE == 4 && a < NA - 1 && M.dir >= 0 && M.dir != a) continue;   // one-component temperature: only that mean
+        const double v = tile[a][i];
+        if (v != 0.0) atomicAdd(out[a] + o, v);
+      }
+    }
+    __syncwarp();
   }
 }
 // calc_poynt_flux (io/calc_df.F90:561-604, epoch1d :441-474, epoch3d :585-650): E x B / mu0 at the cell centres
@@ -816,12 +992,6 @@ inline int nblocks(size_t total, int cap = 148 * 16) {
   if (b < 1) b = 1;
   if (b > (size_t)cap) b = cap;
   return (int)b;
-}
-
-inline int nbr1(const epb_config &c, int d, int s) {
-  int o[3] = {0, 0, 0};
-  o[d] = s;
-  return c.neighbour[(o[2] + 1) * 9 + (o[1] + 1) * 3 + (o[0] + 1)];
 }
 
 void fill_field_params(epb_handle *h, FieldParams &F) {
@@ -2552,6 +2722,22 @@ static void moment2_fill(epb_handle *h, int is, const SlotView &V, Moment2Op &M)
   M.sqrt_part_m = sqrt(S.cfg.mass);
 }
 
+// One pass of calc_ekbar / calc_temperature over a range of particles: the slot-column kernel for the arena of the 2D
+// default layout, the per-particle scatter for everything else (EPB_DEBUG=1 EPB_MOMENT_GENERIC=1: always the latter).
+static void launch_moment2(epb_handle *h, const Moment2Op &M) {
+  static const int generic = epb_env("EPB_MOMENT_GENERIC") ? atoi(epb_env("EPB_MOMENT_GENERIC")) : 0;
+  if (!generic && h->tg.layout == 2 && h->tg.T[0] == 16 && h->tg.cpt % 32 == 0 && M.nd == 2 && M.r.cnt && M.r.K && M.mode >= 3 && M.mode <= 5) {
+    const int ngroups = h->tg.nkeys / 32;
+    const int blocks = std::min((ngroups + MS_WARPS - 1) / MS_WARPS, 148 * 16);
+    if (M.mode == 3) k_moment2_slots<3><<<blocks, MS_WARPS * 32, 0, h->stream>>>(M, h->tg);
+    else if (M.mode == 4) k_moment2_slots<4><<<blocks, MS_WARPS * 32, 0, h->stream>>>(M, h->tg);
+    else k_moment2_slots<5><<<blocks, MS_WARPS * 32, 0, h->stream>>>(M, h->tg);
+  } else {
+    k_moment2<<<nblocks((size_t)M.r.n, 148 * 32), 256, 0, h->stream>>>(M);
+  }
+  h->launches++;
+}
+
 // calc_ekbar (io/calc_df.F90:116-221, sub 0), calc_ekflux (:415-557, sub 1..6), calc_average_momentum (:1239-1317,
 // sub 7..9), calc_average_weight (:811-873, sub 10: nearest cell, no ghost-cell sums or fill): result in work array 9
 static int calc_ratio_dev(epb_handle *h, int ispecies, int sub) {
@@ -2583,8 +2769,7 @@ static int calc_ratio_dev(epb_handle *h, int ispecies, int sub) {
       M.a0 = h->f(A);
       M.a1 = h->f(WT);
       for (int q = 0; q < 3; q++) M.mean[q] = nullptr;
-      k_moment2<<<nblocks((size_t)V[v].r.n, 148 * 32), 256, 0, h->stream>>>(M);
-      h->launches++;
+      launch_moment2(h, M);
     }
     if (avg_weight) continue;
     int rc = moment_bcs_species(h, A, is);
@@ -2630,8 +2815,7 @@ static int calc_temperature_dev(epb_handle *h, int ispecies, int dir) {
         M.a0 = h->f(SIG);
         M.a1 = h->f(CNT);
         for (int q = 0; q < 3; q++) M.mean[q] = h->f(MEAN0 + q);
-        k_moment2<<<nblocks((size_t)V[v].r.n, 148 * 32), 256, 0, h->stream>>>(M);
-        h->launches++;
+        launch_moment2(h, M);
       }
       int rc = EPB_OK;
       if (pass == 0) {

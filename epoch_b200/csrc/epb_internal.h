@@ -285,6 +285,13 @@ inline const char *epb_env(const char *name) {
   static const int debug = getenv("EPB_DEBUG") ? atoi(getenv("EPB_DEBUG")) : 0;
   return debug ? getenv(name) : nullptr;
 }
+// a / b for a divisor whose reciprocal rb = 1.0 / b is at hand: the product, then one residual correction through
+// two FMAs.  Equal to the IEEE quotient except for rare last-place cases, and free of the slow-path branch of the
+// compiler's division, so several of them overlap in the pipeline (moments and collisions: results held to 1e-12).
+__device__ __forceinline__ double div_rcp(double a, double b, double rb) {
+  const double q = a * rb;
+  return fma(fma(-q, b, a), rb, q);
+}
 inline int epb_push_variant() {
   static int v = -1;
   if (v < 0) { const char *e = epb_env("EPB_PUSH_VARIANT"); v = e ? atoi(e) : 5; }
