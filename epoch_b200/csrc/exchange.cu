@@ -265,7 +265,7 @@ int epb_agree_exchange_caps(epb_handle *h) {
   for (int q = 0; q < 27; q++) h->xcap[q] = 0;
   if (c.nranks <= 1 || !h->nccl) return EPB_OK;
   long long prop[4] = {0, 0, 0, 0};
-  long long maxcap = 0, maxout = h->out_cap;
+  long long maxcap = 0;
   for (auto &S : h->sp) maxcap = std::max<long long>(maxcap, S.cap);
   for (int d = 0; d < c.ndims; d++) {
     prop[d] = std::max<long long>(65536, maxcap / std::max(1, c.n[d]));
@@ -283,7 +283,6 @@ int epb_agree_exchange_caps(epb_handle *h) {
     if (nz == 1) h->xcap[q] = (int)prop[o[0] != 0 ? 0 : (o[1] != 0 ? 1 : 2)];
     else if (nz > 1) h->xcap[q] = (int)prop[3];
   }
-  (void)maxout;
   return EPB_OK;
 }
 

@@ -2009,7 +2009,6 @@ __global__ void __launch_bounds__(P3_THREADS, 2) push_tiled_3d(const __grid_cons
   for (int q = tid; q < 3 * JT3; q += P3_THREADS) sJ[q] = 0.0;
   __syncthreads();
 
-  const double c = EPB_C;
   const double third = P.third;
   double *S = sS_all + warp * S3ROWS * SPITCH;
   double *Qd = sQd_all + warp * Q3DBL * Q3CAP;
@@ -2615,7 +2614,6 @@ __global__ void __launch_bounds__(B3_THREADS, 2) push_bag_3d(const __grid_consta
   const int my_tot = my_cnt + my_a;
   const int maxcnt = __reduce_max_sync(FULL, my_tot);
 
-  const double c = EPB_C;
   const double third = P.third;
   double *Qd = sQd_all + warp * Q3DBL * Q3CAP;
   int *Qk = sQk_all + warp * Q3CAP;
@@ -2942,7 +2940,6 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
     if (P.tg.ntiles > 0) {
       if (P.tg.layout == 2) {
         static bool attr_s = false;
-        static int minb = 3;
         if (!attr_s) {
           cudaFuncSetAttribute(push_slots_2d<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
           cudaFuncSetAttribute(push_slots_2d<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
@@ -2950,7 +2947,6 @@ inline void launch_push(const PushParams &P, int nd, bool tiled, cudaStream_t s,
           cudaFuncSetAttribute(push_slots_2d<8, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pushslots_smem<8>());
           attr_s = true;
         }
-        (void)minb;
         if (P.hc_push) {   // Higuera-Cary rotation: the same kernels with the other gamma (particles.F90:386-398)
           if (P.rowd == 32) push_slots_2d<8, 3, false, true><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);
           else push_slots_2d<8, 3, true, true><<<P.tg.ntiles, 128, pushslots_smem<8>(), s>>>(P);

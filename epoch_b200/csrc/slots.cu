@@ -207,11 +207,6 @@ __global__ void __launch_bounds__(256) k_aos(const __grid_constant__ AosOp A) {
 __global__ void k_clamp_counts(const int *cnt, int *out, int n, int R) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = min(cnt[i], R);
 }
-__global__ void k_set_flags(unsigned char *f, const int *count_dev, int base_is_count, int n, unsigned char v) {
-  // flags of n entries appended at *count_dev (read before k_bump runs on the same stream)
-  const int base = base_is_count ? *count_dev : 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f[base + i] = v;
-}
 __global__ void k_bump(int *count_dev, int n) { *count_dev += n; }
 
 }  // namespace
