@@ -274,6 +274,8 @@ def test_ekbar_temperature_decomposed_equals_single_rank(bc):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("ndims,n,bc", [(1, (64,), "periodic"), (2, (32, 24), "periodic"), (2, (32, 24), "reflect"),
+                                        # extents that are no multiple of the 16 x 8-cell tiles: padding columns of k_moment2_slots
+                                        (2, (21, 13), "periodic"), (2, (19, 11), "reflect"),
                                         (3, (10, 9, 8), "periodic"), (3, (10, 9, 8), "reflect")])
 def test_ekbar_temperature_match_oracle_gpu(ndims, n, bc):
     from tests.gpu_util import make_pair, rel_l2, run_both
@@ -370,7 +372,8 @@ def test_species_current_sums_to_deposited_current_scale():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ndims,n,bc", [(1, (64,), "periodic"), (2, (32, 24), "reflect"), (3, (10, 9, 8), "periodic")])
+@pytest.mark.parametrize("ndims,n,bc", [(1, (64,), "periodic"), (2, (32, 24), "reflect"), (2, (21, 13), "periodic"),
+                                        (3, (10, 9, 8), "periodic")])
 def test_flux_momentum_current_weight_match_oracle_gpu(ndims, n, bc):
     from tests.gpu_util import make_pair, rel_l2, run_both
     dk = decks.thermal(ndims, n, ppc=5, temp_k=2.0e9, bc=bc, two_species=True, drift=(3.0e-23, -1.0e-23, 2.0e-23))
