@@ -705,9 +705,12 @@ struct DestOp {
   int *dest;
   int *count;      // [nranks]
   int *err;
+  int drop;        // moving window, x_min ranks: particles with x < drop_below are not kept (remove_particles, window.F90:324-345)
+  double drop_below;
 };
 __global__ void __launch_bounds__(256) k_dest(const __grid_constant__ DestOp D) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < D.n; i += (long long)gridDim.x * blockDim.x) {
+    if (D.drop && D.x[0][i] < D.drop_below) { D.dest[i] = -1; continue; }
     int co[3] = {0, 0, 0};
     bool ok = true;
     for (int d = 0; d < D.nd; d++) {
@@ -754,10 +757,82 @@ __global__ void k_absmax(const double *a, size_t n, unsigned long long *out) {
   if (m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
+// shift_fields on an x_max rank after the arrays have moved one cell to the left (window.F90:126-143, epoch1d
+// :114-127, epoch3d :141-160): the outermost ghost layer keeps what it held (shift_field's loop stops one short), the
+// incoming cell takes the boundary snapshots and its neighbours are averaged.  One thread per transverse point.
+struct WindowFixOp {
+  double *f[9];
+  const double *snap;   // [6][plane] of the x_max side
+  int nd, sz[3], nx;
+  size_t plane;
+};
+__global__ void __launch_bounds__(256) k_window_fix(const __grid_constant__ WindowFixOp O) {
+  const int ey_ = O.nd >= 2 ? O.sz[1] : 1, ez_ = O.nd >= 3 ? O.sz[2] : 1;
+  const size_t total = (size_t)ey_ * ez_;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % ey_) + 1 - NG, k = (int)(t / ey_) + 1 - NG;
+    const int jj = O.nd >= 2 ? j : 1, kk = O.nd >= 3 ? k : 1;
+    const int nx = O.nx;
+    size_t o = (size_t)(nx + NG - 1);                 // cell (nx, j, k); x is the fastest index: cell nx + a is at o + a
+    if (O.nd >= 2) o += (size_t)O.sz[0] * (size_t)(jj + NG - 1);
+    if (O.nd >= 3) o += (size_t)O.sz[0] * (size_t)O.sz[1] * (size_t)(kk + NG - 1);
+    for (int q = 0; q < 9; q++) O.f[q][o + NG] = O.f[q][o + NG - 1];
+#define SN(q) O.snap[(size_t)(q) * O.plane + t]
+    double *ex = O.f[EPB_EX], *ey = O.f[EPB_EY], *ez = O.f[EPB_EZ], *bx = O.f[EPB_BX], *by = O.f[EPB_BY], *bz = O.f[EPB_BZ];
+    ex[o] = SN(EPB_EX);
+    ex[o + 1] = SN(EPB_EX);
+    ey[o + 1] = SN(EPB_EY);
+    ez[o + 1] = SN(EPB_EZ);
+    ex[o - 1] = 0.5 * (ex[o - 2] + ex[o]);
+    ey[o] = 0.5 * (ey[o - 1] + ey[o + 1]);
+    ez[o] = 0.5 * (ez[o - 1] + ez[o + 1]);
+    bx[o + 1] = SN(EPB_BX);
+    by[o] = SN(EPB_BY);
+    bz[o] = SN(EPB_BZ);
+    bx[o] = 0.5 * (bx[o - 1] + bx[o + 1]);
+    by[o - 1] = 0.5 * (by[o - 2] + by[o]);
+    bz[o - 1] = 0.5 * (bz[o - 2] + bz[o]);
+#undef SN
+  }
+}
+
+// what makes a redistribution a window shift: the x geometry of the new window
+struct WindowArgs { double x_grid_min; };
+
+int redistribute_impl(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd_, const epb_config *ncfg,
+                      const epb_species *nsp, epb_handle **out, const WindowArgs *win);
+
 }  // namespace
 
 extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd_, const epb_config *ncfg,
                                 const epb_species *nsp, epb_handle **out) {
+  return redistribute_impl(oh, od, nd_, ncfg, nsp, out, nullptr);
+}
+
+// One cell of shift_window (housekeeping/window.F90:62-94) plus the particle_bcs that follows it (:383-385), as a
+// redistribution onto the same decomposition one cell further along x: every field cell goes to the rank that owns
+// it in the new window (shift_field + field_bc), the incoming cell of the x_max ranks is fixed up (k_window_fix),
+// particles left of the new x_min are dropped on the x_min ranks (remove_particles) and the others go to the rank
+// whose [x_min_local, x_max_local) of the NEW grid holds them.  insert_particles is the host's (epb_append_species
+// afterwards).  Collective; *out replaces old_h.
+extern "C" int epb_shift_window(epb_handle *oh, const epb_decomp *d, const epb_config *ncfg, const epb_species *nsp,
+                                double x_grid_min, epb_handle **out) {
+  if (!oh || !d || !ncfg || !out) return EPB_ERR_ARG;
+  for (int s = 0; s < 2; s++)
+    if (oh->cfg.bc_field[s] == EPB_BC_PERIODIC || ncfg->bc_field[s] == EPB_BC_PERIODIC)
+      return epb_fail(oh, EPB_ERR_UNSUPPORTED, "epb_shift_window: the window moves along a non-periodic x only");
+  for (int q = 0; q < 3; q++)
+    if (ncfg->n[q] != oh->cfg.n[q] || ncfg->n_global[q] != oh->cfg.n_global[q])
+      return epb_fail(oh, EPB_ERR_ARG, "epb_shift_window: the decomposition must stay as it is");
+  WindowArgs w;
+  w.x_grid_min = x_grid_min;
+  return redistribute_impl(oh, d, d, ncfg, nsp, out, &w);
+}
+
+namespace {
+
+int redistribute_impl(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd_, const epb_config *ncfg,
+                      const epb_species *nsp, epb_handle **out, const WindowArgs *win) {
   if (!oh || !od || !nd_ || !ncfg || !out) return EPB_ERR_ARG;
   *out = nullptr;
   const epb_config &oc = oh->cfg;
@@ -808,12 +883,20 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
       const int co[3] = {me % npx, (me / npx) % npy, me / (npx * npy)};
       for (int d = 0; d < nd; d++) { omin[d] = od->cell_min[d][co[d]]; nmin[d] = nd_->cell_min[d][co[d]]; }
     }
-    const Box my_old = owned_box(*od, oc, me), my_new = owned_box(*nd_, oc, me);
+    // window shift: in the numbering of the old window the new one owns the same cells one further along x
+    const int xs = win ? 1 : 0;
+    nmin[0] += xs;
+    auto new_box = [&](int p) {
+      Box b = owned_box(*nd_, oc, p);
+      b.lo[0] += xs; b.hi[0] += xs;
+      return b;
+    };
+    const Box my_old = owned_box(*od, oc, me), my_new = new_box(me);
     std::vector<Box> sbox(nranks), rbox(nranks);
     std::vector<char> shas(nranks, 0), rhas(nranks, 0);
     std::vector<size_t> soff(nranks + 1, 0), roff(nranks + 1, 0);
     for (int p = 0; p < nranks; p++) {
-      shas[p] = intersect(my_old, owned_box(*nd_, oc, p), sbox[p]);
+      shas[p] = intersect(my_old, new_box(p), sbox[p]);
       rhas[p] = intersect(my_new, owned_box(*od, oc, p), rbox[p]);
       soff[p + 1] = soff[p] + (shas[p] ? 3 * box_cells(sbox[p]) : 0);
       roff[p + 1] = roff[p] + (rhas[p] ? 3 * box_cells(rbox[p]) : 0);
@@ -844,6 +927,17 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
       rc = epb_halo_exchange(nh, f0, 3, false);   // do_field_mpi_with_lengths (remap_field, balance.F90:1082)
       if (rc) return fail(rc);
     }
+    if (win && ncfg->is_boundary[1]) {
+      WindowFixOp W;
+      for (int q = 0; q < 9; q++) W.f[q] = nh->f(q);
+      W.snap = nh->snap + (size_t)6 * nh->plane;
+      W.nd = nd;
+      for (int q = 0; q < 3; q++) W.sz[q] = nh->sz[q];
+      W.nx = ncfg->n[0];
+      W.plane = nh->plane;
+      k_window_fix<<<nblk(nh->plane), 256, 0, st>>>(W);
+      nh->launches++;
+    }
   }
 
   // ---- particles: distribute_particles ------------------------------------------------------------------------
@@ -864,7 +958,8 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
   for (int d = 0; d < nd; d++) {
     D.nproc[d] = nd_->nproc[d];
     const double dx = oc.dx[d];
-    const double x_grid_min = oc.gmin[d] + dx / 2.0;   // setup.F90:169,180
+    // setup.F90:169,180; the moving window accumulates its own x_grid_min (window.F90:74)
+    const double x_grid_min = (win && d == 0) ? win->x_grid_min : oc.gmin[d] + dx / 2.0;
     const int np = nd_->nproc[d];
     for (int ip = 0; ip < np; ip++) {
       const double gmin_ip = x_grid_min + (double)(nd_->cell_min[d][ip] - 1) * dx;   // x_grid_mins(iproc)
@@ -875,6 +970,8 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
   }
   D.dest = d_dest;
   D.count = d_cnt;
+  D.drop = (win && oc.is_boundary[0]) ? 1 : 0;
+  D.drop_below = ncfg->gmin[0];
   if (!nh->d_err) {
     if (cudaMalloc(&nh->d_err, sizeof(int)) != cudaSuccess) { cleanup(); return fail(EPB_ERR_CUDA); }
     cudaMemsetAsync(nh->d_err, 0, sizeof(int), st);
@@ -973,3 +1070,5 @@ extern "C" int epb_redistribute(epb_handle *oh, const epb_decomp *od, const epb_
   *out = nh;
   return EPB_OK;
 }
+
+}  // namespace

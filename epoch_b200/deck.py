@@ -109,6 +109,18 @@ class Deck:
     cpml_kappa_max: float = 20.0
     cpml_a_max: float = 0.15
     cpml_sigma_max: float = 0.7
+    # window block (deck_window_block.f90): move_window, window_v_x, window_start_time, window_stop_time.  The
+    # boundary conditions after the move are the ones before it here (bc_x_min_after_move ... default to them).
+    move_window: bool = False
+    window_v_x: float = 0.0
+    window_start_time: float = 0.0
+    window_stop_time: float = 1.0e300
+    # state of the moving window (window.F90:62-94): x_grid_min and xb_min as shift_window has accumulated them
+    # (None: the grid of setup_grid); dx is frozen at its setup_grid value the first time the window moves
+    window_grid_min: Optional[float] = None
+    window_xb_min: Optional[float] = None
+    window_dx: Optional[float] = None
+    window_shifts: int = 0
 
     # -- grid (setup.F90:162-204) ------------------------------------------
     def cpml_t(self) -> int:
@@ -121,12 +133,34 @@ class Deck:
         return int(self.n[d]) + 2 * self.cpml_t()
 
     def dx(self, d: int) -> float:
-        # setup.F90:168: length_x / REAL(nx_global - 2 * cpml_thickness)
+        # setup.F90:168: length_x / REAL(nx_global - 2 * cpml_thickness); not recomputed when the window moves
+        if d == 0 and self.window_dx is not None:
+            return self.window_dx
         return (self.xmax[d] - self.xmin[d]) / float(self.n[d])
 
     def grid_min(self, d: int) -> float:
         # setup.F90:169,180: x_grid_min = x_min - dx * cpml_thickness, then shifted to the cell centre
+        if d == 0 and self.window_grid_min is not None:
+            return self.window_grid_min
         return (self.xmin[d] - self.dx(d) * self.cpml_t()) + self.dx(d) / 2.0
+
+    def shift_window_geometry(self) -> None:
+        """The grid part of one pass of shift_window's loop (window.F90:73-86): x_grid_min = x_global(1) + dx,
+        xb_min = xb_global(1) + dx, x_min = xb_min + dx * cpml_thickness, x_max = xb_global(nx_global+1) - dx *
+        cpml_thickness, each accumulated in floating point exactly like that; dx and length_x stay."""
+        dx = self.dx(0)
+        t = self.cpml_t()
+        if self.window_dx is None:
+            xb = self.xmin[0] - dx * t                      # setup.F90:169,176
+            self.window_grid_min = xb + dx / 2.0
+            self.window_xb_min = xb
+            self.window_dx = dx
+            self.xmin, self.xmax = list(self.xmin), list(self.xmax)
+        self.window_grid_min = self.window_grid_min + dx
+        self.window_xb_min = self.window_xb_min + dx
+        self.xmin[0] = self.window_xb_min + dx * t
+        self.xmax[0] = (self.window_xb_min + float(self.ncells(0) + 1 - 1) * dx) - dx * t
+        self.window_shifts += 1
 
     def x_global(self, d: int, i):
         """Cell-centre coordinate of global cell i (1-based), setup.F90:188."""
@@ -410,6 +444,27 @@ def run(deck: Deck, backend, local_ranks: Sequence[int], on_dump: Optional[Calla
     if on_dump is not None and clock.due(time, False):
         on_dump(step, time)
     nsteps = deck.nsteps if max_steps is None else max_steps
+    window_started, window_shift_fraction = False, 0.0
+
+    def moving_window(t):
+        # window.F90:350-392; the shift itself (shift_window, setup_bc_lists, particle_bcs) is the backend's
+        nonlocal window_started, window_shift_fraction
+        if not deck.move_window:
+            return
+        if not window_started and deck.window_start_time <= t < deck.window_stop_time:
+            window_shift_fraction = 0.0
+            window_started = True
+        if window_started:
+            if t >= deck.window_stop_time or deck.window_v_x <= 0.0:
+                return
+            window_shift_fraction = window_shift_fraction + dt * deck.window_v_x / deck.dx(0)
+            cells = int(np.floor(window_shift_fraction))
+            if cells > 0:
+                for _ in range(cells):
+                    deck.shift_window_geometry()
+                backend.shift_window(cells)
+                window_shift_fraction = window_shift_fraction - float(cells)
+
     while True:
         backend.fields_half()
         backend.push()
@@ -423,6 +478,7 @@ def run(deck: Deck, backend, local_ranks: Sequence[int], on_dump: Optional[Calla
         time = time + dt / 2.0
         push_sources(time)
         backend.fields_final()
+        moving_window(time)
     if on_dump is not None:
         on_dump(step, time)
     return step, time

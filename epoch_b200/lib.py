@@ -22,7 +22,7 @@ SYMBOLS = (
     "epb_cell_counts", "epb_field_device_ptr", "epb_set_laser_source", "epb_init_boundaries",
     "epb_fields_half", "epb_push", "epb_current_finish", "epb_fields_final", "epb_sort",
     "epb_global_count", "epb_launch_count", "epb_push_kernel_ms", "epb_field_energy", "epb_step_scalars_async", "epb_wait_scalars",
-    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute", "epb_collide", "epb_collide_pairs_test", "epb_set_boundary_temperature",
+    "epb_kinetic_energy", "epb_calc_moment", "epb_load_profile", "epb_redistribute", "epb_shift_window", "epb_collide", "epb_collide_pairs_test", "epb_set_boundary_temperature",
 )
 
 
@@ -126,6 +126,8 @@ def load():
     L.epb_collide.argtypes = [vp, C.POINTER(Collisions)]
     L.epb_collide_pairs_test.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
     L.epb_redistribute.argtypes = [vp, C.POINTER(Decomp), C.POINTER(Decomp), C.POINTER(Config), C.POINTER(SpeciesCfg),
+                                   C.POINTER(vp)]
+    L.epb_shift_window.argtypes = [vp, C.POINTER(Decomp), C.POINTER(Config), C.POINTER(SpeciesCfg), C.c_double,
                                    C.POINTER(vp)]
     L.epb_load_profile.argtypes = [vp, i32, dp]
     L.epb_launch_count.argtypes = [vp]; L.epb_launch_count.restype = i64

@@ -225,6 +225,29 @@ class Simulation:
         if self._stream is not None:
             self._chk(self.L.epb_set_stream(self._h, C.c_void_p(self._stream)))
 
+    def shift_window(self, cells: int = 1, inserted: Optional[Sequence[np.ndarray]] = None,
+                     capacities: Optional[Sequence[int]] = None):
+        """One cell of the moving window (window.F90:62-94, :383-385) on the device: epb_shift_window, then the new
+        plasma.  The driver has already moved the deck's grid (Deck.shift_window_geometry).  `inserted`: per species
+        the particles insert_particles created on this rank ((n, ndims + 4), pack_particle order; None or empty on
+        ranks that are not on the x_max edge) -- drawing them is the host's job (deck expressions, KISS stream)."""
+        if int(cells) != 1:
+            raise EpbError("Simulation.shift_window moves one cell per call (dt * window_v_x / dx < 1 under the CFL limit)")
+        cfg, sp, geo = build_config(self.deck, self.rank, capacities=capacities, **self._build_args)
+        d = _decomp(self.deck)
+        out = C.c_void_p()
+        rc = self.L.epb_shift_window(self._h, C.byref(d), C.byref(cfg), sp, C.c_double(self.deck.grid_min(0)), C.byref(out))
+        if rc != 0:
+            self._chk(rc)
+        self._h = out
+        self.cfg, self.species_cfg, self.geo = cfg, sp, geo
+        if self._stream is not None:
+            self._chk(self.L.epb_set_stream(self._h, C.c_void_p(self._stream)))
+        if inserted is not None:
+            for isp, arr in enumerate(inserted):
+                if arr is not None and len(arr):
+                    self.append_species(isp, arr)
+
     # ------------------------------------------------------------------
     def _chk(self, rc):
         if rc != 0:

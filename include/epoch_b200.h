@@ -247,6 +247,22 @@ typedef struct epb_decomp {
 int epb_redistribute(epb_handle *old_h, const epb_decomp *old_d, const epb_decomp *new_d, const epb_config *new_cfg,
                      const epb_species *new_species, epb_handle **out);
 
+/* -- moving window (housekeeping/window.F90) -------------------------------------------------------------------
+ * One cell of shift_window (:62-94) and the setup_bc_lists / particle_bcs that moving_window runs after it (:383-385).
+ * The caller has moved its grid by one cell along x the way window.F90:73-86 does (x_grid_min = x_global(1) + dx,
+ * xb_min, x_min, x_max accumulated; dx unchanged) and passes the config of THIS rank in the new window -- same
+ * decomposition `d`, same extents, grid_min_local / min_local / max_local / gmin / gmax / min_outer / max_outer of
+ * the new grid, the boundary conditions to use from now on (bc_*_after_move) -- and the new x_grid_min.  The library
+ * builds the new device state: every field array one cell to the left with the ghost cells refilled from the
+ * neighbours (shift_field + field_bc), the incoming cell of the x_max ranks fixed up (:126-143), particles left of
+ * the new x_min removed on the x_min ranks (remove_particles :324-345), every other particle on the rank whose
+ * [x_min_local, x_max_local) of the new grid holds it.  insert_particles (:182-320) consumes the host's random
+ * numbers and deck expressions and stays the host's: hand the new plasma over with epb_append_species afterwards.
+ * Collective.  *out replaces old_h.  Not for CPML runs or non-zero boundary snapshots (as epb_redistribute); laser
+ * sources and wall temperatures are per-step / per-handle inputs and have to be set again. */
+int epb_shift_window(epb_handle *old_h, const epb_decomp *d, const epb_config *new_cfg, const epb_species *new_species,
+                     double x_grid_min, epb_handle **out);
+
 /* -- binary collisions ---------------------------------------------------------------------------------------
  * particle_collisions (physics_packages/collisions.F90:86-214), called by PROGRAM pic after push_particles on the
  * steps where MODULO(step, coll_n_step) == coll_n_step - 1 (epoch2d.F90:219-236).  The per-cell lists the reference

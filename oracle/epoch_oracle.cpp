@@ -207,6 +207,7 @@ struct Rank {
   Arr psi[3][4];
   std::vector<std::vector<Particle>> part;       // per species
   std::vector<std::vector<int64_t>> bnd_cand;    // boundary candidate indices per species
+  std::vector<std::vector<Particle>> inserted;   // per species: what the window's insert_particles created since orc_window_clear_inserted
   Rng rng;
 };
 
@@ -218,6 +219,7 @@ struct World {
   double d[3] = {1, 1, 1};  // dx,dy,dz
   double length[3] = {0, 0, 0};
   double grid_min[3] = {0, 0, 0};  // x_grid_min (cell centre of global cell 1)
+  double xb_min[3] = {0, 0, 0};    // xb_global(1): the low edge of global cell 1 (setup.F90:176-177), moved by the window
   double min_outer[3], max_outer[3];
   std::vector<int> cell_min[3], cell_max[3];
   bool periods[3] = {false, false, false};
@@ -358,6 +360,7 @@ void setup_world(World &w) {
     w.length[d] = cf.xmax[d] - cf.xmin[d];
     w.d[d] = w.length[d] / (double)(w.n_ext[d] - 2 * w.cpml_t);
     double g = cf.xmin[d] - w.d[d] * w.cpml_t;
+    w.xb_min[d] = g;
     w.grid_min[d] = g + w.d[d] / 2.0;
     // utilities.f90:367-369
     double boundary_shift = (double)((1 + png + w.cpml_t) / 2);
@@ -463,6 +466,7 @@ void setup_world(World &w) {
       }
     R.part.resize(w.sp.size());
     R.bnd_cand.resize(w.sp.size());
+    R.inserted.resize(w.sp.size());
     // setup.F90:566-571
     R.rng.init(cf.seed + rk);
   }
@@ -2278,6 +2282,213 @@ void auto_load(World &w) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Moving window: housekeeping/window.F90 (epoch1d / epoch2d / epoch3d; the x direction only, as there)
+// ---------------------------------------------------------------------------
+// The species description of this harness is a uniform density inside a box with uniform temperature and drift
+// (SpeciesCfg).  The reference evaluates the deck's density / temperature / drift functions at pack_ix = nx and
+// pack_iy = 0 .. ny+1 (ghost positions included, no periodic wrap); here a transverse position outside the domain
+// takes the domain's edge value, which is what a constant deck expression gives.
+static double window_density(const World &w, const Rank &R, const SpeciesCfg &S, int iy, int iz) {
+  const int nd = w.nd;
+  int ii[3] = {R.n[0], iy, iz};
+  bool in = true;
+  for (int d = 0; d < nd; d++) {
+    int gi = ii[d] + R.gmin[d] - 1;
+    if (d > 0) gi = std::min(std::max(gi, 1), w.n_ext[d]);
+    const double xc = x_global(w, d, gi);
+    if (xc < S.box_lo[d] || xc >= S.box_hi[d]) in = false;
+  }
+  double v = in ? S.density : 0.0;
+  const double dmin = 2.220446049250313e-16;   // initial_conditions%density_min = EPSILON(1.0_num), deck_species_block.F90
+  if (v < dmin) v = 0.0;
+  return v;
+}
+
+// insert_particles (epoch2d window.F90:182-320, epoch1d :158-262, epoch3d :197-352): one cell of fresh plasma beyond
+// the right-hand edge, on the x_max ranks, BEFORE the grid moves
+template <int ND>
+void window_insert_particles(World &w) {
+  const double dmin = 2.220446049250313e-16;
+  for (Rank &R : w.r) {
+    if (!R.is_bnd[1]) continue;
+    for (size_t is = 0; is < w.sp.size(); is++) {
+      const SpeciesCfg &S = w.sp[is];
+      const int64_t npart_per_cell = (int64_t)std::floor(S.npart_per_cell);
+      const double npart_frac = S.npart_per_cell - (double)npart_per_cell;
+      const double x_grid_max = x_global(w, 0, w.n_ext[0]);
+      const double x0 = x_grid_max + 0.5 * w.d[0];
+      std::vector<Particle> app;
+      auto momentum = [&](Particle &P, const double *temp_local, const double *drift_local) {
+        for (int i = 0; i < 3; i++) {
+          // momentum_from_temperature, particle_temperature.F90:388-398
+          const double stdev = std::sqrt(temp_local[i] * kb * S.mass);
+          P.p[i] = R.rng.box_muller(stdev, drift_local[i]);
+        }
+      };
+      if (ND == 1) {
+        const double density = window_density(w, R, S, 1, 1);
+        if (density < dmin) continue;
+        int64_t n_frac = 0;
+        if (npart_frac > 0.0 && R.rng.random() < npart_frac) n_frac = 1;
+        const double wdata = w.d[0] / (double)(npart_per_cell + n_frac);
+        for (int64_t ipart = 1; ipart <= npart_per_cell + n_frac; ipart++) {
+          Particle P;
+          std::memset(&P, 0, sizeof P);
+          P.pos[0] = x0 + R.rng.random() * w.d[0];
+          momentum(P, S.temp, S.drift);
+          P.w = density * wdata;
+          app.push_back(P);
+        }
+      } else {
+        const int ny = R.n[1], nz = ND >= 3 ? R.n[2] : 1;
+        const int kz0 = ND >= 3 ? 0 : 1, kz1 = ND >= 3 ? nz + 1 : 1;
+        // density(0:ny+1[, 0:nz+1]); temperature and drift are uniform here
+        std::vector<double> dens((size_t)(ny + 2) * (ND >= 3 ? nz + 2 : 1));
+        auto D = [&](int iy, int iz) -> double & { return dens[(size_t)(ND >= 3 ? iz : 0) * (ny + 2) + iy]; };
+        for (int iz = kz0; iz <= kz1; iz++)
+          for (int iy = 0; iy <= ny + 1; iy++) D(iy, ND >= 3 ? iz : 0) = window_density(w, R, S, iy, iz);
+        for (int iz = 1; iz <= nz; iz++)
+          for (int iy = 1; iy <= ny; iy++) {
+            const int kz = ND >= 3 ? iz : 0;
+            if (D(iy, kz) < dmin) continue;
+            int64_t n_frac = 0;
+            if (npart_frac > 0.0 && R.rng.random() < npart_frac) n_frac = 1;
+            double wdata = w.d[0] * w.d[1];
+            if (ND >= 3) wdata = wdata * w.d[2];
+            wdata = wdata / (double)(npart_per_cell + n_frac);
+            for (int64_t ipart = 1; ipart <= npart_per_cell + n_frac; ipart++) {
+              Particle P;
+              std::memset(&P, 0, sizeof P);
+              const double cell_frac_y = 0.5 - R.rng.random();
+              double cell_frac_z = 0.0;
+              if (ND >= 3) cell_frac_z = 0.5 - R.rng.random();
+              P.pos[0] = x0 + R.rng.random() * w.d[0];
+              P.pos[1] = x_global(w, 1, iy + R.gmin[1] - 1) - cell_frac_y * w.d[1];
+              if (ND >= 3) P.pos[2] = x_global(w, 2, iz + R.gmin[2] - 1) - cell_frac_z * w.d[2];
+              double gy[3], gz[3] = {0.0, 1.0, 0.0};
+              const double cy2 = cell_frac_y * cell_frac_y;
+              gy[0] = 0.5 * (0.25 + cy2 + cell_frac_y);
+              gy[1] = 0.75 - cy2;
+              gy[2] = 0.5 * (0.25 + cy2 - cell_frac_y);
+              if (ND >= 3) {
+                const double cz2 = cell_frac_z * cell_frac_z;
+                gz[0] = 0.5 * (0.25 + cz2 + cell_frac_z);
+                gz[1] = 0.75 - cz2;
+                gz[2] = 0.5 * (0.25 + cz2 - cell_frac_z);
+              }
+              double temp_local[3] = {0.0, 0.0, 0.0}, drift_local[3] = {0.0, 0.0, 0.0};
+              for (int i = 0; i < 3; i++) {
+                if (ND == 2) {
+                  for (int sy = -1; sy <= 1; sy++) {
+                    temp_local[i] = temp_local[i] + gy[sy + 1] * S.temp[i];
+                    drift_local[i] = drift_local[i] + gy[sy + 1] * S.drift[i];
+                  }
+                } else {
+                  for (int sz_ = -1; sz_ <= 1; sz_++)
+                    for (int sy = -1; sy <= 1; sy++) {
+                      temp_local[i] = temp_local[i] + gy[sy + 1] * gz[sz_ + 1] * S.temp[i];
+                      drift_local[i] = drift_local[i] + gy[sy + 1] * gz[sz_ + 1] * S.drift[i];
+                    }
+                }
+              }
+              momentum(P, temp_local, drift_local);
+              double weight_local = 0.0;
+              if (ND == 2) {
+                for (int sy = -1; sy <= 1; sy++) weight_local = weight_local + gy[sy + 1] * D(iy + sy, 0);
+              } else {
+                for (int sz_ = -1; sz_ <= 1; sz_++)
+                  for (int sy = -1; sy <= 1; sy++) weight_local = weight_local + gy[sy + 1] * gz[sz_ + 1] * D(iy + sy, iz + sz_);
+              }
+              P.w = weight_local * wdata;
+              app.push_back(P);
+            }
+          }
+      }
+      R.part[is].insert(R.part[is].end(), app.begin(), app.end());
+      R.inserted[is].insert(R.inserted[is].end(), app.begin(), app.end());
+    }
+  }
+}
+
+// shift_window (window.F90:62-94) for one cell: insert, move the grid (x_grid_min, xb_min, x_min, x_max accumulate
+// one dx at a time exactly as there; dx and length_x are not recomputed), setup_grid_x (utilities.f90:343-381),
+// remove_particles (:324-345), shift_fields (:98-178)
+template <int ND>
+void shift_window_once(World &w) {
+  const double dx = w.d[0];
+  window_insert_particles<ND>(w);
+  w.grid_min[0] = x_global(w, 0, 1) + dx;
+  w.xb_min[0] = w.xb_min[0] + dx;                       // xb_global(1) + dx
+  w.cfg.xmin[0] = w.xb_min[0] + dx * (double)w.cpml_t;
+  w.cfg.xmax[0] = (w.xb_min[0] + (double)(w.n_ext[0] + 1 - 1) * dx) - dx * (double)w.cpml_t;   // xb_global(nx_global+1) - ...
+  for (Rank &R : w.r) {
+    R.grid_min_local[0] = x_global(w, 0, w.cell_min[0][R.coords[0]]);
+    const double hdx = 0.5 * dx;
+    R.min_local[0] = R.grid_min_local[0] - hdx;
+    R.max_local[0] = x_global(w, 0, w.cell_max[0][R.coords[0]] + 1) - hdx;
+  }
+  const double boundary_shift = (double)((1 + png + w.cpml_t) / 2);
+  w.min_outer[0] = w.cfg.xmin[0] - boundary_shift * dx;
+  w.max_outer[0] = w.cfg.xmax[0] + boundary_shift * dx;
+  // remove_particles: only processors on the left
+  for (Rank &R : w.r) {
+    if (!R.is_bnd[0]) continue;
+    for (auto &pl : R.part) {
+      size_t k = 0;
+      for (size_t i = 0; i < pl.size(); i++)
+        if (!(pl[i].pos[0] < w.cfg.xmin[0])) pl[k++] = pl[i];
+      pl.resize(k);
+    }
+  }
+  // shift_fields: every array one cell to the left (ghost cells included), then field_bc
+  for (int which = 0; which < NFIELD; which++) {
+    for (Rank &R : w.r) {
+      Arr &a = R.f[which];
+      const Box b = full_box(a);
+      for (int k = b.lo[2]; k <= b.hi[2]; k++)
+        for (int j = b.lo[1]; j <= b.hi[1]; j++)
+          for (int i = 1 - NG; i <= R.n[0] + NG - 1; i++) a(i, j, k) = a(i + 1, j, k);
+    }
+    field_bc(w, which);
+  }
+  // fix the incoming field cell on the x_max ranks (window.F90:126-143)
+  for (Rank &R : w.r) {
+    if (!R.is_bnd[1]) continue;
+    const int nx = R.n[0];
+    Arr &ex = R.f[EX], &ey = R.f[EY], &ez = R.f[EZ], &bx = R.f[BX], &by = R.f[BY], &bz = R.f[BZ];
+    const Box b = full_box(ex);
+    for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++) {
+        ex(nx, j, k) = R.snap_max[EX](1, j, k);
+        ex(nx + 1, j, k) = R.snap_max[EX](1, j, k);
+        ey(nx + 1, j, k) = R.snap_max[EY](1, j, k);
+        ez(nx + 1, j, k) = R.snap_max[EZ](1, j, k);
+        ex(nx - 1, j, k) = 0.5 * (ex(nx - 2, j, k) + ex(nx, j, k));
+        ey(nx, j, k) = 0.5 * (ey(nx - 1, j, k) + ey(nx + 1, j, k));
+        ez(nx, j, k) = 0.5 * (ez(nx - 1, j, k) + ez(nx + 1, j, k));
+        bx(nx + 1, j, k) = R.snap_max[BX](1, j, k);
+        by(nx, j, k) = R.snap_max[BY](1, j, k);
+        bz(nx, j, k) = R.snap_max[BZ](1, j, k);
+        bx(nx, j, k) = 0.5 * (bx(nx - 1, j, k) + bx(nx + 1, j, k));
+        by(nx - 1, j, k) = 0.5 * (by(nx - 2, j, k) + by(nx, j, k));
+        bz(nx - 1, j, k) = 0.5 * (bz(nx - 2, j, k) + bz(nx, j, k));
+      }
+  }
+}
+
+// the part of moving_window (window.F90:350-397) that follows the decision to shift: shift_window(cells),
+// setup_bc_lists, particle_bcs.  The decision (window_shift_fraction += dt * window_v_x / dx ...) is the host's.
+void shift_window(World &w, int cells) {
+  for (int i = 0; i < cells; i++) {
+    if (w.nd == 1) shift_window_once<1>(w);
+    else if (w.nd == 2) shift_window_once<2>(w);
+    else shift_window_once<3>(w);
+  }
+  setup_bc_lists(w);
+  particle_bcs(w);
+}
+
 template <int ND>
 void init_sequence(World &w) {
   // epoch2d.F90:144-162
@@ -2414,6 +2625,35 @@ void orc_push_only(void *h) {
   push_all(w);
 }
 void orc_particle_bcs(void *h) { particle_bcs(*(World *)h); }
+// moving window: shift by `cells` cells (returns -1 for a configuration window.F90 is not restated for)
+int orc_shift_window(void *h, int cells) {
+  World &w = *(World *)h;
+  if (w.cpml_t != 0 || w.periods[0]) return -1;
+  shift_window(w, cells);
+  return 0;
+}
+// the particles insert_particles created since the last clear: count, then the data in orc_get_particles' layout
+int64_t orc_window_inserted_count(void *h, int rk, int is) { return (int64_t)((World *)h)->r[rk].inserted[is].size(); }
+void orc_window_inserted(void *h, int rk, int is, double *out) {
+  World &w = *(World *)h;
+  const int nd = w.nd, nv = nd + 4;
+  const auto &pl = w.r[rk].inserted[is];
+  for (size_t i = 0; i < pl.size(); i++) {
+    double *o = out + i * nv;
+    for (int d = 0; d < nd; d++) o[d] = pl[i].pos[d];
+    for (int d = 0; d < 3; d++) o[nd + d] = pl[i].p[d];
+    o[nd + 3] = pl[i].w;
+  }
+}
+void orc_window_clear_inserted(void *h) {
+  for (Rank &R : ((World *)h)->r)
+    for (auto &v : R.inserted) v.clear();
+}
+// x_grid_min, xb_min, x_min, x_max of the x axis as the window has left them
+void orc_window_geometry(void *h, double out[4]) {
+  World &w = *(World *)h;
+  out[0] = w.grid_min[0]; out[1] = w.xb_min[0]; out[2] = w.cfg.xmin[0]; out[3] = w.cfg.xmax[0];
+}
 void orc_setup_bc_lists(void *h) { setup_bc_lists(*(World *)h); }
 void orc_current_finish(void *h) { current_finish(*(World *)h); }
 void orc_efield_bcs(void *h) { efield_bcs(*(World *)h); }

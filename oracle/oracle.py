@@ -80,6 +80,15 @@ def lib():
         L.orc_calc_moment.restype = None
         L.orc_set_boundary_temperature.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
         L.orc_set_boundary_temperature.restype = None
+        L.orc_shift_window.argtypes = [C.c_void_p, C.c_int]
+        L.orc_window_inserted_count.restype = C.c_int64
+        L.orc_window_inserted_count.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_window_inserted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_window_inserted.restype = None
+        L.orc_window_clear_inserted.argtypes = [C.c_void_p]
+        L.orc_window_clear_inserted.restype = None
+        L.orc_window_geometry.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_window_geometry.restype = None
         L.orc_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.orc_collide.restype = None
         L.orc_collide_pairs_test.argtypes = [C.c_int] + [C.c_void_p] * 7
@@ -245,6 +254,35 @@ class Oracle:
         n = len(self.deck.species)
         cp = np.ascontiguousarray(np.asarray(coll_pairs, dtype=np.float64).reshape(n, n))
         lib().orc_collide(self._h, int(coll_n_step), int(use_nanbu), float(coulomb_log), cp.ctypes.data)
+
+    # -- moving window (housekeeping/window.F90) -------------------------------
+    def shift_window(self, cells):
+        """shift_window(cells) + setup_bc_lists + particle_bcs (window.F90:383-385).  The particles insert_particles
+        created are kept per rank and species until window_clear_inserted (window_inserted)."""
+        if lib().orc_shift_window(self._h, int(cells)) != 0:
+            raise RuntimeError("the oracle's moving window is restated for non-periodic x without CPML")
+        self._window_shifts = getattr(self, "_window_shifts", 0) + int(cells)
+        # the driver moves the deck's grid (Deck.shift_window_geometry, once per cell, before this call): both
+        # restatements of window.F90:73-86 must agree to the bit
+        if getattr(self.deck, "window_shifts", 0) == self._window_shifts:
+            g = self.window_geometry()
+            assert (self.deck.window_grid_min, self.deck.window_xb_min, self.deck.xmin[0], self.deck.xmax[0]) == g, \
+                "host-side window geometry differs from the oracle's"
+
+    def window_inserted(self, rk, isp):
+        n = lib().orc_window_inserted_count(self._h, rk, isp)
+        out = np.empty((n, self.nd + 4), dtype=np.float64)
+        if n:
+            lib().orc_window_inserted(self._h, rk, isp, out.ctypes.data)
+        return out
+
+    def window_clear_inserted(self):
+        lib().orc_window_clear_inserted(self._h)
+
+    def window_geometry(self):
+        g = (C.c_double * 4)()
+        lib().orc_window_geometry(self._h, g)
+        return tuple(g)
 
     def push(self): lib().orc_push(self._h)
     def push_only(self): lib().orc_push_only(self._h)
