@@ -56,6 +56,12 @@ def make_deck(name, world):
         dk = _cpml_case(3 if name == "cpml3d" else 2, particles=True)
         dk.nproc = (1, world, 1) if name == "cpml2d_y" else (world, 1, 1) if world < 4 else (2, world // 2, 1)
         return dk, 40, 1e-12
+    if name in ("window2d", "window3d", "window1d"):   # moving window at c: fields and particles change rank as the box moves
+        from tests.test_window import window_deck
+        nd = int(name[6])
+        n = {1: (96,), 2: (48, 24), 3: (24, 9, 8)}[nd]
+        npr = (world, 1, 1) if (world < 4 or nd == 1) else (2, world // 2, 1)
+        return window_deck(nd, n, ppc=4, nproc=npr, nsteps=16), 16, 1e-12
     raise KeyError(name)
 
 
@@ -85,9 +91,17 @@ def run_case(name, rank, world, share_id, strict=True, sort_interval=2, moments=
         def push(self): o.push(); sim.push()
         def current_finish(self): o.current_finish(); sim.current_finish()
         def fields_final(self): o.fields_final(); sim.fields_final()
+        def shift_window(self, cells):
+            # insert_particles is the host's (KISS stream, deck expressions): the oracle's new plasma goes to the device
+            o.window_clear_inserted()
+            o.shift_window(cells)
+            sim.shift_window(cells, [o.window_inserted(rank, isp) for isp in range(len(dk.species))])
 
     D.run(dk, Both(), ranks, None, max_steps=nsteps)
     res = {"case": name, "rank": rank, "ok": True, "msgs": []}
+    if dk.move_window and dk.window_shifts < 4:
+        res["ok"] = False
+        res["msgs"].append(f"the window moved only {dk.window_shifts} cells")
     for f in FIELDS:
         e = rel_l2(sim.download_field(f), o.field(rank, f))
         if not e <= tol:
