@@ -60,6 +60,13 @@ MODULE epoch_b200_mod
     INTEGER(C_INT32_T) :: n_global_min(3)
   END TYPE epb_config
 
+  ! struct epb_decomp (include/epoch_b200.h): cell_x_min(1:nprocx) ... of mpi_routines.F90:317-351 per axis
+  TYPE, BIND(C) :: epb_decomp
+    INTEGER(C_INT32_T) :: nproc(3)
+    TYPE(C_PTR) :: cell_min(3)
+    TYPE(C_PTR) :: cell_max(3)
+  END TYPE epb_decomp
+
   ! struct epb_species
   TYPE, BIND(C) :: epb_species
     REAL(C_DOUBLE) :: charge
@@ -128,6 +135,17 @@ MODULE epoch_b200_mod
       INTEGER(C_INT), VALUE :: ispecies
       INTEGER(C_INT64_T), VALUE :: n
       REAL(C_DOUBLE), INTENT(IN) :: packed(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION epb_shift_window(handle, d, cfg, species, x_grid_min_new, new_handle) &
+        BIND(C, NAME='epb_shift_window') RESULT(rc)
+      IMPORT :: C_INT, C_PTR, C_DOUBLE, epb_config, epb_species, epb_decomp
+      TYPE(C_PTR), VALUE :: handle
+      TYPE(epb_decomp), INTENT(IN) :: d
+      TYPE(epb_config), INTENT(IN) :: cfg
+      TYPE(epb_species), INTENT(IN) :: species(*)
+      REAL(C_DOUBLE), VALUE :: x_grid_min_new
+      TYPE(C_PTR), INTENT(OUT) :: new_handle
       INTEGER(C_INT) :: rc
     END FUNCTION
     FUNCTION epb_append_species(handle, ispecies, n, packed) &
@@ -250,7 +268,7 @@ CONTAINS
     TYPE(epb_species), ALLOCATABLE :: sp(:)
     CHARACTER(KIND=C_CHAR) :: id(128)
     INTEGER(C_INT32_T) :: info(4)
-    INTEGER :: ispecies, i, ix, iy, ierr
+    INTEGER :: ierr
 
     CALL b200_check(epb_abi_info(info))
     IF (info(1) /= C_SIZEOF(cfg)) CALL b200_check(1_C_INT)
@@ -266,6 +284,33 @@ CONTAINS
     IF (rank == 0) PRINT *, '*** ERROR *** epoch_b200: only the default (triangle) particle shape is supported'
     CALL abort_code(c_err_generic_error)
 #endif
+
+    CALL b200_fill_config(cfg, sp)
+    CALL b200_check(epb_create(cfg, sp, b200))
+    DEALLOCATE(sp)
+
+    IF (nproc > 1) THEN
+      IF (rank == 0) CALL b200_check(epb_nccl_unique_id(id))
+      CALL MPI_BCAST(id, 128, MPI_CHARACTER, 0, comm, ierr)
+      CALL b200_check(epb_set_comm(b200, id))
+    END IF
+
+    CALL b200_upload
+    ! setup_bc_lists + particle_bcs + efield_bcs + bfield_final_bcs(dt/2), epoch2d.F90:144-162
+    CALL b200_push_laser_sources
+    CALL b200_check(epb_init_boundaries(b200))
+
+  END SUBROUTINE b200_attach
+
+
+
+  ! The mirror of the shared_data globals the path reads, as they are NOW (b200_attach; again after the moving window
+  ! or the balancer has changed the grid or the decomposition).
+  SUBROUTINE b200_fill_config(cfg, sp)
+
+    TYPE(epb_config), INTENT(OUT) :: cfg
+    TYPE(epb_species), ALLOCATABLE, INTENT(OUT) :: sp(:)
+    INTEGER :: ispecies, i, ix, iy
 
     cfg%ndims = c_ndims
     cfg%n = (/ nx, ny, 1 /)
@@ -345,21 +390,39 @@ CONTAINS
       sp(ispecies)%capacity = species_list(ispecies)%attached_list%count * 3 / 2 + 65536
     END DO
 
-    CALL b200_check(epb_create(cfg, sp, b200))
+  END SUBROUTINE b200_fill_config
+
+
+
+  ! housekeeping/window.F90, one pass of shift_window's loop (:69-92).  insert_particles keeps building its
+  ! append_list (it consumes the deck expressions and the random stream) but no longer appends it on the host; the
+  ! grid update (:73-86, setup_grid_x) stays as it is; then this routine replaces remove_particles and shift_fields
+  ! (:88-91) and the setup_bc_lists / particle_bcs of moving_window (:384-385), and the new plasma follows with
+  ! b200_append.  species%count of the host lists is stale while the device owns the particles: size the capacities
+  ! from update_particle_count's numbers in a long run.
+  SUBROUTINE b200_shift_window
+
+    TYPE(epb_config) :: cfg
+    TYPE(epb_species), ALLOCATABLE :: sp(:)
+    TYPE(epb_decomp) :: d
+    TYPE(C_PTR) :: new_handle
+    INTEGER(C_INT32_T), TARGET :: cxmin(nprocx), cxmax(nprocx), cymin(nprocy), cymax(nprocy)
+    INTEGER(C_INT32_T), TARGET :: one(1)
+
+    CALL b200_fill_config(cfg, sp)   ! x_grid_min_local, x_min_local, x_min ... of the window that has just moved
+    cxmin = cell_x_min(1:nprocx)
+    cxmax = cell_x_max(1:nprocx)
+    cymin = cell_y_min(1:nprocy)
+    cymax = cell_y_max(1:nprocy)
+    one = 1
+    d%nproc = (/ nprocx, nprocy, 1 /)
+    d%cell_min = (/ C_LOC(cxmin), C_LOC(cymin), C_LOC(one) /)
+    d%cell_max = (/ C_LOC(cxmax), C_LOC(cymax), C_LOC(one) /)
+    CALL b200_check(epb_shift_window(b200, d, cfg, sp, x_grid_min, new_handle))
+    b200 = new_handle   ! the old device state is gone; laser sources are handed over every step anyway
     DEALLOCATE(sp)
 
-    IF (nproc > 1) THEN
-      IF (rank == 0) CALL b200_check(epb_nccl_unique_id(id))
-      CALL MPI_BCAST(id, 128, MPI_CHARACTER, 0, comm, ierr)
-      CALL b200_check(epb_set_comm(b200, id))
-    END IF
-
-    CALL b200_upload
-    ! setup_bc_lists + particle_bcs + efield_bcs + bfield_final_bcs(dt/2), epoch2d.F90:144-162
-    CALL b200_push_laser_sources
-    CALL b200_check(epb_init_boundaries(b200))
-
-  END SUBROUTINE b200_attach
+  END SUBROUTINE b200_shift_window
 
 
 
