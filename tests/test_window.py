@@ -5,8 +5,6 @@ The reference holds no numbers for a moving-window run (parity unpinned, DESIGN.
 held to what the routines are built for -- the arrays move one cell, the grid moves with them to the bit on the
 host and in the oracle, a decomposed run equals the one-rank run, a pulse followed at c stays put in the window, the
 plasma stays uniform -- and the CUDA path (epb_shift_window) is held to the oracle."""
-import copy
-
 import numpy as np
 import pytest
 
