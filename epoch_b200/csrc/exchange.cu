@@ -12,6 +12,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "epb_internal.h"
@@ -863,12 +864,25 @@ int redistribute_impl(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd
     if (m != 0)
       return epb_fail(oh, EPB_ERR_UNSUPPORTED, "epb_redistribute: non-zero initial fields on a laser / outflow boundary (their snapshots are not re-cut)");
   }
+  // EPB_DEBUG=1 EPB_REDIST_TIMING=1: wall time of the phases on stderr (each one closed by a device synchronize)
+  static const bool timing = epb_env("EPB_REDIST_TIMING") && atoi(epb_env("EPB_REDIST_TIMING"));
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[epb redistribute%s rank %d] %-10s %8.3f ms\n", win ? " (window)" : "", me, what,
+            std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
+  lap("checks");
   epb_handle *nh = nullptr;
   int rc = epb_create(ncfg, nsp, &nh);
   if (rc) return epb_fail(oh, rc, "epb_redistribute: epb_create for the new decomposition failed");
   for (int is = 0; is < (int)oh->sp.size() && !rc; is++)   // columns as deep as the ones they replace
     if (oh->sp[is].slots && nh->sp[is].slots) rc = epb_slots_ensure_rows(nh, is, oh->sp[is].R);
   if (rc) { oh->err = nh->err; epb_destroy(nh); return rc; }
+  lap("create");
   nh->nccl = oh->nccl;   // the communicator moves to the new state (same ranks, same Cartesian topology)
   nh->time_push = oh->time_push;
   ncclComm_t comm = (ncclComm_t)nh->nccl;
@@ -940,6 +954,7 @@ int redistribute_impl(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd
     }
   }
 
+  lap("fields");
   // ---- particles: distribute_particles ------------------------------------------------------------------------
   const int nv = nd + 4;
   const long long CH = 4 << 20;
@@ -1062,11 +1077,13 @@ int redistribute_impl(epb_handle *oh, const epb_decomp *od, const epb_decomp *nd
     }
   }
   oh->nccl = nullptr;   // moved
+  lap("particles");
   {
     int rcx = epb_agree_exchange_caps(nh);
     if (rcx) return rcx;
   }
   epb_destroy(oh);
+  lap("destroy");
   *out = nh;
   return EPB_OK;
 }
