@@ -135,6 +135,79 @@ def test_plasma_stays_uniform_under_the_window():
     assert np.allclose(ins[:, -1], w, rtol=1e-12)
 
 
+class _Stream:
+    """The rank's KISS stream with random_box_muller on top (random_generator.f90:112-173: polar method, the second
+    deviate of a pair is kept for the next call), written independently of the oracle's C++ from the Fortran."""
+    def __init__(self, seed, n=200000):
+        from oracle.oracle import kiss
+        self.u, self.i, self.cached = kiss(seed, n), 0, None
+
+    def random(self):
+        v = self.u[self.i]
+        self.i += 1
+        return float(v)
+
+    def box_muller(self, stdev, mu):
+        if self.cached is not None:
+            r, self.cached = self.cached * stdev + mu, None
+            return r
+        while True:
+            r1, r2 = 2.0 * self.random() - 1.0, 2.0 * self.random() - 1.0
+            w = r1 * r1 + r2 * r2
+            if 2.2250738585072014e-308 < w < 1.0:
+                break
+        w = np.sqrt((-2.0 * np.log(w)) / w)
+        self.cached = r2 * w
+        return r1 * w * stdev + mu
+
+
+def test_insert_particles_against_an_independent_restatement():
+    """epoch2d window.F90:182-320 once more, in Python straight from the Fortran (order of the random draws, the
+    y weights, the weight formula), on the rank's KISS stream: every inserted particle equal to the oracle's bit
+    for bit, for two species (the second one with a fractional particle count per cell)."""
+    dk = window_deck(2, (12, 6), ppc=3, laser=False, temp_k=2.0e7)
+    dk.species.append(D.Species("proton", D.q0, 1836.2 * D.m0, npart_per_cell=2.5, density=3.0e24,
+                                temp=(1.0e6, 2.0e6, 3.0e6), drift=(1.0e-24, 0.0, -2.0e-24),
+                                bc_particle=["open", "open", "periodic", "periodic"]))
+    o = Oracle(dk)           # no auto_load: the stream is untouched (setup.F90:566-571: seed + rank, 1000 draws)
+    o.init()
+    x_grid_max = float(dk.x_global(0, dk.n[0]))
+    dx, dy = dk.dx(0), dk.dx(1)
+    dk.shift_window_geometry()
+    o.shift_window(1)
+    g = _Stream(dk.seed + 0)
+    for isp, s in enumerate(dk.species):
+        npc = int(np.floor(s.npart_per_cell))
+        frac = s.npart_per_cell - npc
+        x0 = x_grid_max + 0.5 * dx
+        want = []
+        for iy in range(1, dk.n[1] + 1):
+            n_frac = 0
+            if frac > 0.0 and g.random() < frac:
+                n_frac = 1
+            wdata = dx * dy / (npc + n_frac)
+            for _ in range(npc + n_frac):
+                cf = 0.5 - g.random()
+                x = x0 + g.random() * dx
+                y = float(dk.x_global(1, iy)) - cf * dy
+                gy = [0.5 * (0.25 + cf * cf + cf), 0.75 - cf * cf, 0.5 * (0.25 + cf * cf - cf)]
+                p = []
+                for i in range(3):
+                    t = d = 0.0
+                    for k in range(3):
+                        t = t + gy[k] * s.temp[i]
+                        d = d + gy[k] * s.drift[i]
+                    p.append((t, d))
+                p = [g.box_muller(np.sqrt(t * D.kb * s.mass), d) for t, d in p]
+                wl = 0.0
+                for k in range(3):
+                    wl = wl + gy[k] * s.density
+                want.append([x, y] + p + [wl * wdata])
+        got = o.window_inserted(0, isp)
+        assert got.shape == (len(want), 6), (isp, got.shape, len(want))
+        assert np.array_equal(got, np.array(want)), isp
+
+
 # ---------------------------------------------------------------------------------------------------------
 # CUDA path against the oracle: epb_shift_window + epb_append_species
 # ---------------------------------------------------------------------------------------------------------
