@@ -243,3 +243,112 @@ def test_collisions_inside_the_pic_loop_gpu():
     t1 = _temps_ev(sim.download_species(0))
     t0 = _temps_ev(p)
     assert (t1[0] - t1[1]) < 0.98 * (t0[0] - t0[1])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# A second restatement of the Nanbu / Perez pair (collisions.F90:984-1101 = :516-633), scalar Python written from
+# the Fortran independently of oracle/collisions_oracle.inc, against the oracle's pair operator bit for bit.
+# The reference holds no numbers for collisions ("parity unpinned"): a slip in the long chain of formulas would
+# have to be made twice to pass.  sin / cos / acos / log / exp / sinh are the same libm on both sides.
+# ---------------------------------------------------------------------------------------------------------
+def _pair_np_python(p1_in, p2_in, w1, w2, ran, m1, m2, q1, q2, s_fac, s_fac_prime, sp_den, inter):
+    c, m0_, eps, c_tiny = CL, M0, 2.220446049250313e-16, 2.2250738585072014e-308
+    dot = lambda a, b: a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+    p1 = [float(v) / c for v in p1_in]
+    p2 = [float(v) / c for v in p2_in]
+    p1_norm = [v / m0_ for v in p1]
+    p2_norm = [v / m0_ for v in p2]
+    if dot(p1_norm, p1_norm) < eps and dot(p2_norm, p2_norm) < eps:
+        return None
+    vc = [a - b for a, b in zip(p1_norm, p2_norm)]
+    if dot(vc, vc) < eps:
+        return None
+    p1_norm = [v / m1 for v in p1]
+    gm1 = math.sqrt(dot(p1_norm, p1_norm) + 1.0) * m1
+    p2_norm = [v / m2 for v in p2]
+    gm2 = math.sqrt(dot(p2_norm, p2_norm) + 1.0) * m2
+    gm = gm1 + gm2
+    v1 = [v / gm1 for v in p1]
+    v2 = [v / gm2 for v in p2]
+    vc = [(a + b) / gm for a, b in zip(p1, p2)]
+    vc_sq = dot(vc, vc)
+    gamma_rel_inv = math.sqrt(1.0 - vc_sq)
+    gc = 1.0 / gamma_rel_inv
+    gc_m1_vc = (gc - 1.0) / vc_sq
+    t = (gc_m1_vc * dot(vc, v1) - gc) * gm1
+    p3 = [a + t * b for a, b in zip(p1, vc)]
+    v_sq = dot(vc, v1)
+    gm3 = (1.0 - v_sq) * gc * gm1
+    v_sq = dot(vc, v2)
+    gm4 = (1.0 - v_sq) * gc * gm2
+    p_mag2 = dot(p3, p3)
+    p_mag = math.sqrt(p_mag2)
+    q12 = q1 * q2
+    fac = q12 * q12 * s_fac / (gm1 * gm2)
+    t1 = gm3 * gm4 / p_mag2 + 1.0
+    s12 = fac * gc * p_mag * c / gm * (t1 * t1)
+    v_rel = gm * p_mag * c / (gm3 * gm4 * gc)
+    s_prime = s_fac_prime * (m1 + m2) * v_rel / sp_den
+    s12 = min(s12, s_prime)
+    ran1 = float(ran[0])
+    ran2 = float(ran[1]) * 2.0 * math.pi
+    branch = 0 if s12 < 0.1 else 1 if s12 < 3.0 else 2 if s12 < 6.0 else 3
+    if s12 < 0.1:
+        cosp = 1.0 + s12 * math.log(max(ran1, 5e-9))
+    elif s12 < 3.0:
+        a_inv = 0.0056958 + (0.9560202 + (-0.508139 + (0.47913906 + (-0.12788975 + 0.02389567
+                 * s12) * s12) * s12) * s12) * s12
+        a = 1.0 / a_inv
+        cosp = a_inv * math.log(math.exp(-a) + 2.0 * ran1 * math.sinh(a))
+    elif s12 < 6.0:
+        a = 3.0 * math.exp(-s12)
+        cosp = math.log(math.exp(-a) + 2.0 * ran1 * math.sinh(a)) / a
+    else:
+        cosp = 2.0 * ran1 - 1.0
+    cosp = max(min(cosp, 1.0), -1.0)
+    sinp = math.sin(math.acos(cosp))
+    p_perp2 = p3[0] * p3[0] + p3[1] * p3[1]
+    p_perp = math.sqrt(p_perp2)
+    p_tot = math.sqrt(p_perp2 + p3[2] * p3[2])
+    p_perp_inv = 1.0 / (p_perp + c_tiny)
+    mat = [[p3[0] * p3[2] * p_perp_inv, -p3[1] * p_tot * p_perp_inv, p3[0]],
+           [p3[1] * p3[2] * p_perp_inv, p3[0] * p_tot * p_perp_inv, p3[1]],
+           [-p_perp, 0.0, p3[2]]]
+    sinp_cos = sinp * math.cos(ran2)
+    sinp_sin = sinp * math.sin(ran2)
+    p3 = [mat[i][0] * sinp_cos + mat[i][1] * sinp_sin + mat[i][2] * cosp for i in range(3)]
+    p4 = [-v for v in p3]
+    # inter_collisions_np :1087-1096 rejects by the weight ratio with a third random number; intra_collisions_np
+    # :627-632 always updates both particles
+    ran1 = float(ran[2]) if inter else -1.0
+    out1, out2 = [float(v) for v in p1_in], [float(v) for v in p2_in]
+    if ran1 < w2 / w1:
+        t = gc_m1_vc * dot(vc, p3) + gm3 * gc
+        out1 = [(a + t * b) * c for a, b in zip(p3, vc)]
+    if ran1 < w1 / w2:
+        t = gc_m1_vc * dot(vc, p4) + gm4 * gc
+        out2 = [(a + t * b) * c for a, b in zip(p4, vc)]
+    return out1, out2, branch
+
+
+@pytest.mark.parametrize("inter", [0, 1])
+def test_nanbu_pair_equals_an_independent_restatement_bit_for_bit(inter):
+    O.build()
+    m1, m2 = M0, (1836.2 * M0 if inter else M0)
+    q1, q2 = -Q0, (Q0 if inter else -Q0)
+    n = 3000
+    p1, p2, ran = _pairs(n, m1, m2, 3000.0, 31 + inter)
+    rng = np.random.default_rng(8)
+    w1 = np.where(rng.random(n) < 0.5, 3.0e10, 1.0e10)     # unequal weights: the rejection branches
+    w2 = np.full(n, 2.0e10)
+    branches = [0, 0, 0, 0]
+    for loglam, dt in ((10.0, 1e-16), (10.0, 3e-14), (10.0, 4e-13), (10.0, 1e-11)):   # s12 < 0.1, < 3, < 6, >= 6
+        env = _env(m1, m2, q1, q2, 1, inter, loglam=loglam, dt=dt)
+        a, b, done = _run_pairs(O.lib().orc_collide_pairs_test, p1, p2, w1, w2, ran, env)
+        for i in range(n):
+            r = _pair_np_python(p1[i], p2[i], w1[i], w2[i], ran[i], m1, m2, q1, q2, env[9], env[10], env[11], inter)
+            assert (r is not None) == bool(done[i])
+            if r is not None:
+                assert np.array_equal(np.array(r[0]), a[i]) and np.array_equal(np.array(r[1]), b[i]), (dt, i)
+                branches[r[2]] += 1
+    assert min(branches) >= 200, branches          # every branch of the inversion was taken many times
