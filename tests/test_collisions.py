@@ -352,3 +352,135 @@ def test_nanbu_pair_equals_an_independent_restatement_bit_for_bit(inter):
                 assert np.array_equal(np.array(r[0]), a[i]) and np.array_equal(np.array(r[1]), b[i]), (dt, i)
                 branches[r[2]] += 1
     assert min(branches) >= 200, branches          # every branch of the inversion was taken many times
+
+
+# The same for the Sentoku-Kemp pair (collisions.F90:751-880 = :296-430) with coll_freq (:1119-1142), new_coords
+# (:1189-1220) and weighted_particles_correction (:1146-1185).
+def _new_coords_python(v):
+    c_tiny = 2.2250738585072014e-308
+    vmag = math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+    vtrans = math.sqrt(v[1] * v[1] + v[2] * v[2])
+    if vtrans > c_tiny:
+        c1 = [x / vmag for x in v]
+        c2 = [0.0 / vtrans, v[2] / vtrans, -v[1] / vtrans]
+        den = vmag * vtrans
+        c3 = [vtrans * vtrans / den, -(v[0] * v[1]) / den, -(v[0] * v[2]) / den]
+        return c1, c2, c3
+    return [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]
+
+
+def _pair_sk_python(p1_in, p2_in, w1, w2, ran, m1, m2, q1, q2, dens, log_lambda, factor, np_, dt_coll):
+    c, eps, c_tiny, huge = CL, 2.220446049250313e-16, 2.2250738585072014e-308, 1.7976931348623157e308
+    cc, mc0, pi, eps0 = CL * CL, 2.73092429345209278e-22, math.pi, D.epsilon0
+    dot = lambda a, b: a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+    rnd = iter(float(r) for r in ran)
+    p1, p2 = [float(v) for v in p1_in], [float(v) for v in p2_in]
+    wr = w1 / w2
+    p1_norm, p2_norm = [v / mc0 for v in p1], [v / mc0 for v in p2]
+    if dot(p1_norm, p1_norm) < eps and dot(p2_norm, p2_norm) < eps:
+        return None
+    vc = [a - b for a, b in zip(p1_norm, p2_norm)]
+    if dot(vc, vc) < eps:
+        return None
+    e1 = c * math.sqrt(dot(p1, p1) + (m1 * c) * (m1 * c))
+    e2 = c * math.sqrt(dot(p2, p2) + (m2 * c) * (m2 * c))
+    vc = [(a + b) * cc / (e1 + e2) for a, b in zip(p1, p2)]
+    vc_sq = dot(vc, vc)
+    vc_sq_cc = vc_sq / cc
+    gamma_rel2 = 1.0 / (1.0 - vc_sq_cc)
+    gamma_rel = math.sqrt(gamma_rel2)
+    gamma_rel_m1 = gamma_rel2 * vc_sq_cc / (gamma_rel + 1.0)
+    p1_vc, p2_vc = dot(p1, vc), dot(p2, vc)
+    tvar = p1_vc * gamma_rel_m1 / (vc_sq + c_tiny)
+    t = tvar - gamma_rel * e1 / cc
+    p3 = [a + b * t for a, b in zip(p1, vc)]
+    tvar = p2_vc * gamma_rel_m1 / (vc_sq + c_tiny)
+    t = tvar - gamma_rel * e2 / cc
+    p4 = [a + b * t for a, b in zip(p2, vc)]
+    p3_mag = math.sqrt(dot(p3, p3))
+    e3 = gamma_rel * (e1 - p1_vc)
+    e4 = gamma_rel * (e2 - p2_vc)
+    v3 = [a * cc / e3 for a in p3]
+    v4 = [a * cc / e4 for a in p4]
+    tvar = 1.0 - (dot(v3, v4) / cc)
+    vr = [(a - b) / tvar for a, b in zip(v3, v4)]
+    vrabs = math.sqrt(dot(vr, vr))
+    # coll_freq
+    mu = (m1 * m2) / (m1 + m2)
+    nu = 0.0
+    if vrabs > 0.0:
+        q12 = q1 * q2
+        numerator = q12 * q12 * dens * log_lambda
+        denominator = 4.0 * pi * (eps0 * eps0) * (mu * mu) * (vrabs * vrabs * vrabs)
+        if not (denominator <= 0.0 or math.frexp(numerator)[1] - math.frexp(denominator)[1] >= 1024):
+            nu = numerator / denominator
+    nu = min(nu * factor * np_ * dt_coll, 0.02)
+    c1, c2, c3 = _new_coords_python(vr)
+    ran1 = (1.0 - 1.0e-10) * next(rnd) + 0.5e-10
+    ran2 = 2.0 * pi * next(rnd)
+    delta = math.sqrt(-2.0 * nu * math.log(ran1)) * math.sin(ran2)
+    ran2 = 2.0 * pi * next(rnd)
+    sin_theta = 2.0 * delta / (1.0 + delta * delta)
+    cos_theta = (1.0 - delta * delta) / (1.0 + delta * delta)
+    vcr = v3 if m1 > m2 else v4
+    vcr2 = dot(vcr, vcr)
+    gamma_rel_r = 1.0 / math.sqrt(1.0 - (vcr2 / cc))
+    denominator = gamma_rel_r * (cos_theta - math.sqrt(vcr2) / max(vrabs, c_tiny))
+    if abs(denominator) > math.sqrt(c_tiny):
+        tan_theta_cm = sin_theta / denominator
+        tan_theta_cm2 = tan_theta_cm * tan_theta_cm
+    else:
+        tan_theta_cm = tan_theta_cm2 = huge
+    sin_theta = tan_theta_cm / math.sqrt(1.0 + tan_theta_cm2)
+    cos_theta = 1.0 / math.sqrt(1.0 + tan_theta_cm2)
+    cr, sr = math.cos(ran2), math.sin(ran2)
+    p3 = [p3_mag * (a * cos_theta + b * sin_theta * cr + d * sin_theta * sr) for a, b, d in zip(c1, c2, c3)]
+    p4 = [-v for v in p3]
+    tvar = dot(p3, vc) * gamma_rel_m1 / vc_sq
+    t = tvar + gamma_rel * e3 / cc
+    p5 = [a + b * t for a, b in zip(p3, vc)]
+    tvar = dot(p4, vc) * gamma_rel_m1 / vc_sq
+    t = tvar + gamma_rel * e4 / cc
+    p6 = [a + b * t for a, b in zip(p4, vc)]
+    e5 = c * math.sqrt(dot(p5, p5) + (m1 * c) * (m1 * c))
+    e6 = c * math.sqrt(dot(p6, p6) + (m2 * c) * (m2 * c))
+
+    def correction(wtr, p, p_scat, en, en_scat, mass):
+        en_after = (1.0 - wtr) * en + wtr * en_scat
+        p_after = [(1.0 - wtr) * a + wtr * b for a, b in zip(p, p_scat)]
+        p_mag = math.sqrt(dot(p_after, p_after))
+        gamma_en = en_after / (mass * cc)
+        pm = p_mag / mass / c
+        gamma_p = math.sqrt(1.0 + pm * pm)
+        if gamma_p < gamma_en:
+            delta_p = mass * c * math.sqrt(gamma_en * gamma_en - gamma_p * gamma_p)
+            _, d2, d3 = _new_coords_python(p_after)
+            phi = 2.0 * pi * next(rnd)
+            cp, sp = math.cos(phi), math.sin(phi)
+            return [a + delta_p * (b * cp + d * sp) for a, b, d in zip(p_after, d2, d3)]
+        return p_scat
+
+    if wr > 1.0 + 2.0 * eps:
+        p5 = correction(w2 / w1, p1, p5, e1, e5, m1)
+    elif wr < 1.0 - 2.0 * eps:
+        p6 = correction(w1 / w2, p2, p6, e2, e6, m2)
+    return p5, p6
+
+
+@pytest.mark.parametrize("inter", [0, 1])
+def test_sentoku_kemp_pair_equals_an_independent_restatement_bit_for_bit(inter):
+    O.build()
+    m1, m2 = M0, (1836.2 * M0 if inter else M0)
+    q1, q2 = -Q0, (Q0 if inter else -Q0)
+    n = 3000
+    p1, p2, ran = _pairs(n, m1, m2, 3000.0, 41 + inter)
+    rng = np.random.default_rng(9)
+    w1 = np.where(rng.random(n) < 0.34, 3.0e10, np.where(rng.random(n) < 0.5, 2.0e10, 1.0e10))   # wr > 1, = 1, < 1
+    w2 = np.full(n, 2.0e10)
+    env = _env(m1, m2, q1, q2, 0, inter)
+    a, b, done = _run_pairs(O.lib().orc_collide_pairs_test, p1, p2, w1, w2, ran, env)
+    assert done.all()
+    for i in range(n):
+        r = _pair_sk_python(p1[i], p2[i], w1[i], w2[i], ran[i], m1, m2, q1, q2, env[4], env[5], env[6], env[7], env[8])
+        assert np.array_equal(np.array(r[0]), a[i]) and np.array_equal(np.array(r[1]), b[i]), i
+    assert len(set(w1)) == 3
