@@ -141,3 +141,66 @@ def test_thermal_wall_distribution_gpu(ndims, n):
         assert abs(np.mean(h[:, ndims] ** 2) / (2 * mk * T_WALL) - 1.0) < 0.05
         assert abs(np.mean(h[:, ndims + 1] ** 2) / (mk * 2 * T_WALL) - 1.0) < 0.05
         assert abs(np.mean(h[:, ndims + 2] ** 2) / (mk * 3 * T_WALL) - 1.0) < 0.05
+
+
+def test_thermal_reemission_equals_an_independent_restatement():
+    """The thermal branch of particle_bcs (boundary.F90:1104-1148, :1190-1234) with flux_momentum_from_temperature and
+    momentum_from_temperature (particle_temperature.F90:388-460) once more, in Python from the Fortran on the rank's
+    KISS stream: every re-emitted particle equal to the oracle's bit for bit (order of the draws: two deviates for the
+    Rayleigh normal component, then the two tangential ones; the wall temperature interpolated with the triangle
+    weights in y; the position mirrored about the OUTER edge)."""
+    from tests.test_window import _Stream
+    dk = _deck(2, (16, 12), ppc=1)
+    dk.species[0].bc_particle = ["thermal", "thermal", "periodic", "periodic"]
+    dk.bc_field = ["reflect", "reflect", "periodic", "periodic"]
+    o = O.Oracle(dk)          # no auto_load: the stream is untouched (seed + rank, 1000 draws)
+    for side, t in _walls(dk)[:2]:
+        o.set_boundary_temperature(0, 0, side, t)
+    rng = np.random.default_rng(12)
+    n = 600
+    dx, dy = dk.dx(0), dk.dx(1)
+    p = np.zeros((n, 6))
+    p[:, 1] = dk.xmin[1] + rng.random(n) * (dk.xmax[1] - dk.xmin[1])
+    p[:, 2:5] = rng.standard_normal((n, 3)) * 1.0e-23
+    p[:, 5] = 1.0
+    # a third beyond x_max_outer, a third beyond x_min_outer, a third between the wall and its outer edge, shuffled
+    kind = rng.integers(0, 3, n)
+    p[:, 0] = np.where(kind == 0, dk.xmax[0] + (2.0 + rng.random(n) * 0.3) * dx,
+                       np.where(kind == 1, dk.xmin[0] - (2.0 + rng.random(n) * 0.3) * dx,
+                                dk.xmax[0] + rng.random(n) * 1.9 * dx))
+    o.set_particles(0, 0, p)
+    O.lib().orc_setup_bc_lists(o._h)
+    o.particle_bcs()
+    got = o.get_particles(0, 0)
+    mo, xo = o.outer()
+    info = o.rank_info(0)
+    g = _Stream(dk.seed + 0)
+    m = dk.species[0].mass
+    want = p.copy()
+    for P in want:
+        part_pos = float(P[0])
+        for sgn, beyond, outer, tw in ((-1, part_pos < mo[0], mo[0], _walls(dk)[0][1]),
+                                       (+1, part_pos >= xo[0], xo[0], _walls(dk)[1][1])):
+            if not beyond:
+                continue
+            cell_y_r = (float(P[1]) - info["grid_min_local"][1]) / dy
+            cell_y = math.floor(cell_y_r + 0.5)
+            cf = float(cell_y) - cell_y_r
+            cf2 = cf * cf
+            gy = (0.5 * (0.25 + cf2 + cf), 0.75 - cf2, 0.5 * (0.25 + cf2 - cf))
+            temp = []
+            for i in range(3):
+                t = 0.0
+                for k in range(3):
+                    t = t + gy[k] * tw[i]
+                temp.append(t)
+            direction = -float(sgn)
+            mom1 = g.box_muller(math.sqrt(temp[0] * D.kb * m), 0.0)
+            mom2 = g.box_muller(math.sqrt(temp[0] * D.kb * m), 0.0)
+            P[2] = direction * math.sqrt(mom1 * mom1 + mom2 * mom2)
+            P[3] = g.box_muller(math.sqrt(temp[1] * D.kb * m), 0.0)
+            P[4] = g.box_muller(math.sqrt(temp[2] * D.kb * m), 0.0)
+            P[0] = 2.0 * outer - part_pos
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert (kind == 0).sum() > 100 and (kind == 1).sum() > 100
