@@ -92,6 +92,8 @@ def lib():
         L.orc_collide.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.orc_collide.restype = None
         L.orc_collide_pairs_test.argtypes = [C.c_int] + [C.c_void_p] * 7
+        L.orc_coulomb_log.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_coulomb_log.restype = None
         L.orc_collide_pairs_test.restype = None
         _LIB = L
     return _LIB

@@ -484,3 +484,41 @@ def test_sentoku_kemp_pair_equals_an_independent_restatement_bit_for_bit(inter):
         r = _pair_sk_python(p1[i], p2[i], w1[i], w2[i], ran[i], m1, m2, q1, q2, env[4], env[5], env[6], env[7], env[8])
         assert np.array_equal(np.array(r[0]), a[i]) and np.array_equal(np.array(r[1]), b[i]), i
     assert len(set(w1)) == 3
+
+
+def test_coulomb_log_equals_an_independent_restatement():
+    """calc_coulomb_log (collisions.F90:1288-1316) in Python from the Fortran against the oracle's, bit for bit, over
+    the floors (100 eV, 100 q0 J), the density cut-off, the classical and the quantum branch of bmin, and the floor
+    of 1 on the result."""
+    O.build()
+    rng = np.random.default_rng(6)
+    n = 20000
+    a = np.empty((n, 7))
+    a[:, 0] = 10.0 ** rng.uniform(-19, -12, n)          # ekbar1 [J]: below and above 100 eV
+    a[:, 1] = 10.0 ** rng.uniform(0, 6, n)              # temp2 [eV]
+    a[:, 2] = 10.0 ** rng.uniform(-1, 32, n)            # densities, some below the cut-off of 1 m^-3
+    a[:, 3] = 10.0 ** rng.uniform(-1, 32, n)
+    a[:, 4] = -Q0
+    a[:, 5] = np.where(rng.random(n) < 0.5, Q0, -Q0) * rng.integers(1, 20, n)
+    a[:, 6] = np.where(rng.random(n) < 0.5, M0, 1836.2 * M0)
+    out = np.empty(n)
+    O.lib().orc_coulomb_log(n, np.ascontiguousarray(a).ctypes.data, out.ctypes.data)
+    h_bar, cc = 1.054571725336289397963133257349698e-34, CL * CL
+    kinds = set()
+    for i in range(n):
+        ekbar1, temp2, dens1, dens2, q1, q2, m1 = (float(v) for v in a[i])
+        local_ekbar1 = max(ekbar1, 100.0 * Q0)
+        local_temp2 = max(temp2, 100.0)
+        if dens1 <= 1.0 or dens2 <= 1.0:
+            want, kind = 1.0, "thin"
+        else:
+            bmax = math.sqrt(D.epsilon0 * Q0 * local_temp2 / (abs(q2) * Q0 * dens2))
+            b0 = abs(q1 * q2) / (8.0 * math.pi * D.epsilon0 * local_ekbar1)
+            gamm = (local_ekbar1 / (m1 * cc)) + 1.0
+            dB = 2.0 * math.pi * h_bar / (math.sqrt(gamm * gamm - 1.0) * m1 * CL)
+            bmin = max(b0, dB)
+            want = max(1.0, math.log(bmax / bmin))
+            kind = ("floor" if want == 1.0 else "classical" if b0 > dB else "quantum")
+        kinds.add(kind)
+        assert out[i] == want, (i, a[i], out[i], want)
+    assert kinds == {"thin", "floor", "classical", "quantum"}
