@@ -12,6 +12,7 @@ import pytest
 
 from epoch_b200 import deck as D
 from oracle import oracle as O
+from tests.gpu_util import sorted_rows
 
 M0, Q0, CL = D.m0, D.q0, D.c
 
@@ -522,3 +523,103 @@ def test_coulomb_log_equals_an_independent_restatement():
         kinds.add(kind)
         assert out[i] == want, (i, a[i], out[i], want)
     assert kinds == {"thin", "floor", "classical", "quantum"}
+
+
+def test_collision_step_equals_an_independent_restatement():
+    """A whole collision step of one species on one rank, fixed Coulomb logarithm, once more in Python from the
+    Fortran: reorder_particles_to_grid (split_particle.F90:29-77), calc_coll_number_density (:1320-1363), the
+    Durstenfeld shuffle of every cell list on the rank's KISS stream (:1224-1284, cells in iy, ix order), then
+    intra_collisions_np per cell (:446-646): the pair count with the odd particle wrapping round to the head of the
+    list, the weight-sum factor, the per-cell constants, the pairs in list order drawing two random numbers each (none
+    for a pair that is skipped).  The oracle's particles after collide() must be the same set, bit for bit."""
+    from tests.test_window import _Stream
+    O.build()
+    n = (5, 4)
+    dx = 1.0e-8
+    ppc_mean = 7
+    sp = [D.Species("electron", -Q0, M0, npart_per_cell=ppc_mean, density=1.0e28, temp=(0.0, 0.0, 0.0))]
+    dk = D.Deck(2, list(n), [0.0, 0.0], [dx * n[0], dx * n[1]], ["periodic"] * 4, species=sp)
+    o = O.Oracle(dk)                    # no auto_load: the KISS stream is untouched
+    o.init()
+    rng = np.random.default_rng(21)
+    npart = ppc_mean * n[0] * n[1]
+    p = np.zeros((npart, 6))
+    p[:, 0] = rng.random(npart) * dx * n[0]          # uneven counts per cell, some of them odd
+    p[:, 1] = rng.random(npart) * dx * n[1]
+    p[:, 2:5] = rng.standard_normal((npart, 3)) * math.sqrt(M0 * 300.0 * Q0) * np.array([1.0, 0.3, 0.3])
+    p[:, 5] = 1.0e28 * dx * dx / ppc_mean * rng.choice([1.0, 2.0], npart)
+    o.set_particles(0, 0, p)
+    log_lambda, user_factor = 10.0, 1.0
+    o.collide([[user_factor]], coulomb_log=log_lambda, use_nanbu=True)
+    got = o.get_particles(0, 0)
+
+    info = o.rank_info(0)
+    gmin = info["grid_min_local"]
+    dt_coll = dk.dt() * 1.0
+    g = _Stream(dk.seed + 0)
+    cells = {}
+    for P in p.copy():
+        cx = math.floor((P[0] - gmin[0]) / dx + 1.5)
+        cy = math.floor((P[1] - gmin[1]) / dx + 1.5)
+        cells.setdefault((cx, cy), []).append(P)
+    idx = 1.0 / dx / dx
+    dens = {}
+    for k, v in cells.items():      # summed in list order BEFORE the shuffle, then scaled (no sum(): it compensates)
+        d = 0.0
+        for P in v:
+            d = d + float(P[5])
+        dens[k] = d * idx
+    order = [(ix, iy) for iy in range(1, n[1] + 1) for ix in range(1, n[0] + 1)]
+    for k in order:                                   # shuffle_particle_list_random
+        lst = cells.get(k, [])
+        if len(lst) <= 2:
+            continue
+        for i in range(len(lst), 1, -1):
+            sw = math.floor(i * g.random()) + 1
+            lst[i - 1], lst[sw - 1] = lst[sw - 1], lst[i - 1]
+    pi4_eps2_c4 = 4.0 * math.pi * (D.epsilon0 * D.epsilon0) * ((CL * CL) * (CL * CL))
+    pi_fac = (4.0 * math.pi / 3.0) ** (1.0 / 3.0)
+
+    class Draw:                                       # ran1, ran2 of a pair, drawn when the pair first asks
+        def __init__(self):
+            self.v = []
+
+        def __getitem__(self, i):
+            while len(self.v) <= i:
+                self.v.append(g.random())
+            return self.v[i]
+
+    odd = 0
+    for k in order:                                   # intra_collisions_np
+        lst = cells.get(k, [])
+        icount = len(lst)
+        if icount <= 1:
+            continue
+        pcount = icount // 2 + icount % 2
+        odd += icount % 2
+        nxt = lambda i: (i + 1) % icount              # the list is circular while the routine runs
+        factor, cur = 0.0, 0
+        for _ in range(pcount):
+            imp = nxt(cur)
+            factor = factor + min(float(lst[cur][5]), float(lst[imp][5]))
+            cur = nxt(imp)
+        factor = user_factor / factor / 2.0
+        d = dens[k]
+        cell_fac = d * d * dt_coll * factor * dx * dx
+        s_fac = cell_fac * log_lambda / pi4_eps2_c4
+        dens_23 = d ** (2.0 / 3.0)
+        s_fac_prime = cell_fac * pi_fac / dens_23
+        cur = 0
+        for _ in range(pcount):
+            imp = nxt(cur)
+            r = _pair_np_python(lst[cur][2:5], lst[imp][2:5], float(lst[cur][5]), float(lst[imp][5]), Draw(),
+                                M0, M0, -Q0, -Q0, s_fac, s_fac_prime, max(M0, M0), 0)
+            if r is not None:
+                lst[cur][2:5], lst[imp][2:5] = r[0], r[1]
+            cur = nxt(imp)
+    want = np.array([P for k in order for P in cells.get(k, [])])
+    assert odd >= 3
+    assert got.shape == want.shape
+    assert np.array_equal(sorted_rows(got), sorted_rows(want))
+    moved = np.abs(sorted_rows(got)[:, 2:5] - sorted_rows(p)[:, 2:5]).max(axis=1) > 0
+    assert moved.mean() > 0.5                      # and the step did scatter most particles
