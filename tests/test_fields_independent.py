@@ -1,0 +1,164 @@
+"""The field half of the step once more, in numpy straight from the Fortran of epoch2d: update_e_field /
+update_b_field (fields.f90:206-225, :427-439, order 2, Yee), update_eb_fields_half / _final (:533-582), efield_bcs /
+bfield_bcs / bfield_final_bcs (boundary.F90:808-944) with field_clamp_zero (:473-530) and the ghost-cell copy of a
+periodic axis, outflow_bcs_x_min / x_max (laser.f90:310-458) and the start-up sequence of epoch2d.F90:144-162 (dt halved
+for the first bfield_final_bcs).  The reference's golden sums pin these routines to 1e-5 only (np.isclose in its
+tests); against this restatement the oracle is equal bit for bit, ghost cells included, on the reference's own 2D
+laser deck shape (laser on x_min, outflow on x_max, periodic y)."""
+import numpy as np
+
+from epoch_b200 import deck as D
+from oracle.oracle import Oracle
+from tests import decks
+
+NG = 5
+STAG = {"ex": (1, 0), "ey": (0, 1), "ez": (0, 0), "bx": (0, 1), "by": (1, 0), "bz": (1, 1)}   # staggered in x, y
+
+
+class NumpyFields:
+    """backend of deck.run for a vacuum run on one rank"""
+
+    def __init__(self, dk):
+        self.dk = dk
+        self.nx, self.ny = dk.n
+        shape = (self.ny + 2 * NG, self.nx + 2 * NG)
+        self.f = {k: np.zeros(shape) for k in ("ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz")}
+        self.src = {}
+        self.dt = dk.dt()
+
+    def S(self, name, i0, i1, j0, j1):
+        """Fortran section name(i0:i1, j0:j1)"""
+        return self.f[name][j0 + NG - 1:j1 + NG, i0 + NG - 1:i1 + NG]
+
+    def set_laser_source(self, lr, side, s1, s2):
+        self.src[side] = (np.asarray(s1, dtype=np.float64).copy(), np.asarray(s2, dtype=np.float64).copy())
+
+    # -- ghost cells ------------------------------------------------------------------------
+    def field_bc(self, name):
+        a, ny = self.f[name], self.ny          # x is not periodic: nothing there; y: copy from the other end
+        a[ny + NG:ny + 2 * NG, :] = a[NG:2 * NG, :]
+        a[0:NG, :] = a[ny:ny + NG, :]
+
+    def clamp_zero_x(self, name, side):
+        a, nn = self.f[name], self.nx
+        F = lambda i: a[:, i + NG - 1]
+        if side == 0:
+            if STAG[name][0]:
+                for i in range(1, NG):
+                    a[:, i - NG + NG - 1] = -F(NG - i)
+                a[:, 0 + NG - 1] = 0.0
+            else:
+                for i in range(1, NG + 1):
+                    a[:, i - NG + NG - 1] = -F(NG + 1 - i)
+        else:
+            if STAG[name][0]:
+                a[:, nn + NG - 1] = 0.0
+                for i in range(1, NG):
+                    a[:, nn + i + NG - 1] = -F(nn - i)
+            else:
+                for i in range(1, NG + 1):
+                    a[:, nn + i + NG - 1] = -F(nn + 1 - i)
+
+    def efield_bcs(self):
+        for k in ("ex", "ey", "ez"):
+            self.field_bc(k)
+        for side in (0, 1):                     # simple_laser and simple_outflow both clamp; y is periodic
+            for k in ("ex", "ey", "ez"):
+                self.clamp_zero_x(k, side)
+
+    def bfield_bcs(self, mpi_only):
+        for k in ("bx", "by", "bz"):
+            self.field_bc(k)
+        if mpi_only:
+            return
+        for side in (0, 1):
+            for k in ("bx", "by", "bz"):
+                self.clamp_zero_x(k, side)
+
+    # -- updates ----------------------------------------------------------------------------
+    def coeffs(self):
+        hdt = 0.5 * self.dt
+        hdtx, hdty = hdt / self.dk.dx(0), hdt / self.dk.dx(1)
+        return hdtx, hdty, hdtx * (D.c * D.c), hdty * (D.c * D.c), hdt / D.epsilon0
+
+    def update_e_field(self):
+        nx, ny, S = self.nx, self.ny, self.S
+        _, _, cnx, cny, fac = self.coeffs()
+        ex = S("ex", 0, nx, 0, ny) + cny * (S("bz", 0, nx, 0, ny) - S("bz", 0, nx, -1, ny - 1)) - fac * S("jx", 0, nx, 0, ny)
+        ey = S("ey", 0, nx, 0, ny) - cnx * (S("bz", 0, nx, 0, ny) - S("bz", -1, nx - 1, 0, ny)) - fac * S("jy", 0, nx, 0, ny)
+        ez = S("ez", 0, nx, 0, ny) + cnx * (S("by", 0, nx, 0, ny) - S("by", -1, nx - 1, 0, ny)) \
+            - cny * (S("bx", 0, nx, 0, ny) - S("bx", 0, nx, -1, ny - 1)) - fac * S("jz", 0, nx, 0, ny)
+        S("ex", 0, nx, 0, ny)[...], S("ey", 0, nx, 0, ny)[...], S("ez", 0, nx, 0, ny)[...] = ex, ey, ez
+
+    def update_b_field(self):
+        nx, ny, S = self.nx, self.ny, self.S
+        hdtx, hdty, _, _, _ = self.coeffs()
+        bx = S("bx", 0, nx, 0, ny) - hdty * (S("ez", 0, nx, 1, ny + 1) - S("ez", 0, nx, 0, ny))
+        by = S("by", 0, nx, 0, ny) + hdtx * (S("ez", 1, nx + 1, 0, ny) - S("ez", 0, nx, 0, ny))
+        bz = S("bz", 0, nx, 0, ny) - hdtx * (S("ey", 1, nx + 1, 0, ny) - S("ey", 0, nx, 0, ny)) \
+            + hdty * (S("ex", 0, nx, 1, ny + 1) - S("ex", 0, nx, 0, ny))
+        S("bx", 0, nx, 0, ny)[...], S("by", 0, nx, 0, ny)[...], S("bz", 0, nx, 0, ny)[...] = bx, by, bz
+
+    def outflow_bcs(self, dt):
+        nx, ny, S, c = self.nx, self.ny, self.S, D.c
+        dtc2 = dt * c * c
+        lx, ly = dtc2 / self.dk.dx(0), dtc2 / self.dk.dx(1)
+        sum_, diff, dt_eps = 1.0 / (lx + c), lx - c, dt / D.epsilon0
+        line = lambda name, i: S(name, i, i, 0, ny)[:, 0]
+        zero = np.zeros(ny + 1)                 # the boundary snapshots of a run that starts from zero fields
+        # x_min, laserpos = 1
+        s1, s2 = self.src.get(0, (zero, zero))
+        S("bx", 0, 0, 0, ny)[:, 0] = zero
+        bz0 = sum_ * (4.0 * s1 + 2.0 * (zero + c * zero) - 2.0 * line("ey", 1) + dt_eps * line("jy", 1) + diff * line("bz", 1))
+        by0 = sum_ * (-4.0 * s2 - 2.0 * (zero - c * zero) + 2.0 * line("ez", 1)
+                      - ly * (line("bx", 1) - S("bx", 1, 1, -1, ny - 1)[:, 0]) - dt_eps * line("jz", 1) + diff * line("by", 1))
+        S("bz", 0, 0, 0, ny)[:, 0], S("by", 0, 0, 0, ny)[:, 0] = bz0, by0
+        # x_max, laserpos = nx
+        s1, s2 = self.src.get(1, (zero, zero))
+        S("bx", nx + 1, nx + 1, 0, ny)[:, 0] = zero
+        bzn = sum_ * (-4.0 * s1 - 2.0 * (zero - c * zero) + 2.0 * line("ey", nx) - dt_eps * line("jy", nx) + diff * line("bz", nx - 1))
+        byn = sum_ * (4.0 * s2 + 2.0 * (zero + c * zero) - 2.0 * line("ez", nx)
+                      + ly * (line("bx", nx) - S("bx", nx, nx, -1, ny - 1)[:, 0]) + dt_eps * line("jz", nx) + diff * line("by", nx - 1))
+        S("bz", nx, nx, 0, ny)[:, 0], S("by", nx, nx, 0, ny)[:, 0] = bzn, byn
+
+    def bfield_final_bcs(self, dt):
+        self.bfield_bcs(False)
+        self.outflow_bcs(dt)
+        self.bfield_bcs(True)
+
+    # -- deck.run ---------------------------------------------------------------------------
+    def init(self):
+        self.efield_bcs()
+        self.bfield_final_bcs(self.dt / 2.0)
+
+    def fields_half(self):
+        self.update_e_field()
+        self.efield_bcs()
+        self.update_b_field()
+        self.bfield_bcs(True)
+
+    def push(self):
+        pass
+
+    def current_finish(self):
+        pass
+
+    def fields_final(self):
+        self.update_b_field()
+        self.bfield_final_bcs(self.dt)
+        self.update_e_field()
+        self.efield_bcs()
+
+
+def test_field_step_equals_an_independent_restatement():
+    res = []
+    for make in (Oracle, NumpyFields):
+        dk = decks.laser2d(n=48)
+        dk.lasers[0].pol_angle = 0.4            # both source terms
+        b = make(dk)
+        D.run(dk, b, [0], None, max_steps=60)
+        res.append(b)
+    o, m = res
+    assert max(np.abs(o.field(0, k)).max() for k in ("ey", "ez", "by", "bz")) > 0
+    for k in ("ex", "ey", "ez", "bx", "by", "bz"):
+        assert np.array_equal(o.field(0, k)[0], m.f[k]), k
