@@ -101,7 +101,7 @@ class NumpyFields:
 
     def outflow_bcs(self, dt):
         nx, ny, S, c = self.nx, self.ny, self.S, D.c
-        dtc2 = dt * c * c
+        dtc2 = dt * (c * c)
         lx, ly = dtc2 / self.dk.dx(0), dtc2 / self.dk.dx(1)
         sum_, diff, dt_eps = 1.0 / (lx + c), lx - c, dt / D.epsilon0
         line = lambda name, i: S(name, i, i, 0, ny)[:, 0]
