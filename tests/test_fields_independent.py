@@ -162,3 +162,115 @@ def test_field_step_equals_an_independent_restatement():
     assert max(np.abs(o.field(0, k)).max() for k in ("ey", "ez", "by", "bz")) > 0
     for k in ("ex", "ey", "ez", "bx", "by", "bz"):
         assert np.array_equal(o.field(0, k)[0], m.f[k]), k
+
+
+class NumpyFields1D:
+    """the same for epoch1d: fields.f90:150-166 and the B update of :228-237 without the kappas, laser.f90:260-392"""
+
+    def __init__(self, dk):
+        self.dk, self.nx, self.dt = dk, dk.n[0], dk.dt()
+        self.f = {k: np.zeros(self.nx + 2 * NG) for k in ("ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz")}
+        self.src = {}
+
+    def S(self, name, i0, i1):
+        return self.f[name][i0 + NG - 1:i1 + NG]
+
+    def set_laser_source(self, lr, side, s1, s2):
+        self.src[side] = (float(np.asarray(s1).ravel()[0]), float(np.asarray(s2).ravel()[0]))
+
+    def clamp_zero(self, name, side):
+        a, nn = self.f[name], self.nx
+        F = lambda i: i + NG - 1
+        if side == 0:
+            if STAG[name][0]:
+                for i in range(1, NG):
+                    a[F(i - NG)] = -a[F(NG - i)]
+                a[F(0)] = 0.0
+            else:
+                for i in range(1, NG + 1):
+                    a[F(i - NG)] = -a[F(NG + 1 - i)]
+        else:
+            if STAG[name][0]:
+                a[F(nn)] = 0.0
+                for i in range(1, NG):
+                    a[F(nn + i)] = -a[F(nn - i)]
+            else:
+                for i in range(1, NG + 1):
+                    a[F(nn + i)] = -a[F(nn + 1 - i)]
+
+    def efield_bcs(self):
+        for side in (0, 1):
+            for k in ("ex", "ey", "ez"):
+                self.clamp_zero(k, side)
+
+    def bfield_bcs(self, mpi_only):
+        if mpi_only:
+            return
+        for side in (0, 1):
+            for k in ("bx", "by", "bz"):
+                self.clamp_zero(k, side)
+
+    def update_e_field(self):
+        nx, S = self.nx, self.S
+        hdt = 0.5 * self.dt
+        cnx, fac = (hdt / self.dk.dx(0)) * (D.c * D.c), hdt / D.epsilon0
+        ex = S("ex", 0, nx) - fac * S("jx", 0, nx)
+        ey = S("ey", 0, nx) - cnx * (S("bz", 0, nx) - S("bz", -1, nx - 1)) - fac * S("jy", 0, nx)
+        ez = S("ez", 0, nx) + cnx * (S("by", 0, nx) - S("by", -1, nx - 1)) - fac * S("jz", 0, nx)
+        S("ex", 0, nx)[...], S("ey", 0, nx)[...], S("ez", 0, nx)[...] = ex, ey, ez
+
+    def update_b_field(self):
+        nx, S = self.nx, self.S
+        hdtx = 0.5 * self.dt / self.dk.dx(0)
+        by = S("by", 0, nx) + hdtx * (S("ez", 1, nx + 1) - S("ez", 0, nx))
+        bz = S("bz", 0, nx) - hdtx * (S("ey", 1, nx + 1) - S("ey", 0, nx))
+        S("by", 0, nx)[...], S("bz", 0, nx)[...] = by, bz
+
+    def bfield_final_bcs(self, dt):
+        self.bfield_bcs(False)
+        c, f, F, nx = D.c, self.f, (lambda i: i + NG - 1), self.nx
+        dtc2 = dt * (c * c)
+        lx = dtc2 / self.dk.dx(0)
+        sum_, diff, dt_eps = 1.0 / (lx + c), lx - c, dt / D.epsilon0
+        s1, s2 = self.src.get(0, (0.0, 0.0))
+        f["bx"][F(0)] = 0.0
+        bz0 = sum_ * (4.0 * s1 + 2.0 * (0.0 + c * 0.0) - 2.0 * f["ey"][F(1)] + dt_eps * f["jy"][F(1)] + diff * f["bz"][F(1)])
+        by0 = sum_ * (-4.0 * s2 - 2.0 * (0.0 - c * 0.0) + 2.0 * f["ez"][F(1)] - dt_eps * f["jz"][F(1)] + diff * f["by"][F(1)])
+        f["bz"][F(0)], f["by"][F(0)] = bz0, by0
+        s1, s2 = self.src.get(1, (0.0, 0.0))
+        f["bx"][F(nx + 1)] = 0.0
+        bzn = sum_ * (-4.0 * s1 - 2.0 * (0.0 - c * 0.0) + 2.0 * f["ey"][F(nx)] - dt_eps * f["jy"][F(nx)] + diff * f["bz"][F(nx - 1)])
+        byn = sum_ * (4.0 * s2 + 2.0 * (0.0 + c * 0.0) - 2.0 * f["ez"][F(nx)] + dt_eps * f["jz"][F(nx)] + diff * f["by"][F(nx - 1)])
+        f["bz"][F(nx)], f["by"][F(nx)] = bzn, byn
+        self.bfield_bcs(True)
+
+    def init(self):
+        self.efield_bcs()
+        self.bfield_final_bcs(self.dt / 2.0)
+
+    def fields_half(self):
+        self.update_e_field(); self.efield_bcs(); self.update_b_field(); self.bfield_bcs(True)
+
+    def push(self):
+        pass
+
+    def current_finish(self):
+        pass
+
+    def fields_final(self):
+        self.update_b_field(); self.bfield_final_bcs(self.dt); self.update_e_field(); self.efield_bcs()
+
+
+def test_field_step_1d_equals_an_independent_restatement():
+    """epoch1d/tests/laser/input.deck itself (the reference's first golden-sum deck), 200 steps"""
+    res = []
+    for make in (Oracle, NumpyFields1D):
+        dk = decks.laser1d()
+        dk.lasers[0].pol_angle = 0.3
+        b = make(dk)
+        D.run(dk, b, [0], None, max_steps=200)
+        res.append(b)
+    o, m = res
+    assert max(np.abs(o.field(0, k)).max() for k in ("ey", "ez", "by", "bz")) > 0
+    for k in ("ex", "ey", "ez", "bx", "by", "bz"):
+        assert np.array_equal(o.field(0, k)[0, 0], m.f[k]), k
