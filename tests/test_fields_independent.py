@@ -274,3 +274,148 @@ def test_field_step_1d_equals_an_independent_restatement():
     assert max(np.abs(o.field(0, k)).max() for k in ("ey", "ez", "by", "bz")) > 0
     for k in ("ex", "ey", "ez", "bx", "by", "bz"):
         assert np.array_equal(o.field(0, k)[0, 0], m.f[k]), k
+
+
+class NumpyFields3D:
+    """the same for epoch3d: fields.f90:312-337, :637-655 (order 2, Yee), laser.f90:350-506, boundary.F90 of that tree"""
+    STAG3 = {"ex": (1, 0, 0), "ey": (0, 1, 0), "ez": (0, 0, 1), "bx": (0, 1, 1), "by": (1, 0, 1), "bz": (1, 1, 0)}
+
+    def __init__(self, dk):
+        self.dk, self.dt = dk, dk.dt()
+        self.nx, self.ny, self.nz = dk.n
+        shape = (self.nz + 2 * NG, self.ny + 2 * NG, self.nx + 2 * NG)
+        self.f = {k: np.zeros(shape) for k in ("ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz")}
+        self.src = {}
+
+    def S(self, name, ix, iy, iz):
+        """Fortran section name(ix0:ix1, iy0:iy1, iz0:iz1)"""
+        sl = lambda r: slice(r[0] + NG - 1, r[1] + NG)
+        return self.f[name][sl(iz), sl(iy), sl(ix)]
+
+    def set_laser_source(self, lr, side, s1, s2):
+        shp = (self.nz + 1, self.ny + 1)     # (0:ny, 0:nz), y fastest
+        self.src[side] = (np.asarray(s1, dtype=np.float64).reshape(shp).copy(), np.asarray(s2, dtype=np.float64).reshape(shp).copy())
+
+    def field_bc(self, name):
+        a, ny, nz = self.f[name], self.ny, self.nz      # x not periodic; y then z: copy from the other end
+        a[:, ny + NG:ny + 2 * NG, :] = a[:, NG:2 * NG, :]
+        a[:, 0:NG, :] = a[:, ny:ny + NG, :]
+        a[nz + NG:nz + 2 * NG, :, :] = a[NG:2 * NG, :, :]
+        a[0:NG, :, :] = a[nz:nz + NG, :, :]
+
+    def clamp_zero_x(self, name, side):
+        a, nn = self.f[name], self.nx
+        F = lambda i: i + NG - 1
+        if side == 0:
+            if self.STAG3[name][0]:
+                for i in range(1, NG):
+                    a[:, :, F(i - NG)] = -a[:, :, F(NG - i)]
+                a[:, :, F(0)] = 0.0
+            else:
+                for i in range(1, NG + 1):
+                    a[:, :, F(i - NG)] = -a[:, :, F(NG + 1 - i)]
+        else:
+            if self.STAG3[name][0]:
+                a[:, :, F(nn)] = 0.0
+                for i in range(1, NG):
+                    a[:, :, F(nn + i)] = -a[:, :, F(nn - i)]
+            else:
+                for i in range(1, NG + 1):
+                    a[:, :, F(nn + i)] = -a[:, :, F(nn + 1 - i)]
+
+    def efield_bcs(self):
+        for k in ("ex", "ey", "ez"):
+            self.field_bc(k)
+        for side in (0, 1):
+            for k in ("ex", "ey", "ez"):
+                self.clamp_zero_x(k, side)
+
+    def bfield_bcs(self, mpi_only):
+        for k in ("bx", "by", "bz"):
+            self.field_bc(k)
+        if mpi_only:
+            return
+        for side in (0, 1):
+            for k in ("bx", "by", "bz"):
+                self.clamp_zero_x(k, side)
+
+    def update_e_field(self):
+        S, X, Y, Z = self.S, (0, self.nx), (0, self.ny), (0, self.nz)
+        m = lambda r: (r[0] - 1, r[1] - 1)
+        hdt = 0.5 * self.dt
+        cc = D.c * D.c
+        cnx, cny, cnz = (hdt / self.dk.dx(0)) * cc, (hdt / self.dk.dx(1)) * cc, (hdt / self.dk.dx(2)) * cc
+        fac = hdt / D.epsilon0
+        ex = S("ex", X, Y, Z) + cny * (S("bz", X, Y, Z) - S("bz", X, m(Y), Z)) - cnz * (S("by", X, Y, Z) - S("by", X, Y, m(Z))) \
+            - fac * S("jx", X, Y, Z)
+        ey = S("ey", X, Y, Z) + cnz * (S("bx", X, Y, Z) - S("bx", X, Y, m(Z))) - cnx * (S("bz", X, Y, Z) - S("bz", m(X), Y, Z)) \
+            - fac * S("jy", X, Y, Z)
+        ez = S("ez", X, Y, Z) + cnx * (S("by", X, Y, Z) - S("by", m(X), Y, Z)) - cny * (S("bx", X, Y, Z) - S("bx", X, m(Y), Z)) \
+            - fac * S("jz", X, Y, Z)
+        S("ex", X, Y, Z)[...], S("ey", X, Y, Z)[...], S("ez", X, Y, Z)[...] = ex, ey, ez
+
+    def update_b_field(self):
+        S, X, Y, Z = self.S, (0, self.nx), (0, self.ny), (0, self.nz)
+        p = lambda r: (r[0] + 1, r[1] + 1)
+        hdt = 0.5 * self.dt
+        hx, hy, hz = hdt / self.dk.dx(0), hdt / self.dk.dx(1), hdt / self.dk.dx(2)
+        bx = S("bx", X, Y, Z) - hy * (S("ez", X, p(Y), Z) - S("ez", X, Y, Z)) + hz * (S("ey", X, Y, p(Z)) - S("ey", X, Y, Z))
+        by = S("by", X, Y, Z) - hz * (S("ex", X, Y, p(Z)) - S("ex", X, Y, Z)) + hx * (S("ez", p(X), Y, Z) - S("ez", X, Y, Z))
+        bz = S("bz", X, Y, Z) - hx * (S("ey", p(X), Y, Z) - S("ey", X, Y, Z)) + hy * (S("ex", X, p(Y), Z) - S("ex", X, Y, Z))
+        S("bx", X, Y, Z)[...], S("by", X, Y, Z)[...], S("bz", X, Y, Z)[...] = bx, by, bz
+
+    def bfield_final_bcs(self, dt):
+        self.bfield_bcs(False)
+        S, c, nx, Y, Z = self.S, D.c, self.nx, (0, self.ny), (0, self.nz)
+        m = lambda r: (r[0] - 1, r[1] - 1)
+        dtc2 = dt * (c * c)
+        lx, ly, lz = dtc2 / self.dk.dx(0), dtc2 / self.dk.dx(1), dtc2 / self.dk.dx(2)
+        sum_, diff, dt_eps = 1.0 / (lx + c), lx - c, dt / D.epsilon0
+        P = lambda name, i, yy=Y, zz=Z: S(name, (i, i), yy, zz)[:, :, 0]
+        zero = np.zeros((self.nz + 1, self.ny + 1))
+        s1, s2 = self.src.get(0, (zero, zero))
+        P("bx", 0)[...] = zero
+        bz0 = sum_ * (4.0 * s1 + 2.0 * (zero + c * zero) - 2.0 * P("ey", 1) - lz * (P("bx", 1) - P("bx", 1, Y, m(Z)))
+                      + dt_eps * P("jy", 1) + diff * P("bz", 1))
+        by0 = sum_ * (-4.0 * s2 - 2.0 * (zero - c * zero) + 2.0 * P("ez", 1) - ly * (P("bx", 1) - P("bx", 1, m(Y), Z))
+                      - dt_eps * P("jz", 1) + diff * P("by", 1))
+        P("bz", 0)[...], P("by", 0)[...] = bz0, by0
+        s1, s2 = self.src.get(1, (zero, zero))
+        P("bx", nx + 1)[...] = zero
+        bzn = sum_ * (-4.0 * s1 - 2.0 * (zero - c * zero) + 2.0 * P("ey", nx) + lz * (P("bx", nx) - P("bx", nx, Y, m(Z)))
+                      - dt_eps * P("jy", nx) + diff * P("bz", nx - 1))
+        byn = sum_ * (4.0 * s2 + 2.0 * (zero + c * zero) - 2.0 * P("ez", nx) + ly * (P("bx", nx) - P("bx", nx, m(Y), Z))
+                      + dt_eps * P("jz", nx) + diff * P("by", nx - 1))
+        P("bz", nx)[...], P("by", nx)[...] = bzn, byn
+        self.bfield_bcs(True)
+
+    def init(self):
+        self.efield_bcs()
+        self.bfield_final_bcs(self.dt / 2.0)
+
+    def fields_half(self):
+        self.update_e_field(); self.efield_bcs(); self.update_b_field(); self.bfield_bcs(True)
+
+    def push(self):
+        pass
+
+    def current_finish(self):
+        pass
+
+    def fields_final(self):
+        self.update_b_field(); self.bfield_final_bcs(self.dt); self.update_e_field(); self.efield_bcs()
+
+
+def test_field_step_3d_equals_an_independent_restatement():
+    """epoch3d/tests/laser/input.deck at 28^3 cells, 40 steps, with a second polarisation component"""
+    res = []
+    for make in (Oracle, NumpyFields3D):
+        dk = decks.laser3d(n=28)
+        dk.lasers[0].pol_angle = 0.5
+        b = make(dk)
+        D.run(dk, b, [0], None, max_steps=40)
+        res.append(b)
+    o, m = res
+    assert min(np.abs(o.field(0, k)).max() for k in ("ex", "ey", "ez", "bx", "by", "bz")) > 0
+    for k in ("ex", "ey", "ez", "bx", "by", "bz"):
+        assert np.array_equal(o.field(0, k), m.f[k]), k
