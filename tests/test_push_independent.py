@@ -17,7 +17,7 @@ from tests import decks
 NG = 5
 
 
-def push_particles_2d(dk, fields, parts, charge, mass, gmin_local):
+def push_particles_2d(dk, fields, parts, charge, mass, gmin_local, hc=None):
     """One call of push_particles for one species on one rank.  fields: dict name -> array [y][x] with ghosts;
     parts: (n, 6) x y px py pz w, updated in place; returns jx, jy, jz."""
     c = D.c
@@ -89,26 +89,8 @@ def push_particles_2d(dk, fields, parts, charge, mass, gmin_local):
         bx_part = gather(bx, gx, cell_x1, hy, cell_y2)
         by_part = gather(by, hx, cell_x2, gy, cell_y1)
         bz_part = gather(bz, hx, cell_x2, hy, cell_y2)
-        uxm = part_ux + cmratio * ex_part
-        uym = part_uy + cmratio * ey_part
-        uzm = part_uz + cmratio * ez_part
-        gamma_rel = math.sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0)
-        root = ccmratio / gamma_rel
-        taux, tauy, tauz = bx_part * root, by_part * root, bz_part * root
-        taux2, tauy2, tauz2 = taux * taux, tauy * tauy, tauz * tauz
-        tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2)
-        uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm
-               + 2.0 * ((taux * tauy + tauz) * uym
-               + (taux * tauz - tauy) * uzm)) * tau
-        uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym
-               + 2.0 * ((tauy * tauz + taux) * uzm
-               + (tauy * taux - tauz) * uxm)) * tau
-        uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm
-               + 2.0 * ((tauz * taux + tauy) * uxm
-               + (tauz * tauy - taux) * uym)) * tau
-        part_ux = uxp + cmratio * ex_part
-        part_uy = uyp + cmratio * ey_part
-        part_uz = uzp + cmratio * ez_part
+        part_ux, part_uy, part_uz = _boris((part_ux, part_uy, part_uz), (ex_part, ey_part, ez_part),
+                                           (bx_part, by_part, bz_part), cmratio, ccmratio, hc)
         part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz
         gamma_rel = math.sqrt(part_u2 + 1.0)
         igamma = 1.0 / gamma_rel
@@ -172,15 +154,27 @@ def _tri(cf, shift=0):
     return w
 
 
-def _boris(part_u, e_part, b_part, cmratio, ccmratio):
-    """particles.F90:400-428, identical text in the three trees"""
+def _boris(part_u, e_part, b_part, cmratio, ccmratio, hc=None):
+    """particles.F90:382-428, identical text in the three trees; hc = (part_q, dt, part_m): the -DHC_PUSH gamma
+    (Higuera-Cary, :386-398)"""
     part_ux, part_uy, part_uz = part_u
     ex_part, ey_part, ez_part = e_part
     bx_part, by_part, bz_part = b_part
     uxm = part_ux + cmratio * ex_part
     uym = part_uy + cmratio * ey_part
     uzm = part_uz + cmratio * ez_part
-    gamma_rel = math.sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0)
+    if hc is None:
+        gamma_rel = math.sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0)
+    else:
+        part_q, dt, part_m = hc
+        gamma_rel = uxm * uxm + uym * uym + uzm * uzm + 1.0
+        alpha = 0.5 * part_q * dt / part_m
+        beta_x, beta_y, beta_z = alpha * bx_part, alpha * by_part, alpha * bz_part
+        beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z
+        sigma = gamma_rel - beta2
+        beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm
+        gamma_rel = sigma + math.sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u))
+        gamma_rel = math.sqrt(0.5 * gamma_rel)
     root = ccmratio / gamma_rel
     taux, tauy, tauz = bx_part * root, by_part * root, bz_part * root
     taux2, tauy2, tauz2 = taux * taux, tauy * tauy, tauz * tauz
@@ -201,7 +195,7 @@ def _tz(a, b):
     return int(a / b)      # Fortran integer division truncates towards zero
 
 
-def push_particles_1d(dk, fields, parts, charge, mass, gmin_local):
+def push_particles_1d(dk, fields, parts, charge, mass, gmin_local, hc=None):
     """epoch1d/src/particles.F90:143-507 (+ include/triangle/*.inc of that tree).  parts: (n, 5) x px py pz w."""
     c = D.c
     dx, dt = dk.dx(0), dk.dt()
@@ -236,7 +230,7 @@ def push_particles_1d(dk, fields, parts, charge, mass, gmin_local):
         cell_x2 = cell_x2 + 1
         e_part = (g3(fields["ex"], hx, cell_x2), g3(fields["ey"], gx, cell_x1), g3(fields["ez"], gx, cell_x1))
         b_part = (g3(fields["bx"], gx, cell_x1), g3(fields["by"], hx, cell_x2), g3(fields["bz"], hx, cell_x2))
-        part_ux, part_uy, part_uz = _boris((part_ux, part_uy, part_uz), e_part, b_part, cmratio, ccmratio)
+        part_ux, part_uy, part_uz = _boris((part_ux, part_uy, part_uz), e_part, b_part, cmratio, ccmratio, hc)
         part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz
         gamma_rel = math.sqrt(part_u2 + 1.0)
         root = c / gamma_rel
@@ -273,7 +267,7 @@ def push_particles_1d(dk, fields, parts, charge, mass, gmin_local):
     return jx, jy, jz
 
 
-def push_particles_3d(dk, fields, parts, charge, mass, gmin_local):
+def push_particles_3d(dk, fields, parts, charge, mass, gmin_local, hc=None):
     """epoch3d/src/particles.F90:150-650 (+ include/triangle/*.inc of that tree).  parts: (n, 7) x y z px py pz w."""
     c = D.c
     dx, dy, dz, dt = dk.dx(0), dk.dx(1), dk.dx(2), dk.dt()
@@ -328,7 +322,7 @@ def push_particles_3d(dk, fields, parts, charge, mass, gmin_local):
                   gather(fields["ez"], gx, x1, gy, y1, hz, z2))
         b_part = (gather(fields["bx"], gx, x1, hy, y2, hz, z2), gather(fields["by"], hx, x2, gy, y1, hz, z2),
                   gather(fields["bz"], hx, x2, hy, y2, gz, z1))
-        part_ux, part_uy, part_uz = _boris(tuple(u), e_part, b_part, cmratio, ccmratio)
+        part_ux, part_uy, part_uz = _boris(tuple(u), e_part, b_part, cmratio, ccmratio, hc)
         part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz
         gamma_rel = math.sqrt(part_u2 + 1.0)
         root = dtco2 / gamma_rel
@@ -390,9 +384,11 @@ def push_particles_3d(dk, fields, parts, charge, mass, gmin_local):
 import pytest
 
 
+@pytest.mark.parametrize("hc_push", [False, True])
 @pytest.mark.parametrize("ndims,n", [(1, (40,)), (2, (14, 11)), (3, (8, 7, 6))])
-def test_oracle_push_equals_an_independent_restatement_bit_for_bit(ndims, n):
+def test_oracle_push_equals_an_independent_restatement_bit_for_bit(ndims, n, hc_push):
     dk = decks.thermal(ndims, n, ppc=6 if ndims < 3 else 3, temp_k=4.0e9)   # hot: many particles change cell in a step
+    dk.hc_push = hc_push
     o = Oracle(dk)
     o.auto_load()
     o.init()
@@ -407,7 +403,7 @@ def test_oracle_push_equals_an_independent_restatement_bit_for_bit(ndims, n):
     info = o.rank_info(0)
     s = dk.species[0]
     push = {1: push_particles_1d, 2: push_particles_2d, 3: push_particles_3d}[ndims]
-    mine = push(dk, fields, p, s.charge, s.mass, info["grid_min_local"])
+    mine = push(dk, fields, p, s.charge, s.mass, info["grid_min_local"], (s.charge, dk.dt(), s.mass) if hc_push else None)
     o.push_only()
     q = o.get_particles(0, 0)
     assert q.shape == p.shape
