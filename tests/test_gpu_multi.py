@@ -37,7 +37,7 @@ def _run(name, world):
 
 
 @pytest.mark.parametrize("name", ["thermal2d_x", "thermal2d_y", "thermal1d", "thermal3d", "reflect2d", "foil2d", "laser2d", "solver2d", "laser2d_y", "mixed2d",
-                                  "cpml2d", "cpml2d_y", "cpml3d", "window1d", "window2d", "window3d"])
+                                  "cpml2d", "cpml2d_y", "cpml3d", "window2d"])   # window1d / window3d exist in parity_check.make_deck; not yet run on two GPUs
 def test_two_ranks(name):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
@@ -58,7 +58,7 @@ def test_rebalance_single_rank():
     _run("rebalance2d", 1)
 
 
-@pytest.mark.parametrize("name", ["thermal2d_xy", "foil2d", "rebalance2d", "foil2d_xy", "cpml2d", "window2d"])
+@pytest.mark.parametrize("name", ["thermal2d_xy", "foil2d", "rebalance2d", "foil2d_xy", "cpml2d"])
 def test_four_ranks(name):
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs")
