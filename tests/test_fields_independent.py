@@ -34,10 +34,45 @@ class NumpyFields:
         self.src[side] = (np.asarray(s1, dtype=np.float64).copy(), np.asarray(s2, dtype=np.float64).copy())
 
     # -- ghost cells ------------------------------------------------------------------------
+    def periodic(self, d):
+        return self.dk.bc_field[2 * d] == "periodic"
+
     def field_bc(self, name):
-        a, ny = self.f[name], self.ny          # x is not periodic: nothing there; y: copy from the other end
-        a[ny + NG:ny + 2 * NG, :] = a[NG:2 * NG, :]
-        a[0:NG, :] = a[ny:ny + NG, :]
+        a, nx, ny = self.f[name], self.nx, self.ny     # a periodic axis copies from its other end, x before y
+        if self.periodic(0):
+            a[:, nx + NG:nx + 2 * NG] = a[:, NG:2 * NG]
+            a[:, 0:NG] = a[:, nx:nx + NG]
+        if self.periodic(1):
+            a[ny + NG:ny + 2 * NG, :] = a[NG:2 * NG, :]
+            a[0:NG, :] = a[ny:ny + NG, :]
+
+    def clamp_zero_y(self, name, side):
+        a, nn = self.f[name], self.ny
+        F = lambda i: i + NG - 1
+        if side == 0:
+            if STAG[name][1]:
+                for i in range(1, NG):
+                    a[F(i - NG), :] = -a[F(NG - i), :]
+                a[F(0), :] = 0.0
+            else:
+                for i in range(1, NG + 1):
+                    a[F(i - NG), :] = -a[F(NG + 1 - i), :]
+        else:
+            if STAG[name][1]:
+                a[F(nn), :] = 0.0
+                for i in range(1, NG):
+                    a[F(nn + i), :] = -a[F(nn - i), :]
+            else:
+                for i in range(1, NG + 1):
+                    a[F(nn + i), :] = -a[F(nn + 1 - i), :]
+
+    def clamp(self, names):
+        # DO i = 1, 2*c_ndims: x_min, x_max, y_min, y_max; simple_laser and simple_outflow both clamp
+        for b in range(4):
+            if self.periodic(b // 2):
+                continue
+            for k in names:
+                (self.clamp_zero_x if b < 2 else self.clamp_zero_y)(k, b % 2)
 
     def clamp_zero_x(self, name, side):
         a, nn = self.f[name], self.nx
@@ -62,18 +97,14 @@ class NumpyFields:
     def efield_bcs(self):
         for k in ("ex", "ey", "ez"):
             self.field_bc(k)
-        for side in (0, 1):                     # simple_laser and simple_outflow both clamp; y is periodic
-            for k in ("ex", "ey", "ez"):
-                self.clamp_zero_x(k, side)
+        self.clamp(("ex", "ey", "ez"))
 
     def bfield_bcs(self, mpi_only):
         for k in ("bx", "by", "bz"):
             self.field_bc(k)
         if mpi_only:
             return
-        for side in (0, 1):
-            for k in ("bx", "by", "bz"):
-                self.clamp_zero_x(k, side)
+        self.clamp(("bx", "by", "bz"))
 
     # -- updates ----------------------------------------------------------------------------
     def coeffs(self):
@@ -140,9 +171,33 @@ class NumpyFields:
                       + ly * (line("bx", nx) - S("bx", nx, nx, -1, ny - 1)[:, 0]) + dt_eps * line("jz", nx) + diff * line("by", nx - 1))
         S("bz", nx, nx, 0, ny)[:, 0], S("by", nx, nx, 0, ny)[:, 0] = bzn, byn
 
+    def outflow_bcs_y(self, dt):
+        """outflow_bcs_y_min / y_max, laser.f90:462-610"""
+        nx, ny, S, c = self.nx, self.ny, self.S, D.c
+        dtc2 = dt * (c * c)
+        lx, ly = dtc2 / self.dk.dx(0), dtc2 / self.dk.dx(1)
+        sum_, diff, dt_eps = 1.0 / (ly + c), ly - c, dt / D.epsilon0
+        row = lambda name, j, i0=0, i1=None: S(name, i0, nx if i1 is None else i1, j, j)[0, :]
+        zero = np.zeros(nx + 1)
+        s1, s2 = self.src.get(2, (zero, zero))
+        S("by", 0, nx, 0, 0)[0, :] = zero
+        bx0 = sum_ * (4.0 * s1 + 2.0 * (zero + c * zero) - 2.0 * row("ez", 1) - lx * (row("by", 1) - row("by", 1, -1, nx - 1))
+                      + dt_eps * row("jz", 1) + diff * row("bx", 1))
+        bz0 = sum_ * (-4.0 * s2 - 2.0 * (zero - c * zero) + 2.0 * row("ex", 1) - dt_eps * row("jx", 1) + diff * row("bz", 1))
+        S("bx", 0, nx, 0, 0)[0, :], S("bz", 0, nx, 0, 0)[0, :] = bx0, bz0
+        s1, s2 = self.src.get(3, (zero, zero))
+        S("by", 0, nx, ny + 1, ny + 1)[0, :] = zero
+        bxn = sum_ * (-4.0 * s1 - 2.0 * (zero - c * zero) + 2.0 * row("ez", ny) + lx * (row("by", ny) - row("by", ny, -1, nx - 1))
+                      - dt_eps * row("jz", ny) + diff * row("bx", ny - 1))
+        bzn = sum_ * (4.0 * s2 + 2.0 * (zero + c * zero) - 2.0 * row("ex", ny) + dt_eps * row("jx", ny) + diff * row("bz", ny - 1))
+        S("bx", 0, nx, ny, ny)[0, :], S("bz", 0, nx, ny, ny)[0, :] = bxn, bzn
+
     def bfield_final_bcs(self, dt):
         self.bfield_bcs(False)
-        self.outflow_bcs(dt)
+        if not self.periodic(0):
+            self.outflow_bcs(dt)
+        if not self.periodic(1):
+            self.outflow_bcs_y(dt)
         self.bfield_bcs(True)
 
     # -- deck.run ---------------------------------------------------------------------------
@@ -443,3 +498,18 @@ def test_field_step_3d_equals_an_independent_restatement():
     assert min(np.abs(o.field(0, k)).max() for k in ("ex", "ey", "ez", "bx", "by", "bz")) > 0
     for k in ("ex", "ey", "ez", "bx", "by", "bz"):
         assert np.array_equal(o.field(0, k), m.f[k]), k
+
+
+def test_field_step_y_face_laser_equals_an_independent_restatement():
+    """laser on y_min, outflow on y_max, periodic x (outflow_bcs_y_min / y_max, clamp on the y walls)"""
+    res = []
+    for make in (Oracle, NumpyFields):
+        dk = decks.laser2d_y(n=40)
+        dk.lasers[0].pol_angle = 0.7
+        b = make(dk)
+        D.run(dk, b, [0], None, max_steps=60)
+        res.append(b)
+    o, m = res
+    assert min(np.abs(o.field(0, k)).max() for k in ("ex", "ez", "bx", "bz")) > 0
+    for k in ("ex", "ey", "ez", "bx", "by", "bz"):
+        assert np.array_equal(o.field(0, k)[0], m.f[k]), k
