@@ -141,6 +141,27 @@ class NumpyFields:
         dxp = lambda name, k: S(name, k, nx + k, 0, ny) - S(name, 1 - k, nx + 1 - k, 0, ny)       # f(ix+k) - f(ix-k+1)
         dyp = lambda name, k: S(name, 0, nx, k, ny + k) - S(name, 0, nx, 1 - k, ny + 1 - k)
         bx, by, bz = S("bx", 0, nx, 0, ny).copy(), S("by", 0, nx, 0, ny).copy(), S("bz", 0, nx, 0, ny).copy()
+        if getattr(self.dk, "maxwell_solver", "yee") != "yee":
+            # fields.f90:441-465: alpha / beta / delta weighted differences (order 2 only)
+            st = self.dk.stencil()
+            ax, ay, bxy, byx, dlx, dly = st["alphax"], st["alphay"], st["betaxy"], st["betayx"], st["deltax"], st["deltay"]
+            T = lambda name, di, dj: S(name, di, nx + di, dj, ny + dj)             # f(ix + di, iy + dj)
+
+            def ddy(name):   # the y difference, weighted across x
+                return (ay * (T(name, 0, 1) - T(name, 0, 0))
+                        + byx * (T(name, 1, 1) - T(name, 1, 0) + T(name, -1, 1) - T(name, -1, 0))
+                        + dly * (T(name, 0, 2) - T(name, 0, -1)))
+
+            def ddx(name):   # the x difference, weighted across y
+                return (ax * (T(name, 1, 0) - T(name, 0, 0))
+                        + bxy * (T(name, 1, 1) - T(name, 0, 1) + T(name, 1, -1) - T(name, 0, -1))
+                        + dlx * (T(name, 2, 0) - T(name, -1, 0)))
+
+            bx = bx - hdty * ddy("ez")
+            by = by + hdtx * ddx("ez")
+            bz = bz - hdtx * ddx("ey") + hdty * ddy("ex")
+            S("bx", 0, nx, 0, ny)[...], S("by", 0, nx, 0, ny)[...], S("bz", 0, nx, 0, ny)[...] = bx, by, bz
+            return
         for k in range(1, len(cs) + 1):
             bx = bx - cy[k - 1] * dyp("ez", k)
             by = by + cx[k - 1] * dxp("ez", k)
@@ -513,3 +534,22 @@ def test_field_step_y_face_laser_equals_an_independent_restatement():
     assert min(np.abs(o.field(0, k)).max() for k in ("ex", "ez", "bx", "bz")) > 0
     for k in ("ex", "ey", "ez", "bx", "by", "bz"):
         assert np.array_equal(o.field(0, k)[0], m.f[k]), k
+
+
+@pytest.mark.parametrize("solver", ["lehe_x", "lehe_y", "pukhov", "custom"])
+def test_extended_stencils_equal_an_independent_restatement(solver):
+    """the non-Yee B update (fields.f90:441-465) with the coefficients set_maxwell_solver derives"""
+    res = []
+    for make in (Oracle, NumpyFields):
+        dk = decks.laser2d(n=40)
+        dk.maxwell_solver = solver
+        if solver == "custom":
+            dk.stencil_custom = dict(betaxy=0.11, betayx=0.07, deltax=-0.03, deltay=0.02, dt=0.9 * dk.dx(0) / D.c / 2 ** 0.5)
+        dk.lasers[0].pol_angle = 0.4
+        b = make(dk)
+        D.run(dk, b, [0], None, max_steps=50)
+        res.append(b)
+    o, m = res
+    assert min(np.abs(o.field(0, k)).max() for k in ("ey", "ez", "by", "bz")) > 0
+    for k in ("ex", "ey", "ez", "bx", "by", "bz"):
+        assert np.array_equal(o.field(0, k)[0], m.f[k]), (solver, k)
